@@ -1,0 +1,109 @@
+/* oracle/ref_driver.c -- TEST INFRASTRUCTURE.
+ *
+ * Drives the reference's McKernel (rendered by the reference's own Python and
+ * compiled unchanged behind clshim.h) on CPU cores.  Compiled once per rendered
+ * kernel by oracle/refkernel.py with -DXO_REF_GEOMETRY=0|1|2 (mcml|mcvox|mccyl).
+ *
+ * Two schedules:
+ *  - xo_ref_run_static : the deterministic "block" schedule of DESIGN.md
+ *    (work-item t simulates packets [base_t, base_t+n_t) with its own MWC
+ *    stream) -- a legal outcome of the reference's racing atomic packet counter
+ *    (mcml.template.c:460,790).  Implemented without touching the kernel: the
+ *    packet counter is reset per work-item and the int/float buffers are shifted
+ *    so Trace rows land at row base_t + k.
+ *  - xo_ref_run_dynamic: P host threads, work-item p on thread p, shared atomic
+ *    counter -- what an OpenCL CPU runtime does; used as the CPU baseline.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <pthread.h>
+#include <stdlib.h>
+
+_Thread_local size_t xo_ref_global_id;
+
+#ifndef XO_REF_GEOMETRY
+#define XO_REF_GEOMETRY 0
+#endif
+
+typedef struct {
+	uint32_t num_packets;
+	uint32_t *num_packets_done;
+	uint32_t *num_kernels;
+	float rmax;
+	uint64_t *rng_x;
+	const uint32_t *rng_a;
+	/* geometry: mcml/mccyl: g0=num_layers(u32 by value), g1=layers
+	 *           mcvox: g1=voxel_cfg, g2=voxel data, g0=num_materials, g3=materials */
+	uint32_t g0;
+	const void *g1, *g2, *g3;
+	const void *source, *surface, *trace, *fluence, *detectors;
+	const float *fp_lut;
+	int32_t *int_buffer;
+	float *float_buffer;
+	uint64_t *accumulator_buffer;
+	/* trace row strides (0 when no trace): floats per packet, ints per packet */
+	uint64_t trace_float_stride, trace_int_stride;
+} xo_ref_args;
+
+#if XO_REF_GEOMETRY == 1
+void McKernel(uint32_t, uint32_t *, uint32_t *, float, uint64_t *, const uint32_t *,
+	const void *, const void *, uint32_t, const void *,
+	const void *, const void *, const void *, const void *, const void *, const float *,
+	int32_t *, float *, uint64_t *);
+static void call_kernel(const xo_ref_args *a, uint32_t n, uint32_t *done,
+		int32_t *ibuf, float *fbuf) {
+	McKernel(n, done, a->num_kernels, a->rmax, a->rng_x, a->rng_a,
+		a->g1, a->g2, a->g0, a->g3,
+		a->source, a->surface, a->trace, a->fluence, a->detectors, a->fp_lut,
+		ibuf, fbuf, a->accumulator_buffer);
+}
+#else
+void McKernel(uint32_t, uint32_t *, uint32_t *, float, uint64_t *, const uint32_t *,
+	uint32_t, const void *,
+	const void *, const void *, const void *, const void *, const void *, const float *,
+	int32_t *, float *, uint64_t *);
+static void call_kernel(const xo_ref_args *a, uint32_t n, uint32_t *done,
+		int32_t *ibuf, float *fbuf) {
+	McKernel(n, done, a->num_kernels, a->rmax, a->rng_x, a->rng_a,
+		a->g0, a->g1,
+		a->source, a->surface, a->trace, a->fluence, a->detectors, a->fp_lut,
+		ibuf, fbuf, a->accumulator_buffer);
+}
+#endif
+
+void xo_ref_run_static(const xo_ref_args *a, uint32_t nthreads) {
+	uint32_t N = a->num_packets, q = N / nthreads, r = N % nthreads;
+	uint64_t base = 0;
+	for (uint32_t t = 0; t < nthreads; ++t) {
+		uint32_t n_t = q + (t < r ? 1u : 0u);
+		uint32_t done = 0;
+		xo_ref_global_id = t;
+		if (n_t)
+			call_kernel(a, n_t, &done,
+				a->int_buffer + base*a->trace_int_stride,
+				a->float_buffer + base*a->trace_float_stride);
+		base += n_t;
+	}
+	*a->num_packets_done = N + nthreads;
+}
+
+typedef struct { const xo_ref_args *a; uint32_t gid; } worker_arg;
+static void *worker(void *p) {
+	worker_arg *w = (worker_arg *)p;
+	xo_ref_global_id = w->gid;
+	call_kernel(w->a, w->a->num_packets, w->a->num_packets_done,
+		w->a->int_buffer, w->a->float_buffer);
+	return NULL;
+}
+
+void xo_ref_run_dynamic(const xo_ref_args *a, uint32_t nthreads) {
+	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t)*nthreads);
+	worker_arg *wa = (worker_arg *)malloc(sizeof(worker_arg)*nthreads);
+	for (uint32_t t = 0; t < nthreads; ++t) {
+		wa[t].a = a; wa[t].gid = t;
+		pthread_create(&th[t], NULL, worker, &wa[t]);
+	}
+	for (uint32_t t = 0; t < nthreads; ++t)
+		pthread_join(th[t], NULL);
+	free(th); free(wa);
+}

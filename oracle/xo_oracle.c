@@ -1,0 +1,926 @@
+/* oracle/xo_oracle.c -- TEST INFRASTRUCTURE: CPU restatement of the reference's
+ * photon-packet kernels.  Never linked into, imported by or shipped with the
+ * product (pyxopto_b200); see oracle/xo_oracle.h.
+ *
+ * Each function cites the reference text it restates (paths relative to
+ * /root/reference/xopto).  Floating-point expressions keep the reference's
+ * operand order, so with -ffp-contract=off and math=XO_MATH_LIBM this file is
+ * bit-identical to the reference kernel compiled by gcc behind clshim.h
+ * (oracle/_ref, checked by tests/test_oracle_vs_ref.py in the build container
+ * and pinned for the GPU box by tests/golden/).
+ */
+#include <math.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include "xo_oracle.h"
+#include "xo_detmath.h"
+
+#define FP_0 0.0f
+#define FP_1 1.0f
+#define FP_2 2.0f
+#define FP_0p5 0.5f
+#define FP_2PI 6.283185307179586f
+#define FP_COS_90 0.0f
+#define FP_COS_0 (1.0f - FP_COS_90)
+#define FP_COS_30 0.8660254037844386f
+#define FP_INV_C 3.3356409519815204e-09f
+#define FP_RMIN 1e-12f
+#define FP_PLMIN 1e-12f
+#define ACCU_K 0x7FFFFF
+
+/* event flags, mcbase.template.h:664-681 */
+#define EV_REFLECTION 1u
+#define EV_REFRACTION 2u
+#define EV_BOUNDARY_HIT 4u
+#define EV_LAUNCH 8u
+#define EV_ABSORPTION 16u
+#define EV_SCATTERING 32u
+#define EV_TERMINATED 64u
+#define EV_ESCAPED 128u
+
+typedef struct { float x, y, z; } p3f;
+typedef struct { float x, y; } p2f;
+typedef struct { float a11, a12, a13, a21, a22, a23, a31, a32, a33; } m3f;
+
+/* ---- packed plugin structs (ctypes layouts of the reference) -------------- */
+/* mcml/mclayer/layer.py:57-69 */
+typedef struct {
+	float thickness, top, bottom, n, cc_top, cc_bottom, mus, mua, inv_mut, mua_inv_mut;
+	/* McPf follows */
+} ml_layer;
+/* mccyl/mclayer/layer.py:119-130 */
+typedef struct {
+	float r_inner, r_outer, n, cc_inner, cc_outer, mus, mua, inv_mut, mua_inv_mut;
+} cyl_layer;
+/* mcbase/mcmaterial.py:52-62 */
+typedef struct { float n, mus, mua, inv_mut, mua_inv_mut; } vox_material;
+/* mcvox/mcgeometry/voxel.py:96-121 */
+typedef struct { p3f top_left, bottom_right, size; int32_t nx, ny, nz; } vox_cfg;
+
+typedef struct { float g; } pf_hg;                          /* mcpf/hg.py:49 */
+typedef struct { float g, beta; } pf_mhg;                   /* mcpf/mhg.py:52 */
+typedef struct { float g, a, inv_a, a1, a2; } pf_gk;        /* mcpf/gk.py:58 */
+typedef struct { float a, b, c; uint32_t offset, size; } pf_lut; /* mcpf/lut.py:78 */
+
+typedef struct { p3f position, dir_medium, dir_sample, dir_reflected; float reflectance; } src_line;
+typedef struct { m3f T; p3f position, direction; p2f sigma; float clip, reflectance; } src_gauss_ml;
+typedef struct { m3f T; p3f position, direction; float radius, cos_min, n; } src_ufiber;
+typedef struct { p3f position; uint32_t layer_index; } src_isopoint;
+
+typedef struct { p3f direction; float cos_min; uint32_t offset; } det_total;
+typedef struct { p3f direction; p2f position; float r_min, inv_dr, cos_min;
+	uint32_t n, offset; int32_t log_scale; } det_radial;
+typedef struct { p3f direction; float x_min, inv_dx, y_min, inv_dy, cos_min;
+	uint32_t n_x, n_y, offset; } det_cartesian;
+typedef struct { m3f T; p2f position; float core_r_squared, core_spacing, cos_min;
+	uint32_t offset; } det_six;
+typedef struct { p3f direction; p2f position; float r_min, inv_dr, pl_min, inv_dpl, cos_min;
+	uint32_t n_r, n_pl, offset; int32_t r_log_scale, pl_log_scale; } det_radialpl;
+typedef struct { p3f direction; float cos_min, pl_min, inv_dpl;
+	uint32_t n_pl, offset; int32_t pl_log_scale; } det_totalpl;
+typedef struct { p3f direction; float fi_min, inv_dfi, z_min, inv_dz, cos_min;
+	uint32_t n_fi, n_z, offset; } det_fiz;
+
+typedef struct { p3f inv_step, top_left; uint32_t nx, ny, nz, offset; int32_t k; } flu_xyz;
+typedef struct { p3f center; float inv_dr, inv_dz; uint32_t n_r, n_z, offset; int32_t k; } flu_rz;
+typedef struct { float inv_step[4], top_left[4]; uint32_t shape[4]; uint32_t offset; int32_t k; } flu_xyzt;
+
+typedef struct { int32_t max_events; uint32_t data_off, count_off, event_mask; } trace_cfg;
+
+/* ---- simulator state (mcml.template.h McSimState) ------------------------- */
+typedef struct {
+	const xo_oracle_job *job;
+	p3f pos, dir;
+	uint64_t rng_x;
+	uint32_t rng_a;
+	float weight;
+	uint32_t photon_index;
+	int32_t layer_index;      /* layer (mcml/mccyl) or material index (mcvox) */
+	uint32_t event_flags;
+	float opl;
+	uint32_t trace_count;
+	int32_t vx, vy, vz;       /* mcvox voxel index */
+	uint64_t iterations;
+	volatile uint32_t *dyn_counter;   /* dynamic schedule packet counter */
+} sim_t;
+
+/* ---- math binding ------------------------------------------------------- */
+#define PORTABLE(s) ((s)->job->math == XO_MATH_PORTABLE)
+static inline float m_log(const sim_t *s, float x) { return PORTABLE(s) ? xo_logf(x) : logf(x); }
+static inline float m_exp(const sim_t *s, float x) { return PORTABLE(s) ? xo_expf(x) : expf(x); }
+static inline float m_cbrt(const sim_t *s, float x) { return PORTABLE(s) ? xo_cbrtf(x) : cbrtf(x); }
+static inline float m_pow(const sim_t *s, float x, float y) { return PORTABLE(s) ? xo_powf(x, y) : powf(x, y); }
+static inline float m_atan2(const sim_t *s, float y, float x) { return PORTABLE(s) ? xo_atan2f(y, x) : atan2f(y, x); }
+static inline void m_sincos(const sim_t *s, float x, float *sn, float *cs) {
+	if (PORTABLE(s)) { *sn = xo_sincosf(x, cs); }
+	else { *cs = cosf(x); *sn = sinf(x); }
+}
+#define m_sqrt(x) sqrtf(x)
+#define m_div(a, b) ((float)(a)/(float)(b))
+static inline float fclip(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+static inline int32_t iclip(int32_t x, int32_t lo, int32_t hi) { return x < lo ? lo : (x > hi ? hi : x); }
+static inline int fsign(float x) { return (x >= FP_0) ? 1 : -1; }
+
+/* ---- RNG: mcbase.template.c:1576-1594 -------------------------------------- */
+static inline float rng_next(uint64_t *x, uint32_t a) {
+	*x = (*x & 0xFFFFFFFFull)*a + (*x >> 32);
+	return (float)(uint32_t)*x / (float)0xFFFFFFFFu;
+}
+static inline float sim_random(sim_t *s) { return rng_next(&s->rng_x, s->rng_a); }
+
+void xo_oracle_rng_test(uint64_t x, uint32_t a, uint32_t n, float *out) {
+	for (uint32_t i = 0; i < n; ++i) out[i] = rng_next(&x, a);
+}
+
+/* ---- seeds: src/rng/rng.cpp:64-103 ---------------------------------------- */
+int xo_oracle_init_rng(uint64_t *x, uint32_t *a, const uint32_t *fora,
+		uint32_t n_rng, uint64_t xinit) {
+	uint32_t begin = fora[0];
+	if (xinit == 0ull || (uint32_t)(xinit >> 32) >= begin - 1 ||
+			(uint32_t)xinit >= 0xffffffffu)
+		return 1;
+	for (uint32_t i = 0; i < n_rng; ++i) {
+		a[i] = fora[i + 1];
+		x[i] = 0;
+		while (x[i] == 0 || (uint32_t)(x[i] >> 32) >= fora[i + 1] - 1 ||
+				(uint32_t)x[i] >= 0xffffffffu) {
+			xinit = (xinit & 0xffffffffull)*begin + (xinit >> 32);
+			x[i] = (uint32_t)floor(((double)(uint32_t)xinit/4294967296.0)*fora[i + 1]);
+			x[i] <<= 32;
+			xinit = (xinit & 0xffffffffull)*begin + (xinit >> 32);
+			x[i] += (uint32_t)xinit;
+		}
+	}
+	return 0;
+}
+
+/* ---- accumulators: mcbase.template.c:58-61 --------------------------------- */
+static inline void accu_deposit(sim_t *s, uint32_t index, uint32_t w) {
+	__atomic_fetch_add(&s->job->accumulator_buffer[index], (uint64_t)w, __ATOMIC_RELAXED);
+}
+/* mcml.template.h:606 weight_to_int + the `*(cond)` idiom of every detector */
+static inline uint32_t weight_to_u32(float weight, int accept) {
+	return (uint32_t)((weight*ACCU_K + FP_0p5)*accept);
+}
+
+/* ---- vector helpers: mcbase.template.c:693-700,868-990 --------------------- */
+static inline float dot3(const p3f *a, const p3f *b) { return a->x*b->x + a->y*b->y + a->z*b->z; }
+static inline void transform3(const m3f *m, const p3f *v, p3f *r) {
+	r->x = m->a11*v->x + m->a12*v->y + m->a13*v->z;
+	r->y = m->a21*v->x + m->a22*v->y + m->a23*v->z;
+	r->z = m->a31*v->x + m->a32*v->y + m->a33*v->z;
+}
+static inline void normalize3(p3f *a) {
+	float k = m_div(FP_1, m_sqrt(a->x*a->x + a->y*a->y + a->z*a->z));
+	a->x = a->x*k; a->y = a->y*k; a->z = a->z*k;
+}
+
+/* ---- boundary physics: mcbase.template.c:1229-1507 ------------------------- */
+static inline float cos_critical(float n1, float n2) {
+	return (n1 > n2) ? m_sqrt(FP_1 - m_div(n2*n2, n1*n1)) : FP_0;
+}
+static float reflectance(float n1, float n2, float cos1, float cos_crit) {
+	float Rp, Rs, R = FP_1, n1_d_n2, sin1, sin2, cos2, n_cos1, n_cos2;
+	cos1 = fabsf(cos1);
+	if (n1 == n2) return FP_0;
+	if (cos1 > cos_crit) {
+		n1_d_n2 = m_div(n1, n2);
+		sin1 = m_sqrt(FP_1 - cos1*cos1);
+		if (cos1 >= FP_COS_0) sin1 = FP_0;
+		sin2 = fminf(FP_1, n1_d_n2*sin1);
+		cos2 = m_sqrt(FP_1 - sin2*sin2);
+		n_cos1 = n1_d_n2*cos1;
+		n_cos2 = n1_d_n2*cos2;
+		Rs = m_div(n_cos1 - cos2, n_cos1 + cos2); Rs *= Rs;
+		Rp = m_div(n_cos2 - cos1, n_cos2 + cos1); Rp *= Rp;
+		R = FP_0p5*(Rp + Rs);
+		if (cos1 <= FP_COS_90 || sin2 == FP_1) return FP_1;
+	}
+	return R;
+}
+static inline void reflect3(const p3f *p, const p3f *n, p3f *r) {
+	float p_n_2 = FP_2*dot3(p, n);
+	r->x = p->x - n->x*p_n_2; r->y = p->y - n->y*p_n_2; r->z = p->z - n->z*p_n_2;
+}
+static inline void refract3(const p3f *p, const p3f *n, float n1, float n2, p3f *r) {
+	float cos1 = dot3(p, n);
+	float n1_d_n2 = m_div(n1, n2);
+	float sin2_squared = n1_d_n2*n1_d_n2*(FP_1 - cos1*cos1);
+	float k = fsign(cos1)*(n1_d_n2*fabsf(cos1) - m_sqrt(FP_1 - sin2_squared));
+	r->x = n1_d_n2*p->x - k*n->x; r->y = n1_d_n2*p->y - k*n->y; r->z = n1_d_n2*p->z - k*n->z;
+}
+static inline int refract3_safe(const p3f *p, const p3f *n, float n1, float n2, p3f *r) {
+	float cos1 = dot3(p, n);
+	float n1_d_n2 = m_div(n1, n2);
+	float sin2_squared = n1_d_n2*n1_d_n2*(FP_1 - cos1*cos1);
+	if (sin2_squared > FP_1) return 1;
+	float k = fsign(cos1)*(n1_d_n2*fabsf(cos1) - m_sqrt(FP_1 - sin2_squared));
+	r->x = n1_d_n2*p->x - k*n->x; r->y = n1_d_n2*p->y - k*n->y; r->z = n1_d_n2*p->z - k*n->z;
+	return 0;
+}
+
+/* mcbase.template.c:1522-1555 (renormalisation is unconditional) */
+static void scatter_direction(const sim_t *s, p3f *dir, float cos_theta, float fi) {
+	float sin_fi, cos_fi, sin_theta, px, k, stcf, stsf;
+	sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+	m_sincos(s, fi, &sin_fi, &cos_fi);
+	stcf = sin_theta*cos_fi;
+	stsf = sin_theta*sin_fi;
+	px = dir->x;
+	if (fabsf(dir->z) >= FP_COS_0) {
+		dir->x = stcf;
+		dir->y = stsf;
+		dir->z = copysignf(cos_theta, dir->z*cos_theta);
+	} else {
+		k = m_sqrt(FP_1 - dir->z*dir->z);
+		dir->x = m_div(stcf*px*dir->z - stsf*dir->y, k) + px*cos_theta;
+		dir->y = m_div(stcf*dir->y*dir->z + stsf*px, k) + dir->y*cos_theta;
+		dir->z = (-stcf)*k + dir->z*cos_theta;
+	}
+	normalize3(dir);
+}
+
+/* ---- layer / material access --------------------------------------------- */
+static inline size_t layer_stride(const xo_oracle_job *j) {
+	switch (j->geometry) {
+		case XO_GEOM_MCML: return sizeof(ml_layer) + (size_t)j->pf_size;
+		case XO_GEOM_MCCYL: return sizeof(cyl_layer) + (size_t)j->pf_size;
+		default: return sizeof(vox_material) + (size_t)j->pf_size;
+	}
+}
+static inline const ml_layer *ml_layer_at(const xo_oracle_job *j, int32_t i) {
+	return (const ml_layer *)((const char *)j->layers + (size_t)i*layer_stride(j));
+}
+static inline const cyl_layer *cyl_layer_at(const xo_oracle_job *j, int32_t i) {
+	return (const cyl_layer *)((const char *)j->layers + (size_t)i*layer_stride(j));
+}
+static inline const vox_material *vox_material_at(const xo_oracle_job *j, int32_t i) {
+	return (const vox_material *)((const char *)j->layers + (size_t)i*layer_stride(j));
+}
+static inline const void *current_pf(const sim_t *s) {
+	const xo_oracle_job *j = s->job;
+	const char *base = (const char *)j->layers + (size_t)s->layer_index*layer_stride(j);
+	return base + (layer_stride(j) - (size_t)j->pf_size);
+}
+/* refractive index of layer/material i in any geometry */
+static inline float medium_n(const xo_oracle_job *j, int32_t i) {
+	switch (j->geometry) {
+		case XO_GEOM_MCML: return ml_layer_at(j, i)->n;
+		case XO_GEOM_MCCYL: return cyl_layer_at(j, i)->n;
+		default: return vox_material_at(j, i)->n;
+	}
+}
+static inline void medium_props(const sim_t *s, float *mus, float *mua,
+		float *inv_mut, float *mua_inv_mut, float *n) {
+	const xo_oracle_job *j = s->job;
+	switch (j->geometry) {
+		case XO_GEOM_MCML: { const ml_layer *l = ml_layer_at(j, s->layer_index);
+			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
+		case XO_GEOM_MCCYL: { const cyl_layer *l = cyl_layer_at(j, s->layer_index);
+			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
+		default: { const vox_material *l = vox_material_at(j, s->layer_index);
+			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
+	}
+}
+
+/* ---- phase functions ------------------------------------------------------- */
+static float pf_sample_angles(sim_t *s, float *azimuth) {
+	const void *pf = current_pf(s);
+	float cos_theta;
+	switch (s->job->pf_kind) {
+	case XO_PF_HG: {                                   /* mcpf/hg.py:74-90 */
+		float g = ((const pf_hg *)pf)->g, k;
+		*azimuth = FP_2PI*sim_random(s);
+		k = m_div(FP_1 - g*g, FP_1 + g*(FP_2*sim_random(s) - FP_1));
+		cos_theta = m_div(FP_1 + g*g - k*k, FP_2*g);
+		if (g == FP_0) cos_theta = FP_1 - FP_2*sim_random(s);
+		return fmaxf(fminf(cos_theta, FP_1), -FP_1);
+	}
+	case XO_PF_MHG: {                                  /* mcpf/mhg.py:84-105 */
+		float g = ((const pf_mhg *)pf)->g, beta = ((const pf_mhg *)pf)->beta, k;
+		*azimuth = FP_2PI*sim_random(s);
+		if (sim_random(s) <= beta) {
+			k = m_div(FP_1 - g*g, FP_1 + g*(FP_2*sim_random(s) - FP_1));
+			cos_theta = m_div(FP_1 + g*g - k*k, FP_2*g);
+			if (g == FP_0) cos_theta = FP_1 - FP_2*sim_random(s);
+		} else {
+			cos_theta = m_cbrt(s, FP_2*sim_random(s) - FP_1);
+		}
+		return fclip(cos_theta, -FP_1, FP_1);
+	}
+	case XO_PF_GK: {                                   /* mcpf/gk.py:99-132 */
+		const pf_gk *p = (const pf_gk *)pf;
+		float g = p->g, a = p->a, inv_a = p->inv_a, a1 = p->a1, a2 = p->a2, tmp;
+		*azimuth = FP_2PI*sim_random(s);
+		if (g == FP_0) {
+			cos_theta = FP_1 - FP_2*sim_random(s);
+		} else if (a == FP_0) {
+			cos_theta = a1 + m_pow(s, m_div(FP_1 - g, FP_1 + g), FP_2*sim_random(s))*a2;
+		} else {
+			tmp = a1*sim_random(s) + a2;
+			tmp = FP_1 + g*g - m_pow(s, tmp, -inv_a);
+			cos_theta = m_div(tmp, FP_2*g);
+		}
+		return fclip(cos_theta, -FP_1, FP_1);
+	}
+	case XO_PF_LUT: {                                  /* mcpf/lut.py:125-158 */
+		const pf_lut *p = (const pf_lut *)pf;
+		float a = p->a, b = p->b, c = p->c, fp_index, fp_index_floor, d;
+		size_t offset = p->offset, lut_size = p->size - 1, index;
+		const float *lut = s->job->fp_lut;
+		*azimuth = FP_2PI*sim_random(s);
+		fp_index = (m_div(a, sim_random(s) - c) - b + FP_1)*lut_size*FP_0p5;
+		fp_index_floor = floorf(fp_index);
+		d = fp_index - fp_index_floor;
+		index = (size_t)(int32_t)fp_index_floor;
+		{
+			/* mc_min(index + 1, lut_size) casts both to mc_int_t */
+			int32_t i1 = (int32_t)(index + 1), ls = (int32_t)lut_size;
+			int32_t i2 = i1 < ls ? i1 : ls;
+			cos_theta = lut[offset + index]*(FP_1 - d) + lut[offset + (size_t)i2]*d;
+		}
+		return cos_theta;
+	}
+	}
+	return FP_1;
+}
+
+/* ---- detectors ------------------------------------------------------------- */
+enum { LOC_TOP = 0, LOC_BOTTOM = 1, LOC_SPECULAR = 2 };
+
+static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, float weight) {
+	const xo_oracle_job *j = s->job;
+	const char *base = (const char *)j->detectors + j->det_offset[loc];
+	switch (j->det_kind[loc]) {
+	case XO_DET_TOTAL: {                               /* mcdetector/total.py:86-110 */
+		const det_total *d = (const det_total *)base;
+		p3f dd = d->direction;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+		if (w > 0) accu_deposit(s, d->offset, w);
+		break;
+	}
+	case XO_DET_RADIAL: {                              /* mcdetector/radial.py:117-150 */
+		const det_radial *d = (const det_radial *)base;
+		float dx = pos->x - d->position.x, dy = pos->y - d->position.y;
+		float r = m_sqrt(dx*dx + dy*dy);
+		if (d->log_scale) r = m_log(s, fmaxf(r, FP_RMIN));
+		int32_t ri = (int32_t)((r - d->r_min)*d->inv_dr);
+		uint32_t index = (uint32_t)iclip(ri, 0, (int32_t)(d->n - 1));
+		p3f dd = d->direction;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+		if (w > 0) accu_deposit(s, d->offset + index, w);
+		break;
+	}
+	case XO_DET_CARTESIAN: {                           /* mcdetector/cartesian.py:124-157 */
+		const det_cartesian *d = (const det_cartesian *)base;
+		int32_t ix = (int32_t)((pos->x - d->x_min)*d->inv_dx);
+		ix = iclip(ix, 0, (int32_t)(d->n_x - 1));
+		int32_t iy = (int32_t)((pos->y - d->y_min)*d->inv_dy);
+		iy = iclip(iy, 0, (int32_t)(d->n_y - 1));
+		uint32_t index = (uint32_t)iy*d->n_x + (uint32_t)ix;
+		p3f dd = d->direction;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+		if (w > 0) accu_deposit(s, index + d->offset, w);
+		break;
+	}
+	case XO_DET_SIXAROUNDONE: {                        /* mcdetector/probe/sixaroundone.py:103-192 */
+		const det_six *d = (const det_six *)base;
+		uint32_t fiber_index = 7;
+		p3f rel = { pos->x - d->position.x, pos->y - d->position.y, FP_0 };
+		p3f mc_pos, dp; float dx, dy, r2;
+		m3f T = d->T;
+		mc_pos.x = rel.x; mc_pos.y = rel.y; mc_pos.z = FP_0;
+		transform3(&T, &mc_pos, &dp);
+		dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+		if (r2 <= d->core_r_squared) fiber_index = 0;
+		mc_pos.x = fabsf(rel.x) - d->core_spacing; mc_pos.y = rel.y;
+		transform3(&T, &mc_pos, &dp);
+		dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+		if (r2 <= d->core_r_squared) fiber_index = (rel.x >= FP_0) ? 1 : 4;
+		mc_pos.x = fabsf(rel.x) - d->core_spacing*FP_0p5;
+		mc_pos.y = fabsf(rel.y) - d->core_spacing*FP_COS_30;
+		transform3(&T, &mc_pos, &dp);
+		dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+		if (r2 <= d->core_r_squared)
+			fiber_index = (rel.x >= FP_0) ? ((rel.y >= FP_0) ? 2 : 6) : ((rel.y >= FP_0) ? 3 : 5);
+		if (fiber_index > 6) return;
+		float pz = T.a31*dir->x + T.a32*dir->y + T.a33*dir->z;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(pz));
+		if (w > 0) accu_deposit(s, d->offset + fiber_index, w);
+		break;
+	}
+	case XO_DET_RADIALPL: {                            /* mcdetector/radialpl.py:138-180 */
+		const det_radialpl *d = (const det_radialpl *)base;
+		float dx = pos->x - d->position.x, dy = pos->y - d->position.y;
+		float r = m_sqrt(dx*dx + dy*dy);
+		if (d->r_log_scale) r = m_log(s, fmaxf(r, FP_RMIN));
+		int32_t ri = iclip((int32_t)((r - d->r_min)*d->inv_dr), 0, (int32_t)(d->n_r - 1));
+		float pl = s->opl;
+		if (d->pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		int32_t pi = iclip((int32_t)((pl - d->pl_min)*d->inv_dpl), 0, (int32_t)(d->n_pl - 1));
+		uint32_t index = (uint32_t)pi*d->n_r + (uint32_t)ri;
+		p3f dd = d->direction;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+		if (w > 0) accu_deposit(s, d->offset + index, w);
+		break;
+	}
+	case XO_DET_TOTALPL: {                             /* mcdetector/totalpl.py:101-121 */
+		const det_totalpl *d = (const det_totalpl *)base;
+		float pl = s->opl;
+		if (d->pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		int32_t pi = iclip((int32_t)((pl - d->pl_min)*d->inv_dpl), 0, (int32_t)(d->n_pl - 1));
+		p3f dd = d->direction;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+		if (w > 0) accu_deposit(s, d->offset + (uint32_t)pi, w);
+		break;
+	}
+	default: break;
+	}
+}
+
+/* ---- fluence --------------------------------------------------------------- */
+static void fluence_deposit_at(sim_t *s, const p3f *pos, float weight, float mua) {
+	const xo_oracle_job *j = s->job;
+	switch (j->fluence_kind) {
+	case XO_FLU_XYZ: {                                 /* mcfluence/fluence.py:103-143 */
+		const flu_xyz *f = (const flu_xyz *)j->fluence;
+		float fx = (pos->x - f->top_left.x)*f->inv_step.x;
+		float fy = (pos->y - f->top_left.y)*f->inv_step.y;
+		float fz = (pos->z - f->top_left.z)*f->inv_step.z;
+		if (fx >= 0 && fy >= 0 && fz >= 0 && fx < f->nx && fy < f->ny && fz < f->nz) {
+			uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz;
+			uint32_t index = (iz*f->ny + iy)*f->nx + ix;
+			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
+			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
+			accu_deposit(s, f->offset + index, w);
+		}
+		break;
+	}
+	case XO_FLU_RZ: {                                  /* mcfluence/fluencerz.py:112-160 */
+		const flu_rz *f = (const flu_rz *)j->fluence;
+		float dx = pos->x - f->center.x, dy = pos->y - f->center.y;
+		float r = m_sqrt(dx*dx + dy*dy);
+		float dz = pos->z - f->center.z;
+		float fr = r*f->inv_dr, fz = dz*f->inv_dz;
+		if (fr >= 0 && fz >= 0 && fr < f->n_r && fz < f->n_z) {
+			uint32_t ir = (uint32_t)fr, iz = (uint32_t)fz;
+			uint32_t index = iz*f->n_r + ir;
+			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
+			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
+			accu_deposit(s, f->offset + index, w);
+		}
+		break;
+	}
+	case XO_FLU_XYZT: {                                /* mcfluence/fluencet.py:107-158 */
+		const flu_xyzt *f = (const flu_xyzt *)j->fluence;
+		float fx = (pos->x - f->top_left[0])*f->inv_step[0];
+		float fy = (pos->y - f->top_left[1])*f->inv_step[1];
+		float fz = (pos->z - f->top_left[2])*f->inv_step[2];
+		float ft = (s->opl*FP_INV_C - f->top_left[3])*f->inv_step[3];
+		if (ft >= FP_0 && fx >= FP_0 && fy >= FP_0 && fz >= FP_0 &&
+				fx < f->shape[0] && fy < f->shape[1] && fz < f->shape[2] && ft < f->shape[3]) {
+			uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz, it = (uint32_t)ft;
+			uint32_t index = ((iz*f->shape[1] + iy)*f->shape[0] + ix)*f->shape[3] + it;
+			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
+			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
+			accu_deposit(s, f->offset + index, w);
+		}
+		break;
+	}
+	default: break;
+	}
+}
+
+/* ---- trace: mcbase/mctrace.py:541-585 -------------------------------------- */
+static int trace_event(sim_t *s, uint32_t event_count) {
+	const trace_cfg *t = (const trace_cfg *)s->job->trace;
+	/* mc_min(event_count, max_events - 1) on mc_int_t */
+	int32_t ec = (int32_t)event_count, me = t->max_events - 1;
+	uint32_t pos = (uint32_t)(ec < me ? ec : me)*8u +
+		s->photon_index*(uint32_t)t->max_events*8u + t->data_off;
+	if (s->job->use_events && !(t->event_mask & s->event_flags))
+		return 0;
+	float *fb = s->job->float_buffer;
+	fb[pos++] = s->pos.x; fb[pos++] = s->pos.y; fb[pos++] = s->pos.z;
+	fb[pos++] = s->dir.x; fb[pos++] = s->dir.y; fb[pos++] = s->dir.z;
+	fb[pos++] = s->weight;
+	fb[pos++] = s->job->track_opl ? s->opl : FP_0;
+	return 1;
+}
+static inline void trace_this_event(sim_t *s) {          /* mcml.template.c:255-258 */
+	if (trace_event(s, s->trace_count)) s->trace_count++;
+}
+static inline void trace_finalize(sim_t *s) {            /* mcml.template.c:263-265 */
+	const trace_cfg *t = (const trace_cfg *)s->job->trace;
+	s->job->int_buffer[t->count_off + s->photon_index] = (int32_t)s->trace_count;
+}
+
+/* ---- sources (mcml) -------------------------------------------------------- */
+static void launch_mcml(sim_t *s) {
+	const xo_oracle_job *j = s->job;
+	switch (j->src_kind) {
+	case XO_SRC_LINE: {                                /* mcsource/line.py:95-110 */
+		const src_line *src = (const src_line *)j->source;
+		s->weight = FP_1 - src->reflectance;
+		s->pos = src->position;
+		s->dir = src->dir_sample;
+		if (j->det_kind[LOC_SPECULAR]) {
+			p3f d = src->dir_reflected;
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &d, src->reflectance);
+		}
+		s->layer_index = 1;
+		break;
+	}
+	case XO_SRC_GAUSSIANBEAM: {                        /* mcsource/gaussianbeam.py:119-165 */
+		const src_gauss_ml *src = (const src_gauss_ml *)j->source;
+		float cos_fi, sin_fi, r; p3f pt_src, pt_mc;
+		r = m_sqrt(-FP_2*m_log(s, FP_1 - sim_random(s)));
+		r = fminf(r, src->clip);
+		m_sincos(s, FP_2PI*sim_random(s), &sin_fi, &cos_fi);
+		pt_src.x = r*cos_fi*src->sigma.x;
+		pt_src.y = r*sin_fi*src->sigma.y;
+		pt_src.z = FP_0;
+		m3f T = src->T;
+		transform3(&T, &pt_src, &pt_mc);
+		float k = m_div(FP_0 - pt_mc.z, src->direction.z);
+		pt_mc.x += k*src->direction.x;
+		pt_mc.y += k*src->direction.y;
+		pt_mc.z = FP_0;
+		s->pos.x = src->position.x + pt_mc.x;
+		s->pos.y = src->position.y + pt_mc.y;
+		s->pos.z = FP_0;
+		s->dir = src->direction;
+		s->layer_index = 1;
+		s->weight = FP_1 - src->reflectance;
+		if (j->det_kind[LOC_SPECULAR]) {
+			p3f dir_in = { s->dir.x, s->dir.y, -s->dir.z }, dir;
+			p3f normal = { FP_0, FP_0, -FP_1 };
+			refract3(&dir_in, &normal, medium_n(j, 1), medium_n(j, 0), &dir);
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &dir, src->reflectance);
+		}
+		break;
+	}
+	case XO_SRC_UNIFORMFIBER: {                        /* mcsource/fiber.py:273-331 */
+		const src_ufiber *src = (const src_ufiber *)j->source;
+		float sin_fi, cos_fi, sin_theta, cos_theta; p3f pt_src, pt_mc;
+		float r = m_sqrt(sim_random(s))*src->radius;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		pt_src.x = r*cos_fi; pt_src.y = r*sin_fi; pt_src.z = FP_0;
+		m3f T = src->T;
+		transform3(&T, &pt_src, &pt_mc);
+		float k = m_div(FP_0 - pt_mc.z, src->direction.z);
+		pt_mc.x += k*src->direction.x;
+		pt_mc.y += k*src->direction.y;
+		pt_mc.z = FP_0;
+		s->pos.x = src->position.x + pt_mc.x;
+		s->pos.y = src->position.y + pt_mc.y;
+		s->pos.z = FP_0;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		cos_theta = FP_1 - sim_random(s)*(FP_1 - src->cos_min);
+		sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+		sin_theta = m_div(sin_theta, src->n);
+		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+		pt_src.x = cos_fi*sin_theta; pt_src.y = sin_fi*sin_theta; pt_src.z = cos_theta;
+		p3f direction;
+		transform3(&T, &pt_src, &direction);
+		float cc = cos_critical(src->n, medium_n(j, 1));
+		p3f normal = { FP_0, FP_0, FP_1 };
+		p3f refracted = direction;
+		if (pt_mc.z > cc)             /* never true: pt_mc.z == 0 */
+			refract3(&pt_mc, &normal, src->n, medium_n(j, 1), &refracted);
+		s->dir = refracted;
+		float specular_r = reflectance(src->n, medium_n(j, 1), direction.z, cc);
+		s->weight = FP_1 - specular_r;
+		if (j->det_kind[LOC_SPECULAR])
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &direction, specular_r);
+		s->layer_index = 1;
+		break;
+	}
+	case XO_SRC_ISOTROPICPOINT: {                      /* mcsource/point.py:76-135 */
+		const src_isopoint *src = (const src_isopoint *)j->source;
+		float sin_fi, cos_fi, sin_theta, cos_theta, specular_r = FP_0;
+		p3f position = src->position, direction;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		cos_theta = FP_1 - FP_2*sim_random(s);
+		sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+		direction.x = cos_fi*sin_theta; direction.y = sin_fi*sin_theta; direction.z = cos_theta;
+		p3f refracted = direction;
+		if (position.z <= FP_0) {
+			float cc = ml_layer_at(j, 0)->cc_bottom;
+			if (direction.z > cc) {
+				p3f normal = { FP_0, FP_0, FP_1 };
+				float n_sample = medium_n(j, 1), n_medium = medium_n(j, 0);
+				refract3(&direction, &normal, n_sample, n_medium, &refracted);
+				specular_r = reflectance(n_medium, n_sample, direction.z, cc);
+				float t = m_div(-position.z, direction.z);
+				position.x += direction.x*t;
+				position.y += direction.y*t;
+			} else {
+				specular_r = FP_1;
+			}
+			position.z = FP_0;
+		}
+		s->dir = refracted;
+		s->pos = position;
+		if (j->det_kind[LOC_SPECULAR])
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &direction, specular_r);
+		s->weight = FP_1 - specular_r;
+		s->layer_index = (int32_t)src->layer_index;
+		break;
+	}
+	default: break;
+	}
+}
+
+/* `source->position` (mcml.template.c:380): byte offset depends on the source struct */
+static inline p3f source_position(const xo_oracle_job *j) {
+	size_t off = 0;
+	switch (j->src_kind) {
+		case XO_SRC_GAUSSIANBEAM: off = (j->geometry == XO_GEOM_MCVOX) ? 0 : sizeof(m3f); break;
+		case XO_SRC_UNIFORMFIBER: off = sizeof(m3f); break;
+		default: off = 0; break;
+	}
+	return *(const p3f *)((const char *)j->source + off);
+}
+
+/* ---- mcml boundary: mcml.template.c:80-203 --------------------------------- */
+static uint32_t boundary_mcml(sim_t *s, int32_t next_index) {
+	const xo_oracle_job *j = s->job;
+	const ml_layer *cur = ml_layer_at(j, s->layer_index);
+	const ml_layer *nxt = ml_layer_at(j, next_index);
+	float cos_crit, cos1, sin1, cos2, sin2, n_cos1, n_cos2, n2, n1_d_n2, R, Rs, Rp;
+	p3f *dir = &s->dir;
+	cos_crit = (dir->z < FP_0) ? cur->cc_top : cur->cc_bottom;
+	n2 = nxt->n;
+	if (cur->n == n2) {
+		s->layer_index = next_index;
+		return EV_REFRACTION;
+	}
+	dir->z = -dir->z;
+	cos1 = fabsf(dir->z);
+	if (cos1 > cos_crit) {
+		if (cos1 > FP_COS_0) {                 /* unreachable: FP_COS_0 == 1 */
+			R = m_div(cur->n - n2, cur->n + n2);
+			if (R*R < sim_random(s)) {
+				s->layer_index = next_index;
+				dir->z = -dir->z;
+				return EV_REFRACTION;
+			} else {
+				return EV_REFLECTION;
+			}
+		}
+		n1_d_n2 = m_div(cur->n, n2);
+		sin1 = m_sqrt(FP_1 - cos1*cos1);
+		if (cos1 >= FP_COS_0) sin1 = FP_0;
+		sin2 = fminf(FP_1, n1_d_n2*sin1);
+		cos2 = m_sqrt(FP_1 - sin2*sin2);
+		n_cos1 = n1_d_n2*cos1;
+		n_cos2 = n1_d_n2*cos2;
+		Rs = m_div(n_cos1 - cos2, n_cos1 + cos2); Rs *= Rs;
+		Rp = m_div(n_cos2 - cos1, n_cos2 + cos1); Rp *= Rp;
+		R = FP_0p5*(Rs + Rp);
+		if (cos1 <= FP_COS_90 || sin2 == FP_1) R = FP_1;
+		if (R < sim_random(s)) {
+			s->layer_index = next_index;
+			dir->x *= n1_d_n2;
+			dir->y *= n1_d_n2;
+			dir->z = -copysignf(cos2, dir->z);
+			return EV_REFRACTION;
+		}
+	}
+	return EV_REFLECTION;
+}
+
+static inline void sim_scatter(sim_t *s) {               /* mcml.template.c:277-290 */
+	float fi, cos_theta = pf_sample_angles(s, &fi);
+	scatter_direction(s, &s->dir, cos_theta, fi);
+}
+
+/* survival lottery, mcml.template.c:737-753 */
+static inline void lottery(sim_t *s, int *done) {
+	const xo_oracle_job *j = s->job;
+	if (s->weight < j->weight_min) {
+		if (j->use_lottery) {
+			if (sim_random(s) > j->lottery_chance) *done = 1;
+			else s->weight = m_div(s->weight, j->lottery_chance);
+		} else {
+			*done = 1;
+		}
+	}
+}
+
+/* next packet index for this work-item, or 0 when exhausted */
+typedef struct { uint32_t next, end; } quota_t;
+static inline int next_packet(sim_t *s, quota_t *q) {
+	if (s->dyn_counter) {
+		s->photon_index = __atomic_fetch_add(s->dyn_counter, 1u, __ATOMIC_RELAXED);
+		return s->photon_index < s->job->num_packets;
+	}
+	if (q->next >= q->end) return 0;
+	s->photon_index = q->next++;
+	return 1;
+}
+
+static void fluence_deposit_weight(sim_t *s, const p3f *pos, float deposit, float mua) {
+	if (s->job->fluence_kind) fluence_deposit_at(s, pos, deposit, mua);
+}
+
+/* ---- mcml work-item: mcml.template.c:346-824 -------------------------------- */
+static void workitem_mcml(sim_t *s, quota_t *q) {
+	const xo_oracle_job *j = s->job;
+	const p3f src_pos = source_position(j);
+	float step, deposit, rmax = j->rmax;
+	int32_t next_index;
+	int done = 0;
+	const int tr = j->trace_flags;
+
+	if (!next_packet(s, q)) return;
+	s->opl = FP_0; s->trace_count = 0; s->event_flags = 0;
+	launch_mcml(s);
+	s->event_flags |= EV_LAUNCH;
+	if (tr & XO_TRACE_START) trace_this_event(s);
+
+	while (!done) {
+		const ml_layer *L = ml_layer_at(j, s->layer_index);
+		s->iterations++;
+		if (j->method == XO_METHOD_MBL)
+			step = m_div(-m_log(s, sim_random(s)), L->mus);
+		else
+			step = -m_log(s, sim_random(s))*L->inv_mut;
+		step = fminf(step, FLT_MAX);
+		next_index = s->layer_index;
+		if (s->pos.z + step*s->dir.z < L->top) {
+			--next_index;
+			if (fabsf(s->dir.z) != FP_0) step = m_div(L->top - s->pos.z, s->dir.z);
+		}
+		if (s->pos.z + step*s->dir.z >= L->bottom) {
+			++next_index;
+			if (fabsf(s->dir.z) != FP_0) step = m_div(L->bottom - s->pos.z, s->dir.z);
+		}
+		s->pos.x = s->pos.x + s->dir.x*step;
+		s->pos.y = s->pos.y + s->dir.y*step;
+		s->pos.z = s->pos.z + s->dir.z*step;
+		if (j->track_opl) s->opl += L->n*step;
+		if (s->layer_index < next_index) s->pos.z = L->bottom;
+		if (s->layer_index > next_index) s->pos.z = L->top;
+
+		if (j->method == XO_METHOD_MBL) {              /* mcml.template.c:584-666 */
+			float mua = L->mua;
+			float deposit_fraction = FP_1 - m_exp(s, -mua*step);
+			deposit = deposit_fraction*s->weight;
+			s->weight -= deposit;
+			s->event_flags |= EV_ABSORPTION;
+			if (j->fluence_kind) {
+				float step_back = (mua != FP_0) ?
+					step - m_div(-m_log(s, FP_1 - sim_random(s)*deposit_fraction), mua) : FP_0;
+				p3f dp = { s->pos.x - step_back*s->dir.x, s->pos.y - step_back*s->dir.y,
+					s->pos.z - step_back*s->dir.z };
+				fluence_deposit_weight(s, &dp, deposit, L->mua);
+			}
+		}
+
+		if (next_index != s->layer_index) {
+			uint32_t bf = boundary_mcml(s, next_index);
+			s->event_flags |= bf | EV_BOUNDARY_HIT;
+			if (s->layer_index <= 0 || s->layer_index >= (int32_t)j->num_layers - 1) {
+				if (s->layer_index <= 0) {
+					if (j->det_kind[LOC_TOP])
+						detector_deposit(s, LOC_TOP, &s->pos, &s->dir, s->weight);
+				} else if (j->det_kind[LOC_BOTTOM]) {
+					detector_deposit(s, LOC_BOTTOM, &s->pos, &s->dir, s->weight);
+				}
+				done = 1;
+			}
+			if (j->method == XO_METHOD_MBL) lottery(s, &done);
+		} else if (j->method == XO_METHOD_MBL) {
+			sim_scatter(s);
+			s->event_flags |= EV_SCATTERING;
+			lottery(s, &done);
+		} else if (j->method == XO_METHOD_AR) {        /* mcml.template.c:705-721 */
+			L = ml_layer_at(j, s->layer_index);
+			if (sim_random(s) < L->mua_inv_mut) {
+				deposit = s->weight;
+				done = 1;
+				s->weight -= deposit;
+				s->event_flags |= EV_ABSORPTION;
+				fluence_deposit_weight(s, &s->pos, deposit, L->mua);
+			} else {
+				sim_scatter(s);
+				s->event_flags |= EV_SCATTERING;
+			}
+		} else {                                       /* AW, mcml.template.c:722-754 */
+			deposit = s->weight*L->mua_inv_mut;
+			s->weight -= deposit;
+			s->event_flags |= EV_ABSORPTION;
+			fluence_deposit_weight(s, &s->pos, deposit, L->mua);
+			sim_scatter(s);
+			s->event_flags |= EV_SCATTERING;
+			lottery(s, &done);
+		}
+
+		{   /* mcml.template.c:759-763 */
+			p3f d = { s->pos.x - src_pos.x, s->pos.y - src_pos.y, s->pos.z - src_pos.z };
+			if (dot3(&d, &d) > rmax*rmax) { done = 1; s->event_flags |= EV_ESCAPED; }
+		}
+		s->event_flags |= done ? EV_TERMINATED : 0;
+		if (tr == XO_TRACE_ALL) trace_this_event(s);
+		else if ((tr & XO_TRACE_END) && done) trace_this_event(s);
+		s->event_flags = 0;
+
+		if (done) {
+			if (tr) trace_finalize(s);
+			if (next_packet(s, q)) {
+				s->trace_count = 0;
+				s->opl = FP_0;
+				launch_mcml(s);
+				s->event_flags |= EV_LAUNCH;
+				if (tr & XO_TRACE_START) trace_this_event(s);
+				done = 0;
+			}
+		}
+	}
+}
+
+#include "xo_oracle_vox.inc"
+#include "xo_oracle_cyl.inc"
+
+static void run_workitem(xo_oracle_job *job, uint32_t t, quota_t *q, volatile uint32_t *dyn,
+		uint32_t *num_kernels, uint64_t *iterations) {
+	sim_t s;
+	memset(&s, 0, sizeof(s));
+	s.job = job;
+	s.rng_x = job->rng_x[t];
+	s.rng_a = job->rng_a[t];
+	s.weight = FP_1;
+	s.dyn_counter = dyn;
+	uint32_t before = q ? q->next : 0;
+	switch (job->geometry) {
+		case XO_GEOM_MCML: workitem_mcml(&s, q); break;
+		case XO_GEOM_MCVOX: workitem_mcvox(&s, q); break;
+		case XO_GEOM_MCCYL: workitem_mccyl(&s, q); break;
+	}
+	(void)before;
+	if (s.iterations > 0) {
+		__atomic_fetch_add(num_kernels, 1u, __ATOMIC_RELAXED);
+		job->rng_x[t] = s.rng_x;     /* mcml.template.c:821 (only if a packet was taken) */
+	}
+	__atomic_fetch_add(iterations, s.iterations, __ATOMIC_RELAXED);
+}
+
+int xo_oracle_run(xo_oracle_job *job) {
+	uint32_t N = job->num_packets, T = job->num_threads;
+	if (T == 0) return 1;
+	uint32_t qn = N/T, r = N % T, base = 0;
+	job->num_kernels = 0; job->num_iterations = 0;
+	for (uint32_t t = 0; t < T; ++t) {
+		uint32_t n_t = qn + (t < r ? 1u : 0u);
+		quota_t q = { base, base + n_t };
+		if (n_t) run_workitem(job, t, &q, NULL, &job->num_kernels, &job->num_iterations);
+		base += n_t;
+	}
+	job->num_packets_done = N + T;
+	return 0;
+}
+
+typedef struct { xo_oracle_job *job; uint32_t t; volatile uint32_t *counter; } dyn_arg;
+static void *dyn_worker(void *p) {
+	dyn_arg *d = (dyn_arg *)p;
+	run_workitem(d->job, d->t, NULL, d->counter, &d->job->num_kernels, &d->job->num_iterations);
+	return NULL;
+}
+int xo_oracle_run_dynamic(xo_oracle_job *job, uint32_t ncpu) {
+	if (ncpu == 0) return 1;
+	volatile uint32_t counter = 0;
+	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t)*ncpu);
+	dyn_arg *da = (dyn_arg *)malloc(sizeof(dyn_arg)*ncpu);
+	job->num_kernels = 0; job->num_iterations = 0;
+	for (uint32_t t = 0; t < ncpu; ++t) {
+		da[t].job = job; da[t].t = t; da[t].counter = &counter;
+		pthread_create(&th[t], NULL, dyn_worker, &da[t]);
+	}
+	for (uint32_t t = 0; t < ncpu; ++t) pthread_join(th[t], NULL);
+	job->num_packets_done = counter;
+	free(th); free(da);
+	return 0;
+}
+
+void xo_oracle_math_probe(int32_t fn, int32_t math, uint32_t n,
+		const float *in0, const float *in1, float *out0, float *out1) {
+	xo_oracle_job j; memset(&j, 0, sizeof(j)); j.math = math;
+	sim_t s; memset(&s, 0, sizeof(s)); s.job = &j;
+	for (uint32_t i = 0; i < n; ++i) {
+		switch (fn) {
+			case 0: out0[i] = m_log(&s, in0[i]); break;
+			case 1: m_sincos(&s, in0[i], &out0[i], &out1[i]); break;
+			case 2: out0[i] = m_cbrt(&s, in0[i]); break;
+			case 3: out0[i] = m_pow(&s, in0[i], in1[i]); break;
+			case 4: out0[i] = m_exp(&s, in0[i]); break;
+			case 5: out0[i] = m_atan2(&s, in0[i], in1[i]); break;
+			case 6: out0[i] = m_sqrt(in0[i]); break;
+			case 7: out0[i] = m_div(in0[i], in1[i]); break;
+		}
+	}
+}
