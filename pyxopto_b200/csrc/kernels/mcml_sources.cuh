@@ -1,0 +1,139 @@
+// mcml_sources.cuh -- photon packet sources of the layered simulator.
+//
+// Struct members = packed `McSource` of the reference plugins
+// (xopto/mcml/mcsource/{line,gaussianbeam,fiber,point}.py `cl_type`);
+// `launch()` draws the same uniforms in the same order as `mcsim_launch`.
+// `Ctx` gives access to layer refractive indices and the specular detector.
+#pragma once
+#include "xo_core.cuh"
+
+namespace xo {
+
+// Every launch() fills pos/dir/weight/layer and returns the direction + weight
+// to hand to the specular detector (weight < 0: nothing to deposit).
+struct Launch {
+	P3 pos, dir;
+	float weight;
+	i32 layer;
+	P3 spec_dir;
+	float spec_weight;
+};
+
+struct SrcLine {                    // mcsource/line.py:57-63
+	P3 position, direction_medium, direction_sample, direction_reflected;
+	float reflectance;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		(void)rng; (void)ctx;
+		L.weight = 1.0f - reflectance;
+		L.pos = position;
+		L.dir = direction_sample;
+		L.spec_dir = direction_reflected;
+		L.spec_weight = reflectance;
+		L.layer = 1;
+	}
+};
+
+struct SrcGaussianBeam {            // mcsource/gaussianbeam.py:75-85 (pack=1)
+	M3 T; P3 position, direction; P2 sigma; float clip, reflectance;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf;
+		float r = M::sqrt(-2.0f*M::log(1.0f - rng.next()));
+		r = fminf(r, clip);
+		M::sincos(XO_FP_2PI*rng.next(), &sf, &cf);
+		P3 ps = { r*cf*sigma.x, r*sf*sigma.y, 0.0f };
+		P3 pm = transform3(T, ps);
+		float k = M::div(0.0f - pm.z, direction.z);
+		pm.x += k*direction.x;
+		pm.y += k*direction.y;
+		L.pos.x = position.x + pm.x;
+		L.pos.y = position.y + pm.y;
+		L.pos.z = 0.0f;
+		L.dir = direction;
+		L.layer = 1;
+		L.weight = 1.0f - reflectance;
+		if (Ctx::has_specular) {
+			P3 din = { direction.x, direction.y, -direction.z };
+			P3 normal = { 0.0f, 0.0f, -1.0f };
+			L.spec_dir = refract3(din, normal, ctx.layer_n(1), ctx.layer_n(0));
+		}
+		L.spec_weight = reflectance;
+	}
+};
+
+struct SrcUniformFiber {            // mcsource/fiber.py:224-232
+	M3 T; P3 position, direction; float radius, cos_min, n;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf;
+		float r = M::sqrt(rng.next())*radius;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		P3 ps = { r*cf, r*sf, 0.0f };
+		P3 pm = transform3(T, ps);
+		float k = M::div(0.0f - pm.z, direction.z);
+		pm.x += k*direction.x;
+		pm.y += k*direction.y;
+		L.pos.x = position.x + pm.x;
+		L.pos.y = position.y + pm.y;
+		L.pos.z = 0.0f;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 1.0f - rng.next()*(1.0f - cos_min);
+		float st = M::sqrt(1.0f - ct*ct);
+		st = M::div(st, n);
+		ct = M::sqrt(1.0f - st*st);
+		P3 ds = { cf*st, sf*st, ct };
+		P3 d = transform3(T, ds);
+		float n1 = ctx.layer_n(1);
+		float cc = cos_critical(n, n1);
+		// The reference tests the launch-plane offset z (== 0) against cc, so
+		// the direction enters the sample un-refracted.
+		L.dir = d;
+		float rs = reflectance(n, n1, d.z, cc);
+		L.weight = 1.0f - rs;
+		L.spec_dir = d;
+		L.spec_weight = rs;
+		L.layer = 1;
+	}
+};
+
+struct SrcIsotropicPoint {          // mcsource/point.py:46-49
+	P3 position; u32 layer_index;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf, rs = 0.0f;
+		P3 p = position;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 1.0f - 2.0f*rng.next();
+		float st = M::sqrt(1.0f - ct*ct);
+		P3 d = { cf*st, sf*st, ct };
+		P3 rd = d;
+		if (p.z <= 0.0f) {
+			float cc = ctx.layer_cc_bottom(0);
+			if (d.z > cc) {
+				P3 normal = { 0.0f, 0.0f, 1.0f };
+				float ns = ctx.layer_n(1), nm = ctx.layer_n(0);
+				rd = refract3(d, normal, ns, nm);
+				rs = reflectance(nm, ns, d.z, cc);
+				float t = M::div(-p.z, d.z);
+				p.x += d.x*t;
+				p.y += d.y*t;
+			} else {
+				rs = 1.0f;
+			}
+			p.z = 0.0f;
+		}
+		L.dir = rd;
+		L.pos = p;
+		L.spec_dir = d;
+		L.spec_weight = rs;
+		L.weight = 1.0f - rs;
+		L.layer = (i32)layer_index;
+	}
+};
+
+}  // namespace xo

@@ -1,0 +1,33 @@
+// xo_aux_kernels.cuh -- helper kernels: RNG known-answer hook and the
+// elementary-function probe used by the parity tests.
+//  * RngKernel  : counterpart of the reference's RngKernel
+//                 (xopto/mcbase/kernel/mcbase.template.c:1640-1646)
+//  * MathProbe  : evaluates one function of the active math binding
+//                 (DetMath when XO_DETERMINISTIC=1, FastMath otherwise)
+#pragma once
+#include "xo_core.cuh"
+
+extern "C" __global__ void RngKernel(xo::u64 x, xo::u32 a, xo::u32 n, float *buffer) {
+	if (blockIdx.x*blockDim.x + threadIdx.x == 0) {
+		xo::Rng rng; rng.x = x; rng.a = a;
+		for (xo::u32 i = 0; i < n; ++i) buffer[i] = rng.next();
+	}
+}
+
+extern "C" __global__ void MathProbe(int fn, xo::u32 n, const float *in0, const float *in1,
+		float *out0, float *out1) {
+	using namespace xo;
+	u32 i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float a = in0[i], b = in1[i];
+	switch (fn) {
+		case 0: out0[i] = M::log(a); break;
+		case 1: M::sincos(a, &out0[i], &out1[i]); break;
+		case 2: out0[i] = M::cbrt(a); break;
+		case 3: out0[i] = M::pow(a, b); break;
+		case 4: out0[i] = M::exp(a); break;
+		case 5: out0[i] = M::atan2(a, b); break;
+		case 6: out0[i] = M::sqrt(a); break;
+		case 7: out0[i] = M::div(a, b); break;
+	}
+}

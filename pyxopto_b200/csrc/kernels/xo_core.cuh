@@ -1,0 +1,226 @@
+// xo_core.cuh -- shared device code of the mcml / mcvox / mccyl kernels.
+//
+// Hand-written CUDA for sm_100a.  Functionally this is the B200 counterpart of
+// xopto/mcbase/kernel/mcbase.template.{h,c} (RNG, vector helpers, boundary
+// physics, scattering rotation, 64-bit fixed-point accumulators); structure and
+// data layout are this engine's own:
+//   * the per-thread MWC state lives in registers (one IMAD.WIDE per draw),
+//   * packed plugin structs arrive BY VALUE as __grid_constant__ kernel
+//     parameters (constant bank -> uniform operands, no loads),
+//   * per-thread-indexed tables (layers / materials / pf LUT) are staged in
+//     shared memory,
+//   * small accumulators (detectors) are privatised per CTA in shared memory as
+//     lo/hi 32-bit words and flushed with 64-bit REDs at CTA exit; large grids
+//     (fluence) use RED.E.ADD.64 straight to L2.
+#pragma once
+#include "xo_math.cuh"
+
+namespace xo {
+
+typedef unsigned int u32;
+typedef int i32;
+typedef unsigned long long u64;
+typedef long long i64;
+
+#ifndef XO_DETERMINISTIC
+#define XO_DETERMINISTIC 0
+#endif
+#if XO_DETERMINISTIC
+typedef DetMath M;
+#else
+typedef FastMath M;
+#endif
+
+#define XO_FP_2PI 6.283185307179586f
+#define XO_FP_COS_30 0.8660254037844386f
+#define XO_FP_INV_C 3.3356409519815204e-09f
+#define XO_FP_RMIN 1e-12f
+#define XO_FP_PLMIN 1e-12f
+#define XO_ACCU_K 8388607.0f
+
+// event flags (values as in mcbase.template.h:664-681 so Trace event masks mean the same)
+enum : u32 {
+	EV_REFLECTION = 1u, EV_REFRACTION = 2u, EV_BOUNDARY_HIT = 4u, EV_LAUNCH = 8u,
+	EV_ABSORPTION = 16u, EV_SCATTERING = 32u, EV_TERMINATED = 64u, EV_ESCAPED = 128u
+};
+enum { METHOD_AW = 0, METHOD_AR = 1, METHOD_MBL = 2 };
+enum { LOC_TOP = 0, LOC_BOTTOM = 1, LOC_SPECULAR = 2 };
+
+// ---- packed vector types (ctypes layout: tightly packed 4-byte members) -----
+struct P3 { float x, y, z; };
+struct P2 { float x, y; };
+struct M3 { float a11, a12, a13, a21, a22, a23, a31, a32, a33; };
+
+__device__ __forceinline__ float dot3(const P3 &a, const P3 &b) {
+#if XO_DETERMINISTIC
+	return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+#else
+	return a.x*b.x + a.y*b.y + a.z*b.z;
+#endif
+}
+__device__ __forceinline__ P3 transform3(const M3 &m, const P3 &v) {
+	P3 r;
+	r.x = m.a11*v.x + m.a12*v.y + m.a13*v.z;
+	r.y = m.a21*v.x + m.a22*v.y + m.a23*v.z;
+	r.z = m.a31*v.x + m.a32*v.y + m.a33*v.z;
+	return r;
+}
+__device__ __forceinline__ float clipf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ i32 clipi(i32 x, i32 lo, i32 hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ float signf(float x) { return (x >= 0.0f) ? 1.0f : -1.0f; }
+// C float->int conversion of the reference (convert_int / (uint32_t) casts):
+// CUDA's cvt.rzi saturates where C is undefined; identical on every reachable value.
+__device__ __forceinline__ i32 f2i(float x) { return __float2int_rz(x); }
+__device__ __forceinline__ u32 f2u(float x) { return __float2uint_rz(x); }
+
+// ---- RNG: 64-bit multiply-with-carry, state in registers -------------------
+// Same recurrence and float mapping as fp_random_single (mcbase.template.c:1576):
+//   x <- lo32(x)*a + hi32(x);  u = RN(float(lo32(x))) / RN(float(0xFFFFFFFF)) = RN(float(lo32 x))*2^-32
+// (the divisor rounds to 2^32, so the IEEE division is an exact scaling).
+struct Rng {
+	u64 x;
+	u32 a;
+	__device__ __forceinline__ float next() {
+		x = (u64)(u32)x*(u64)a + (x >> 32);
+		return __uint2float_rn((u32)x)*2.3283064365386963e-10f;
+	}
+};
+
+// ---- boundary physics (Fresnel, Snell) --------------------------------------
+__device__ __forceinline__ float cos_critical(float n1, float n2) {
+	return (n1 > n2) ? M::sqrt(1.0f - M::div(n2*n2, n1*n1)) : 0.0f;
+}
+
+// unpolarised Fresnel reflectance; cos1 = incidence cosine, cc = critical cosine
+__device__ inline float reflectance(float n1, float n2, float cos1, float cc) {
+	float R = 1.0f;
+	cos1 = fabsf(cos1);
+	if (n1 == n2) return 0.0f;
+	if (cos1 > cc) {
+		float n12 = M::div(n1, n2);
+		float sin1 = M::sqrt(1.0f - cos1*cos1);
+		if (cos1 >= 1.0f) sin1 = 0.0f;
+		float sin2 = fminf(1.0f, n12*sin1);
+		float cos2 = M::sqrt(1.0f - sin2*sin2);
+		float nc1 = n12*cos1, nc2 = n12*cos2;
+		float Rs = M::div(nc1 - cos2, nc1 + cos2); Rs *= Rs;
+		float Rp = M::div(nc2 - cos1, nc2 + cos1); Rp *= Rp;
+		R = 0.5f*(Rp + Rs);
+		if (cos1 <= 0.0f || sin2 == 1.0f) return 1.0f;
+	}
+	return R;
+}
+
+__device__ __forceinline__ P3 reflect3(const P3 &p, const P3 &n) {
+	float k = 2.0f*dot3(p, n);
+	P3 r = { p.x - n.x*k, p.y - n.y*k, p.z - n.z*k };
+	return r;
+}
+__device__ __forceinline__ P3 refract3(const P3 &p, const P3 &n, float n1, float n2) {
+	float cos1 = dot3(p, n);
+	float n12 = M::div(n1, n2);
+	float sin2sq = n12*n12*(1.0f - cos1*cos1);
+	float k = signf(cos1)*(n12*fabsf(cos1) - M::sqrt(1.0f - sin2sq));
+	P3 r = { n12*p.x - k*n.x, n12*p.y - k*n.y, n12*p.z - k*n.z };
+	return r;
+}
+__device__ __forceinline__ bool refract3_safe(const P3 &p, const P3 &n, float n1, float n2, P3 *r) {
+	float cos1 = dot3(p, n);
+	float n12 = M::div(n1, n2);
+	float sin2sq = n12*n12*(1.0f - cos1*cos1);
+	if (sin2sq > 1.0f) return true;
+	float k = signf(cos1)*(n12*fabsf(cos1) - M::sqrt(1.0f - sin2sq));
+	r->x = n12*p.x - k*n.x; r->y = n12*p.y - k*n.y; r->z = n12*p.z - k*n.z;
+	return false;
+}
+
+// ---- scattering rotation -----------------------------------------------------
+// Rotates `d` by polar cosine ct and azimuth fi, then renormalises (the
+// reference always renormalises in single precision, mcbase.template.c:1551).
+__device__ __forceinline__ void scatter_direction(P3 &d, float ct, float fi) {
+	float sf, cf;
+	float st = M::sqrt(1.0f - ct*ct);
+	M::sincos(fi, &sf, &cf);
+	float stcf = st*cf, stsf = st*sf;
+	float px = d.x;
+	if (fabsf(d.z) >= 1.0f) {
+		d.x = stcf;
+		d.y = stsf;
+		d.z = copysignf(ct, d.z*ct);
+	} else {
+#if XO_DETERMINISTIC
+		float k = M::sqrt(1.0f - d.z*d.z);
+		d.x = M::div(stcf*px*d.z - stsf*d.y, k) + px*ct;
+		d.y = M::div(stcf*d.y*d.z + stsf*px, k) + d.y*ct;
+		d.z = (-stcf)*k + d.z*ct;
+#else
+		float k2 = 1.0f - d.z*d.z;
+		float ik = rsqrtf(k2);
+		float nx = (stcf*px*d.z - stsf*d.y)*ik + px*ct;
+		float ny = (stcf*d.y*d.z + stsf*px)*ik + d.y*ct;
+		d.z = d.z*ct - stcf*(k2*ik);
+		d.x = nx; d.y = ny;
+#endif
+	}
+#if XO_DETERMINISTIC
+	float k = M::div(1.0f, M::sqrt(d.x*d.x + d.y*d.y + d.z*d.z));
+#else
+	float k = rsqrtf(d.x*d.x + d.y*d.y + d.z*d.z);
+#endif
+	d.x *= k; d.y *= k; d.z *= k;
+}
+
+// ---- accumulators ------------------------------------------------------------
+// The flat accumulator buffer holds detector bins first (pack order) and the
+// fluence grid after them.  Bins [0, priv_len) are privatised per CTA in shared
+// memory as (lo, hi) 32-bit pairs -- the reference's accu_64_deposit_32 carry
+// trick (mcbase.template.c:58-61) applied to shared memory, where 32-bit ATOMS
+// are native.  Integer adds commute, so totals are exact under any schedule.
+struct Accu {
+	u64 *global;
+	u32 *priv;        // shared memory, 2*priv_len words
+	u32 priv_len;
+	__device__ __forceinline__ void add(u32 index, u32 w) const {
+		if (index < priv_len) {
+			u32 old = atomicAdd(priv + 2*index, w);
+			if (old + w < old) atomicAdd(priv + 2*index + 1, 1u);
+		} else {
+			atomicAdd(global + index, (u64)w);
+		}
+	}
+	// large-grid deposit that bypasses the private window test
+	__device__ __forceinline__ void add_global(u32 index, u32 w) const {
+		atomicAdd(global + index, (u64)w);
+	}
+	__device__ __forceinline__ void zero_private() const {
+		for (u32 i = threadIdx.x; i < 2*priv_len; i += blockDim.x) priv[i] = 0;
+	}
+	__device__ __forceinline__ void flush_private() const {
+		for (u32 i = threadIdx.x; i < priv_len; i += blockDim.x) {
+			u64 v = ((u64)priv[2*i + 1] << 32) | priv[2*i];
+			if (v) atomicAdd(global + i, v);
+		}
+	}
+};
+
+// weight -> fixed point with the detector acceptance test folded in:
+// (uint32)((w*K + 0.5)*(int)accept)   (mcml.template.h:606 + mcdetector/*.py)
+__device__ __forceinline__ u32 weight_u32(float w, bool accept) {
+#if XO_DETERMINISTIC
+	float v = __fadd_rn(__fmul_rn(w, XO_ACCU_K), 0.5f);
+#else
+	float v = fmaf(w, XO_ACCU_K, 0.5f);
+#endif
+	return accept ? f2u(v) : 0u;
+}
+
+// block-schedule quota of work-item t (deterministic mode)
+__device__ __forceinline__ void static_quota(u32 N, u32 T, u32 t, u32 *first, u32 *end) {
+	u32 q = N/T, r = N % T;
+	u32 n_t = q + (t < r ? 1u : 0u);
+	u32 base = t*q + (t < r ? t : r);
+	*first = base;
+	*end = base + n_t;
+}
+
+}  // namespace xo

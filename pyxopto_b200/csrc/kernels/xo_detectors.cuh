@@ -1,0 +1,123 @@
+// xo_detectors.cuh -- surface / specular detectors.
+//
+// Struct members = packed `Mc{Top,Bottom,Specular}Detector` of the reference
+// plugins (xopto/mcml/mcdetector/*.py `cl_type`); `deposit()` restates the bin
+// selection and acceptance test of the plugin's `mcsim_*_detector_deposit` and
+// pushes the fixed-point weight through the CTA-private accumulator window.
+#pragma once
+#include "xo_core.cuh"
+
+namespace xo {
+
+// absent detector: DetectorDefault {int64 dummy} (mcdetector/base.py:145-146)
+struct DetNone {
+	i64 dummy;
+	static constexpr bool active = false;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &, const P3 &, const P3 &, float, float) const {}
+};
+
+struct DetTotal {                   // mcdetector/total.py
+	P3 direction; float cos_min; u32 offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		(void)pos;
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add(offset, iw);
+	}
+};
+
+struct DetRadial {                  // mcdetector/radial.py
+	P3 direction; P2 position; float r_min, inv_dr, cos_min; u32 n, offset; i32 log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		float dx = pos.x - position.x, dy = pos.y - position.y;
+		float r = M::sqrt(dx*dx + dy*dy);
+		if (log_scale) r = M::log(fmaxf(r, XO_FP_RMIN));
+		i32 ri = clipi(f2i((r - r_min)*inv_dr), 0, (i32)(n - 1));
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add(offset + (u32)ri, iw);
+	}
+};
+
+struct DetCartesian {               // mcdetector/cartesian.py
+	P3 direction; float x_min, inv_dx, y_min, inv_dy, cos_min; u32 n_x, n_y, offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		i32 ix = clipi(f2i((pos.x - x_min)*inv_dx), 0, (i32)(n_x - 1));
+		i32 iy = clipi(f2i((pos.y - y_min)*inv_dy), 0, (i32)(n_y - 1));
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add((u32)iy*n_x + (u32)ix + offset, iw);
+	}
+};
+
+struct DetSixAroundOne {            // mcdetector/probe/sixaroundone.py
+	M3 T; P2 position; float core_r_squared, core_spacing, cos_min; u32 offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		u32 fiber = 7;
+		float rx = pos.x - position.x, ry = pos.y - position.y;
+		P3 p = { rx, ry, 0.0f };
+		P3 q = transform3(T, p);
+		if (q.x*q.x + q.y*q.y <= core_r_squared) fiber = 0;
+		p.x = fabsf(rx) - core_spacing; p.y = ry;
+		q = transform3(T, p);
+		if (q.x*q.x + q.y*q.y <= core_r_squared) fiber = (rx >= 0.0f) ? 1 : 4;
+		p.x = fabsf(rx) - core_spacing*0.5f;
+		p.y = fabsf(ry) - core_spacing*XO_FP_COS_30;
+		q = transform3(T, p);
+		if (q.x*q.x + q.y*q.y <= core_r_squared)
+			fiber = (rx >= 0.0f) ? ((ry >= 0.0f) ? 2 : 6) : ((ry >= 0.0f) ? 3 : 5);
+		if (fiber > 6) return;
+		float pz = T.a31*dir.x + T.a32*dir.y + T.a33*dir.z;
+		u32 iw = weight_u32(w, cos_min <= fabsf(pz));
+		if (iw > 0) acc.add(offset + fiber, iw);
+	}
+};
+
+struct DetRadialPl {                // mcdetector/radialpl.py
+	P3 direction; P2 position; float r_min, inv_dr, pl_min, inv_dpl, cos_min;
+	u32 n_r, n_pl, offset; i32 r_log_scale, pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		float dx = pos.x - position.x, dy = pos.y - position.y;
+		float r = M::sqrt(dx*dx + dy*dy);
+		if (r_log_scale) r = M::log(fmaxf(r, XO_FP_RMIN));
+		i32 ri = clipi(f2i((r - r_min)*inv_dr), 0, (i32)(n_r - 1));
+		float pl = opl;
+		if (pl_log_scale) pl = M::log(fmaxf(pl, XO_FP_PLMIN));
+		i32 pi = clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add(offset + (u32)pi*n_r + (u32)ri, iw);
+	}
+};
+
+struct DetTotalPl {                 // mcdetector/totalpl.py
+	P3 direction; float cos_min, pl_min, inv_dpl; u32 n_pl, offset; i32 pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		(void)pos;
+		float pl = opl;
+		if (pl_log_scale) pl = M::log(fmaxf(pl, XO_FP_PLMIN));
+		i32 pi = clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add(offset + (u32)pi, iw);
+	}
+};
+
+// packed McDetectors {top, bottom, specular} (mcdetector/base.py:321-327);
+// natural alignment as laid out by ctypes.
+template <class Top, class Bottom, class Specular>
+struct Detectors {
+	Top top;
+	Bottom bottom;
+	Specular specular;
+};
+
+}  // namespace xo

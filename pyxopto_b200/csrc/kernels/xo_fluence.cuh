@@ -1,0 +1,126 @@
+// xo_fluence.cuh -- fluence / deposition accumulators and the packet trace.
+//
+// Struct members = packed `McFluence` / `McTrace` of the reference plugins
+// (xopto/mcbase/mcfluence/{fluence,fluencerz,fluencet}.py, mcbase/mctrace.py
+// `cl_type`).  Deposits go straight to the 64-bit global grid with RED.E.ADD.64;
+// the voxel index arithmetic restates `mcsim_fluence_deposit_at`.
+#pragma once
+#include "xo_core.cuh"
+
+namespace xo {
+
+struct FluNone {
+	i32 dummy;
+	static constexpr bool active = false;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &, const P3 &, float, float, float) const {}
+};
+
+#ifndef XO_FLUENCE_RATE
+#define XO_FLUENCE_RATE 0
+#endif
+
+__device__ __forceinline__ u32 fluence_weight(float w, float mua, i32 k) {
+#if XO_FLUENCE_RATE
+	w *= (mua != 0.0f) ? M::div(1.0f, mua) : 0.0f;
+#else
+	(void)mua;
+#endif
+#if XO_DETERMINISTIC
+	return f2u(__fadd_rn(__fmul_rn(w, (float)k), 0.5f));
+#else
+	return f2u(fmaf(w, (float)k, 0.5f));
+#endif
+}
+
+struct FluXyz {                     // mcfluence/fluence.py:57-63
+	P3 inv_step, top_left; u32 nx, ny, nz, offset; i32 k;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, float w, float mua, float) const {
+		float fx = (pos.x - top_left.x)*inv_step.x;
+		float fy = (pos.y - top_left.y)*inv_step.y;
+		float fz = (pos.z - top_left.z)*inv_step.z;
+		if (fx >= 0.0f && fy >= 0.0f && fz >= 0.0f &&
+				fx < (float)nx && fy < (float)ny && fz < (float)nz) {
+			u32 index = (f2u(fz)*ny + f2u(fy))*nx + f2u(fx);
+			acc.add_global(offset + index, fluence_weight(w, mua, k));
+		}
+	}
+};
+
+struct FluRz {                      // mcfluence/fluencerz.py:64-72
+	P3 center; float inv_dr, inv_dz; u32 n_r, n_z, offset; i32 k;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, float w, float mua, float) const {
+		float dx = pos.x - center.x, dy = pos.y - center.y;
+		float r = M::sqrt(dx*dx + dy*dy);
+		float dz = pos.z - center.z;
+		float fr = r*inv_dr, fz = dz*inv_dz;
+		if (fr >= 0.0f && fz >= 0.0f && fr < (float)n_r && fz < (float)n_z) {
+			u32 index = f2u(fz)*n_r + f2u(fr);
+			acc.add_global(offset + index, fluence_weight(w, mua, k));
+		}
+	}
+};
+
+struct FluXyzt {                    // mcfluence/fluencet.py:57-63
+	float inv_step[4], top_left[4]; u32 shape[4]; u32 offset; i32 k;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, float w, float mua, float opl) const {
+		float fx = (pos.x - top_left[0])*inv_step[0];
+		float fy = (pos.y - top_left[1])*inv_step[1];
+		float fz = (pos.z - top_left[2])*inv_step[2];
+		float ft = (opl*XO_FP_INV_C - top_left[3])*inv_step[3];
+		if (ft >= 0.0f && fx >= 0.0f && fy >= 0.0f && fz >= 0.0f &&
+				fx < (float)shape[0] && fy < (float)shape[1] &&
+				fz < (float)shape[2] && ft < (float)shape[3]) {
+			u32 index = ((f2u(fz)*shape[1] + f2u(fy))*shape[0] + f2u(fx))*shape[3] + f2u(ft);
+			acc.add_global(offset + index, fluence_weight(w, mua, k));
+		}
+	}
+};
+
+// ---- trace ------------------------------------------------------------------
+#ifndef XO_TRACE
+#define XO_TRACE 0
+#endif
+#ifndef XO_USE_EVENTS
+#define XO_USE_EVENTS 0
+#endif
+#define XO_TRACE_START 1
+#define XO_TRACE_END 2
+#define XO_TRACE_ALL 7
+
+struct TraceCfg {                   // mcbase/mctrace.py:504-510
+	i32 max_events; u32 data_off, count_off, event_mask;
+};
+struct TraceNone { i32 dummy; };
+
+// one event = 8 floats {x,y,z,px,py,pz,w,pl}; overflow keeps overwriting the
+// last slot while the count keeps growing (mctrace.py:543-545,578-581)
+__device__ __forceinline__ bool trace_event(const TraceCfg &t, float *fbuf, u32 packet,
+		u32 count, u32 flags, const P3 &pos, const P3 &dir, float w, float opl) {
+#if XO_USE_EVENTS
+	if (!(t.event_mask & flags)) return false;
+#else
+	(void)flags;
+#endif
+	i32 slot = (i32)count < t.max_events - 1 ? (i32)count : t.max_events - 1;
+	u32 p = (u32)slot*8u + packet*(u32)t.max_events*8u + t.data_off;
+	float *dst = fbuf + p;
+#if XO_TRACE_ALIGNED
+	float4 *d4 = reinterpret_cast<float4 *>(dst);
+	d4[0] = make_float4(pos.x, pos.y, pos.z, dir.x);
+	d4[1] = make_float4(dir.y, dir.z, w, opl);
+#else
+	dst[0] = pos.x; dst[1] = pos.y; dst[2] = pos.z;
+	dst[3] = dir.x; dst[4] = dir.y; dst[5] = dir.z;
+	dst[6] = w; dst[7] = opl;
+#endif
+	return true;
+}
+
+}  // namespace xo

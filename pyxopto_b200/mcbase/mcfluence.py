@@ -1,0 +1,293 @@
+"""Fluence / deposition accumulators (mirror of ``xopto/mcbase/mcfluence``:
+Fluence, FluenceRz, Fluencet).  ``mode='deposition'`` accumulates absorbed
+weight, ``mode='fluence'`` divides each deposit by the local mua."""
+from typing import Tuple
+
+import numpy as np
+
+from ..cl import cltypes
+from .mcobject import McObject
+from .mcutil.axis import Axis, RadialAxis  # noqa: F401  (re-exported like the reference)
+
+_K_DEFAULT = 0x7FFFFF
+
+
+def _check_mode(mode):
+    if mode not in ('fluence', 'deposition'):
+        raise ValueError('The value of mode parameter must be '
+                         '"fluence" or "deposition" but got {}!'.format(mode))
+
+
+class _FluenceBase(McObject):
+    def _init_common(self, mode, k=_K_DEFAULT, data=None, nphotons=0):
+        _check_mode(mode)
+        self._mode, self._k, self._data, self._nphotons = mode, k, data, nphotons
+
+    nphotons = property(lambda self: self._nphotons)
+    mode = property(lambda self: self._mode)
+
+    def _set_k(self, k):
+        self._k = max(1, min(int(k), int(2**31 - 1)))
+
+    k = property(lambda self: self._k, _set_k, None,
+                 'Weight to fixed-point conversion factor.')
+
+    def _set_raw(self, data):
+        self._data = data
+
+    raw = property(lambda self: self._data, _set_raw, None, 'Raw accumulator data.')
+
+    def cl_options(self, mc):
+        return [('MC_USE_FLUENCE', True),
+                ('MC_FLUENCE_MODE_RATE', self._mode == 'fluence')] + self._extra_options
+
+    _extra_options = []
+
+    def update_data(self, mc, data, nphotons, **kwargs):
+        accumulators = data[np.dtype(mc.types.np_accu)]
+        if self._data is not None:
+            self._data.flat += accumulators[0]*(1.0/self.k)
+            self._nphotons += nphotons
+        else:
+            self._data = accumulators[0]*(1.0/self.k)
+            self._data.shape = self.shape
+            self._nphotons = nphotons
+
+    def update(self, obj):
+        if self._data is not None:
+            if self.shape != obj.shape:
+                raise TypeError('Cannot update with fluence data of incompatible shape!')
+            self._data += obj.raw
+            self._nphotons += obj.nphotons
+        else:
+            self._data = obj.raw
+            self._nphotons = obj.nphotons
+
+
+class Fluence(_FluenceBase):
+    """Cartesian x-y-z grid; raw data shape (nz, ny, nx) (mcfluence/fluence.py)."""
+    cu_type = 'xo::FluXyz'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClFluence(cltypes.Structure):
+            _fields_ = [('inv_step', T.mc_point3f_t), ('top_left', T.mc_point3f_t),
+                        ('shape', T.mc_point3s_t), ('offset', T.mc_size_t),
+                        ('k', T.mc_int_t)]
+        return ClFluence
+
+    def __init__(self, xaxis=None, yaxis: Axis = None, zaxis: Axis = None,
+                 mode: str = 'deposition'):
+        super().__init__()
+        data, nphotons, k = None, 0, _K_DEFAULT
+        if isinstance(xaxis, Fluence):
+            f = xaxis
+            xaxis, yaxis, zaxis = Axis(f.xaxis), Axis(f.yaxis), Axis(f.zaxis)
+            nphotons, mode, k = f.nphotons, f.mode, f.k
+            if f.raw is not None:
+                data = np.copy(f.raw)
+        xaxis = Axis(-0.5, 0.5, 1) if xaxis is None else xaxis
+        yaxis = Axis(-0.5, 0.5, 1) if yaxis is None else yaxis
+        zaxis = Axis(0.0, 1.0, 1) if zaxis is None else zaxis
+        for name, ax in (('x', xaxis), ('y', yaxis), ('z', zaxis)):
+            if ax.logscale:
+                raise ValueError('Fluence does not support logarithmic {} axis!'.format(name))
+        self._x_axis, self._y_axis, self._z_axis = xaxis, yaxis, zaxis
+        self._init_common(mode, k, data, nphotons)
+
+    shape = property(lambda self: (self._z_axis.n, self._y_axis.n, self._x_axis.n))
+    xaxis = property(lambda self: self._x_axis)
+    yaxis = property(lambda self: self._y_axis)
+    zaxis = property(lambda self: self._z_axis)
+    x = property(lambda self: self._x_axis.centers)
+    y = property(lambda self: self._y_axis.centers)
+    z = property(lambda self: self._z_axis.centers)
+    dx = property(lambda self: abs(self._x_axis.step))
+    dy = property(lambda self: abs(self._y_axis.step))
+    dz = property(lambda self: abs(self._z_axis.step))
+
+    @property
+    def data(self):
+        return self._data*(1.0/(max(self.nphotons, 1)*self.dx*self.dy*self.dz))
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        for c, ax in zip('xyz', (self._x_axis, self._y_axis, self._z_axis)):
+            setattr(target.top_left, c, ax.start)
+            setattr(target.inv_step, c, 1.0/ax.step)
+            setattr(target.shape, c, ax.n)
+        target.k = self._k
+        return target
+
+    def todict(self):
+        return {'type': 'Fluence', 'mode': self._mode, 'xaxis': self._x_axis.todict(),
+                'yaxis': self._y_axis.todict(), 'zaxis': self._z_axis.todict()}
+
+    @classmethod
+    def fromdict(cls, data):
+        d = dict(data)
+        d.pop('type')
+        return cls(Axis.fromdict(d.pop('xaxis')), Axis.fromdict(d.pop('yaxis')),
+                   Axis.fromdict(d.pop('zaxis')), **d)
+
+
+class FluenceRz(_FluenceBase):
+    """Radially symmetric r-z grid (mcfluence/fluencerz.py).
+
+    Quirk kept from the reference: ``shape`` is reported as (n_r, n_z) although
+    the kernel stores bins z-major (index = iz*n_r + ir, fluencerz.py:140,292).
+    ``raw_zr`` exposes the data with its true (n_z, n_r) layout."""
+    cu_type = 'xo::FluRz'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClFluenceRz(cltypes.Structure):
+            _fields_ = [('center', T.mc_point3f_t), ('inv_dr', T.mc_fp_t),
+                        ('inv_dz', T.mc_fp_t), ('n_r', T.mc_size_t),
+                        ('n_z', T.mc_size_t), ('offset', T.mc_size_t),
+                        ('k', T.mc_int_t)]
+        return ClFluenceRz
+
+    def __init__(self, raxis=None, zaxis: Axis = None,
+                 center: Tuple[float, float] = (0.0, 0.0), mode: str = 'deposition'):
+        super().__init__()
+        data, nphotons, k = None, 0, _K_DEFAULT
+        if isinstance(raxis, FluenceRz):
+            f = raxis
+            raxis, zaxis, center = Axis(f.raxis), Axis(f.zaxis), f.center
+            nphotons, mode, k = f.nphotons, f.mode, f.k
+            if f.raw is not None:
+                data = np.copy(f.raw)
+        raxis = Axis(0.0, 1.0, 1) if raxis is None else raxis
+        zaxis = Axis(0.0, 1.0, 1) if zaxis is None else zaxis
+        if raxis.logscale or zaxis.logscale:
+            raise ValueError('FluenceRz does not support logarithmic axes!')
+        self._r_axis, self._z_axis = raxis, zaxis
+        self._center = np.zeros((2,))
+        self._center[:] = center
+        self._init_common(mode, k, data, nphotons)
+
+    shape = property(lambda self: (self._r_axis.n, self._z_axis.n))
+    raxis = property(lambda self: self._r_axis)
+    zaxis = property(lambda self: self._z_axis)
+    r = property(lambda self: self._r_axis.centers)
+    z = property(lambda self: self._z_axis.centers)
+    dr = property(lambda self: abs(self._r_axis.step))
+    dz = property(lambda self: abs(self._z_axis.step))
+
+    def _set_center(self, c):
+        self._center[:] = c
+
+    center = property(lambda self: self._center, _set_center)
+
+    @property
+    def raw_zr(self):
+        return None if self._data is None else \
+            self._data.reshape(self._z_axis.n, self._r_axis.n)
+
+    @property
+    def data(self):
+        area = np.pi*(self._r_axis.edges[1:]**2 - self._r_axis.edges[:-1]**2)
+        k = 1.0/(self.nphotons*area*self.dz)
+        k.shape = (1, k.size)
+        return self._data*k
+
+    @property
+    def data_zr(self):
+        area = np.pi*(self._r_axis.edges[1:]**2 - self._r_axis.edges[:-1]**2)
+        return self.raw_zr/(max(self.nphotons, 1)*area[None, :]*self.dz)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        target.center.x, target.center.y = self._center
+        target.center.z = self._z_axis.start
+        target.inv_dr = 1.0/self._r_axis.step if self._r_axis.step != 0.0 else 0.0
+        target.inv_dz = 1.0/self._z_axis.step
+        target.n_r, target.n_z = self._r_axis.n, self._z_axis.n
+        target.k = self._k
+        return target
+
+    def todict(self):
+        return {'type': 'FluenceRz', 'mode': self._mode, 'raxis': self._r_axis.todict(),
+                'zaxis': self._z_axis.todict(), 'center': self._center.tolist()}
+
+    @classmethod
+    def fromdict(cls, data):
+        d = dict(data)
+        d.pop('type')
+        return cls(Axis.fromdict(d.pop('raxis')), Axis.fromdict(d.pop('zaxis')), **d)
+
+
+class Fluencet(_FluenceBase):
+    """Time-resolved x-y-z-t grid; raw shape (nz, ny, nx, nt) (mcfluence/fluencet.py).
+    Time = optical path length / c, so the kernel tracks the optical path length."""
+    cu_type = 'xo::FluXyzt'
+    _extra_options = [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClFluencet(cltypes.Structure):
+            _fields_ = [('inv_step', T.mc_point4f_t), ('top_left', T.mc_point4f_t),
+                        ('shape', T.mc_point4s_t), ('offset', T.mc_size_t),
+                        ('k', T.mc_int_t)]
+        return ClFluencet
+
+    def __init__(self, xaxis=None, yaxis: Axis = None, zaxis: Axis = None,
+                 taxis: Axis = None, mode: str = 'deposition'):
+        super().__init__()
+        data, nphotons, k = None, 0, _K_DEFAULT
+        if isinstance(xaxis, Fluencet):
+            f = xaxis
+            xaxis, yaxis, zaxis, taxis = (Axis(f.xaxis), Axis(f.yaxis),
+                                          Axis(f.zaxis), Axis(f.taxis))
+            nphotons, mode, k = f.nphotons, f.mode, f.k
+            if f.raw is not None:
+                data = np.copy(f.raw)
+        xaxis = Axis(-0.5, 0.5, 1) if xaxis is None else xaxis
+        yaxis = Axis(-0.5, 0.5, 1) if yaxis is None else yaxis
+        zaxis = Axis(0.0, 1.0, 1) if zaxis is None else zaxis
+        taxis = Axis(0.0, 1.0, 1) if taxis is None else taxis
+        self._x_axis, self._y_axis, self._z_axis, self._t_axis = xaxis, yaxis, zaxis, taxis
+        self._init_common(mode, k, data, nphotons)
+
+    shape = property(lambda self: (self._z_axis.n, self._y_axis.n,
+                                   self._x_axis.n, self._t_axis.n))
+    xaxis = property(lambda self: self._x_axis)
+    yaxis = property(lambda self: self._y_axis)
+    zaxis = property(lambda self: self._z_axis)
+    taxis = property(lambda self: self._t_axis)
+    x = property(lambda self: self._x_axis.centers)
+    y = property(lambda self: self._y_axis.centers)
+    z = property(lambda self: self._z_axis.centers)
+    t = property(lambda self: self._t_axis.centers)
+    dx = property(lambda self: abs(self._x_axis.step))
+    dy = property(lambda self: abs(self._y_axis.step))
+    dz = property(lambda self: abs(self._z_axis.step))
+    dt = property(lambda self: abs(self._t_axis.step))
+
+    @property
+    def data(self):
+        return self._data*(1.0/(max(self.nphotons, 1)*self.dx*self.dy*self.dz*self.dt))
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        for c, ax in zip('xyzw', (self._x_axis, self._y_axis, self._z_axis, self._t_axis)):
+            setattr(target.top_left, c, ax.start)
+            setattr(target.inv_step, c, 1.0/ax.step)
+            setattr(target.shape, c, ax.n)
+        target.k = self._k
+        return target
+
+    def todict(self):
+        return {'type': 'Fluencet', 'mode': self._mode, 'xaxis': self._x_axis.todict(),
+                'yaxis': self._y_axis.todict(), 'zaxis': self._z_axis.todict(),
+                'taxis': self._t_axis.todict()}

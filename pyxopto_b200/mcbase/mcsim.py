@@ -1,0 +1,377 @@
+"""Simulator base class: kernel assembly + ``run()`` (counterpart of the shared
+parts of ``xopto/mc{ml,vox,cyl}/mc.py``: ``_pack``, ``_build_src``, ``run``).
+
+Kernel assembly: where the reference renders one OpenCL-C translation unit from
+plugin text fragments (mcbase/mcsrc.py + jinja2, mc.py:531-626), this engine
+emits a ~30-line CUDA translation unit that (1) maps the resolved compile-time
+options onto ``XO_*`` defines, (2) binds the plugin slots to the hand-written
+CUDA structs of ``csrc/kernels`` with typedefs, (3) pins the struct layouts with
+``static_assert(sizeof(...))`` against the ctypes structs (the compile-time twin
+of the reference's ``sizeof_datatypes`` kernel, mc.py:674-728) and (4) includes
+the geometry kernel header.  NVRTC compiles it for sm_100a; cubins are cached
+in-tree by content hash.
+"""
+import ctypes
+import time
+
+import numpy as np
+
+from . import mcoptions, mctypes
+from .mcworker import CuWorker, compile_kernel
+
+DEFAULT_BLOCK = 256
+PRIVATE_BINS_MAX = 4096          # detector bins privatised per CTA (32 KB)
+LUT_SHARED_MAX_BYTES = 64*1024   # pf lookup tables staged in shared memory
+
+
+def _c_float(v: float) -> str:
+    v = float(np.float32(v))
+    if np.isinf(v):
+        return '__int_as_float(0x7f800000)' if v > 0 else '__int_as_float(0xff800000)'
+    return '{!r}f'.format(v)
+
+
+class McBase(CuWorker):
+    """Plugin bookkeeping, option resolution, TU emission and the run loop."""
+
+    kernel_header = None     # e.g. 'mcml_kernel.cuh'
+    geometry = None          # 'mcml' | 'mcvox' | 'mccyl'
+
+    def __init__(self, source, detectors=None, trace=None, fluence=None,
+                 surface=None, types=mctypes.McDataTypesSingle, options=None,
+                 rnginit=None, cl_devices=None, cl_build_options=None,
+                 cl_profiling: bool = False):
+        super().__init__(types=types, cl_devices=cl_devices,
+                         cl_build_options=cl_build_options,
+                         cl_profiling=cl_profiling, rnginit=rnginit)
+        if surface is not None:
+            raise NotImplementedError(
+                'Surface layouts are not part of the accelerated path yet '
+                '(SURVEY.md 8f-3).')
+        self._source = source
+        self._detectors = detectors
+        self._trace = trace
+        self._fluence = fluence
+        self._options = list(options or [])
+        self._rmax = float('inf')
+        self._packed = {}
+        self._run_report = {}
+        self._reduce_hook = None
+        self._last_src = None
+        # plugin types are frozen at construction (mc.py:344-389, 486-529)
+        self._obj_types = {
+            'source': type(source),
+            'detectors': None if detectors is None else detectors.types(),
+            'fluence': type(fluence), 'trace': type(trace)}
+
+    # -- user-facing properties -------------------------------------------------
+    def _set_rmax(self, r):
+        self._rmax = float(r)
+
+    rmax = property(lambda self: self._rmax, _set_rmax, None,
+                    'Packets farther than rmax from the source are terminated.')
+    source = property(lambda self: self._source)
+    detectors = property(lambda self: self._detectors)
+    trace = property(lambda self: self._trace)
+    fluence = property(lambda self: self._fluence)
+    surface = property(lambda self: None)
+    run_report = property(lambda self: self._run_report)
+    options = property(lambda self: self._options)
+
+    # -- options ----------------------------------------------------------------
+    def _plugin_option_lists(self):
+        lists = [self._types.cl_options(self), self._options]
+        for obj in (self._source, self._detectors, self._fluence, self._trace):
+            if obj is not None:
+                lists.append(obj.fetch_cl_options(self))
+        return lists
+
+    def resolved_options(self) -> dict:
+        return mcoptions.resolve_cl_options(*self._plugin_option_lists())
+
+    @property
+    def deterministic(self) -> bool:
+        return bool(self.resolved_options().get('XO_DETERMINISTIC', False))
+
+    # -- packing ----------------------------------------------------------------
+    def _check_types(self):
+        if type(self._source) is not self._obj_types['source']:
+            raise ValueError('The photon packet source type/kind must not '
+                             'change between simulation calls!')
+        if self._detectors is not None and \
+                self._detectors.types() != self._obj_types['detectors']:
+            raise ValueError('Detector types must not change between simulation calls!')
+
+    def _pack_medium(self):
+        raise NotImplementedError
+
+    def _pack(self, nphotons: int):
+        """Assign buffer offsets (pack order: medium, source, detectors, fluence,
+        trace - mc.py:466-529) and fill the packed structs."""
+        self._clear_allocations()
+        self._check_types()
+        self._pack_medium()
+        self._packed['source'], _, _ = self._source.cl_pack(
+            self, self._packed.get('source'))
+        if self._detectors is not None:
+            self._packed['detectors'] = self._detectors.cl_pack(
+                self, self._packed.get('detectors'))
+        if self._fluence is not None:
+            self._packed['fluence'] = self._fluence.cl_pack(
+                self, self._packed.get('fluence'))
+        if self._trace is not None:
+            self._packed['trace'] = self._trace.cl_pack(
+                self, self._packed.get('trace'), int(nphotons))
+        return self._packed
+
+    # -- translation unit -------------------------------------------------------
+    def _plugin_bindings(self):
+        """[(typedef name, CUDA struct, packed ctypes struct or None)]"""
+        raise NotImplementedError
+
+    def _detector_bindings(self):
+        from ..mcml import mcdetector
+        dets = self._detectors
+        out = []
+        for loc, Name in (('top', 'XoDetTop'), ('bottom', 'XoDetBottom'),
+                          ('specular', 'XoDetSpecular')):
+            det = getattr(dets, loc) if dets is not None else mcdetector.DetectorDefault()
+            out.append((Name, det.fetch_cu_type(self), det.fetch_cl_type(self)))
+        return out
+
+    def kernel_source(self, block: int = DEFAULT_BLOCK, min_blocks: int = 1) -> str:
+        """The CUDA translation unit for the current plugin set / options."""
+        opts = self.resolved_options()
+        if opts.get('MC_USE_ENHANCED_RNG') or opts.get('MC_USE_DOUBLE_PRECISION'):
+            raise NotImplementedError('Enhanced RNG / double precision kernels '
+                                      'are not part of the accelerated path.')
+        trace_flags = int(opts.get('MC_USE_TRACE', 0))
+        lines = [
+            '// generated by pyxopto_b200 ({})'.format(self.geometry),
+            '#define XO_DETERMINISTIC {}'.format(int(bool(opts.get('XO_DETERMINISTIC', False)))),
+            '#define XO_METHOD {}'.format(int(opts.get('MC_METHOD', 0))),
+            '#define XO_USE_LOTTERY {}'.format(int(bool(opts.get('MC_USE_LOTTERY', True)))),
+            '#define XO_WEIGHT_MIN {}'.format(_c_float(opts.get('MC_PACKET_WEIGHT_MIN', 1e-4))),
+            '#define XO_LOTTERY_CHANCE {}'.format(
+                _c_float(opts.get('MC_PACKET_LOTTERY_CHANCE', 0.1))),
+            '#define XO_TRACE {}'.format(trace_flags),
+            '#define XO_USE_EVENTS {}'.format(int(bool(opts.get('MC_USE_EVENTS', False)))),
+            '#define XO_TRACK_OPL {}'.format(
+                int(bool(opts.get('MC_TRACK_OPTICAL_PATHLENGTH', False)))),
+            '#define XO_FLUENCE_RATE {}'.format(
+                int(bool(opts.get('MC_FLUENCE_MODE_RATE', False)))),
+            '#define XO_TRACE_ALIGNED {}'.format(int(self._trace_aligned())),
+            '#define XO_BLOCK {}'.format(int(block)),
+            '#define XO_MIN_BLOCKS {}'.format(int(min_blocks)),
+        ]
+        lines += self._extra_defines(opts)
+        lines += ['#include "xo_core.cuh"', '#include "xo_pf.cuh"',
+                  '#include "xo_detectors.cuh"', '#include "xo_fluence.cuh"']
+        lines += self._extra_includes()
+        checks = []
+        for name, cu_type, cl_type in self._plugin_bindings():
+            lines.append('typedef {} {};'.format(cu_type, name))
+            if cl_type is not None:
+                checks.append('static_assert(sizeof({}) == {}, "{} layout differs from '
+                              'the packed host struct");'.format(
+                                  name, ctypes.sizeof(cl_type), name))
+        lines.append('#include "{}"'.format(self.kernel_header))
+        lines += checks
+        lines += self._extra_checks()
+        return '\n'.join(lines) + '\n'
+
+    def _extra_defines(self, opts):
+        return []
+
+    def _extra_includes(self):
+        return []
+
+    def _extra_checks(self):
+        return []
+
+    def _trace_aligned(self) -> bool:
+        tr = self._packed.get('trace')
+        return self._trace is not None and tr is not None and \
+            tr.data_buffer_offset % 4 == 0
+
+    def export_src(self, filename: str = None, nphotons: int = 1) -> str:
+        self._pack(nphotons)
+        src = self.kernel_source()
+        if filename:
+            with open(filename, 'w') as f:
+                f.write(src)
+        return src
+
+    def compile(self, nphotons: int = 1, block: int = DEFAULT_BLOCK, min_blocks: int = 1,
+                arch: str = 'sm_100a'):
+        """NVRTC-compile the kernel for the current configuration without a
+        device (used by ``__graft_entry__.build`` and the CPU test-suite)."""
+        self._pack(nphotons)
+        src = self.kernel_source(block, min_blocks)
+        return compile_kernel(src, self.deterministic, arch=arch,
+                              extra_options=self._cl_build_options)
+
+    # -- launch ----------------------------------------------------------------
+    def _shared_layout(self, medium_bytes: int):
+        """(dynamic shared bytes, lut floats staged, private bins)."""
+        lut_len = 0
+        if len(self._float_lut) and self._float_lut.size*4 <= LUT_SHARED_MAX_BYTES:
+            lut_len = self._float_lut.size
+        priv_len = 0
+        if self._detectors is not None:
+            det_bins = 0
+            for det in self._detectors:
+                for a in self.cl_rw_accumulator_allocator.allocations(det):
+                    det_bins = max(det_bins, a.offset + a.size)
+            priv_len = min(det_bins, PRIVATE_BINS_MAX)
+        words = (medium_bytes//4 + 3) & ~3
+        if lut_len:
+            words += (lut_len + 3) & ~3
+        words += 2*priv_len
+        return words*4 + 16, lut_len, priv_len
+
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk):
+        raise NotImplementedError
+
+    def _medium_bytes(self) -> int:
+        raise NotImplementedError
+
+    def _upload_medium(self):
+        raise NotImplementedError
+
+    def _packed_or_dummy(self, key, size=8):
+        p = self._packed.get(key)
+        if p is None:
+            return bytes(size)
+        return p
+
+    def run(self, nphotons: int, out=None, wgsize: int = None, maxthreads: int = None,
+            copyseeds: bool = False, exportsrc: str = None, verbose: bool = False,
+            download: bool = True):
+        """Simulate ``nphotons`` packets.  Returns ``(trace, fluence, detectors)``
+        result objects like the reference (mc.py:730-1018); with ``out`` the new
+        data are accumulated into the given previous results."""
+        nphotons = int(nphotons)
+        if nphotons > self._types.mc_cnt_max or nphotons > 0xFFFFFFFF:
+            raise ValueError('Maximum number of photon packets that can be '
+                             'simulated in a single run is limited to {:,d}!'.format(
+                                 min(self._types.mc_cnt_max, 0xFFFFFFFF)))
+        t0 = time.perf_counter()
+        self._ensure_device()
+        self._pack(nphotons)
+        block = int(wgsize) if wgsize else DEFAULT_BLOCK
+        deterministic = self.deterministic
+        src = self.kernel_source(block=block, min_blocks=1)
+        self._last_src = src
+        if exportsrc:
+            with open(exportsrc, 'w') as f:
+                f.write(src)
+        mod = self._module(src, deterministic)
+        kernel = mod.kernel('McKernel')
+        t_build = time.perf_counter()
+
+        # uploads (mc.py:840-884)
+        self._upload_seeds(copy=False)
+        counters = np.zeros(2, dtype=np.uint32)
+        cbuf = self.cl_r_buffer('counters', counters)
+        self._upload_medium()
+        if len(self._float_lut):
+            lut_host = self._float_lut.pack_into(None).astype(np.float32)
+        else:
+            lut_host = np.zeros(4, np.float32)
+        lbuf = self.cl_r_buffer('fp_lut', lut_host)
+        abuf = self._rw_flat_buffer('accumulator')
+        fbuf = self._rw_flat_buffer('float')
+        ibuf = self._rw_flat_buffer('int')
+        shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
+        grid, block = self.launch_geometry(kernel, block, shared, maxthreads)
+        nthreads = grid*block
+        if deterministic:
+            chunk = 0
+        else:
+            chunk = int(min(max(nphotons//(nthreads*8), 1), 64))
+        bufs = dict(counters=cbuf, lut=lbuf, accu=abuf, floats=fbuf, ints=ibuf,
+                    rng_x=self._cl_buffers['rng_seeds_x'],
+                    rng_a=self._cl_buffers['rng_seeds_a'])
+        args = self._kernel_args(nphotons, bufs, lut_len, priv_len, chunk)
+        t_up = time.perf_counter()
+
+        ev0, ev1 = self._events
+        ev0.record(self._stream)
+        kernel.launch(self._stream, grid, block, args, dynamic_shared=shared)
+        ev1.record(self._stream)
+        if self._reduce_hook is not None:
+            self._reduce_hook(self, abuf, self.cl_rw_accumulator_allocator.size)
+        self._stream.synchronize()
+        t_exec = time.perf_counter()
+        kernel_ms = ev0.elapsed_ms(ev1)
+
+        cbuf.download(self._stream, counters)
+        if copyseeds:
+            self._cl_buffers['rng_seeds_x'].download(self._stream, self._rng_seeds_x)
+
+        results = (None, None, None)
+        if download:
+            results = self._collect_results(nphotons, out)
+        t_down = time.perf_counter()
+        self._run_report = {
+            'upload': t_up - t_build, 'build': t_build - t0,
+            'execution': t_exec - t_up, 'download': t_down - t_exec,
+            'kernel_ms': kernel_ms, 'threads': int(counters[1]),
+            'launched_threads': nthreads, 'grid': grid, 'block': block,
+            'shared_bytes': shared, 'private_bins': priv_len, 'lut_shared': lut_len,
+            'chunk': chunk, 'items': nphotons, 'cache_hit': mod.cache_hit,
+            'kernel_attributes': kernel.attributes(),
+        }
+        if verbose:
+            print('pyxopto_b200 run: build {:.3f} s, upload {:.3f} s, kernel {:.3f} ms, '
+                  'download {:.3f} s, {} threads'.format(
+                      t_build - t0, t_up - t_build, kernel_ms, t_down - t_exec, nthreads))
+        return results
+
+    def _collect_results(self, nphotons, out):
+        out_trace = out_fluence = out_detectors = None
+        if out is not None:
+            out_trace, out_fluence, out_detectors = out
+        trace_res = fluence_res = detectors_res = None
+        if self._trace is not None:
+            trace_res = out_trace if out_trace is not None else type(self._trace)(self._trace)
+            data = self._download_allocations(self._trace, nphotons)
+            trace_res.update_data(self, data, nphotons=nphotons)
+        if self._fluence is not None:
+            fluence_res = out_fluence if out_fluence is not None \
+                else type(self._fluence)(self._fluence)
+            data = self._download_allocations(self._fluence, nphotons)
+            fluence_res.update_data(self, data, nphotons=nphotons)
+        if self._detectors is not None:
+            detectors_res = out_detectors if out_detectors is not None \
+                else type(self._detectors)(self._detectors)
+            for det, res in zip(self._detectors, detectors_res):
+                data = self._download_allocations(det, nphotons)
+                if data:
+                    detectors_res.update_data(self, res, data, nphotons=nphotons)
+        return trace_res, fluence_res, detectors_res
+
+    # -- raw access (tests / multi-GPU reduction) ---------------------------------
+    def download_raw(self):
+        """Flat (accumulators, ints, floats) buffers of the last run."""
+        out = []
+        for kind in ('accumulator', 'int', 'float'):
+            alloc = self._allocators[kind]
+            host = np.zeros(max(alloc.size, 1), dtype=alloc.dtype)
+            self._cl_buffers['rw_' + kind].download(self._stream, host)
+            out.append(host)
+        return tuple(out)
+
+    def download_seeds(self) -> np.ndarray:
+        x = np.empty_like(self._rng_seeds_x)
+        self._cl_buffers['rng_seeds_x'].download(self._stream, x)
+        return x
+
+    def rng_test(self, n: int, x=None, a=None) -> np.ndarray:
+        """Device draw sequence of one (x, a) pair (``RngKernel`` hook,
+        mc.py:1320-1362): known-answer test for seed compatibility."""
+        from .rngkernel import rng_test
+        x = self._rng_seeds_x[0] if x is None else x
+        a = self._rng_seeds_a[0] if a is None else a
+        return rng_test(self, int(n), int(x), int(a))

@@ -1,0 +1,256 @@
+"""Device runtime shared by the simulators (counterpart of
+``xopto/mcbase/mcworker.py``: ClWorker + buffer/LUT/RNG mixins).
+
+Holds the CUDA context/stream (through ``libxopto_b200.so``), the three flat
+read-write buffers with their allocators, the read-only float LUT pool, the
+per-thread MWC seeds, and the NVRTC kernel cache.  Everything on the device goes
+through :mod:`pyxopto_b200.cu.abi`; there is no other execution path.
+"""
+import hashlib
+import os
+import time
+
+import numpy as np
+
+from .. import KERNEL_PATH, KERNEL_CACHE_PATH, VERBOSE
+from ..cl import clinfo, clrng
+from ..cu import abi
+from . import mctypes
+from .mcutil.buffer import BufferAllocator
+from .mcutil.lut import LutManager
+
+# the safe-prime table holds 500 000 multipliers; one seeds the seed generator
+MAX_SEEDS = 499999
+TARGET_ARCH = 'sm_100a'             # B200; the only architecture this engine targets
+
+_header_cache = None
+
+
+def kernel_headers() -> dict:
+    """All ``csrc/kernels/*.cuh`` files as in-memory NVRTC headers."""
+    global _header_cache
+    if _header_cache is None:
+        hdrs = {}
+        for name in sorted(os.listdir(KERNEL_PATH)):
+            if name.endswith('.cuh'):
+                with open(os.path.join(KERNEL_PATH, name)) as f:
+                    hdrs[name] = f.read()
+        _header_cache = hdrs
+    return _header_cache
+
+
+def nvrtc_options(deterministic: bool, extra=()) -> list:
+    opts = ['--std=c++17', '-lineinfo', '-default-device']
+    if deterministic:
+        opts += ['--fmad=false', '--prec-div=true', '--prec-sqrt=true', '--ftz=false']
+    else:
+        opts += ['--use_fast_math', '--extra-device-vectorization']
+    return opts + list(extra)
+
+
+def compile_kernel(src: str, deterministic: bool, arch: str = TARGET_ARCH,
+                   extra_options=(), use_cache: bool = True):
+    """TU text -> (cubin bytes, log, cache_hit).  Works without a GPU."""
+    headers = kernel_headers()
+    options = nvrtc_options(deterministic, extra_options)
+    h = hashlib.sha256()
+    h.update(src.encode())
+    h.update(arch.encode())
+    h.update('\0'.join(options).encode())
+    for name in sorted(headers):
+        h.update(name.encode())
+        h.update(headers[name].encode())
+    key = h.hexdigest()[:32]
+    path = os.path.join(KERNEL_CACHE_PATH, '{}_{}.cubin'.format(arch, key))
+    if use_cache and os.path.exists(path):
+        with open(path, 'rb') as f:
+            return f.read(), '', True
+    cubin, log = abi.compile_cubin(src, 'xo_kernel.cu', arch, options, headers)
+    if use_cache:
+        try:
+            os.makedirs(KERNEL_CACHE_PATH, exist_ok=True)
+            tmp = path + '.tmp{}'.format(os.getpid())
+            with open(tmp, 'wb') as f:
+                f.write(cubin)
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    return cubin, log, False
+
+
+class CuWorker:
+    """Base class of the ``Mc`` simulators."""
+
+    def __init__(self, types=mctypes.McDataTypesSingle, cl_devices=None,
+                 cl_build_options=None, cl_profiling: bool = False, rnginit=None):
+        self._types = types
+        self._cl_device_arg = cl_devices
+        self._cl_build_options = list(cl_build_options or [])
+        self._cl_profiling = bool(cl_profiling)
+        self._ctx = None
+        self._stream = None
+        self._cl_buffers = {}
+        self._np_buffers = {}
+        self._allocators = {
+            'accumulator': BufferAllocator(types.np_accu),
+            'float': BufferAllocator(types.np_float),
+            'int': BufferAllocator(types.np_int),
+        }
+        self._float_lut = LutManager(types.np_float)
+        self._rng = clrng.Random()
+        self._rng_seeds_x, self._rng_seeds_a = self._rng.seeds(MAX_SEEDS, xinit=rnginit)
+        self._seeds_on_device = False
+        self._modules = {}
+        self._events = None
+
+    # -- device ---------------------------------------------------------------
+    def _device_ordinal(self) -> int:
+        d = self._cl_device_arg
+        if d is None:
+            return int(os.environ.get('LOCAL_RANK', 0)) if os.environ.get(
+                'XOPTO_DEVICE_FROM_RANK') else 0
+        if isinstance(d, clinfo.Device):
+            return d.ordinal
+        if isinstance(d, (int, np.integer)):
+            return int(d)
+        if isinstance(d, str):
+            return clinfo.device(d).ordinal
+        if isinstance(d, (list, tuple)) and d:
+            first = d[0]
+            return first.ordinal if isinstance(first, clinfo.Device) else int(first)
+        raise TypeError('Unsupported cl_devices argument {!r}'.format(d))
+
+    def _ensure_device(self):
+        if self._ctx is None:
+            self._ctx = abi.Context(self._device_ordinal())
+            self._stream = abi.Stream(self._ctx)
+            self._events = (abi.Event(self._ctx), abi.Event(self._ctx))
+        return self._ctx
+
+    cl_context = property(lambda self: self._ensure_device())
+    cl_queue = property(lambda self: (self._ensure_device(), self._stream)[1])
+    cl_device = property(lambda self: self._ensure_device().info)
+    types = property(lambda self: self._types)
+    rng = property(lambda self: self._rng)
+    rng_seeds_x = property(lambda self: self._rng_seeds_x)
+    rng_seeds_a = property(lambda self: self._rng_seeds_a)
+    cl_buffers = property(lambda self: self._cl_buffers)
+    np_buffers = property(lambda self: self._np_buffers)
+
+    @property
+    def cl_max_threads(self) -> int:
+        return (MAX_SEEDS//512)*512          # 499 712, mcworker.py:1227
+
+    # -- allocators / LUTs ------------------------------------------------------
+    cl_rw_accumulator_allocator = property(lambda self: self._allocators['accumulator'])
+    cl_rw_float_allocator = property(lambda self: self._allocators['float'])
+    cl_rw_int_allocator = property(lambda self: self._allocators['int'])
+    float_r_lut_manager = property(lambda self: self._float_lut)
+
+    def cl_allocate_rw_accumulator_buffer(self, owner, shape, download=True):
+        return self._allocators['accumulator'].allocate(owner, shape, download)
+
+    def cl_allocate_rw_float_buffer(self, owner, shape, download=True):
+        return self._allocators['float'].allocate(owner, shape, download)
+
+    def cl_allocate_rw_int_buffer(self, owner, shape, download=True):
+        return self._allocators['int'].allocate(owner, shape, download)
+
+    def append_r_lut(self, data: np.ndarray, force: bool = False):
+        return self._float_lut.append(data, force)
+
+    def clear_r_luts(self):
+        self._float_lut.clear()
+
+    def _clear_allocations(self):
+        for a in self._allocators.values():
+            a.clear()
+        self.clear_r_luts()
+
+    # -- buffers ----------------------------------------------------------------
+    def _buffer(self, name: str, nbytes: int) -> abi.Buffer:
+        """Named device buffer of at least ``nbytes`` (re-allocated on growth)."""
+        self._ensure_device()
+        buf = self._cl_buffers.get(name)
+        if buf is None or buf.size < nbytes:
+            if buf is not None:
+                buf.release()
+            buf = abi.Buffer(self._ctx, max(int(nbytes), 16))
+            self._cl_buffers[name] = buf
+        return buf
+
+    def cl_r_buffer(self, name: str, host=None, size: int = None) -> abi.Buffer:
+        """Upload a packed struct / array into a named read-only buffer."""
+        if host is None:
+            return self._buffer(name, size or 16)
+        if isinstance(host, np.ndarray):
+            host = np.ascontiguousarray(host)
+            nbytes = host.nbytes
+        else:
+            nbytes = len(bytes(memoryview(host).cast('B')))
+        buf = self._buffer(name, nbytes)
+        buf.upload(self._stream, host, blocking=True)
+        return buf
+
+    def _rw_flat_buffer(self, kind: str, fill: bool = True) -> abi.Buffer:
+        alloc = self._allocators[kind]
+        nbytes = max(alloc.size, 1)*alloc.dtype.itemsize
+        buf = self._buffer('rw_' + kind, nbytes)
+        if fill:
+            buf.fill(self._stream, 0, np.uint32, count=(nbytes + 3)//4)
+        return buf
+
+    def _upload_seeds(self, copy: bool = False):
+        if not self._seeds_on_device or copy:
+            self.cl_r_buffer('rng_seeds_x', self._rng_seeds_x)
+            self.cl_r_buffer('rng_seeds_a', self._rng_seeds_a)
+            self._seeds_on_device = True
+
+    def _download_allocations(self, owner, nphotons: int):
+        """{dtype: [ndarray per allocation]} for one plugin (cf. mc.py:1020-1038)."""
+        out = {}
+        for kind, alloc in self._allocators.items():
+            buf = self._cl_buffers.get('rw_' + kind)
+            for a in alloc.allocations(owner):
+                if not a.download:
+                    continue
+                if hasattr(owner, 'np_buffer'):
+                    host = owner.np_buffer(self, a, nphotons=nphotons)
+                else:
+                    host = np.empty(a.shape, dtype=a.dtype)
+                buf.download(self._stream, host, offset=a.offset*alloc.dtype.itemsize)
+                out.setdefault(alloc.dtype, []).append(host)
+        return out
+
+    # -- kernels ----------------------------------------------------------------
+    def _module(self, src: str, deterministic: bool):
+        """Build (or fetch from cache) and load the module for a TU."""
+        self._ensure_device()
+        key = hashlib.sha1(src.encode()).hexdigest() + str(deterministic)
+        mod = self._modules.get(key)
+        if mod is None:
+            t0 = time.perf_counter()
+            cubin, log, hit = compile_kernel(
+                src, deterministic, arch=self._ctx.arch,
+                extra_options=self._cl_build_options)
+            mod = abi.Module(self._ctx, cubin=cubin)
+            mod.build_log = log
+            mod.build_time = time.perf_counter() - t0
+            mod.cache_hit = hit
+            if VERBOSE:
+                print('pyxopto_b200: kernel {} in {:.3f} s'.format(
+                    'loaded from cache' if hit else 'built', mod.build_time))
+            self._modules[key] = mod
+        return mod
+
+    def launch_geometry(self, kernel, block: int, dynamic_shared: int,
+                        maxthreads: int = None):
+        """(grid, block): one resident wave of CTAs over all SMs, capped by the
+        number of available MWC seeds (499 712) and ``maxthreads``."""
+        info = self._ctx.info
+        per_sm = max(kernel.occupancy(block, dynamic_shared), 1)
+        grid = info['multiprocessor_count']*per_sm
+        limit = self.cl_max_threads if maxthreads is None else \
+            min(int(maxthreads), self.cl_max_threads)
+        grid = max(1, min(grid, limit//block))
+        return grid, block

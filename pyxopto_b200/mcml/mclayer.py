@@ -1,0 +1,132 @@
+"""Layer stack of the planar simulator (mirror of ``xopto/mcml/mclayer/layer.py``)."""
+from ..cl import cltypes
+from ..mcbase.mcobject import McObject
+from ..mcbase.mcutil import boundary
+
+
+class Layer(McObject):
+    cu_type = 'xo::MlLayer'
+
+    @staticmethod
+    def layer_type(mc, pf_type):
+        T = mc.types
+        class ClLayer(cltypes.Structure):
+            _fields_ = [
+                ('thickness', T.mc_fp_t), ('top', T.mc_fp_t), ('bottom', T.mc_fp_t),
+                ('n', T.mc_fp_t), ('cos_critical_top', T.mc_fp_t),
+                ('cos_critical_bottom', T.mc_fp_t), ('mus', T.mc_fp_t),
+                ('mua', T.mc_fp_t), ('inv_mut', T.mc_fp_t),
+                ('mua_inv_mut', T.mc_fp_t), ('pf', pf_type)]
+        return ClLayer
+
+    def cl_type(self, mc):
+        return self.layer_type(mc, self.pf.fetch_cl_type(mc))
+
+    def __init__(self, d: float, n: float, mua: float, mus: float, pf):
+        super().__init__()
+        self.d, self.n, self.mua, self.mus = float(d), float(n), float(mua), float(mus)
+        self._pf = pf
+
+    def _set_pf(self, pf):
+        if type(self._pf) is not type(pf):
+            raise ValueError('The scattering phase function type '
+                             'of the layer must not change!')
+        self._pf = pf
+
+    pf = property(lambda self: self._pf, _set_pf, None, 'Phase function object.')
+
+    def cl_pack(self, mc, target=None):
+        """Packs the fields that do not depend on neighbouring layers
+        (layer.py:304-354)."""
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        mut = self.mua + self.mus
+        inv_mut = 1.0/mut if mut > 0.0 else float('inf')
+        mua_inv_mut = 1.0 if self.mus == 0.0 else self.mua*inv_mut
+        target.thickness, target.n = self.d, self.n
+        target.mua, target.mus = self.mua, self.mus
+        target.inv_mut, target.mua_inv_mut = inv_mut, mua_inv_mut
+        self.pf.cl_pack(mc, target.pf)
+        return target
+
+    def todict(self):
+        return {'d': self.d, 'n': self.n, 'mua': self.mua, 'mus': self.mus,
+                'pf': self.pf.todict(), 'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'Layer(d={}, n={}, mua={}, mus={}, pf={})'.format(
+            self.d, self.n, self.mua, self.mus, self.pf)
+
+
+class Layers(McObject):
+    """Stack of layers; the first and last describe the surrounding medium."""
+
+    def __init__(self, layers):
+        super().__init__()
+        if isinstance(layers, Layers):
+            layers = list(layers)
+        self._layers = list(layers)
+        if len(self._layers) < 3:
+            raise ValueError('A layer stack needs at least 3 layers '
+                             '(2 surrounding + 1 sample layer)!')
+        pf_type = type(self._layers[0].pf)
+        if any(type(l.pf) is not pf_type for l in self._layers):
+            raise ValueError('All the layers must use the same scattering '
+                             'phase function model!')
+
+    def cl_type(self, mc):
+        return self._layers[0].fetch_cl_type(mc)*len(self._layers)
+
+    def cl_pack(self, mc, target=None):
+        """Packs the stack; top/bottom are accumulated in fp32 exactly like the
+        reference (layer.py:981-1000): bottom_i = fp32(fp32(bottom_{i-1}) + d_i)."""
+        n_layers = len(self._layers)
+        if target is None or len(target) != n_layers:
+            target = self.fetch_cl_type(mc)()
+        inf = float('inf')
+        for i, layer in enumerate(self._layers):
+            layer.cl_pack(mc, target[i])
+            cc_top = boundary.cos_critical(layer.n, self._layers[i - 1].n) if i > 0 else 0.0
+            cc_bottom = boundary.cos_critical(layer.n, self._layers[i + 1].n) \
+                if i + 1 < n_layers else 0.0
+            if i == 0:
+                target[i].top, target[i].bottom, target[i].thickness = -inf, 0.0, inf
+            elif i == n_layers - 1:
+                target[i].top, target[i].bottom = target[i - 1].bottom, inf
+                target[i].thickness = inf
+            else:
+                target[i].top = target[i - 1].bottom
+                target[i].bottom = target[i - 1].bottom + layer.d
+            target[i].cos_critical_top = cc_top
+            target[i].cos_critical_bottom = cc_bottom
+            layer.pf.cl_pack(mc, target[i].pf)
+        return target
+
+    def thickness(self) -> float:
+        return sum(l.d for l in self._layers[1:-1])
+
+    def layer_index(self, z: float) -> int:
+        """Index of the layer that contains depth z."""
+        if z < 0.0:
+            return 0
+        bottom = 0.0
+        for i, layer in enumerate(self._layers[1:-1], start=1):
+            bottom += layer.d
+            if z < bottom:
+                return i
+        return len(self._layers) - 1
+
+    def layer(self, index):
+        return self._layers[index]
+
+    def __getitem__(self, i):
+        return self._layers[i]
+
+    def __len__(self):
+        return len(self._layers)
+
+    def __iter__(self):
+        return iter(self._layers)
+
+    def todict(self):
+        return {'layers': [l.todict() for l in self._layers], 'type': 'Layers'}

@@ -1,0 +1,261 @@
+"""Photon packet sources of the planar simulator (mirror of ``xopto/mcml/mcsource``:
+Line, GaussianBeam, UniformFiber, IsotropicPoint)."""
+from typing import Tuple
+
+import numpy as np
+
+from ..cl import cltypes
+from ..mcbase.mcobject import McObject
+from ..mcbase.mcutil import boundary, geometry
+from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
+
+
+class Source(McObject):
+    def update(self, other):
+        for key in self._update_keys:
+            if isinstance(other, dict):
+                if key in other:
+                    setattr(self, key, other[key])
+            else:
+                setattr(self, key, getattr(other, key))
+
+    _update_keys = ()
+
+
+def _unit(v, name='direction'):
+    v = np.array(v, dtype=np.float64)
+    norm = np.linalg.norm(v)
+    if norm == 0.0:
+        raise ValueError('The norm/length of the propagation {} '
+                         'vector must not be 0!'.format(name))
+    return v/norm
+
+
+class Line(Source):
+    """Infinitely thin beam (mcsource/line.py)."""
+    cu_type = 'xo::SrcLine'
+    _update_keys = ('position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClLine(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('direction_medium', T.mc_point3f_t),
+                        ('direction_sample', T.mc_point3f_t),
+                        ('direction_reflected', T.mc_point3f_t),
+                        ('reflectance', T.mc_fp_t)]
+        return ClLine
+
+    def __init__(self, position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self._direction = np.zeros((3,))
+        self.position = position
+        self.direction = direction
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        self._direction[:] = _unit(d)
+
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        d = self._direction
+        t = -self._position[2]/d[2]
+        position = self._position + d*t
+        position[2] = 0.0
+        n1, n2 = mc.layer(0).n, mc.layer(1).n
+        reflectance = boundary.reflectance(n1, n2, d[2])
+        if reflectance >= 1.0:
+            raise ValueError('The line source is fully reflected from the top '
+                             'surface of the sample!')
+        sin1 = (1.0 - d[2]**2)**0.5
+        sin2 = max(min(n1*sin1/n2, 1.0), -1.0)
+        refracted = (d[0]*n1/n2, d[1]*n1/n2, np.sign(d[2])*(1 - sin2**2)**0.5)
+        target.position.fromarray(position)
+        target.direction_medium.fromarray(d)
+        target.direction_sample.fromarray(refracted)
+        target.direction_reflected.fromarray((d[0], d[1], -d[2]))
+        target.reflectance = reflectance
+        return target, None, None
+
+    def todict(self):
+        return {'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class GaussianBeam(Source):
+    """Collimated Gaussian beam (mcsource/gaussianbeam.py)."""
+    cu_type = 'xo::SrcGaussianBeam'
+    _update_keys = ('sigma', 'clip', 'position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClGaussianBeam(cltypes.Structure):
+            _pack_ = 1
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('sigma', T.mc_point2f_t),
+                        ('clip', T.mc_fp_t), ('reflectance', T.mc_fp_t)]
+        return ClGaussianBeam
+
+    def __init__(self, sigma, clip: float = 5.0, position=(0.0, 0.0, 0.0),
+                 direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self._sigma = np.zeros((2,))
+        self.sigma, self.clip = sigma, clip
+        self.position, self.direction = position, direction
+
+    def _set_sigma(self, s):
+        self._sigma[:] = s
+        if np.any(self._sigma < 0.0):
+            raise ValueError('Beam diameter/sigma must not be negative!')
+
+    def _set_clip(self, c):
+        self._clip = float(c)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        d = _unit(d)
+        if d[-1] <= 0.0:
+            raise ValueError('Z component of the propagation direction '
+                             'must be positive!')
+        self._direction[:] = d
+
+    sigma = property(lambda self: self._sigma, _set_sigma)
+    clip = property(lambda self: self._clip, _set_clip)
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    @staticmethod
+    def fwhm2sigma(fwhm: float) -> float:
+        return fwhm/(8*np.log(2))**0.5
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        k = (0.0 - self._position[2])/self._direction[2]
+        position = self._position + k*self._direction
+        position[2] = 0.0
+        n1, n2 = mc.layers[0].n, mc.layers[1].n
+        direction = boundary.refract(self._direction, (0.0, 0.0, 1.0), n1, n2)
+        reflectance = boundary.reflectance(n1, n2, abs(self._direction[-1]))
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.position.fromarray(position)
+        target.direction.fromarray(direction)
+        target.sigma.fromarray(self._sigma)
+        target.clip = self._clip
+        target.reflectance = reflectance
+        return target, None, None
+
+    def todict(self):
+        return {'sigma': self._sigma.tolist(), 'clip': self._clip,
+                'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class UniformFiber(Source):
+    """Optical fiber with uniform emission within the NA (mcsource/fiber.py)."""
+    cu_type = 'xo::SrcUniformFiber'
+    _update_keys = ('fiber', 'position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformFiber(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('cos_min', T.mc_fp_t), ('n', T.mc_fp_t)]
+        return ClUniformFiber
+
+    def __init__(self, fiber: MultimodeFiber, position=(0.0, 0.0, 0.0),
+                 direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._fiber = fiber
+        self._position = np.zeros((3,))
+        self._direction = np.zeros((3,))
+        self.position, self.direction = position, direction
+
+    def _set_fiber(self, f):
+        self._fiber = f
+
+    def _set_position(self, p):
+        self._position[:] = p
+        self._position[2] = 0.0
+
+    def _set_direction(self, d):
+        norm = np.linalg.norm(d)
+        if norm == 0.0:
+            raise ValueError('The direction vector is singular!')
+        d = np.asarray(d, dtype=np.float64)*(1.0/norm)
+        if d[-1] <= 0.0:
+            raise ValueError('Z component of the propagation direction '
+                             'must be positive!')
+        self._direction[:] = d
+
+    fiber = property(lambda self: self._fiber, _set_fiber)
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.n = self._fiber.ncore
+        target.cos_min = (1.0 - self._fiber.na**2)**0.5
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+    def todict(self):
+        return {'fiber': self._fiber.todict(), 'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class IsotropicPoint(Source):
+    """Isotropic point source above or inside the sample (mcsource/point.py)."""
+    cu_type = 'xo::SrcIsotropicPoint'
+    _update_keys = ('position',)
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClIsotropicPoint(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('layer_index', T.mc_size_t)]
+        return ClIsotropicPoint
+
+    def __init__(self, position=(0.0, 0.0, 0.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self.position = position
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        if self._position[2] >= mc.layers.thickness():
+            raise ValueError('The source must be located above or within '
+                             'the sample but not under the sample!')
+        target.position.fromarray(self._position)
+        target.layer_index = 1 if self._position[2] <= 0.0 else \
+            mc.layer_index(self._position[2])
+        return target, None, None
+
+    def todict(self):
+        return {'position': self._position.tolist(), 'type': type(self).__name__}

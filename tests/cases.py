@@ -1,0 +1,125 @@
+"""Named simulator configurations shared by the golden-vector generator (which
+builds them with the *reference* package) and the tests (which build them with
+``pyxopto_b200``).  The two packages expose the same plugin API, so every case is
+a function of the simulator module ``mc`` (``xopto.mcml.mc`` or
+``pyxopto_b200.mcml.mc``) - the tests therefore read like reference scripts.
+"""
+import numpy as np
+
+RNGINIT = 123456789
+
+
+def _layers(mc, pf, stack='two'):
+    L = mc.mclayer.Layer
+    if stack == 'slab':      # BASELINE config 1: 10 mm slab, n=1.33, mua 1/cm, mus 100/cm
+        return mc.mclayer.Layers([
+            L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+            L(d=1e-2, n=1.33, mua=1e2, mus=100e2, pf=pf),
+            L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf)])
+    return mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=1e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=2e-3, n=1.4, mua=0.5e2, mus=50e2, pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf)])
+
+
+def _fiber(mc):
+    try:
+        from xopto.mcml.mcutil import fiber as fiberutil   # reference
+        if mc.__name__.startswith('xopto'):
+            return fiberutil.MultimodeFiber(200e-6, 220e-6, 1.462, 0.22)
+    except ImportError:
+        pass
+    return mc.mcsource.MultimodeFiber(200e-6, 220e-6, 1.462, 0.22)
+
+
+def _hg_lut():
+    """(params, lut) of a 2000-point Hg(0.8) lookup table; generated once with
+    the reference's xopto.pf.Hg(0.8).mclut(2000) and stored as a fixture."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lut_hg08_2000.npz'))
+    return f['params'], f['lut']
+
+
+def mcml_c1_slab(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(Axis(0.0, 10e-3, 1000)),
+        bottom=mc.mcdetector.Radial(Axis(0.0, 10e-3, 1000)),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8), 'slab'), mc.mcsource.Line(), det,
+                 rnginit=RNGINIT, **kw), dict(rmax=float('inf'))
+
+
+def mcml_hg_line_radial(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(Axis(0, 10e-3, 1000)),
+        bottom=mc.mcdetector.Radial(Axis(0, 10e-3, 100), cosmin=0.5),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det,
+                 rnginit=RNGINIT, **kw), dict(rmax=20e-3)
+
+
+def mcml_mhg_gauss_cart_flurz(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Cartesian(Axis(-2e-3, 2e-3, 40)),
+        specular=mc.mcdetector.Radial(Axis(0, 1e-3, 10)))
+    flu = mc.mcfluence.FluenceRz(Axis(0, 2e-3, 40), Axis(0, 3e-3, 60))
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.8, 0.9)), mc.mcsource.GaussianBeam(100e-6), det,
+                 fluence=flu, rnginit=987654321, **kw), dict(rmax=20e-3)
+
+
+def mcml_gk_fiber_six_flu(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.SixAroundOne(fib), bottom=mc.mcdetector.Total(),
+        specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.Fluence(Axis(-1e-3, 1e-3, 20), Axis(-1e-3, 1e-3, 20),
+                               Axis(0, 3e-3, 30), mode='deposition')
+    return mc.Mc(_layers(mc, mc.mcpf.Gk(0.8, 0.5)), mc.mcsource.UniformFiber(fib), det,
+                 fluence=flu, rnginit=5555, **kw), dict(rmax=20e-3)
+
+
+def mcml_lut_iso_radialpl_trace(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    params, lut = _hg_lut()
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.RadialPl(Axis(0, 5e-3, 50), Axis(0, 0.05, 100)),
+        bottom=mc.mcdetector.TotalPl(Axis(0, 0.05, 100)))
+    tr = mc.mctrace.Trace(maxlen=50, options=mc.mctrace.Trace.TRACE_ALL)
+    return mc.Mc(_layers(mc, mc.mcpf.Lut(params, lut)),
+                 mc.mcsource.IsotropicPoint((0, 0, 0.5e-3)), det, trace=tr,
+                 rnginit=777, **kw), dict(rmax=20e-3)
+
+
+def mcml_hg_line_total_fluencet(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(cosmin=0.9),
+                                  bottom=mc.mcdetector.Total())
+    flu = mc.mcfluence.Fluencet(Axis(-1e-3, 1e-3, 10), Axis(-1e-3, 1e-3, 10),
+                                Axis(0, 3e-3, 15), Axis(0, 50e-12, 20))
+    tr = mc.mctrace.Trace(maxlen=2, options=mc.mctrace.Trace.TRACE_START |
+                          mc.mctrace.Trace.TRACE_END, plon=True)
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.0)), mc.mcsource.Line((0, 0, 0), (0.3, 0, 1)), det,
+                 fluence=flu, trace=tr, rnginit=4242, **kw), dict(rmax=5e-3)
+
+
+MCML_CASES = {
+    'mcml_c1_slab': mcml_c1_slab,
+    'mcml_hg_line_radial': mcml_hg_line_radial,
+    'mcml_mhg_gauss_cart_flurz': mcml_mhg_gauss_cart_flurz,
+    'mcml_gk_fiber_six_flu': mcml_gk_fiber_six_flu,
+    'mcml_lut_iso_radialpl_trace': mcml_lut_iso_radialpl_trace,
+    'mcml_hg_line_total_fluencet': mcml_hg_line_total_fluencet,
+}
+
+ALL_CASES = dict(MCML_CASES)
+GEOMETRY = {name: name.split('_')[0] for name in ALL_CASES}
+
+# (packets, work-items) of the static block schedule used for the golden vectors
+GOLDEN_RUN = {name: (3000, 16) for name in ALL_CASES}
+GOLDEN_RUN['mcml_c1_slab'] = (4000, 64)
+GOLDEN_RUN['mcml_lut_iso_radialpl_trace'] = (800, 16)

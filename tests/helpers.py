@@ -1,0 +1,33 @@
+"""Shared helpers of the test-suite."""
+import importlib
+import os
+
+import numpy as np
+
+import cases
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+
+
+def build_sim(name: str, **kw):
+    """Case ``name`` built with the pyxopto_b200 host mirror."""
+    geom = cases.GEOMETRY[name]
+    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
+    sim, attrs = cases.ALL_CASES[name](mc, **kw)
+    for k, v in attrs.items():
+        setattr(sim, k, v)
+    return sim, geom, mc
+
+
+def packed_bytes(sim) -> dict:
+    out = {}
+    for key, val in sim._packed.items():
+        if val is None:
+            continue
+        out[key] = val.tobytes() if isinstance(val, np.ndarray) else \
+            bytes(memoryview(val).cast('B'))
+    return out

@@ -1,0 +1,124 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through
+libxopto_b200.so, against the CPU oracle on the same seeded inputs.
+
+Deterministic mode (static block schedule, IEEE arithmetic, portable elementary
+functions) must be BIT-EXACT: 64-bit fixed-point accumulators, trace buffers
+(float bit patterns), per-packet event counts and the advanced MWC states.
+Throughput mode (dynamic schedule, MUFU math) must agree statistically.
+"""
+import numpy as np
+import pytest
+
+import cases
+import xo_oracle
+from helpers import build_sim
+
+pytestmark = pytest.mark.gpu
+
+
+def _det_sim(name):
+    from pyxopto_b200.mcbase import mcoptions
+    return build_sim(name, options=[mcoptions.McDeterministic.on])
+
+
+def test_library_sees_a_b200():
+    from pyxopto_b200.cu import abi
+    assert abi.device_count() >= 1
+    info = abi.device_info(0)
+    assert info['cc_major'] >= 9, info
+
+
+def test_rng_stream_matches_reference_mapping():
+    sim, _, _ = build_sim('mcml_c1_slab')
+    for t in (0, 1, 77):
+        x, a = int(sim.rng_seeds_x[t]), int(sim.rng_seeds_a[t])
+        dev = sim.rng_test(64, x, a)
+        assert np.array_equal(dev, xo_oracle.rng_test(x, a, 64))
+
+
+@pytest.mark.parametrize('fn', ['log', 'sincos', 'cbrt', 'pow', 'exp', 'atan2', 'sqrt', 'div'])
+def test_deterministic_math_bit_exact(fn):
+    from pyxopto_b200.mcbase import rngkernel
+    sim, _, _ = build_sim('mcml_c1_slab')
+    sim._ensure_device()
+    rs = np.random.RandomState(11)
+    n = 200000
+    u = rs.rand(n).astype(np.float32)
+    v = rs.rand(n).astype(np.float32)
+    if fn == 'log':
+        a, b = np.concatenate([u, [0.0, 1.0, 2.0**-32, 3.4e38]]).astype(np.float32), None
+    elif fn == 'sincos':
+        a, b = (u*np.float32(6.2831855)).astype(np.float32), None
+    elif fn == 'cbrt':
+        a, b = (2*u - 1).astype(np.float32), None
+    elif fn == 'pow':
+        a, b = (u + np.float32(0.01)).astype(np.float32), (-4*v).astype(np.float32)
+    elif fn == 'exp':
+        a, b = (-20*u).astype(np.float32), None
+    elif fn == 'atan2':
+        a, b = (2*u - 1).astype(np.float32), (2*v - 1).astype(np.float32)
+    else:
+        a, b = (u + np.float32(1e-3)).astype(np.float32), (v + np.float32(1e-3)).astype(np.float32)
+    d0, d1 = rngkernel.math_probe(sim, fn, a, b, deterministic=True)
+    o0, o1 = xo_oracle.math_probe(fn, xo_oracle.MATH_PORTABLE, a, b)
+    assert np.array_equal(d0.view(np.uint32), o0.view(np.uint32))
+    if fn == 'sincos':
+        assert np.array_equal(d1.view(np.uint32), o1.view(np.uint32))
+
+
+@pytest.mark.parametrize('name', sorted(cases.ALL_CASES))
+def test_deterministic_mode_bit_exact(name):
+    sim, geom, _ = _det_sim(name)
+    n, _ = cases.GOLDEN_RUN[name]
+    n *= 4
+    threads, block = 256, 64
+    sim.run(n, maxthreads=threads, wgsize=block, download=False)
+    assert sim.run_report['launched_threads'] == threads
+    accu, ints, floats = sim.download_raw()
+    x_after = sim.download_seeds()[:threads]
+    desc = xo_oracle.describe(sim, geom)
+    ref = xo_oracle.run(desc, n, threads, sim.rng_seeds_x[:threads],
+                        sim.rng_seeds_a[:threads], math=xo_oracle.MATH_PORTABLE)
+    assert np.array_equal(accu, ref['accu'])
+    assert np.array_equal(ints, ref['ints'])
+    assert np.array_equal(floats.view(np.uint32), ref['floats'].view(np.uint32))
+    assert np.array_equal(x_after, ref['rng_x'][:threads])
+    assert sim.run_report['threads'] == ref['num_kernels']
+
+
+@pytest.mark.parametrize('name', ['mcml_c1_slab', 'mcml_mhg_gauss_cart_flurz',
+                                  'mcml_gk_fiber_six_flu'])
+def test_throughput_mode_statistics(name):
+    """Fast mode vs oracle (libm, different schedule): totals within 4 sigma."""
+    sim, geom, _ = build_sim(name)
+    n = 200000
+    sim.run(n, download=False)
+    accu, _, _ = sim.download_raw()
+    desc = xo_oracle.describe(sim, geom)
+    ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
+                        math=xo_oracle.MATH_LIBM)
+    K = 0x7FFFFF
+    owners = [d for d in sim.detectors] + ([sim.fluence] if sim.fluence else [])
+    for owner in owners:
+        for a in sim.cl_rw_accumulator_allocator.allocations(owner):
+            tot_gpu = accu[a.offset:a.offset + a.size].sum()/K/n
+            tot_ref = ref['accu'][a.offset:a.offset + a.size].sum()/K/n
+            # per-packet weight is in [0,1]: sigma of the mean <= sqrt(p/n)
+            sigma = np.sqrt(max(tot_ref, 1e-6)/n)*np.sqrt(2)
+            assert abs(tot_gpu - tot_ref) <= 4*sigma + 1e-5, (
+                type(owner).__name__, tot_gpu, tot_ref)
+
+
+def test_run_returns_reference_style_results():
+    sim, _, mc = build_sim('mcml_c1_slab')
+    trace, fluence, detectors = sim.run(100000)
+    assert trace is None and fluence is None
+    r = detectors.top.reflectance
+    assert r.shape == (1000,)
+    total = detectors.top.raw.sum()/detectors.top.nphotons
+    spec = detectors.specular.raw.sum()/detectors.specular.nphotons
+    assert abs(spec - ((1.33 - 1)/(1.33 + 1))**2) < 1e-6     # Fresnel, SURVEY 8c
+    assert 0.36 < total < 0.42
+    # continuation: accumulate into previous results
+    _, _, detectors2 = sim.run(100000, out=(None, None, detectors))
+    assert detectors2.top.nphotons == 200000
