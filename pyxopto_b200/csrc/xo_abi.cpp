@@ -11,6 +11,7 @@
 #include <nvrtc.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -69,7 +70,7 @@ std::string g_cu_error;
 void load_cuda() {
 	const char *names[] = {"libcuda.so.1", "libcuda.so"};
 	for (const char *n : names) {
-		g_cu.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		g_cu.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
 		if (g_cu.handle) break;
 	}
 	if (!g_cu.handle) {
@@ -128,7 +129,7 @@ void load_nvrtc() {
 	names.push_back("libnvrtc.so");
 	names.push_back("/usr/local/cuda/lib64/libnvrtc.so");
 	for (auto &n : names) {
-		g_rtc.handle = dlopen(n.c_str(), RTLD_NOW | RTLD_GLOBAL);
+		g_rtc.handle = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
 		if (g_rtc.handle) break;
 	}
 	if (!g_rtc.handle) {
@@ -153,9 +154,13 @@ int need_nvrtc() {
 enum class Kind : uint32_t { Ctx = 0x58430001, Stream, Module, Kernel, Buffer, Event, Blob };
 
 struct Object { Kind kind; };
-struct Ctx : Object { CUdevice dev; CUcontext ctx; int ordinal; int cc_major, cc_minor; };
+// A context stays alive until the last object created from it is destroyed, so
+// host-language finalisers may run in any order (Python GC does not order them).
+struct Ctx : Object { CUdevice dev; CUcontext ctx; int ordinal; int cc_major, cc_minor;
+	std::atomic<int> refs{1}; };
 struct Stream : Object { Ctx *ctx; CUstream s; };
-struct Module : Object { Ctx *ctx; CUmodule m; };
+struct Kernel;
+struct Module : Object { Ctx *ctx; CUmodule m; std::vector<Kernel *> kernels; };
 struct Kernel : Object { Module *mod; CUfunction f; };
 struct Buffer : Object { Ctx *ctx; CUdeviceptr p; size_t size; };
 struct Event : Object { Ctx *ctx; CUevent e; };
@@ -173,6 +178,15 @@ struct CtxScope {
 	explicit CtxScope(Ctx *c) { if (c && g_cu.cuCtxPushCurrent_v2(c->ctx) == CUDA_SUCCESS) pushed = true; }
 	~CtxScope() { if (pushed) { CUcontext old; g_cu.cuCtxPopCurrent_v2(&old); } }
 };
+
+void ctx_retain(Ctx *c) { c->refs.fetch_add(1); }
+void ctx_release(Ctx *c) {
+	if (c->refs.fetch_sub(1) == 1) {
+		g_cu.cuDevicePrimaryCtxRelease_v2(c->dev);
+		c->kind = Kind(0);
+		delete c;
+	}
+}
 
 int compile_to_cubin(const char *src, const char *name, const char *arch,
 		const char *const *options, int32_t n_options,
@@ -285,9 +299,7 @@ int xo_ctx_create(int32_t ordinal, xo_handle *ctx) {
 int xo_ctx_destroy(xo_handle h) {
 	Ctx *c = as<Ctx>(h, Kind::Ctx);
 	if (!c) return fail(XO_ERR_INVALID, "invalid context handle");
-	g_cu.cuDevicePrimaryCtxRelease_v2(c->dev);
-	c->kind = Kind(0);
-	delete c;
+	ctx_release(c);
 	return XO_OK;
 }
 
@@ -299,6 +311,7 @@ int xo_stream_create(xo_handle hctx, xo_handle *stream) {
 	CU(cuStreamCreate(&s, CU_STREAM_NON_BLOCKING));
 	Stream *st = new Stream();
 	st->kind = Kind::Stream; st->ctx = c; st->s = s;
+	ctx_retain(c);
 	*stream = to_handle(st);
 	return XO_OK;
 }
@@ -309,7 +322,10 @@ int xo_stream_destroy(xo_handle h) {
 	CtxScope scope(s->ctx);
 	g_cu.cuStreamDestroy_v2(s->s);
 	s->kind = Kind(0);
+	Ctx *owner = s->ctx;
 	delete s;
+	{ CUcontext old; if (scope.pushed) { g_cu.cuCtxPopCurrent_v2(&old); scope.pushed = false; } }
+	ctx_release(owner);
 	return XO_OK;
 }
 
@@ -374,6 +390,7 @@ int xo_module_load(xo_handle hctx, const void *image, size_t size, xo_handle *mo
 	CU(cuModuleLoadData(&m, image));
 	Module *mod = new Module();
 	mod->kind = Kind::Module; mod->ctx = c; mod->m = m;
+	ctx_retain(c);
 	*module = to_handle(mod);
 	return XO_OK;
 }
@@ -400,8 +417,12 @@ int xo_module_unload(xo_handle h) {
 	if (!m) return fail(XO_ERR_INVALID, "invalid module handle");
 	CtxScope scope(m->ctx);
 	g_cu.cuModuleUnload(m->m);
+	for (Kernel *k : m->kernels) { k->kind = Kind(0); delete k; }
 	m->kind = Kind(0);
+	Ctx *owner = m->ctx;
 	delete m;
+	{ CUcontext old; if (scope.pushed) { g_cu.cuCtxPopCurrent_v2(&old); scope.pushed = false; } }
+	ctx_release(owner);
 	return XO_OK;
 }
 
@@ -416,6 +437,7 @@ int xo_module_get_kernel(xo_handle h, const char *name, xo_handle *kernel) {
 	if (rc) return rc;
 	Kernel *k = new Kernel();
 	k->kind = Kind::Kernel; k->mod = m; k->f = f;
+	m->kernels.push_back(k);
 	*kernel = to_handle(k);
 	return XO_OK;
 }
@@ -453,6 +475,7 @@ int xo_buffer_alloc(xo_handle hctx, size_t size, xo_handle *buffer) {
 	CU(cuMemAlloc_v2(&p, size ? size : 1));
 	Buffer *b = new Buffer();
 	b->kind = Kind::Buffer; b->ctx = c; b->p = p; b->size = size;
+	ctx_retain(c);
 	*buffer = to_handle(b);
 	return XO_OK;
 }
@@ -463,7 +486,10 @@ int xo_buffer_free(xo_handle h) {
 	CtxScope scope(b->ctx);
 	g_cu.cuMemFree_v2(b->p);
 	b->kind = Kind(0);
+	Ctx *owner = b->ctx;
 	delete b;
+	{ CUcontext old; if (scope.pushed) { g_cu.cuCtxPopCurrent_v2(&old); scope.pushed = false; } }
+	ctx_release(owner);
 	return XO_OK;
 }
 
@@ -585,6 +611,7 @@ int xo_event_create(xo_handle hctx, xo_handle *event) {
 	CU(cuEventCreate(&e, CU_EVENT_DEFAULT));
 	Event *ev = new Event();
 	ev->kind = Kind::Event; ev->ctx = c; ev->e = e;
+	ctx_retain(c);
 	*event = to_handle(ev);
 	return XO_OK;
 }
@@ -595,7 +622,10 @@ int xo_event_destroy(xo_handle h) {
 	CtxScope scope(e->ctx);
 	g_cu.cuEventDestroy_v2(e->e);
 	e->kind = Kind(0);
+	Ctx *owner = e->ctx;
 	delete e;
+	{ CUcontext old; if (scope.pushed) { g_cu.cuCtxPopCurrent_v2(&old); scope.pushed = false; } }
+	ctx_release(owner);
 	return XO_OK;
 }
 
