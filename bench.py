@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Headline benchmark: photon packets/s of the mcml 5-layer skin configuration
+(BASELINE.json configs[1], concrete definition in benchcfg.c2_skin / SURVEY 8d).
+
+    python bench.py --gpus N --steps K --warmup W [--config c2_skin] [--packets P]
+    python bench.py --impl reference ...      (the reference's own kernel on host cores)
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE).  A step simulates
+P packets per GPU (default 1.25e8 = 1e9 / 8, weak scaling) with a rank-specific
+MWC seed set and, for N > 1, combines the 64-bit fixed-point accumulators with a
+single NCCL all-reduce.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import benchcfg  # noqa: E402
+
+SM_COUNT_B200 = 148
+FP32_LANES_PER_SM = 128
+SFU_LANES_PER_SM = 16
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'sm_max_mhz': 1965.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle-reason sampler running during the timed region."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(',')]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                    power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)),
+                'power_w': float(np.median(power)), 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def cpu_reference_run(config: str, sample_packets: int, threads: int):
+    """The reference's own kernel (oracle/_ref, built here from the rendered
+    reference text) or, when that .so is absent, the oracle port, on host cores
+    with the dynamic schedule.  Returns (packets/s, kind, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import importlib
+    import refbench
+    geom = benchcfg.GEOMETRY[config]
+    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
+    sim = benchcfg.CONFIGS[config](mc)
+    return refbench.run(sim, geom, config, sample_packets, threads)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--config', default='c2_skin', choices=sorted(benchcfg.CONFIGS))
+    ap.add_argument('--packets', type=float, default=None,
+                    help='packets per GPU per step (default 1.25e8 for c2_skin)')
+    ap.add_argument('--cpu-sample', type=float, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    ncores = os.cpu_count() or 1
+    config = args.config
+    metric = 'photon packets/s ({})'.format(
+        'mcml 5-layer skin' if config == 'c2_skin' else config)
+    workload = {
+        'c2_skin': 'mcml 5-layer skin (Skin3 @550nm), UniformFiber + SixAroundOne, '
+                   'MHg(beta=0.9), FluenceRz 250x500',
+        'c1_slab': 'mcml single slab mua=1/cm mus=100/cm g=0.8 n=1.33, Line + Radial',
+    }.get(config, config)
+
+    # ---------------- reference arm: the reference kernel on host cores --------
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        sample = int(args.cpu_sample or (3e5 if config == 'c2_skin' else 5e4))
+        times = []
+        kind = 'port'
+        for i in range(args.warmup + args.steps):
+            pps, kind, secs = cpu_reference_run(config, sample, ncores)
+            if i >= args.warmup:
+                times.append(secs)
+        total = sum(times)
+        value = sample*len(times)/total
+        line = {
+            'impl': 'reference', 'metric': metric, 'value': value, 'unit': 'packets/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3*total/len(times), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload, 'packets_per_step': sample,
+                       'schedule': 'dynamic atomic packet counter, one work-item per host thread'},
+            'cpu_baseline': {'value': value, 'unit': 'packets/s', 'cores': ncores,
+                             'kind': kind,
+                             'sample': '{} packets per step, {} timed steps'.format(sample, len(times))},
+            'e2e': {'value': value, 'unit': 'packets/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- native arm --------------------------------------------------
+    import importlib
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    from pyxopto_b200.cu import abi
+    geom = benchcfg.GEOMETRY[config]
+    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
+    packets = int(args.packets or (1.25e8 if config == 'c2_skin' else 1e7))
+    sim = benchcfg.CONFIGS[config](mc, rnginit=benchcfg.RNGINIT + rank, cl_devices=local_rank)
+
+    reduce_tensor = {}
+
+    def allreduce(sim_, abuf, count):
+        """single NCCL all-reduce of the uint64 accumulators (as int64: two's
+        complement addition is the same operation)"""
+        key = (abuf.device_ptr, count)
+        if key not in reduce_tensor:
+            class _Wrap:
+                pass
+            w = _Wrap()
+            w.__cuda_array_interface__ = {
+                'shape': (int(count),), 'typestr': '<i8', 'data': (abuf.device_ptr, False),
+                'version': 2}
+            reduce_tensor.clear()
+            reduce_tensor[key] = torch.as_tensor(w, device=torch.device('cuda', local_rank))
+        sim_._stream.synchronize()
+        dist.all_reduce(reduce_tensor[key])
+        torch.cuda.synchronize()
+
+    if world > 1:
+        sim._reduce_hook = allreduce
+
+    def barrier():
+        sim._stream.synchronize()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    # warm-up (also builds/loads the kernel)
+    for _ in range(max(args.warmup, 1)):
+        sim.run(packets, download=False)
+    barrier()
+
+    # ---- device-resident loop: `value` -------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernel_ms, iters = [], []
+    ev_start, ev_stop = abi.Event(sim.cl_context), abi.Event(sim.cl_context)
+    barrier()
+    t0 = time.perf_counter()
+    ev_start.record(sim._stream)
+    for _ in range(args.steps):
+        sim.run(packets, download=False)
+        kernel_ms.append(sim.run_report['kernel_ms'])
+        iters.append(sim.run_report['iterations'])
+    ev_stop.record(sim._stream)
+    barrier()
+    t1 = time.perf_counter()
+    loop_ms_events = ev_start.elapsed_ms(ev_stop)
+    clocks = sampler.stop() if rank == 0 else None
+    loop_s = t1 - t0
+
+    # ---- end-to-end loop through the public API: `e2e` ----------------------------
+    barrier()
+    t2 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        trace, fluence, detectors = sim.run(packets)
+        checksum = float(detectors.top.raw.sum()) + float(fluence.raw.sum())
+    barrier()
+    t3 = time.perf_counter()
+    e2e_s = t3 - t2
+    from pyxopto_b200.cl import cltypes
+    P = sim._packed
+    h2d = sum(len(cltypes.raw_bytes(P[k])) for k in P if P[k] is not None) + 16
+    d2h = int(sim.cl_rw_accumulator_allocator.size)*8 + 16
+
+    if world > 1:
+        t = torch.tensor([loop_s, e2e_s, loop_ms_events], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        loop_s, e2e_s, loop_ms_events = [float(v) for v in t.tolist()]
+
+    total_packets = packets*world*args.steps
+    value = total_packets/loop_s
+    e2e_value = total_packets/e2e_s
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        sm_mhz_max = float(peaks.get('sm_max_mhz', 1965.0))
+        info = sim.cl_context.info
+        sms = info['multiprocessor_count']
+        issue_peak = sms*FP32_LANES_PER_SM*sm_mhz_max*1e6     # thread-instr/s
+        sfu_peak = sms*SFU_LANES_PER_SM*sm_mhz_max*1e6
+        alu_ops, sfu_ops = benchcfg.OPS_PER_ITERATION[config]
+        k_ms = float(np.mean(kernel_ms))
+        iter_per_launch = float(np.mean(iters))
+        achieved = iter_per_launch*(alu_ops + sfu_ops)/(k_ms*1e-3)
+        achieved_sfu = iter_per_launch*sfu_ops/(k_ms*1e-3)
+        roofline = {
+            'bound': 'issue', 'achieved': achieved/1e9, 'peak': issue_peak/1e9,
+            'unit': 'G thread-instr/s', 'frac': achieved/issue_peak,
+            'traffic': None,
+            'kernel': 'McKernel', 'kernel_ms': k_ms,
+            'iterations_per_launch': iter_per_launch,
+            'iterations_per_packet': iter_per_launch/packets,
+            'algorithmic_ops_per_iteration': {'alu_fma': alu_ops, 'mufu': sfu_ops},
+            'sfu': {'achieved': achieved_sfu/1e9, 'peak': sfu_peak/1e9,
+                    'frac': achieved_sfu/sfu_peak},
+            'atomics_per_s': iter_per_launch/(k_ms*1e-3) if config == 'c2_skin' else None,
+            'peak_source': 'sm_max_mhz of MEASURED_PEAKS.json ({}) x {} SMs x {} FP32 lanes; '
+                           'hbm is not the bound of this path (working set < 2 MB)'.format(
+                               peaks_src, sms, FP32_LANES_PER_SM),
+            'kernel_share_of_step': k_ms*args.steps/(loop_ms_events if loop_ms_events > 0 else 1),
+        }
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            sample = int(args.cpu_sample or (2e6 if config == 'c2_skin' else 3e5))
+            try:
+                pps, kind, secs = cpu_reference_run(config, sample, ncores)
+                cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
+                                'kind': kind,
+                                'sample': '{} packets of the same workload in {:.1f} s'.format(
+                                    sample, secs)}
+            except Exception as exc:    # the baseline must never take the bench down
+                cpu_baseline = {'value': None, 'unit': 'packets/s', 'cores': ncores,
+                                'kind': 'port', 'sample': 'failed: {!r}'.format(exc)}
+        rr = sim.run_report
+        line = {
+            'metric': metric, 'value': value, 'unit': 'packets/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3*loop_s/args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {
+                'workload': workload, 'packets_per_gpu_per_step': packets,
+                'global_packets_per_step': packets*world,
+                'parallelism': 'packets sharded over {} GPU(s), disjoint MWC seed sets'
+                               '{}'.format(world, ', 1 NCCL all-reduce of the uint64 '
+                                           'accumulators per step' if world > 1 else ''),
+                'mode': 'throughput (MUFU math, dynamic chunked packet counter)',
+                'l2': 'inputs are < 2 MB of constants; every step re-zeroes and rewrites '
+                      'the accumulator grid, no cached outputs are reused',
+                'grid': rr['grid'], 'block': rr['block'],
+                'registers': rr['kernel_attributes']['num_regs'],
+            },
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'packets/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3*e2e_s/args.steps,
+                    'checksum': checksum},
+            'gpu_launches': args.steps,
+            'roofline': roofline,
+            'cpu_baseline': cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,76 @@
+"""Concrete synthetic definitions of the BASELINE.json configs,
+written against the simulator-module API so they can be instantiated with
+``pyxopto_b200`` (bench, smoke, tests) or with the reference (oracle/build_ref.py).
+
+C2 optical properties are the reference's ``xopto.materials.skin.Skin3()``
+defaults evaluated at 550 nm with ``create_mc_layers`` (materials/skin/model.py:
+1032-1066, 1121-1146) in this container; the subcutis is cut at 10 mm as SURVEY
+8d prescribes.  They are plain numbers here because ``xopto.materials`` is input
+generation, outside the accelerated path.
+"""
+import numpy as np
+
+RNGINIT = 0x2545F4914F6CDD1D
+
+SKIN3_550NM = [
+    # (d [m], n, mua [1/m], mus [1/m], g)
+    (1e-4, 1.334683329053798, 2493.6873583265165, 15079.876661995619, 0.9),   # epidermis
+    (2e-3, 1.3865225836400437, 1001.2238137598148, 10079.982905825484, 0.8),  # dermis
+    (1e-2, 1.3865225836400437, 792.2425907825923, 5039.991452912742, 0.8),    # subcutis
+]
+MHG_BETA = 0.9
+
+
+def _fiber(mc):
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcml.mcutil import fiber as fiberutil
+        return fiberutil.MultimodeFiber(200e-6, 220e-6, 1.462, 0.22)
+    return mc.mcsource.MultimodeFiber(200e-6, 220e-6, 1.462, 0.22)
+
+
+def c1_slab(mc, rnginit=123456789, **kw):
+    """BASELINE configs[0]: single slab, Line source, Radial reflectance."""
+    Axis = mc.mcdetector.Axis
+    pf = mc.mcpf.Hg(0.8)
+    L = mc.mclayer.Layer
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(0.0)),
+        L(d=10e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(0.0))])
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0.0, 10e-3, 1000)))
+    sim = mc.Mc(layers, mc.mcsource.Line(), det, rnginit=rnginit, **kw)
+    return sim
+
+
+def c2_skin(mc, rnginit=RNGINIT, pf='mhg', **kw):
+    """BASELINE configs[1]: 5-entry skin stack, UniformFiber source,
+    SixAroundOne detector, MHg phase function, FluenceRz 250 x 500."""
+    Axis = mc.mcdetector.Axis
+    L = mc.mclayer.Layer
+
+    def make_pf(g):
+        return mc.mcpf.MHg(g, MHG_BETA) if pf == 'mhg' else mc.mcpf.Hg(g)
+
+    stack = [L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=make_pf(0.0))]
+    for d, n, mua, mus, g in SKIN3_550NM:
+        stack.append(L(d=d, n=n, mua=mua, mus=mus, pf=make_pf(g)))
+    stack.append(L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=make_pf(0.0)))
+    fib = _fiber(mc)
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.SixAroundOne(fib, spacing=220e-6))
+    flu = mc.mcfluence.FluenceRz(Axis(0.0, 5e-3, 250), Axis(0.0, 5e-3, 500))
+    sim = mc.Mc(mc.mclayer.Layers(stack), mc.mcsource.UniformFiber(fib), det,
+                fluence=flu, rnginit=rnginit, **kw)
+    return sim
+
+
+# algorithmic thread-operations per loop iteration: the
+# per-unit figure of the roofline.  (ALU/FMA ops, MUFU ops)
+OPS_PER_ITERATION = {
+    'c1_slab': (85, 11),
+    'c2_skin': (105, 12),
+    'c3_vox': (83, 5.5),
+}
+
+CONFIGS = {'c1_slab': c1_slab, 'c2_skin': c2_skin}
+GEOMETRY = {'c1_slab': 'mcml', 'c2_skin': 'mcml'}
+PACKETS = {'c1_slab': 10**6, 'c2_skin': 10**9}

@@ -53,8 +53,9 @@ class XoRefArgs(ctypes.Structure):
 
 
 def compile_rendered(src: str, geometry: str, name: str = None,
-                     cflags=None, outdir: str = REF_DIR) -> str:
-    """gcc-compile rendered reference kernel text; returns the .so path."""
+                     cflags=None, outdir: str = REF_DIR, stable: bool = False) -> str:
+    """gcc-compile rendered reference kernel text; returns the .so path.
+    ``stable``: fixed file name ``libref_<name>.so`` (bench baselines)."""
     cflags = list(CFLAGS_EXACT if cflags is None else cflags)
     os.makedirs(outdir, exist_ok=True)
     with open(os.path.join(HERE, 'clshim.h'), 'rb') as f:
@@ -65,7 +66,9 @@ def compile_rendered(src: str, geometry: str, name: str = None,
         src.encode() + shim + drv + ' '.join(cflags).encode() +
         geometry.encode()).hexdigest()[:16]
     so = os.path.join(outdir, 'libref_{}_{}.so'.format(name or geometry, digest))
-    if os.path.exists(so):
+    if stable:
+        so = os.path.join(outdir, 'libref_{}.so'.format(name))
+    elif os.path.exists(so):
         return so
     with tempfile.TemporaryDirectory() as tmp:
         ksrc = os.path.join(tmp, 'kernel.c')

@@ -153,6 +153,7 @@ McKernel(
 	if (pk_next >= num_packets) pk_end = pk_next;
 #endif
 	bool started = false;
+	u32 iterations = 0;
 
 	if (pk_next < pk_end) {
 		started = true;
@@ -184,6 +185,7 @@ McKernel(
 		while (!done) {
 			const MlLayer &L = sh_layers[layer];
 			float step;
+			++iterations;
 #if XO_METHOD == 2
 			step = M::div(-M::log(rng.next()), L.mus);
 #else
@@ -308,6 +310,13 @@ McKernel(
 	}
 #undef XO_LAUNCH_PACKET
 	if (started) atomicAdd(num_kernels, 1u);
+	// loop-iteration count (the roofline's unit of work): one 64-bit RED per warp
+	{
+		const u32 mask = __activemask();
+		u32 warp_iters = __reduce_add_sync(mask, iterations);
+		if ((threadIdx.x & 31u) == (u32)(__ffs(mask) - 1) && warp_iters)
+			atomicAdd(reinterpret_cast<u64 *>(num_kernels + 1), (u64)warp_iters);
+	}
 
 	__syncthreads();
 	acc.flush_private();

@@ -272,7 +272,7 @@ class McBase(CuWorker):
 
         # uploads (mc.py:840-884)
         self._upload_seeds(copy=False)
-        counters = np.zeros(2, dtype=np.uint32)
+        counters = np.zeros(4, dtype=np.uint32)   # done, kernels, iterations (u64)
         cbuf = self.cl_r_buffer('counters', counters)
         self._upload_medium()
         if len(self._float_lut):
@@ -318,6 +318,7 @@ class McBase(CuWorker):
             'upload': t_up - t_build, 'build': t_build - t0,
             'execution': t_exec - t_up, 'download': t_down - t_exec,
             'kernel_ms': kernel_ms, 'threads': int(counters[1]),
+            'iterations': int(counters[2:4].view(np.uint64)[0]),
             'launched_threads': nthreads, 'grid': grid, 'block': block,
             'shared_bytes': shared, 'private_bins': priv_len, 'lut_shared': lut_len,
             'chunk': chunk, 'items': nphotons, 'cache_hit': mod.cache_hit,
