@@ -74,3 +74,35 @@ OPS_PER_ITERATION = {
 CONFIGS = {'c1_slab': c1_slab, 'c2_skin': c2_skin}
 GEOMETRY = {'c1_slab': 'mcml', 'c2_skin': 'mcml'}
 PACKETS = {'c1_slab': 10**6, 'c2_skin': 10**9}
+
+
+def c3_vox(mc, rnginit=RNGINIT, n=201, **kw):
+    """BASELINE configs[2]: 201^3 voxel 2-layer skin with an embedded blood
+    vessel (5 um voxels), GaussianBeam(sigma=50 um), Fluence deposition grid
+    (parameters as in xopto/dataset/render/mcvox.py:39-46)."""
+    A = mc.mcgeometry.Axis
+    vs = 5e-6
+    half = n/2*vs
+    vox = mc.mcgeometry.Voxels(A(-half, half, n), A(-half, half, n), A(0.0, n*vs, n))
+    M = mc.mcmaterial.Material
+    nref = 1.337
+    mats = mc.mcmaterial.Materials([
+        M(n=nref, mua=0.0001e2, mus=1.0e2, pf=mc.mcpf.Hg(1.0)),
+        M(n=nref, mua=16.5724e2, mus=375.9398e2, pf=mc.mcpf.Hg(0.9)),
+        M(n=nref, mua=0.4585e2, mus=356.5406e2, pf=mc.mcpf.Hg(0.9)),
+        M(n=nref, mua=230.5427e2, mus=93.9850e2, pf=mc.mcpf.Hg(0.9))])
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    sim = mc.Mc(vox, mats, mc.mcsource.GaussianBeam(50e-6), fluence=flu,
+                rnginit=rnginit, **kw)
+    sim.rmax = 25e-3
+    z, y, x = sim.voxels.meshgrid()
+    m = sim.voxels.material
+    m[z <= 100e-6] = 1
+    m[z > 100e-6] = 2
+    m[(x**2 + (z - 500e-6)**2) <= (100e-6)**2] = 3
+    return sim
+
+
+CONFIGS['c3_vox'] = c3_vox
+GEOMETRY['c3_vox'] = 'mcvox'
+PACKETS['c3_vox'] = 10**8

@@ -69,6 +69,8 @@ typedef struct { p3f position, dir_medium, dir_sample, dir_reflected; float refl
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip, reflectance; } src_gauss_ml;
 typedef struct { m3f T; p3f position, direction; float radius, cos_min, n; } src_ufiber;
 typedef struct { p3f position; uint32_t layer_index; } src_isopoint;
+typedef struct { m3f T; p3f position, direction; p2f sigma; float clip; } src_gauss_vox;  /* mcvox/mcsource/gaussianbeam.py:71-77 */
+typedef struct { p3f position; } src_isopoint_vox;                                  /* mcvox/mcsource/point.py:44-46 */
 
 typedef struct { p3f direction; float cos_min; uint32_t offset; } det_total;
 typedef struct { p3f direction; p2f position; float r_min, inv_dr, cos_min;
@@ -639,7 +641,7 @@ static void launch_mcml(sim_t *s) {
 static inline p3f source_position(const xo_oracle_job *j) {
 	size_t off = 0;
 	switch (j->src_kind) {
-		case XO_SRC_GAUSSIANBEAM: off = (j->geometry == XO_GEOM_MCVOX) ? 0 : sizeof(m3f); break;
+		case XO_SRC_GAUSSIANBEAM: off = sizeof(m3f); break;
 		case XO_SRC_UNIFORMFIBER: off = sizeof(m3f); break;
 		default: off = 0; break;
 	}

@@ -1,0 +1,114 @@
+// mcvox_sources.cuh -- photon packet sources of the voxelised simulator.
+//
+// Struct members = packed `McSource` of xopto/mcvox/mcsource/{line,gaussianbeam,
+// point}.py; launch() consumes the same uniform draws as `mcsim_launch`.
+// `Ctx` (VoxCtx) exposes the voxel box, the voxel -> material lookup and the
+// material refractive indices.
+#pragma once
+#include "xo_core.cuh"
+#include "mcml_sources.cuh"     // struct Launch
+
+namespace xo {
+
+struct VoxSrcLine {                 // mcvox/mcsource/line.py:57-63
+	P3 position, direction_medium, direction_sample, direction_reflected;
+	float reflectance;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)rng; (void)ctx; (void)prev_pos;
+		L.weight = 1.0f - reflectance;
+		L.pos = position;
+		L.dir = direction_sample;
+		L.spec_dir = direction_reflected;
+		L.spec_weight = reflectance;
+	}
+};
+
+// Specular reflectance + refracted direction of a ray entering the box at a
+// point whose voxel is looked up from `lookup_pos` (see the IsotropicPoint note).
+template <class Ctx>
+__device__ __forceinline__ float vox_enter(const Ctx &ctx, const P3 &lookup_pos,
+		const P3 &normal, const P3 &direction, P3 *refracted) {
+	float n_out = ctx.material_n(0);
+	i32 vx, vy, vz;
+	ctx.position_to_voxel(lookup_pos, &vx, &vy, &vz);
+	vx = clipi(vx, 0, ctx.cfg.nx - 1);
+	vy = clipi(vy, 0, ctx.cfg.ny - 1);
+	vz = clipi(vz, 0, ctx.cfg.nz - 1);
+	float n_in = ctx.material_n(ctx.voxel_material(vx, vy, vz));
+	*refracted = direction;
+	refract3_safe(direction, normal, n_out, n_in, refracted);
+	return reflectance(n_out, n_in, dot3(normal, direction), cos_critical(n_out, n_in));
+}
+
+struct VoxSrcGaussianBeam {         // mcvox/mcsource/gaussianbeam.py:71-77
+	M3 T; P3 position, direction; P2 sigma; float clip;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		float sf, cf, rs = 0.0f;
+		float r = M::sqrt(-2.0f*M::log(1.0f - rng.next()));
+		r = fminf(r, clip);
+		M::sincos(XO_FP_2PI*rng.next(), &sf, &cf);
+		P3 ps = { r*cf*sigma.x, r*sf*sigma.y, 0.0f };
+		P3 pm = transform3(T, ps);
+		pm.x += position.x; pm.y += position.y; pm.z += position.z;
+		P3 d = direction;
+		if (ctx.box_contains(pm)) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
+		P3 isect, normal;
+		if (ctx.box_intersect(pm, d, &isect, &normal)) {
+			L.pos = isect;
+			d.x = -d.x; d.y = -d.y; d.z = -d.z;
+			normal.x = -normal.x; normal.y = -normal.y; normal.z = -normal.z;
+			P3 refracted;
+			rs = vox_enter(ctx, isect, normal, d, &refracted);
+			L.dir = refracted;
+			L.spec_dir = d;
+			L.spec_weight = rs;
+		} else {
+			L.pos = ctx.cfg.top_left;
+			L.dir.x = 0.0f; L.dir.y = 0.0f; L.dir.z = 1.0f;
+			rs = 1.0f;
+			L.spec_weight = -1.0f;      // the reference deposits nothing on a miss
+		}
+		L.weight = 1.0f - rs;
+	}
+};
+
+struct VoxSrcIsotropicPoint {       // mcvox/mcsource/point.py:44-46
+	P3 position;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		float sf, cf, rs = 0.0f;
+		P3 p = position;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 1.0f - 2.0f*rng.next();
+		float st = M::sqrt(1.0f - ct*ct);
+		P3 d = { cf*st, sf*st, ct };
+		if (!ctx.box_contains(p)) {
+			P3 isect, normal;
+			if (ctx.box_intersect(p, d, &isect, &normal)) {
+				p = isect;
+				// Reference quirks kept for parity (point.py:105-117): the voxel
+				// under the entry point is looked up from the simulator's
+				// *previous* position, and the refracted direction is computed
+				// into a shadowed variable, i.e. the packet keeps `d`.
+				P3 unused;
+				rs = vox_enter(ctx, prev_pos, normal, d, &unused);
+			} else {
+				p = ctx.cfg.top_left;
+				rs = 1.0f;
+			}
+		}
+		L.pos = p;
+		L.dir = d;
+		L.spec_dir = d;
+		L.spec_weight = rs;
+		L.weight = 1.0f - rs;
+	}
+};
+
+}  // namespace xo

@@ -1,0 +1,129 @@
+"""Voxelised simulator ``Mc`` (drop-in for ``xopto.mcvox.mc.Mc``, mcvox/mc.py:76-1100)
+on top of the CUDA kernel ``csrc/kernels/mcvox_kernel.cuh``.
+
+    from pyxopto_b200.mcvox import mc
+    voxels = mc.mcgeometry.Voxels(xaxis, yaxis, zaxis)
+    sim = mc.Mc(voxels, materials, mc.mcsource.GaussianBeam(50e-6), fluence=...)
+    sim.voxels.material[...] = 1
+    trace, fluence, detectors = sim.run(1e6)
+"""
+import ctypes
+
+import numpy as np
+
+from ..cl import clinfo, clrng, cltypes            # noqa: F401
+from ..mcbase import mcoptions, mctypes, mcobject  # noqa: F401
+from ..mcbase import mcpf, mcfluence, mctrace, mcmaterial  # noqa: F401
+from ..mcbase.mcobject import McObject             # noqa: F401
+from ..mcbase.mcsim import McBase
+from ..mcml import mcdetector                      # noqa: F401  (same detector family)
+from . import mcgeometry, mcsource                 # noqa: F401
+
+
+class Mc(McBase):
+    kernel_header = 'mcvox_kernel.cuh'
+    geometry = 'mcvox'
+
+    def __init__(self, voxels, materials, source, detectors=None, trace=None,
+                 fluence=None, surface=None, types=mctypes.McDataTypesSingle,
+                 options=None, rnginit=None, cl_devices=None, cl_build_options=None,
+                 cl_profiling: bool = False):
+        super().__init__(source, detectors=detectors, trace=trace, fluence=fluence,
+                         surface=surface, types=types, options=options,
+                         rnginit=rnginit, cl_devices=cl_devices,
+                         cl_build_options=cl_build_options, cl_profiling=cl_profiling)
+        if not isinstance(materials, mcmaterial.Materials):
+            materials = mcmaterial.Materials(materials)
+        self._voxels = voxels
+        self._materials = materials
+        self._voxels.data(self)            # allocate the material-index array
+        self._obj_types['pf'] = type(materials[0].pf)
+        self._voxels_on_device = False
+
+    voxels = property(lambda self: self._voxels)
+    materials = property(lambda self: self._materials)
+
+    def material(self, index):
+        """Material by index or at a position (mcvox/mc.py:420-450).  The
+        reference indexes the [z, y, x] array with an (x, y, z) tuple here; kept
+        for parity (it only matters for the specular term of asymmetric grids)."""
+        material_index = 0
+        if isinstance(index, (int, np.integer)):
+            material_index = int(index)
+        elif self._voxels.contains(index):
+            ind = self._voxels.index(index)
+            material_index = int(self._voxels[ind]['material_index'])
+        return self._materials[material_index]
+
+    # -- packing -----------------------------------------------------------------
+    def _pack_medium(self):
+        if type(self._materials[0].pf) is not self._obj_types['pf']:
+            raise ValueError('The scattering phase function kind/type must not '
+                             'change between simulation calls!')
+        self._packed['materials'] = self._materials.cl_pack(
+            self, self._packed.get('materials'))
+        self._packed['voxels'] = self._voxels.cl_pack(self, self._packed.get('voxels'))
+
+    def _medium_bytes(self) -> int:
+        return len(cltypes.raw_bytes(self._packed['materials']))
+
+    def _upload_medium(self):
+        self.cl_r_buffer('materials', self._packed['materials'])
+        if self._voxels.update_required() or not self._voxels_on_device:
+            data = np.ascontiguousarray(self._voxels.data(self)).view(np.int32)
+            self.cl_r_buffer('voxel_data', data)
+            self._voxels_on_device = True
+
+    # -- translation unit ----------------------------------------------------------
+    def _plugin_bindings(self):
+        pf = self._materials[0].pf
+        out = [('XoPf', pf.fetch_cu_type(self), pf.fetch_cl_type(self)),
+               ('XoSource', self._source.fetch_cu_type(self),
+                self._source.fetch_cl_type(self))]
+        out += self._detector_bindings()
+        if self._fluence is not None:
+            out.append(('XoFluence', self._fluence.fetch_cu_type(self),
+                        self._fluence.fetch_cl_type(self)))
+        else:
+            out.append(('XoFluence', 'xo::FluNone', None))
+        return out
+
+    def _extra_includes(self):
+        return ['#include "mcvox_sources.cuh"']
+
+    def _extra_checks(self):
+        checks = [
+            'static_assert(sizeof(xo::VoxMaterial) == {}, "McMaterial layout differs '
+            'from the packed host struct");'.format(
+                ctypes.sizeof(self._materials[0].fetch_cl_type(self))),
+            'static_assert(sizeof(xo::VoxCfg) == {}, "McVoxelConfig layout differs '
+            'from the packed host struct");'.format(
+                ctypes.sizeof(self._voxels.fetch_cl_type(self)))]
+        if self._detectors is not None:
+            checks.append('static_assert(sizeof(xo::XoDetectors) == {}, "McDetectors '
+                          'layout differs from the packed host struct");'.format(
+                              ctypes.sizeof(self._detectors.fetch_cl_type(self))))
+        return checks
+
+    # -- launch ---------------------------------------------------------------------
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk):
+        if self._detectors is not None:
+            dets = self._packed['detectors']
+        else:
+            dets = mcdetector.Detectors().cl_pack(self)
+        return [
+            np.uint32(nphotons),
+            (bufs['counters'], 0), (bufs['counters'], 4),
+            np.float32(self._rmax),
+            bufs['rng_x'], bufs['rng_a'],
+            self._packed['voxels'],
+            self._cl_buffers['voxel_data'],
+            np.uint32(len(self._materials)),
+            self._cl_buffers['materials'],
+            self._packed['source'],
+            self._packed_or_dummy('trace', 4),
+            self._packed_or_dummy('fluence', 4),
+            dets,
+            bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
+            np.uint32(lut_len), np.uint32(priv_len), np.uint32(max(chunk, 1)),
+        ]

@@ -1,0 +1,154 @@
+"""Photon packet sources of the voxelised simulator (mirror of
+``xopto/mcvox/mcsource``: Line, GaussianBeam, IsotropicPoint)."""
+import numpy as np
+
+from ..cl import cltypes
+from ..mcbase.mcutil import boundary, geometry
+from ..mcml.mcsource import Source, _unit
+from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
+
+
+class Line(Source):
+    """Infinitely thin beam entering the voxel box (mcvox/mcsource/line.py)."""
+    cu_type = 'xo::VoxSrcLine'
+    _update_keys = ('position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClLine(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('direction_medium', T.mc_point3f_t),
+                        ('direction_sample', T.mc_point3f_t),
+                        ('direction_reflected', T.mc_point3f_t),
+                        ('reflectance', T.mc_fp_t)]
+        return ClLine
+
+    def __init__(self, position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self._direction = np.zeros((3,))
+        self.position, self.direction = position, direction
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        self._direction[:] = _unit(d)
+
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        search = -self._direction if mc.voxels.contains(self._position) else self._direction
+        position, normal = mc.voxels.intersect(self._position, search)
+        if position is None:
+            raise ValueError('The line source does not intersect the voxelized sample!')
+        medium, sample = mc.materials[0], mc.material(position)
+        reflectance = boundary.reflectance(
+            medium.n, sample.n, np.abs(np.dot(normal, self._direction)))
+        if reflectance >= 1.0:
+            raise ValueError('The line source is fully reflected from the '
+                             'surface of the voxelized sample!')
+        target.position.fromarray(position)
+        target.direction_medium.fromarray(self._direction)
+        target.direction_sample.fromarray(
+            boundary.refract(self._direction, normal, medium.n, sample.n))
+        target.direction_reflected.fromarray(boundary.reflect(self._direction, normal))
+        target.reflectance = reflectance
+        return target, None, None
+
+    def todict(self):
+        return {'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class GaussianBeam(Source):
+    """Collimated Gaussian beam (mcvox/mcsource/gaussianbeam.py)."""
+    cu_type = 'xo::VoxSrcGaussianBeam'
+    _update_keys = ('sigma', 'clip', 'position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClGaussianBeam(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('sigma', T.mc_point2f_t),
+                        ('clip', T.mc_fp_t)]
+        return ClGaussianBeam
+
+    def __init__(self, sigma, clip: float = 5.0, position=(0.0, 0.0, 0.0),
+                 direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self._sigma = np.zeros((2,))
+        self.sigma, self.clip = sigma, clip
+        self.position, self.direction = position, direction
+
+    def _set_sigma(self, s):
+        self._sigma[:] = s
+        if np.any(self._sigma < 0.0):
+            raise ValueError('Beam diameter/sigma must not be negative!')
+
+    def _set_clip(self, c):
+        self._clip = float(c)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        self._direction[:] = _unit(d)
+
+    sigma = property(lambda self: self._sigma, _set_sigma)
+    clip = property(lambda self: self._clip, _set_clip)
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.sigma.fromarray(self._sigma)
+        target.clip = self._clip
+        return target, None, None
+
+    def todict(self):
+        return {'sigma': self._sigma.tolist(), 'clip': self._clip,
+                'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class IsotropicPoint(Source):
+    """Isotropic point source inside or outside the voxel box (mcvox/mcsource/point.py)."""
+    cu_type = 'xo::VoxSrcIsotropicPoint'
+    _update_keys = ('position',)
+
+    @staticmethod
+    def cl_type(mc):
+        class ClIsotropicPoint(cltypes.Structure):
+            _fields_ = [('position', mc.types.mc_point3f_t)]
+        return ClIsotropicPoint
+
+    def __init__(self, position=(0.0, 0.0, 0.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self.position = position
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.position.fromarray(self._position)
+        return target, None, None
+
+    def todict(self):
+        return {'position': self._position.tolist(), 'type': type(self).__name__}

@@ -123,3 +123,75 @@ GEOMETRY = {name: name.split('_')[0] for name in ALL_CASES}
 GOLDEN_RUN = {name: (3000, 16) for name in ALL_CASES}
 GOLDEN_RUN['mcml_c1_slab'] = (4000, 64)
 GOLDEN_RUN['mcml_lut_iso_radialpl_trace'] = (800, 16)
+
+
+# ---------------------------------------------------------------------------
+# voxelised cases
+def _vox_grid(mc, n=(24, 20, 28), voxel=25e-6):
+    A = mc.mcgeometry.Axis
+    nx, ny, nz = n
+    return mc.mcgeometry.Voxels(A(-nx/2*voxel, nx/2*voxel, nx), A(-ny/2*voxel, ny/2*voxel, ny),
+                                A(0.0, nz*voxel, nz))
+
+
+def _vox_materials(mc, pf_factory, n_vessel=1.337):
+    M = mc.mcmaterial.Material
+    return mc.mcmaterial.Materials([
+        M(n=1.0, mua=0.0, mus=0.0, pf=pf_factory(1.0)),
+        M(n=1.337, mua=16.5724e2, mus=375.9398e2, pf=pf_factory(0.9)),
+        M(n=1.4, mua=0.4585e2, mus=356.5406e2, pf=pf_factory(0.9)),
+        M(n=n_vessel, mua=230.5427e2, mus=93.9850e2, pf=pf_factory(0.9))])
+
+
+def _fill_skin_vessel(sim, depth=100e-6, center=350e-6, radius=120e-6):
+    z, y, x = sim.voxels.meshgrid()
+    m = sim.voxels.material
+    m[z <= depth] = 1
+    m[z > depth] = 2
+    m[(x**2 + (z - center)**2) <= radius**2] = 3
+    return sim
+
+
+def mcvox_gauss_fluence(mc, **kw):
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc)
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(A(0, 0.4e-3, 40)), bottom=mc.mcdetector.Total(),
+        specular=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg), mc.mcsource.GaussianBeam(50e-6),
+                detectors=det, fluence=flu, rnginit=2468, **kw)
+    return _fill_skin_vessel(sim), dict(rmax=25e-3)
+
+
+def mcvox_line_mhg_trace(mc, **kw):
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc, n=(16, 16, 20))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Cartesian(A(-0.2e-3, 0.2e-3, 16)),
+                                  bottom=mc.mcdetector.Radial(A(0, 0.3e-3, 10), cosmin=0.3))
+    tr = mc.mctrace.Trace(maxlen=40, options=mc.mctrace.Trace.TRACE_ALL, plon=True)
+    sim = mc.Mc(vox, _vox_materials(mc, lambda g: mc.mcpf.MHg(g, 0.85), n_vessel=1.36),
+                mc.mcsource.Line((10e-6, -5e-6, 0.0), (0.2, 0.1, 1.0)),
+                detectors=det, trace=tr, rnginit=1357, **kw)
+    return _fill_skin_vessel(sim, center=250e-6, radius=80e-6), dict(rmax=5e-3)
+
+
+def mcvox_isopoint_fluencerate(mc, **kw):
+    vox = _vox_grid(mc, n=(20, 20, 20))
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='fluence')
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg), mc.mcsource.IsotropicPoint((0, 0, -0.2e-3)),
+                detectors=det, fluence=flu, rnginit=97531, **kw)
+    return _fill_skin_vessel(sim, center=250e-6, radius=80e-6), dict(rmax=5e-3)
+
+
+MCVOX_CASES = {
+    'mcvox_gauss_fluence': mcvox_gauss_fluence,
+    'mcvox_line_mhg_trace': mcvox_line_mhg_trace,
+    'mcvox_isopoint_fluencerate': mcvox_isopoint_fluencerate,
+}
+ALL_CASES.update(MCVOX_CASES)
+GEOMETRY.update({name: 'mcvox' for name in MCVOX_CASES})
+GOLDEN_RUN.update({'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
+                   'mcvox_isopoint_fluencerate': (2000, 16)})
