@@ -126,18 +126,20 @@ def main():
     ncores = os.cpu_count() or 1
     config = args.config
     metric = 'photon packets/s ({})'.format(
-        'mcml 5-layer skin' if config == 'c2_skin' else config)
+        {'c2_skin': 'mcml 5-layer skin', 'c3_vox': 'mcvox 201^3 fluence'}.get(config, config))
     workload = {
         'c2_skin': 'mcml 5-layer skin (Skin3 @550nm), UniformFiber + SixAroundOne, '
                    'MHg(beta=0.9), FluenceRz 250x500',
         'c1_slab': 'mcml single slab mua=1/cm mus=100/cm g=0.8 n=1.33, Line + Radial',
+        'c3_vox': 'mcvox 201^3 voxel 2-layer skin + blood vessel (5 um voxels), '
+                  'GaussianBeam sigma 50 um, Fluence deposition grid',
     }.get(config, config)
 
     # ---------------- reference arm: the reference kernel on host cores --------
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        sample = int(args.cpu_sample or (3e5 if config == 'c2_skin' else 5e4))
+        sample = int(args.cpu_sample or {'c2_skin': 3e5, 'c3_vox': 2e4}.get(config, 5e4))
         times = []
         kind = 'port'
         for i in range(args.warmup + args.steps):
@@ -176,30 +178,14 @@ def main():
     from pyxopto_b200.cu import abi
     geom = benchcfg.GEOMETRY[config]
     mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
-    packets = int(args.packets or (1.25e8 if config == 'c2_skin' else 1e7))
-    sim = benchcfg.CONFIGS[config](mc, rnginit=benchcfg.RNGINIT + rank, cl_devices=local_rank)
-
-    reduce_tensor = {}
-
-    def allreduce(sim_, abuf, count):
-        """single NCCL all-reduce of the uint64 accumulators (as int64: two's
-        complement addition is the same operation)"""
-        key = (abuf.device_ptr, count)
-        if key not in reduce_tensor:
-            class _Wrap:
-                pass
-            w = _Wrap()
-            w.__cuda_array_interface__ = {
-                'shape': (int(count),), 'typestr': '<i8', 'data': (abuf.device_ptr, False),
-                'version': 2}
-            reduce_tensor.clear()
-            reduce_tensor[key] = torch.as_tensor(w, device=torch.device('cuda', local_rank))
-        sim_._stream.synchronize()
-        dist.all_reduce(reduce_tensor[key])
-        torch.cuda.synchronize()
+    packets = int(args.packets or {'c2_skin': 1.25e8, 'c3_vox': 1.25e7}.get(config, 1e7))
+    from pyxopto_b200 import parallel as _par
+    sim = benchcfg.CONFIGS[config](mc, rnginit=_par.seed_for_rank(benchcfg.RNGINIT, rank),
+                                   cl_devices=local_rank)
 
     if world > 1:
-        sim._reduce_hook = allreduce
+        from pyxopto_b200 import parallel
+        sim._reduce_hook = parallel.NcclAccumulatorReducer(local_rank)
 
     def barrier():
         sim._stream.synchronize()
@@ -238,7 +224,8 @@ def main():
     h2d = d2h = 0
     for _ in range(args.steps):
         trace, fluence, detectors = sim.run(packets)
-        checksum = float(detectors.top.raw.sum()) + float(fluence.raw.sum())
+        checksum = (float(detectors.top.raw.sum()) if detectors is not None else 0.0) + \
+            (float(fluence.raw.sum()) if fluence is not None else 0.0)
     barrier()
     t3 = time.perf_counter()
     e2e_s = t3 - t2
@@ -278,7 +265,7 @@ def main():
             'algorithmic_ops_per_iteration': {'alu_fma': alu_ops, 'mufu': sfu_ops},
             'sfu': {'achieved': achieved_sfu/1e9, 'peak': sfu_peak/1e9,
                     'frac': achieved_sfu/sfu_peak},
-            'atomics_per_s': iter_per_launch/(k_ms*1e-3) if config == 'c2_skin' else None,
+            'atomics_per_s': (iter_per_launch/(k_ms*1e-3) if config == 'c2_skin' else None),
             'peak_source': 'sm_max_mhz of MEASURED_PEAKS.json ({}) x {} SMs x {} FP32 lanes; '
                            'hbm is not the bound of this path (working set < 2 MB)'.format(
                                peaks_src, sms, FP32_LANES_PER_SM),
@@ -286,7 +273,7 @@ def main():
         }
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
-            sample = int(args.cpu_sample or (2e6 if config == 'c2_skin' else 3e5))
+            sample = int(args.cpu_sample or {'c2_skin': 2e6, 'c3_vox': 1e5}.get(config, 3e5))
             try:
                 pps, kind, secs = cpu_reference_run(config, sample, ncores)
                 cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
