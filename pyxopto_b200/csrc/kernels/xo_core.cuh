@@ -84,7 +84,14 @@ struct Rng {
 		x = (u64)(u32)x*(u64)a + (x >> 32);
 		return __uint2float_rn((u32)x)*2.3283064365386963e-10f;
 	}
+	// the same draw before the 2^-32 scaling, RN(float(lo32 x)) in [0, 2^32]:
+	// throughput-mode callers fold the scale into their own constants
+	__device__ __forceinline__ float next_raw() {
+		x = (u64)(u32)x*(u64)a + (x >> 32);
+		return __uint2float_rn((u32)x);
+	}
 };
+#define XO_RNG_SCALE 2.3283064365386963e-10f
 
 // ---- boundary physics (Fresnel, Snell) --------------------------------------
 __device__ __forceinline__ float cos_critical(float n1, float n2) {
@@ -213,6 +220,29 @@ __device__ __forceinline__ u32 weight_u32(float w, bool accept) {
 #endif
 	return accept ? f2u(v) : 0u;
 }
+
+// ---- packet budget ------------------------------------------------------------
+// Deterministic mode: work-item t owns the packets of its static quota.
+// Throughput mode: the reference's global packet counter (mcml.template.c:460,
+// 790), claimed `chunk` packets per atomic; `dry` is set once the counter has
+// passed the budget so a finished lane never touches the counter again.
+struct Budget {
+	u32 next, end;
+	bool dry;
+	__device__ __forceinline__ bool claim(u32 N, u32 *counter, u32 chunk, u32 *packet) {
+#if !XO_DETERMINISTIC
+		if (next >= end && !dry) {
+			next = atomicAdd(counter, chunk);
+			if (next >= N) { dry = true; end = next; }
+			else end = (N - next < chunk) ? N : next + chunk;
+		}
+#else
+		(void)N; (void)counter; (void)chunk;
+#endif
+		if (next < end) { *packet = next++; return true; }
+		return false;
+	}
+};
 
 // block-schedule quota of work-item t (deterministic mode)
 __device__ __forceinline__ void static_quota(u32 N, u32 T, u32 t, u32 *first, u32 *end) {

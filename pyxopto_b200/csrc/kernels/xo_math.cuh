@@ -25,6 +25,18 @@ namespace xo {
 struct FastMath {
 	static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
 	static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
+	// one MUFU.RCP
+	static __device__ __forceinline__ float rcp_approx(float a) {
+		float r;
+		asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+		return r;
+	}
+	// one MUFU.LG2 (callers pass normal numbers or 0)
+	static __device__ __forceinline__ float lg2(float a) {
+		float r;
+		asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+		return r;
+	}
 	// sqrt.approx = one MUFU.SQRT (the IEEE version costs ~10 instructions)
 	static __device__ __forceinline__ float sqrt(float a) {
 		float r;

@@ -5,10 +5,53 @@
 // consumes the same uniform draws in the same order as the plugin's
 // `mcsim_pf_sample_angles`, so the MWC streams stay aligned with the reference.
 // `lut` is the shared-memory (or global) copy of the float lookup-table pool.
+//
+// Throughput mode additionally uses a *prepared* form (`Fast`): constants that
+// depend only on the layer / material (1-g, 2g, (1+g^2)/2g ...) are computed
+// once per CTA when the medium table is staged in shared memory and are kept in
+// registers while a packet stays in the layer, so the per-event work is the
+// random draw plus a handful of FMAs and one MUFU.  Same distribution, same
+// draws; only the association of the floating-point operations differs.
 #pragma once
 #include "xo_core.cuh"
 
 namespace xo {
+
+// Henyey-Greenstein polar cosine from the prepared constants:
+//   k = (1-g^2)/(1 + g(2r-1)),  ct = (1+g^2-k^2)/(2g)
+//   with q = 1/((1-g) + 2g r):  ct = A - B q^2,  A=(1+g^2)/(2g),  B=(1-g^2)^2/(2g)
+// `f` is the raw draw RN(float(u32)) in [0, 2^32]; d1 carries the 2^-32.
+struct HgFast {
+	float d0, d1, A, B;             // d1 == 0  <=>  g == 0 (isotropic)
+	__device__ __forceinline__ void prepare(float g) {
+		d0 = 1.0f - g;
+		d1 = 2.0f*g*2.3283064365386963e-10f;
+		if (g != 0.0f) {
+			float inv2g = 1.0f/(2.0f*g);
+			A = (1.0f + g*g)*inv2g;
+			B = (1.0f - g*g)*(1.0f - g*g)*inv2g;
+		} else {
+			A = 0.0f; B = 0.0f;
+		}
+	}
+	// f: the raw draw; `wanted` is false when the caller discards the result
+	// (then the extra isotropic draw of g == 0 must not be consumed either)
+	__device__ __forceinline__ float polar(float f, Rng &rng, bool wanted = true) const {
+		float q = FastMath::rcp_approx(fmaf(f, d1, d0));
+		float ct = fmaf(-(B*q), q, A);
+		if (d1 == 0.0f && wanted) ct = fmaf(rng.next_raw(), -2.0f*2.3283064365386963e-10f, 1.0f);
+		return ct;
+	}
+};
+
+// prepared form of the phase functions that have nothing worth precomputing
+template <class Pf>
+struct PfPlainFast {
+	Pf pf;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		return pf.sample(rng, lut, azimuth);
+	}
+};
 
 struct PfHg {                       // mcpf/hg.py:49-50
 	float g;
@@ -22,6 +65,15 @@ struct PfHg {                       // mcpf/hg.py:49-50
 		if (g == 0.0f) ct = 1.0f - 2.0f*rng.next();
 		return fmaxf(fminf(ct, 1.0f), -1.0f);
 	}
+	struct Fast {
+		HgFast hg;
+		__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+			(void)lut;
+			*azimuth = rng.next_raw()*(XO_FP_2PI*2.3283064365386963e-10f);
+			return fmaxf(fminf(hg.polar(rng.next_raw(), rng), 1.0f), -1.0f);
+		}
+	};
+	__device__ __forceinline__ void prepare(Fast &f) const { f.hg.prepare(g); }
 };
 
 struct PfMHg {                      // mcpf/mhg.py:52-58
@@ -40,6 +92,27 @@ struct PfMHg {                      // mcpf/mhg.py:52-58
 			ct = M::cbrt(2.0f*rng.next() - 1.0f);
 		}
 		return clipf(ct, -1.0f, 1.0f);
+	}
+	struct Fast {
+		HgFast hg;
+		float beta_raw;             // beta * 2^32 (compared against the raw draw)
+		__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+			(void)lut;
+			// both branches consume the same third draw: evaluate both (8 + 6
+			// instructions) and select, instead of a divergent branch that
+			// nearly every warp would take both ways
+			*azimuth = rng.next_raw()*(XO_FP_2PI*2.3283064365386963e-10f);
+			const bool use_hg = rng.next_raw() <= beta_raw;
+			const float f = rng.next_raw();
+			float ct_hg = hg.polar(f, rng, use_hg);
+			float ct_rl = FastMath::cbrt(fmaf(f, 2.0f*2.3283064365386963e-10f, -1.0f));
+			float ct = use_hg ? ct_hg : ct_rl;
+			return fmaxf(fminf(ct, 1.0f), -1.0f);
+		}
+	};
+	__device__ __forceinline__ void prepare(Fast &f) const {
+		f.hg.prepare(g);
+		f.beta_raw = beta*4294967296.0f;
 	}
 };
 
@@ -61,6 +134,8 @@ struct PfGk {                       // mcpf/gk.py:58-66
 		}
 		return clipf(ct, -1.0f, 1.0f);
 	}
+	typedef PfPlainFast<PfGk> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
 };
 
 struct PfLut {                      // mcpf/lut.py:78-85
@@ -78,6 +153,8 @@ struct PfLut {                      // mcpf/lut.py:78-85
 		if (i1 > (i32)last) i1 = (i32)last;
 		return lut[offset + i0]*(1.0f - d) + lut[offset + (u32)i1]*d;
 	}
+	typedef PfPlainFast<PfLut> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
 };
 
 }  // namespace xo

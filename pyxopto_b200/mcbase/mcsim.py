@@ -161,6 +161,7 @@ class McBase(CuWorker):
             '#define XO_FLUENCE_RATE {}'.format(
                 int(bool(opts.get('MC_FLUENCE_MODE_RATE', False)))),
             '#define XO_TRACE_ALIGNED {}'.format(int(self._trace_aligned())),
+            '#define XO_USE_RMAX {}'.format(int(self._rmax_needed())),
             '#define XO_BLOCK {}'.format(int(block)),
             '#define XO_MIN_BLOCKS {}'.format(int(min_blocks)),
         ]
@@ -182,6 +183,20 @@ class McBase(CuWorker):
 
     def _extra_defines(self, opts):
         return []
+
+    def _rmax_needed(self) -> bool:
+        """False when the rmax test can never fire (compiled out of the loop)."""
+        return bool(np.isfinite(np.float32(self._rmax)))
+
+    # idle lanes per warp that trigger a joint launch (throughput mode); sources
+    # with a long launch path amortise it over more lanes
+    refill_lanes = None
+    chunk_max = 16
+
+    def _refill_lanes(self) -> int:
+        if self.refill_lanes is not None:
+            return int(min(max(self.refill_lanes, 1), 32))
+        return int(getattr(self._source, 'cu_refill_lanes', 1))
 
     def _extra_includes(self):
         return []
@@ -230,7 +245,7 @@ class McBase(CuWorker):
         words += 2*priv_len
         return words*4 + 16, lut_len, priv_len
 
-    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk):
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill):
         raise NotImplementedError
 
     def _medium_bytes(self) -> int:
@@ -289,11 +304,14 @@ class McBase(CuWorker):
         if deterministic:
             chunk = 0
         else:
-            chunk = int(min(max(nphotons//(nthreads*8), 1), 64))
+            # packets claimed per atomic: small enough that the last chunk of a
+            # lane (the load-imbalance tail) is < 2 % of its work
+            chunk = int(min(max(nphotons//(nthreads*64), 1), self.chunk_max))
         bufs = dict(counters=cbuf, lut=lbuf, accu=abuf, floats=fbuf, ints=ibuf,
                     rng_x=self._cl_buffers['rng_seeds_x'],
                     rng_a=self._cl_buffers['rng_seeds_a'])
-        args = self._kernel_args(nphotons, bufs, lut_len, priv_len, chunk)
+        refill = 1 if deterministic else self._refill_lanes()
+        args = self._kernel_args(nphotons, bufs, lut_len, priv_len, chunk, refill)
         t_up = time.perf_counter()
 
         ev0, ev1 = self._events
@@ -321,7 +339,7 @@ class McBase(CuWorker):
             'iterations': int(counters[2:4].view(np.uint64)[0]),
             'launched_threads': nthreads, 'grid': grid, 'block': block,
             'shared_bytes': shared, 'private_bins': priv_len, 'lut_shared': lut_len,
-            'chunk': chunk, 'items': nphotons, 'cache_hit': mod.cache_hit,
+            'chunk': chunk, 'refill': refill, 'items': nphotons, 'cache_hit': mod.cache_hit,
             'kernel_attributes': kernel.attributes(),
         }
         if verbose:

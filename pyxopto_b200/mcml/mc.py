@@ -53,7 +53,9 @@ class Mc(McBase):
         self._packed['layers'] = self._layers.cl_pack(self, self._packed.get('layers'))
 
     def _medium_bytes(self) -> int:
-        return len(cltypes.raw_bytes(self._packed['layers']))
+        # packed layers + the per-layer derived constants the kernel appends
+        # (xo::MlFastLayer, <= 96 B per layer)
+        return len(cltypes.raw_bytes(self._packed['layers'])) + 96*len(self._layers) + 32
 
     def _upload_medium(self):
         self.cl_r_buffer('layers', self._packed['layers'])
@@ -87,7 +89,7 @@ class Mc(McBase):
         return checks
 
     # -- launch ---------------------------------------------------------------------
-    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk):
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill):
         from . import mcdetector as md
         T = self._types
         if self._detectors is not None:
@@ -108,4 +110,5 @@ class Mc(McBase):
             dets,
             bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
             np.uint32(lut_len), np.uint32(priv_len), np.uint32(max(chunk, 1)),
+            np.uint32(refill),
         ]

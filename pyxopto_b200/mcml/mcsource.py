@@ -92,6 +92,7 @@ class Line(Source):
 class GaussianBeam(Source):
     """Collimated Gaussian beam (mcsource/gaussianbeam.py)."""
     cu_type = 'xo::SrcGaussianBeam'
+    cu_refill_lanes = 4     # long launch path: launch jointly (mcsim._refill_lanes)
     _update_keys = ('sigma', 'clip', 'position', 'direction')
 
     @staticmethod
@@ -167,6 +168,7 @@ class GaussianBeam(Source):
 class UniformFiber(Source):
     """Optical fiber with uniform emission within the NA (mcsource/fiber.py)."""
     cu_type = 'xo::SrcUniformFiber'
+    cu_refill_lanes = 6     # long launch path: launch jointly (mcsim._refill_lanes)
     _update_keys = ('fiber', 'position', 'direction')
 
     @staticmethod
@@ -227,6 +229,7 @@ class UniformFiber(Source):
 class IsotropicPoint(Source):
     """Isotropic point source above or inside the sample (mcsource/point.py)."""
     cu_type = 'xo::SrcIsotropicPoint'
+    cu_refill_lanes = 4     # long launch path: launch jointly (mcsim._refill_lanes)
     _update_keys = ('position',)
 
     @staticmethod

@@ -106,7 +106,7 @@ class Mc(McBase):
         return checks
 
     # -- launch ---------------------------------------------------------------------
-    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk):
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill):
         if self._detectors is not None:
             dets = self._packed['detectors']
         else:

@@ -67,6 +67,7 @@ class Line(Source):
 class GaussianBeam(Source):
     """Collimated Gaussian beam (mcvox/mcsource/gaussianbeam.py)."""
     cu_type = 'xo::VoxSrcGaussianBeam'
+    cu_refill_lanes = 6     # long launch path: launch jointly (mcsim._refill_lanes)
     _update_keys = ('sigma', 'clip', 'position', 'direction')
 
     @staticmethod
@@ -126,6 +127,7 @@ class GaussianBeam(Source):
 class IsotropicPoint(Source):
     """Isotropic point source inside or outside the voxel box (mcvox/mcsource/point.py)."""
     cu_type = 'xo::VoxSrcIsotropicPoint'
+    cu_refill_lanes = 6     # long launch path: launch jointly (mcsim._refill_lanes)
     _update_keys = ('position',)
 
     @staticmethod
