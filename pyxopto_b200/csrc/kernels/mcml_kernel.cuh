@@ -6,13 +6,16 @@
 // machine mapping:
 //   * one packet per thread, regenerated in place until the packet budget is
 //     exhausted, packet state entirely in registers;
-//   * deferred rare work: the long, rarely taken paths of the loop -- a layer
-//     interface (Fresnel, detector deposit, reload of the layer constants) and
-//     the launch of a new packet -- are not executed where they occur.  The lane
-//     parks in a PENDING state and idles until at least `refill` lanes of its
-//     warp are pending; then all of them run the deferred code together.  With
-//     one packet per lane these paths otherwise execute with 1-2 active lanes in
-//     most loop trips (ncu: 27 % of the issue slots of the 5-layer skin case);
+//   * warp launch queue (throughput mode): new packets are not launched by the
+//     lane that needs one.  When the queue of a warp is empty, all 32 lanes run
+//     the source code together (one atomic claims 32 packet indices) and park
+//     the launched packets in a per-warp shared-memory queue; a lane whose packet
+//     terminated pops one (3 LDS).  The long launch path therefore always runs
+//     with full warps instead of the 1-2 lanes that happen to need a packet;
+//   * deferred interface physics (throughput mode): a lane that hits a layer
+//     interface parks in a BND state and idles until at least `refill` lanes of
+//     its warp wait there (or nothing else runs); then they run Fresnel /
+//     detector deposit / reload of the layer constants together;
 //   * layer table (+ derived per-layer constants + pf lookup tables) staged once
 //     per CTA in shared memory; the constants of the *current* layer are cached
 //     in registers and reloaded only when the packet changes layer;
@@ -24,12 +27,12 @@
 //     racing atomic counter (mcml.template.c:460,790); throughput mode = the
 //     same counter, but claimed in chunks of `chunk` packets per atomic.
 //
-// Two loop bodies share the skeleton: the deterministic body evaluates the
-// reference's expressions in the reference's order with DetMath (bit-exact
-// against the oracle); the throughput body is the same physics re-associated
-// for the SM (step constants folded, one MUFU per transcendental, the boundary
-// division only on the divergent boundary path, Fresnel from a precomputed
-// index ratio).
+// Two loops share prologue and epilogue: the deterministic loop evaluates the
+// reference's expressions in the reference's order with DetMath, each work-item
+// launching its own packets from its own MWC stream (bit-exact against the
+// oracle); the throughput loop is the same physics re-associated for the SM
+// (step constants folded, one MUFU per transcendental, the boundary division
+// only on the divergent boundary path, Fresnel from a precomputed index ratio).
 //
 // The translation unit that includes this header must define the configuration:
 //   typedef ... XoPf; XoSource; XoDetTop; XoDetBottom; XoDetSpecular; XoFluence;
@@ -164,8 +167,9 @@ McKernel(
 	xo::u64 *accumulator_buffer,
 	xo::u32 lut_len,            // floats of fp_lut staged in shared memory (0: read global)
 	xo::u32 priv_len,           // accumulator bins privatised per CTA
-	xo::u32 chunk,              // packets claimed per atomic (throughput mode)
-	xo::u32 refill)             // pending lanes per warp that trigger the deferred work (1..32)
+	const __grid_constant__ xo::FluWindow window,   // fluence cells privatised per CTA
+	xo::u32 chunk,              // unused (kept for a stable argument list)
+	xo::u32 refill)             // lanes per warp waiting at an interface that trigger its joint handling
 {
 	using namespace xo;
 	extern __shared__ __align__(16) unsigned char xo_smem[];
@@ -213,6 +217,17 @@ McKernel(
 	acc.priv = reinterpret_cast<u32 *>(xo_smem) + off_words;
 	acc.priv_len = priv_len;
 	acc.zero_private();
+	acc.win = acc.priv + 2*priv_len;
+	const u32 win_len = window.ext0*window.ext1*window.ext2;
+	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
+#if !XO_DETERMINISTIC
+	// per-warp launch queue: 32 slots of {pos, weight | dir, packet | layer, trace count}
+	off_words += 2*priv_len + win_len;
+	off_words = (off_words + 3u) & ~3u;
+	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
+	float4 *q_b = q_a + 32;
+	u32 *q_l = reinterpret_cast<u32 *>(xo_smem) + off_words + blockDim.x*8u + (threadIdx.x & ~31u);
+#endif
 	__syncthreads();
 
 	const u32 gid = blockIdx.x*blockDim.x + threadIdx.x;
@@ -227,27 +242,10 @@ McKernel(
 	(void)rmax;
 #endif
 	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
-	(void)tcfg;
+	(void)tcfg; (void)chunk;
 
-	// ---- packet budget -------------------------------------------------------
-	Budget budget;
-	budget.dry = false;
-#if XO_DETERMINISTIC
-	static_quota(num_packets, gridDim.x*blockDim.x, gid, &budget.next, &budget.end);
-#else
-	budget.next = 0; budget.end = 0;
-#endif
-
-	// ---- lane state ------------------------------------------------------------
-	// RUN: a packet is in flight.  BND_*: the packet sits on the top / bottom
-	// interface of its layer, interface physics pending.  DEAD: needs a new
-	// packet.  DRY: no packets left for this lane.
-	enum : u32 { ST_RUN = 0, ST_BND_TOP = 1, ST_BND_BOTTOM = 2, ST_DEAD = 3, ST_DRY = 4 };
-	u32 state = ST_DEAD;
-	u32 n_dry = 0;                  // warp-uniform count of DRY lanes
 	bool started = false;
 	u32 iterations = 0;
-
 	// packet state (registers)
 	P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
 	float weight = 0.0f;
@@ -255,22 +253,7 @@ McKernel(
 	float opl = 0.0f;
 	u32 packet = 0, trace_count = 0, flags = 0;
 	(void)opl; (void)packet; (void)trace_count; (void)flags;
-#if !XO_DETERMINISTIC
-	// constants of the current layer (registers; reloaded on layer change)
-	MlHot c_hot = { 0.0f, 0.0f, 0.0f, 0.0f };
-	MlAux c_aux = { 0.0f, 1.0f, 0.0f, 0.0f };
-	XoPf::Fast c_pf;
-	(void)c_aux;
-#define XO_LOAD_LAYER(idx) do { \
-		const MlFastLayer &F_ = sh_fast[idx]; \
-		c_hot = F_.hot; c_pf = F_.pf.v; \
-		if (XO_NEEDS_OPL || XO_METHOD != 0 || XO_FLUENCE_RATE) c_aux = F_.aux; \
-	} while (0)
-#else
-#define XO_LOAD_LAYER(idx) do { } while (0)
-#endif
 
-	// end of a loop trip for this lane: rmax test, trace event, termination
 #if XO_USE_RMAX
 #define XO_RMAX_TEST() do { \
 		float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
@@ -291,6 +274,157 @@ McKernel(
 #else
 #define XO_TRACE_TRIP() do { } while (0)
 #endif
+
+#if XO_DETERMINISTIC
+	// ======== deterministic loop: reference expressions, reference order =========
+	// (mcml.template.c:456-816; one packet after the other from this work-item's
+	// static quota, launch and interface physics inline)
+	u32 pk_next, pk_end;
+	static_quota(num_packets, gridDim.x*blockDim.x, gid, &pk_next, &pk_end);
+	(void)refill;
+	if (pk_next < pk_end) {
+		started = true;
+		bool done = false;
+
+#define XO_LAUNCH_PACKET() do { \
+		Launch L_; \
+		packet = pk_next++; \
+		source.launch(rng, ctx, L_); \
+		pos = L_.pos; dir = L_.dir; weight = L_.weight; layer = L_.layer; \
+		if (XoDetSpecular::active) \
+			detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f); \
+		flags |= EV_LAUNCH; \
+		if (XO_TRACE & XO_TRACE_START) { \
+			if (trace_event(tcfg, float_buffer, packet, trace_count, flags, \
+					pos, dir, weight, opl)) ++trace_count; \
+		} \
+	} while (0)
+
+		XO_LAUNCH_PACKET();
+		while (!done) {
+			const MlLayer &L = sh_layers[layer];
+			float step;
+			++iterations;
+#if XO_METHOD == 2
+			step = M::div(-M::log(rng.next()), L.mus);
+#else
+			step = -M::log(rng.next())*L.inv_mut;
+#endif
+			step = fminf(step, XO_FLT_MAX);
+			i32 next_layer = layer;
+			const float top = L.top, bottom = L.bottom;
+			if (pos.z + step*dir.z < top) {
+				--next_layer;
+				if (fabsf(dir.z) != 0.0f) step = M::div(top - pos.z, dir.z);
+			}
+			if (pos.z + step*dir.z >= bottom) {
+				++next_layer;
+				if (fabsf(dir.z) != 0.0f) step = M::div(bottom - pos.z, dir.z);
+			}
+			pos.x = pos.x + dir.x*step;
+			pos.y = pos.y + dir.y*step;
+			pos.z = pos.z + dir.z*step;
+			if (XO_NEEDS_OPL) opl += L.n*step;
+			if (layer < next_layer) pos.z = bottom;
+			if (layer > next_layer) pos.z = top;
+#if XO_METHOD == 2
+			{   // microscopic Beer-Lambert (mcml.template.c:584-666)
+				float mua = L.mua;
+				float frac = 1.0f - M::exp(-mua*step);
+				float deposit = frac*weight;
+				weight -= deposit;
+				flags |= EV_ABSORPTION;
+				if (XoFluence::active) {
+					float back = (mua != 0.0f) ?
+						step - M::div(-M::log(1.0f - rng.next()*frac), mua) : 0.0f;
+					P3 dp = { pos.x - back*dir.x, pos.y - back*dir.y, pos.z - back*dir.z };
+					fluence.deposit(acc, window, dp, deposit, mua, opl);
+				}
+			}
+#endif
+			if (next_layer != layer) {
+				u32 bf = ml_boundary(L, sh_layers[next_layer], dir, layer, next_layer, rng);
+				flags |= bf | EV_BOUNDARY_HIT;
+				if (layer <= 0) {
+					if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
+					done = true;
+				} else if (layer >= (i32)num_layers - 1) {
+					if (XoDetBottom::active) detectors.bottom.deposit(acc, pos, dir, weight, opl);
+					done = true;
+				}
+			} else {
+#if XO_METHOD == 1
+				// albedo rejection (mcml.template.c:705-721)
+				if (rng.next() < L.mua_inv_mut) {
+					float deposit = weight;
+					done = true;
+					weight -= deposit;
+					flags |= EV_ABSORPTION;
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+				} else {
+					float fi, ct = L.pf.sample(rng, lut, &fi);
+					scatter_direction(dir, ct, fi);
+					flags |= EV_SCATTERING;
+				}
+#else
+#if XO_METHOD == 0
+				{   // albedo weight (mcml.template.c:722-731)
+					float deposit = weight*L.mua_inv_mut;
+					weight -= deposit;
+					flags |= EV_ABSORPTION;
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+				}
+#endif
+				float fi, ct = L.pf.sample(rng, lut, &fi);
+				scatter_direction(dir, ct, fi);
+				flags |= EV_SCATTERING;
+#endif
+			}
+#if XO_METHOD != 1
+			// survival lottery (mcml.template.c:737-753); for AW only after a
+			// scattering event, for MBL after every step
+			if ((XO_METHOD == 2 || !(flags & EV_BOUNDARY_HIT)) && weight < XO_WEIGHT_MIN) {
+#if XO_USE_LOTTERY
+				if (rng.next() > XO_LOTTERY_CHANCE) done = true;
+				else weight = M::div(weight, XO_LOTTERY_CHANCE);
+#else
+				done = true;
+#endif
+			}
+#endif
+			XO_RMAX_TEST();
+			XO_TRACE_TRIP();
+			flags = 0;
+			if (done && pk_next < pk_end) {
+				trace_count = 0;
+				opl = 0.0f;
+				XO_LAUNCH_PACKET();
+				done = false;
+			}
+		}
+	}
+#undef XO_LAUNCH_PACKET
+#else
+	// ======== throughput loop ======================================================
+	// Lane states.  RUN: a packet is in flight.  BND_*: the packet sits on the
+	// top / bottom interface of its layer, interface physics pending.  DEAD:
+	// needs a packet from the warp's launch queue.  DRY: no packets left.
+	enum : u32 { ST_RUN = 0, ST_BND_TOP = 1, ST_BND_BOTTOM = 2, ST_DEAD = 3, ST_DRY = 4 };
+	const u32 lane = threadIdx.x & 31u;
+	const u32 lanemask_lt = (1u << lane) - 1u;
+	u32 state = ST_DEAD;
+	u32 n_dry = 0, q_count = 0;     // warp-uniform
+	bool q_dry = false;             // warp-uniform: the packet budget is exhausted
+	// constants of the current layer (registers; reloaded on layer change)
+	MlHot c_hot = { 0.0f, 0.0f, 0.0f, 0.0f };
+	MlAux c_aux = { 0.0f, 1.0f, 0.0f, 0.0f };
+	XoPf::Fast c_pf;
+	(void)c_aux;
+#define XO_LOAD_LAYER(idx) do { \
+		const MlFastLayer &F_ = sh_fast[idx]; \
+		c_hot = F_.hot; c_pf = F_.pf.v; \
+		if (XO_NEEDS_OPL || XO_METHOD != 0 || XO_FLUENCE_RATE) c_aux = F_.aux; \
+	} while (0)
 #define XO_END_TRIP() do { \
 		XO_RMAX_TEST(); \
 		XO_TRACE_TRIP(); \
@@ -300,9 +434,8 @@ McKernel(
 #if XO_USE_LOTTERY
 #define XO_LOTTERY() do { \
 		if (weight < XO_WEIGHT_MIN) { \
-			if (rng.next() > XO_LOTTERY_CHANCE) done = true; \
-			else weight = XO_DETERMINISTIC ? M::div(weight, XO_LOTTERY_CHANCE) \
-				: weight*(1.0f/XO_LOTTERY_CHANCE); \
+			if (rng.next_raw() > XO_LOTTERY_CHANCE*4294967296.0f) done = true; \
+			else weight *= (1.0f/XO_LOTTERY_CHANCE); \
 		} \
 	} while (0)
 #else
@@ -310,27 +443,74 @@ McKernel(
 #endif
 
 	for (;;) {
-		const u32 n_run = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_RUN));
-		const u32 n_pending = 32u - n_dry - n_run;
-		if (n_pending >= refill || n_run == 0u) {
-			if (n_pending == 0u) break;         // every lane is DRY
-			// ======== deferred work, executed jointly by the pending lanes ========
-			if (state == ST_BND_TOP || state == ST_BND_BOTTOM) {
+		// ---- hand new packets to the lanes that need one -------------------------
+		const u32 dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
+		if (dead_mask != 0u) {
+			if (q_count == 0u && !q_dry) {
+				// queue empty: all 32 lanes launch one packet each into the queue
+				u32 base = 0;
+				if (lane == 0u) base = atomicAdd(num_packets_done, 32u);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				const u32 n_new = base < num_packets ?
+					(num_packets - base < 32u ? num_packets - base : 32u) : 0u;
+				q_dry = n_new < 32u;
+				if (lane < n_new) {
+					Launch L_;
+					source.launch(rng, ctx, L_);
+					if (XoDetSpecular::active)
+						detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
+					u32 tc = 0;
+					if (XO_TRACE & XO_TRACE_START) {
+						if (trace_event(tcfg, float_buffer, base + lane, 0u, EV_LAUNCH,
+								L_.pos, L_.dir, L_.weight, 0.0f)) tc = 1u;
+					}
+					q_a[lane] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
+					q_b[lane] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, __uint_as_float(base + lane));
+					q_l[lane] = (u32)L_.layer | (tc << 16);
+				}
+				__syncwarp();
+				q_count = n_new;
+			}
+			if (state == ST_DEAD) {
+				const u32 rank = (u32)__popc(dead_mask & lanemask_lt);
+				if (rank < q_count) {
+					const u32 slot = q_count - 1u - rank;
+					const float4 a = q_a[slot], b = q_b[slot];
+					const u32 l = q_l[slot];
+					pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
+					dir.x = b.x; dir.y = b.y; dir.z = b.z; packet = __float_as_uint(b.w);
+					layer = (i32)(l & 0xffffu); trace_count = l >> 16;
+					XO_LOAD_LAYER(layer);
+					opl = 0.0f;
+					flags = EV_LAUNCH;
+					state = ST_RUN;
+					started = true;
+				} else if (q_dry) {
+					state = ST_DRY;
+				}
+			}
+			const u32 n_dead = (u32)__popc(dead_mask);
+			q_count -= (n_dead < q_count) ? n_dead : q_count;
+			__syncwarp();
+			if (q_dry) {
+				n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
+				if (n_dry == 32u) break;
+			}
+		}
+		// ---- interface physics, executed jointly by the lanes waiting for it ------
+		const u32 bnd_mask = __ballot_sync(0xffffffffu, state - 1u < 2u);
+		if (bnd_mask != 0u) {
+			bool go = (u32)__popc(bnd_mask) >= refill;
+			if (!go) go = __ballot_sync(0xffffffffu, state == ST_RUN) == 0u;
+			if (go && state - 1u < 2u) {
 				const bool up = (state == ST_BND_TOP);
 				bool done = false;
-#if XO_DETERMINISTIC
-				const i32 next_layer = up ? layer - 1 : layer + 1;
-				u32 bf = ml_boundary(sh_layers[layer], sh_layers[next_layer], dir, layer, next_layer, rng);
-				flags |= bf | EV_BOUNDARY_HIT;
-				const bool through = (layer == next_layer);
-#else
 				const MlIface I = sh_fast[layer].iface;
 				const bool through = ml_boundary_fast(up ? I.n12_top : I.n12_bottom,
 					up ? I.cc_top : I.cc_bottom, dir, rng);
 				flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
-				if (through) layer += up ? -1 : 1;
-#endif
 				if (through) {
+					layer += up ? -1 : 1;
 					if (layer <= 0) {
 						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
 						done = true;
@@ -346,112 +526,11 @@ McKernel(
 #endif
 				XO_END_TRIP();
 			}
-			if (state == ST_DEAD) {
-				if (budget.claim(num_packets, num_packets_done, chunk, &packet)) {
-					Launch L_;
-					source.launch(rng, ctx, L_);
-					pos = L_.pos; dir = L_.dir; weight = L_.weight; layer = L_.layer;
-					if (XoDetSpecular::active)
-						detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
-					XO_LOAD_LAYER(layer);
-					opl = 0.0f;
-					trace_count = 0;
-					flags = EV_LAUNCH;
-					if (XO_TRACE & XO_TRACE_START) {
-						if (trace_event(tcfg, float_buffer, packet, trace_count, flags,
-								pos, dir, weight, opl)) ++trace_count;
-					}
-					state = ST_RUN;
-					started = true;
-				} else {
-					state = ST_DRY;
-				}
-			}
-			n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
-			continue;
 		}
 		if (state != ST_RUN) continue;
 
+		// ---- one step of the packet ----------------------------------------------------
 		++iterations;
-#if XO_DETERMINISTIC
-		// ======== deterministic body: reference expressions, reference order ====
-		const MlLayer &L = sh_layers[layer];
-		float step;
-#if XO_METHOD == 2
-		step = M::div(-M::log(rng.next()), L.mus);
-#else
-		step = -M::log(rng.next())*L.inv_mut;
-#endif
-		step = fminf(step, XO_FLT_MAX);
-		i32 next_layer = layer;
-		const float top = L.top, bottom = L.bottom;
-		if (pos.z + step*dir.z < top) {
-			--next_layer;
-			if (fabsf(dir.z) != 0.0f) step = M::div(top - pos.z, dir.z);
-		}
-		if (pos.z + step*dir.z >= bottom) {
-			++next_layer;
-			if (fabsf(dir.z) != 0.0f) step = M::div(bottom - pos.z, dir.z);
-		}
-		pos.x = pos.x + dir.x*step;
-		pos.y = pos.y + dir.y*step;
-		pos.z = pos.z + dir.z*step;
-		if (XO_NEEDS_OPL) opl += L.n*step;
-		if (layer < next_layer) pos.z = bottom;
-		if (layer > next_layer) pos.z = top;
-#if XO_METHOD == 2
-		{   // microscopic Beer-Lambert (mcml.template.c:584-666)
-			float mua = L.mua;
-			float frac = 1.0f - M::exp(-mua*step);
-			float deposit = frac*weight;
-			weight -= deposit;
-			flags |= EV_ABSORPTION;
-			if (XoFluence::active) {
-				float back = (mua != 0.0f) ?
-					step - M::div(-M::log(1.0f - rng.next()*frac), mua) : 0.0f;
-				P3 dp = { pos.x - back*dir.x, pos.y - back*dir.y, pos.z - back*dir.z };
-				fluence.deposit(acc, dp, deposit, mua, opl);
-			}
-		}
-#endif
-		if (next_layer != layer) {
-			// interface physics deferred (mcml.template.c:669-703)
-			state = (next_layer < layer) ? ST_BND_TOP : ST_BND_BOTTOM;
-			continue;
-		}
-		bool done = false;
-#if XO_METHOD == 1
-		// albedo rejection (mcml.template.c:705-721)
-		if (rng.next() < L.mua_inv_mut) {
-			float deposit = weight;
-			done = true;
-			weight -= deposit;
-			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit(acc, pos, deposit, L.mua, opl);
-		} else {
-			float fi, ct = L.pf.sample(rng, lut, &fi);
-			scatter_direction(dir, ct, fi);
-			flags |= EV_SCATTERING;
-		}
-#else
-#if XO_METHOD == 0
-		{   // albedo weight (mcml.template.c:722-731)
-			float deposit = weight*L.mua_inv_mut;
-			weight -= deposit;
-			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit(acc, pos, deposit, L.mua, opl);
-		}
-#endif
-		float fi, ct = L.pf.sample(rng, lut, &fi);
-		scatter_direction(dir, ct, fi);
-		flags |= EV_SCATTERING;
-		// survival lottery (mcml.template.c:737-753); for AW only after a
-		// scattering event, for MBL after every step
-		XO_LOTTERY();
-#endif
-		XO_END_TRIP();
-#else
-		// ======== throughput body ===============================================
 		float step = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
 		const float zs = fmaf(step, dir.z, pos.z);
 		const bool hit_top = zs < c_hot.top;
@@ -476,7 +555,7 @@ McKernel(
 				float back = (c_aux.mua != 0.0f) ?
 					step + FastMath::log(1.0f - rng.next()*frac)*FastMath::rcp_approx(c_aux.mua) : 0.0f;
 				P3 dp = { pos.x - back*dir.x, pos.y - back*dir.y, pos.z - back*dir.z };
-				fluence.deposit(acc, dp, deposit, c_aux.mua, opl);
+				fluence.deposit(acc, window, dp, deposit, c_aux.mua, opl);
 			}
 		}
 #endif
@@ -491,7 +570,7 @@ McKernel(
 			done = true;
 			weight = 0.0f;
 			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit(acc, pos, deposit, c_aux.mua, opl);
+			if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_aux.mua, opl);
 		} else {
 			float fi, ct = c_pf.sample(rng, lut, &fi);
 			scatter_direction(dir, ct, fi);
@@ -503,7 +582,7 @@ McKernel(
 			float deposit = weight*c_hot.absorb;
 			weight -= deposit;
 			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit(acc, pos, deposit, c_aux.mua, opl);
+			if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_aux.mua, opl);
 		}
 #endif
 		float fi, ct = c_pf.sample(rng, lut, &fi);
@@ -512,15 +591,20 @@ McKernel(
 		XO_LOTTERY();
 #endif
 		XO_END_TRIP();
-#endif  // XO_DETERMINISTIC
 	}
 #undef XO_LOAD_LAYER
-#undef XO_RMAX_TEST
-#undef XO_TRACE_TRIP
 #undef XO_END_TRIP
 #undef XO_LOTTERY
+	// every lane drew from its stream (queue refills), whether or not it ever
+	// carried a packet: all states go back
+	rng_state_x[gid] = rng.x;
+#endif  // XO_DETERMINISTIC
+#undef XO_RMAX_TEST
+#undef XO_TRACE_TRIP
 	if (started) {
+#if XO_DETERMINISTIC
 		rng_state_x[gid] = rng.x;
+#endif
 		atomicAdd(num_kernels, 1u);
 	}
 	// loop-trip count (the roofline's unit of work): one 64-bit RED per warp
@@ -532,6 +616,7 @@ McKernel(
 
 	__syncthreads();
 	acc.flush_private();
+	if (XoFluence::active) flush_window(fluence, acc, window);
 #if XO_DETERMINISTIC
 	if (gid == 0) *num_packets_done = num_packets;
 #endif

@@ -115,6 +115,7 @@ McKernel(
 	xo::u64 *accumulator_buffer,
 	xo::u32 lut_len,
 	xo::u32 priv_len,
+	const __grid_constant__ xo::FluWindow window,
 	xo::u32 chunk)
 {
 	using namespace xo;
@@ -140,6 +141,8 @@ McKernel(
 	acc.priv = reinterpret_cast<u32 *>(xo_smem) + off_words;
 	acc.priv_len = priv_len;
 	acc.zero_private();
+	acc.win = acc.priv + 2*priv_len;
+	for (u32 i = threadIdx.x; i < window.ext0*window.ext1*window.ext2; i += blockDim.x) acc.win[i] = 0;
 	__syncthreads();
 
 	const u32 gid = blockIdx.x*blockDim.x + threadIdx.x;
@@ -228,7 +231,7 @@ McKernel(
 					float back = (mua != 0.0f) ?
 						d_ok - M::div(-M::log(1.0f - rng.next()*frac), mua) : 0.0f;
 					P3 dp = { pos.x - back*dir.x, pos.y - back*dir.y, pos.z - back*dir.z };
-					fluence.deposit(acc, dp, deposit, mua, opl);
+					fluence.deposit(acc, window, dp, deposit, mua, opl);
 				}
 			}
 #endif
@@ -286,7 +289,7 @@ McKernel(
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
 					done = true;
-					if (XoFluence::active) fluence.deposit(acc, pos, deposit, Mt.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua, opl);
 				} else {
 					float fi, ct = Mt.pf.sample(rng, lut, &fi);
 					scatter_direction(dir, ct, fi);
@@ -298,7 +301,7 @@ McKernel(
 					float deposit = weight*Mt.mua_inv_mut;
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
-					if (XoFluence::active) fluence.deposit(acc, pos, deposit, Mt.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua, opl);
 				}
 #endif
 				float fi, ct = Mt.pf.sample(rng, lut, &fi);
@@ -360,6 +363,7 @@ McKernel(
 	}
 	__syncthreads();
 	acc.flush_private();
+	if (XoFluence::active) flush_window(fluence, acc, window);
 #if XO_DETERMINISTIC
 	if (gid == 0) *num_packets_done = num_packets;
 #endif

@@ -13,8 +13,19 @@ struct FluNone {
 	i32 dummy;
 	static constexpr bool active = false;
 	static constexpr bool needs_opl = false;
-	__device__ __forceinline__ void deposit(const Accu &, const P3 &, float, float, float) const {}
+	__device__ __forceinline__ void deposit(const Accu &, const FluWindow &, const P3 &, float, float, float) const {}
+	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 };
+
+// adds the CTA-private window back into the global grid (end of the kernel)
+template <class Flu>
+__device__ __forceinline__ void flush_window(const Flu &flu, const Accu &acc, const FluWindow &win) {
+	const u32 n = win.ext0*win.ext1*win.ext2;
+	for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+		u32 v = acc.win[i];
+		if (v) atomicAdd(acc.global + flu.window_index(win, i), (u64)v);
+	}
+}
 
 #ifndef XO_FLUENCE_RATE
 #define XO_FLUENCE_RATE 0
@@ -37,15 +48,29 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 	P3 inv_step, top_left; u32 nx, ny, nz, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
-	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, float w, float mua, float) const {
-		float fx = (pos.x - top_left.x)*inv_step.x;
-		float fy = (pos.y - top_left.y)*inv_step.y;
-		float fz = (pos.z - top_left.z)*inv_step.z;
-		if (fx >= 0.0f && fy >= 0.0f && fz >= 0.0f &&
-				fx < (float)nx && fy < (float)ny && fz < (float)nz) {
-			u32 index = (f2u(fz)*ny + f2u(fy))*nx + f2u(fx);
-			acc.add_global(offset + index, fluence_weight(w, mua, k));
+	// The reference tests 0 <= f < n in floating point and then truncates
+	// (fluence.py:103-143).  floor-conversion + one unsigned compare per axis is
+	// the same predicate for every non-NaN f: negative f floors to a negative
+	// integer (huge as unsigned), f >= n converts to >= n or saturates.
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float) const {
+		u32 ix = (u32)__float2int_rd((pos.x - top_left.x)*inv_step.x);
+		u32 iy = (u32)__float2int_rd((pos.y - top_left.y)*inv_step.y);
+		u32 iz = (u32)__float2int_rd((pos.z - top_left.z)*inv_step.z);
+		if (ix < nx && iy < ny && iz < nz) {
+			u32 lx = ix - win.org0, ly = iy - win.org1, lz = iz - win.org2;
+			u32 iw = fluence_weight(w, mua, k);
+			if (lx < win.ext0 && ly < win.ext1 && lz < win.ext2) {
+				if (acc.add_window((lz*win.ext1 + ly)*win.ext0 + lx, iw))
+					acc.carry_global(offset + (iz*ny + iy)*nx + ix);
+			} else {
+				acc.add_global(offset + (iz*ny + iy)*nx + ix, iw);
+			}
 		}
+	}
+	__device__ __forceinline__ u32 window_index(const FluWindow &win, u32 local) const {
+		u32 lx = local % win.ext0, t = local/win.ext0;
+		u32 ly = t % win.ext1, lz = t/win.ext1;
+		return offset + ((lz + win.org2)*ny + (ly + win.org1))*nx + lx + win.org0;
 	}
 };
 
@@ -53,15 +78,25 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 	P3 center; float inv_dr, inv_dz; u32 n_r, n_z, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
-	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, float w, float mua, float) const {
+	// bounds test in the integer domain, see FluXyz::deposit (fluencerz.py:112-160)
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float) const {
 		float dx = pos.x - center.x, dy = pos.y - center.y;
 		float r = M::sqrt(dx*dx + dy*dy);
 		float dz = pos.z - center.z;
-		float fr = r*inv_dr, fz = dz*inv_dz;
-		if (fr >= 0.0f && fz >= 0.0f && fr < (float)n_r && fz < (float)n_z) {
-			u32 index = f2u(fz)*n_r + f2u(fr);
-			acc.add_global(offset + index, fluence_weight(w, mua, k));
+		u32 ir = (u32)__float2int_rd(r*inv_dr), iz = (u32)__float2int_rd(dz*inv_dz);
+		if (ir < n_r && iz < n_z) {
+			u32 lr = ir - win.org0, lz = iz - win.org1;
+			u32 iw = fluence_weight(w, mua, k);
+			if (lr < win.ext0 && lz < win.ext1) {
+				if (acc.add_window(lz*win.ext0 + lr, iw)) acc.carry_global(offset + iz*n_r + ir);
+			} else {
+				acc.add_global(offset + iz*n_r + ir, iw);
+			}
 		}
+	}
+	__device__ __forceinline__ u32 window_index(const FluWindow &win, u32 local) const {
+		u32 lr = local % win.ext0, lz = local/win.ext0;
+		return offset + (lz + win.org1)*n_r + lr + win.org0;
 	}
 };
 
@@ -69,7 +104,8 @@ struct FluXyzt {                    // mcfluence/fluencet.py:57-63
 	float inv_step[4], top_left[4]; u32 shape[4]; u32 offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = true;
-	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, float w, float mua, float opl) const {
+	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float opl) const {
 		float fx = (pos.x - top_left[0])*inv_step[0];
 		float fy = (pos.y - top_left[1])*inv_step[1];
 		float fz = (pos.z - top_left[2])*inv_step[2];

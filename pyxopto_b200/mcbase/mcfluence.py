@@ -53,6 +53,21 @@ class _FluenceBase(McObject):
             self._data.shape = self.shape
             self._nphotons = nphotons
 
+    def cu_window(self, mc, max_bins: int, focus):
+        """(org0, org1, org2, ext0, ext1, ext2): block of grid cells around the
+        point ``focus`` (source position) that each CTA accumulates in shared
+        memory (xo::FluWindow); at most ``max_bins`` cells.  Default: none."""
+        return (0, 0, 0, 0, 0, 0)
+
+    @staticmethod
+    def _window_axis(axis, n_want: int, at: float, lead: float = 0.25):
+        """First cell and cell count of a window of ~n_want cells of ``axis``
+        placed so that ``at`` lies ``lead`` of the way into it."""
+        n = int(min(max(n_want, 1), axis.n))
+        i_at = int(np.floor((at - axis.start)/axis.step)) if axis.step != 0.0 else 0
+        first = int(min(max(i_at - int(lead*n), 0), axis.n - n))
+        return first, n
+
     def update(self, obj):
         if self._data is not None:
             if self.shape != obj.shape:
@@ -121,6 +136,21 @@ class Fluence(_FluenceBase):
             setattr(target.shape, c, ax.n)
         target.k = self._k
         return target
+
+    def cu_window(self, mc, max_bins: int, focus):
+        axes = (self._x_axis, self._y_axis, self._z_axis)
+        steps = [abs(a.step) for a in axes]
+        if max_bins < 8 or min(steps) <= 0.0:
+            return (0, 0, 0, 0, 0, 0)
+        # cube of equal physical edge, clipped to the grid; spare cells go to z
+        edge = (max_bins*steps[0]*steps[1]*steps[2])**(1.0/3.0)
+        nx = int(min(max(edge//steps[0], 1), axes[0].n))
+        ny = int(min(max(edge//steps[1], 1), axes[1].n))
+        nz = int(min(max(max_bins//(nx*ny), 1), axes[2].n))
+        x0, nx = self._window_axis(axes[0], nx, focus[0], 0.5)
+        y0, ny = self._window_axis(axes[1], ny, focus[1], 0.5)
+        z0, nz = self._window_axis(axes[2], nz, focus[2], 0.25)
+        return (x0, y0, z0, nx, ny, nz)
 
     def todict(self):
         return {'type': 'Fluence', 'mode': self._mode, 'xaxis': self._x_axis.todict(),
@@ -212,6 +242,20 @@ class FluenceRz(_FluenceBase):
         target.n_r, target.n_z = self._r_axis.n, self._z_axis.n
         target.k = self._k
         return target
+
+    def cu_window(self, mc, max_bins: int, focus):
+        dr, dz = abs(self._r_axis.step), abs(self._z_axis.step)
+        if max_bins < 4 or dr <= 0.0 or dz <= 0.0:
+            return (0, 0, 0, 0, 0, 0)
+        # physical window R x 2R (radius x depth), clipped to the grid
+        radius = np.sqrt(max_bins*dr*dz/2.0)
+        n_r = int(min(max(radius//dr, 1), self._r_axis.n))
+        n_z = int(min(max(max_bins//n_r, 1), self._z_axis.n))
+        n_r = int(min(max(max_bins//n_z, 1), self._r_axis.n))
+        rc = float(np.hypot(focus[0] - self._center[0], focus[1] - self._center[1]))
+        r0, n_r = self._window_axis(self._r_axis, n_r, rc, 0.5)
+        z0, n_z = self._window_axis(self._z_axis, n_z, focus[2], 0.25)
+        return (r0, z0, 0, n_r, n_z, 1)
 
     def todict(self):
         return {'type': 'FluenceRz', 'mode': self._mode, 'raxis': self._r_axis.todict(),

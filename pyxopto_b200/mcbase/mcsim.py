@@ -20,6 +20,10 @@ from . import mcoptions, mctypes
 from .mcworker import CuWorker, compile_kernel
 
 DEFAULT_BLOCK = 256
+# with a fluence grid one 1024-thread CTA per SM shares a single large window of
+# the grid in shared memory (xo::FluWindow)
+FLUENCE_BLOCK = 1024
+SHARED_RESERVE = 2048            # static shared memory + driver reserve per CTA
 PRIVATE_BINS_MAX = 4096          # detector bins privatised per CTA (32 KB)
 LUT_SHARED_MAX_BYTES = 64*1024   # pf lookup tables staged in shared memory
 
@@ -191,6 +195,7 @@ class McBase(CuWorker):
     # idle lanes per warp that trigger a joint launch (throughput mode); sources
     # with a long launch path amortise it over more lanes
     refill_lanes = None
+    min_blocks = 1                   # __launch_bounds__ second argument
     chunk_max = 16
 
     def _refill_lanes(self) -> int:
@@ -227,6 +232,36 @@ class McBase(CuWorker):
                               extra_options=self._cl_build_options)
 
     # -- launch ----------------------------------------------------------------
+    def _source_focus(self):
+        pos = getattr(self._source, 'position', None)
+        if pos is None:
+            return (0.0, 0.0, 0.0)
+        return tuple(float(v) for v in np.asarray(pos, dtype=np.float64).reshape(-1)[:3])
+
+    fluence_window_bytes = None      # None: automatic
+    fluence_block = FLUENCE_BLOCK
+
+    def _fluence_window(self, block: int, base_bytes: int):
+        """xo::FluWindow (6 x uint32) for the current fluence plugin."""
+        none = np.zeros(6, dtype=np.uint32)
+        if self._fluence is None or not hasattr(self._fluence, 'cu_window'):
+            return none
+        budget = self.fluence_window_bytes
+        if budget is None:
+            cap = self._ctx.info['max_shared_per_block_optin'] if self._ctx is not None \
+                else 227*1024
+            if block >= 512:
+                # 1024 threads per SM: one CTA of 1024 or two of 512
+                budget = cap//(1024//min(block, 1024)) - SHARED_RESERVE - base_bytes
+            else:
+                budget = 40*1024 - base_bytes
+        bins = int(max(budget, 0))//4
+        win = self._fluence.cu_window(self, bins, self._source_focus())
+        win = np.asarray(win, dtype=np.uint32)
+        if int(win[3])*int(win[4])*int(win[5]) > bins:
+            return none
+        return win
+
     def _shared_layout(self, medium_bytes: int):
         """(dynamic shared bytes, lut floats staged, private bins)."""
         lut_len = 0
@@ -245,7 +280,7 @@ class McBase(CuWorker):
         words += 2*priv_len
         return words*4 + 16, lut_len, priv_len
 
-    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill):
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill, window):
         raise NotImplementedError
 
     def _medium_bytes(self) -> int:
@@ -274,9 +309,14 @@ class McBase(CuWorker):
         t0 = time.perf_counter()
         self._ensure_device()
         self._pack(nphotons)
-        block = int(wgsize) if wgsize else DEFAULT_BLOCK
         deterministic = self.deterministic
-        src = self.kernel_source(block=block, min_blocks=1)
+        if wgsize:
+            block = int(wgsize)
+        elif self._fluence is not None and not deterministic:
+            block = self.fluence_block
+        else:
+            block = DEFAULT_BLOCK
+        src = self.kernel_source(block=block, min_blocks=int(self.min_blocks))
         self._last_src = src
         if exportsrc:
             with open(exportsrc, 'w') as f:
@@ -299,6 +339,9 @@ class McBase(CuWorker):
         fbuf = self._rw_flat_buffer('float')
         ibuf = self._rw_flat_buffer('int')
         shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
+        queue_bytes = 0 if deterministic else 36*block + 16   # per-warp launch queues
+        window = self._fluence_window(block, shared + queue_bytes)
+        shared += 4*int(window[3])*int(window[4])*int(window[5]) + queue_bytes
         grid, block = self.launch_geometry(kernel, block, shared, maxthreads)
         nthreads = grid*block
         if deterministic:
@@ -311,7 +354,7 @@ class McBase(CuWorker):
                     rng_x=self._cl_buffers['rng_seeds_x'],
                     rng_a=self._cl_buffers['rng_seeds_a'])
         refill = 1 if deterministic else self._refill_lanes()
-        args = self._kernel_args(nphotons, bufs, lut_len, priv_len, chunk, refill)
+        args = self._kernel_args(nphotons, bufs, lut_len, priv_len, chunk, refill, window)
         t_up = time.perf_counter()
 
         ev0, ev1 = self._events
@@ -339,7 +382,7 @@ class McBase(CuWorker):
             'iterations': int(counters[2:4].view(np.uint64)[0]),
             'launched_threads': nthreads, 'grid': grid, 'block': block,
             'shared_bytes': shared, 'private_bins': priv_len, 'lut_shared': lut_len,
-            'chunk': chunk, 'refill': refill, 'items': nphotons, 'cache_hit': mod.cache_hit,
+            'chunk': chunk, 'refill': refill, 'fluence_window': [int(v) for v in window], 'items': nphotons, 'cache_hit': mod.cache_hit,
             'kernel_attributes': kernel.attributes(),
         }
         if verbose:

@@ -89,7 +89,7 @@ class Mc(McBase):
         return checks
 
     # -- launch ---------------------------------------------------------------------
-    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill):
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill, window):
         from . import mcdetector as md
         T = self._types
         if self._detectors is not None:
@@ -109,6 +109,6 @@ class Mc(McBase):
             self._packed_or_dummy('fluence', 4),
             dets,
             bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
-            np.uint32(lut_len), np.uint32(priv_len), np.uint32(max(chunk, 1)),
+            np.uint32(lut_len), np.uint32(priv_len), window, np.uint32(max(chunk, 1)),
             np.uint32(refill),
         ]

@@ -22,6 +22,7 @@ from . import mcgeometry, mcsource                 # noqa: F401
 
 class Mc(McBase):
     kernel_header = 'mcvox_kernel.cuh'
+    fluence_block = 512      # the voxel kernel needs > 64 registers per thread
     geometry = 'mcvox'
 
     def __init__(self, voxels, materials, source, detectors=None, trace=None,
@@ -106,7 +107,7 @@ class Mc(McBase):
         return checks
 
     # -- launch ---------------------------------------------------------------------
-    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill):
+    def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill, window):
         if self._detectors is not None:
             dets = self._packed['detectors']
         else:
@@ -125,5 +126,5 @@ class Mc(McBase):
             self._packed_or_dummy('fluence', 4),
             dets,
             bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
-            np.uint32(lut_len), np.uint32(priv_len), np.uint32(max(chunk, 1)),
+            np.uint32(lut_len), np.uint32(priv_len), window, np.uint32(max(chunk, 1)),
         ]

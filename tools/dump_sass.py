@@ -7,7 +7,8 @@ import benchcfg
 name = sys.argv[1]
 mc = importlib.import_module('pyxopto_b200.%s.mc' % benchcfg.GEOMETRY[name])
 sim = benchcfg.CONFIGS[name](mc)
-cubin, log, hit = sim.compile(1000, block=256)
+block = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+cubin, log, hit = sim.compile(1000, block=block)
 path = '/tmp/%s.cubin' % name
 open(path, 'wb').write(cubin)
 out = sys.argv[2] if len(sys.argv) > 2 else '/tmp/%s.sass' % name
