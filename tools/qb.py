@@ -1,15 +1,17 @@
-import sys, time
-sys.path.insert(0,'/root/repo')
+"""Developer timing probe: python tools/qb.py config n [wgsize]"""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import benchcfg
 import importlib
 name = sys.argv[1]; n = int(float(sys.argv[2]))
+kw = {'wgsize': int(sys.argv[3])} if len(sys.argv) > 3 else {}
 mc = importlib.import_module("pyxopto_b200.%s.mc" % benchcfg.GEOMETRY[name]); sim = benchcfg.CONFIGS[name](mc)
-sim.run(10000, download=False)
+sim.run(10000, download=False, **kw)
 for i in range(3):
-    sim.run(n, download=False)
+    sim.run(n, download=False, **kw)
     rr = sim.run_report
-    print(name, 'n=%.0e kernel %.2f ms -> %.3e packets/s, %.1f iter/packet, %.3e iter/s | grid %d x %d regs %d smem %d priv %d chunk %d' % (n, rr['kernel_ms'], n/rr['kernel_ms']*1e3, rr['iterations']/n, rr['iterations']/rr['kernel_ms']*1e3, rr['grid'], rr['block'], rr['kernel_attributes']['num_regs'], rr['shared_bytes'], rr['private_bins'], rr['chunk']), flush=True)
-t=time.perf_counter(); tr, fl, det = sim.run(n); dt=time.perf_counter()-t
+    print(name, 'n=%.0e kernel %.2f ms -> %.3e packets/s, %.1f iter/packet, %.3e iter/s | grid %d x %d regs %d smem %d priv %d win %s' % (n, rr['kernel_ms'], n/rr['kernel_ms']*1e3, rr['iterations']/n, rr['iterations']/rr['kernel_ms']*1e3, rr['grid'], rr['block'], rr['kernel_attributes']['num_regs'], rr['shared_bytes'], rr['private_bins'], rr['fluence_window']), flush=True)
+t=time.perf_counter(); tr, fl, det = sim.run(n, **kw); dt=time.perf_counter()-t
 print('e2e run %.3f s -> %.3e packets/s' % (dt, n/dt), {k: (round(v,4) if isinstance(v,float) else v) for k,v in sim.run_report.items() if k in ('upload','execution','download','build')})
 print("det", None if det is None else det.top.raw.sum()/n)
 if fl is not None: print('fluence total', fl.raw.sum()/n)
