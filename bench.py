@@ -133,6 +133,8 @@ def main():
         'c1_slab': 'mcml single slab mua=1/cm mus=100/cm g=0.8 n=1.33, Line + Radial',
         'c3_vox': 'mcvox 201^3 voxel 2-layer skin + blood vessel (5 um voxels), '
                   'GaussianBeam sigma 50 um, Fluence deposition grid',
+        'c5_cyl': 'mccyl single cylinder r=5 mm n=1.337 mua=1/cm mus=100/cm g=0.8, '
+                  'Line + FiZ 64x100',
     }.get(config, config)
 
     # ---------------- reference arm: the reference kernel on host cores --------
@@ -224,7 +226,7 @@ def main():
     h2d = d2h = 0
     for _ in range(args.steps):
         trace, fluence, detectors = sim.run(packets)
-        checksum = (float(detectors.top.raw.sum()) if detectors is not None else 0.0) + \
+        checksum = sum(float(d.raw.sum()) for d in (detectors or ()) if hasattr(d, 'raw')) + \
             (float(fluence.raw.sum()) if fluence is not None else 0.0)
     barrier()
     t3 = time.perf_counter()

@@ -106,3 +106,30 @@ def c3_vox(mc, rnginit=RNGINIT, n=201, **kw):
 CONFIGS['c3_vox'] = c3_vox
 GEOMETRY['c3_vox'] = 'mcvox'
 PACKETS['c3_vox'] = 10**8
+
+
+def c5_cyl(mc, rnginit=RNGINIT, **kw):
+    """BASELINE configs[4], mccyl variant: one cylinder of radius
+    5 mm (water, n = 1.337) in air, Line source along +x through the axis,
+    FiZ(64 x 100) detector on the outer surface."""
+    Axis = mc.mcdetector.Axis
+    L = mc.mclayer.Layer
+    pf = mc.mcpf.Hg(0.8)
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=10e-3, n=1.337, mua=1e2, mus=100e2, pf=pf)])
+    det = mc.mcdetector.Detectors(
+        outer=mc.mcdetector.FiZ(Axis(-np.pi, np.pi, 64), Axis(-5e-3, 5e-3, 100)))
+    sim = mc.Mc(layers, mc.mcsource.Line((-10e-3, 0.0, 0.0), (1.0, 0.0, 0.0)), det,
+                rnginit=rnginit, **kw)
+    sim.rmax = 25e-3
+    return sim
+
+
+CONFIGS['c5_cyl'] = c5_cyl
+GEOMETRY['c5_cyl'] = 'mccyl'
+PACKETS['c5_cyl'] = 10**7
+# mcml AW + Hg (85, 11) with the two plane tests (4 ALU) replaced by the ray /
+# cylinder quadratic of mccyl.template.c:147-209: a, b, c (9), 1/2a (1 + 1 MUFU),
+# outer discriminant + root (6 + 1 MUFU), inner discriminant test (4)
+OPS_PER_ITERATION['c5_cyl'] = (101, 13)

@@ -83,8 +83,10 @@ typedef struct { p3f direction; p2f position; float r_min, inv_dr, pl_min, inv_d
 	uint32_t n_r, n_pl, offset; int32_t r_log_scale, pl_log_scale; } det_radialpl;
 typedef struct { p3f direction; float cos_min, pl_min, inv_dpl;
 	uint32_t n_pl, offset; int32_t pl_log_scale; } det_totalpl;
-typedef struct { p3f direction; float fi_min, inv_dfi, z_min, inv_dz, cos_min;
+/* mccyl/mcdetector/fiz.py:44-56 (pack=1), mccyl/mcdetector/total.py:44-50 */
+typedef struct { float fi_min, inv_dfi, z_min, inv_dz, cos_min;
 	uint32_t n_fi, n_z, offset; } det_fiz;
+typedef struct { float cos_min; uint32_t offset; } det_total_cyl;
 
 typedef struct { p3f inv_step, top_left; uint32_t nx, ny, nz, offset; int32_t k; } flu_xyz;
 typedef struct { p3f center; float inv_dr, inv_dz; uint32_t n_r, n_z, offset; int32_t k; } flu_rz;
@@ -439,6 +441,28 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		if (w > 0) accu_deposit(s, d->offset + (uint32_t)pi, w);
 		break;
 	}
+	case XO_DET_FIZ: {                                 /* mccyl/mcdetector/fiz.py:86-120 */
+		const det_fiz *d = (const det_fiz *)base;
+		float fi = m_atan2(s, pos->y, pos->x);
+		int32_t index_fi = iclip((int32_t)((fi - d->fi_min)*d->inv_dfi), 0, (int32_t)(d->n_fi - 1));
+		int32_t index_z = iclip((int32_t)((pos->z - d->z_min)*d->inv_dz), 0, (int32_t)(d->n_z - 1));
+		uint32_t index = (uint32_t)index_z*d->n_fi + (uint32_t)index_fi;
+		float k = m_sqrt(pos->x*pos->x + pos->y*pos->y);
+		k = (k > FP_0) ? m_div(FP_1, k) : FP_0;
+		p3f normal = { pos->x*k, pos->y*k, FP_0 };
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &normal)));
+		if (w > 0) accu_deposit(s, index + d->offset, w);
+		break;
+	}
+	case XO_DET_TOTAL_CYL: {                           /* mccyl/mcdetector/total.py:75-100 */
+		const det_total_cyl *d = (const det_total_cyl *)base;
+		float r = m_sqrt(pos->x*pos->x + pos->y*pos->y);
+		float k = (r > FP_0) ? m_div(FP_1, r) : FP_0;
+		p3f normal = { pos->x*k, pos->y*k, FP_0 };
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &normal)));
+		if (w > 0) accu_deposit(s, d->offset, w);
+		break;
+	}
 	default: break;
 	}
 }
@@ -643,6 +667,7 @@ static inline p3f source_position(const xo_oracle_job *j) {
 	switch (j->src_kind) {
 		case XO_SRC_GAUSSIANBEAM: off = sizeof(m3f); break;
 		case XO_SRC_UNIFORMFIBER: off = sizeof(m3f); break;
+		case XO_SRC_UNIFORMBEAM: off = sizeof(m3f); break;
 		default: off = 0; break;
 	}
 	return *(const p3f *)((const char *)j->source + off);

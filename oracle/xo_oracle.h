@@ -25,7 +25,7 @@ enum {
 	XO_DET_NONE = 0, XO_DET_TOTAL = 1, XO_DET_RADIAL = 2, XO_DET_CARTESIAN = 3,
 	XO_DET_SIXAROUNDONE = 4, XO_DET_RADIALPL = 5, XO_DET_TOTALPL = 6,
 	XO_DET_SYMMETRICX = 7, XO_DET_FIZ = 8, XO_DET_CARTESIANPL = 9,
-	XO_DET_SIXAROUNDONEPL = 10
+	XO_DET_SIXAROUNDONEPL = 10, XO_DET_TOTAL_CYL = 11
 };
 enum {
 	XO_FLU_NONE = 0, XO_FLU_XYZ = 1, XO_FLU_RZ = 2, XO_FLU_XYZT = 3,

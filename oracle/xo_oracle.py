@@ -30,6 +30,7 @@ SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
             'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10}
+DET_KIND_TOTAL_CYL = 11
 FLU_KIND = {'NoneType': 0, 'Fluence': 1, 'FluenceRz': 2, 'Fluencet': 3,
             'FluenceRzt': 4, 'FluenceCyl': 5}
 
@@ -166,9 +167,16 @@ def describe(mc_obj, geometry: str) -> dict:
     det_kind, det_off = [0, 0, 0], [0, 0, 0]
     if dets is not None:
         dstruct = type(P['detectors'])
-        for i, loc in enumerate(('top', 'bottom', 'specular')):
+        # mccyl: `outer` takes the slot of `top`, there is no `bottom`
+        locs = ('outer', None, 'specular') if geometry == 'mccyl' \
+            else ('top', 'bottom', 'specular')
+        for i, loc in enumerate(locs):
+            if loc is None:
+                continue
             det = getattr(dets, loc)
             det_kind[i] = DET_KIND[_name(det)]
+            if geometry == 'mccyl' and det_kind[i] == DET_KIND['Total']:
+                det_kind[i] = DET_KIND_TOTAL_CYL
             det_off[i] = getattr(dstruct, loc).offset
         d['detectors'] = _raw(P['detectors'])
     d['det_kind'], d['det_offset'] = det_kind, det_off

@@ -106,7 +106,9 @@ struct SrcIsotropicPoint {          // mcsource/point.py:46-49
 	template <class Ctx>
 	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
 		float sf, cf, rs = 0.0f;
-		P3 p = position;
+		// component-wise copy: nvrtc 12.9 mis-forwards a struct copy of a
+		// __grid_constant__ member that is modified on one path only
+		P3 p = { position.x, position.y, position.z };
 		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
 		float ct = 1.0f - 2.0f*rng.next();
 		float st = M::sqrt(1.0f - ct*ct);

@@ -55,7 +55,7 @@ struct VoxSrcGaussianBeam {         // mcvox/mcsource/gaussianbeam.py:71-77
 		P3 ps = { r*cf*sigma.x, r*sf*sigma.y, 0.0f };
 		P3 pm = transform3(T, ps);
 		pm.x += position.x; pm.y += position.y; pm.z += position.z;
-		P3 d = direction;
+		P3 d = { direction.x, direction.y, direction.z };
 		if (ctx.box_contains(pm)) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
 		P3 isect, normal;
 		if (ctx.box_intersect(pm, d, &isect, &normal)) {
@@ -83,7 +83,7 @@ struct VoxSrcIsotropicPoint {       // mcvox/mcsource/point.py:44-46
 	template <class Ctx>
 	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
 		float sf, cf, rs = 0.0f;
-		P3 p = position;
+		P3 p = { position.x, position.y, position.z };
 		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
 		float ct = 1.0f - 2.0f*rng.next();
 		float st = M::sqrt(1.0f - ct*ct);

@@ -111,12 +111,48 @@ struct DetTotalPl {                 // mcdetector/totalpl.py
 	}
 };
 
+// ---- cylindrical geometry (mccyl): acceptance against the radial normal ----
+struct DetFiZ {                     // mccyl/mcdetector/fiz.py:44-56 (pack=1)
+	float fi_min, inv_dfi, z_min, inv_dz, cos_min; u32 n_fi, n_z, offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		float fi = M::atan2(pos.y, pos.x);
+		i32 ifi = clipi(f2i((fi - fi_min)*inv_dfi), 0, (i32)(n_fi - 1));
+		i32 iz = clipi(f2i((pos.z - z_min)*inv_dz), 0, (i32)(n_z - 1));
+		float k = M::sqrt(pos.x*pos.x + pos.y*pos.y);
+		k = (k > 0.0f) ? M::div(1.0f, k) : 0.0f;
+		P3 normal = { pos.x*k, pos.y*k, 0.0f };
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, normal)));
+		if (iw > 0) acc.add((u32)iz*n_fi + (u32)ifi + offset, iw);
+	}
+};
+
+struct DetTotalCyl {                // mccyl/mcdetector/total.py:44-50
+	float cos_min; u32 offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		float r = M::sqrt(pos.x*pos.x + pos.y*pos.y);
+		float k = (r > 0.0f) ? M::div(1.0f, r) : 0.0f;
+		P3 normal = { pos.x*k, pos.y*k, 0.0f };
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, normal)));
+		if (iw > 0) acc.add(offset, iw);
+	}
+};
+
 // packed McDetectors {top, bottom, specular} (mcdetector/base.py:321-327);
 // natural alignment as laid out by ctypes.
 template <class Top, class Bottom, class Specular>
 struct Detectors {
 	Top top;
 	Bottom bottom;
+	Specular specular;
+};
+// packed McDetectors {outer, specular} of mccyl (mccyl/mcdetector/base.py:302-307)
+template <class Outer, class Specular>
+struct CylDetectors {
+	Outer outer;
 	Specular specular;
 };
 

@@ -195,3 +195,118 @@ ALL_CASES.update(MCVOX_CASES)
 GEOMETRY.update({name: 'mcvox' for name in MCVOX_CASES})
 GOLDEN_RUN.update({'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
                    'mcvox_isopoint_fluencerate': (2000, 16)})
+
+
+# ---------------------------------------------------------------------------
+# cylindrical cases (layer 0 = surrounding medium, diameters decrease inwards)
+def _cyl_layers(mc, pf, stack='two'):
+    L = mc.mclayer.Layer
+    if stack == 'one':        # BASELINE config 5, mccyl variant: one cylinder r = 5 mm
+        return mc.mclayer.Layers([
+            L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+            L(d=10e-3, n=1.337, mua=1e2, mus=100e2, pf=pf)])
+    return mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=6e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=3e-3, n=1.4, mua=0.5e2, mus=50e2, pf=pf),
+        L(d=1e-3, n=1.4, mua=5e2, mus=20e2, pf=pf)])
+
+
+def mccyl_hg_line_fiz(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        outer=mc.mcdetector.FiZ(Axis(-np.pi, np.pi, 64), Axis(-5e-3, 5e-3, 100)),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_cyl_layers(mc, mc.mcpf.Hg(0.8), 'one'),
+                 mc.mcsource.Line((-10e-3, 0.0, 0.0), (1.0, 0.0, 0.0)), det,
+                 rnginit=RNGINIT, **kw), dict(rmax=25e-3)
+
+
+def mccyl_mhg_gauss_total(mc, fluence=False, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(outer=mc.mcdetector.Total(cosmin=0.5),
+                                  specular=mc.mcdetector.FiZ(Axis(-np.pi, np.pi, 16)))
+    flu = mc.mcfluence.FluenceRz(Axis(0, 3e-3, 30), Axis(-2e-3, 2e-3, 40)) if fluence else None
+    return mc.Mc(_cyl_layers(mc, mc.mcpf.MHg(0.8, 0.9)),
+                 mc.mcsource.GaussianBeam(0.4e-3, position=(-8e-3, 0.5e-3, 0.0),
+                                          direction=(1.0, 0.1, 0.05)), det,
+                 fluence=flu, rnginit=31337, **kw), dict(rmax=20e-3)
+
+
+def mccyl_mhg_gauss_total_flurz(mc, **kw):
+    return mccyl_mhg_gauss_total(mc, fluence=True, **kw)
+
+
+def mccyl_gk_ubeam_fiz_trace(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        outer=mc.mcdetector.FiZ(Axis(-np.pi, np.pi, 12), Axis(-3e-3, 3e-3, 10), cosmin=0.2),
+        specular=mc.mcdetector.Total())
+    tr = mc.mctrace.Trace(maxlen=60, options=mc.mctrace.Trace.TRACE_ALL, plon=True)
+    return mc.Mc(_cyl_layers(mc, mc.mcpf.Gk(0.7, 0.5)),
+                 mc.mcsource.UniformBeam((1e-3, 5.8e-3), position=(-6e-3, 0.0, 0.0)), det,
+                 trace=tr, rnginit=8642, **kw), dict(rmax=15e-3)
+
+
+def mccyl_hg_isopoint_inside(mc, fluence=False, **kw):
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(outer=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.Fluence(Axis(-3e-3, 3e-3, 12), Axis(-3e-3, 3e-3, 12),
+                               Axis(-2e-3, 2e-3, 8), mode='deposition') if fluence else None
+    return mc.Mc(_cyl_layers(mc, mc.mcpf.Hg(0.0)),
+                 mc.mcsource.IsotropicPoint((1.0e-3, 0.2e-3, 0.0)), det,
+                 fluence=flu, rnginit=1122, **kw), dict(rmax=10e-3)
+
+
+def mccyl_hg_isopoint_fluence(mc, **kw):
+    return mccyl_hg_isopoint_inside(mc, fluence=True, **kw)
+
+
+def mccyl_hg_isopoint_outside(mc, **kw):
+    det = mc.mcdetector.Detectors(outer=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    return mc.Mc(_cyl_layers(mc, mc.mcpf.Hg(0.9)),
+                 mc.mcsource.IsotropicPoint((-4e-3, 0.0, 0.0)), det,
+                 rnginit=2233, **kw), dict(rmax=float('inf'))
+
+
+MCCYL_CASES = {
+    'mccyl_hg_line_fiz': mccyl_hg_line_fiz,
+    'mccyl_mhg_gauss_total': mccyl_mhg_gauss_total,
+    'mccyl_gk_ubeam_fiz_trace': mccyl_gk_ubeam_fiz_trace,
+    'mccyl_hg_isopoint_inside': mccyl_hg_isopoint_inside,
+    'mccyl_hg_isopoint_outside': mccyl_hg_isopoint_outside,
+}
+ALL_CASES.update(MCCYL_CASES)
+GEOMETRY.update({name: 'mccyl' for name in MCCYL_CASES})
+GOLDEN_RUN.update({'mccyl_hg_line_fiz': (1500, 16), 'mccyl_mhg_gauss_total': (2000, 16),
+                   'mccyl_gk_ubeam_fiz_trace': (600, 16), 'mccyl_hg_isopoint_inside': (2000, 16),
+                   'mccyl_hg_isopoint_outside': (3000, 16)})
+
+# Configurations the reference cannot build (its mccyl fluence wrapper calls
+# mcsim_fluence_deposit with a position argument the header does not declare,
+# mccyl.template.c:404-421): no golden vectors exist; the CUDA path is compared
+# with the oracle's restatement of the evident semantics only ("parity unpinned").
+UNPINNED_CASES = {
+    'mccyl_mhg_gauss_total_flurz': mccyl_mhg_gauss_total_flurz,
+    'mccyl_hg_isopoint_fluence': mccyl_hg_isopoint_fluence,
+}
+UNPINNED_GEOMETRY = {name: 'mccyl' for name in UNPINNED_CASES}
+UNPINNED_RUN = {name: (2000, 16) for name in UNPINNED_CASES}
+
+
+def mcml_hg_isopoint_outside(mc, **kw):
+    """Point source above the sample: launch refracts through the top surface
+    (the path of mcsource/point.py:96-121 that modifies the position)."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 50)),
+                                  bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Radial(Axis(0, 5e-3, 50)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.9)),
+                 mc.mcsource.IsotropicPoint((0.2e-3, -0.1e-3, -1e-3)), det,
+                 rnginit=60606, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hg_isopoint_outside'] = mcml_hg_isopoint_outside
+ALL_CASES['mcml_hg_isopoint_outside'] = mcml_hg_isopoint_outside
+GEOMETRY['mcml_hg_isopoint_outside'] = 'mcml'
+GOLDEN_RUN['mcml_hg_isopoint_outside'] = (3000, 16)

@@ -11,7 +11,7 @@ import pytest
 
 import cases
 import xo_oracle
-from helpers import build_sim
+from helpers import build_sim, run_size
 
 pytestmark = pytest.mark.gpu
 
@@ -66,10 +66,10 @@ def test_deterministic_math_bit_exact(fn):
         assert np.array_equal(d1.view(np.uint32), o1.view(np.uint32))
 
 
-@pytest.mark.parametrize('name', sorted(cases.ALL_CASES))
+@pytest.mark.parametrize('name', sorted(cases.ALL_CASES) + sorted(cases.UNPINNED_CASES))
 def test_deterministic_mode_bit_exact(name):
     sim, geom, _ = _det_sim(name)
-    n, _ = cases.GOLDEN_RUN[name]
+    n, _ = run_size(name)
     n *= 4
     threads, block = 256, 64
     sim.run(n, maxthreads=threads, wgsize=block, download=False)
@@ -87,7 +87,9 @@ def test_deterministic_mode_bit_exact(name):
 
 
 @pytest.mark.parametrize('name', ['mcml_c1_slab', 'mcml_mhg_gauss_cart_flurz',
-                                  'mcml_gk_fiber_six_flu'])
+                                  'mcml_gk_fiber_six_flu', 'mcvox_gauss_fluence',
+                                  'mccyl_hg_line_fiz', 'mccyl_mhg_gauss_total_flurz',
+                                  'mccyl_hg_isopoint_outside'])
 def test_throughput_mode_statistics(name):
     """Fast mode vs oracle (libm, different schedule): totals within 4 sigma."""
     sim, geom, _ = build_sim(name)
