@@ -107,3 +107,16 @@ void xo_ref_run_dynamic(const xo_ref_args *a, uint32_t nthreads) {
 		pthread_join(th[t], NULL);
 	free(th); free(wa);
 }
+
+#ifdef XO_REF_HAS_SV
+/* the reference's SamplingVolume kernel (mcsv.template.c:236), one work-item:
+ * no random numbers, integer accumulation -> schedule independent */
+void SamplingVolume(uint32_t, uint32_t *, uint32_t *, const void *, const void *,
+	uint64_t *, int32_t *, float *, uint64_t *);
+void xo_ref_run_sv(uint32_t npackets, const void *trace, const void *sv,
+		uint64_t *total_weight, int32_t *ibuf, float *fbuf, uint64_t *abuf) {
+	uint32_t processed = 0, kernels = 0;
+	xo_ref_global_id = 0;
+	SamplingVolume(npackets, &processed, &kernels, trace, sv, total_weight, ibuf, fbuf, abuf);
+}
+#endif

@@ -75,9 +75,10 @@ def compile_rendered(src: str, geometry: str, name: str = None,
         with open(ksrc, 'w') as f:
             f.write('#include "clshim.h"\n')
             f.write(src)
+        has_sv = ['-DXO_REF_HAS_SV'] if 'void SamplingVolume(' in src else []
         cmd = ['gcc', '-std=gnu11', '-fgnu89-inline', '-w', '-fPIC', '-shared',
                '-pthread', '-I', HERE, '-DXO_REF_GEOMETRY=%d' % GEOMETRY_ID[geometry]
-               ] + cflags + [ksrc, os.path.join(HERE, 'ref_driver.c'),
+               ] + has_sv + cflags + [ksrc, os.path.join(HERE, 'ref_driver.c'),
                              '-o', so + '.tmp', '-lm']
         subprocess.check_call(cmd)
     os.replace(so + '.tmp', so)
@@ -192,3 +193,33 @@ class RefKernel:
         fn(ctypes.byref(args), int(nthreads))
         return dict(accu=accu, ints=ints, floats=floats, rng_x=x,
                     num_kernels=int(nk[0]), done=int(done[0]), lut=lut)
+
+    def sampling_volume(self, sv, trace_n: np.ndarray, trace_data: np.ndarray):
+        """The reference's ``SamplingVolume`` kernel on trace rows (``trace_n``:
+        int32[n], ``trace_data``: float32[n*maxlen*8]).  Host part as in
+        mcml/mc.py:1040-1215: the allocators are cleared, the trace and the
+        sampling volume are packed again and the rows are uploaded."""
+        m = self.mc
+        trace = m.trace
+        n = int(np.asarray(trace_n).size)
+        m.cl_rw_accumulator_allocator.clear()
+        m.cl_rw_float_allocator.clear()
+        m.cl_rw_int_allocator.clear()
+        tp = trace.cl_pack(m, None, nphotons=n)
+        sp = sv.cl_pack(m, None)
+        accu = np.zeros(max(int(m.cl_rw_accumulator_allocator.size), 1), np.uint64)
+        ibuf = np.zeros(max(int(m.cl_rw_int_allocator.size), 1), np.int32)
+        fbuf = np.zeros(max(int(m.cl_rw_float_allocator.size), 1), np.float32)
+        _, do, co, _ = np.frombuffer(bytes(memoryview(tp).cast('B')), np.uint32)[:4].tolist()
+        ibuf[co:co + n] = trace_n
+        flat = np.asarray(trace_data, np.float32).reshape(-1)
+        fbuf[do:do + flat.size] = flat
+        total = np.zeros(1, np.uint64)
+        fn = self._lib.xo_ref_run_sv
+        fn.argtypes = [ctypes.c_uint32] + [ctypes.c_void_p]*6
+        fn.restype = None
+        fn(n, ctypes.addressof(tp), ctypes.addressof(sp), total.ctypes.data,
+           ibuf.ctypes.data, fbuf.ctypes.data, accu.ctypes.data)
+        return dict(accu=accu, total_weight=int(total[0]),
+                    packed_sv=bytes(memoryview(sp).cast('B')),
+                    packed_sv_trace=bytes(memoryview(tp).cast('B')))

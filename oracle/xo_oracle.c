@@ -12,6 +12,7 @@
 #include <math.h>
 #include <float.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -873,6 +874,7 @@ static void workitem_mcml(sim_t *s, quota_t *q) {
 
 #include "xo_oracle_vox.inc"
 #include "xo_oracle_cyl.inc"
+#include "xo_oracle_sv.inc"
 
 static void run_workitem(xo_oracle_job *job, uint32_t t, quota_t *q, volatile uint32_t *dyn,
 		uint32_t *num_kernels, uint64_t *iterations) {

@@ -86,6 +86,12 @@ void xo_oracle_rng_test(uint64_t x, uint32_t a, uint32_t n, float *out);
 /* seed derivation restated from xopto/src/rng/rng.cpp:64-103 */
 int xo_oracle_init_rng(uint64_t *x, uint32_t *a, const uint32_t *fora,
 	uint32_t n_rng, uint64_t xinit);
+/* SamplingVolume kernel restated (mcsv.template.c:236-420): packed McTrace and
+ * McSamplingVolume, the int / float / accumulator flat buffers; returns the
+ * number of loop trips */
+uint64_t xo_oracle_sampling_volume(uint32_t npackets, const void *trace, const void *sv,
+	uint64_t *total_weight, const int32_t *int_buffer, const float *fp_buffer,
+	uint64_t *accu_buffer);
 /* elementary function probes for the GPU math parity test */
 void xo_oracle_math_probe(int32_t fn, int32_t math, uint32_t n,
 	const float *in0, const float *in1, float *out0, float *out1);

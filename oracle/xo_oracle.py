@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libxo_oracle.so')
 SOURCES = ['xo_oracle.c', 'xo_oracle.h', 'xo_detmath.h',
-           'xo_oracle_vox.inc', 'xo_oracle_cyl.inc']
+           'xo_oracle_vox.inc', 'xo_oracle_cyl.inc', 'xo_oracle_sv.inc']
 
 GEOMETRY = {'mcml': 0, 'mcvox': 1, 'mccyl': 2}
 METHOD = {'aw': 0, 'albedo_weight': 0, 'ar': 1, 'albedo_rejection': 1,
@@ -97,6 +97,8 @@ def lib(fast: bool = False):
         L.xo_oracle_math_probe.argtypes = [
             ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32] + [ctypes.c_void_p]*4
         L.xo_oracle_math_probe.restype = None
+        L.xo_oracle_sampling_volume.argtypes = [ctypes.c_uint32] + [ctypes.c_void_p]*6
+        L.xo_oracle_sampling_volume.restype = ctypes.c_uint64
         _libs[fast] = L
     return _libs[fast]
 
@@ -275,3 +277,19 @@ def run(desc: dict, nphotons: int, nthreads: int, rng_x: np.ndarray,
     return dict(accu=accu, ints=ints, floats=floats, rng_x=x,
                 num_kernels=int(job.num_kernels), done=int(job.num_packets_done),
                 iterations=int(job.num_iterations))
+
+
+def sampling_volume(trace_packed, sv_packed, npackets: int, ints: np.ndarray,
+                    floats: np.ndarray, accu_size: int) -> dict:
+    """SamplingVolume kernel restated: returns dict(accu, total_weight, steps)."""
+    tp, sp = _raw(trace_packed), _raw(sv_packed)
+    tb = ctypes.create_string_buffer(tp, len(tp))
+    sb = ctypes.create_string_buffer(sp, len(sp))
+    ints = np.ascontiguousarray(ints, np.int32)
+    floats = np.ascontiguousarray(floats, np.float32)
+    accu = np.zeros(max(int(accu_size), 1), np.uint64)
+    total = np.zeros(1, np.uint64)
+    steps = lib().xo_oracle_sampling_volume(
+        int(npackets), ctypes.addressof(tb), ctypes.addressof(sb), total.ctypes.data,
+        ints.ctypes.data, floats.ctypes.data, accu.ctypes.data)
+    return dict(accu=accu, total_weight=int(total[0]), steps=int(steps))

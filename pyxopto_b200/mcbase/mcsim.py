@@ -414,6 +414,87 @@ class McBase(CuWorker):
                     detectors_res.update_data(self, res, data, nphotons=nphotons)
         return trace_res, fluence_res, detectors_res
 
+    # -- sampling volume (config 4) ----------------------------------------------
+    _SV_SRC = '#define XO_DETERMINISTIC {det}\n#include "xo_sv_kernel.cuh"\n'
+
+    def _pack_sampling_volume(self, trace, sv, nphotons: int):
+        """Clears the allocators and packs the trace rows + the sampling volume
+        the way the reference does before its ``SamplingVolume`` kernel
+        (mc.py:1098-1107).  Returns (packed McTrace, packed McSamplingVolume)."""
+        for a in self._allocators.values():
+            a.clear()
+        self._packed['sv_trace'] = trace.cl_pack(
+            self, self._packed.get('sv_trace'), nphotons=int(nphotons))
+        self._packed['sv'] = sv.cl_pack(self, self._packed.get('sv'))
+        return self._packed['sv_trace'], self._packed['sv']
+
+    def sampling_volume(self, trace, sv, wgsize: int = None, maxthreads: int = None,
+                        exportsrc: str = None, verbose: bool = False):
+        """Accumulate the sampling volume ``sv`` from the packets of ``trace``
+        (counterpart of ``Mc.sampling_volume``, mc.py:1040-1215)."""
+        if self._trace is None:
+            raise RuntimeError(
+                'This Monte Carlo simulator was build without the Trace '
+                'functionallity (the trace argument of :py:meth:Mc.__init__) '
+                'was None! Sampling volume analysis requires trace functionality!')
+        t0 = time.perf_counter()
+        self._ensure_device()
+        nphotons = int(trace.nphotons)
+        deterministic = self.deterministic
+        src = self._SV_SRC.format(det=int(deterministic))
+        if exportsrc:
+            with open(exportsrc, 'w') as f:
+                f.write(src)
+        kernel = self._module(src, deterministic).kernel('SamplingVolume')
+        tp, sp = self._pack_sampling_volume(trace, sv, nphotons)
+        counters = np.zeros(4, dtype=np.uint32)   # processed, kernels, steps (u64)
+        cbuf = self.cl_r_buffer('counters', counters)
+        total = np.zeros(1, dtype=np.uint64)
+        tbuf = self.cl_r_buffer('sv_total_weight', total)
+        abuf = self._rw_flat_buffer('accumulator')
+        fbuf = self._rw_flat_buffer('float', fill=False)
+        ibuf = self._rw_flat_buffer('int', fill=False)
+        itemsize = np.dtype(self._types.np_float).itemsize
+        if nphotons:
+            n_host = np.ascontiguousarray(trace.n, dtype=self._types.np_int)
+            d_host = np.ascontiguousarray(trace.data, dtype=trace.dtype(self)).view(
+                self._types.np_float).reshape(-1)
+            ibuf.upload(self._stream, n_host, offset=int(tp.count_buffer_offset)*4,
+                        blocking=True)
+            fbuf.upload(self._stream, d_host, offset=int(tp.data_buffer_offset)*itemsize,
+                        blocking=True)
+        block = int(wgsize) if wgsize else 256
+        grid, block = self.launch_geometry(kernel, block, 0, maxthreads)
+        if nphotons:
+            grid = max(1, min(grid, (nphotons + block - 1)//block))
+        t1 = time.perf_counter()
+        ev0, ev1 = self._events
+        ev0.record(self._stream)
+        kernel.launch(self._stream, grid, block, [
+            np.uint32(nphotons), (cbuf, 0), (cbuf, 4), tp, sp, tbuf, ibuf, fbuf, abuf])
+        ev1.record(self._stream)
+        self._stream.synchronize()
+        t2 = time.perf_counter()
+        cbuf.download(self._stream, counters)
+        tbuf.download(self._stream, total)
+        accus = []
+        for a in self.cl_rw_accumulator_allocator.allocations(sv):
+            host = np.empty(a.shape, dtype=a.dtype)
+            abuf.download(self._stream, host, offset=a.offset*8)
+            accus.append(host)
+        if accus:
+            sv.update_data(self, accumulators=accus, nphotons=nphotons,
+                           total_weight=total[0])
+        self._run_report.update(
+            upload=t1 - t0, execution=t2 - t1, download=time.perf_counter() - t2,
+            items=nphotons, threads=int(counters[1]), sv_kernel_ms=ev0.elapsed_ms(ev1),
+            sv_steps=int(counters[2:4].view(np.uint64)[0]), sv_grid=grid, sv_block=block)
+        if verbose:
+            print('SamplingVolume processed {:d} packets in {:d} threads: kernel '
+                  '{:.3f} ms'.format(nphotons, int(counters[1]),
+                                     self._run_report['sv_kernel_ms']))
+        return sv
+
     # -- raw access (tests / multi-GPU reduction) ---------------------------------
     def download_raw(self):
         """Flat (accumulators, ints, floats) buffers of the last run."""

@@ -7,7 +7,7 @@ import numpy as np
 from ..cl import cltypes
 from . import mctypes
 from .mcobject import McObject
-from .mcutil.axis import Axis
+from .mcutil.axis import Axis  # noqa: F401  (re-exported like xopto.mcbase.mcsv.Axis)
 
 
 class SamplingVolume(McObject):
@@ -32,7 +32,7 @@ class SamplingVolume(McObject):
             weight = sv.weight
         self._x_axis, self._y_axis, self._z_axis = xaxis, yaxis, zaxis
         self._data, self._weight = data, weight
-        self._k = mctypes.McFloat32.mc_fp_maxint
+        self._k = mctypes.McDataTypesSingle.mc_fp_maxint    # McFloat32.mc_fp_maxint
         if self._x_axis.n*self._y_axis.n*self._z_axis.n <= 0:
             raise ValueError('Sampling volume accumulator array has one or '
                              'dimensions equal to zero!')

@@ -310,3 +310,20 @@ MCML_CASES['mcml_hg_isopoint_outside'] = mcml_hg_isopoint_outside
 ALL_CASES['mcml_hg_isopoint_outside'] = mcml_hg_isopoint_outside
 GEOMETRY['mcml_hg_isopoint_outside'] = 'mcml'
 GOLDEN_RUN['mcml_hg_isopoint_outside'] = (3000, 16)
+
+
+# ---------------------------------------------------------------------------
+# sampling volumes evaluated on the traces of the cases above (config 4)
+def make_sv(mc, name):
+    A = mc.mcsv.Axis
+    return {
+        'mcml_lut_iso_radialpl_trace': lambda: mc.mcsv.SamplingVolume(
+            A(-1e-3, 1e-3, 20), A(-1e-3, 1e-3, 16), A(0.0, 3e-3, 30)),
+        'mcvox_line_mhg_trace': lambda: mc.mcsv.SamplingVolume(
+            A(-0.2e-3, 0.2e-3, 16), A(-0.2e-3, 0.2e-3, 16), A(0.0, 0.5e-3, 20)),
+        'mccyl_gk_ubeam_fiz_trace': lambda: mc.mcsv.SamplingVolume(
+            A(-3e-3, 3e-3, 24), A(-3e-3, 3e-3, 24), A(-1e-3, 1e-3, 8)),
+    }[name]()
+
+
+SV_CASES = ('mcml_lut_iso_radialpl_trace', 'mcvox_line_mhg_trace', 'mccyl_gk_ubeam_fiz_trace')

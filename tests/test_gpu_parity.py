@@ -124,3 +124,40 @@ def test_run_returns_reference_style_results():
     # continuation: accumulate into previous results
     _, _, detectors2 = sim.run(100000, out=(None, None, detectors))
     assert detectors2.top.nphotons == 200000
+
+
+@pytest.mark.parametrize('name', cases.SV_CASES)
+def test_sampling_volume_bit_exact_and_fast(name):
+    """Mc.sampling_volume on the device vs the oracle's restatement of the
+    reference SamplingVolume kernel, fed with the same trace rows: deterministic
+    mode bit-exact (64-bit voxel accumulators + total weight); throughput mode
+    (MUFU division / square root) within 1e-4 of the grid total."""
+    sim, geom, mc = _det_sim(name)
+    n = run_size(name)[0]
+    trace, _, _ = sim.run(n, maxthreads=256, wgsize=64)
+    assert trace.nphotons == n
+    sv = cases.make_sv(mc, name)
+    sim.sampling_volume(trace, sv)
+    accu, _, _ = sim.download_raw()
+    tp, sp = sim._packed['sv_trace'], sim._packed['sv']
+    ints = np.zeros(max(sim.cl_rw_int_allocator.size, 1), np.int32)
+    floats = np.zeros(max(sim.cl_rw_float_allocator.size, 1), np.float32)
+    ints[tp.count_buffer_offset:tp.count_buffer_offset + n] = trace.n
+    rows = np.ascontiguousarray(trace.data).view(np.float32).reshape(-1)
+    floats[tp.data_buffer_offset:tp.data_buffer_offset + rows.size] = rows
+    ref = xo_oracle.sampling_volume(tp, sp, n, ints, floats,
+                                    sim.cl_rw_accumulator_allocator.size)
+    assert np.array_equal(accu, ref['accu'])
+    assert sv.weight == ref['total_weight']/sv.k
+    assert sim.run_report['sv_steps'] == ref['steps']
+    assert ref['accu'].sum() > 0
+    # reference-style result object
+    assert sv.data.shape == sv.shape
+    total = float(ref['accu'].sum())
+    assert abs(sv.data.sum()*sv.k*sv._multiplier() - total) <= 1e-9*total
+
+    fast, _, mc2 = build_sim(name)
+    sv2 = cases.make_sv(mc2, name)
+    fast.sampling_volume(trace, sv2)
+    assert abs(sv2.data.sum() - sv.data.sum()) <= 1e-4*sv.data.sum()
+    assert sv2.weight == pytest.approx(sv.weight, rel=1e-6)

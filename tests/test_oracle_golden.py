@@ -66,3 +66,31 @@ def test_oracle_seed_derivation_matches_library():
     x, a = xo_oracle.init_rng(fora, 1000, 123456789)
     x2, a2 = clrng.Random().seeds(1000, xinit=123456789)
     assert np.array_equal(x, x2) and np.array_equal(a, a2)
+
+
+@pytest.mark.parametrize('name', cases.SV_CASES)
+def test_sampling_volume_oracle_bit_exact_vs_reference_kernel(name):
+    """The SamplingVolume restatement against the reference kernel's own output
+    on the (unfiltered) golden trace rows; also pins the packed McSamplingVolume
+    and the re-packed McTrace of the host mirror."""
+    sim, geom, mc = build_sim(name)
+    g = golden(name)
+    n, _ = cases.GOLDEN_RUN[name]
+    sim._pack(n)
+    _, do, co, _ = np.frombuffer(g['packed_trace'].tobytes(), np.uint32)[:4].tolist()
+    ml = int(sim.trace.maxlen)
+    rows = g['floats'][do:do + n*ml*8]
+    cnt = g['ints'][co:co + n]
+    sv = cases.make_sv(mc, name)
+    tp, sp = sim._pack_sampling_volume(sim.trace, sv, n)
+    assert bytes(memoryview(sp).cast('B')) == g['sv_packed'].tobytes()
+    assert bytes(memoryview(tp).cast('B')) == g['sv_packed_trace'].tobytes()
+    ints = np.zeros(max(sim.cl_rw_int_allocator.size, 1), np.int32)
+    floats = np.zeros(max(sim.cl_rw_float_allocator.size, 1), np.float32)
+    ints[tp.count_buffer_offset:tp.count_buffer_offset + n] = cnt
+    floats[tp.data_buffer_offset:tp.data_buffer_offset + rows.size] = rows
+    res = xo_oracle.sampling_volume(tp, sp, n, ints, floats,
+                                    sim.cl_rw_accumulator_allocator.size)
+    assert np.array_equal(res['accu'], g['sv_accu'])
+    assert res['total_weight'] == int(g['sv_total_weight'])
+    assert res['accu'].sum() > 0
