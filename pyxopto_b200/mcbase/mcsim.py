@@ -308,6 +308,7 @@ class McBase(CuWorker):
                                  min(self._types.mc_cnt_max, 0xFFFFFFFF)))
         t0 = time.perf_counter()
         self._ensure_device()
+        self._device_trace = None        # rows of the previous run are overwritten
         self._pack(nphotons)
         deterministic = self.deterministic
         if wgsize:
@@ -398,8 +399,25 @@ class McBase(CuWorker):
         trace_res = fluence_res = detectors_res = None
         if self._trace is not None:
             trace_res = out_trace if out_trace is not None else type(self._trace)(self._trace)
-            data = self._download_allocations(self._trace, nphotons)
-            trace_res.update_data(self, data, nphotons=nphotons)
+            if self._trace.filter is not None and self.device_trace_filter:
+                n_sel, rows, n_dropped = self.filter_trace_on_device(nphotons)
+                data = {np.dtype(self._types.np_float): [rows],
+                        np.dtype(self._types.np_int): [n_sel]}
+                trace_res.update_data(self, data, nphotons=nphotons, prefiltered=True,
+                                      n_dropped=n_dropped)
+            else:
+                data = self._download_allocations(self._trace, nphotons)
+                trace_res.update_data(self, data, nphotons=nphotons)
+                tp = self._packed['trace']
+                self._device_trace = dict(
+                    n=nphotons, maxlen=int(self._trace.maxlen),
+                    ints=(self._cl_buffers['rw_int'], 4*int(tp.count_buffer_offset)),
+                    floats=(self._cl_buffers['rw_float'], 4*int(tp.data_buffer_offset)))
+            if out_trace is None and (self._trace.filter is None or self.device_trace_filter):
+                # the rows of this result are still on the device
+                token = object()
+                self._device_trace['token'] = token
+                trace_res._device_token = token
         if self._fluence is not None:
             fluence_res = out_fluence if out_fluence is not None \
                 else type(self._fluence)(self._fluence)
@@ -413,6 +431,60 @@ class McBase(CuWorker):
                 if data:
                     detectors_res.update_data(self, res, data, nphotons=nphotons)
         return trace_res, fluence_res, detectors_res
+
+    # -- device-side trace filter ------------------------------------
+    # True: a Trace with a Filter is filtered and compacted on the device and
+    # only the accepted rows are downloaded; False: the reference's flow
+    # (download every row, filter on the host).  Both give identical results.
+    device_trace_filter = True
+    _FILTER_SRC = '#include "xo_trace_kernels.cuh"\n'
+
+    def filter_trace_on_device(self, nphotons: int, download: bool = True):
+        """Evaluate ``self.trace.filter`` on the trace rows of the last run where
+        they are, compact the accepted rows in packet order and return
+        ``(n, rows, n_dropped)`` (``rows``: structured array [accepted, maxlen]).
+        With ``download=False`` only the counts are read back and the compact
+        rows stay on the device for ``sampling_volume``."""
+        from ..cu import abi
+        trace = self._trace
+        tp = self._packed['trace']
+        nphotons = int(nphotons)
+        mod = self._module(self._FILTER_SRC, True)
+        counts, ranges = trace.filter.cu_pack(trace.plon)
+        fcfg = (ctypes.c_uint32*8)(*[int(v) for v in counts])
+        rbuf = self.cl_r_buffer('filter_ranges', ranges)
+        block = 256
+        grid = max((nphotons + block - 1)//block, 1)
+        flags = self._buffer('filter_flags', 4*max(nphotons, 1))
+        cta = self._buffer('filter_cta_counts', 4*grid)
+        counters = np.zeros(2, dtype=np.uint32)          # dropped, accepted
+        cbuf = self.cl_r_buffer('filter_counters', counters)
+        ibuf, fbuf = self._cl_buffers['rw_int'], self._cl_buffers['rw_float']
+        ev0, ev1 = self._events
+        ev0.record(self._stream)
+        mod.kernel('TraceFilterFlags').launch(self._stream, grid, block, [
+            np.uint32(nphotons), tp, fcfg, rbuf, ibuf, fbuf, flags, cta, cbuf])
+        mod.kernel('TraceFilterScan').launch(self._stream, 1, 1024, [
+            np.uint32(grid), cta, (cbuf, 0)])
+        cbuf.download(self._stream, counters)
+        n_dropped, n_sel = int(counters[0]), int(counters[1])
+        maxlen = int(trace.maxlen)
+        obuf_i = self._buffer('trace_compact_int', 4*max(n_sel, 1))
+        obuf_f = self._buffer('trace_compact_float', 32*maxlen*max(n_sel, 1))
+        mod.kernel('TraceCompact').launch(self._stream, grid, block, [
+            np.uint32(nphotons), tp, flags, cta, ibuf, fbuf, obuf_i, obuf_f])
+        ev1.record(self._stream)
+        self._stream.synchronize()
+        self._run_report['filter_ms'] = ev0.elapsed_ms(ev1)
+        self._run_report['filter_accepted'] = n_sel
+        n_host = np.zeros((n_sel,), dtype=self._types.np_int)
+        rows = np.zeros((n_sel, maxlen), dtype=trace.dtype(self))
+        if n_sel:
+            obuf_i.download(self._stream, n_host)
+            if download:
+                obuf_f.download(self._stream, rows)
+        self._device_trace = dict(n=n_sel, maxlen=maxlen, ints=obuf_i, floats=obuf_f)
+        return n_host, rows, n_dropped
 
     # -- sampling volume (config 4) ----------------------------------------------
     _SV_SRC = '#define XO_DETERMINISTIC {det}\n#include "xo_sv_kernel.cuh"\n'
@@ -452,17 +524,34 @@ class McBase(CuWorker):
         total = np.zeros(1, dtype=np.uint64)
         tbuf = self.cl_r_buffer('sv_total_weight', total)
         abuf = self._rw_flat_buffer('accumulator')
-        fbuf = self._rw_flat_buffer('float', fill=False)
-        ibuf = self._rw_flat_buffer('int', fill=False)
         itemsize = np.dtype(self._types.np_float).itemsize
-        if nphotons:
-            n_host = np.ascontiguousarray(trace.n, dtype=self._types.np_int)
-            d_host = np.ascontiguousarray(trace.data, dtype=trace.dtype(self)).view(
-                self._types.np_float).reshape(-1)
-            ibuf.upload(self._stream, n_host, offset=int(tp.count_buffer_offset)*4,
-                        blocking=True)
-            fbuf.upload(self._stream, d_host, offset=int(tp.data_buffer_offset)*itemsize,
-                        blocking=True)
+        dev = getattr(self, '_device_trace', None)
+        resident = bool(
+            nphotons and dev is not None and dev.get('token') is not None and
+            dev.get('token') is getattr(trace, '_device_token', None) and
+            dev['n'] == nphotons and dev['maxlen'] == int(trace.maxlen))
+        if resident:
+            # rows never left the device: read them where the run / the device
+            # filter put them (offsets folded into the pointers)
+            ibuf_arg, fbuf_arg = dev['ints'], dev['floats']
+            tp_arg = type(tp)()
+            ctypes.memmove(ctypes.addressof(tp_arg), ctypes.addressof(tp), ctypes.sizeof(tp))
+            tp_arg.data_buffer_offset = 0
+            tp_arg.count_buffer_offset = 0
+        else:
+            tp_arg = tp
+            fbuf = self._rw_flat_buffer('float', fill=False)
+            ibuf = self._rw_flat_buffer('int', fill=False)
+            ibuf_arg, fbuf_arg = ibuf, fbuf
+            self._device_trace = None      # the flat buffers are overwritten
+            if nphotons:
+                n_host = np.ascontiguousarray(trace.n, dtype=self._types.np_int)
+                d_host = np.ascontiguousarray(trace.data, dtype=trace.dtype(self)).view(
+                    self._types.np_float).reshape(-1)
+                ibuf.upload(self._stream, n_host, offset=int(tp.count_buffer_offset)*4,
+                            blocking=True)
+                fbuf.upload(self._stream, d_host,
+                            offset=int(tp.data_buffer_offset)*itemsize, blocking=True)
         block = int(wgsize) if wgsize else 256
         grid, block = self.launch_geometry(kernel, block, 0, maxthreads)
         if nphotons:
@@ -471,7 +560,8 @@ class McBase(CuWorker):
         ev0, ev1 = self._events
         ev0.record(self._stream)
         kernel.launch(self._stream, grid, block, [
-            np.uint32(nphotons), (cbuf, 0), (cbuf, 4), tp, sp, tbuf, ibuf, fbuf, abuf])
+            np.uint32(nphotons), (cbuf, 0), (cbuf, 4), tp_arg, sp, tbuf, ibuf_arg, fbuf_arg,
+            abuf])
         ev1.record(self._stream)
         self._stream.synchronize()
         t2 = time.perf_counter()
@@ -488,6 +578,7 @@ class McBase(CuWorker):
         self._run_report.update(
             upload=t1 - t0, execution=t2 - t1, download=time.perf_counter() - t2,
             items=nphotons, threads=int(counters[1]), sv_kernel_ms=ev0.elapsed_ms(ev1),
+            sv_rows_resident=resident,
             sv_steps=int(counters[2:4].view(np.uint64)[0]), sv_grid=grid, sv_block=block)
         if verbose:
             print('SamplingVolume processed {:d} packets in {:d} threads: kernel '

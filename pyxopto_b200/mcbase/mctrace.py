@@ -126,6 +126,32 @@ class Filter:
                   reset=False)
         return valid
 
+    def cu_pack(self, plon: bool = True):
+        """(counts, ranges) for the device-side filter (TraceFilterFlags in
+        csrc/kernels/xo_trace_kernels.cuh): ``counts`` = uint32[8] {nx, ny, nz,
+        npz, nr, ndir, npl, plon}, ``ranges`` = the float32 constants in that
+        order.  Constants are rounded to binary32 exactly where numpy rounds
+        them when ``mask`` compares float32 trace fields with Python floats."""
+        f32 = np.float32
+        vals = []
+        counts = []
+        for items in (self._x, self._y, self._z, self._pz):
+            counts.append(0 if items is None else len(items))
+            for g in (items or ()):
+                vals += [f32(g[0]), f32(g[1])]
+        counts.append(0 if self._r is None else len(self._r))
+        for g in (self._r or ()):
+            vals += [f32(g[0]**2), f32(g[1]**2), f32(g[2][0]), f32(g[2][1])]
+        counts.append(0 if self._dir is None else len(self._dir))
+        for g in (self._dir or ()):
+            vals += [f32(g[0]), f32(g[1]), f32(g[2][0]), f32(g[2][1]), f32(g[2][2])]
+        counts.append(0 if self._pl is None else len(self._pl))
+        for g in (self._pl or ()):
+            vals += [f32(g[0]), f32(g[1])]
+        counts.append(int(bool(plon)))
+        return (np.array(counts, dtype=np.uint32),
+                np.array(vals + [0.0], dtype=np.float32))
+
     def __call__(self, trace_obj, update: bool = True):
         if not isinstance(trace_obj, Trace):
             raise TypeError('Trace filter can be applied only to Trace objects!')
@@ -216,11 +242,18 @@ class Trace(McObject):
 
     filter = property(lambda self: self._filter, _set_filter)
 
+    # token of the device-resident copy of the rows (set by Mc.run, dropped as
+    # soon as the host arrays are replaced): lets Mc.sampling_volume skip the
+    # re-upload of rows that never left the device
+    _device_token = None
+
     def _set_data(self, d):
         self._data = d
+        self._device_token = None
 
     def _set_n(self, n):
         self._n = n
+        self._device_token = None
 
     data = property(lambda self: self._data, _set_data)
     n = property(lambda self: self._n, _set_n)
@@ -271,7 +304,11 @@ class Trace(McObject):
             self._n_dropped = self._filter(self, update=True)[1]
             self._terminal = None
 
-    def update_data(self, mc, data, nphotons, **kwargs):
+    def update_data(self, mc, data, nphotons, prefiltered: bool = False,
+                    n_dropped: int = 0, **kwargs):
+        """Adopt the rows of a run (mctrace.py:1120-1172).  ``prefiltered``: the
+        rows were already selected by the device-side filter, which also counted
+        ``n_dropped``; the host filter is then skipped."""
         new_data = data[np.dtype(mc.types.np_float)][0]
         new_n = data[np.dtype(mc.types.np_int)][0]
         self._terminal = self._overflow_mask = None
@@ -281,12 +318,17 @@ class Trace(McObject):
                                  'of different maximum length!')
             tmp = type(self)(self)
             tmp.data = tmp.n = None
-            tmp.update_data(mc, data, nphotons)
+            tmp.update_data(mc, data, nphotons, prefiltered=prefiltered,
+                            n_dropped=n_dropped)
             self._n = np.hstack([self._n, tmp.n])
             self._data = np.vstack([self._data, tmp.data])
+            self._device_token = None
         else:
             self._n, self._data = new_n, new_data
-            self.apply_filter()
+            if prefiltered:
+                self._n_dropped = int(n_dropped)
+            else:
+                self.apply_filter()
 
     def todict(self):
         return {'type': 'Trace', 'maxlen': self._maxlen, 'options': self._options,

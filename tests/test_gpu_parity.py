@@ -161,3 +161,47 @@ def test_sampling_volume_bit_exact_and_fast(name):
     fast.sampling_volume(trace, sv2)
     assert abs(sv2.data.sum() - sv.data.sum()) <= 1e-4*sv.data.sum()
     assert sv2.weight == pytest.approx(sv.weight, rel=1e-6)
+
+
+def _filters(mc):
+    F = mc.mctrace.Filter
+    inf = float('inf')
+    return {
+        'mcml_lut_iso_radialpl_trace': F(
+            z=(-inf, 1e-9), pz=(-1.0, -0.3), r=(0.0, 2e-3, (0.1e-3, 0.0)),
+            x=[(-1.0, -0.05e-3), (0.05e-3, 1.0)], pl=(0.0, 0.01)),
+        'mcvox_line_mhg_trace': F(
+            z=[(-inf, 0.0), (0.45e-3, inf)], dir=(0.5, 1.0, (0.0, 0.0, -1.0))),
+        'mccyl_gk_ubeam_fiz_trace': F(
+            y=(-2e-3, 2e-3), dir=[(0.2, 1.0, (1.0, 0.0, 0.0)), (0.2, 1.0, (-1.0, 0.0, 0.0))]),
+    }
+
+
+@pytest.mark.parametrize('name', cases.SV_CASES)
+def test_device_trace_filter_equals_host_filter(name):
+    """Filter + stable compaction on the device (8f-1) vs the reference's flow
+    (download everything, numpy filter on the host): same rows in the same
+    order, same counts, same n_dropped; the compact rows feed sampling_volume
+    without leaving the device."""
+    from pyxopto_b200.mcbase import mcoptions
+    n = run_size(name)[0]*4
+    results = []
+    for on_device in (True, False):
+        sim, geom, mc = build_sim(name, options=[mcoptions.McDeterministic.on])
+        sim.trace.filter = _filters(mc)[name]
+        sim.device_trace_filter = on_device
+        trace, _, _ = sim.run(n, maxthreads=256, wgsize=64)
+        results.append((sim, mc, trace))
+    (sim_d, mc_d, tr_d), (sim_h, mc_h, tr_h) = results
+    assert 0 < tr_h.nphotons < n
+    assert tr_d.nphotons == tr_h.nphotons
+    assert tr_d.dropped == tr_h.dropped
+    assert np.array_equal(tr_d.n, tr_h.n)
+    assert tr_d.data.tobytes() == tr_h.data.tobytes()
+    # sampling volume from device-resident rows == from re-uploaded host rows
+    sv_d = sim_d.sampling_volume(tr_d, cases.make_sv(mc_d, name))
+    assert sim_d.run_report['sv_rows_resident'] is True
+    sv_h = sim_h.sampling_volume(tr_h, cases.make_sv(mc_h, name))
+    assert sim_h.run_report['sv_rows_resident'] is False
+    assert np.array_equal(sv_d.data, sv_h.data) and sv_d.weight == sv_h.weight
+    assert sv_d.data.sum() > 0
