@@ -118,6 +118,8 @@ def main():
                     help='packets per GPU per step (default 1.25e8 for c2_skin)')
     ap.add_argument('--cpu-sample', type=float, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sweep', type=int, default=0,
+                    help='c5_slab only: configurations per step, run as a pipelined sweep')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -133,6 +135,10 @@ def main():
         'c1_slab': 'mcml single slab mua=1/cm mus=100/cm g=0.8 n=1.33, Line + Radial',
         'c3_vox': 'mcvox 201^3 voxel 2-layer skin + blood vessel (5 um voxels), '
                   'GaussianBeam sigma 50 um, Fluence deposition grid',
+        'c4_trace': 'mcml slab, RadialPl 100x300 (path-length resolved) + Trace maxlen 512 of every '
+                    'packet + device filter + sampling_volume 200^3',
+        'c5_slab': 'mcml semi-infinite n=1.337 under air, (mua, musr) sweep point(s), g=0.8, '
+                   'Line + Radial 500, rmax 25 mm',
         'c5_cyl': 'mccyl single cylinder r=5 mm n=1.337 mua=1/cm mus=100/cm g=0.8, '
                   'Line + FiZ 64x100',
     }.get(config, config)
@@ -141,7 +147,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        sample = int(args.cpu_sample or {'c2_skin': 3e5, 'c3_vox': 2e4}.get(config, 5e4))
+        sample = int(args.cpu_sample or {'c2_skin': 3e5, 'c3_vox': 2e4, 'c4_trace': 2e4}.get(config, 5e4))
         times = []
         kind = 'port'
         for i in range(args.warmup + args.steps):
@@ -180,7 +186,8 @@ def main():
     from pyxopto_b200.cu import abi
     geom = benchcfg.GEOMETRY[config]
     mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
-    packets = int(args.packets or {'c2_skin': 1.25e8, 'c3_vox': 1.25e7}.get(config, 1e7))
+    packets = int(args.packets or {'c2_skin': 1.25e8, 'c3_vox': 1.25e7,
+                                   'c4_trace': 1e6}.get(config, 1e7))
     from pyxopto_b200 import parallel as _par
     sim = benchcfg.CONFIGS[config](mc, rnginit=_par.seed_for_rank(benchcfg.RNGINIT, rank),
                                    cl_devices=local_rank)
@@ -195,9 +202,58 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
 
+    # one step of the configuration, device-resident (`value`) and through the
+    # public API with host results (`e2e`)
+    sv_ms = []
+    if config == 'c4_trace':
+        def step_device():
+            sim.run(packets, download=False)
+            rr = dict(sim.run_report)
+            sim.filter_trace_on_device(packets, download=False)
+            sim.sampling_volume(None, benchcfg.c4_sampling_volume(mc), download=False)
+            sv_ms.append(sim.run_report['sv_kernel_ms'] + sim.run_report['filter_ms'])
+            return rr
+
+        def step_e2e():
+            trace, fluence, detectors = sim.run(packets)
+            sv = sim.sampling_volume(trace, benchcfg.c4_sampling_volume(mc))
+            return detectors, fluence, float(sv.data.sum())
+    elif config == 'c5_slab' and args.sweep:
+        # config 5 as it is meant to be run: a pipelined sweep over (mua, musr)
+        from pyxopto_b200 import mcsweep
+        grid_cfgs = benchcfg.c5_grid()
+        stride = max(len(grid_cfgs)//args.sweep, 1)
+        sweep_cfgs = grid_cfgs[::stride][:args.sweep]
+        sweep = mcsweep.Sweep(sim)
+        ev_a, ev_b = abi.Event(sim.cl_context), abi.Event(sim.cl_context)
+
+        def step_device():
+            ev_a.record(sim._stream)
+            sweep.run(sweep_cfgs, packets)
+            ev_b.record(sim._stream)
+            sim._stream.synchronize()
+            rr = dict(sim.run_report)
+            rr['kernel_ms'] = ev_a.elapsed_ms(ev_b)       # all kernels of the sweep
+            rr['iterations'] = int(sweep.report['iterations'].sum())
+            rr.setdefault('kernel_attributes', {'num_regs': None})
+            return rr
+
+        def step_e2e():
+            idx, rows = sweep.run(sweep_cfgs, packets)
+            refl = sweep.detector(rows, sim.detectors.top, packets)
+            return None, None, float(refl.sum())
+    else:
+        def step_device():
+            sim.run(packets, download=False)
+            return sim.run_report
+
+        def step_e2e():
+            trace, fluence, detectors = sim.run(packets)
+            return detectors, fluence, 0.0
+
     # warm-up (also builds/loads the kernel)
     for _ in range(max(args.warmup, 1)):
-        sim.run(packets, download=False)
+        step_device()
     barrier()
 
     # ---- device-resident loop: `value` -------------------------------------------
@@ -210,9 +266,9 @@ def main():
     t0 = time.perf_counter()
     ev_start.record(sim._stream)
     for _ in range(args.steps):
-        sim.run(packets, download=False)
-        kernel_ms.append(sim.run_report['kernel_ms'])
-        iters.append(sim.run_report['iterations'])
+        rr_step = step_device()
+        kernel_ms.append(rr_step['kernel_ms'])
+        iters.append(rr_step['iterations'])
     ev_stop.record(sim._stream)
     barrier()
     t1 = time.perf_counter()
@@ -225,9 +281,9 @@ def main():
     t2 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(args.steps):
-        trace, fluence, detectors = sim.run(packets)
+        detectors, fluence, extra = step_e2e()
         checksum = sum(float(d.raw.sum()) for d in (detectors or ()) if hasattr(d, 'raw')) + \
-            (float(fluence.raw.sum()) if fluence is not None else 0.0)
+            (float(fluence.raw.sum()) if fluence is not None else 0.0) + extra
     barrier()
     t3 = time.perf_counter()
     e2e_s = t3 - t2
@@ -235,13 +291,17 @@ def main():
     P = sim._packed
     h2d = sum(len(cltypes.raw_bytes(P[k])) for k in P if P[k] is not None) + 16
     d2h = int(sim.cl_rw_accumulator_allocator.size)*8 + 16
+    if config == 'c4_trace':
+        # accepted trace rows + their counts, then the sampling-volume grid
+        d2h += int(sim.run_report.get('filter_accepted', 0))*(32*int(sim.trace.maxlen) + 4)
 
     if world > 1:
         t = torch.tensor([loop_s, e2e_s, loop_ms_events], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         loop_s, e2e_s, loop_ms_events = [float(v) for v in t.tolist()]
 
-    total_packets = packets*world*args.steps
+    per_step = packets*(args.sweep if (config == 'c5_slab' and args.sweep) else 1)
+    total_packets = per_step*world*args.steps
     value = total_packets/loop_s
     e2e_value = total_packets/e2e_s
 
@@ -263,7 +323,7 @@ def main():
             'traffic': None,
             'kernel': 'McKernel', 'kernel_ms': k_ms,
             'iterations_per_launch': iter_per_launch,
-            'iterations_per_packet': iter_per_launch/packets,
+            'iterations_per_packet': iter_per_launch/per_step,
             'algorithmic_ops_per_iteration': {'alu_fma': alu_ops, 'mufu': sfu_ops},
             'sfu': {'achieved': achieved_sfu/1e9, 'peak': sfu_peak/1e9,
                     'frac': achieved_sfu/sfu_peak},
@@ -273,9 +333,24 @@ def main():
                                peaks_src, sms, FP32_LANES_PER_SM),
             'kernel_share_of_step': k_ms*args.steps/(loop_ms_events if loop_ms_events > 0 else 1),
         }
+        if config == 'c4_trace':
+            # the trace stream binds this configuration: one 32 B event record per
+            # loop iteration, written once
+            hbm_peak = float(peaks.get('hbm_gbs', peaks.get('hbm_gbps', 6650.0)))
+            bytes_per_launch = iter_per_launch*benchcfg.TRACE_BYTES_PER_ITERATION
+            roofline.update({
+                'bound': 'hbm', 'achieved': bytes_per_launch/(k_ms*1e-3)/1e9,
+                'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': bytes_per_launch/(k_ms*1e-3)/1e9/hbm_peak,
+                'algorithmic_bytes_per_iteration': benchcfg.TRACE_BYTES_PER_ITERATION,
+                'issue': {'achieved': achieved/1e9, 'peak': issue_peak/1e9,
+                          'frac': achieved/issue_peak},
+                'filter_plus_sampling_volume_ms': float(np.mean(sv_ms)) if sv_ms else None,
+                'peak_source': 'hbm_gbs of MEASURED_PEAKS.json ({})'.format(peaks_src),
+            })
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
-            sample = int(args.cpu_sample or {'c2_skin': 2e6, 'c3_vox': 1e5}.get(config, 3e5))
+            sample = int(args.cpu_sample or {'c2_skin': 2e6, 'c3_vox': 1e5, 'c4_trace': 2e4}.get(config, 3e5))
             try:
                 pps, kind, secs = cpu_reference_run(config, sample, ncores)
                 cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
@@ -292,8 +367,9 @@ def main():
             'ms_per_step': 1e3*loop_s/args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {
-                'workload': workload, 'packets_per_gpu_per_step': packets,
-                'global_packets_per_step': packets*world,
+                'workload': workload, 'packets_per_gpu_per_step': per_step,
+                'global_packets_per_step': per_step*world,
+                'sweep_configs_per_step': args.sweep or None,
                 'parallelism': 'packets sharded over {} GPU(s), disjoint MWC seed sets'
                                '{}'.format(world, ', 1 NCCL all-reduce of the uint64 '
                                            'accumulators per step' if world > 1 else ''),
@@ -301,13 +377,13 @@ def main():
                 'l2': 'inputs are < 2 MB of constants; every step re-zeroes and rewrites '
                       'the accumulator grid, no cached outputs are reused',
                 'grid': rr['grid'], 'block': rr['block'],
-                'registers': rr['kernel_attributes']['num_regs'],
+                'registers': rr.get('kernel_attributes', {}).get('num_regs'),
             },
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'packets/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3*e2e_s/args.steps,
                     'checksum': checksum},
-            'gpu_launches': args.steps,
+            'gpu_launches': args.steps*(5 if config == 'c4_trace' else max(args.sweep, 1)),
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
         }

@@ -133,3 +133,72 @@ PACKETS['c5_cyl'] = 10**7
 # cylinder quadratic of mccyl.template.c:147-209: a, b, c (9), 1/2a (1 + 1 MUFU),
 # outer discriminant + root (6 + 1 MUFU), inner discriminant test (4)
 OPS_PER_ITERATION['c5_cyl'] = (101, 13)
+
+
+def c4_trace(mc, rnginit=RNGINIT, maxlen=512, **kw):
+    """BASELINE configs[3] on the C1 slab: path-length resolved
+    RadialPl reflectance (300 bins of 1 mm optical path ~ 3.3 ps), full Trace of
+    every packet (maxlen 512, optical path length on) with a terminal-event
+    filter selecting packets that leave through the top surface 0.5-1.5 mm from
+    the source within 12.7 deg of the normal (a detector fibre), followed by
+    ``sampling_volume`` on a 200^3 grid of 20 um voxels."""
+    Axis = mc.mcdetector.Axis
+    pf = mc.mcpf.Hg(0.8)
+    L = mc.mclayer.Layer
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(0.0)),
+        L(d=10e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(0.0))])
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.RadialPl(Axis(0.0, 10e-3, 100), plaxis=Axis(0.0, 0.3, 300)))
+    flt = mc.mctrace.Filter(z=(-float('inf'), 0.0), r=(0.5e-3, 1.5e-3, (0.0, 0.0)),
+                            pz=(-1.0, -float(np.cos(np.deg2rad(12.7)))))
+    tr = mc.mctrace.Trace(maxlen=maxlen, options=mc.mctrace.Trace.TRACE_ALL, plon=True,
+                          filter=flt)
+    sim = mc.Mc(layers, mc.mcsource.Line(), det, trace=tr, rnginit=rnginit, **kw)
+    sim.rmax = 25e-3
+    return sim
+
+
+def c4_sampling_volume(mc):
+    A = mc.mcsv.Axis
+    return mc.mcsv.SamplingVolume(A(-2e-3, 2e-3, 200), A(-2e-3, 2e-3, 200), A(0.0, 4e-3, 200))
+
+
+CONFIGS['c4_trace'] = c4_trace
+GEOMETRY['c4_trace'] = 'mcml'
+PACKETS['c4_trace'] = 10**6
+# C1's loop (85, 11) plus the optical path length (1 FMA) and the trace event
+# (address 3 IMAD + 2 STG.128); the binding resource is the 32 B trace record
+# written per iteration (HBM), see bench.py
+OPS_PER_ITERATION['c4_trace'] = (91, 11)
+TRACE_BYTES_PER_ITERATION = 32
+
+
+def c5_slab(mc, rnginit=RNGINIT, mua=1e2, musr=20e2, **kw):
+    """BASELINE configs[4], mcml variant: semi-infinite water
+    (n = 1.337) under air, Line source, Radial(0..5 mm, 500 bins) reflectance,
+    rmax = 25 mm; one point of the 64 x 64 (mua, musr) grid, g = 0.8."""
+    Axis = mc.mcdetector.Axis
+    g = 0.8
+    L = mc.mclayer.Layer
+    layers = mc.mclayer.Layers([
+        L(d=float('inf'), n=1.0, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(0.0)),
+        L(d=float('inf'), n=1.337, mua=mua, mus=musr/(1.0 - g), pf=mc.mcpf.Hg(g)),
+        L(d=float('inf'), n=1.0, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(0.0))])
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0.0, 5e-3, 500)))
+    sim = mc.Mc(layers, mc.mcsource.Line(), det, rnginit=rnginit, **kw)
+    sim.rmax = 25e-3
+    return sim
+
+
+def c5_grid(n_mua=64, n_musr=64, g=0.8):
+    """The (mua, musr) sweep of config 5 as Sweep descriptors."""
+    return [{1: {'mua': float(mua), 'mus': float(musr/(1.0 - g))}}
+            for mua in np.linspace(0.0, 5e2, n_mua) for musr in np.linspace(5e2, 35e2, n_musr)]
+
+
+CONFIGS['c5_slab'] = c5_slab
+GEOMETRY['c5_slab'] = 'mcml'
+PACKETS['c5_slab'] = 10**7
+OPS_PER_ITERATION['c5_slab'] = (85, 11)

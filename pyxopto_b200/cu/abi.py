@@ -317,6 +317,40 @@ class Buffer:
             pass
 
 
+class _PinnedBlock:
+    """Owner of one page-locked host allocation (xo_host_alloc)."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p(0)
+        check(lib().xo_host_alloc(ctx.handle, max(self.nbytes, 1), ctypes.byref(p)))
+        self.ptr = p.value
+        self.ctypes_array = (ctypes.c_ubyte*max(self.nbytes, 1)).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().xo_host_free(self.ctx.handle, ctypes.c_void_p(self.ptr))
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+def pinned_empty(ctx: Context, shape, dtype) -> np.ndarray:
+    """NumPy array in page-locked host memory: device <-> host copies of it run
+    at full PCIe rate and can be asynchronous.  The allocation lives as long as
+    the array (or any view of it) does."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    block = _PinnedBlock(ctx, n*dtype.itemsize)
+    flat = np.frombuffer(block.ctypes_array, dtype=np.uint8, count=n*dtype.itemsize)
+    arr = flat.view(dtype).reshape(shape)
+    # np.frombuffer keeps `block.ctypes_array` alive; tie the block to it
+    block.ctypes_array._xo_block = block
+    return arr
+
+
 def _host_ptr(host):
     if isinstance(host, np.ndarray):
         if not host.flags['C_CONTIGUOUS']:

@@ -35,6 +35,20 @@ def _c_float(v: float) -> str:
     return '{!r}f'.format(v)
 
 
+class _ResidentRows:
+    """Stand-in for a Trace whose rows only exist on the device."""
+
+    def __init__(self, dev: dict, trace):
+        self.nphotons, self.maxlen = dev['n'], dev['maxlen']
+        if dev.get('token') is None:
+            dev['token'] = object()
+        self._device_token = dev['token']
+        self._trace = trace
+
+    def cl_pack(self, mc, target=None, nphotons=None):
+        return self._trace.cl_pack(mc, target, nphotons=nphotons)
+
+
 class McBase(CuWorker):
     """Plugin bookkeeping, option resolution, TU emission and the run loop."""
 
@@ -297,7 +311,7 @@ class McBase(CuWorker):
 
     def run(self, nphotons: int, out=None, wgsize: int = None, maxthreads: int = None,
             copyseeds: bool = False, exportsrc: str = None, verbose: bool = False,
-            download: bool = True):
+            download: bool = True, synchronize: bool = True):
         """Simulate ``nphotons`` packets.  Returns ``(trace, fluence, detectors)``
         result objects like the reference (mc.py:730-1018); with ``out`` the new
         data are accumulated into the given previous results."""
@@ -309,6 +323,9 @@ class McBase(CuWorker):
         t0 = time.perf_counter()
         self._ensure_device()
         self._device_trace = None        # rows of the previous run are overwritten
+        if not synchronize and (download or copyseeds):
+            raise ValueError('synchronize=False requires download=False, copyseeds=False')
+        self._async_uploads = not synchronize
         self._pack(nphotons)
         deterministic = self.deterministic
         if wgsize:
@@ -329,7 +346,7 @@ class McBase(CuWorker):
         # uploads (mc.py:840-884)
         self._upload_seeds(copy=False)
         counters = np.zeros(4, dtype=np.uint32)   # done, kernels, iterations (u64)
-        cbuf = self.cl_r_buffer('counters', counters)
+        cbuf = self.cl_r_buffer(self._counters_name(), counters)
         self._upload_medium()
         if len(self._float_lut):
             lut_host = self._float_lut.pack_into(None).astype(np.float32)
@@ -364,6 +381,13 @@ class McBase(CuWorker):
         ev1.record(self._stream)
         if self._reduce_hook is not None:
             self._reduce_hook(self, abuf, self.cl_rw_accumulator_allocator.size)
+        self._async_uploads = False
+        if not synchronize:
+            # queued only (mcsweep.Sweep): the caller orders its own copies on
+            # the stream and waits on its own events
+            self._run_report = {'items': nphotons, 'grid': grid, 'block': block,
+                                'launched_threads': nthreads, 'cache_hit': mod.cache_hit}
+            return (None, None, None)
         self._stream.synchronize()
         t_exec = time.perf_counter()
         kernel_ms = ev0.elapsed_ms(ev1)
@@ -501,7 +525,8 @@ class McBase(CuWorker):
         return self._packed['sv_trace'], self._packed['sv']
 
     def sampling_volume(self, trace, sv, wgsize: int = None, maxthreads: int = None,
-                        exportsrc: str = None, verbose: bool = False):
+                        exportsrc: str = None, verbose: bool = False,
+                        download: bool = True):
         """Accumulate the sampling volume ``sv`` from the packets of ``trace``
         (counterpart of ``Mc.sampling_volume``, mc.py:1040-1215)."""
         if self._trace is None:
@@ -511,6 +536,12 @@ class McBase(CuWorker):
                 'was None! Sampling volume analysis requires trace functionality!')
         t0 = time.perf_counter()
         self._ensure_device()
+        if trace is None:
+            # the rows of the last run (or of filter_trace_on_device), in place
+            dev = getattr(self, '_device_trace', None)
+            if dev is None:
+                raise RuntimeError('No trace rows are resident on the device!')
+            trace = _ResidentRows(dev, self._trace)
         nphotons = int(trace.nphotons)
         deterministic = self.deterministic
         src = self._SV_SRC.format(det=int(deterministic))
@@ -568,7 +599,7 @@ class McBase(CuWorker):
         cbuf.download(self._stream, counters)
         tbuf.download(self._stream, total)
         accus = []
-        for a in self.cl_rw_accumulator_allocator.allocations(sv):
+        for a in (self.cl_rw_accumulator_allocator.allocations(sv) if download else ()):
             host = np.empty(a.shape, dtype=a.dtype)
             abuf.download(self._stream, host, offset=a.offset*8)
             accus.append(host)

@@ -189,13 +189,28 @@ class CuWorker:
         else:
             nbytes = len(bytes(memoryview(host).cast('B')))
         buf = self._buffer(name, nbytes)
-        buf.upload(self._stream, host, blocking=True)
+        # pageable host memory is staged by the driver before the call returns,
+        # so the asynchronous form is safe for the (small) packed structs
+        buf.upload(self._stream, host, blocking=not self._async_uploads)
         return buf
+
+    # sweeps double-buffer the accumulators on the device (mcsweep.Sweep)
+    _accumulator_slot = 0
+    _async_uploads = False
+
+    def _rw_name(self, kind: str) -> str:
+        if kind == 'accumulator' and self._accumulator_slot:
+            return 'rw_accumulator_{}'.format(self._accumulator_slot)
+        return 'rw_' + kind
+
+    def _counters_name(self) -> str:
+        return 'counters_{}'.format(self._accumulator_slot) if self._accumulator_slot \
+            else 'counters'
 
     def _rw_flat_buffer(self, kind: str, fill: bool = True) -> abi.Buffer:
         alloc = self._allocators[kind]
         nbytes = max(alloc.size, 1)*alloc.dtype.itemsize
-        buf = self._buffer('rw_' + kind, nbytes)
+        buf = self._buffer(self._rw_name(kind), nbytes)
         if fill:
             buf.fill(self._stream, 0, np.uint32, count=(nbytes + 3)//4)
         return buf

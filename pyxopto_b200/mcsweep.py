@@ -1,0 +1,132 @@
+"""Optical-property sweeps (BASELINE config 5; counterpart of the reference's
+sweep callers ``dataset/render/mcml.py:38-95`` + ``mcbase/mcrun.py:49-92``,
+which call ``Mc.run`` once per configuration and pay a full host round trip
+each time).
+
+A sweep keeps ONE simulator - one compiled kernel, one set of device buffers -
+and streams configurations through it:
+
+  * every configuration only rewrites the packed medium / source structs (a few
+    hundred bytes) and re-zeroes the accumulators on the device;
+  * the accumulator buffer is double-buffered on the device and lands in
+    page-locked host rows with asynchronous copies, so configuration i+1 is
+    simulated while the results of configuration i cross PCIe;
+  * the only synchronisation per configuration is one event wait.
+
+Multi-GPU: configurations are dealt round-robin to the ranks (static
+``config i -> rank i % world``), one process per GPU, no collective on the data
+path; ``gather()`` assembles the per-rank rows with one all-gather.
+"""
+import time
+
+import numpy as np
+
+
+def partition(n_configs: int, world: int, rank: int) -> np.ndarray:
+    """Indices of the configurations simulated by ``rank`` (round-robin)."""
+    return np.arange(int(rank), int(n_configs), int(world), dtype=np.int64)
+
+
+class Sweep:
+    def __init__(self, sim, rank: int = 0, world: int = 1):
+        """``sim``: a ``pyxopto_b200`` simulator (any geometry) whose plugin
+        *types* stay fixed over the sweep (what the reference requires between
+        ``run`` calls as well, mc.py:486-529)."""
+        self.sim = sim
+        self.rank, self.world = int(rank), int(world)
+        self.report = {}
+
+    def run(self, configs, nphotons: int, apply=None, wgsize: int = None,
+            maxthreads: int = None):
+        """Simulate ``nphotons`` packets for every configuration of this rank.
+
+        ``configs``: sequence of configuration descriptors; ``apply(sim, cfg)``
+        updates the simulator (layers, source, ... ) for one of them.  Without
+        ``apply`` a descriptor is a dict ``{layer index: {attr: value}}``.
+
+        Returns ``(indices, accumulators)``: the global indices of this rank's
+        configurations and a ``uint64[len(indices), accumulator size]`` array of
+        raw fixed-point accumulators (detector bins first, fluence after, pack
+        order) - ``Sweep.detector(...)`` converts rows to reference units."""
+        from .cu import abi
+        sim = self.sim
+        apply = apply or _apply_layer_updates
+        mine = partition(len(configs), self.world, self.rank)
+        nphotons = int(nphotons)
+        sim._ensure_device()
+        t0 = time.perf_counter()
+        rows = counters = None
+        pending = None                  # (row index, event) of the copy in flight
+        slots = [None, None]
+        events = [abi.Event(sim.cl_context), abi.Event(sim.cl_context)]
+        for k, index in enumerate(mine):
+            apply(sim, configs[int(index)])
+            slot = k & 1
+            sim._accumulator_slot = slot          # device double buffer
+            sim.run(nphotons, wgsize=wgsize, maxthreads=maxthreads, download=False,
+                    synchronize=False)
+            size = int(sim.cl_rw_accumulator_allocator.size)
+            if rows is None:
+                rows = abi.pinned_empty(sim.cl_context, (len(mine), size), np.uint64)
+                counters = abi.pinned_empty(sim.cl_context, (len(mine), 4), np.uint32)
+            abuf = sim._cl_buffers[sim._rw_name('accumulator')]
+            abuf.download(sim._stream, rows[k], blocking=False)
+            sim._cl_buffers[sim._counters_name()].download(
+                sim._stream, counters[k], blocking=False)
+            events[slot].record(sim._stream)
+            slots[slot] = k
+            if pending is not None:
+                events[pending].synchronize()     # results of configuration k-1
+            pending = slot
+        if pending is not None:
+            events[pending].synchronize()
+        sim._stream.synchronize()
+        sim._accumulator_slot = 0
+        iterations = counters[:, 2:4].copy().view(np.uint64).reshape(-1) \
+            if rows is not None else np.zeros(0, np.uint64)
+        self.report = dict(seconds=time.perf_counter() - t0, configs=len(mine),
+                           packets=nphotons*len(mine), iterations=iterations,
+                           threads=counters[:, 1].copy() if rows is not None else None)
+        if rows is None:
+            rows = np.zeros((0, 0), np.uint64)
+        return mine, rows
+
+    def detector(self, rows: np.ndarray, det, nphotons: int) -> np.ndarray:
+        """Rows -> per-configuration detector data in the reference's units
+        (what ``det.raw`` would hold after ``Mc.run``: weight, not normalised)."""
+        sim = self.sim
+        out = []
+        for a in sim.cl_rw_accumulator_allocator.allocations(det):
+            block = rows[:, a.offset:a.offset + a.size].astype(np.float64)
+            out.append((block*(1.0/sim.types.mc_accu_k)).reshape((rows.shape[0],) + tuple(a.shape)))
+        return out[0] if len(out) == 1 else out
+
+    def gather(self, indices: np.ndarray, rows: np.ndarray, n_configs: int) -> np.ndarray:
+        """All ranks get the rows of all configurations, in configuration order
+        (one all-gather of the fixed-point rows over torch.distributed)."""
+        if self.world == 1:
+            return rows
+        import torch
+        import torch.distributed as dist
+        per_rank = (int(n_configs) + self.world - 1)//self.world
+        width = rows.shape[1]
+        local = np.zeros((per_rank, width), np.int64)
+        local[:rows.shape[0]] = rows.view(np.int64)
+        t = torch.from_numpy(local)
+        dev = torch.device('cuda', torch.cuda.current_device()) \
+            if dist.get_backend() == 'nccl' else torch.device('cpu')
+        t = t.to(dev)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        full = np.zeros((int(n_configs), width), np.uint64)
+        for r in range(self.world):
+            idx = partition(n_configs, self.world, r)
+            full[idx] = out[r].cpu().numpy().view(np.uint64)[:idx.size]
+        return full
+
+
+def _apply_layer_updates(sim, cfg: dict):
+    for layer_index, attrs in cfg.items():
+        layer = sim.layers[int(layer_index)]
+        for name, value in attrs.items():
+            setattr(layer, name, value)

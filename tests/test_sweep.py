@@ -1,0 +1,56 @@
+"""Config-5 sweeps (pyxopto_b200/mcsweep.py): static round-robin partition (CPU)
+and, on the GPU, the pipelined sweep against one blocking ``Mc.run`` per
+configuration."""
+import numpy as np
+import pytest
+
+from pyxopto_b200 import mcsweep
+
+
+def test_partition_round_robin_is_disjoint_and_covering():
+    for n in (0, 1, 7, 4096):
+        for world in (1, 2, 3, 8):
+            seen = np.concatenate([mcsweep.partition(n, world, r) for r in range(world)])
+            assert sorted(seen.tolist()) == list(range(n))
+            sizes = [mcsweep.partition(n, world, r).size for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _configs():
+    g = 0.8
+    return [{1: {'mua': float(mua), 'mus': float(musr/(1.0 - g))}}
+            for mua in np.linspace(0.0, 5e2, 3) for musr in np.linspace(5e2, 35e2, 3)]
+
+
+def _sweep_sim():
+    import benchcfg
+    from pyxopto_b200.mcbase import mcoptions
+    from pyxopto_b200.mcml import mc
+    return benchcfg.c5_slab(mc, options=[mcoptions.McDeterministic.on]), mc
+
+
+@pytest.mark.gpu
+def test_pipelined_sweep_equals_one_run_per_configuration():
+    n = 20000
+    configs = _configs()
+    sim, mc = _sweep_sim()
+    sweep = mcsweep.Sweep(sim)
+    idx, rows = sweep.run(configs, n, maxthreads=1024, wgsize=64)
+    assert idx.tolist() == list(range(len(configs)))
+    ref_sim, _ = _sweep_sim()
+    for i, cfg in enumerate(configs):
+        mcsweep._apply_layer_updates(ref_sim, cfg)
+        ref_sim.run(n, maxthreads=1024, wgsize=64, download=False)
+        accu = ref_sim.download_raw()[0]
+        assert np.array_equal(rows[i], accu), i
+    refl = sweep.detector(rows, sim.detectors.top, n)
+    assert refl.shape == (len(configs), 500)
+    total = refl.sum(axis=1)/n
+    assert (total > 0.01).all() and (total < 1.0).all()
+    # more absorption -> less diffuse reflectance at fixed scattering
+    assert total[0] > total[3] > total[6]
+    # rank 1 of 2 simulates the odd configurations
+    sweep2 = mcsweep.Sweep(_sweep_sim()[0], rank=1, world=2)
+    idx2, rows2 = sweep2.run(configs, n, maxthreads=1024, wgsize=64)
+    assert idx2.tolist() == list(range(1, len(configs), 2))
+    assert rows2.shape == (len(idx2), rows.shape[1])
