@@ -1,0 +1,311 @@
+// mcvox_dda_loop.cuh -- throughput loop of the voxel kernel (body fragment,
+// included inside McKernel of mcvox_kernel.cuh when XO_VOX_DDA).
+//
+// Same physics as one iteration of the reference loop
+// (xopto/mcvox/kernel/mcvox.template.c:667-1014), re-expressed for the SM:
+//
+//   * The reference draws a fresh exponential step in every iteration and
+//     divides three face distances by the direction (3 divisions + 1 log per
+//     voxel crossing).  Here a straight flight is ONE ray: origin `pos`, the
+//     free path `t_s` drawn once, and an incremental voxel walk (Amanatides &
+//     Woo): per axis the ray parameter of the next face `tm` and the parameter
+//     increment per voxel `td`.  A crossing is min3 + one predicated add per
+//     axis + the material lookup of the entered voxel.  Statistically identical:
+//     the exponential distribution is memoryless, so "fresh step after every
+//     crossing inside one material" == "one step for the whole flight"; a fresh
+//     step IS drawn whenever the material changes or the packet is reflected
+//     (the reference's behaviour).  The iteration counter
+//     counts crossings + interactions, i.e. the reference's loop trips.
+//   * 85 % of the trips are crossings (~25 instructions), 15 % interactions
+//     (~110: deposit, phase function, rotation, new ray).  Executed as one
+//     divergent loop a warp would run both paths every trip.  Instead each lane
+//     is a small state machine and the warp runs the crossing step for the lanes
+//     in RUN state until `refill` lanes wait for something else; then the
+//     waiting lanes execute their interaction / interface / relaunch jointly.
+//   * new packets come from a per-warp launch queue filled by all 32 lanes
+//     together (as in mcml_kernel.cuh).
+//   * rmax: the reference tests |pos - source| > rmax after every trip.  A ray
+//     leaves the (convex) sphere once, at parameter `t_rmax` computed per ray,
+//     so the test of a crossing is one compare (compiled out by the host when
+//     the voxel box lies inside the sphere).
+{
+	enum : u32 { ST_RUN = 0, ST_SCAT = 1, ST_BND = 2 /* +axis: 2,3,4 */, ST_SETUP = 5,
+		ST_DEAD = 6, ST_DRY = 7 };
+	const u32 lane = threadIdx.x & 31u;
+	const u32 lanemask_lt = (1u << lane) - 1u;
+	const u32 gnx = (u32)cfg.nx, gny = (u32)cfg.ny, gnz = (u32)cfg.nz;
+	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
+	(void)tcfg; (void)chunk; (void)nthreads;
+
+	u32 state = ST_DEAD;
+	u32 n_dry = 0, q_count = 0;     // warp-uniform
+	bool q_dry = false;             // warp-uniform: the packet budget is exhausted
+	// packet
+	P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
+	float weight = 0.0f, opl = 0.0f;
+	u32 packet = 0, trace_count = 0, flags = 0;
+	(void)opl; (void)packet; (void)trace_count; (void)flags;
+	// ray: voxel walk state
+	i32 ix = 0, iy = 0, iz = 0, sx = 1, sy = 1, sz = 1, mat = 0;
+	float tmx = 0.0f, tmy = 0.0f, tmz = 0.0f, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
+	float t_s = 0.0f, t_evt = 0.0f;
+#if XO_USE_RMAX
+	float t_rmax = 0.0f;
+#endif
+	// constants of the current material (registers; reloaded on material change)
+	VoxHot c_hot = { 0.0f, 0.0f, 0.0f, 1.0f };
+	XoPf::Fast c_pf;
+#define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
+#define XO_VOXEL(x, y, z) __ldg(voxels + ((u32)(z)*gny + (u32)(y))*gnx + (u32)(x))
+#if XO_USE_RMAX
+#define XO_RMAX_TEST() do { \
+		float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
+		if (ex_*ex_ + ey_*ey_ + ez_*ez_ > rmax2) { done = true; flags |= EV_ESCAPED; } \
+	} while (0)
+#else
+#define XO_RMAX_TEST() do { } while (0)
+#endif
+#if XO_TRACE
+#define XO_TRACE_TRIP() do { \
+		flags |= done ? EV_TERMINATED : 0u; \
+		if (XO_TRACE == XO_TRACE_ALL || ((XO_TRACE & XO_TRACE_END) && done)) { \
+			if (trace_event(tcfg, float_buffer, packet, trace_count, flags, \
+					pos, dir, weight, opl)) ++trace_count; \
+		} \
+		if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
+	} while (0)
+#else
+#define XO_TRACE_TRIP() do { } while (0)
+#endif
+#define XO_END_TRIP() do { \
+		if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; } \
+		XO_RMAX_TEST(); \
+		XO_TRACE_TRIP(); \
+		flags = 0; \
+		state = done ? ST_DEAD : ST_SETUP; \
+	} while (0)
+
+	for (;;) {
+		// ---- hand new packets to the lanes that need one -------------------------
+		const u32 dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
+		if (dead_mask != 0u) {
+			if (q_count == 0u && !q_dry) {
+				// queue empty: all 32 lanes launch one packet each into the queue
+				u32 base = 0;
+				if (lane == 0u) base = atomicAdd(num_packets_done, 32u);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				const u32 n_new = base < num_packets ?
+					(num_packets - base < 32u ? num_packets - base : 32u) : 0u;
+				q_dry = n_new < 32u;
+				if (lane < n_new) {
+					Launch L_;
+					source.launch(rng, ctx, pos, L_);
+					if (XoDetSpecular::active && L_.spec_weight >= 0.0f)
+						detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
+					u32 tc = 0;
+					if (XO_TRACE & XO_TRACE_START) {
+						if (trace_event(tcfg, float_buffer, base + lane, 0u, EV_LAUNCH,
+								L_.pos, L_.dir, L_.weight, 0.0f)) tc = 1u;
+					}
+					q_a[lane] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
+					q_b[lane] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, __uint_as_float(base + lane));
+					q_l[lane] = tc;
+				}
+				__syncwarp();
+				q_count = n_new;
+			}
+			if (state == ST_DEAD) {
+				const u32 rank = (u32)__popc(dead_mask & lanemask_lt);
+				if (rank < q_count) {
+					const u32 slot = q_count - 1u - rank;
+					const float4 a = q_a[slot], b = q_b[slot];
+					trace_count = q_l[slot];
+					pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
+					dir.x = b.x; dir.y = b.y; dir.z = b.z; packet = __float_as_uint(b.w);
+					// voxel under the launch point (mcvox.template.c:206-220), kept
+					// inside the grid
+					ctx.position_to_voxel(pos, &ix, &iy, &iz);
+					ix = clipi(ix, 0, cfg.nx - 1);
+					iy = clipi(iy, 0, cfg.ny - 1);
+					iz = clipi(iz, 0, cfg.nz - 1);
+					mat = XO_VOXEL(ix, iy, iz);
+					XO_LOAD_MAT(mat);
+					opl = 0.0f;
+					flags = EV_LAUNCH;
+					state = ST_SETUP;
+					started = true;
+				} else if (q_dry) {
+					state = ST_DRY;
+				}
+			}
+			const u32 n_dead = (u32)__popc(dead_mask);
+			q_count -= (n_dead < q_count) ? n_dead : q_count;
+			__syncwarp();
+			if (q_dry) {
+				n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
+				if (n_dry == 32u) break;
+			}
+		}
+
+		// ---- a face between different materials, or the face of the grid -----------
+		// (mcvox.template.c:275-388).  The crossing step already moved the voxel
+		// index across the face on axis `state - ST_BND`.
+		if (state - ST_BND < 3u) {
+			const u32 axis = state - ST_BND;
+			bool done = false;
+			pos.x = fmaf(dir.x, t_evt, pos.x);
+			pos.y = fmaf(dir.y, t_evt, pos.y);
+			pos.z = fmaf(dir.z, t_evt, pos.z);
+			if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_evt, opl);
+			const bool escaping = !((u32)ix < gnx && (u32)iy < gny && (u32)iz < gnz);
+			const i32 next_mat = escaping ? 0 : XO_VOXEL(ix, iy, iz);
+			const float n1 = c_hot.n, n2 = sh_fast[next_mat].hot.n;
+			bool through = true;
+			if (n1 != n2) {
+				const float n12 = n1*FastMath::rcp_approx(n2);
+				const float n21 = n2*FastMath::rcp_approx(n1);
+				const float cc = (n1 > n2) ? FastMath::sqrt(fmaxf(fmaf(-n21, n21, 1.0f), 0.0f)) : 0.0f;
+				if (axis == 0u) through = fresnel_axis_fast(n12, cc, dir.x, dir.y, dir.z, rng);
+				else if (axis == 1u) through = fresnel_axis_fast(n12, cc, dir.y, dir.x, dir.z, rng);
+				else through = fresnel_axis_fast(n12, cc, dir.z, dir.x, dir.y, rng);
+			}
+			flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
+			if (through) {
+				if (escaping) {
+					if (iz < 0) {
+						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
+					} else if (iz >= cfg.nz) {
+						if (XoDetBottom::active) detectors.bottom.deposit(acc, pos, dir, weight, opl);
+					}
+					done = true;
+				} else if (next_mat != mat) {
+					mat = next_mat;
+					XO_LOAD_MAT(mat);
+				}
+			} else {
+				// reflected: back into the voxel the packet came from
+				if (axis == 0u) ix -= sx;
+				else if (axis == 1u) iy -= sy;
+				else iz -= sz;
+			}
+			XO_END_TRIP();
+		}
+
+		// ---- interaction: absorb, scatter, lottery (mcvox.template.c:925-981) -------
+		if (state == ST_SCAT) {
+			bool done = false;
+			++iterations;
+			pos.x = fmaf(dir.x, t_s, pos.x);
+			pos.y = fmaf(dir.y, t_s, pos.y);
+			pos.z = fmaf(dir.z, t_s, pos.z);
+			if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_s, opl);
+#if XO_METHOD == 1
+			if (rng.next() < c_hot.absorb) {
+				float deposit = weight;
+				done = true;
+				weight = 0.0f;
+				flags |= EV_ABSORPTION;
+				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
+			} else {
+				float fi, ct = c_pf.sample(rng, lut, &fi);
+				scatter_direction(dir, ct, fi);
+				flags |= EV_SCATTERING;
+			}
+#else
+			{
+				float deposit = weight*c_hot.absorb;
+				weight -= deposit;
+				flags |= EV_ABSORPTION;
+				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
+			}
+			float fi, ct = c_pf.sample(rng, lut, &fi);
+			scatter_direction(dir, ct, fi);
+			flags |= EV_SCATTERING;
+			if (weight < XO_WEIGHT_MIN) {
+#if XO_USE_LOTTERY
+				if (rng.next_raw() > XO_LOTTERY_CHANCE*4294967296.0f) done = true;
+				else weight *= (1.0f/XO_LOTTERY_CHANCE);
+#else
+				done = true;
+#endif
+			}
+#endif
+			XO_END_TRIP();
+		}
+
+		// ---- new ray from `pos` along `dir` in voxel (ix, iy, iz) -----------------------
+		if (state == ST_SETUP) {
+			const float rx = FastMath::rcp_approx(dir.x), ry = FastMath::rcp_approx(dir.y),
+				rz = FastMath::rcp_approx(dir.z);
+			const bool fx = dir.x >= 0.0f, fy = dir.y >= 0.0f, fz = dir.z >= 0.0f;
+			sx = fx ? 1 : -1; sy = fy ? 1 : -1; sz = fz ? 1 : -1;
+			// exit faces of the current voxel (mcvox.template.c:173-196)
+			const float facex = fmaf((float)(ix + (fx ? 1 : 0)), cfg.size.x, cfg.top_left.x);
+			const float facey = fmaf((float)(iy + (fy ? 1 : 0)), cfg.size.y, cfg.top_left.y);
+			const float facez = fmaf((float)(iz + (fz ? 1 : 0)), cfg.size.z, cfg.top_left.z);
+			tmx = (dir.x != 0.0f) ? fmaxf((facex - pos.x)*rx, 0.0f) : XO_INF;
+			tmy = (dir.y != 0.0f) ? fmaxf((facey - pos.y)*ry, 0.0f) : XO_INF;
+			tmz = (dir.z != 0.0f) ? fmaxf((facez - pos.z)*rz, 0.0f) : XO_INF;
+			tdx = cfg.size.x*fabsf(rx);
+			tdy = cfg.size.y*fabsf(ry);
+			tdz = cfg.size.z*fabsf(rz);
+			t_s = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
+#if XO_USE_RMAX
+			{   // parameter at which the ray leaves the rmax sphere around the source
+				const float ex = pos.x - src_pos.x, ey = pos.y - src_pos.y, ez = pos.z - src_pos.z;
+				const float b = ex*dir.x + ey*dir.y + ez*dir.z;
+				const float c = ex*ex + ey*ey + ez*ez - rmax2;
+				t_rmax = FastMath::sqrt(fmaxf(fmaf(b, b, -c), 0.0f)) - b;
+			}
+#endif
+			state = ST_RUN;
+		}
+
+		// ---- voxel walk: lanes in RUN state cross faces until enough lanes wait ------
+		for (;;) {
+			if (state == ST_RUN) {
+				const float tmin = fminf(tmx, fminf(tmy, tmz));
+				if (!(tmin < t_s)) {
+					state = ST_SCAT;
+				} else {
+					++iterations;
+					const bool px = (tmx == tmin);
+					const bool py = !px && (tmy == tmin);
+					const bool pz = !px && !py;
+					if (px) { tmx += tdx; ix += sx; }
+					if (py) { tmy += tdy; iy += sy; }
+					if (pz) { tmz += tdz; iz += sz; }
+					i32 m2 = -1;
+					if ((u32)ix < gnx && (u32)iy < gny && (u32)iz < gnz) m2 = XO_VOXEL(ix, iy, iz);
+#if XO_USE_RMAX
+					if (tmin > t_rmax) m2 = -1;        // first face beyond rmax: handled as an event
+#endif
+					if (m2 != mat) {
+						state = px ? ST_BND : (py ? ST_BND + 1u : ST_BND + 2u);
+						t_evt = tmin;
+					}
+#if XO_TRACE == XO_TRACE_ALL
+					else {
+						// the reference records every loop trip
+						P3 pc = { fmaf(dir.x, tmin, pos.x), fmaf(dir.y, tmin, pos.y), fmaf(dir.z, tmin, pos.z) };
+						if (trace_event(tcfg, float_buffer, packet, trace_count,
+								flags | EV_BOUNDARY_HIT | EV_REFRACTION, pc, dir, weight,
+								XO_NEEDS_OPL ? fmaf(c_hot.n, tmin, opl) : 0.0f)) ++trace_count;
+						flags = 0;
+					}
+#endif
+				}
+			}
+			const u32 n_out = (u32)__popc(__ballot_sync(0xffffffffu, state != ST_RUN));
+			if (n_out - n_dry >= refill || n_out == 32u) break;
+		}
+	}
+#undef XO_LOAD_MAT
+#undef XO_VOXEL
+#undef XO_RMAX_TEST
+#undef XO_TRACE_TRIP
+#undef XO_END_TRIP
+	// every lane drew from its stream (queue refills), whether or not it ever
+	// carried a packet: all states go back
+	rng_state_x[gid] = rng.x;
+}

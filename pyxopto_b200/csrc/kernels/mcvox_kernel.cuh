@@ -38,6 +38,22 @@ typedef TraceNone XoTrace;
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
 #define XO_FP_EPS 1.1920929e-07f
 
+// Throughput mode (albedo weight / albedo rejection) runs the DDA formulation
+// below; deterministic mode and microscopic Beer-Lambert keep the reference's
+// iteration structure (one fresh step + three face divisions per iteration).
+#define XO_VOX_DDA (!XO_DETERMINISTIC && XO_METHOD != 2)
+#ifndef XO_VOX_THRESH_MAX
+#define XO_VOX_THRESH_MAX 32
+#endif
+
+// Per-material record of the throughput loop, derived once per CTA when the
+// material table is staged in shared memory: exactly the register cache of the
+// current material (two LDS.128 on a material change).
+struct __align__(16) VoxHot { float step_k, absorb, mua, n; };
+	// step_k = -ln2/mut: step = lg2(u)*step_k
+struct __align__(16) VoxPfFast { XoPf::Fast v; };
+struct VoxFastMat { VoxHot hot; VoxPfFast pf; };
+
 struct VoxCtx {
 	const VoxCfg &cfg;
 	const VoxMaterial *materials;   // shared memory
@@ -116,7 +132,8 @@ McKernel(
 	xo::u32 lut_len,
 	xo::u32 priv_len,
 	const __grid_constant__ xo::FluWindow window,
-	xo::u32 chunk)
+	xo::u32 chunk,
+	xo::u32 refill)             // throughput mode: waiting lanes per warp that trigger their joint handling
 {
 	using namespace xo;
 	extern __shared__ __align__(16) unsigned char xo_smem[];
@@ -129,6 +146,20 @@ McKernel(
 		for (u32 i = threadIdx.x; i < mat_words; i += blockDim.x) dst[i] = src[i];
 	}
 	u32 off_words = (mat_words + 3u) & ~3u;
+#if XO_VOX_DDA
+	VoxFastMat *sh_fast = reinterpret_cast<VoxFastMat *>(reinterpret_cast<u32 *>(xo_smem) + off_words);
+	for (u32 i = threadIdx.x; i < num_materials; i += blockDim.x) {
+		const VoxMaterial &Mg = materials[i];
+		VoxFastMat F;
+		F.hot.step_k = -0.6931471805599453f*Mg.inv_mut;
+		F.hot.absorb = Mg.mua_inv_mut;
+		F.hot.mua = Mg.mua;
+		F.hot.n = Mg.n;
+		Mg.pf.prepare(F.pf.v);
+		sh_fast[i] = F;
+	}
+	off_words += num_materials*(u32)(sizeof(VoxFastMat)/4);
+#endif
 	float *sh_lut = reinterpret_cast<float *>(xo_smem) + off_words;
 	const float *lut = fp_lut;
 	if (XoPf::uses_lut && lut_len) {
@@ -142,7 +173,16 @@ McKernel(
 	acc.priv_len = priv_len;
 	acc.zero_private();
 	acc.win = acc.priv + 2*priv_len;
-	for (u32 i = threadIdx.x; i < window.ext0*window.ext1*window.ext2; i += blockDim.x) acc.win[i] = 0;
+	const u32 win_len = window.ext0*window.ext1*window.ext2;
+	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
+#if XO_VOX_DDA
+	// per-warp launch queue: 32 slots of {pos, weight | dir, packet | trace count}
+	off_words += 2*priv_len + win_len;
+	off_words = (off_words + 3u) & ~3u;
+	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
+	float4 *q_b = q_a + 32;
+	u32 *q_l = reinterpret_cast<u32 *>(xo_smem) + off_words + blockDim.x*8u + (threadIdx.x & ~31u);
+#endif
 	__syncthreads();
 
 	const u32 gid = blockIdx.x*blockDim.x + threadIdx.x;
@@ -155,6 +195,12 @@ McKernel(
 	const P3 src_pos = source.origin();
 	const float rmax2 = rmax*rmax;
 
+	bool started = false;
+	u32 iterations = 0;
+#if XO_VOX_DDA
+#include "mcvox_dda_loop.cuh"
+#else
+	(void)refill;
 	u32 pk_next, pk_end;
 #if XO_DETERMINISTIC
 	static_quota(num_packets, nthreads, gid, &pk_next, &pk_end);
@@ -165,8 +211,6 @@ McKernel(
 	pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
 	if (pk_next >= num_packets) pk_end = pk_next;
 #endif
-	bool started = false;
-	u32 iterations = 0;
 
 	if (pk_next < pk_end) {
 		started = true;
@@ -354,6 +398,7 @@ McKernel(
 		rng_state_x[gid] = rng.x;
 	}
 #undef XO_LAUNCH_PACKET
+#endif  // XO_VOX_DDA
 	if (started) atomicAdd(num_kernels, 1u);
 	{
 		const u32 mask = __activemask();

@@ -141,6 +141,35 @@ __device__ __forceinline__ bool refract3_safe(const P3 &p, const P3 &n, float n1
 	return false;
 }
 
+#if !XO_DETERMINISTIC
+// Fresnel / Snell at an interface whose normal is a coordinate axis (throughput
+// mode): dn = direction component along the normal, da / db the tangential ones,
+// n12 = n1/n2, cc = critical cosine.  One square root instead of two; the special
+// cases of `reflectance` (cos1 <= 0, sin2 == 1) fall out of the formula
+// (cos1 > cc >= 0; cos2 == 0 gives Rs = Rp^2 = 1).  Consumes one draw only above
+// the critical angle, like the reference.  Returns true when the packet passes.
+__device__ __forceinline__ bool fresnel_axis_fast(float n12, float cc, float &dn, float &da,
+		float &db, Rng &rng) {
+	float cos1 = fabsf(dn);
+	if (cos1 > cc) {
+		float s2 = (n12*n12)*fmaf(-cos1, cos1, 1.0f);
+		float cos2 = FastMath::sqrt(fmaxf(1.0f - s2, 0.0f));
+		float a = n12*cos1, b = n12*cos2;
+		float rs = (a - cos2)*FastMath::rcp_approx(a + cos2);
+		float rp = (b - cos1)*FastMath::rcp_approx(b + cos1);
+		float R = 0.5f*fmaf(rs, rs, rp*rp);
+		if (R*4294967296.0f < rng.next_raw()) {
+			da *= n12;
+			db *= n12;
+			dn = copysignf(cos2, dn);
+			return true;
+		}
+	}
+	dn = -dn;
+	return false;
+}
+#endif
+
 // ---- scattering rotation -----------------------------------------------------
 // Rotates `d` by polar cosine ct and azimuth fi, then renormalises (the
 // reference always renormalises in single precision, mcbase.template.c:1551).

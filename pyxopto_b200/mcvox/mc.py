@@ -67,7 +67,33 @@ class Mc(McBase):
         self._packed['voxels'] = self._voxels.cl_pack(self, self._packed.get('voxels'))
 
     def _medium_bytes(self) -> int:
-        return len(cltypes.raw_bytes(self._packed['materials']))
+        # packed materials + the per-material derived constants the throughput
+        # loop appends (xo::VoxFastMat, <= 48 B per material)
+        return len(cltypes.raw_bytes(self._packed['materials'])) + \
+            48*len(self._materials) + 32
+
+    # waiting lanes per warp that trigger their joint handling (throughput loop)
+    wait_lanes = 16
+
+    def _refill_lanes(self) -> int:
+        if self.refill_lanes is not None:
+            return int(min(max(self.refill_lanes, 1), 32))
+        return int(self.wait_lanes)
+
+    def _rmax_needed(self) -> bool:
+        """Packets only exist inside the voxel box: the rmax test can fire only
+        if some corner of the box is farther than rmax from the source."""
+        rmax = float(np.float32(self._rmax))
+        if not np.isfinite(rmax):
+            return False
+        src = np.asarray(self._source_focus(), dtype=np.float64)
+        v = self._voxels
+        far = 0.0
+        for x in (v.xaxis.start, v.xaxis.stop):
+            for y in (v.yaxis.start, v.yaxis.stop):
+                for z in (v.zaxis.start, v.zaxis.stop):
+                    far = max(far, float(np.linalg.norm(np.array([x, y, z]) - src)))
+        return far*(1.0 + 1e-5) >= rmax
 
     def _upload_medium(self):
         self.cl_r_buffer('materials', self._packed['materials'])
@@ -128,4 +154,5 @@ class Mc(McBase):
             dets,
             bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
             np.uint32(lut_len), np.uint32(priv_len), window, np.uint32(max(chunk, 1)),
+            np.uint32(refill),
         ]
