@@ -22,6 +22,12 @@
 //     is a small state machine and the warp runs the crossing step for the lanes
 //     in RUN state until `refill` lanes wait for something else; then the
 //     waiting lanes execute their interaction / interface / relaunch jointly.
+//   * the voxel -> material map is read from a compact copy (uint8, one voxel of
+//     sentinel padding on every side, power-of-two strides; mcvox/mc.py): the
+//     linear index is the packed coordinate triple, one add per crossing moves
+//     it, leaving the grid is a "material change" to the sentinel, and the few
+//     hundred KB around the beam stay L1-resident (the int32 map of the
+//     reference layout is 4x larger and every lookup went to L2).
 //   * new packets come from a per-warp launch queue filled by all 32 lanes
 //     together (as in mcml_kernel.cuh).
 //   * rmax: the reference tests |pos - source| > rmax after every trip.  A ray
@@ -33,7 +39,8 @@
 		ST_DEAD = 6, ST_DRY = 7 };
 	const u32 lane = threadIdx.x & 31u;
 	const u32 lanemask_lt = (1u << lane) - 1u;
-	const u32 gnx = (u32)cfg.nx, gny = (u32)cfg.ny, gnz = (u32)cfg.nz;
+	const u32 vox_bxy = vox_bx + vox_by;
+	const u32 vox_mx = (1u << vox_bx) - 1u, vox_my = (1u << vox_by) - 1u;
 	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
 	(void)tcfg; (void)chunk; (void)nthreads;
 
@@ -46,7 +53,9 @@
 	u32 packet = 0, trace_count = 0, flags = 0;
 	(void)opl; (void)packet; (void)trace_count; (void)flags;
 	// ray: voxel walk state
-	i32 ix = 0, iy = 0, iz = 0, sx = 1, sy = 1, sz = 1, mat = 0;
+	u32 idx = 0;                    // packed voxel index (x+1) | (y+1) << bx | (z+1) << bxy
+	i32 stx = 1, sty = 1, stz = 1;  // its increment per crossing on each axis
+	u32 mat = 0;
 	float tmx = 0.0f, tmy = 0.0f, tmz = 0.0f, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
 	float t_s = 0.0f, t_evt = 0.0f;
 #if XO_USE_RMAX
@@ -56,7 +65,7 @@
 	VoxHot c_hot = { 0.0f, 0.0f, 0.0f, 1.0f };
 	XoPf::Fast c_pf;
 #define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
-#define XO_VOXEL(x, y, z) __ldg(voxels + ((u32)(z)*gny + (u32)(y))*gnx + (u32)(x))
+#define XO_VOXEL(i) ((u32)__ldg(voxels8 + (i)))
 #if XO_USE_RMAX
 #define XO_RMAX_TEST() do { \
 		float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
@@ -124,11 +133,13 @@
 					dir.x = b.x; dir.y = b.y; dir.z = b.z; packet = __float_as_uint(b.w);
 					// voxel under the launch point (mcvox.template.c:206-220), kept
 					// inside the grid
+					i32 ix, iy, iz;
 					ctx.position_to_voxel(pos, &ix, &iy, &iz);
 					ix = clipi(ix, 0, cfg.nx - 1);
 					iy = clipi(iy, 0, cfg.ny - 1);
 					iz = clipi(iz, 0, cfg.nz - 1);
-					mat = XO_VOXEL(ix, iy, iz);
+					idx = (u32)(ix + 1) | ((u32)(iy + 1) << vox_bx) | ((u32)(iz + 1) << vox_bxy);
+					mat = XO_VOXEL(idx);
 					XO_LOAD_MAT(mat);
 					opl = 0.0f;
 					flags = EV_LAUNCH;
@@ -157,8 +168,9 @@
 			pos.y = fmaf(dir.y, t_evt, pos.y);
 			pos.z = fmaf(dir.z, t_evt, pos.z);
 			if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_evt, opl);
-			const bool escaping = !((u32)ix < gnx && (u32)iy < gny && (u32)iz < gnz);
-			const i32 next_mat = escaping ? 0 : XO_VOXEL(ix, iy, iz);
+			const u32 entered = XO_VOXEL(idx);
+			const bool escaping = (entered == XO_VOX_SENTINEL);
+			const u32 next_mat = escaping ? 0u : entered;
 			const float n1 = c_hot.n, n2 = sh_fast[next_mat].hot.n;
 			bool through = true;
 			if (n1 != n2) {
@@ -172,6 +184,7 @@
 			flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 			if (through) {
 				if (escaping) {
+					const i32 iz = (i32)(idx >> vox_bxy) - 1;
 					if (iz < 0) {
 						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
 					} else if (iz >= cfg.nz) {
@@ -184,9 +197,7 @@
 				}
 			} else {
 				// reflected: back into the voxel the packet came from
-				if (axis == 0u) ix -= sx;
-				else if (axis == 1u) iy -= sy;
-				else iz -= sz;
+				idx -= (u32)(axis == 0u ? stx : (axis == 1u ? sty : stz));
 			}
 			XO_END_TRIP();
 		}
@@ -238,11 +249,14 @@
 			const float rx = FastMath::rcp_approx(dir.x), ry = FastMath::rcp_approx(dir.y),
 				rz = FastMath::rcp_approx(dir.z);
 			const bool fx = dir.x >= 0.0f, fy = dir.y >= 0.0f, fz = dir.z >= 0.0f;
-			sx = fx ? 1 : -1; sy = fy ? 1 : -1; sz = fz ? 1 : -1;
-			// exit faces of the current voxel (mcvox.template.c:173-196)
-			const float facex = fmaf((float)(ix + (fx ? 1 : 0)), cfg.size.x, cfg.top_left.x);
-			const float facey = fmaf((float)(iy + (fy ? 1 : 0)), cfg.size.y, cfg.top_left.y);
-			const float facez = fmaf((float)(iz + (fz ? 1 : 0)), cfg.size.z, cfg.top_left.z);
+			stx = fx ? 1 : -1;
+			sty = (fy ? 1 : -1) << vox_bx;
+			stz = (fz ? 1 : -1) << vox_bxy;
+			// exit faces of the current voxel (mcvox.template.c:173-196); the packed
+			// index holds coordinate + 1
+			const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 0 : 1)), cfg.size.x, cfg.top_left.x);
+			const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 0 : 1)), cfg.size.y, cfg.top_left.y);
+			const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 0 : 1)), cfg.size.z, cfg.top_left.z);
 			tmx = (dir.x != 0.0f) ? fmaxf((facex - pos.x)*rx, 0.0f) : XO_INF;
 			tmy = (dir.y != 0.0f) ? fmaxf((facey - pos.y)*ry, 0.0f) : XO_INF;
 			tmz = (dir.z != 0.0f) ? fmaxf((facez - pos.z)*rz, 0.0f) : XO_INF;
@@ -272,13 +286,12 @@
 					const bool px = (tmx == tmin);
 					const bool py = !px && (tmy == tmin);
 					const bool pz = !px && !py;
-					if (px) { tmx += tdx; ix += sx; }
-					if (py) { tmy += tdy; iy += sy; }
-					if (pz) { tmz += tdz; iz += sz; }
-					i32 m2 = -1;
-					if ((u32)ix < gnx && (u32)iy < gny && (u32)iz < gnz) m2 = XO_VOXEL(ix, iy, iz);
+					if (px) { tmx += tdx; idx += (u32)stx; }
+					if (py) { tmy += tdy; idx += (u32)sty; }
+					if (pz) { tmz += tdz; idx += (u32)stz; }
+					u32 m2 = XO_VOXEL(idx);
 #if XO_USE_RMAX
-					if (tmin > t_rmax) m2 = -1;        // first face beyond rmax: handled as an event
+					if (tmin > t_rmax) m2 = ~0u;       // first face beyond rmax: handled as an event
 #endif
 					if (m2 != mat) {
 						state = px ? ST_BND : (py ? ST_BND + 1u : ST_BND + 2u);

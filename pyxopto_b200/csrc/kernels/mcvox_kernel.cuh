@@ -41,7 +41,11 @@ typedef TraceNone XoTrace;
 // Throughput mode (albedo weight / albedo rejection) runs the DDA formulation
 // below; deterministic mode and microscopic Beer-Lambert keep the reference's
 // iteration structure (one fresh step + three face divisions per iteration).
-#define XO_VOX_DDA (!XO_DETERMINISTIC && XO_METHOD != 2)
+#ifndef XO_VOX_PACKED
+#define XO_VOX_PACKED 0
+#endif
+#define XO_VOX_DDA (!XO_DETERMINISTIC && XO_METHOD != 2 && XO_VOX_PACKED)
+#define XO_VOX_SENTINEL 255
 #ifndef XO_VOX_THRESH_MAX
 #define XO_VOX_THRESH_MAX 32
 #endif
@@ -133,7 +137,10 @@ McKernel(
 	xo::u32 priv_len,
 	const __grid_constant__ xo::FluWindow window,
 	xo::u32 chunk,
-	xo::u32 refill)             // throughput mode: waiting lanes per warp that trigger their joint handling
+	xo::u32 refill,             // throughput mode: waiting lanes per warp that trigger their joint handling
+	const unsigned char *voxels8,   // throughput mode: padded uint8 material map (mcvox/mc.py)
+	xo::u32 vox_bx,             // ... its index = (x+1) | (y+1) << vox_bx | (z+1) << (vox_bx + vox_by)
+	xo::u32 vox_by)
 {
 	using namespace xo;
 	extern __shared__ __align__(16) unsigned char xo_smem[];
@@ -200,7 +207,7 @@ McKernel(
 #if XO_VOX_DDA
 #include "mcvox_dda_loop.cuh"
 #else
-	(void)refill;
+	(void)refill; (void)voxels8; (void)vox_bx; (void)vox_by;
 	u32 pk_next, pk_end;
 #if XO_DETERMINISTIC
 	static_quota(num_packets, nthreads, gid, &pk_next, &pk_end);
