@@ -35,8 +35,7 @@
 //     so the test of a crossing is one compare (compiled out by the host when
 //     the voxel box lies inside the sphere).
 {
-	enum : u32 { ST_RUN = 0, ST_SCAT = 1, ST_BND = 2 /* +axis: 2,3,4 */, ST_SETUP = 5,
-		ST_DEAD = 6, ST_DRY = 7 };
+	enum : u32 { ST_RUN = 0, ST_SCAT = 1, ST_BND = 2, ST_SETUP = 3, ST_DEAD = 4, ST_DRY = 5 };
 	const u32 lane = threadIdx.x & 31u;
 	const u32 lanemask_lt = (1u << lane) - 1u;
 	const u32 vox_bxy = vox_bx + vox_by;
@@ -53,8 +52,15 @@
 	u32 packet = 0, trace_count = 0, flags = 0;
 	(void)opl; (void)packet; (void)trace_count; (void)flags;
 	// ray: voxel walk state
-	u32 idx = 0;                    // packed voxel index (x+1) | (y+1) << bx | (z+1) << bxy
-	i32 stx = 1, sty = 1, stz = 1;  // its increment per crossing on each axis
+	// The walk keeps the low address word of the current voxel in the compact
+	// map, vlo = lo32(voxels8) + packed index (x+1) | (y+1) << bx | (z+1) << bxy;
+	// the host guarantees that the map does not straddle a 4 GB boundary, so a
+	// crossing is one 32-bit add and the high word is a constant.
+	const u32 vbase_lo = (u32)reinterpret_cast<u64>(voxels8);
+	const u32 vbase_hi = (u32)(reinterpret_cast<u64>(voxels8) >> 32);
+	u32 vlo = vbase_lo;
+	i32 stx = 1, sty = 1, stz = 1;  // address increment per crossing on each axis
+	i32 last_d = 0;                 // increment of the last crossing (names its axis)
 	u32 mat = 0;
 	float tmx = 0.0f, tmy = 0.0f, tmz = 0.0f, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
 	float t_s = 0.0f, t_evt = 0.0f;
@@ -65,7 +71,7 @@
 	VoxHot c_hot = { 0.0f, 0.0f, 0.0f, 1.0f };
 	XoPf::Fast c_pf;
 #define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
-#define XO_VOXEL(i) ((u32)__ldg(voxels8 + (i)))
+#define XO_VOXEL(lo) ((u32)__ldg(reinterpret_cast<const unsigned char *>(((u64)vbase_hi << 32) | (u64)(lo))))
 #if XO_USE_RMAX
 #define XO_RMAX_TEST() do { \
 		float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
@@ -138,8 +144,8 @@
 					ix = clipi(ix, 0, cfg.nx - 1);
 					iy = clipi(iy, 0, cfg.ny - 1);
 					iz = clipi(iz, 0, cfg.nz - 1);
-					idx = (u32)(ix + 1) | ((u32)(iy + 1) << vox_bx) | ((u32)(iz + 1) << vox_bxy);
-					mat = XO_VOXEL(idx);
+					vlo = vbase_lo + ((u32)(ix + 1) | ((u32)(iy + 1) << vox_bx) | ((u32)(iz + 1) << vox_bxy));
+					mat = XO_VOXEL(vlo);
 					XO_LOAD_MAT(mat);
 					opl = 0.0f;
 					flags = EV_LAUNCH;
@@ -160,15 +166,15 @@
 
 		// ---- a face between different materials, or the face of the grid -----------
 		// (mcvox.template.c:275-388).  The crossing step already moved the voxel
-		// index across the face on axis `state - ST_BND`.
-		if (state - ST_BND < 3u) {
-			const u32 axis = state - ST_BND;
+		// address across the face, by `last_d`.
+		if (state == ST_BND) {
+			const u32 axis = (last_d == stx) ? 0u : ((last_d == sty) ? 1u : 2u);
 			bool done = false;
 			pos.x = fmaf(dir.x, t_evt, pos.x);
 			pos.y = fmaf(dir.y, t_evt, pos.y);
 			pos.z = fmaf(dir.z, t_evt, pos.z);
 			if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_evt, opl);
-			const u32 entered = XO_VOXEL(idx);
+			const u32 entered = XO_VOXEL(vlo);
 			const bool escaping = (entered == XO_VOX_SENTINEL);
 			const u32 next_mat = escaping ? 0u : entered;
 			const float n1 = c_hot.n, n2 = sh_fast[next_mat].hot.n;
@@ -184,7 +190,7 @@
 			flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 			if (through) {
 				if (escaping) {
-					const i32 iz = (i32)(idx >> vox_bxy) - 1;
+					const i32 iz = (i32)((vlo - vbase_lo) >> vox_bxy) - 1;
 					if (iz < 0) {
 						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
 					} else if (iz >= cfg.nz) {
@@ -197,7 +203,7 @@
 				}
 			} else {
 				// reflected: back into the voxel the packet came from
-				idx -= (u32)(axis == 0u ? stx : (axis == 1u ? sty : stz));
+				vlo -= (u32)last_d;
 			}
 			XO_END_TRIP();
 		}
@@ -254,6 +260,7 @@
 			stz = (fz ? 1 : -1) << vox_bxy;
 			// exit faces of the current voxel (mcvox.template.c:173-196); the packed
 			// index holds coordinate + 1
+			const u32 idx = vlo - vbase_lo;
 			const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 0 : 1)), cfg.size.x, cfg.top_left.x);
 			const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 0 : 1)), cfg.size.y, cfg.top_left.y);
 			const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 0 : 1)), cfg.size.z, cfg.top_left.z);
@@ -276,41 +283,46 @@
 		}
 
 		// ---- voxel walk: lanes in RUN state cross faces until enough lanes wait ------
+		const u32 wake = (refill + n_dry < 32u) ? refill + n_dry : 32u;
 		for (;;) {
-			if (state == ST_RUN) {
-				const float tmin = fminf(tmx, fminf(tmy, tmz));
-				if (!(tmin < t_s)) {
-					state = ST_SCAT;
-				} else {
-					++iterations;
-					const bool px = (tmx == tmin);
-					const bool py = !px && (tmy == tmin);
-					const bool pz = !px && !py;
-					if (px) { tmx += tdx; idx += (u32)stx; }
-					if (py) { tmy += tdy; idx += (u32)sty; }
-					if (pz) { tmz += tdz; idx += (u32)stz; }
-					u32 m2 = XO_VOXEL(idx);
+#pragma unroll
+			for (int u_ = 0; u_ < XO_VOX_UNROLL; ++u_) {
+				if (state == ST_RUN) {
+					const float tmin = fminf(tmx, fminf(tmy, tmz));
+					if (!(tmin < t_s)) {
+						state = ST_SCAT;
+					} else {
+						++iterations;
+						const bool px = (tmx == tmin);
+						const bool py = !px && (tmy == tmin);
+						const bool pz = !px && !py;
+						if (px) tmx += tdx;
+						if (py) tmy += tdy;
+						if (pz) tmz += tdz;
+						last_d = px ? stx : (py ? sty : stz);
+						vlo += (u32)last_d;
+						u32 m2 = XO_VOXEL(vlo);
 #if XO_USE_RMAX
-					if (tmin > t_rmax) m2 = ~0u;       // first face beyond rmax: handled as an event
+						if (tmin > t_rmax) m2 = ~0u;   // first face beyond rmax: handled as an event
 #endif
-					if (m2 != mat) {
-						state = px ? ST_BND : (py ? ST_BND + 1u : ST_BND + 2u);
-						t_evt = tmin;
-					}
+						if (m2 != mat) {
+							state = ST_BND;
+							t_evt = tmin;
+						}
 #if XO_TRACE == XO_TRACE_ALL
-					else {
-						// the reference records every loop trip
-						P3 pc = { fmaf(dir.x, tmin, pos.x), fmaf(dir.y, tmin, pos.y), fmaf(dir.z, tmin, pos.z) };
-						if (trace_event(tcfg, float_buffer, packet, trace_count,
-								flags | EV_BOUNDARY_HIT | EV_REFRACTION, pc, dir, weight,
-								XO_NEEDS_OPL ? fmaf(c_hot.n, tmin, opl) : 0.0f)) ++trace_count;
-						flags = 0;
-					}
+						else {
+							// the reference records every loop trip
+							P3 pc = { fmaf(dir.x, tmin, pos.x), fmaf(dir.y, tmin, pos.y), fmaf(dir.z, tmin, pos.z) };
+							if (trace_event(tcfg, float_buffer, packet, trace_count,
+									flags | EV_BOUNDARY_HIT | EV_REFRACTION, pc, dir, weight,
+									XO_NEEDS_OPL ? fmaf(c_hot.n, tmin, opl) : 0.0f)) ++trace_count;
+							flags = 0;
+						}
 #endif
+					}
 				}
 			}
-			const u32 n_out = (u32)__popc(__ballot_sync(0xffffffffu, state != ST_RUN));
-			if (n_out - n_dry >= refill || n_out == 32u) break;
+			if ((u32)__popc(__ballot_sync(0xffffffffu, state != ST_RUN)) >= wake) break;
 		}
 	}
 #undef XO_LOAD_MAT

@@ -46,8 +46,8 @@ typedef TraceNone XoTrace;
 #endif
 #define XO_VOX_DDA (!XO_DETERMINISTIC && XO_METHOD != 2 && XO_VOX_PACKED)
 #define XO_VOX_SENTINEL 255
-#ifndef XO_VOX_THRESH_MAX
-#define XO_VOX_THRESH_MAX 32
+#ifndef XO_VOX_UNROLL
+#define XO_VOX_UNROLL 2             // crossing steps per warp vote
 #endif
 
 // Per-material record of the throughput loop, derived once per CTA when the

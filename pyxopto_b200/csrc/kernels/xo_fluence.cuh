@@ -30,6 +30,10 @@ __device__ __forceinline__ void flush_window(const Flu &flu, const Accu &acc, co
 #ifndef XO_FLUENCE_RATE
 #define XO_FLUENCE_RATE 0
 #endif
+// 0: the host passes an empty FluWindow (every deposit goes to the global grid)
+#ifndef XO_FLU_WINDOW
+#define XO_FLU_WINDOW 1
+#endif
 
 __device__ __forceinline__ u32 fluence_weight(float w, float mua, i32 k) {
 #if XO_FLUENCE_RATE
@@ -59,7 +63,7 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 		if (ix < nx && iy < ny && iz < nz) {
 			u32 lx = ix - win.org0, ly = iy - win.org1, lz = iz - win.org2;
 			u32 iw = fluence_weight(w, mua, k);
-			if (lx < win.ext0 && ly < win.ext1 && lz < win.ext2) {
+			if (XO_FLU_WINDOW && lx < win.ext0 && ly < win.ext1 && lz < win.ext2) {
 				if (acc.add_window((lz*win.ext1 + ly)*win.ext0 + lx, iw))
 					acc.carry_global(offset + (iz*ny + iy)*nx + ix);
 			} else {
@@ -87,7 +91,7 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 		if (ir < n_r && iz < n_z) {
 			u32 lr = ir - win.org0, lz = iz - win.org1;
 			u32 iw = fluence_weight(w, mua, k);
-			if (lr < win.ext0 && lz < win.ext1) {
+			if (XO_FLU_WINDOW && lr < win.ext0 && lz < win.ext1) {
 				if (acc.add_window(lz*win.ext0 + lr, iw)) acc.carry_global(offset + iz*n_r + ir);
 			} else {
 				acc.add_global(offset + iz*n_r + ir, iw);

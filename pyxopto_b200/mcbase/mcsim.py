@@ -180,6 +180,7 @@ class McBase(CuWorker):
                 int(bool(opts.get('MC_FLUENCE_MODE_RATE', False)))),
             '#define XO_TRACE_ALIGNED {}'.format(int(self._trace_aligned())),
             '#define XO_USE_RMAX {}'.format(int(self._rmax_needed())),
+            '#define XO_FLU_WINDOW {}'.format(int(self._window_enabled())),
             '#define XO_BLOCK {}'.format(int(block)),
             '#define XO_MIN_BLOCKS {}'.format(int(min_blocks)),
         ]
@@ -255,10 +256,14 @@ class McBase(CuWorker):
     fluence_window_bytes = None      # None: automatic
     fluence_block = FLUENCE_BLOCK
 
+    def _window_enabled(self) -> bool:
+        return self._fluence is not None and hasattr(self._fluence, 'cu_window') and \
+            self.fluence_window_bytes != 0
+
     def _fluence_window(self, block: int, base_bytes: int):
         """xo::FluWindow (6 x uint32) for the current fluence plugin."""
         none = np.zeros(6, dtype=np.uint32)
-        if self._fluence is None or not hasattr(self._fluence, 'cu_window'):
+        if not self._window_enabled():
             return none
         budget = self.fluence_window_bytes
         if budget is None:

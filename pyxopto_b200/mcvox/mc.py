@@ -130,7 +130,18 @@ class Mc(McBase):
                     raise ValueError('Voxel material indices must be in [0, {})!'.format(
                         len(self._materials)))
                 packed[1:nz + 1, 1:ny + 1, 1:nx + 1] = mat
-                self.cl_r_buffer('voxel_packed', packed)
+                # the voxel walk steps the low address word only: the map must not
+                # straddle a 4 GB boundary (re-allocate in the unlikely case it does)
+                parked = []
+                for _ in range(4):
+                    buf = self.cl_r_buffer('voxel_packed', packed)
+                    if (buf.device_ptr & 0xFFFFFFFF) + packed.nbytes <= 1 << 32:
+                        break
+                    parked.append(self._cl_buffers.pop('voxel_packed'))
+                else:
+                    raise RuntimeError('Could not place the compact voxel map inside '
+                                       'one 4 GB address window.')
+                del parked
             self._voxels_on_device = True
 
     # -- translation unit ----------------------------------------------------------

@@ -111,6 +111,48 @@ def test_throughput_mode_statistics(name):
                 type(owner).__name__, tot_gpu, tot_ref)
 
 
+@pytest.mark.parametrize('name', ['mcvox_gauss_fluence', 'mcvox_isopoint_fluencerate',
+                                  'mcml_mhg_gauss_cart_flurz'])
+def test_throughput_mode_profiles(name):
+    """Fast mode vs oracle beyond totals: every bin of the marginal profiles of
+    the fluence grid (along each axis) and every detector bin must agree within
+    5 sigma.  The throughput loops re-associate the geometry (mcvox: one ray per
+    flight + incremental voxel walk), so this pins where the energy goes."""
+    sim, geom, _ = build_sim(name)
+    n = 400000
+    sim.run(n, download=False)
+    accu, _, _ = sim.download_raw()
+    desc = xo_oracle.describe(sim, geom)
+    ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
+                        math=xo_oracle.MATH_LIBM)
+    K = 0x7FFFFF
+
+    def check(gpu, cpu, scale, what):
+        gpu = gpu.astype(np.float64)/scale/n
+        cpu = cpu.astype(np.float64)/scale/n
+        # per-packet contribution to a bin is in [0, 1] (weight units)
+        sigma = np.sqrt(np.maximum(cpu, 1e-6)/n)*np.sqrt(2)
+        bad = np.abs(gpu - cpu) > 5*sigma + 2e-5
+        assert not bad.any(), (what, np.flatnonzero(bad)[:5], gpu[bad][:5], cpu[bad][:5])
+
+    for det in sim.detectors or ():
+        for a in sim.cl_rw_accumulator_allocator.allocations(det):
+            check(accu[a.offset:a.offset + a.size], ref['accu'][a.offset:a.offset + a.size],
+                  K, type(det).__name__)
+    flu = sim.fluence
+    for a in sim.cl_rw_accumulator_allocator.allocations(flu):
+        g = accu[a.offset:a.offset + a.size].reshape(a.shape)
+        c = ref['accu'][a.offset:a.offset + a.size].reshape(a.shape)
+        k = float(flu.k)
+        if sim.resolved_options().get('MC_FLUENCE_MODE_RATE'):
+            # rate mode stores weight/mua: normalise to weight units with the
+            # smallest mua so the [0, 1] bound on a contribution holds
+            k *= 1.0/min(m.mua for m in sim.materials if m.mua > 0) if geom == 'mcvox' else 1.0
+        for axis in range(g.ndim):
+            other = tuple(i for i in range(g.ndim) if i != axis)
+            check(g.sum(axis=other), c.sum(axis=other), k, ('fluence', axis))
+
+
 def test_run_returns_reference_style_results():
     sim, _, mc = build_sim('mcml_c1_slab')
     trace, fluence, detectors = sim.run(100000)

@@ -10,6 +10,7 @@ for spec in sys.argv[3].split(';'):
     for kv in filter(None, spec.split(',')):
         k, v = kv.split('=')
         if k == 'wgsize': kw['wgsize'] = int(v)
+        elif k.startswith('D'): sim._cl_build_options.append('-%s=%s' % (k, v))
         else: setattr(sim, k, int(v))
     sim.run(10000, download=False, **kw)
     best = 1e9
