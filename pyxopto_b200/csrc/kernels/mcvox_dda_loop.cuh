@@ -53,7 +53,9 @@
 	(void)opl; (void)packet; (void)trace_count; (void)flags;
 	// ray: voxel walk state
 	// The walk keeps the low address word of the current voxel in the compact
-	// map, vlo = lo32(voxels8) + packed index (x+1) | (y+1) << bx | (z+1) << bxy;
+	// map, vlo = lo32(voxels8) + packed index (x+2) | (y+2) << bx | (z+2) << bxy
+	// (two voxels of padding: the speculative second crossing of a trip may look
+	// one voxel beyond the sentinel layer);
 	// the host guarantees that the map does not straddle a 4 GB boundary, so a
 	// crossing is one 32-bit add and the high word is a constant.
 	const u32 vbase_lo = (u32)reinterpret_cast<u64>(voxels8);
@@ -144,7 +146,7 @@
 					ix = clipi(ix, 0, cfg.nx - 1);
 					iy = clipi(iy, 0, cfg.ny - 1);
 					iz = clipi(iz, 0, cfg.nz - 1);
-					vlo = vbase_lo + ((u32)(ix + 1) | ((u32)(iy + 1) << vox_bx) | ((u32)(iz + 1) << vox_bxy));
+					vlo = vbase_lo + ((u32)(ix + 2) | ((u32)(iy + 2) << vox_bx) | ((u32)(iz + 2) << vox_bxy));
 					mat = XO_VOXEL(vlo);
 					XO_LOAD_MAT(mat);
 					opl = 0.0f;
@@ -190,7 +192,7 @@
 			flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 			if (through) {
 				if (escaping) {
-					const i32 iz = (i32)((vlo - vbase_lo) >> vox_bxy) - 1;
+					const i32 iz = (i32)((vlo - vbase_lo) >> vox_bxy) - 2;
 					if (iz < 0) {
 						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
 					} else if (iz >= cfg.nz) {
@@ -259,11 +261,11 @@
 			sty = (fy ? 1 : -1) << vox_bx;
 			stz = (fz ? 1 : -1) << vox_bxy;
 			// exit faces of the current voxel (mcvox.template.c:173-196); the packed
-			// index holds coordinate + 1
+			// index holds coordinate + 2
 			const u32 idx = vlo - vbase_lo;
-			const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 0 : 1)), cfg.size.x, cfg.top_left.x);
-			const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 0 : 1)), cfg.size.y, cfg.top_left.y);
-			const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 0 : 1)), cfg.size.z, cfg.top_left.z);
+			const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 1 : 2)), cfg.size.x, cfg.top_left.x);
+			const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 1 : 2)), cfg.size.y, cfg.top_left.y);
+			const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 1 : 2)), cfg.size.z, cfg.top_left.z);
 			tmx = (dir.x != 0.0f) ? fmaxf((facex - pos.x)*rx, 0.0f) : XO_INF;
 			tmy = (dir.y != 0.0f) ? fmaxf((facey - pos.y)*ry, 0.0f) : XO_INF;
 			tmz = (dir.z != 0.0f) ? fmaxf((facez - pos.z)*rz, 0.0f) : XO_INF;
@@ -283,43 +285,77 @@
 		}
 
 		// ---- voxel walk: lanes in RUN state cross faces until enough lanes wait ------
+		// Two crossings per trip.  The lookup of the second one is issued before
+		// the first has returned (its address needs only the face parameters):
+		// a warp waits for L2 once per two crossings, since with 20+ lanes per
+		// lookup some lane always misses L1.  The second crossing is committed
+		// only if the first one stayed inside the material.
 		const u32 wake = (refill + n_dry < 32u) ? refill + n_dry : 32u;
 		for (;;) {
-#pragma unroll
-			for (int u_ = 0; u_ < XO_VOX_UNROLL; ++u_) {
-				if (state == ST_RUN) {
-					const float tmin = fminf(tmx, fminf(tmy, tmz));
-					if (!(tmin < t_s)) {
-						state = ST_SCAT;
-					} else {
-						++iterations;
-						const bool px = (tmx == tmin);
-						const bool py = !px && (tmy == tmin);
-						const bool pz = !px && !py;
-						if (px) tmx += tdx;
-						if (py) tmy += tdy;
-						if (pz) tmz += tdz;
-						last_d = px ? stx : (py ? sty : stz);
-						vlo += (u32)last_d;
-						u32 m2 = XO_VOXEL(vlo);
+			if (state == ST_RUN) {
+				const float tmin_a = fminf(tmx, fminf(tmy, tmz));
+				if (!(tmin_a < t_s)) {
+					state = ST_SCAT;
+				} else {
+					++iterations;
+					const bool px = (tmx == tmin_a);
+					const bool py = !px && (tmy == tmin_a);
+					const bool pz = !px && !py;
+					if (px) tmx += tdx;
+					if (py) tmy += tdy;
+					if (pz) tmz += tdz;
+					last_d = px ? stx : (py ? sty : stz);
+					vlo += (u32)last_d;
+					u32 m_a = XO_VOXEL(vlo);
+					// second crossing, speculative
+					const float tmin_b = fminf(tmx, fminf(tmy, tmz));
+					const bool ok_b = tmin_b < t_s;
+					const bool qx = (tmx == tmin_b);
+					const bool qy = !qx && (tmy == tmin_b);
+					const bool qz = !qx && !qy;
+					const i32 d_b = qx ? stx : (qy ? sty : stz);
+					const u32 vlo_b = vlo + (u32)d_b;
+					u32 m_b = mat;
+					if (ok_b) m_b = XO_VOXEL(vlo_b);
 #if XO_USE_RMAX
-						if (tmin > t_rmax) m2 = ~0u;   // first face beyond rmax: handled as an event
+					// first face beyond rmax: handled as an event
+					if (tmin_a > t_rmax) m_a = ~0u;
+					if (tmin_b > t_rmax) m_b = ~0u;
 #endif
-						if (m2 != mat) {
-							state = ST_BND;
-							t_evt = tmin;
-						}
 #if XO_TRACE == XO_TRACE_ALL
-						else {
-							// the reference records every loop trip
-							P3 pc = { fmaf(dir.x, tmin, pos.x), fmaf(dir.y, tmin, pos.y), fmaf(dir.z, tmin, pos.z) };
-							if (trace_event(tcfg, float_buffer, packet, trace_count,
-									flags | EV_BOUNDARY_HIT | EV_REFRACTION, pc, dir, weight,
-									XO_NEEDS_OPL ? fmaf(c_hot.n, tmin, opl) : 0.0f)) ++trace_count;
-							flags = 0;
-						}
+#define XO_TRACE_CROSSING(tmin_) do { \
+						P3 pc_ = { fmaf(dir.x, tmin_, pos.x), fmaf(dir.y, tmin_, pos.y), fmaf(dir.z, tmin_, pos.z) }; \
+						if (trace_event(tcfg, float_buffer, packet, trace_count, \
+								flags | EV_BOUNDARY_HIT | EV_REFRACTION, pc_, dir, weight, \
+								XO_NEEDS_OPL ? fmaf(c_hot.n, tmin_, opl) : 0.0f)) ++trace_count; \
+						flags = 0; \
+					} while (0)
+#else
+#define XO_TRACE_CROSSING(tmin_) do { } while (0)
 #endif
+					if (m_a != mat) {
+						state = ST_BND;
+						t_evt = tmin_a;
+					} else {
+						XO_TRACE_CROSSING(tmin_a);      // the reference records every loop trip
+						if (!ok_b) {
+							state = ST_SCAT;
+						} else {
+							++iterations;
+							if (qx) tmx += tdx;
+							if (qy) tmy += tdy;
+							if (qz) tmz += tdz;
+							vlo = vlo_b;
+							last_d = d_b;
+							if (m_b != mat) {
+								state = ST_BND;
+								t_evt = tmin_b;
+							} else {
+								XO_TRACE_CROSSING(tmin_b);
+							}
+						}
 					}
+#undef XO_TRACE_CROSSING
 				}
 			}
 			if ((u32)__popc(__ballot_sync(0xffffffffu, state != ST_RUN)) >= wake) break;

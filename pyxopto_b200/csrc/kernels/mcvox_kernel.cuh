@@ -46,9 +46,6 @@ typedef TraceNone XoTrace;
 #endif
 #define XO_VOX_DDA (!XO_DETERMINISTIC && XO_METHOD != 2 && XO_VOX_PACKED)
 #define XO_VOX_SENTINEL 255
-#ifndef XO_VOX_UNROLL
-#define XO_VOX_UNROLL 2             // crossing steps per warp vote
-#endif
 
 // Per-material record of the throughput loop, derived once per CTA when the
 // material table is staged in shared memory: exactly the register cache of the

@@ -100,15 +100,16 @@ class Mc(McBase):
         return far*(1.0 + 1e-5) >= rmax
 
     # -- compact voxel map of the throughput loop -------------------------------------
-    # uint8 material indices in a box padded by one voxel of the sentinel 255 on
-    # every side, axis strides rounded up to powers of two: the linear index IS the
-    # packed coordinate triple (x+1) | (y+1) << bx | (z+1) << (bx+by), leaving the
-    # grid is just another "material change", and the hot region fits the L1 cache.
+    # uint8 material indices in a box padded by two voxels of the sentinel 255 on
+    # every side (the walk looks one voxel ahead speculatively), axis strides
+    # rounded up to powers of two: the linear index IS the packed coordinate triple
+    # (x+2) | (y+2) << bx | (z+2) << (bx+by), and leaving the grid is just another
+    # "material change".
     VOX_SENTINEL = 255
 
     def _vox_pack_bits(self):
         nz, ny, nx = self._voxels.shape
-        return tuple(int(n + 1).bit_length() for n in (nx, ny, nz))
+        return tuple(int(n + 3).bit_length() for n in (nx, ny, nz))
 
     def _vox_packed(self) -> bool:
         return len(self._materials) <= self.VOX_SENTINEL and sum(self._vox_pack_bits()) <= 31
@@ -129,7 +130,7 @@ class Mc(McBase):
                 if mat.size and (mat.min() < 0 or mat.max() >= len(self._materials)):
                     raise ValueError('Voxel material indices must be in [0, {})!'.format(
                         len(self._materials)))
-                packed[1:nz + 1, 1:ny + 1, 1:nx + 1] = mat
+                packed[2:nz + 2, 2:ny + 2, 2:nx + 2] = mat
                 # the voxel walk steps the low address word only: the map must not
                 # straddle a 4 GB boundary (re-allocate in the unlikely case it does)
                 parked = []
