@@ -186,7 +186,7 @@ def main():
     from pyxopto_b200.cu import abi
     geom = benchcfg.GEOMETRY[config]
     mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
-    packets = int(args.packets or {'c2_skin': 1.25e8, 'c3_vox': 1.25e7,
+    packets = int(args.packets or {'c2_skin': 1.25e8, 'c3_vox': 1e8,
                                    'c4_trace': 1e6}.get(config, 1e7))
     from pyxopto_b200 import parallel as _par
     sim = benchcfg.CONFIGS[config](mc, rnginit=_par.seed_for_rank(benchcfg.RNGINIT, rank),
@@ -350,8 +350,14 @@ def main():
             })
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
-            sample = int(args.cpu_sample or {'c2_skin': 2e6, 'c3_vox': 1e5, 'c4_trace': 2e4}.get(config, 3e5))
             try:
+                if args.cpu_sample:
+                    sample = int(args.cpu_sample)
+                else:
+                    # pilot run, then a sample sized for ~12 s of CPU work
+                    pilot = int({'c4_trace': 5e3}.get(config, 5e4))
+                    pps0, _, _ = cpu_reference_run(config, pilot, ncores)
+                    sample = int(min(max(pps0*12.0, pilot), 2e8 if config != 'c4_trace' else 1e5))
                 pps, kind, secs = cpu_reference_run(config, sample, ncores)
                 cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
                                 'kind': kind,

@@ -31,8 +31,13 @@ def run(sim, geometry: str, config: str, nphotons: int, threads: int):
     nphotons = int(nphotons)
     sim._pack(nphotons)
     so = os.path.join(HERE, '_ref', 'libref_{}.so'.format(config))
+    lib = None
     if os.path.exists(so):
-        lib = ctypes.CDLL(so)
+        try:
+            lib = ctypes.CDLL(so)
+        except OSError:          # unusable build: fall back to the port
+            lib = None
+    if lib is not None:
         lib.xo_ref_run_dynamic.argtypes = [ctypes.POINTER(XoRefArgs), ctypes.c_uint32]
         lib.xo_ref_run_dynamic.restype = None
         keep = []

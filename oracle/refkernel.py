@@ -12,6 +12,7 @@ written to a temporary directory and only the compiled ``.so`` is kept under
 import ctypes
 import hashlib
 import os
+import re
 import subprocess
 import tempfile
 
@@ -75,7 +76,10 @@ def compile_rendered(src: str, geometry: str, name: str = None,
         with open(ksrc, 'w') as f:
             f.write('#include "clshim.h"\n')
             f.write(src)
-        has_sv = ['-DXO_REF_HAS_SV'] if 'void SamplingVolume(' in src else []
+        # the SamplingVolume kernel is rendered into every source but compiled
+        # only under MC_USE_SAMPLING_VOLUME (set by Trace, mcsv.template.c)
+        has_sv = ['-DXO_REF_HAS_SV'] if re.search(
+            r'^\s*#define\s+MC_USE_SAMPLING_VOLUME\s+(TRUE|1)\b', src, re.M) else []
         cmd = ['gcc', '-std=gnu11', '-fgnu89-inline', '-w', '-fPIC', '-shared',
                '-pthread', '-I', HERE, '-DXO_REF_GEOMETRY=%d' % GEOMETRY_ID[geometry]
                ] + has_sv + cflags + [ksrc, os.path.join(HERE, 'ref_driver.c'),

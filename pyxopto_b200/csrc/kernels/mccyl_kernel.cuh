@@ -151,6 +151,7 @@ McKernel(
 	acc.priv_len = priv_len;
 	acc.zero_private();
 	acc.win = acc.priv + 2*priv_len;
+	acc.bind();
 	for (u32 i = threadIdx.x; i < window.ext0*window.ext1*window.ext2; i += blockDim.x) acc.win[i] = 0;
 	__syncthreads();
 

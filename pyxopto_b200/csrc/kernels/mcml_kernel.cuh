@@ -168,7 +168,7 @@ McKernel(
 	xo::u32 lut_len,            // floats of fp_lut staged in shared memory (0: read global)
 	xo::u32 priv_len,           // accumulator bins privatised per CTA
 	const __grid_constant__ xo::FluWindow window,   // fluence cells privatised per CTA
-	xo::u32 chunk,              // unused (kept for a stable argument list)
+	xo::u32 chunk,              // throughput mode: lanes per warp waiting for a packet that trigger a pop
 	xo::u32 refill)             // lanes per warp waiting at an interface that trigger its joint handling
 {
 	using namespace xo;
@@ -218,6 +218,7 @@ McKernel(
 	acc.priv_len = priv_len;
 	acc.zero_private();
 	acc.win = acc.priv + 2*priv_len;
+	acc.bind();
 	const u32 win_len = window.ext0*window.ext1*window.ext2;
 	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
 #if !XO_DETERMINISTIC
@@ -242,7 +243,7 @@ McKernel(
 	(void)rmax;
 #endif
 	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
-	(void)tcfg; (void)chunk;
+	(void)tcfg;
 
 	bool started = false;
 	u32 iterations = 0;
@@ -444,8 +445,12 @@ McKernel(
 
 	for (;;) {
 		// ---- hand new packets to the lanes that need one -------------------------
+		// (a lane that ran out of packets waits until `chunk` lanes need one, or
+		// nothing else is running: popping for one lane at a time would run the
+		// pop path at 1-2 lanes per warp)
 		const u32 dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
-		if (dead_mask != 0u) {
+		if (dead_mask != 0u && ((u32)__popc(dead_mask) >= chunk ||
+				__ballot_sync(0xffffffffu, state == ST_RUN) == 0u)) {
 			if (q_count == 0u && !q_dry) {
 				// queue empty: all 32 lanes launch one packet each into the queue
 				u32 base = 0;
@@ -505,6 +510,16 @@ McKernel(
 			if (go && state - 1u < 2u) {
 				const bool up = (state == ST_BND_TOP);
 				bool done = false;
+#if XO_METHOD != 2
+				{   // move onto the interface (mcml.template.c:541-582)
+					const float zb = up ? c_hot.top : c_hot.bottom;
+					const float step = (dir.z != 0.0f) ? (zb - pos.z)*FastMath::rcp_approx(dir.z) : 0.0f;
+					pos.x = fmaf(dir.x, step, pos.x);
+					pos.y = fmaf(dir.y, step, pos.y);
+					pos.z = zb;
+					if (XO_NEEDS_OPL) opl = fmaf(c_aux.n, step, opl);
+				}
+#endif
 				const MlIface I = sh_fast[layer].iface;
 				const bool through = ml_boundary_fast(up ? I.n12_top : I.n12_bottom,
 					up ? I.cc_top : I.cc_bottom, dir, rng);
@@ -535,6 +550,7 @@ McKernel(
 		const float zs = fmaf(step, dir.z, pos.z);
 		const bool hit_top = zs < c_hot.top;
 		const bool hit = hit_top || zs >= c_hot.bottom;
+#if XO_METHOD == 2
 		if (hit) {
 			const float zb = hit_top ? c_hot.top : c_hot.bottom;
 			if (dir.z != 0.0f) step = (zb - pos.z)*FastMath::rcp_approx(dir.z);
@@ -545,7 +561,6 @@ McKernel(
 		pos.x = fmaf(dir.x, step, pos.x);
 		pos.y = fmaf(dir.y, step, pos.y);
 		if (XO_NEEDS_OPL) opl = fmaf(c_aux.n, step, opl);
-#if XO_METHOD == 2
 		{
 			float frac = 1.0f - FastMath::exp(-c_aux.mua*step);
 			float deposit = frac*weight;
@@ -558,11 +573,22 @@ McKernel(
 				fluence.deposit(acc, window, dp, deposit, c_aux.mua, opl);
 			}
 		}
-#endif
 		if (hit) {
 			state = hit_top ? ST_BND_TOP : ST_BND_BOTTOM;
 			continue;
 		}
+#else
+		if (hit) {
+			// the move onto the interface (one division) is part of the deferred
+			// interface handling: the packet stays where it is until then
+			state = hit_top ? ST_BND_TOP : ST_BND_BOTTOM;
+			continue;
+		}
+		pos.z = zs;
+		pos.x = fmaf(dir.x, step, pos.x);
+		pos.y = fmaf(dir.y, step, pos.y);
+		if (XO_NEEDS_OPL) opl = fmaf(c_aux.n, step, opl);
+#endif
 		bool done = false;
 #if XO_METHOD == 1
 		if (rng.next() < c_hot.absorb) {

@@ -177,6 +177,7 @@ McKernel(
 	acc.priv_len = priv_len;
 	acc.zero_private();
 	acc.win = acc.priv + 2*priv_len;
+	acc.bind();
 	const u32 win_len = window.ext0*window.ext1*window.ext2;
 	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
 #if XO_VOX_DDA

@@ -80,14 +80,33 @@ __device__ __forceinline__ u32 f2u(float x) { return __float2uint_rz(x); }
 struct Rng {
 	u64 x;
 	u32 a;
-	__device__ __forceinline__ float next() {
+	// one step of the recurrence as IMAD.WIDE.U32 + IADD3 + IADD3.X (the plain C
+	// expression compiles to twice as many instructions: the compiler
+	// materialises the zero-extended carry word as a register pair)
+	__device__ __forceinline__ void step() {
+#if XO_DETERMINISTIC
 		x = (u64)(u32)x*(u64)a + (x >> 32);
+#else
+		u32 lo = (u32)x, hi = (u32)(x >> 32);
+		asm("{\n\t"
+			".reg .u64 p;\n\t"
+			".reg .u32 pl, ph;\n\t"
+			"mul.wide.u32 p, %0, %2;\n\t"
+			"mov.b64 {pl, ph}, p;\n\t"
+			"add.cc.u32 %0, pl, %1;\n\t"
+			"addc.u32 %1, ph, 0;\n\t"
+			"}" : "+r"(lo), "+r"(hi) : "r"(a));
+		x = ((u64)hi << 32) | lo;
+#endif
+	}
+	__device__ __forceinline__ float next() {
+		step();
 		return __uint2float_rn((u32)x)*2.3283064365386963e-10f;
 	}
 	// the same draw before the 2^-32 scaling, RN(float(lo32 x)) in [0, 2^32]:
 	// throughput-mode callers fold the scale into their own constants
 	__device__ __forceinline__ float next_raw() {
-		x = (u64)(u32)x*(u64)a + (x >> 32);
+		step();
 		return __uint2float_rn((u32)x);
 	}
 };
@@ -222,15 +241,29 @@ __device__ __forceinline__ void scatter_direction(P3 &d, float ct, float fi) {
 // when peaked (per-address serialisation in the L2 slice).
 struct FluWindow { u32 org0, org1, org2, ext0, ext1, ext2; };
 
+// 32-bit shared-memory atomic add on a shared-space address (ATOMS.ADD with the
+// address in one register; through a generic pointer the compiler rebuilds the
+// shared window base from SR_CgaCtaId before every atomic)
+__device__ __forceinline__ u32 atoms_add(u32 saddr, u32 v) {
+	u32 old;
+	asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+	return old;
+}
+__device__ __forceinline__ u32 shared_address(const void *p) {
+	return (u32)__cvta_generic_to_shared(p);
+}
+
 struct Accu {
 	u64 *global;
 	u32 *priv;        // shared memory, 2*priv_len words
 	u32 priv_len;
 	u32 *win;         // shared memory, ext0*ext1*ext2 words (0 extents: no window)
+	u32 priv_s, win_s;  // shared-space addresses of priv / win (set by bind())
+	__device__ __forceinline__ void bind() { priv_s = shared_address(priv); win_s = shared_address(win); }
 	// returns true when the 32-bit partial sum wrapped around (the caller then
 	// forwards 2^32 to the global bin with carry_global)
 	__device__ __forceinline__ bool add_window(u32 local, u32 w) const {
-		u32 old = atomicAdd(win + local, w);
+		u32 old = atoms_add(win_s + 4u*local, w);
 		return old + w < old;
 	}
 	__device__ __forceinline__ void carry_global(u32 index) const {
@@ -238,8 +271,8 @@ struct Accu {
 	}
 	__device__ __forceinline__ void add(u32 index, u32 w) const {
 		if (index < priv_len) {
-			u32 old = atomicAdd(priv + 2*index, w);
-			if (old + w < old) atomicAdd(priv + 2*index + 1, 1u);
+			u32 old = atoms_add(priv_s + 8u*index, w);
+			if (old + w < old) atoms_add(priv_s + 8u*index + 4u, 1u);
 		} else {
 			atomicAdd(global + index, (u64)w);
 		}

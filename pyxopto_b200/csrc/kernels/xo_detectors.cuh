@@ -61,6 +61,14 @@ struct DetSixAroundOne {            // mcdetector/probe/sixaroundone.py
 	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
 		u32 fiber = 7;
 		float rx = pos.x - position.x, ry = pos.y - position.y;
+#if !XO_DETERMINISTIC
+		// Early out (throughput mode): T is a rotation, so a point inside the core
+		// of any of the seven fibres lies within spacing + r_core/|a33| of the
+		// probe centre; (a + b)^2 <= 2 (a^2 + b^2) avoids the square root.  Most
+		// packets leave the surface far from the probe.
+		if (rx*rx + ry*ry > 2.0f*fmaf(core_r_squared, FastMath::rcp_approx(T.a33*T.a33),
+				core_spacing*core_spacing)) return;
+#endif
 		P3 p = { rx, ry, 0.0f };
 		P3 q = transform3(T, p);
 		if (q.x*q.x + q.y*q.y <= core_r_squared) fiber = 0;

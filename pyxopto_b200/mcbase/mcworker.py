@@ -102,6 +102,7 @@ class CuWorker:
         self._seeds_on_device = False
         self._modules = {}
         self._events = None
+        self._pinned_downloads = {}
 
     # -- device ---------------------------------------------------------------
     def _device_ordinal(self) -> int:
@@ -221,6 +222,8 @@ class CuWorker:
             self.cl_r_buffer('rng_seeds_a', self._rng_seeds_a)
             self._seeds_on_device = True
 
+    PINNED_MIN_BYTES = 1 << 20
+
     def _download_allocations(self, owner, nphotons: int):
         """{dtype: [ndarray per allocation]} for one plugin (cf. mc.py:1020-1038)."""
         out = {}
@@ -231,6 +234,16 @@ class CuWorker:
                     continue
                 if hasattr(owner, 'np_buffer'):
                     host = owner.np_buffer(self, a, nphotons=nphotons)
+                elif kind == 'accumulator' and a.size*alloc.dtype.itemsize >= self.PINNED_MIN_BYTES:
+                    # large grids (201^3 x 8 B = 65 MB) come back through a page-locked
+                    # staging array that is reused by every run: update_data() only
+                    # reads the raw integers (raw += accu*(1/k))
+                    key = (kind, a.offset, a.shape)
+                    host = self._pinned_downloads.get(key)
+                    if host is None:
+                        self._pinned_downloads.clear()
+                        host = abi.pinned_empty(self._ctx, a.shape, a.dtype)
+                        self._pinned_downloads[key] = host
                 else:
                     host = np.empty(a.shape, dtype=a.dtype)
                 buf.download(self._stream, host, offset=a.offset*alloc.dtype.itemsize)

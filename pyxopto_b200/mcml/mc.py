@@ -53,6 +53,10 @@ class Mc(McBase):
                              'change between simulation calls!')
         self._packed['layers'] = self._layers.cl_pack(self, self._packed.get('layers'))
 
+    # lanes of a warp waiting for a new packet that trigger a pop from the warp's
+    # launch queue (throughput mode)
+    pop_batch = 1
+
     def _medium_bytes(self) -> int:
         # packed layers + the per-layer derived constants the kernel appends
         # (xo::MlFastLayer, <= 96 B per layer)
@@ -110,6 +114,7 @@ class Mc(McBase):
             self._packed_or_dummy('fluence', 4),
             dets,
             bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
-            np.uint32(lut_len), np.uint32(priv_len), window, np.uint32(max(chunk, 1)),
+            np.uint32(lut_len), np.uint32(priv_len), window,
+            np.uint32(min(max(int(self.pop_batch), 1), 32)),
             np.uint32(refill),
         ]
