@@ -60,15 +60,13 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 		u32 ix = (u32)__float2int_rd((pos.x - top_left.x)*inv_step.x);
 		u32 iy = (u32)__float2int_rd((pos.y - top_left.y)*inv_step.y);
 		u32 iz = (u32)__float2int_rd((pos.z - top_left.z)*inv_step.z);
-		if (ix < nx && iy < ny && iz < nz) {
-			u32 lx = ix - win.org0, ly = iy - win.org1, lz = iz - win.org2;
-			u32 iw = fluence_weight(w, mua, k);
-			if (XO_FLU_WINDOW && lx < win.ext0 && ly < win.ext1 && lz < win.ext2) {
-				if (acc.add_window((lz*win.ext1 + ly)*win.ext0 + lx, iw))
-					acc.carry_global(offset + (iz*ny + iy)*nx + ix);
-			} else {
-				acc.add_global(offset + (iz*ny + iy)*nx + ix, iw);
-			}
+		u32 lx = ix - win.org0, ly = iy - win.org1, lz = iz - win.org2;
+		// the window lies inside the grid: a hit there needs no grid bounds test
+		if (XO_FLU_WINDOW && lx < win.ext0 && ly < win.ext1 && lz < win.ext2) {
+			if (acc.add_window((lz*win.ext1 + ly)*win.ext0 + lx, fluence_weight(w, mua, k)))
+				acc.carry_global(offset + (iz*ny + iy)*nx + ix);
+		} else if (ix < nx && iy < ny && iz < nz) {
+			acc.add_global(offset + (iz*ny + iy)*nx + ix, fluence_weight(w, mua, k));
 		}
 	}
 	__device__ __forceinline__ u32 window_index(const FluWindow &win, u32 local) const {
@@ -88,14 +86,13 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 		float r = M::sqrt(dx*dx + dy*dy);
 		float dz = pos.z - center.z;
 		u32 ir = (u32)__float2int_rd(r*inv_dr), iz = (u32)__float2int_rd(dz*inv_dz);
-		if (ir < n_r && iz < n_z) {
-			u32 lr = ir - win.org0, lz = iz - win.org1;
-			u32 iw = fluence_weight(w, mua, k);
-			if (XO_FLU_WINDOW && lr < win.ext0 && lz < win.ext1) {
-				if (acc.add_window(lz*win.ext0 + lr, iw)) acc.carry_global(offset + iz*n_r + ir);
-			} else {
-				acc.add_global(offset + iz*n_r + ir, iw);
-			}
+		u32 lr = ir - win.org0, lz = iz - win.org1;
+		// the window lies inside the grid: a hit there needs no grid bounds test
+		if (XO_FLU_WINDOW && lr < win.ext0 && lz < win.ext1) {
+			if (acc.add_window(lz*win.ext0 + lr, fluence_weight(w, mua, k)))
+				acc.carry_global(offset + iz*n_r + ir);
+		} else if (ir < n_r && iz < n_z) {
+			acc.add_global(offset + iz*n_r + ir, fluence_weight(w, mua, k));
 		}
 	}
 	__device__ __forceinline__ u32 window_index(const FluWindow &win, u32 local) const {

@@ -153,6 +153,54 @@ def test_throughput_mode_profiles(name):
             check(g.sum(axis=other), c.sum(axis=other), k, ('fluence', axis))
 
 
+@pytest.mark.parametrize('config,n', [('c1_slab', 10**8), ('c2_skin', 5*10**7),
+                                      ('c3_vox', 2*10**7), ('c5_cyl', 2*10**7)])
+def test_fast_mode_agrees_with_deterministic_mode_at_scale(config, n):
+    """BASELINE.json's fast-mode criterion at full size: totals of every detector
+    and of the fluence grid from the throughput kernel agree with the
+    deterministic kernel (bit-exact against the oracle, see above) within 3 sigma
+    and 1e-3 relative at 1e8 packets (1e-3 scaled by sqrt(1e8/n) for the smaller
+    runs); the fluence depth profile agrees bin by bin within 4 sigma."""
+    import importlib
+    import benchcfg
+    from pyxopto_b200.mcbase import mcoptions
+    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(benchcfg.GEOMETRY[config]))
+    res = []
+    for opts in ([], [mcoptions.McDeterministic.on]):
+        sim = benchcfg.CONFIGS[config](mc, options=opts)
+        sim.run(n, download=False)
+        res.append((sim, sim.download_raw()[0]))
+    (sim, fast), (_, det) = res
+    rel_tol = 1e-3*np.sqrt(1e8/n)
+    K = float(0x7FFFFF)
+    owners = [d for d in (sim.detectors or ())] + ([sim.fluence] if sim.fluence else [])
+    checked = 0
+    for owner in owners:
+        scale = float(owner.k) if owner is sim.fluence else K
+        for a in sim.cl_rw_accumulator_allocator.allocations(owner):
+            f = fast[a.offset:a.offset + a.size].astype(np.float64)/scale/n
+            d = det[a.offset:a.offset + a.size].astype(np.float64)/scale/n
+            tf, td = f.sum(), d.sum()
+            sigma = np.sqrt(max(td, 1e-9)/n)*np.sqrt(2)
+            assert abs(tf - td) <= 3*sigma + 1e-7, (type(owner).__name__, tf, td, sigma)
+            if td > 0.01:
+                assert abs(tf - td) <= rel_tol*td, (type(owner).__name__, tf, td)
+            checked += 1
+            if owner is sim.fluence:
+                # depth profile: sum over all but the slowest (z) axis
+                fz = f.reshape(a.shape).reshape(a.shape[0], -1).sum(axis=1) if len(a.shape) > 1 \
+                    else f
+                dz = d.reshape(a.shape).reshape(a.shape[0], -1).sum(axis=1) if len(a.shape) > 1 \
+                    else d
+                if type(owner).__name__ == 'FluenceRz':
+                    fz = f.reshape(-1, owner.shape[0]).sum(axis=1)
+                    dz = d.reshape(-1, owner.shape[0]).sum(axis=1)
+                sig = np.sqrt(np.maximum(dz, 1e-9)/n)*np.sqrt(2)
+                bad = np.abs(fz - dz) > 4*sig + 1e-7
+                assert not bad.any(), (np.flatnonzero(bad)[:5], fz[bad][:5], dz[bad][:5])
+    assert checked > 0
+
+
 def test_run_returns_reference_style_results():
     sim, _, mc = build_sim('mcml_c1_slab')
     trace, fluence, detectors = sim.run(100000)
