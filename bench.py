@@ -317,10 +317,22 @@ def main():
         iter_per_launch = float(np.mean(iters))
         achieved = iter_per_launch*(alu_ops + sfu_ops)/(k_ms*1e-3)
         achieved_sfu = iter_per_launch*sfu_ops/(k_ms*1e-3)
+        # DRAM bytes of the kernel from the committed ncu capture (per launch, at the
+        # capture's launch size; the working set of this path lives in L2)
+        traffic, traffic_note = None, None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+                tr = json.load(f).get(config)
+            if tr:
+                traffic = tr['dram_bytes']
+                traffic_note = 'dram read+write bytes of one McKernel launch of {:.0e} packets ' \
+                               '({})'.format(tr['launch_packets'], tr['capture'])
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {
             'bound': 'issue', 'achieved': achieved/1e9, 'peak': issue_peak/1e9,
             'unit': 'G thread-instr/s', 'frac': achieved/issue_peak,
-            'traffic': None,
+            'traffic': traffic, 'traffic_note': traffic_note,
             'kernel': 'McKernel', 'kernel_ms': k_ms,
             'iterations_per_launch': iter_per_launch,
             'iterations_per_packet': iter_per_launch/per_step,

@@ -108,6 +108,34 @@ void xo_ref_run_dynamic(const xo_ref_args *a, uint32_t nthreads) {
 	free(th); free(wa);
 }
 
+/* P host threads executing `nitems` >= P work-items (thread p runs work-items
+ * p, p+P, ...): what an OpenCL CPU runtime does with a global size larger than
+ * the core count.  Needed for mccyl, whose reference kernel gives every
+ * work-item a budget of 1e6 loop trips (mccyl.template.c:681). */
+typedef struct { const xo_ref_args *a; uint32_t first, stride, nitems; } items_arg;
+static void *items_worker(void *p) {
+	items_arg *w = (items_arg *)p;
+	for (uint32_t gid = w->first; gid < w->nitems; gid += w->stride) {
+		if (*(volatile uint32_t *)w->a->num_packets_done >= w->a->num_packets) break;
+		xo_ref_global_id = gid;
+		call_kernel(w->a, w->a->num_packets, w->a->num_packets_done,
+			w->a->int_buffer, w->a->float_buffer);
+	}
+	return NULL;
+}
+
+void xo_ref_run_dynamic_items(const xo_ref_args *a, uint32_t nthreads, uint32_t nitems) {
+	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t)*nthreads);
+	items_arg *wa = (items_arg *)malloc(sizeof(items_arg)*nthreads);
+	for (uint32_t t = 0; t < nthreads; ++t) {
+		wa[t].a = a; wa[t].first = t; wa[t].stride = nthreads; wa[t].nitems = nitems;
+		pthread_create(&th[t], NULL, items_worker, &wa[t]);
+	}
+	for (uint32_t t = 0; t < nthreads; ++t)
+		pthread_join(th[t], NULL);
+	free(th); free(wa);
+}
+
 #ifdef XO_REF_HAS_SV
 /* the reference's SamplingVolume kernel (mcsv.template.c:236), one work-item:
  * no random numbers, integer accumulation -> schedule independent */

@@ -38,8 +38,14 @@ def run(sim, geometry: str, config: str, nphotons: int, threads: int):
         except OSError:          # unusable build: fall back to the port
             lib = None
     if lib is not None:
-        lib.xo_ref_run_dynamic.argtypes = [ctypes.POINTER(XoRefArgs), ctypes.c_uint32]
-        lib.xo_ref_run_dynamic.restype = None
+        lib.xo_ref_run_dynamic_items.argtypes = [ctypes.POINTER(XoRefArgs), ctypes.c_uint32,
+                                                 ctypes.c_uint32]
+        lib.xo_ref_run_dynamic_items.restype = None
+        # work-items: one per host thread; mccyl gives each work-item a budget of
+        # 1e6 loop trips (mccyl.template.c:681), so it needs many more
+        nitems = int(threads)
+        if geometry == 'mccyl':
+            nitems = int(min(max(threads, nphotons//1000 + threads), len(sim.rng_seeds_x)))
         keep = []
 
         def buf(raw, minsize=16):
@@ -54,8 +60,8 @@ def run(sim, geometry: str, config: str, nphotons: int, threads: int):
         lut = sim.float_r_lut_manager.pack_into(None).astype(np.float32)
         done = np.zeros(1, np.uint32)
         nk = np.zeros(1, np.uint32)
-        x = sim.rng_seeds_x[:threads].copy()
-        a = np.ascontiguousarray(sim.rng_seeds_a[:threads])
+        x = sim.rng_seeds_x[:nitems].copy()
+        a = np.ascontiguousarray(sim.rng_seeds_a[:nitems])
         args = XoRefArgs()
         args.num_packets = nphotons
         args.num_packets_done = done.ctypes.data
@@ -82,9 +88,9 @@ def run(sim, geometry: str, config: str, nphotons: int, threads: int):
         args.float_buffer = floats.ctypes.data
         args.accumulator_buffer = accu.ctypes.data
         t = time.perf_counter()
-        lib.xo_ref_run_dynamic(ctypes.byref(args), int(threads))
+        lib.xo_ref_run_dynamic_items(ctypes.byref(args), int(threads), nitems)
         dt = time.perf_counter() - t
-        assert int(done[0]) >= nphotons
+        assert int(done[0]) >= nphotons, (int(done[0]), nphotons)
         return nphotons/dt, 'reference', dt
     desc = xo_oracle.describe(sim, geometry)
     t = time.perf_counter()
