@@ -675,6 +675,81 @@ static inline p3f source_position(const xo_oracle_job *j) {
 }
 
 /* ---- mcml boundary: mcml.template.c:80-203 --------------------------------- */
+/* ---- sample surface layouts (mcml) ----------------------------------------- */
+/* mcsurface/lambertian.py: struct {reflectance, specular} */
+typedef struct { float reflectance, specular; } surf_lambertian;
+/* mcsurface/probe/sixaroundone.py:87-103 */
+typedef struct { m3f T; p2f position; float core_spacing;
+	float cladding_r_squared, cladding_n, cladding_cc;
+	float core_r_squared, core_n, core_cc;
+	float cutout_r_squared, cutout_n, cutout_cc;
+	float probe_r_squared, probe_reflectivity; } surf_six;
+enum { SURF_CONTINUE = 0, SURF_REFLECTED = 1 };
+
+static int surf_six_fiber(const surf_six *l, float r2, float *n2, float *cc) {
+	if (r2 <= l->cladding_r_squared) {
+		if (r2 <= l->core_r_squared) { *n2 = l->core_n; *cc = l->core_cc; return 1; }
+		*n2 = l->cladding_n; *cc = l->cladding_cc;
+		return 1;
+	}
+	return 0;
+}
+
+/* mcsim_{top,bottom}_surface_layout_handler of the plugin at surface `which` */
+static int surface_layout_handler(sim_t *s, int which, float *n2, float *cc) {
+	const xo_oracle_job *j = s->job;
+	const char *base = (const char *)j->surface + j->surf_offset[which];
+	switch (j->surf_kind[which]) {
+	case XO_SURF_LAMBERTIAN: {                         /* mcsurface/lambertian.py:78-113 */
+		const surf_lambertian *l = (const surf_lambertian *)base;
+		float sin_fi, cos_fi, sin_theta, cos_theta;
+		if (sim_random(s) > l->specular) {
+			sin_theta = m_sqrt(sim_random(s));
+			cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+			m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+			{
+				float z = fsign(-s->dir.z)*cos_theta;
+				s->dir.x = cos_fi*sin_theta;
+				s->dir.y = sin_fi*sin_theta;
+				s->dir.z = z;
+			}
+		} else {
+			s->dir.z = -s->dir.z;
+		}
+		s->weight = s->weight*l->reflectance;
+		return SURF_REFLECTED;
+	}
+	case XO_SURF_SIXAROUNDONE: {                       /* mcsurface/probe/sixaroundone.py:156-290 */
+		const surf_six *l = (const surf_six *)base;
+		p3f rel = { s->pos.x - l->position.x, s->pos.y - l->position.y, FP_0 };
+		p3f mc_pos, lp; float dx, dy, r2;
+		m3f T = l->T;
+		mc_pos.x = rel.x; mc_pos.y = rel.y; mc_pos.z = FP_0;
+		transform3(&T, &mc_pos, &lp);
+		dx = lp.x; dy = lp.y; r2 = dx*dx + dy*dy;
+		if (surf_six_fiber(l, r2, n2, cc)) return SURF_CONTINUE;
+		mc_pos.x = fabsf(rel.x) - l->core_spacing; mc_pos.y = rel.y;
+		transform3(&T, &mc_pos, &lp);
+		dx = lp.x; dy = lp.y; r2 = dx*dx + dy*dy;
+		if (surf_six_fiber(l, r2, n2, cc)) return SURF_CONTINUE;
+		mc_pos.x = fabsf(rel.x) - l->core_spacing*FP_0p5;
+		mc_pos.y = fabsf(rel.y) - l->core_spacing*FP_COS_30;
+		transform3(&T, &mc_pos, &lp);
+		dx = lp.x; dy = lp.y; r2 = dx*dx + dy*dy;
+		if (surf_six_fiber(l, r2, n2, cc)) return SURF_CONTINUE;
+		dx = rel.x; dy = rel.y; r2 = dx*dx + dy*dy;
+		if (r2 <= l->cutout_r_squared) { *n2 = l->cutout_n; *cc = l->cutout_cc; return SURF_CONTINUE; }
+		if (r2 <= l->probe_r_squared) {
+			s->dir.z = -s->dir.z;
+			s->weight = s->weight*l->probe_reflectivity;
+			return SURF_REFLECTED;
+		}
+		return SURF_CONTINUE;
+	}
+	}
+	return SURF_CONTINUE;
+}
+
 static uint32_t boundary_mcml(sim_t *s, int32_t next_index) {
 	const xo_oracle_job *j = s->job;
 	const ml_layer *cur = ml_layer_at(j, s->layer_index);
@@ -683,6 +758,12 @@ static uint32_t boundary_mcml(sim_t *s, int32_t next_index) {
 	p3f *dir = &s->dir;
 	cos_crit = (dir->z < FP_0) ? cur->cc_top : cur->cc_bottom;
 	n2 = nxt->n;
+	/* surface layouts (mcml.template.c:100-126) */
+	if (j->surf_kind[0] != XO_SURF_NONE && next_index == 0) {
+		if (surface_layout_handler(s, 0, &n2, &cos_crit) != SURF_CONTINUE) return EV_REFLECTION;
+	} else if (j->surf_kind[1] != XO_SURF_NONE && next_index == (int32_t)j->num_layers - 1) {
+		if (surface_layout_handler(s, 1, &n2, &cos_crit) != SURF_CONTINUE) return EV_REFLECTION;
+	}
 	if (cur->n == n2) {
 		s->layer_index = next_index;
 		return EV_REFRACTION;

@@ -31,6 +31,7 @@ enum {
 	XO_FLU_NONE = 0, XO_FLU_XYZ = 1, XO_FLU_RZ = 2, XO_FLU_XYZT = 3,
 	XO_FLU_RZT = 4, XO_FLU_CYL = 5
 };
+enum { XO_SURF_NONE = 0, XO_SURF_LAMBERTIAN = 1, XO_SURF_SIXAROUNDONE = 2 };
 enum { XO_TRACE_NONE = 0, XO_TRACE_START = 1, XO_TRACE_END = 2, XO_TRACE_ALL = 7 };
 
 typedef struct xo_oracle_job {
@@ -51,7 +52,8 @@ typedef struct xo_oracle_job {
 	int32_t trace_flags;       /* MC_USE_TRACE value */
 	int32_t use_events;        /* MC_USE_EVENTS (trace event mask active) */
 	int32_t track_opl;         /* MC_TRACK_OPTICAL_PATHLENGTH */
-	int32_t reserved[4];
+	int32_t surf_kind[2];      /* top, bottom surface layout (mcml) */
+	int32_t surf_offset[2];    /* byte offsets inside the packed McSurfaceLayouts */
 
 	/* run-time kernel arguments (mcml.template.c:346-376, mcvox.template.c:548) */
 	uint32_t num_packets;
@@ -65,6 +67,7 @@ typedef struct xo_oracle_job {
 	const void *detectors;
 	const void *fluence;
 	const void *trace;
+	const void *surface;       /* packed McSurfaceLayouts (mcml; may be NULL) */
 	const float *fp_lut;
 	uint64_t *rng_x;           /* in/out, one per work-item */
 	const uint32_t *rng_a;

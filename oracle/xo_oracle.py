@@ -31,6 +31,8 @@ DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
             'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10}
 DET_KIND_TOTAL_CYL = 11
+SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
+             'SixAroundOne': 2}
 FLU_KIND = {'NoneType': 0, 'Fluence': 1, 'FluenceRz': 2, 'Fluencet': 3,
             'FluenceRzt': 4, 'FluenceCyl': 5}
 
@@ -45,13 +47,15 @@ class Job(ctypes.Structure):
         ('det_kind', ctypes.c_int32*3), ('det_offset', ctypes.c_int32*3),
         ('fluence_kind', ctypes.c_int32), ('fluence_rate', ctypes.c_int32),
         ('trace_flags', ctypes.c_int32), ('use_events', ctypes.c_int32),
-        ('track_opl', ctypes.c_int32), ('reserved', ctypes.c_int32*4),
+        ('track_opl', ctypes.c_int32),
+        ('surf_kind', ctypes.c_int32*2), ('surf_offset', ctypes.c_int32*2),
         ('num_packets', ctypes.c_uint32), ('num_threads', ctypes.c_uint32),
         ('rmax', ctypes.c_float), ('num_layers', ctypes.c_uint32),
         ('layers', ctypes.c_void_p), ('voxel_cfg', ctypes.c_void_p),
         ('voxels', ctypes.c_void_p), ('source', ctypes.c_void_p),
         ('detectors', ctypes.c_void_p), ('fluence', ctypes.c_void_p),
-        ('trace', ctypes.c_void_p), ('fp_lut', ctypes.c_void_p),
+        ('trace', ctypes.c_void_p), ('surface', ctypes.c_void_p),
+        ('fp_lut', ctypes.c_void_p),
         ('rng_x', ctypes.c_void_p), ('rng_a', ctypes.c_void_p),
         ('int_buffer', ctypes.c_void_p), ('float_buffer', ctypes.c_void_p),
         ('accumulator_buffer', ctypes.c_void_p),
@@ -182,6 +186,15 @@ def describe(mc_obj, geometry: str) -> dict:
             det_off[i] = getattr(dstruct, loc).offset
         d['detectors'] = _raw(P['detectors'])
     d['det_kind'], d['det_offset'] = det_kind, det_off
+    surf = getattr(mc_obj, 'surface', None)
+    d['surf_kind'], d['surf_offset'] = [0, 0], [0, 0]
+    if surf is not None and geometry == 'mcml':
+        packed = P.get('surface_layouts', P.get('surface'))     # reference / this repo
+        sstruct = type(packed)
+        for i, loc in enumerate(('top', 'bottom')):
+            d['surf_kind'][i] = SURF_KIND[_name(getattr(surf, loc))]
+            d['surf_offset'][i] = getattr(sstruct, loc).offset
+        d['surface'] = _raw(packed)
     flu = mc_obj.fluence
     d['fluence_kind'] = FLU_KIND[_name(flu)]
     if flu is not None:
@@ -250,6 +263,10 @@ def run(desc: dict, nphotons: int, nthreads: int, rng_x: np.ndarray,
     job.detectors = buf(desc.get('detectors', b''))
     job.fluence = buf(desc.get('fluence', b''))
     job.trace = buf(desc.get('trace', b''))
+    job.surface = buf(desc.get('surface', b''))
+    for i in range(2):
+        job.surf_kind[i] = desc.get('surf_kind', [0, 0])[i]
+        job.surf_offset[i] = desc.get('surf_offset', [0, 0])[i]
     if desc['geometry'] == 'mcvox':
         job.voxel_cfg = buf(desc['voxel_cfg'])
         vox = np.ascontiguousarray(desc['voxels'], np.int32)

@@ -43,6 +43,7 @@
 #include "xo_pf.cuh"
 #include "xo_detectors.cuh"
 #include "xo_fluence.cuh"
+#include "xo_surface.cuh"
 #include "mcml_sources.cuh"
 
 #ifndef XO_USE_RMAX
@@ -69,6 +70,7 @@ struct __align__(16) MlPfFast { XoPf::Fast v; };
 struct MlFastLayer { MlHot hot; MlPfFast pf; MlAux aux; MlIface iface; };
 
 typedef Detectors<XoDetTop, XoDetBottom, XoDetSpecular> XoDetectors;
+typedef SurfaceLayouts<XoSurfTop, XoSurfBottom> XoSurface;
 #if XO_TRACE
 typedef TraceCfg XoTrace;
 #else
@@ -90,9 +92,19 @@ struct MlCtx {
 // uniform draw is consumed only when the indices differ and incidence is above
 // the critical angle.
 __device__ __forceinline__ u32 ml_boundary(const MlLayer &cur, const MlLayer &nxt,
-		P3 &dir, i32 &layer, i32 next_layer, Rng &rng) {
+		P3 &dir, i32 &layer, i32 next_layer, Rng &rng,
+		const XoSurface &surface, const P3 &pos, float &weight, i32 num_layers) {
 	float cc = (dir.z < 0.0f) ? cur.cc_top : cur.cc_bottom;
 	float n1 = cur.n, n2 = nxt.n;
+	// surface layouts (mcml.template.c:100-126): may override n2 / cc at the
+	// point of incidence, or reflect the packet themselves
+	if (XoSurfTop::active && next_layer == 0) {
+		if (surface.top.handle(rng, pos, dir, weight, &n2, &cc) != SURF_CONTINUE)
+			return EV_REFLECTION;
+	} else if (XoSurfBottom::active && next_layer == num_layers - 1) {
+		if (surface.bottom.handle(rng, pos, dir, weight, &n2, &cc) != SURF_CONTINUE)
+			return EV_REFLECTION;
+	}
 	if (n1 == n2) { layer = next_layer; return EV_REFRACTION; }
 	dir.z = -dir.z;
 	float cos1 = fabsf(dir.z);
@@ -158,6 +170,7 @@ McKernel(
 	xo::u32 num_layers,
 	const xo::MlLayer *layers,
 	const __grid_constant__ XoSource source,
+	const __grid_constant__ xo::XoSurface surface,
 	const __grid_constant__ xo::XoTrace trace,
 	const __grid_constant__ XoFluence fluence,
 	const __grid_constant__ xo::XoDetectors detectors,
@@ -344,7 +357,8 @@ McKernel(
 			}
 #endif
 			if (next_layer != layer) {
-				u32 bf = ml_boundary(L, sh_layers[next_layer], dir, layer, next_layer, rng);
+				u32 bf = ml_boundary(L, sh_layers[next_layer], dir, layer, next_layer, rng,
+					surface, pos, weight, (i32)num_layers);
 				flags |= bf | EV_BOUNDARY_HIT;
 				if (layer <= 0) {
 					if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
@@ -521,8 +535,23 @@ McKernel(
 				}
 #endif
 				const MlIface I = sh_fast[layer].iface;
-				const bool through = ml_boundary_fast(up ? I.n12_top : I.n12_bottom,
-					up ? I.cc_top : I.cc_bottom, dir, rng);
+				float n12 = up ? I.n12_top : I.n12_bottom, cc = up ? I.cc_top : I.cc_bottom;
+				bool through;
+				int surf = SURF_CONTINUE;
+				if ((XoSurfTop::active && up && layer == 1) ||
+						(XoSurfBottom::active && !up && layer == (i32)num_layers - 2)) {
+					// sample surface with a layout (mcml.template.c:100-126)
+					const float n_out = sh_layers[up ? 0 : (i32)num_layers - 1].n;
+					float n2 = n_out;
+					surf = up ? surface.top.handle(rng, pos, dir, weight, &n2, &cc)
+						: surface.bottom.handle(rng, pos, dir, weight, &n2, &cc);
+					if (n2 != n_out) {
+						const float n1 = sh_layers[layer].n;
+						n12 = (n1 == n2) ? 1.0f : n1*FastMath::rcp_approx(n2);
+					}
+				}
+				if (surf != SURF_CONTINUE) through = false;
+				else through = ml_boundary_fast(n12, cc, dir, rng);
 				flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 				if (through) {
 					layer += up ? -1 : 1;

@@ -1,0 +1,102 @@
+// xo_surface.cuh -- sample surface layouts of the layered kernel.
+//
+// Struct members = packed `Mc{Top,Bottom}SurfaceLayout` of the reference plugins
+// (xopto/mcml/mcsurface/{base,lambertian}.py, mcsurface/probe/sixaroundone.py
+// `cl_type`).  `handle()` restates `mcsim_{top,bottom}_surface_layout_handler`:
+// it is called when a packet reaches the sample surface, before the Fresnel
+// logic of the interface (mcml.template.c:100-126), and either
+//   * returns SURF_CONTINUE, possibly after overriding the refractive index n2 /
+//     critical cosine cc of the medium behind the surface at the point of
+//     incidence (fibre core, cladding, cut-out), or
+//   * reflects the packet itself (direction, weight) and returns SURF_REFLECTED.
+#pragma once
+#include "xo_core.cuh"
+
+namespace xo {
+
+enum { SURF_CONTINUE = 0, SURF_REFLECTED = 1 };
+
+// absent layout: SurfaceLayoutDefault {int64 dummy} (mcsurface/base.py:124-152)
+struct SurfNone {
+	i64 dummy;
+	static constexpr bool active = false;
+	__device__ __forceinline__ int handle(Rng &, const P3 &, P3 &, float &, float *, float *) const {
+		return SURF_CONTINUE;
+	}
+};
+
+struct SurfLambertian {             // mcsurface/lambertian.py
+	float reflectance, specular;
+	static constexpr bool active = true;
+	__device__ __forceinline__ int handle(Rng &rng, const P3 &pos, P3 &dir, float &weight,
+			float *n2, float *cc) const {
+		(void)pos; (void)n2; (void)cc;
+		if (rng.next() > specular) {
+			float sf, cf;
+			float st = M::sqrt(rng.next());
+#if XO_DETERMINISTIC
+			float ct = M::sqrt(__fsub_rn(1.0f, __fmul_rn(st, st)));
+			M::sincos(__fmul_rn(rng.next(), XO_FP_2PI), &sf, &cf);
+			float z = __fmul_rn(signf(-dir.z), ct);
+			dir.x = __fmul_rn(cf, st); dir.y = __fmul_rn(sf, st); dir.z = z;
+#else
+			float ct = M::sqrt(1.0f - st*st);
+			M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+			float z = signf(-dir.z)*ct;
+			dir.x = cf*st; dir.y = sf*st; dir.z = z;
+#endif
+		} else {
+			dir.z = -dir.z;
+		}
+		weight = weight*reflectance;
+		return SURF_REFLECTED;
+	}
+};
+
+struct SurfSixAroundOne {           // mcsurface/probe/sixaroundone.py
+	M3 T; P2 position; float core_spacing;
+	float cladding_r_squared, cladding_n, cladding_cc;
+	float core_r_squared, core_n, core_cc;
+	float cutout_r_squared, cutout_n, cutout_cc;
+	float probe_r_squared, probe_reflectivity;
+	static constexpr bool active = true;
+	__device__ __forceinline__ bool fiber(float r2, float *n2, float *cc) const {
+		if (r2 <= cladding_r_squared) {
+			if (r2 <= core_r_squared) { *n2 = core_n; *cc = core_cc; }
+			else { *n2 = cladding_n; *cc = cladding_cc; }
+			return true;
+		}
+		return false;
+	}
+	__device__ __forceinline__ int handle(Rng &rng, const P3 &pos, P3 &dir, float &weight,
+			float *n2, float *cc) const {
+		(void)rng;
+		float rx = pos.x - position.x, ry = pos.y - position.y;
+		P3 p = { rx, ry, 0.0f };
+		P3 q = transform3(T, p);
+		if (fiber(q.x*q.x + q.y*q.y, n2, cc)) return SURF_CONTINUE;
+		p.x = fabsf(rx) - core_spacing; p.y = ry;
+		q = transform3(T, p);
+		if (fiber(q.x*q.x + q.y*q.y, n2, cc)) return SURF_CONTINUE;
+		p.x = fabsf(rx) - core_spacing*0.5f;
+		p.y = fabsf(ry) - core_spacing*XO_FP_COS_30;
+		q = transform3(T, p);
+		if (fiber(q.x*q.x + q.y*q.y, n2, cc)) return SURF_CONTINUE;
+		float r2 = rx*rx + ry*ry;
+		if (r2 <= cutout_r_squared) { *n2 = cutout_n; *cc = cutout_cc; return SURF_CONTINUE; }
+		if (r2 <= probe_r_squared) {
+			dir.z = -dir.z;
+			weight = weight*probe_reflectivity;
+			return SURF_REFLECTED;
+		}
+		return SURF_CONTINUE;
+	}
+};
+
+template <class Top, class Bottom>
+struct SurfaceLayouts {             // mcsurface/base.py:258-263
+	Top top;
+	Bottom bottom;
+};
+
+}  // namespace xo

@@ -53,6 +53,7 @@ class McBase(CuWorker):
     """Plugin bookkeeping, option resolution, TU emission and the run loop."""
 
     kernel_header = None     # e.g. 'mcml_kernel.cuh'
+    supports_surface_layouts = False
     geometry = None          # 'mcml' | 'mcvox' | 'mccyl'
 
     def __init__(self, source, detectors=None, trace=None, fluence=None,
@@ -62,10 +63,11 @@ class McBase(CuWorker):
         super().__init__(types=types, cl_devices=cl_devices,
                          cl_build_options=cl_build_options,
                          cl_profiling=cl_profiling, rnginit=rnginit)
-        if surface is not None:
+        if surface is not None and not self.supports_surface_layouts:
             raise NotImplementedError(
-                'Surface layouts are not part of the accelerated path yet '
-                '(SURVEY.md 8f-3).')
+                'Surface layouts are only part of the accelerated path of the '
+                'layered simulator (mcml).')
+        self._surface = surface
         self._source = source
         self._detectors = detectors
         self._trace = trace
@@ -80,7 +82,8 @@ class McBase(CuWorker):
         self._obj_types = {
             'source': type(source),
             'detectors': None if detectors is None else detectors.types(),
-            'fluence': type(fluence), 'trace': type(trace)}
+            'fluence': type(fluence), 'trace': type(trace),
+            'surface': None if surface is None else surface.types()}
 
     # -- user-facing properties -------------------------------------------------
     def _set_rmax(self, r):
@@ -92,14 +95,14 @@ class McBase(CuWorker):
     detectors = property(lambda self: self._detectors)
     trace = property(lambda self: self._trace)
     fluence = property(lambda self: self._fluence)
-    surface = property(lambda self: None)
+    surface = property(lambda self: self._surface)
     run_report = property(lambda self: self._run_report)
     options = property(lambda self: self._options)
 
     # -- options ----------------------------------------------------------------
     def _plugin_option_lists(self):
         lists = [self._types.cl_options(self), self._options]
-        for obj in (self._source, self._detectors, self._fluence, self._trace):
+        for obj in (self._source, self._surface, self._detectors, self._fluence, self._trace):
             if obj is not None:
                 lists.append(obj.fetch_cl_options(self))
         return lists
@@ -131,6 +134,11 @@ class McBase(CuWorker):
         self._pack_medium()
         self._packed['source'], _, _ = self._source.cl_pack(
             self, self._packed.get('source'))
+        if self._surface is not None:
+            if self._surface.types() != self._obj_types['surface']:
+                raise ValueError('Surface layout types must not change between '
+                                 'simulation calls!')
+            self._packed['surface_layouts'] = self._surface.cl_pack(self, self._packed.get('surface_layouts'))
         if self._detectors is not None:
             self._packed['detectors'] = self._detectors.cl_pack(
                 self, self._packed.get('detectors'))

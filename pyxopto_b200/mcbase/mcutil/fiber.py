@@ -12,6 +12,17 @@ class MultimodeFiber:
         self.ncore = float(ncore)
         self.na = float(na)
 
+    @staticmethod
+    def compute_na(ncore: float, ncladding: float) -> float:
+        return (ncore**2 - ncladding**2)**0.5
+
+    @staticmethod
+    def compute_ncladding(ncore: float, na: float) -> float:
+        return (ncore**2 - na**2)**0.5
+
+    ncladding = property(lambda self: self.compute_ncladding(self.ncore, self.na), None, None,
+                         'Refractive index of the fiber cladding.')
+
     def todict(self) -> dict:
         return {'dcore': self.dcore, 'dcladding': self.dcladding,
                 'ncore': self.ncore, 'na': self.na, 'type': 'MultimodeFiber'}

@@ -17,10 +17,11 @@ from ..mcbase import mcsv                         # noqa: F401
 from ..mcbase import mcpf, mcfluence, mctrace      # noqa: F401
 from ..mcbase.mcobject import McObject             # noqa: F401
 from ..mcbase.mcsim import McBase
-from . import mclayer, mcsource, mcdetector        # noqa: F401
+from . import mclayer, mcsource, mcdetector, mcsurface  # noqa: F401
 
 
 class Mc(McBase):
+    supports_surface_layouts = True
     kernel_header = 'mcml_kernel.cuh'
     geometry = 'mcml'
 
@@ -71,6 +72,7 @@ class Mc(McBase):
         out = [('XoPf', pf.fetch_cu_type(self), pf.fetch_cl_type(self)),
                ('XoSource', self._source.fetch_cu_type(self),
                 self._source.fetch_cl_type(self))]
+        out += self._surface_bindings()
         out += self._detector_bindings()
         if self._fluence is not None:
             out.append(('XoFluence', self._fluence.fetch_cu_type(self),
@@ -79,14 +81,23 @@ class Mc(McBase):
             out.append(('XoFluence', 'xo::FluNone', None))
         return out
 
+    def _surface_bindings(self):
+        layouts = self._surface if self._surface is not None else mcsurface.SurfaceLayouts()
+        return [(name, lay.fetch_cu_type(self), lay.fetch_cl_type(self))
+                for name, lay in (('XoSurfTop', layouts.top), ('XoSurfBottom', layouts.bottom))]
+
     def _extra_includes(self):
-        return ['#include "mcml_sources.cuh"']
+        return ['#include "xo_surface.cuh"', '#include "mcml_sources.cuh"']
 
     def _extra_checks(self):
         import ctypes
         checks = ['static_assert(sizeof(xo::MlLayer) == {}, "McLayer layout differs '
                   'from the packed host struct");'.format(
                       ctypes.sizeof(self._layers[0].fetch_cl_type(self)))]
+        if self._surface is not None:
+            checks.append('static_assert(sizeof(xo::XoSurface) == {}, "McSurfaceLayouts '
+                          'layout differs from the packed host struct");'.format(
+                              ctypes.sizeof(self._surface.fetch_cl_type(self))))
         if self._detectors is not None:
             checks.append('static_assert(sizeof(xo::XoDetectors) == {}, "McDetectors '
                           'layout differs from the packed host struct");'.format(
@@ -110,6 +121,8 @@ class Mc(McBase):
             np.uint32(len(self._layers)),
             self._cl_buffers['layers'],
             self._packed['source'],
+            self._packed['surface_layouts'] if self._surface is not None
+            else mcsurface.SurfaceLayouts().cl_pack(self),
             self._packed_or_dummy('trace', 4),
             self._packed_or_dummy('fluence', 4),
             dets,

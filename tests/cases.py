@@ -107,7 +107,46 @@ def mcml_hg_line_total_fluencet(mc, **kw):
                  fluence=flu, trace=tr, rnginit=4242, **kw), dict(rmax=5e-3)
 
 
+def mcml_surface_six_lambert(mc, **kw):
+    """Surface layouts (mcml/mcsurface): a six-around-one probe with a filled
+    cut-out and a reflective tip on the top surface, a partly specular
+    Lambertian reflector under a thin two-layer sample."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    L = mc.mclayer.Layer
+    pf = mc.mcpf.Hg(0.8)
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=0.3e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=0.4e-3, n=1.4, mua=0.5e2, mus=50e2, pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf)])
+    surf = mc.mcsurface.SurfaceLayouts(
+        top=mc.mcsurface.SixAroundOne(fib, spacing=240e-6, diameter=3e-3, reflectivity=0.6,
+                                      cutout=0.9e-3, cutoutn=1.6, position=(20e-6, -10e-6),
+                                      direction=(0.05, 0.0, 1.0)),
+        bottom=mc.mcsurface.LambertianReflector(reflectance=0.9, specular=0.3))
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.SixAroundOne(fib, spacing=240e-6, position=(20e-6, -10e-6),
+                                       direction=(0.05, 0.0, 1.0)),
+        bottom=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceRz(Axis(0, 2e-3, 40), Axis(0, 0.7e-3, 35))
+    return mc.Mc(layers, mc.mcsource.UniformFiber(fib), det, fluence=flu, surface=surf,
+                 rnginit=24680, **kw), dict(rmax=20e-3)
+
+
+def mcml_surface_lambert_top(mc, **kw):
+    """Ideal Lambertian reflector on the top surface, open bottom."""
+    Axis = mc.mcdetector.Axis
+    surf = mc.mcsurface.SurfaceLayouts(top=mc.mcsurface.LambertianReflector(0.8, 0.0))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(),
+                                  bottom=mc.mcdetector.Radial(Axis(0, 5e-3, 50)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det, surface=surf,
+                 rnginit=13579, **kw), dict(rmax=20e-3)
+
+
 MCML_CASES = {
+    'mcml_surface_six_lambert': mcml_surface_six_lambert,
+    'mcml_surface_lambert_top': mcml_surface_lambert_top,
     'mcml_c1_slab': mcml_c1_slab,
     'mcml_hg_line_radial': mcml_hg_line_radial,
     'mcml_mhg_gauss_cart_flurz': mcml_mhg_gauss_cart_flurz,

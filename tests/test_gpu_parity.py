@@ -87,7 +87,8 @@ def test_deterministic_mode_bit_exact(name):
 
 
 @pytest.mark.parametrize('name', ['mcml_c1_slab', 'mcml_mhg_gauss_cart_flurz',
-                                  'mcml_gk_fiber_six_flu', 'mcvox_gauss_fluence',
+                                  'mcml_gk_fiber_six_flu', 'mcml_surface_six_lambert',
+                                  'mcml_surface_lambert_top', 'mcvox_gauss_fluence',
                                   'mccyl_hg_line_fiz', 'mccyl_mhg_gauss_total_flurz',
                                   'mccyl_hg_isopoint_outside'])
 def test_throughput_mode_statistics(name):
@@ -112,7 +113,7 @@ def test_throughput_mode_statistics(name):
 
 
 @pytest.mark.parametrize('name', ['mcvox_gauss_fluence', 'mcvox_isopoint_fluencerate',
-                                  'mcml_mhg_gauss_cart_flurz'])
+                                  'mcml_mhg_gauss_cart_flurz', 'mcml_surface_six_lambert'])
 def test_throughput_mode_profiles(name):
     """Fast mode vs oracle beyond totals: every bin of the marginal profiles of
     the fluence grid (along each axis) and every detector bin must agree within
