@@ -65,10 +65,16 @@ typedef struct { float g; } pf_hg;                          /* mcpf/hg.py:49 */
 typedef struct { float g, beta; } pf_mhg;                   /* mcpf/mhg.py:52 */
 typedef struct { float g, a, inv_a, a1, a2; } pf_gk;        /* mcpf/gk.py:58 */
 typedef struct { float a, b, c; uint32_t offset, size; } pf_lut; /* mcpf/lut.py:78 */
+typedef struct { float g1, g2, b; } pf_hg2;                  /* mcpf/hg2.py:58 */
+typedef struct { pf_gk gk_1, gk_2; float b; } pf_gk2;        /* mcpf/gk2.py:61 */
+typedef struct { float g, a, beta, inv_a, a1, a2; } pf_mgk;  /* mcpf/mgk.py:64 */
+typedef struct { float n; } pf_pc;                           /* mcpf/pc.py:50 */
+typedef struct { float n, beta; } pf_mpc;                    /* mcpf/mpc.py:54 */
 
 typedef struct { p3f position, dir_medium, dir_sample, dir_reflected; float reflectance; } src_line;
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip, reflectance; } src_gauss_ml;
 typedef struct { m3f T; p3f position, direction; float radius, cos_min, n; } src_ufiber;
+typedef struct { m3f T; p3f position, direction; p2f radius; float reflectance; } src_ubeam_ml; /* mcsource/uniformbeam.py:36-47 */
 typedef struct { p3f position; uint32_t layer_index; } src_isopoint;
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip; } src_gauss_vox;  /* mcvox/mcsource/gaussianbeam.py:71-77 */
 typedef struct { p3f position; } src_isopoint_vox;                                  /* mcvox/mcsource/point.py:44-46 */
@@ -84,6 +90,11 @@ typedef struct { p3f direction; p2f position; float r_min, inv_dr, pl_min, inv_d
 	uint32_t n_r, n_pl, offset; int32_t r_log_scale, pl_log_scale; } det_radialpl;
 typedef struct { p3f direction; float cos_min, pl_min, inv_dpl;
 	uint32_t n_pl, offset; int32_t pl_log_scale; } det_totalpl;
+/* mcdetector/cartesianpl.py, mcdetector/probe/sixaroundonepl.py */
+typedef struct { p3f direction; float x_min, inv_dx, y_min, inv_dy, pl_min, inv_dpl, cos_min;
+	uint32_t n_x, n_y, n_pl, offset; int32_t pl_log_scale; } det_cartesianpl;
+typedef struct { m3f T; p2f position; float core_r_squared, core_spacing, pl_min, inv_dpl,
+	cos_min; uint32_t n_pl, offset; int32_t pl_log_scale; } det_sixpl;
 /* mccyl/mcdetector/fiz.py:44-56 (pack=1), mccyl/mcdetector/total.py:44-50 */
 typedef struct { float fi_min, inv_dfi, z_min, inv_dz, cos_min;
 	uint32_t n_fi, n_z, offset; } det_fiz;
@@ -331,6 +342,61 @@ static float pf_sample_angles(sim_t *s, float *azimuth) {
 		}
 		return fclip(cos_theta, -FP_1, FP_1);
 	}
+	case XO_PF_HG2: {                                  /* mcpf/hg2.py:100-128 */
+		const pf_hg2 *p = (const pf_hg2 *)pf;
+		float g, k;
+		*azimuth = FP_2PI*sim_random(s);
+		if (sim_random(s) >= p->b) g = p->g1; else g = p->g2;
+		k = m_div(FP_1 - g*g, FP_1 + g*(FP_2*sim_random(s) - FP_1));
+		cos_theta = m_div(FP_1 + g*g - k*k, FP_2*g);
+		if (g == FP_0) cos_theta = FP_1 - FP_2*sim_random(s);
+		return fmaxf(fminf(cos_theta, FP_1), -FP_1);
+	}
+	case XO_PF_GK2:                                    /* mcpf/gk2.py:119-160 */
+	case XO_PF_MGK: {                                  /* mcpf/mgk.py:108-140 */
+		float g, a, inv_a, a1, a2, tmp;
+		*azimuth = FP_2PI*sim_random(s);
+		if (s->job->pf_kind == XO_PF_GK2) {
+			const pf_gk2 *p = (const pf_gk2 *)pf;
+			const pf_gk *q = (sim_random(s) >= p->b) ? &p->gk_1 : &p->gk_2;
+			g = q->g; a = q->a; inv_a = q->inv_a; a1 = q->a1; a2 = q->a2;
+		} else {
+			const pf_mgk *p = (const pf_mgk *)pf;
+			g = p->g; a = p->a; inv_a = p->inv_a; a1 = p->a1; a2 = p->a2;
+			if (!(sim_random(s) <= p->beta)) {
+				cos_theta = m_cbrt(s, FP_2*sim_random(s) - FP_1);
+				return fclip(cos_theta, -FP_1, FP_1);
+			}
+		}
+		if (g == FP_0) {
+			cos_theta = FP_1 - FP_2*sim_random(s);
+		} else if (a == FP_0) {
+			cos_theta = a1 + m_pow(s, m_div(FP_1 - g, FP_1 + g), FP_2*sim_random(s))*a2;
+		} else {
+			tmp = a1*sim_random(s) + a2;
+			tmp = FP_1 + g*g - m_pow(s, tmp, -inv_a);
+			cos_theta = m_div(tmp, FP_2*g);
+		}
+		return fclip(cos_theta, -FP_1, FP_1);
+	}
+	case XO_PF_PC: {                                   /* mcpf/pc.py:82-95 */
+		float n = ((const pf_pc *)pf)->n, r;
+		*azimuth = FP_2PI*sim_random(s);
+		r = sim_random(s);
+		cos_theta = FP_2*m_pow(s, r, m_div(FP_1, n + FP_1)) - FP_1;
+		return fclip(cos_theta, -FP_1, FP_1);
+	}
+	case XO_PF_MPC: {                                  /* mcpf/mpc.py:91-110 */
+		const pf_mpc *p = (const pf_mpc *)pf;
+		*azimuth = FP_2PI*sim_random(s);
+		if (sim_random(s) <= p->beta) {
+			float r = sim_random(s);
+			cos_theta = FP_2*m_pow(s, r, m_div(FP_1, p->n + FP_1)) - FP_1;
+		} else {
+			cos_theta = m_cbrt(s, FP_2*sim_random(s) - FP_1);
+		}
+		return fclip(cos_theta, -FP_1, FP_1);
+	}
 	case XO_PF_LUT: {                                  /* mcpf/lut.py:125-158 */
 		const pf_lut *p = (const pf_lut *)pf;
 		float a = p->a, b = p->b, c = p->c, fp_index, fp_index_floor, d;
@@ -440,6 +506,60 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		p3f dd = d->direction;
 		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
 		if (w > 0) accu_deposit(s, d->offset + (uint32_t)pi, w);
+		break;
+	}
+	case XO_DET_CARTESIANPL: {                         /* mcdetector/cartesianpl.py:131-175 */
+		const det_cartesianpl *d = (const det_cartesianpl *)base;
+		int32_t index_x, index_y, index_pl;
+		size_t index;
+		float pl;
+		p3f dd = d->direction;
+		index_x = (int32_t)((pos->x - d->x_min)*d->inv_dx);
+		index_x = iclip(index_x, 0, (int32_t)d->n_x - 1);
+		index_y = (int32_t)((pos->y - d->y_min)*d->inv_dy);
+		index_y = iclip(index_y, 0, (int32_t)d->n_y - 1);
+		pl = s->opl;
+		if (d->pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		index_pl = (int32_t)((pl - d->pl_min)*d->inv_dpl);
+		index_pl = iclip(index_pl, 0, (int32_t)d->n_pl - 1);
+		index = ((size_t)index_pl*d->n_y + (size_t)index_y)*d->n_x + (size_t)index_x;
+		{
+			uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+			if (w > 0) accu_deposit(s, d->offset + index, w);
+		}
+		break;
+	}
+	case XO_DET_SIXAROUNDONEPL: {                      /* mcdetector/probe/sixaroundonepl.py:128-225 */
+		const det_sixpl *d = (const det_sixpl *)base;
+		uint32_t fiber_index = 7;
+		p3f rel = { pos->x - d->position.x, pos->y - d->position.y, FP_0 };
+		p3f mc_pos, dp; float dx, dy, r2, pl;
+		int32_t pl_index;
+		m3f T = d->T;
+		mc_pos.x = rel.x; mc_pos.y = rel.y; mc_pos.z = FP_0;
+		transform3(&T, &mc_pos, &dp);
+		dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+		if (r2 <= d->core_r_squared) fiber_index = 0;
+		mc_pos.x = fabsf(rel.x) - d->core_spacing; mc_pos.y = rel.y;
+		transform3(&T, &mc_pos, &dp);
+		dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+		if (r2 <= d->core_r_squared) fiber_index = (rel.x >= FP_0) ? 1 : 4;
+		mc_pos.x = fabsf(rel.x) - d->core_spacing*FP_0p5;
+		mc_pos.y = fabsf(rel.y) - d->core_spacing*FP_COS_30;
+		transform3(&T, &mc_pos, &dp);
+		dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+		if (r2 <= d->core_r_squared)
+			fiber_index = (rel.x >= FP_0) ? ((rel.y >= FP_0) ? 2 : 6) : ((rel.y >= FP_0) ? 3 : 5);
+		if (fiber_index > 6) return;
+		pl = s->opl;
+		if (d->pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		pl_index = (int32_t)((pl - d->pl_min)*d->inv_dpl);
+		pl_index = iclip(pl_index, 0, (int32_t)d->n_pl - 1);
+		{
+			float pz = T.a31*dir->x + T.a32*dir->y + T.a33*dir->z;
+			uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(pz));
+			if (w > 0) accu_deposit(s, d->offset + (size_t)pl_index*7 + fiber_index, w);
+		}
 		break;
 	}
 	case XO_DET_FIZ: {                                 /* mccyl/mcdetector/fiz.py:86-120 */
@@ -582,6 +702,38 @@ static void launch_mcml(sim_t *s) {
 		s->dir = src->direction;
 		s->layer_index = 1;
 		s->weight = FP_1 - src->reflectance;
+		if (j->det_kind[LOC_SPECULAR]) {
+			p3f dir_in = { s->dir.x, s->dir.y, -s->dir.z }, dir;
+			p3f normal = { FP_0, FP_0, -FP_1 };
+			refract3(&dir_in, &normal, medium_n(j, 1), medium_n(j, 0), &dir);
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &dir, src->reflectance);
+		}
+		break;
+	}
+	case XO_SRC_UNIFORMBEAM: {                         /* mcsource/uniformbeam.py:75-112 */
+		const src_ubeam_ml *src = (const src_ubeam_ml *)j->source;
+		float cos_fi, sin_fi, rand_sqrt, fi; p3f pt_src, pt_mc;
+		rand_sqrt = m_sqrt(sim_random(s));
+		fi = FP_2PI*sim_random(s);
+		m_sincos(s, fi, &sin_fi, &cos_fi);     /* mc_cos(fi), mc_sin(fi) */
+		pt_src.x = rand_sqrt*cos_fi*src->radius.x;
+		pt_src.y = rand_sqrt*sin_fi*src->radius.y;
+		pt_src.z = FP_0;
+		{
+			m3f T = src->T;
+			float k;
+			transform3(&T, &pt_src, &pt_mc);
+			k = m_div(FP_0 - pt_mc.z, src->direction.z);
+			pt_mc.x += k*src->direction.x;
+			pt_mc.y += k*src->direction.y;
+			pt_mc.z = FP_0;
+		}
+		s->pos.x = src->position.x + pt_mc.x;
+		s->pos.y = src->position.y + pt_mc.y;
+		s->pos.z = FP_0;
+		s->dir = src->direction;
+		s->weight = FP_1 - src->reflectance;
+		s->layer_index = 1;
 		if (j->det_kind[LOC_SPECULAR]) {
 			p3f dir_in = { s->dir.x, s->dir.y, -s->dir.z }, dir;
 			p3f normal = { FP_0, FP_0, -FP_1 };

@@ -24,7 +24,8 @@ GEOMETRY = {'mcml': 0, 'mcvox': 1, 'mccyl': 2}
 METHOD = {'aw': 0, 'albedo_weight': 0, 'ar': 1, 'albedo_rejection': 1,
           'mbl': 2, 'microscopic_beer_lambert': 2}
 MATH_LIBM, MATH_PORTABLE = 0, 1
-PF_KIND = {'Hg': 1, 'MHg': 2, 'Gk': 3, 'Lut': 4, 'LutEx': 4}
+PF_KIND = {'Hg': 1, 'MHg': 2, 'Gk': 3, 'Lut': 4, 'LutEx': 4, 'Hg2': 5, 'Gk2': 6,
+           'MGk': 7, 'Pc': 8, 'MPc': 9}
 SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
             'IsotropicPoint': 4, 'UniformBeam': 5}
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,

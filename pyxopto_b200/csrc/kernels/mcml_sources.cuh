@@ -64,6 +64,34 @@ struct SrcGaussianBeam {            // mcsource/gaussianbeam.py:75-85 (pack=1)
 	}
 };
 
+struct SrcUniformBeam {             // mcsource/uniformbeam.py:36-47
+	M3 T; P3 position, direction; P2 radius; float reflectance;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf;
+		float rs = M::sqrt(rng.next());
+		M::sincos(XO_FP_2PI*rng.next(), &sf, &cf);
+		P3 ps = { rs*cf*radius.x, rs*sf*radius.y, 0.0f };
+		P3 pm = transform3(T, ps);
+		float k = M::div(0.0f - pm.z, direction.z);
+		pm.x += k*direction.x;
+		pm.y += k*direction.y;
+		L.pos.x = position.x + pm.x;
+		L.pos.y = position.y + pm.y;
+		L.pos.z = 0.0f;
+		L.dir = direction;
+		L.layer = 1;
+		L.weight = 1.0f - reflectance;
+		if (Ctx::has_specular) {
+			P3 din = { direction.x, direction.y, -direction.z };
+			P3 normal = { 0.0f, 0.0f, -1.0f };
+			L.spec_dir = refract3(din, normal, ctx.layer_n(1), ctx.layer_n(0));
+		}
+		L.spec_weight = reflectance;
+	}
+};
+
 struct SrcUniformFiber {            // mcsource/fiber.py:224-232
 	M3 T; P3 position, direction; float radius, cos_min, n;
 	__device__ __forceinline__ P3 origin() const { return position; }

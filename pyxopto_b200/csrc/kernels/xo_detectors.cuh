@@ -105,6 +105,51 @@ struct DetRadialPl {                // mcdetector/radialpl.py
 	}
 };
 
+struct DetCartesianPl {             // mcdetector/cartesianpl.py
+	P3 direction; float x_min, inv_dx, y_min, inv_dy, pl_min, inv_dpl, cos_min;
+	u32 n_x, n_y, n_pl, offset; i32 pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		i32 ix = clipi(f2i((pos.x - x_min)*inv_dx), 0, (i32)(n_x - 1));
+		i32 iy = clipi(f2i((pos.y - y_min)*inv_dy), 0, (i32)(n_y - 1));
+		float pl = opl;
+		if (pl_log_scale) pl = M::log(fmaxf(pl, XO_FP_PLMIN));
+		i32 pi = clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add(offset + ((u32)pi*n_y + (u32)iy)*n_x + (u32)ix, iw);
+	}
+};
+
+struct DetSixAroundOnePl {          // mcdetector/probe/sixaroundonepl.py
+	M3 T; P2 position; float core_r_squared, core_spacing, pl_min, inv_dpl, cos_min;
+	u32 n_pl, offset; i32 pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		u32 fiber = 7;
+		float rx = pos.x - position.x, ry = pos.y - position.y;
+		P3 p = { rx, ry, 0.0f };
+		P3 q = transform3(T, p);
+		if (q.x*q.x + q.y*q.y <= core_r_squared) fiber = 0;
+		p.x = fabsf(rx) - core_spacing; p.y = ry;
+		q = transform3(T, p);
+		if (q.x*q.x + q.y*q.y <= core_r_squared) fiber = (rx >= 0.0f) ? 1 : 4;
+		p.x = fabsf(rx) - core_spacing*0.5f;
+		p.y = fabsf(ry) - core_spacing*XO_FP_COS_30;
+		q = transform3(T, p);
+		if (q.x*q.x + q.y*q.y <= core_r_squared)
+			fiber = (rx >= 0.0f) ? ((ry >= 0.0f) ? 2 : 6) : ((ry >= 0.0f) ? 3 : 5);
+		if (fiber > 6) return;
+		float pl = opl;
+		if (pl_log_scale) pl = M::log(fmaxf(pl, XO_FP_PLMIN));
+		i32 pi = clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
+		float pz = T.a31*dir.x + T.a32*dir.y + T.a33*dir.z;
+		u32 iw = weight_u32(w, cos_min <= fabsf(pz));
+		if (iw > 0) acc.add(offset + (u32)pi*7u + fiber, iw);
+	}
+};
+
 struct DetTotalPl {                 // mcdetector/totalpl.py
 	P3 direction; float cos_min, pl_min, inv_dpl; u32 n_pl, offset; i32 pl_log_scale;
 	static constexpr bool active = true;

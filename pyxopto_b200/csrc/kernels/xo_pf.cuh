@@ -138,6 +138,102 @@ struct PfGk {                       // mcpf/gk.py:58-66
 	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
 };
 
+// polar cosine of the Gegenbauer kernel from its packed constants
+// (mcpf/gk.py:99-132; shared by Gk, MGk and Gk2)
+__device__ __forceinline__ float gk_polar(float g, float a, float inv_a, float a1, float a2, Rng &rng) {
+	float ct;
+	if (g == 0.0f) {
+		ct = 1.0f - 2.0f*rng.next();
+	} else if (a == 0.0f) {
+		ct = a1 + M::pow(M::div(1.0f - g, 1.0f + g), 2.0f*rng.next())*a2;
+	} else {
+		float tmp = a1*rng.next() + a2;
+		tmp = 1.0f + g*g - M::pow(tmp, -inv_a);
+		ct = M::div(tmp, 2.0f*g);
+	}
+	return ct;
+}
+
+struct PfHg2 {                      // mcpf/hg2.py:58-66
+	float g1, g2, b;
+	static constexpr bool uses_lut = false;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		(void)lut;
+		*azimuth = XO_FP_2PI*rng.next();
+		float g = (rng.next() >= b) ? g1 : g2;
+		float k = M::div(1.0f - g*g, 1.0f + g*(2.0f*rng.next() - 1.0f));
+		float ct = M::div(1.0f + g*g - k*k, 2.0f*g);
+		if (g == 0.0f) ct = 1.0f - 2.0f*rng.next();
+		return fmaxf(fminf(ct, 1.0f), -1.0f);
+	}
+	typedef PfPlainFast<PfHg2> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
+struct PfMGk {                      // mcpf/mgk.py:64-72
+	float g, a, beta, inv_a, a1, a2;
+	static constexpr bool uses_lut = false;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		(void)lut;
+		float ct;
+		*azimuth = XO_FP_2PI*rng.next();
+		if (rng.next() <= beta) ct = gk_polar(g, a, inv_a, a1, a2, rng);
+		else ct = M::cbrt(2.0f*rng.next() - 1.0f);
+		return clipf(ct, -1.0f, 1.0f);
+	}
+	typedef PfPlainFast<PfMGk> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
+struct PfGk2 {                      // mcpf/gk2.py:61-69
+	PfGk gk_1, gk_2; float b;
+	static constexpr bool uses_lut = false;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		(void)lut;
+		*azimuth = XO_FP_2PI*rng.next();
+		const bool first = rng.next() >= b;
+		const float g = first ? gk_1.g : gk_2.g, a = first ? gk_1.a : gk_2.a;
+		const float inv_a = first ? gk_1.inv_a : gk_2.inv_a;
+		const float a1 = first ? gk_1.a1 : gk_2.a1, a2 = first ? gk_1.a2 : gk_2.a2;
+		return clipf(gk_polar(g, a, inv_a, a1, a2, rng), -1.0f, 1.0f);
+	}
+	typedef PfPlainFast<PfGk2> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
+struct PfPc {                       // mcpf/pc.py:50-52
+	float n;
+	static constexpr bool uses_lut = false;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		(void)lut;
+		*azimuth = XO_FP_2PI*rng.next();
+		float r = rng.next();
+		float ct = 2.0f*M::pow(r, M::div(1.0f, n + 1.0f)) - 1.0f;
+		return clipf(ct, -1.0f, 1.0f);
+	}
+	typedef PfPlainFast<PfPc> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
+struct PfMPc {                      // mcpf/mpc.py:54-58
+	float n, beta;
+	static constexpr bool uses_lut = false;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		(void)lut;
+		float ct;
+		*azimuth = XO_FP_2PI*rng.next();
+		if (rng.next() <= beta) {
+			float r = rng.next();
+			ct = 2.0f*M::pow(r, M::div(1.0f, n + 1.0f)) - 1.0f;
+		} else {
+			ct = M::cbrt(2.0f*rng.next() - 1.0f);
+		}
+		return clipf(ct, -1.0f, 1.0f);
+	}
+	typedef PfPlainFast<PfMPc> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
 struct PfLut {                      // mcpf/lut.py:78-85
 	float a, b, c;
 	u32 offset, size;

@@ -1,4 +1,5 @@
-"""Scattering phase functions (mirror of ``xopto/mcbase/mcpf``: Hg, MHg, Gk, Lut, LutEx).
+"""Scattering phase functions (mirror of ``xopto/mcbase/mcpf``: Hg, MHg, Hg2, Gk,
+MGk, Gk2, Pc, MPc, Lut, LutEx).
 
 Each class packs the reference's ``McPf`` struct and names the CUDA struct in
 ``csrc/kernels/xo_pf.cuh`` that samples it.
@@ -136,6 +137,209 @@ class Gk(PfBase):
 
     def __repr__(self):
         return 'Gk(g={}, a={})'.format(self._g, self._a)
+
+
+class Hg2(PfBase):
+    """Two-term Henyey-Greenstein (mcpf/hg2.py): (1 - b) Hg(g1 >= 0) + b Hg(g2 <= 0)."""
+    cu_type = 'xo::PfHg2'
+
+    @staticmethod
+    def cl_type(mc):
+        T_HG = Hg.cl_type(mc)
+        class ClHg2(cltypes.Structure):
+            _fields_ = [('hg_1', T_HG), ('hg_2', T_HG), ('b', mc.types.mc_fp_t)]
+        return ClHg2
+
+    def __init__(self, g1: float, g2: float, b: float):
+        super().__init__()
+        self._hg1, self._hg2 = Hg(g1), Hg(g2)
+        self.g1, self.g2, self.b = g1, g2, b
+
+    def _set_g1(self, g):
+        self._hg1.g = min(max(float(g), 0.0), 1.0)
+
+    def _set_g2(self, g):
+        self._hg2.g = min(max(float(g), -1.0), 0.0)
+
+    def _set_b(self, b):
+        self._b = min(max(float(b), 0.0), 1.0)
+
+    g1 = property(lambda self: self._hg1.g, _set_g1, None, 'Anisotropy of the first HG.')
+    g2 = property(lambda self: self._hg2.g, _set_g2, None, 'Anisotropy of the second HG.')
+    b = property(lambda self: self._b, _set_b, None,
+                 'Relative contribution of the second HG term.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        self._hg1.cl_pack(mc, target.hg_1)
+        self._hg2.cl_pack(mc, target.hg_2)
+        target.b = self._b
+        return target
+
+    def todict(self):
+        return {'g1': self.g1, 'g2': self.g2, 'b': self._b, 'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'Hg2(g1={}, g2={}, b={})'.format(self.g1, self.g2, self._b)
+
+
+class Gk2(PfBase):
+    """Two-term Gegenbauer kernel (mcpf/gk2.py)."""
+    cu_type = 'xo::PfGk2'
+
+    @staticmethod
+    def cl_type(mc):
+        T_GK = Gk.cl_type(mc)
+        class ClGk2(cltypes.Structure):
+            _fields_ = [('gk_1', T_GK), ('gk_2', T_GK), ('b', mc.types.mc_fp_t)]
+        return ClGk2
+
+    def __init__(self, g1: float, a1: float, g2: float, a2: float, b: float):
+        super().__init__()
+        self._gk1, self._gk2 = Gk(g1, a1), Gk(g2, a2)
+        self.g1, self.g2, self.a1, self.a2, self.b = g1, g2, a1, a2, b
+
+    def _set_g1(self, g):
+        self._gk1.g = min(max(float(g), 0.0), 1.0)
+
+    def _set_a1(self, a):
+        self._gk1.a = max(float(a), -0.5)
+
+    def _set_g2(self, g):
+        self._gk2.g = min(max(float(g), -1.0), 0.0)
+
+    def _set_a2(self, a):
+        self._gk2.a = max(float(a), -0.5)
+
+    def _set_b(self, b):
+        self._b = min(max(float(b), 0.0), 1.0)
+
+    g1 = property(lambda self: self._gk1.g, _set_g1)
+    a1 = property(lambda self: self._gk1.a, _set_a1)
+    g2 = property(lambda self: self._gk2.g, _set_g2)
+    a2 = property(lambda self: self._gk2.a, _set_a2)
+    b = property(lambda self: self._b, _set_b, None,
+                 'Relative contribution of the second GK term.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        self._gk1.cl_pack(mc, target.gk_1)
+        self._gk2.cl_pack(mc, target.gk_2)
+        target.b = self._b
+        return target
+
+    def todict(self):
+        return {'g1': self.g1, 'a1': self.a1, 'g2': self.g2, 'a2': self.a2, 'b': self._b,
+                'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'Gk2(g1={}, a1={}, g2={}, a2={}, b={})'.format(
+            self.g1, self.a1, self.g2, self.a2, self._b)
+
+
+class MGk(Gk):
+    """Modified Gegenbauer kernel (mcpf/mgk.py): b Gk(g, a) + (1 - b) 3/2 cos^2."""
+    cu_type = 'xo::PfMGk'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClMGk(cltypes.Structure):
+            _fields_ = [('g', T.mc_fp_t), ('a', T.mc_fp_t), ('beta', T.mc_fp_t),
+                        ('inv_a', T.mc_fp_t), ('a1', T.mc_fp_t), ('a2', T.mc_fp_t)]
+        return ClMGk
+
+    def __init__(self, g: float, a: float, b: float):
+        super().__init__(g, a)
+        self.b = b
+
+    def _set_b(self, b):
+        self._b = min(max(float(b), 0.0), 1.0)
+
+    b = property(lambda self: self._b, _set_b, None,
+                 'Contribution of the Gegenbauer kernel term.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        inv_a, a1, a2 = self._precalculated()
+        target.g, target.a, target.beta = self._g, self._a, self._b
+        target.inv_a, target.a1, target.a2 = inv_a, a1, a2
+        return target
+
+    def todict(self):
+        return {'g': self._g, 'a': self._a, 'b': self._b, 'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'MGk(g={}, a={}, b={})'.format(self._g, self._a, self._b)
+
+
+class Pc(PfBase):
+    """Power of cosines (mcpf/pc.py)."""
+    cu_type = 'xo::PfPc'
+
+    @staticmethod
+    def cl_type(mc):
+        class ClPc(cltypes.Structure):
+            _fields_ = [('n', mc.types.mc_fp_t)]
+        return ClPc
+
+    def __init__(self, n: float):
+        super().__init__()
+        self.n = n
+
+    def _set_n(self, n):
+        self._n = float(n)
+
+    n = property(lambda self: self._n, _set_n, None, 'Power of cosine.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        target.n = self._n
+        return target
+
+    def todict(self):
+        return {'n': self._n, 'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'Pc(n={})'.format(self._n)
+
+
+class MPc(Pc):
+    """Modified power of cosines (mcpf/mpc.py): b Pc(n) + (1 - b) 3/2 cos^2."""
+    cu_type = 'xo::PfMPc'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClMPc(cltypes.Structure):
+            _fields_ = [('n', T.mc_fp_t), ('beta', T.mc_fp_t)]
+        return ClMPc
+
+    def __init__(self, n: float, b: float):
+        super().__init__(n)
+        self.b = b
+
+    def _set_b(self, b):
+        self._b = min(max(float(b), 0.0), 1.0)
+
+    b = property(lambda self: self._b, _set_b, None,
+                 'Contribution of the power of cosine term.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        target.n, target.beta = self._n, self._b
+        return target
+
+    def todict(self):
+        return {'n': self._n, 'b': self._b, 'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'MPc(n={}, b={})'.format(self._n, self._b)
 
 
 class Lut(PfBase):

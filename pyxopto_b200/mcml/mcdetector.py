@@ -428,6 +428,146 @@ class TotalPl(Detector):
                 'cosmin': self._cosmin, 'direction': self._direction.tolist()}
 
 
+class CartesianPl(Detector):
+    """x-y grid x optical-path-length histogram; raw indexed [pl, y, x]
+    (cartesianpl.py)."""
+    cu_type = 'xo::DetCartesianPl'
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClCartesianPl(cltypes.Structure):
+            _fields_ = [('direction', T.mc_point3f_t), ('x_min', T.mc_fp_t),
+                        ('inv_dx', T.mc_fp_t), ('y_min', T.mc_fp_t),
+                        ('inv_dy', T.mc_fp_t), ('pl_min', T.mc_fp_t),
+                        ('inv_dpl', T.mc_fp_t), ('cos_min', T.mc_fp_t),
+                        ('n_x', T.mc_size_t), ('n_y', T.mc_size_t),
+                        ('n_pl', T.mc_size_t), ('offset', T.mc_size_t),
+                        ('pl_log_scale', T.mc_int_t)]
+        return ClCartesianPl
+
+    def cl_options(self, mc):
+        return [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    def __init__(self, xaxis, yaxis=None, plaxis=None, cosmin=0.0,
+                 direction=(0.0, 0.0, 1.0)):
+        if isinstance(xaxis, CartesianPl):
+            o = xaxis
+            xaxis, yaxis = type(o.xaxis)(o.xaxis), type(o.yaxis)(o.yaxis)
+            plaxis = type(o.plaxis)(o.plaxis)
+            cosmin, direction = o.cosmin, o.direction
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            if yaxis is None:
+                yaxis = Axis(xaxis)
+            if plaxis is None:
+                plaxis = Axis(0.0, 1.0, 1)
+            raw, nphotons = np.zeros((plaxis.n, yaxis.n, xaxis.n)), 0
+        super().__init__(raw, nphotons)
+        self._x_axis, self._y_axis, self._pl_axis = xaxis, yaxis, plaxis
+        self.cosmin, self.direction = cosmin, direction
+        self._accumulators_area = abs(xaxis.step*yaxis.step)
+
+    xaxis = property(lambda self: self._x_axis)
+    yaxis = property(lambda self: self._y_axis)
+    plaxis = property(lambda self: self._pl_axis)
+    x = property(lambda self: self._x_axis.centers)
+    y = property(lambda self: self._y_axis.centers)
+    pl = property(lambda self: self._pl_axis.centers)
+
+    @property
+    def normalized(self):
+        return self.raw*(1.0/(max(self.nphotons, 1.0)*self._accumulators_area))
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        target.direction.fromarray(self._direction)
+        target.x_min = self._x_axis.start
+        target.inv_dx = 1.0/self._x_axis.step if self._x_axis.n > 1 else 0.0
+        target.y_min = self._y_axis.start
+        target.inv_dy = 1.0/self._y_axis.step if self._y_axis.n > 1 else 0.0
+        target.cos_min = self._cosmin
+        target.n_x, target.n_y = self._x_axis.n, self._y_axis.n
+        target.pl_min, target.inv_dpl = self._pl_axis.scaled_start, _inv_step(self._pl_axis)
+        target.pl_log_scale, target.n_pl = self._pl_axis.logscale, self._pl_axis.n
+        return target
+
+    def todict(self):
+        return {'type': 'CartesianPl', 'xaxis': self._x_axis.todict(),
+                'yaxis': self._y_axis.todict(), 'plaxis': self._pl_axis.todict(),
+                'cosmin': self._cosmin, 'direction': self._direction.tolist()}
+
+
+class SixAroundOnePl(Detector):
+    """Six-around-one fiber probe x optical-path-length histogram; raw indexed
+    [pl, fiber] (probe/sixaroundonepl.py)."""
+    cu_type = 'xo::DetSixAroundOnePl'
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClSixAroundOnePl(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point2f_t),
+                        ('core_r_squared', T.mc_fp_t), ('core_spacing', T.mc_fp_t),
+                        ('pl_min', T.mc_fp_t), ('inv_dpl', T.mc_fp_t),
+                        ('cos_min', T.mc_fp_t), ('n_pl', T.mc_size_t),
+                        ('offset', T.mc_size_t), ('pl_log_scale', T.mc_int_t)]
+        return ClSixAroundOnePl
+
+    def cl_options(self, mc):
+        return [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    def __init__(self, fiber, spacing: float = None, plaxis=None, position=(0.0, 0.0),
+                 direction=(0.0, 0.0, 1.0)):
+        if isinstance(fiber, SixAroundOnePl):
+            o = fiber
+            fiber, spacing, position, direction = o.fiber, o.spacing, o.position, o.direction
+            plaxis = type(o.plaxis)(o.plaxis)
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            if plaxis is None:
+                plaxis = Axis(0.0, 1.0, 1)
+            if spacing is None:
+                spacing = fiber.dcladding
+            raw, nphotons = np.zeros((plaxis.n, 7)), 0
+        super().__init__(raw, nphotons)
+        self._fiber = fiber
+        self._spacing = float(spacing)
+        self._pl_axis = plaxis
+        self._position = np.zeros((2,))
+        self._position[:] = position
+        self.direction = direction
+
+    fiber = property(lambda self: self._fiber)
+    spacing = property(lambda self: self._spacing)
+    plaxis = property(lambda self: self._pl_axis)
+    pl = property(lambda self: self._pl_axis.centers)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        adir = self._direction[0], self._direction[1], abs(self._direction[2])
+        target.transformation.fromarray(geometry.transform_base(adir, (0.0, 0.0, 1.0)))
+        target.core_spacing = self._spacing
+        target.core_r_squared = 0.25*self._fiber.dcore**2
+        target.cos_min = (1.0 - (self._fiber.na/self._fiber.ncore)**2)**0.5
+        target.position.fromarray(self._position)
+        target.pl_min, target.inv_dpl = self._pl_axis.scaled_start, _inv_step(self._pl_axis)
+        target.pl_log_scale, target.n_pl = self._pl_axis.logscale, self._pl_axis.n
+        return target
+
+    def todict(self):
+        return {'type': 'SixAroundOnePl', 'fiber': self._fiber.todict(),
+                'spacing': self._spacing, 'plaxis': self._pl_axis.todict(),
+                'position': self._position.tolist(), 'direction': self._direction.tolist()}
+
+
 class Detectors(McObject):
     """Container {top, bottom, specular} (mcdetector/base.py:295-549)."""
 

@@ -165,6 +165,72 @@ class GaussianBeam(Source):
                 'direction': self._direction.tolist(), 'type': type(self).__name__}
 
 
+class UniformBeam(Source):
+    """Collimated uniform (top-hat) beam with an elliptical cross section
+    (mcsource/uniformbeam.py)."""
+    cu_type = 'xo::SrcUniformBeam'
+    cu_refill_lanes = 4
+    _update_keys = ('diameter', 'position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformBeam(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_point2f_t),
+                        ('reflectance', T.mc_fp_t)]
+        return ClUniformBeam
+
+    def __init__(self, diameter, position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self._diameter = np.zeros((2,))
+        self.diameter = diameter
+        self.position, self.direction = position, direction
+
+    def _set_diameter(self, d):
+        self._diameter[:] = d
+        self._diameter = np.maximum(0.0, self._diameter)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        d = _unit(d)
+        if d[-1] <= 0.0:
+            raise ValueError('Z component of the propagation direction '
+                             'must be positive!')
+        self._direction[:] = d
+
+    diameter = property(lambda self: self._diameter, _set_diameter, None,
+                        'Beam diameter along the x and y axis (m).')
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        k = (0.0 - self._position[2])/self._direction[2]
+        position = self._position + k*self._direction
+        position[2] = 0.0
+        n1, n2 = mc.layers[0].n, mc.layers[1].n
+        direction = boundary.refract(self._direction, (0.0, 0.0, 1.0), n1, n2)
+        reflectance = boundary.reflectance(n1, n2, abs(self._direction[-1]))
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.position.fromarray(position)
+        target.direction.fromarray(direction)
+        target.radius.x = self._diameter[0]*0.5
+        target.radius.y = self._diameter[1]*0.5
+        target.reflectance = reflectance
+        return target, None, None
+
+    def todict(self):
+        return {'diameter': self._diameter.tolist(), 'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
 class UniformFiber(Source):
     """Optical fiber with uniform emission within the NA (mcsource/fiber.py)."""
     cu_type = 'xo::SrcUniformFiber'

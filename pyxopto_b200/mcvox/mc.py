@@ -72,9 +72,9 @@ class Mc(McBase):
 
     def _medium_bytes(self) -> int:
         # packed materials + the per-material derived constants the throughput
-        # loop appends (xo::VoxFastMat, <= 48 B per material)
+        # loop appends (xo::VoxFastMat, <= 64 B per material)
         return len(cltypes.raw_bytes(self._packed['materials'])) + \
-            48*len(self._materials) + 32
+            64*len(self._materials) + 32
 
     # waiting lanes per warp that trigger their joint handling (throughput loop)
     wait_lanes = 16

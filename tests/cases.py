@@ -144,7 +144,59 @@ def mcml_surface_lambert_top(mc, **kw):
                  rnginit=13579, **kw), dict(rmax=20e-3)
 
 
+def mcml_mhg_fiber_cartpl_sixpl(mc, **kw):
+    """Path-length resolved (TOF) detectors: CartesianPl on the bottom surface
+    (linear pl axis) and SixAroundOnePl on the top surface (logarithmic pl axis)."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.SixAroundOnePl(fib, spacing=230e-6,
+                                         plaxis=Axis(1e-4, 0.1, 12, logscale=True)),
+        bottom=mc.mcdetector.CartesianPl(Axis(-1.5e-3, 1.5e-3, 12), Axis(-1e-3, 1e-3, 8),
+                                         plaxis=Axis(0.0, 0.03, 15), cosmin=0.2),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.7, 0.95)), mc.mcsource.UniformFiber(fib), det,
+                 rnginit=1122334455, **kw), dict(rmax=20e-3)
+
+
+def mcml_hg_ubeam_radial(mc, **kw):
+    """Tilted elliptical top-hat beam (mcml UniformBeam), Radial detectors and a
+    specular Cartesian detector."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(Axis(0, 4e-3, 80), position=(0.1e-3, 0.0)),
+        bottom=mc.mcdetector.Radial(Axis(0, 4e-3, 40)),
+        specular=mc.mcdetector.Cartesian(Axis(-1e-3, 1e-3, 10)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.85)),
+                 mc.mcsource.UniformBeam((400e-6, 250e-6), position=(0.1e-3, 0.0, 0.0),
+                                         direction=(0.2, -0.1, 1.0)),
+                 det, rnginit=998877, **kw), dict(rmax=20e-3)
+
+
+def _pf_case(make_pf, rnginit):
+    def case(mc, **kw):
+        Axis = mc.mcdetector.Axis
+        det = mc.mcdetector.Detectors(
+            top=mc.mcdetector.Radial(Axis(0, 5e-3, 100)), bottom=mc.mcdetector.Total(),
+            specular=mc.mcdetector.Total())
+        return mc.Mc(_layers(mc, make_pf(mc)), mc.mcsource.Line((0, 0, 0), (0.1, 0.05, 1.0)),
+                     det, rnginit=rnginit, **kw), dict(rmax=20e-3)
+    return case
+
+
+# the remaining built-in phase functions (mcbase/mcpf: hg2, gk2, mgk, pc, mpc)
+mcml_pf_hg2 = _pf_case(lambda mc: mc.mcpf.Hg2(0.9, -0.3, 0.15), 31)
+mcml_pf_gk2 = _pf_case(lambda mc: mc.mcpf.Gk2(0.85, 0.6, -0.4, 0.5, 0.2), 32)
+mcml_pf_mgk = _pf_case(lambda mc: mc.mcpf.MGk(0.8, 0.7, 0.9), 33)
+mcml_pf_pc = _pf_case(lambda mc: mc.mcpf.Pc(6.0), 34)
+mcml_pf_mpc = _pf_case(lambda mc: mc.mcpf.MPc(8.0, 0.85), 35)
+
+
 MCML_CASES = {
+    'mcml_pf_hg2': mcml_pf_hg2, 'mcml_pf_gk2': mcml_pf_gk2, 'mcml_pf_mgk': mcml_pf_mgk,
+    'mcml_pf_mpc': mcml_pf_mpc,
+    'mcml_hg_ubeam_radial': mcml_hg_ubeam_radial,
+    'mcml_mhg_fiber_cartpl_sixpl': mcml_mhg_fiber_cartpl_sixpl,
     'mcml_surface_six_lambert': mcml_surface_six_lambert,
     'mcml_surface_lambert_top': mcml_surface_lambert_top,
     'mcml_c1_slab': mcml_c1_slab,
@@ -225,14 +277,23 @@ def mcvox_isopoint_fluencerate(mc, **kw):
     return _fill_skin_vessel(sim, center=250e-6, radius=80e-6), dict(rmax=5e-3)
 
 
+def mcvox_gk2_line_total(mc, **kw):
+    vox = _vox_grid(mc, n=(16, 16, 16))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), bottom=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, lambda g: mc.mcpf.Gk2(min(g, 0.9), 0.6, -0.3, 0.5, 0.1)),
+                mc.mcsource.Line(), detectors=det, rnginit=8642, **kw)
+    return _fill_skin_vessel(sim, center=200e-6, radius=60e-6), dict(rmax=5e-3)
+
+
 MCVOX_CASES = {
+    'mcvox_gk2_line_total': mcvox_gk2_line_total,
     'mcvox_gauss_fluence': mcvox_gauss_fluence,
     'mcvox_line_mhg_trace': mcvox_line_mhg_trace,
     'mcvox_isopoint_fluencerate': mcvox_isopoint_fluencerate,
 }
 ALL_CASES.update(MCVOX_CASES)
 GEOMETRY.update({name: 'mcvox' for name in MCVOX_CASES})
-GOLDEN_RUN.update({'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
+GOLDEN_RUN.update({'mcvox_gk2_line_total': (1000, 16), 'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
                    'mcvox_isopoint_fluencerate': (2000, 16)})
 
 
@@ -331,6 +392,12 @@ UNPINNED_CASES = {
 }
 UNPINNED_GEOMETRY = {name: 'mccyl' for name in UNPINNED_CASES}
 UNPINNED_RUN = {name: (2000, 16) for name in UNPINNED_CASES}
+# mcpf/pc.py declares `cl_type(mc)` without `self` / @staticmethod: the reference
+# cannot pack a Pc layer (TypeError), so Pc is pinned through MPc (same sampling
+# branch, reference golden above) and checked oracle <-> GPU only
+UNPINNED_CASES['mcml_pf_pc'] = mcml_pf_pc
+UNPINNED_GEOMETRY['mcml_pf_pc'] = 'mcml'
+UNPINNED_RUN['mcml_pf_pc'] = (3000, 16)
 
 
 def mcml_hg_isopoint_outside(mc, **kw):
