@@ -24,6 +24,7 @@
 #define FP_2 2.0f
 #define FP_0p5 0.5f
 #define FP_2PI 6.283185307179586f
+#define FP_PI 3.141592653589793f
 #define FP_COS_90 0.0f
 #define FP_COS_0 (1.0f - FP_COS_90)
 #define FP_COS_30 0.8660254037844386f
@@ -90,6 +91,9 @@ typedef struct { p3f direction; p2f position; float r_min, inv_dr, pl_min, inv_d
 	uint32_t n_r, n_pl, offset; int32_t r_log_scale, pl_log_scale; } det_radialpl;
 typedef struct { p3f direction; float cos_min, pl_min, inv_dpl;
 	uint32_t n_pl, offset; int32_t pl_log_scale; } det_totalpl;
+/* mcdetector/symmetric.py:45-56 */
+typedef struct { p3f direction; float position_x, x_offset, inv_step, cos_min;
+	uint32_t n_half; int32_t log_scale; uint32_t offset; } det_symx;
 /* mcdetector/cartesianpl.py, mcdetector/probe/sixaroundonepl.py */
 typedef struct { p3f direction; float x_min, inv_dx, y_min, inv_dy, pl_min, inv_dpl, cos_min;
 	uint32_t n_x, n_y, n_pl, offset; int32_t pl_log_scale; } det_cartesianpl;
@@ -103,6 +107,11 @@ typedef struct { float cos_min; uint32_t offset; } det_total_cyl;
 typedef struct { p3f inv_step, top_left; uint32_t nx, ny, nz, offset; int32_t k; } flu_xyz;
 typedef struct { p3f center; float inv_dr, inv_dz; uint32_t n_r, n_z, offset; int32_t k; } flu_rz;
 typedef struct { float inv_step[4], top_left[4]; uint32_t shape[4]; uint32_t offset; int32_t k; } flu_xyzt;
+
+typedef struct { p3f center; float t_min, inv_dr, inv_dz, inv_dt;
+	uint32_t n_r, n_z, n_t, offset; int32_t k; } flu_rzt;       /* mcfluence/fluencerzt.py:54 */
+typedef struct { p2f center; float r_min, fi_min, z_min, inv_dr, inv_dfi, inv_dz;
+	uint32_t n_r, n_fi, n_z, offset; int32_t k; } flu_cyl;       /* mcfluence/fluencecyl.py:56 */
 
 typedef struct { int32_t max_events; uint32_t data_off, count_off, event_mask; } trace_cfg;
 
@@ -508,6 +517,24 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		if (w > 0) accu_deposit(s, d->offset + (uint32_t)pi, w);
 		break;
 	}
+	case XO_DET_SYMMETRICX: {                          /* mcdetector/symmetric.py:106-140 */
+		const det_symx *d = (const det_symx *)base;
+		float x = fabsf(pos->x - d->position_x);
+		int32_t index_x;
+		size_t accu_index;
+		p3f dd = d->direction;
+		if (d->log_scale) x = m_log(s, fmaxf(x, FP_RMIN));
+		index_x = (int32_t)((x - d->x_offset)*d->inv_step);
+		index_x = iclip(index_x, 0, (int32_t)d->n_half - 1);
+		/* the reference reads the simulator position here (== pos at top/bottom) */
+		accu_index = (s->pos.x - d->position_x >= FP_0) ?
+			(size_t)index_x + d->n_half : (size_t)d->n_half - index_x - 1;
+		{
+			uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+			if (w > 0) accu_deposit(s, d->offset + accu_index, w);
+		}
+		break;
+	}
 	case XO_DET_CARTESIANPL: {                         /* mcdetector/cartesianpl.py:131-175 */
 		const det_cartesianpl *d = (const det_cartesianpl *)base;
 		int32_t index_x, index_y, index_pl;
@@ -631,6 +658,40 @@ static void fluence_deposit_at(sim_t *s, const p3f *pos, float weight, float mua
 				fx < f->shape[0] && fy < f->shape[1] && fz < f->shape[2] && ft < f->shape[3]) {
 			uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz, it = (uint32_t)ft;
 			uint32_t index = ((iz*f->shape[1] + iy)*f->shape[0] + ix)*f->shape[3] + it;
+			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
+			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
+			accu_deposit(s, f->offset + index, w);
+		}
+		break;
+	}
+	case XO_FLU_RZT: {                                 /* mcfluence/fluencerzt.py:104-150 */
+		const flu_rzt *f = (const flu_rzt *)j->fluence;
+		float dx = pos->x - f->center.x, dy = pos->y - f->center.y;
+		float r = m_sqrt(dx*dx + dy*dy);
+		float dz = pos->z - f->center.z;
+		float dt = s->opl*FP_INV_C - f->t_min;
+		float fr = r*f->inv_dr, fz = dz*f->inv_dz, ft = dt*f->inv_dt;
+		if (fr >= 0 && fz >= 0 && ft >= 0 && fr < f->n_r && fz < f->n_z && ft < f->n_t) {
+			uint32_t ir = (uint32_t)fr, iz = (uint32_t)fz, it = (uint32_t)ft;
+			uint32_t index = (iz*f->n_r + ir)*f->n_t + it;
+			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
+			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
+			accu_deposit(s, f->offset + index, w);
+		}
+		break;
+	}
+	case XO_FLU_CYL: {                                 /* mcfluence/fluencecyl.py:108-152 */
+		const flu_cyl *f = (const flu_cyl *)j->fluence;
+		/* (the reference reads the simulator position here, which is the
+		 * `position` argument at every call site of AW / AR) */
+		float dx = pos->x - f->center.x, dy = pos->y - f->center.y;
+		float r = m_sqrt(dx*dx + dy*dy);
+		float fi = m_atan2(s, dy, dx) + FP_PI;
+		float fr = (r - f->r_min)*f->inv_dr, fz = (pos->z - f->z_min)*f->inv_dz;
+		float ffi = (fi - f->fi_min)*f->inv_dfi;
+		if (fr >= 0 && fz >= 0 && ffi >= 0 && fr < f->n_r && fz < f->n_z && ffi < f->n_fi) {
+			uint32_t ir = (uint32_t)fr, iz = (uint32_t)fz, ifi = (uint32_t)ffi;
+			uint32_t index = (iz*f->n_fi + ifi)*f->n_r + ir;
 			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
 			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
 			accu_deposit(s, f->offset + index, w);

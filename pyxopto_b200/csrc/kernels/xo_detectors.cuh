@@ -105,6 +105,20 @@ struct DetRadialPl {                // mcdetector/radialpl.py
 	}
 };
 
+struct DetSymmetricX {              // mcdetector/symmetric.py
+	P3 direction; float position_x, x_offset, inv_step, cos_min; u32 n_half; i32 log_scale; u32 offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		float x = fabsf(pos.x - position_x);
+		if (log_scale) x = M::log(fmaxf(x, XO_FP_RMIN));
+		i32 ix = clipi(f2i((x - x_offset)*inv_step), 0, (i32)(n_half - 1));
+		u32 index = (pos.x - position_x >= 0.0f) ? (u32)ix + n_half : n_half - (u32)ix - 1u;
+		u32 iw = weight_u32(w, cos_min <= fabsf(dot3(dir, direction)));
+		if (iw > 0) acc.add(offset + index, iw);
+	}
+};
+
 struct DetCartesianPl {             // mcdetector/cartesianpl.py
 	P3 direction; float x_min, inv_dx, y_min, inv_dy, pl_min, inv_dpl, cos_min;
 	u32 n_x, n_y, n_pl, offset; i32 pl_log_scale;

@@ -120,6 +120,44 @@ struct FluXyzt {                    // mcfluence/fluencet.py:57-63
 	}
 };
 
+struct FluRzt {                     // mcfluence/fluencerzt.py:54-66
+	P3 center; float t_min, inv_dr, inv_dz, inv_dt; u32 n_r, n_z, n_t, offset; i32 k;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float opl) const {
+		float dx = pos.x - center.x, dy = pos.y - center.y;
+		float r = M::sqrt(dx*dx + dy*dy);
+		float dz = pos.z - center.z;
+		float dt = opl*XO_FP_INV_C - t_min;
+		float fr = r*inv_dr, fz = dz*inv_dz, ft = dt*inv_dt;
+		if (fr >= 0.0f && fz >= 0.0f && ft >= 0.0f &&
+				fr < (float)n_r && fz < (float)n_z && ft < (float)n_t) {
+			u32 index = (f2u(fz)*n_r + f2u(fr))*n_t + f2u(ft);
+			acc.add_global(offset + index, fluence_weight(w, mua, k));
+		}
+	}
+};
+
+struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
+	P2 center; float r_min, fi_min, z_min, inv_dr, inv_dfi, inv_dz;
+	u32 n_r, n_fi, n_z, offset; i32 k;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float) const {
+		float dx = pos.x - center.x, dy = pos.y - center.y;
+		float r = M::sqrt(dx*dx + dy*dy);
+		float fi = M::atan2(dy, dx) + 3.141592653589793f;
+		float fr = (r - r_min)*inv_dr, fz = (pos.z - z_min)*inv_dz, ffi = (fi - fi_min)*inv_dfi;
+		if (fr >= 0.0f && fz >= 0.0f && ffi >= 0.0f &&
+				fr < (float)n_r && fz < (float)n_z && ffi < (float)n_fi) {
+			u32 index = (f2u(fz)*n_fi + f2u(ffi))*n_r + f2u(fr);
+			acc.add_global(offset + index, fluence_weight(w, mua, k));
+		}
+	}
+};
+
 // ---- trace ------------------------------------------------------------------
 #ifndef XO_TRACE
 #define XO_TRACE 0

@@ -268,6 +268,140 @@ class FluenceRz(_FluenceBase):
         return cls(Axis.fromdict(d.pop('raxis')), Axis.fromdict(d.pop('zaxis')), **d)
 
 
+class FluenceRzt(_FluenceBase):
+    """Time-resolved radially symmetric grid; bins indexed (z, r, t) in memory,
+    ``shape`` reported as (n_r, n_z, n_t) like the reference (mcfluence/fluencerzt.py)."""
+    cu_type = 'xo::FluRzt'
+    _extra_options = [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClFluenceRzt(cltypes.Structure):
+            _fields_ = [('center', T.mc_point3f_t), ('t_min', T.mc_fp_t),
+                        ('inv_dr', T.mc_fp_t), ('inv_dz', T.mc_fp_t), ('inv_dt', T.mc_fp_t),
+                        ('n_r', T.mc_size_t), ('n_z', T.mc_size_t), ('n_t', T.mc_size_t),
+                        ('offset', T.mc_size_t), ('k', T.mc_int_t)]
+        return ClFluenceRzt
+
+    def __init__(self, raxis=None, zaxis: Axis = None, taxis: Axis = None,
+                 center: Tuple[float, float] = (0.0, 0.0), mode: str = 'deposition'):
+        super().__init__()
+        data, nphotons, k = None, 0, _K_DEFAULT
+        if isinstance(raxis, FluenceRzt):
+            f = raxis
+            raxis, zaxis, taxis, center = Axis(f.raxis), Axis(f.zaxis), Axis(f.taxis), f.center
+            nphotons, mode, k = f.nphotons, f.mode, f.k
+            if f.raw is not None:
+                data = np.copy(f.raw)
+        raxis = Axis(0.0, 1.0, 1) if raxis is None else raxis
+        zaxis = Axis(0.0, 1.0, 1) if zaxis is None else zaxis
+        taxis = Axis(0.0, 1.0, 1) if taxis is None else taxis
+        if raxis.logscale or zaxis.logscale or taxis.logscale:
+            raise ValueError('FluenceRzt does not support logarithmic axes!')
+        self._r_axis, self._z_axis, self._t_axis = raxis, zaxis, taxis
+        self._center = np.zeros((2,))
+        self._center[:] = center
+        self._init_common(mode, k, data, nphotons)
+
+    shape = property(lambda self: (self._r_axis.n, self._z_axis.n, self._t_axis.n))
+    raxis = property(lambda self: self._r_axis)
+    zaxis = property(lambda self: self._z_axis)
+    taxis = property(lambda self: self._t_axis)
+    r = property(lambda self: self._r_axis.centers)
+    z = property(lambda self: self._z_axis.centers)
+    t = property(lambda self: self._t_axis.centers)
+    center = property(lambda self: self._center)
+
+    @property
+    def raw_zrt(self):
+        return None if self._data is None else \
+            self._data.reshape(self._z_axis.n, self._r_axis.n, self._t_axis.n)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        target.center.x, target.center.y = self._center
+        target.center.z = self._z_axis.start
+        target.t_min = self._t_axis.start
+        target.inv_dr = 1.0/self._r_axis.step if self._r_axis.step != 0.0 else 0.0
+        target.inv_dz = 1.0/self._z_axis.step
+        target.inv_dt = 1.0/self._t_axis.step
+        target.n_r, target.n_z, target.n_t = self._r_axis.n, self._z_axis.n, self._t_axis.n
+        target.k = self._k
+        return target
+
+    def todict(self):
+        return {'type': 'FluenceRzt', 'mode': self._mode, 'raxis': self._r_axis.todict(),
+                'zaxis': self._z_axis.todict(), 'taxis': self._t_axis.todict(),
+                'center': self._center.tolist()}
+
+
+class FluenceCyl(_FluenceBase):
+    """Cylindrical r-fi-z grid; raw shape (n_z, n_fi, n_r) (mcfluence/fluencecyl.py)."""
+    cu_type = 'xo::FluCyl'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClFluenceCyl(cltypes.Structure):
+            _fields_ = [('center', T.mc_point2f_t), ('r_min', T.mc_fp_t),
+                        ('fi_min', T.mc_fp_t), ('z_min', T.mc_fp_t),
+                        ('inv_dr', T.mc_fp_t), ('inv_dfi', T.mc_fp_t), ('inv_dz', T.mc_fp_t),
+                        ('n_r', T.mc_size_t), ('n_fi', T.mc_size_t), ('n_z', T.mc_size_t),
+                        ('offset', T.mc_size_t), ('k', T.mc_int_t)]
+        return ClFluenceCyl
+
+    def __init__(self, raxis=None, fiaxis: Axis = None, zaxis: Axis = None,
+                 center: Tuple[float, float] = (0.0, 0.0), mode: str = 'deposition'):
+        super().__init__()
+        data, nphotons, k = None, 0, _K_DEFAULT
+        if isinstance(raxis, FluenceCyl):
+            f = raxis
+            raxis, fiaxis, zaxis, center = Axis(f.raxis), Axis(f.fiaxis), Axis(f.zaxis), f.center
+            nphotons, mode, k = f.nphotons, f.mode, f.k
+            if f.raw is not None:
+                data = np.copy(f.raw)
+        raxis = Axis(0.0, 1.0, 1) if raxis is None else raxis
+        fiaxis = Axis(0.0, 2*np.pi, 1) if fiaxis is None else fiaxis
+        zaxis = Axis(0.0, 1.0, 1) if zaxis is None else zaxis
+        if raxis.logscale or fiaxis.logscale or zaxis.logscale:
+            raise ValueError('FluenceCyl does not support logarithmic axes!')
+        self._r_axis, self._fi_axis, self._z_axis = raxis, fiaxis, zaxis
+        self._center = np.zeros((2,))
+        self._center[:] = center
+        self._init_common(mode, k, data, nphotons)
+
+    shape = property(lambda self: (self._z_axis.n, self._fi_axis.n, self._r_axis.n))
+    raxis = property(lambda self: self._r_axis)
+    fiaxis = property(lambda self: self._fi_axis)
+    zaxis = property(lambda self: self._z_axis)
+    r = property(lambda self: self._r_axis.centers)
+    fi = property(lambda self: self._fi_axis.centers)
+    z = property(lambda self: self._z_axis.centers)
+    center = property(lambda self: self._center)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        target.center.x, target.center.y = self._center
+        target.r_min, target.fi_min, target.z_min = \
+            self._r_axis.start, self._fi_axis.start, self._z_axis.start
+        target.inv_dr = 1.0/self._r_axis.step
+        target.inv_dfi = 1.0/self._fi_axis.step
+        target.inv_dz = 1.0/self._z_axis.step
+        target.n_r, target.n_fi, target.n_z = self._r_axis.n, self._fi_axis.n, self._z_axis.n
+        target.k = self._k
+        return target
+
+    def todict(self):
+        return {'type': 'FluenceCyl', 'mode': self._mode, 'raxis': self._r_axis.todict(),
+                'fiaxis': self._fi_axis.todict(), 'zaxis': self._z_axis.todict(),
+                'center': self._center.tolist()}
+
+
 class Fluencet(_FluenceBase):
     """Time-resolved x-y-z-t grid; raw shape (nz, ny, nx, nt) (mcfluence/fluencet.py).
     Time = optical path length / c, so the kernel tracks the optical path length."""

@@ -11,7 +11,7 @@ import numpy as np
 from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import geometry
-from ..mcbase.mcutil.axis import Axis, RadialAxis  # noqa: F401
+from ..mcbase.mcutil.axis import Axis, RadialAxis, SymmetricAxis  # noqa: F401
 from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
 
 NONE, TOP, BOTTOM, SPECULAR = 'none', 'top', 'bottom', 'specular'
@@ -426,6 +426,57 @@ class TotalPl(Detector):
     def todict(self):
         return {'type': 'TotalPl', 'plaxis': self._pl_axis.todict(),
                 'cosmin': self._cosmin, 'direction': self._direction.tolist()}
+
+
+class SymmetricX(Detector):
+    """Bins along x, symmetric around a center; integrates over y (symmetric.py)."""
+    cu_type = 'xo::DetSymmetricX'
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClSymmetricX(cltypes.Structure):
+            _fields_ = [('direction', T.mc_point3f_t), ('position_x', T.mc_fp_t),
+                        ('x_offset', T.mc_fp_t), ('inv_step', T.mc_fp_t),
+                        ('cos_min', T.mc_fp_t), ('n_half', T.mc_size_t),
+                        ('log_scale', T.mc_int_t), ('offset', T.mc_size_t)]
+        return ClSymmetricX
+
+    def __init__(self, xaxis, cosmin: float = 0.0, direction=(0.0, 0.0, 1.0)):
+        if isinstance(xaxis, SymmetricX):
+            o = xaxis
+            xaxis, cosmin, direction = type(o.xaxis)(o.xaxis), o.cosmin, o.direction
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            raw, nphotons = np.zeros((xaxis.n,)), 0
+        super().__init__(raw, nphotons)
+        self._x_axis = xaxis
+        self.cosmin, self.direction = cosmin, direction
+        self._inv_accumulators_width = 1.0/(xaxis.edges[1:] - xaxis.edges[:-1])
+
+    xaxis = property(lambda self: self._x_axis)
+    x = property(lambda self: self._x_axis.centers)
+    edges = property(lambda self: self._x_axis.edges)
+
+    @property
+    def normalized(self):
+        return self.raw*self._inv_accumulators_width*(1.0/max(self.nphotons, 1.0))
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        target.direction.fromarray(self._direction)
+        target.position_x = self._x_axis.center
+        target.x_offset = self._x_axis.scaled_offset
+        target.inv_step = 1.0/self._x_axis.step if self._x_axis.step != 0.0 else 0.0
+        target.log_scale = self._x_axis.logscale
+        target.n_half = self._x_axis.n_half
+        target.cos_min = self._cosmin
+        return target
+
+    def todict(self):
+        return {'type': 'SymmetricX', 'xaxis': self._x_axis.todict(), 'cosmin': self._cosmin,
+                'direction': self._direction.tolist()}
 
 
 class CartesianPl(Detector):

@@ -192,7 +192,42 @@ mcml_pf_pc = _pf_case(lambda mc: mc.mcpf.Pc(6.0), 34)
 mcml_pf_mpc = _pf_case(lambda mc: mc.mcpf.MPc(8.0, 0.85), 35)
 
 
+def mcml_hg_gauss_fluencerzt(mc, **kw):
+    """Time-resolved r-z deposition (FluenceRzt)."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceRzt(Axis(0, 2e-3, 20), Axis(0, 3e-3, 30), Axis(0, 40e-12, 16),
+                                  center=(0.1e-3, 0.0))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.GaussianBeam(150e-6), det,
+                 fluence=flu, rnginit=60606, **kw), dict(rmax=20e-3)
+
+
+def mcml_hg_fiber_fluencecyl(mc, **kw):
+    """Cylindrical r-fi-z deposition grid (FluenceCyl)."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceCyl(Axis(0, 2e-3, 20), Axis(0, 2*np.pi, 12), Axis(0, 3e-3, 30),
+                                  center=(0.05e-3, -0.05e-3))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)),
+                 mc.mcsource.UniformFiber(fib, position=(0.1e-3, 0, 0), direction=(0.2, 0.1, 1)),
+                 det, fluence=flu, rnginit=70707, **kw), dict(rmax=20e-3)
+
+
+def mcml_hg_line_symmetricx(mc, **kw):
+    """SymmetricX detectors: linear bins on top, logarithmic bins at the bottom."""
+    SA = mc.mcdetector.SymmetricAxis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.SymmetricX(SA(0.1e-3, 3e-3, 30), cosmin=0.3),
+        bottom=mc.mcdetector.SymmetricX(SA(0.0, 3e-3, 20, logscale=True)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line((0.05e-3, 0, 0), (0.1, 0, 1)),
+                 det, rnginit=80808, **kw), dict(rmax=20e-3)
+
+
 MCML_CASES = {
+    'mcml_hg_line_symmetricx': mcml_hg_line_symmetricx,
+    'mcml_hg_gauss_fluencerzt': mcml_hg_gauss_fluencerzt,
+    'mcml_hg_fiber_fluencecyl': mcml_hg_fiber_fluencecyl,
     'mcml_pf_hg2': mcml_pf_hg2, 'mcml_pf_gk2': mcml_pf_gk2, 'mcml_pf_mgk': mcml_pf_mgk,
     'mcml_pf_mpc': mcml_pf_mpc,
     'mcml_hg_ubeam_radial': mcml_hg_ubeam_radial,
