@@ -28,9 +28,8 @@ struct VoxSrcLine {                 // mcvox/mcsource/line.py:57-63
 // Specular reflectance + refracted direction of a ray entering the box at a
 // point whose voxel is looked up from `lookup_pos` (see the IsotropicPoint note).
 template <class Ctx>
-__device__ __forceinline__ float vox_enter(const Ctx &ctx, const P3 &lookup_pos,
-		const P3 &normal, const P3 &direction, P3 *refracted) {
-	float n_out = ctx.material_n(0);
+__device__ __forceinline__ float vox_enter_n(const Ctx &ctx, const P3 &lookup_pos,
+		const P3 &normal, const P3 &direction, P3 *refracted, float n_out) {
 	i32 vx, vy, vz;
 	ctx.position_to_voxel(lookup_pos, &vx, &vy, &vz);
 	vx = clipi(vx, 0, ctx.cfg.nx - 1);
@@ -42,38 +41,107 @@ __device__ __forceinline__ float vox_enter(const Ctx &ctx, const P3 &lookup_pos,
 	return reflectance(n_out, n_in, dot3(normal, direction), cos_critical(n_out, n_in));
 }
 
+template <class Ctx>
+__device__ __forceinline__ float vox_enter(const Ctx &ctx, const P3 &lookup_pos,
+		const P3 &normal, const P3 &direction, P3 *refracted) {
+	return vox_enter_n(ctx, lookup_pos, normal, direction, refracted, ctx.material_n(0));
+}
+
+// Collimated beam whose launch point `pm` (source plane) is projected onto the
+// box surface along the beam direction: shared tail of GaussianBeam / UniformBeam
+// (mcvox/mcsource/gaussianbeam.py:140-188, uniformbeam.py:95-148)
+template <class Ctx>
+__device__ __forceinline__ void vox_beam_enter(const Ctx &ctx, const P3 &pm, const P3 &direction, Launch &L) {
+	float rs = 0.0f;
+	P3 d = { direction.x, direction.y, direction.z };
+	if (ctx.box_contains(pm)) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
+	P3 isect, normal;
+	if (ctx.box_intersect(pm, d, &isect, &normal)) {
+		L.pos = isect;
+		d.x = -d.x; d.y = -d.y; d.z = -d.z;
+		normal.x = -normal.x; normal.y = -normal.y; normal.z = -normal.z;
+		P3 refracted;
+		rs = vox_enter(ctx, isect, normal, d, &refracted);
+		L.dir = refracted;
+		L.spec_dir = d;
+		L.spec_weight = rs;
+	} else {
+		L.pos = ctx.cfg.top_left;
+		L.dir.x = 0.0f; L.dir.y = 0.0f; L.dir.z = 1.0f;
+		rs = 1.0f;
+		L.spec_weight = -1.0f;      // the reference deposits nothing on a miss
+	}
+	L.weight = 1.0f - rs;
+}
+
+struct VoxSrcUniformBeam {          // mcvox/mcsource/uniformbeam.py:36-44
+	M3 T; P3 position, direction; P2 radius;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		float sf, cf;
+		float rs = M::sqrt(rng.next());
+		M::sincos(XO_FP_2PI*rng.next(), &sf, &cf);
+		P3 ps = { rs*cf*radius.x, rs*sf*radius.y, 0.0f };
+		P3 pm = transform3(T, ps);
+		pm.x += position.x; pm.y += position.y; pm.z += position.z;
+		vox_beam_enter(ctx, pm, direction, L);
+	}
+};
+
+struct VoxSrcUniformFiber {         // mcvox/mcsource/fiber.py (UniformFiber)
+	M3 T; P3 position, direction; float radius, cos_min, n;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		float sf, cf, rs = 0.0f;
+		float r = M::sqrt(rng.next())*radius;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		P3 ps = { r*cf, r*sf, 0.0f };
+		P3 pm = transform3(T, ps);
+		pm.x += position.x; pm.y += position.y; pm.z += position.z;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 1.0f - rng.next()*(1.0f - cos_min);
+		float st = M::sqrt(1.0f - ct*ct);
+		st = M::div(st, n);             // emission angle inside the fibre core
+		ct = M::sqrt(1.0f - st*st);
+		P3 pd = { cf*st, sf*st, ct };
+		P3 packet_dir = transform3(T, pd);
+		P3 sd = { direction.x, direction.y, direction.z };
+		if (ctx.box_contains(pm)) { sd.x = -sd.x; sd.y = -sd.y; sd.z = -sd.z; }
+		P3 refracted = packet_dir, p = position, isect, normal;
+		if (ctx.box_intersect(pm, sd, &isect, &normal)) {
+			normal.x = -normal.x; normal.y = -normal.y; normal.z = -normal.z;
+			p = isect;
+			rs = vox_enter_n(ctx, isect, normal, packet_dir, &refracted, n);
+		} else {
+			p = ctx.cfg.top_left;
+			rs = 1.0f;
+		}
+		L.pos = p;
+		L.dir = refracted;
+		L.spec_dir = packet_dir;
+		L.spec_weight = rs;
+		L.weight = 1.0f - rs;
+	}
+};
+
 struct VoxSrcGaussianBeam {         // mcvox/mcsource/gaussianbeam.py:71-77
 	M3 T; P3 position, direction; P2 sigma; float clip;
 	__device__ __forceinline__ P3 origin() const { return position; }
 	template <class Ctx>
 	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
 		(void)prev_pos;
-		float sf, cf, rs = 0.0f;
+		float sf, cf;
 		float r = M::sqrt(-2.0f*M::log(1.0f - rng.next()));
 		r = fminf(r, clip);
 		M::sincos(XO_FP_2PI*rng.next(), &sf, &cf);
 		P3 ps = { r*cf*sigma.x, r*sf*sigma.y, 0.0f };
 		P3 pm = transform3(T, ps);
 		pm.x += position.x; pm.y += position.y; pm.z += position.z;
-		P3 d = { direction.x, direction.y, direction.z };
-		if (ctx.box_contains(pm)) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
-		P3 isect, normal;
-		if (ctx.box_intersect(pm, d, &isect, &normal)) {
-			L.pos = isect;
-			d.x = -d.x; d.y = -d.y; d.z = -d.z;
-			normal.x = -normal.x; normal.y = -normal.y; normal.z = -normal.z;
-			P3 refracted;
-			rs = vox_enter(ctx, isect, normal, d, &refracted);
-			L.dir = refracted;
-			L.spec_dir = d;
-			L.spec_weight = rs;
-		} else {
-			L.pos = ctx.cfg.top_left;
-			L.dir.x = 0.0f; L.dir.y = 0.0f; L.dir.z = 1.0f;
-			rs = 1.0f;
-			L.spec_weight = -1.0f;      // the reference deposits nothing on a miss
-		}
-		L.weight = 1.0f - rs;
+		vox_beam_enter(ctx, pm, direction, L);
 	}
 };
 

@@ -124,6 +124,113 @@ class GaussianBeam(Source):
                 'direction': self._direction.tolist(), 'type': type(self).__name__}
 
 
+class UniformBeam(Source):
+    """Collimated uniform (top-hat) beam with an elliptical cross section
+    (mcvox/mcsource/uniformbeam.py)."""
+    cu_type = 'xo::VoxSrcUniformBeam'
+    cu_refill_lanes = 6
+    _update_keys = ('diameter', 'position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformBeam(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_point2f_t)]
+        return ClUniformBeam
+
+    def __init__(self, diameter, position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._position = np.zeros((3,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self._diameter = np.zeros((2,))
+        self.diameter = diameter
+        self.position, self.direction = position, direction
+
+    def _set_diameter(self, d):
+        self._diameter[:] = d
+        self._diameter = np.maximum(0.0, self._diameter)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        self._direction[:] = _unit(d)
+
+    diameter = property(lambda self: self._diameter, _set_diameter, None,
+                        'Beam diameter along the x and y axis (m).')
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius.x = self._diameter[0]*0.5
+        target.radius.y = self._diameter[1]*0.5
+        return target, None, None
+
+    def todict(self):
+        return {'diameter': self._diameter.tolist(), 'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class UniformFiber(Source):
+    """Multimode fibre with a uniform emission within its NA, pressed against
+    (or pointing at) the voxel box (mcvox/mcsource/fiber.py UniformFiber)."""
+    cu_type = 'xo::VoxSrcUniformFiber'
+    cu_refill_lanes = 6
+    _update_keys = ('fiber', 'position', 'direction')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformFiber(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('cos_min', T.mc_fp_t), ('n', T.mc_fp_t)]
+        return ClUniformFiber
+
+    def __init__(self, fiber, position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        super().__init__()
+        self._fiber = fiber
+        self._position = np.zeros((3,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self.position, self.direction = position, direction
+
+    def _set_fiber(self, f):
+        self._fiber = f
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_direction(self, d):
+        self._direction[:] = _unit(d)
+
+    fiber = property(lambda self: self._fiber, _set_fiber)
+    position = property(lambda self: self._position, _set_position)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.n = self._fiber.ncore
+        target.cos_min = (1.0 - (self._fiber.na)**2)**0.5
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+    def todict(self):
+        return {'fiber': self._fiber.todict(), 'position': self._position.tolist(),
+                'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
 class IsotropicPoint(Source):
     """Isotropic point source inside or outside the voxel box (mcvox/mcsource/point.py)."""
     cu_type = 'xo::VoxSrcIsotropicPoint'

@@ -320,7 +320,34 @@ def mcvox_gk2_line_total(mc, **kw):
     return _fill_skin_vessel(sim, center=200e-6, radius=60e-6), dict(rmax=5e-3)
 
 
+def mcvox_ubeam_radial(mc, **kw):
+    """mcvox UniformBeam (tilted, elliptical) launched from above the box."""
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc, n=(20, 20, 16))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(A(0, 0.3e-3, 15)),
+                                  bottom=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg),
+                mc.mcsource.UniformBeam((120e-6, 80e-6), position=(10e-6, 0, -0.1e-3),
+                                        direction=(0.15, -0.1, 1.0)),
+                detectors=det, rnginit=2244, **kw)
+    return _fill_skin_vessel(sim, center=200e-6, radius=60e-6), dict(rmax=5e-3)
+
+
+def mcvox_ufiber_fluence(mc, **kw):
+    """mcvox UniformFiber in contact with the top surface + deposition grid."""
+    vox = _vox_grid(mc, n=(20, 20, 16))
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg),
+                mc.mcsource.UniformFiber(_fiber(mc), position=(5e-6, -5e-6, 0.0),
+                                         direction=(0.0, 0.1, 1.0)),
+                detectors=det, fluence=flu, rnginit=4466, **kw)
+    return _fill_skin_vessel(sim, center=200e-6, radius=60e-6), dict(rmax=5e-3)
+
+
 MCVOX_CASES = {
+    'mcvox_ubeam_radial': mcvox_ubeam_radial,
+    'mcvox_ufiber_fluence': mcvox_ufiber_fluence,
     'mcvox_gk2_line_total': mcvox_gk2_line_total,
     'mcvox_gauss_fluence': mcvox_gauss_fluence,
     'mcvox_line_mhg_trace': mcvox_line_mhg_trace,
@@ -328,7 +355,8 @@ MCVOX_CASES = {
 }
 ALL_CASES.update(MCVOX_CASES)
 GEOMETRY.update({name: 'mcvox' for name in MCVOX_CASES})
-GOLDEN_RUN.update({'mcvox_gk2_line_total': (1000, 16), 'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
+GOLDEN_RUN.update({'mcvox_ubeam_radial': (1500, 16), 'mcvox_ufiber_fluence': (1500, 16),
+                   'mcvox_gk2_line_total': (1000, 16), 'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
                    'mcvox_isopoint_fluencerate': (2000, 16)})
 
 
