@@ -613,7 +613,7 @@ class McBase(CuWorker):
         tbuf.download(self._stream, total)
         accus = []
         for a in (self.cl_rw_accumulator_allocator.allocations(sv) if download else ()):
-            host = np.empty(a.shape, dtype=a.dtype)
+            host = self._download_host_array('accumulator', a)
             abuf.download(self._stream, host, offset=a.offset*8)
             accus.append(host)
         if accus:

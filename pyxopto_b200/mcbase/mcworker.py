@@ -224,6 +224,22 @@ class CuWorker:
 
     PINNED_MIN_BYTES = 1 << 20
 
+    def _download_host_array(self, kind: str, a) -> np.ndarray:
+        """Host array for the download of allocation ``a``.  Large accumulator
+        grids (201^3 x 8 B = 65 MB) come back through a page-locked staging array
+        that is reused by every run: ``update_data()`` only reads the raw integers
+        (raw += accu*(1/k)), it never keeps the array."""
+        if kind != 'accumulator' or a.size*np.dtype(a.dtype).itemsize < self.PINNED_MIN_BYTES:
+            return np.empty(a.shape, dtype=a.dtype)
+        key = (kind, a.offset, a.shape)
+        host = self._pinned_downloads.get(key)
+        if host is None:
+            if len(self._pinned_downloads) >= 4:
+                self._pinned_downloads.clear()
+            host = abi.pinned_empty(self._ctx, a.shape, a.dtype)
+            self._pinned_downloads[key] = host
+        return host
+
     def _download_allocations(self, owner, nphotons: int):
         """{dtype: [ndarray per allocation]} for one plugin (cf. mc.py:1020-1038)."""
         out = {}
@@ -234,18 +250,8 @@ class CuWorker:
                     continue
                 if hasattr(owner, 'np_buffer'):
                     host = owner.np_buffer(self, a, nphotons=nphotons)
-                elif kind == 'accumulator' and a.size*alloc.dtype.itemsize >= self.PINNED_MIN_BYTES:
-                    # large grids (201^3 x 8 B = 65 MB) come back through a page-locked
-                    # staging array that is reused by every run: update_data() only
-                    # reads the raw integers (raw += accu*(1/k))
-                    key = (kind, a.offset, a.shape)
-                    host = self._pinned_downloads.get(key)
-                    if host is None:
-                        self._pinned_downloads.clear()
-                        host = abi.pinned_empty(self._ctx, a.shape, a.dtype)
-                        self._pinned_downloads[key] = host
                 else:
-                    host = np.empty(a.shape, dtype=a.dtype)
+                    host = self._download_host_array(kind, a)
                 buf.download(self._stream, host, offset=a.offset*alloc.dtype.itemsize)
                 out.setdefault(alloc.dtype, []).append(host)
         return out

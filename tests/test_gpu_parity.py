@@ -202,6 +202,51 @@ def test_fast_mode_agrees_with_deterministic_mode_at_scale(config, n):
     assert checked > 0
 
 
+@pytest.mark.parametrize('name', ['mcvox_line_mhg_trace', 'mcml_lut_iso_radialpl_trace',
+                                  'mccyl_gk_ubeam_fiz_trace'])
+def test_throughput_mode_trace_statistics(name):
+    """Trace recording in the throughput loops (mcvox: one event per crossing /
+    interaction of the voxel walk, like the reference's loop trips): the
+    distribution of per-packet event counts, the overflow fraction and the
+    terminal events (position, weight, path length) agree with the oracle."""
+    n = 40000
+    sim, geom, _ = build_sim(name)
+    sim.run(n, download=False)
+    accu, ints, floats = sim.download_raw()
+    desc = xo_oracle.describe(sim, geom)
+    ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
+                        math=xo_oracle.MATH_LIBM)
+    tp = sim._packed['trace']
+    maxlen = int(sim.trace.maxlen)
+    co, do = int(tp.count_buffer_offset), int(tp.data_buffer_offset)
+
+    def unpack(ints_, floats_):
+        cnt = ints_[co:co + n].astype(np.float64)
+        rows = floats_[do:do + n*maxlen*8].reshape(n, maxlen, 8)
+        last = np.minimum(cnt.astype(np.int64), maxlen) - 1
+        term = rows[np.arange(n), np.maximum(last, 0)]
+        return cnt, term
+
+    cg, tg = unpack(ints, floats)
+    cr, tr = unpack(ref['ints'], ref['floats'])
+    assert cg.min() >= 1
+
+    def close(a, b, what, k=5.0):
+        se = np.sqrt((a.var() + b.var())/n)
+        assert abs(a.mean() - b.mean()) <= k*se + 1e-9, (what, a.mean(), b.mean(), se)
+
+    close(cg, cr, 'events per packet')
+    close((cg >= maxlen).astype(float), (cr >= maxlen).astype(float), 'overflow fraction')
+    ok_g, ok_r = cg < maxlen, cr < maxlen
+    for col, what in ((0, 'x'), (1, 'y'), (2, 'z'), (5, 'pz'), (6, 'w'), (7, 'pl')):
+        close(tg[ok_g, col].astype(np.float64), tr[ok_r, col].astype(np.float64),
+              'terminal ' + what)
+    # first recorded event is the launch in both
+    fg = floats[do:do + n*maxlen*8].reshape(n, maxlen, 8)[:, 0, :]
+    fr = ref['floats'][do:do + n*maxlen*8].reshape(n, maxlen, 8)[:, 0, :]
+    close(fg[:, 6].astype(np.float64), fr[:, 6].astype(np.float64), 'launch weight')
+
+
 def test_run_returns_reference_style_results():
     sim, _, mc = build_sim('mcml_c1_slab')
     trace, fluence, detectors = sim.run(100000)
