@@ -307,6 +307,19 @@ class McBase(CuWorker):
         words += 2*priv_len
         return words*4 + 16, lut_len, priv_len
 
+    def _trace_tails_unread(self) -> bool:
+        """True when nothing ever reads trace events beyond a packet's own count:
+        the float buffer holds only trace rows and they leave the device through
+        the device-side filter, whose compaction writes the zero tails itself
+        (TraceCompact), or feed ``sampling_volume``, which reads ``n`` events per
+        packet.  The reference zero-fills the whole trace buffer before every run
+        (16 GB for 1e6 packets x 512 events); here that pass is skipped then."""
+        tr = self._trace
+        if tr is None or tr.filter is None or not self.device_trace_filter:
+            return False
+        allocs = self._allocators['float'].allocations()
+        return bool(allocs) and all(a.owner is tr for a in allocs)
+
     def _kernel_args(self, nphotons, bufs, lut_len, priv_len, chunk, refill, window):
         raise NotImplementedError
 
@@ -367,7 +380,7 @@ class McBase(CuWorker):
             lut_host = np.zeros(4, np.float32)
         lbuf = self.cl_r_buffer('fp_lut', lut_host)
         abuf = self._rw_flat_buffer('accumulator')
-        fbuf = self._rw_flat_buffer('float')
+        fbuf = self._rw_flat_buffer('float', fill=not self._trace_tails_unread())
         ibuf = self._rw_flat_buffer('int')
         shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
         queue_bytes = 0 if deterministic else 36*block + 16   # per-warp launch queues
@@ -506,8 +519,10 @@ class McBase(CuWorker):
         cbuf.download(self._stream, counters)
         n_dropped, n_sel = int(counters[0]), int(counters[1])
         maxlen = int(trace.maxlen)
-        obuf_i = self._buffer('trace_compact_int', 4*max(n_sel, 1))
-        obuf_f = self._buffer('trace_compact_float', 32*maxlen*max(n_sel, 1))
+        # (the accepted count varies from run to run: grow with 50 % headroom so
+        # that a few more rows do not cost a cuMemFree + cuMemAlloc every run)
+        obuf_i = self._buffer_with_headroom('trace_compact_int', 4*max(n_sel, 1))
+        obuf_f = self._buffer_with_headroom('trace_compact_float', 32*maxlen*max(n_sel, 1))
         mod.kernel('TraceCompact').launch(self._stream, grid, block, [
             np.uint32(nphotons), tp, flags, cta, ibuf, fbuf, obuf_i, obuf_f])
         ev1.record(self._stream)

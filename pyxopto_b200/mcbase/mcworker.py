@@ -180,6 +180,13 @@ class CuWorker:
             self._cl_buffers[name] = buf
         return buf
 
+    def _buffer_with_headroom(self, name: str, nbytes: int) -> abi.Buffer:
+        """Like :meth:`_buffer`, but a (re)allocation reserves 1.5 x ``nbytes``."""
+        buf = self._cl_buffers.get(name)
+        if buf is not None and buf.size >= nbytes:
+            return buf
+        return self._buffer(name, nbytes + nbytes//2)
+
     def cl_r_buffer(self, name: str, host=None, size: int = None) -> abi.Buffer:
         """Upload a packed struct / array into a named read-only buffer."""
         if host is None:
