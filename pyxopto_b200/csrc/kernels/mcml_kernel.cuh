@@ -77,6 +77,16 @@ typedef TraceCfg XoTrace;
 typedef TraceNone XoTrace;
 #endif
 
+// Throughput mode with a full trace (one 32-byte event per loop trip and lane):
+// events are staged per lane in shared memory and leave as whole 128-byte lines
+// (4 events), 8 lanes per line -- written directly, every STG.128 of a warp
+// touches 32 different 16 KB-strided rows (32 LSU wavefronts per instruction,
+// measured 1.9 TB/s of the 6.5 TB/s the trace stream could use).
+#ifndef XO_TRACE_STAGED
+#define XO_TRACE_STAGED 0
+#endif
+#define XO_STAGE_F4_PER_WARP 264        // 8 float4 columns x (32 lanes + 1 pad)
+
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetTop::needs_opl || XoDetBottom::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
 
@@ -241,6 +251,12 @@ McKernel(
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;
 	u32 *q_l = reinterpret_cast<u32 *>(xo_smem) + off_words + blockDim.x*8u + (threadIdx.x & ~31u);
+#if XO_TRACE_STAGED
+	off_words += blockDim.x*9u;
+	off_words = (off_words + 3u) & ~3u;
+	float4 *stage = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) +
+		(threadIdx.x >> 5)*XO_STAGE_F4_PER_WARP;
+#endif
 #endif
 	__syncthreads();
 
@@ -276,7 +292,27 @@ McKernel(
 #else
 #define XO_RMAX_TEST() do { } while (0)
 #endif
-#if XO_TRACE
+#if XO_TRACE && XO_TRACE_STAGED && !XO_DETERMINISTIC
+	// staged events of this lane: 4-bit slot mask within the line `stg_line`
+	u32 stg_mask = 0, stg_line = 0;
+	bool stg_pending = false;
+#define XO_TRACE_TRIP() do { \
+		flags |= done ? EV_TERMINATED : 0u; \
+		{ \
+			const u32 last_ = (u32)tcfg.max_events - 1u; \
+			const u32 slot_ = trace_count < last_ ? trace_count : last_; \
+			const u32 col_ = (slot_ & 3u)*2u; \
+			stage[col_*33u + (threadIdx.x & 31u)] = make_float4(pos.x, pos.y, pos.z, dir.x); \
+			stage[(col_ + 1u)*33u + (threadIdx.x & 31u)] = make_float4(dir.y, dir.z, weight, opl); \
+			stg_mask |= 1u << (slot_ & 3u); \
+			stg_line = slot_ >> 2; \
+			++trace_count; \
+			const u32 next_ = trace_count < last_ ? trace_count : last_; \
+			stg_pending = done || (next_ >> 2) != stg_line; \
+		} \
+		if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
+	} while (0)
+#elif XO_TRACE
 #define XO_TRACE_TRIP() do { \
 		flags |= done ? EV_TERMINATED : 0u; \
 		if (XO_TRACE == XO_TRACE_ALL || ((XO_TRACE & XO_TRACE_END) && done)) { \
@@ -458,6 +494,32 @@ McKernel(
 #endif
 
 	for (;;) {
+#if XO_TRACE && XO_TRACE_STAGED
+		// ---- flush completed trace lines: 8 lanes write one 128-byte line ------------
+		{
+			u32 pend = __ballot_sync(0xffffffffu, stg_pending);
+			while (pend != 0u) {
+				// the four lowest pending lanes, one per group of 8 lanes
+				const u32 p0 = pend, p1 = p0 & (p0 - 1u), p2 = p1 & (p1 - 1u), p3 = p2 & (p2 - 1u);
+				const u32 grp = (threadIdx.x >> 3) & 3u;
+				const u32 sel = grp == 0u ? p0 : (grp == 1u ? p1 : (grp == 2u ? p2 : p3));
+				const bool have = sel != 0u;
+				const u32 src = have ? (u32)__ffs((int)sel) - 1u : 0u;
+				const u32 s_mask = __shfl_sync(0xffffffffu, stg_mask, src);
+				const u32 s_line = __shfl_sync(0xffffffffu, stg_line, src);
+				const u32 s_packet = __shfl_sync(0xffffffffu, packet, src);
+				const u32 k = threadIdx.x & 7u;         // float4 of the line; event slot k >> 1
+				if (have && ((s_mask >> (k >> 1)) & 1u)) {
+					float4 *line = reinterpret_cast<float4 *>(float_buffer + tcfg.data_off) +
+						((u64)s_packet*(u64)tcfg.max_events + (u64)s_line*4u)*2u;
+					line[k] = stage[k*33u + src];
+				}
+				pend = p3 & (p3 - 1u);
+			}
+			if (stg_pending) { stg_mask = 0; stg_pending = false; }
+			__syncwarp();
+		}
+#endif
 		// ---- hand new packets to the lanes that need one -------------------------
 		// (a lane that ran out of packets waits until `chunk` lanes need one, or
 		// nothing else is running: popping for one lane at a time would run the
@@ -571,6 +633,10 @@ McKernel(
 				XO_END_TRIP();
 			}
 		}
+#if XO_TRACE && XO_TRACE_STAGED
+		// a completed trace line is flushed (loop top) before the lane records again
+		if (stg_pending) continue;
+#endif
 		if (state != ST_RUN) continue;
 
 		// ---- one step of the packet ----------------------------------------------------

@@ -187,6 +187,7 @@ class McBase(CuWorker):
             '#define XO_FLUENCE_RATE {}'.format(
                 int(bool(opts.get('MC_FLUENCE_MODE_RATE', False)))),
             '#define XO_TRACE_ALIGNED {}'.format(int(self._trace_aligned())),
+            '#define XO_TRACE_STAGED {}'.format(int(self._trace_staged(opts))),
             '#define XO_USE_RMAX {}'.format(int(self._rmax_needed())),
             '#define XO_FLU_WINDOW {}'.format(int(self._window_enabled())),
             '#define XO_BLOCK {}'.format(int(block)),
@@ -236,6 +237,17 @@ class McBase(CuWorker):
         tr = self._packed.get('trace')
         return self._trace is not None and tr is not None and \
             tr.data_buffer_offset % 4 == 0
+
+    def _trace_staged(self, opts=None) -> bool:
+        """Full traces of the layered throughput kernel leave through a
+        shared-memory stage as whole 128-byte lines (mcml_kernel.cuh)."""
+        opts = self.resolved_options() if opts is None else opts
+        return (self.geometry == 'mcml' and self._trace is not None and
+                int(opts.get('MC_USE_TRACE', 0)) == 7 and
+                not opts.get('XO_DETERMINISTIC', False) and
+                not opts.get('MC_USE_EVENTS', False) and
+                self._trace_aligned() and int(self._trace.maxlen) % 4 == 0 and
+                int(self._trace.maxlen) >= 4)
 
     def export_src(self, filename: str = None, nphotons: int = 1) -> str:
         self._pack(nphotons)
@@ -384,6 +396,8 @@ class McBase(CuWorker):
         ibuf = self._rw_flat_buffer('int')
         shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
         queue_bytes = 0 if deterministic else 36*block + 16   # per-warp launch queues
+        if self._trace_staged():
+            queue_bytes += (block//32)*264*16 + 16            # per-warp trace stage
         window = self._fluence_window(block, shared + queue_bytes)
         shared += 4*int(window[3])*int(window[4])*int(window[5]) + queue_bytes
         grid, block = self.launch_geometry(kernel, block, shared, maxthreads)

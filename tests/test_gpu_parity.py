@@ -247,6 +247,70 @@ def test_throughput_mode_trace_statistics(name):
     close(fg[:, 6].astype(np.float64), fr[:, 6].astype(np.float64), 'launch weight')
 
 
+@pytest.mark.parametrize('maxlen', [512, 64, 8])
+def test_staged_trace_rows_are_consistent(maxlen):
+    """Config 4's trace stream leaves the throughput kernel through a per-lane
+    shared-memory stage, one 128-byte line (4 events) at a time.  Every packet's
+    row must be a coherent trajectory (launch event first, unit directions, z
+    inside the slab, optical path length non-decreasing, terminal event last,
+    zero tail) and the per-packet statistics must agree with the oracle."""
+    import benchcfg
+    from pyxopto_b200.mcml import mc
+    n = 30000
+    sim = benchcfg.c4_trace(mc, maxlen=maxlen)
+    sim.device_trace_filter = False          # raw rows wanted: zero-filled tails
+    assert sim._pack(n) is not None and sim._trace_staged()
+    sim.run(n, download=False)
+    accu, ints, floats = sim.download_raw()
+    tp = sim._packed['trace']
+    co, do = int(tp.count_buffer_offset), int(tp.data_buffer_offset)
+    cnt = ints[co:co + n]
+    rows = floats[do:do + n*maxlen*8].reshape(n, maxlen, 8)
+    assert cnt.min() >= 2
+    nrec = np.minimum(cnt, maxlen)
+    idx = np.arange(maxlen)[None, :]
+    valid = idx < nrec[:, None]
+    # zero tails, non-zero recorded events (|dir| = 1)
+    assert not rows[~valid].any()
+    dn = np.linalg.norm(rows[..., 3:6], axis=2)
+    assert np.allclose(dn[valid], 1.0, atol=1e-4)
+    # launch event first: Line source at the origin, weight 1 - Rspecular
+    assert np.allclose(rows[:, 0, :3], 0.0) and np.allclose(rows[:, 0, 5], 1.0)
+    assert np.allclose(rows[:, 0, 6], 1.0 - ((1.33 - 1)/(1.33 + 1))**2, atol=1e-6)
+    z = rows[..., 2]
+    assert z[valid].min() >= -1e-9 and z[valid].max() <= 10e-3 + 1e-8
+    # optical path length never decreases along a row (rows are not interleaved);
+    # the last slot of an overflowed row was overwritten by later events
+    pl = rows[..., 7]
+    ok = cnt <= maxlen
+    d = np.diff(pl, axis=1)
+    pair_valid = valid[:, 1:] & ok[:, None]
+    assert (d[pair_valid] >= 0).all()
+    # packets that did not overflow end on a surface or by the lottery / rmax
+    last = rows[np.arange(n), np.maximum(nrec - 1, 0)]
+    # statistics against the oracle
+    desc = xo_oracle.describe(sim, 'mcml')
+    ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
+                        math=xo_oracle.MATH_LIBM)
+    rcnt = ref['ints'][co:co + n]
+    rrows = ref['floats'][do:do + n*maxlen*8].reshape(n, maxlen, 8)
+    rlast = rrows[np.arange(n), np.maximum(np.minimum(rcnt, maxlen) - 1, 0)]
+
+    def close(a, b, what):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        se = np.sqrt(a.var()/max(a.size, 1) + b.var()/max(b.size, 1))
+        assert abs(a.mean() - b.mean()) <= 5*se + 1e-12, (what, a.mean(), b.mean(), se)
+
+    close(cnt, rcnt, 'events per packet')
+    close((cnt >= maxlen), (rcnt >= maxlen), 'overflow fraction')
+    for col, what in ((2, 'z'), (6, 'w'), (7, 'pl')):
+        close(last[ok, col], rlast[rcnt <= maxlen, col], 'terminal ' + what)
+    # interior events too: mean depth of the k-th event
+    for k in (1, 2, 3, 4, 5, 7):
+        if k < maxlen - 1:
+            close(rows[cnt > k, k, 2], rrows[rcnt > k, k, 2], 'z of event %d' % k)
+
+
 def test_run_returns_reference_style_results():
     sim, _, mc = build_sim('mcml_c1_slab')
     trace, fluence, detectors = sim.run(100000)
