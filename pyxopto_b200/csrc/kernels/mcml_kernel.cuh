@@ -61,13 +61,17 @@ struct MlLayer {                    // mcml/mclayer/layer.py:57-69
 // is staged in shared memory.  `hot`, `pf` (+ `aux`) are exactly the register
 // cache of the current layer, 16-byte aligned so a layer change reloads them
 // with a few LDS.128; `iface` holds what the interface physics needs.
-struct __align__(16) MlHot { float top, bottom, step_k, absorb; };
-	// step_k = -ln2/mut (AW, AR) or -ln2/mus (MBL): step = lg2(u)*step_k
+struct __align__(16) MlHot { float top, bottom, step_k, step_b; };
+	// step_k = -ln2/mut (AW, AR) or -ln2/mus (MBL), step_b = -32 step_k:
+	// step = lg2(raw draw)*step_k + step_b = -ln(u)/mut
+struct __align__(16) MlAbs { float absorb, survive, dep_k, mua; };
+	// absorb = mua/mut, survive = 1 - absorb, dep_k = absorb x (weight -> fixed
+	// point factor of the fluence plugin): AW deposits f2u(w*dep_k + 0.5)
 struct __align__(16) MlIface { float n12_top, cc_top, n12_bottom, cc_bottom; };
 	// n12 = n/n(neighbour), exactly 1 when the indices are equal
-struct __align__(16) MlAux { float mua, n, pad0, pad1; };
+struct __align__(16) MlAux { float n, pad0, pad1, pad2; };
 struct __align__(16) MlPfFast { XoPf::Fast v; };
-struct MlFastLayer { MlHot hot; MlPfFast pf; MlAux aux; MlIface iface; };
+struct MlFastLayer { MlHot hot; MlAbs abs; MlPfFast pf; MlAux aux; MlIface iface; };
 
 typedef Detectors<XoDetTop, XoDetBottom, XoDetSpecular> XoDetectors;
 typedef SurfaceLayouts<XoSurfTop, XoSurfBottom> XoSurface;
@@ -211,13 +215,17 @@ McKernel(
 	for (u32 i = threadIdx.x; i < num_layers; i += blockDim.x) {
 		const MlLayer &Lg = layers[i];
 		MlFastLayer F;
-		F.hot.top = Lg.top; F.hot.bottom = Lg.bottom; F.hot.absorb = Lg.mua_inv_mut;
+		F.hot.top = Lg.top; F.hot.bottom = Lg.bottom;
 #if XO_METHOD == 2
 		F.hot.step_k = -0.6931471805599453f/Lg.mus;
 #else
 		F.hot.step_k = -0.6931471805599453f*Lg.inv_mut;
 #endif
-		F.aux.mua = Lg.mua; F.aux.n = Lg.n; F.aux.pad0 = 0.0f; F.aux.pad1 = 0.0f;
+		F.hot.step_b = -32.0f*F.hot.step_k;
+		F.abs.absorb = Lg.mua_inv_mut; F.abs.survive = 1.0f - Lg.mua_inv_mut;
+		F.abs.dep_k = Lg.mua_inv_mut*fluence.fixed_scale(Lg.mua);
+		F.abs.mua = Lg.mua;
+		F.aux.n = Lg.n; F.aux.pad0 = 0.0f; F.aux.pad1 = 0.0f; F.aux.pad2 = 0.0f;
 		float n_up = (i > 0) ? layers[i - 1].n : Lg.n;
 		float n_dn = (i + 1 < num_layers) ? layers[i + 1].n : Lg.n;
 		F.iface.n12_top = (n_up == Lg.n) ? 1.0f : Lg.n/n_up;
@@ -257,6 +265,10 @@ McKernel(
 	float4 *stage = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) +
 		(threadIdx.x >> 5)*XO_STAGE_F4_PER_WARP;
 #endif
+	// constants of the fluence deposit, pinned in registers by a round trip through
+	// shared memory (XoFluence::Prep)
+	__shared__ typename XoFluence::Prep sh_flu_prep;
+	if (threadIdx.x == 0) sh_flu_prep = fluence.prepare(window);
 #endif
 	__syncthreads();
 
@@ -464,17 +476,22 @@ McKernel(
 	const u32 lane = threadIdx.x & 31u;
 	const u32 lanemask_lt = (1u << lane) - 1u;
 	u32 state = ST_DEAD;
-	u32 n_dry = 0, q_count = 0;     // warp-uniform
+	u32 q_count = 0;                // warp-uniform: packets parked in the warp's launch queue
 	bool q_dry = false;             // warp-uniform: the packet budget is exhausted
+	u32 thr_eff = refill < 1u ? 1u : (refill > 32u ? 32u : refill);   // waiting lanes that trigger a service round
+	(void)chunk;
 	// constants of the current layer (registers; reloaded on layer change)
 	MlHot c_hot = { 0.0f, 0.0f, 0.0f, 0.0f };
-	MlAux c_aux = { 0.0f, 1.0f, 0.0f, 0.0f };
+	MlAbs c_abs = { 0.0f, 1.0f, 0.0f, 0.0f };
+	MlAux c_aux = { 1.0f, 0.0f, 0.0f, 0.0f };
 	XoPf::Fast c_pf;
 	(void)c_aux;
+	const typename XoFluence::Prep flu_prep = sh_flu_prep;
+	(void)flu_prep;
 #define XO_LOAD_LAYER(idx) do { \
 		const MlFastLayer &F_ = sh_fast[idx]; \
-		c_hot = F_.hot; c_pf = F_.pf.v; \
-		if (XO_NEEDS_OPL || XO_METHOD != 0 || XO_FLUENCE_RATE) c_aux = F_.aux; \
+		c_hot = F_.hot; c_abs = F_.abs; c_pf = F_.pf.v; \
+		if (XO_NEEDS_OPL) c_aux = F_.aux; \
 	} while (0)
 #define XO_END_TRIP() do { \
 		XO_RMAX_TEST(); \
@@ -520,70 +537,17 @@ McKernel(
 			__syncwarp();
 		}
 #endif
-		// ---- hand new packets to the lanes that need one -------------------------
-		// (a lane that ran out of packets waits until `chunk` lanes need one, or
-		// nothing else is running: popping for one lane at a time would run the
-		// pop path at 1-2 lanes per warp)
-		const u32 dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
-		if (dead_mask != 0u && ((u32)__popc(dead_mask) >= chunk ||
-				__ballot_sync(0xffffffffu, state == ST_RUN) == 0u)) {
-			if (q_count == 0u && !q_dry) {
-				// queue empty: all 32 lanes launch one packet each into the queue
-				u32 base = 0;
-				if (lane == 0u) base = atomicAdd(num_packets_done, 32u);
-				base = __shfl_sync(0xffffffffu, base, 0);
-				const u32 n_new = base < num_packets ?
-					(num_packets - base < 32u ? num_packets - base : 32u) : 0u;
-				q_dry = n_new < 32u;
-				if (lane < n_new) {
-					Launch L_;
-					source.launch(rng, ctx, L_);
-					if (XoDetSpecular::active)
-						detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
-					u32 tc = 0;
-					if (XO_TRACE & XO_TRACE_START) {
-						if (trace_event(tcfg, float_buffer, base + lane, 0u, EV_LAUNCH,
-								L_.pos, L_.dir, L_.weight, 0.0f)) tc = 1u;
-					}
-					q_a[lane] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
-					q_b[lane] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, __uint_as_float(base + lane));
-					q_l[lane] = (u32)L_.layer | (tc << 16);
-				}
-				__syncwarp();
-				q_count = n_new;
-			}
-			if (state == ST_DEAD) {
-				const u32 rank = (u32)__popc(dead_mask & lanemask_lt);
-				if (rank < q_count) {
-					const u32 slot = q_count - 1u - rank;
-					const float4 a = q_a[slot], b = q_b[slot];
-					const u32 l = q_l[slot];
-					pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
-					dir.x = b.x; dir.y = b.y; dir.z = b.z; packet = __float_as_uint(b.w);
-					layer = (i32)(l & 0xffffu); trace_count = l >> 16;
-					XO_LOAD_LAYER(layer);
-					opl = 0.0f;
-					flags = EV_LAUNCH;
-					state = ST_RUN;
-					started = true;
-				} else if (q_dry) {
-					state = ST_DRY;
-				}
-			}
-			const u32 n_dead = (u32)__popc(dead_mask);
-			q_count -= (n_dead < q_count) ? n_dead : q_count;
-			__syncwarp();
-			if (q_dry) {
-				n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
-				if (n_dry == 32u) break;
-			}
-		}
-		// ---- interface physics, executed jointly by the lanes waiting for it ------
-		const u32 bnd_mask = __ballot_sync(0xffffffffu, state - 1u < 2u);
-		if (bnd_mask != 0u) {
-			bool go = (u32)__popc(bnd_mask) >= refill;
-			if (!go) go = __ballot_sync(0xffffffffu, state == ST_RUN) == 0u;
-			if (go && state - 1u < 2u) {
+		// ---- service round ------------------------------------------------------------
+		// One vote per trip.  Lanes waiting at an interface (BND_*) or for a new packet
+		// (DEAD) idle until `refill` lanes of the warp wait (or every lane that still
+		// has work waits); then the interface physics, the queue refill and the pops
+		// run jointly, in this order -- a packet that leaves the medium in the
+		// interface handler is replaced in the same round.  The rare, long paths run
+		// with several lanes instead of 1-2, and the common trip pays one VOTE.
+		const u32 wait_mask = __ballot_sync(0xffffffffu, state - 1u < 3u);
+		if (__builtin_expect((u32)__popc(wait_mask) >= thr_eff, 0)) {
+			// ---- interface physics ----------------------------------------------------
+			if (state - 1u < 2u) {
 				const bool up = (state == ST_BND_TOP);
 				bool done = false;
 #if XO_METHOD != 2
@@ -632,6 +596,66 @@ McKernel(
 #endif
 				XO_END_TRIP();
 			}
+			// ---- new packets for the lanes that need one -----------------------------------
+			u32 dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
+			while (dead_mask != 0u) {
+				if (q_count == 0u) {
+					if (q_dry) break;
+					// queue empty: all 32 lanes launch one packet each into the queue
+					u32 base = 0;
+					if (lane == 0u) base = atomicAdd(num_packets_done, 32u);
+					base = __shfl_sync(0xffffffffu, base, 0);
+					const u32 n_new = base < num_packets ?
+						(num_packets - base < 32u ? num_packets - base : 32u) : 0u;
+					q_dry = n_new < 32u;
+					if (lane < n_new) {
+						Launch L_;
+						source.launch(rng, ctx, L_);
+						if (XoDetSpecular::active)
+							detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
+						u32 tc = 0;
+						if (XO_TRACE & XO_TRACE_START) {
+							if (trace_event(tcfg, float_buffer, base + lane, 0u, EV_LAUNCH,
+									L_.pos, L_.dir, L_.weight, 0.0f)) tc = 1u;
+						}
+						q_a[lane] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
+						q_b[lane] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, __uint_as_float(base + lane));
+						q_l[lane] = (u32)L_.layer | (tc << 16);
+					}
+					__syncwarp();
+					q_count = n_new;
+					if (n_new == 0u) break;
+				}
+				if (state == ST_DEAD) {
+					const u32 rank = (u32)__popc(dead_mask & lanemask_lt);
+					if (rank < q_count) {
+						const u32 slot = q_count - 1u - rank;
+						const float4 a = q_a[slot], b = q_b[slot];
+						const u32 l = q_l[slot];
+						pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
+						dir.x = b.x; dir.y = b.y; dir.z = b.z; packet = __float_as_uint(b.w);
+						layer = (i32)(l & 0xffffu); trace_count = l >> 16;
+						XO_LOAD_LAYER(layer);
+						opl = 0.0f;
+						flags = EV_LAUNCH;
+						state = ST_RUN;
+						started = true;
+					}
+				}
+				__syncwarp();
+				const u32 n_dead = (u32)__popc(dead_mask);
+				if (n_dead <= q_count) { q_count -= n_dead; break; }
+				// the queue ran out before every waiting lane had a packet: refill, go on
+				q_count = 0u;
+				dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
+			}
+			if (q_dry && q_count == 0u) {
+				// packet budget exhausted: the lanes still waiting for a packet retire
+				if (state == ST_DEAD) state = ST_DRY;
+				const u32 n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
+				if (n_dry == 32u) break;
+				thr_eff = refill < 32u - n_dry ? refill : 32u - n_dry;
+			}
 		}
 #if XO_TRACE && XO_TRACE_STAGED
 		// a completed trace line is flushed (loop top) before the lane records again
@@ -641,7 +665,7 @@ McKernel(
 
 		// ---- one step of the packet ----------------------------------------------------
 		++iterations;
-		float step = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
+		float step = fminf(fmaf(FastMath::lg2(rng.next_raw()), c_hot.step_k, c_hot.step_b), XO_FLT_MAX);
 		const float zs = fmaf(step, dir.z, pos.z);
 		const bool hit_top = zs < c_hot.top;
 		const bool hit = hit_top || zs >= c_hot.bottom;
@@ -657,15 +681,15 @@ McKernel(
 		pos.y = fmaf(dir.y, step, pos.y);
 		if (XO_NEEDS_OPL) opl = fmaf(c_aux.n, step, opl);
 		{
-			float frac = 1.0f - FastMath::exp(-c_aux.mua*step);
+			float frac = 1.0f - FastMath::exp(-c_abs.mua*step);
 			float deposit = frac*weight;
 			weight -= deposit;
 			flags |= EV_ABSORPTION;
 			if (XoFluence::active) {
-				float back = (c_aux.mua != 0.0f) ?
-					step + FastMath::log(1.0f - rng.next()*frac)*FastMath::rcp_approx(c_aux.mua) : 0.0f;
+				float back = (c_abs.mua != 0.0f) ?
+					step + FastMath::log(1.0f - rng.next()*frac)*FastMath::rcp_approx(c_abs.mua) : 0.0f;
 				P3 dp = { pos.x - back*dir.x, pos.y - back*dir.y, pos.z - back*dir.z };
-				fluence.deposit(acc, window, dp, deposit, c_aux.mua, opl);
+				fluence.deposit(acc, window, dp, deposit, c_abs.mua, opl);
 			}
 		}
 		if (hit) {
@@ -686,12 +710,12 @@ McKernel(
 #endif
 		bool done = false;
 #if XO_METHOD == 1
-		if (rng.next() < c_hot.absorb) {
+		if (rng.next() < c_abs.absorb) {
 			float deposit = weight;
 			done = true;
 			weight = 0.0f;
 			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_aux.mua, opl);
+			if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_abs.mua, opl);
 		} else {
 			float fi, ct = c_pf.sample(rng, lut, &fi);
 			scatter_direction(dir, ct, fi);
@@ -699,11 +723,11 @@ McKernel(
 		}
 #else
 #if XO_METHOD == 0
-		{
-			float deposit = weight*c_hot.absorb;
-			weight -= deposit;
+		{   // albedo weight: the deposit leaves as fixed point in one FFMA + F2I
+			const u32 wfix = f2u(fmaf(weight, c_abs.dep_k, 0.5f));
+			weight *= c_abs.survive;
 			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_aux.mua, opl);
+			if (XoFluence::active) fluence.deposit_prep(acc, flu_prep, window, pos, wfix, opl);
 		}
 #endif
 		float fi, ct = c_pf.sample(rng, lut, &fi);

@@ -259,7 +259,13 @@ struct Accu {
 	u32 priv_len;
 	u32 *win;         // shared memory, ext0*ext1*ext2 words (0 extents: no window)
 	u32 priv_s, win_s;  // shared-space addresses of priv / win (set by bind())
-	__device__ __forceinline__ void bind() { priv_s = shared_address(priv); win_s = shared_address(win); }
+	// (the empty asm keeps both addresses in registers: the compiler otherwise
+	// rematerialises them from SR_CgaCtaId and the kernel parameters before every
+	// atomic, 7 instructions per deposit)
+	__device__ __forceinline__ void bind() {
+		priv_s = shared_address(priv); win_s = shared_address(win);
+		asm volatile("" : "+r"(priv_s), "+r"(win_s));
+	}
 	// returns true when the 32-bit partial sum wrapped around (the caller then
 	// forwards 2^32 to the global bin with carry_global)
 	__device__ __forceinline__ bool add_window(u32 local, u32 w) const {

@@ -14,6 +14,11 @@ struct FluNone {
 	static constexpr bool active = false;
 	static constexpr bool needs_opl = false;
 	__device__ __forceinline__ void deposit(const Accu &, const FluWindow &, const P3 &, float, float, float) const {}
+	__device__ __forceinline__ void deposit_fixed(const Accu &, const FluWindow &, const P3 &, u32, float) const {}
+	__device__ __forceinline__ float fixed_scale(float) const { return 0.0f; }
+	struct Prep { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ void deposit_prep(const Accu &, const Prep &, const FluWindow &, const P3 &, u32, float) const {}
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 };
 
@@ -48,6 +53,18 @@ __device__ __forceinline__ u32 fluence_weight(float w, float mua, i32 k) {
 #endif
 }
 
+// weight -> fixed point factor of a layer / material (throughput loops):
+// fluence_weight(w, mua, k) == f2u(fmaf(w, fluence_scale(mua, k), 0.5f)) up to the
+// rounding of the product
+__device__ __forceinline__ float fluence_scale(float mua, i32 k) {
+#if XO_FLUENCE_RATE
+	return (mua != 0.0f) ? (float)k/mua : 0.0f;
+#else
+	(void)mua;
+	return (float)k;
+#endif
+}
+
 struct FluXyz {                     // mcfluence/fluence.py:57-63
 	P3 inv_step, top_left; u32 nx, ny, nz, offset; i32 k;
 	static constexpr bool active = true;
@@ -56,17 +73,28 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 	// (fluence.py:103-143).  floor-conversion + one unsigned compare per axis is
 	// the same predicate for every non-NaN f: negative f floors to a negative
 	// integer (huge as unsigned), f >= n converts to >= n or saturates.
-	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float) const {
+	struct Prep { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
+		deposit_fixed(acc, win, pos, wfix, opl);
+	}
+	// deposit of a weight that is already in fixed point (throughput loops fold
+	// the conversion constant into their per-layer constants, see fixed_scale)
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float opl) const {
+		deposit_fixed(acc, win, pos, fluence_weight(w, mua, k), opl);
+	}
+	__device__ __forceinline__ float fixed_scale(float mua) const { return fluence_scale(mua, k); }
+	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &win, const P3 &pos, u32 wfix, float) const {
 		u32 ix = (u32)__float2int_rd((pos.x - top_left.x)*inv_step.x);
 		u32 iy = (u32)__float2int_rd((pos.y - top_left.y)*inv_step.y);
 		u32 iz = (u32)__float2int_rd((pos.z - top_left.z)*inv_step.z);
 		u32 lx = ix - win.org0, ly = iy - win.org1, lz = iz - win.org2;
 		// the window lies inside the grid: a hit there needs no grid bounds test
 		if (XO_FLU_WINDOW && lx < win.ext0 && ly < win.ext1 && lz < win.ext2) {
-			if (acc.add_window((lz*win.ext1 + ly)*win.ext0 + lx, fluence_weight(w, mua, k)))
+			if (acc.add_window((lz*win.ext1 + ly)*win.ext0 + lx, wfix))
 				acc.carry_global(offset + (iz*ny + iy)*nx + ix);
 		} else if (ix < nx && iy < ny && iz < nz) {
-			acc.add_global(offset + (iz*ny + iy)*nx + ix, fluence_weight(w, mua, k));
+			acc.add_global(offset + (iz*ny + iy)*nx + ix, wfix);
 		}
 	}
 	__device__ __forceinline__ u32 window_index(const FluWindow &win, u32 local) const {
@@ -81,7 +109,42 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
 	// bounds test in the integer domain, see FluXyz::deposit (fluencerz.py:112-160)
-	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float) const {
+	// Throughput loops: the grid constants in the form the deposit uses them, held
+	// in registers for the whole kernel (the kernel passes them through shared
+	// memory once; read from the kernel parameters the loop reloads five uniform
+	// registers from the constant bank per deposit).  The window origin is folded
+	// into the index offsets: l = floor(x*inv_d + b) is the window-local index,
+	// floor(f - n) == floor(f) - n for the integer n.
+	struct Prep { float cx, cy, inv_dr, br, inv_dz, bz; u32 ext0, ext1; };
+	__device__ __forceinline__ Prep prepare(const FluWindow &win) const {
+		Prep p;
+		p.cx = center.x; p.cy = center.y; p.inv_dr = inv_dr; p.inv_dz = inv_dz;
+		p.br = -(float)win.org0;
+		p.bz = -center.z*inv_dz - (float)win.org1;
+		p.ext0 = win.ext0; p.ext1 = win.ext1;
+		return p;
+	}
+	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &p, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
+		if (!XO_FLU_WINDOW) { deposit_fixed(acc, win, pos, wfix, opl); return; }
+		float dx = pos.x - p.cx, dy = pos.y - p.cy;
+		float r = FastMath::sqrt(fmaf(dx, dx, dy*dy));
+		u32 lr = (u32)__float2int_rd(fmaf(r, p.inv_dr, p.br));
+		u32 lz = (u32)__float2int_rd(fmaf(pos.z, p.inv_dz, p.bz));
+		if (lr < p.ext0 && lz < p.ext1) {
+			if (acc.add_window(lz*p.ext0 + lr, wfix))
+				acc.carry_global(offset + (lz + win.org1)*n_r + lr + win.org0);
+		} else {
+			u32 ir = lr + win.org0, iz = lz + win.org1;
+			if (ir < n_r && iz < n_z) acc.add_global(offset + iz*n_r + ir, wfix);
+		}
+	}
+	// deposit of a weight that is already in fixed point (throughput loops fold
+	// the conversion constant into their per-layer constants, see fixed_scale)
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float opl) const {
+		deposit_fixed(acc, win, pos, fluence_weight(w, mua, k), opl);
+	}
+	__device__ __forceinline__ float fixed_scale(float mua) const { return fluence_scale(mua, k); }
+	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &win, const P3 &pos, u32 wfix, float) const {
 		float dx = pos.x - center.x, dy = pos.y - center.y;
 		float r = M::sqrt(dx*dx + dy*dy);
 		float dz = pos.z - center.z;
@@ -89,10 +152,10 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 		u32 lr = ir - win.org0, lz = iz - win.org1;
 		// the window lies inside the grid: a hit there needs no grid bounds test
 		if (XO_FLU_WINDOW && lr < win.ext0 && lz < win.ext1) {
-			if (acc.add_window(lz*win.ext0 + lr, fluence_weight(w, mua, k)))
+			if (acc.add_window(lz*win.ext0 + lr, wfix))
 				acc.carry_global(offset + iz*n_r + ir);
 		} else if (ir < n_r && iz < n_z) {
-			acc.add_global(offset + iz*n_r + ir, fluence_weight(w, mua, k));
+			acc.add_global(offset + iz*n_r + ir, wfix);
 		}
 	}
 	__device__ __forceinline__ u32 window_index(const FluWindow &win, u32 local) const {
@@ -106,7 +169,18 @@ struct FluXyzt {                    // mcfluence/fluencet.py:57-63
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
-	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float opl) const {
+	struct Prep { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
+		deposit_fixed(acc, win, pos, wfix, opl);
+	}
+	// deposit of a weight that is already in fixed point (throughput loops fold
+	// the conversion constant into their per-layer constants, see fixed_scale)
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float opl) const {
+		deposit_fixed(acc, win, pos, fluence_weight(w, mua, k), opl);
+	}
+	__device__ __forceinline__ float fixed_scale(float mua) const { return fluence_scale(mua, k); }
+	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &, const P3 &pos, u32 wfix, float opl) const {
 		float fx = (pos.x - top_left[0])*inv_step[0];
 		float fy = (pos.y - top_left[1])*inv_step[1];
 		float fz = (pos.z - top_left[2])*inv_step[2];
@@ -115,7 +189,7 @@ struct FluXyzt {                    // mcfluence/fluencet.py:57-63
 				fx < (float)shape[0] && fy < (float)shape[1] &&
 				fz < (float)shape[2] && ft < (float)shape[3]) {
 			u32 index = ((f2u(fz)*shape[1] + f2u(fy))*shape[0] + f2u(fx))*shape[3] + f2u(ft);
-			acc.add_global(offset + index, fluence_weight(w, mua, k));
+			acc.add_global(offset + index, wfix);
 		}
 	}
 };
@@ -125,7 +199,18 @@ struct FluRzt {                     // mcfluence/fluencerzt.py:54-66
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
-	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float opl) const {
+	struct Prep { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
+		deposit_fixed(acc, win, pos, wfix, opl);
+	}
+	// deposit of a weight that is already in fixed point (throughput loops fold
+	// the conversion constant into their per-layer constants, see fixed_scale)
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float opl) const {
+		deposit_fixed(acc, win, pos, fluence_weight(w, mua, k), opl);
+	}
+	__device__ __forceinline__ float fixed_scale(float mua) const { return fluence_scale(mua, k); }
+	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &, const P3 &pos, u32 wfix, float opl) const {
 		float dx = pos.x - center.x, dy = pos.y - center.y;
 		float r = M::sqrt(dx*dx + dy*dy);
 		float dz = pos.z - center.z;
@@ -134,7 +219,7 @@ struct FluRzt {                     // mcfluence/fluencerzt.py:54-66
 		if (fr >= 0.0f && fz >= 0.0f && ft >= 0.0f &&
 				fr < (float)n_r && fz < (float)n_z && ft < (float)n_t) {
 			u32 index = (f2u(fz)*n_r + f2u(fr))*n_t + f2u(ft);
-			acc.add_global(offset + index, fluence_weight(w, mua, k));
+			acc.add_global(offset + index, wfix);
 		}
 	}
 };
@@ -145,7 +230,18 @@ struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
-	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float) const {
+	struct Prep { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
+		deposit_fixed(acc, win, pos, wfix, opl);
+	}
+	// deposit of a weight that is already in fixed point (throughput loops fold
+	// the conversion constant into their per-layer constants, see fixed_scale)
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float opl) const {
+		deposit_fixed(acc, win, pos, fluence_weight(w, mua, k), opl);
+	}
+	__device__ __forceinline__ float fixed_scale(float mua) const { return fluence_scale(mua, k); }
+	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &, const P3 &pos, u32 wfix, float) const {
 		float dx = pos.x - center.x, dy = pos.y - center.y;
 		float r = M::sqrt(dx*dx + dy*dy);
 		float fi = M::atan2(dy, dx) + 3.141592653589793f;
@@ -153,7 +249,7 @@ struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
 		if (fr >= 0.0f && fz >= 0.0f && ffi >= 0.0f &&
 				fr < (float)n_r && fz < (float)n_z && ffi < (float)n_fi) {
 			u32 index = (f2u(fz)*n_fi + f2u(ffi))*n_r + f2u(fr);
-			acc.add_global(offset + index, fluence_weight(w, mua, k));
+			acc.add_global(offset + index, wfix);
 		}
 	}
 };

@@ -15,6 +15,12 @@
 #pragma once
 #include "xo_core.cuh"
 
+// 0: the host found no scattering layer / material with g == 0, the isotropic
+// special case of Hg / MHg (one extra draw) is compiled out of the throughput loop
+#ifndef XO_PF_G0
+#define XO_PF_G0 1
+#endif
+
 namespace xo {
 
 // Henyey-Greenstein polar cosine from the prepared constants:
@@ -39,7 +45,7 @@ struct HgFast {
 	__device__ __forceinline__ float polar(float f, Rng &rng, bool wanted = true) const {
 		float q = FastMath::rcp_approx(fmaf(f, d1, d0));
 		float ct = fmaf(-(B*q), q, A);
-		if (d1 == 0.0f && wanted) ct = fmaf(rng.next_raw(), -2.0f*2.3283064365386963e-10f, 1.0f);
+		if (XO_PF_G0 && d1 == 0.0f && wanted) ct = fmaf(rng.next_raw(), -2.0f*2.3283064365386963e-10f, 1.0f);
 		return ct;
 	}
 };

@@ -190,6 +190,7 @@ class McBase(CuWorker):
             '#define XO_TRACE_STAGED {}'.format(int(self._trace_staged(opts))),
             '#define XO_USE_RMAX {}'.format(int(self._rmax_needed())),
             '#define XO_FLU_WINDOW {}'.format(int(self._window_enabled())),
+            '#define XO_PF_G0 {}'.format(int(self._pf_isotropic_possible())),
             '#define XO_BLOCK {}'.format(int(block)),
             '#define XO_MIN_BLOCKS {}'.format(int(min_blocks)),
         ]
@@ -212,6 +213,28 @@ class McBase(CuWorker):
     def _extra_defines(self, opts):
         return []
 
+    def _scattering_pfs(self):
+        """Phase functions of the layers / materials a packet can scatter in."""
+        return None
+
+    def _pf_isotropic_possible(self) -> bool:
+        """False when every scattering phase function has a packed anisotropy
+        ``g != 0``: the kernel then drops the isotropic special case of Hg / MHg
+        (hg.py:74-90 draws a third number when g == 0)."""
+        pfs = self._scattering_pfs()
+        if not pfs:
+            return True
+        for pf in pfs:
+            g = getattr(pf, 'g', None)
+            if g is None:
+                return True
+            try:
+                if float(np.float32(g)) == 0.0:
+                    return True
+            except (TypeError, ValueError):
+                return True
+        return False
+
     def _rmax_needed(self) -> bool:
         """False when the rmax test can never fire (compiled out of the loop)."""
         return bool(np.isfinite(np.float32(self._rmax)))
@@ -219,13 +242,14 @@ class McBase(CuWorker):
     # idle lanes per warp that trigger a joint launch (throughput mode); sources
     # with a long launch path amortise it over more lanes
     refill_lanes = None
+    default_refill_lanes = 1
     min_blocks = 1                   # __launch_bounds__ second argument
     chunk_max = 16
 
     def _refill_lanes(self) -> int:
         if self.refill_lanes is not None:
             return int(min(max(self.refill_lanes, 1), 32))
-        return int(getattr(self._source, 'cu_refill_lanes', 1))
+        return int(getattr(self._source, 'cu_refill_lanes', self.default_refill_lanes))
 
     def _extra_includes(self):
         return []

@@ -49,6 +49,9 @@ class Mc(McBase):
         return self._layers.layer_index(r)
 
     # -- packing -----------------------------------------------------------------
+    def _scattering_pfs(self):
+        return [item.pf for item in list(self._layers)[1:]]
+
     def _pack_medium(self):
         if type(self._layers[1].pf) is not self._obj_types['pf']:
             raise ValueError('The scattering phase function kind/type must not '

@@ -24,6 +24,9 @@ class Mc(McBase):
     supports_surface_layouts = True
     kernel_header = 'mcml_kernel.cuh'
     geometry = 'mcml'
+    # waiting lanes per warp that trigger a service round (measured optimum 2-4
+    # for short-launch sources on slabs: C1 9.9e8 packets/s at 3)
+    default_refill_lanes = 3
 
     def __init__(self, layers, source, detectors=None, trace=None, fluence=None,
                  surface=None, types=mctypes.McDataTypesSingle, options=None,
@@ -48,6 +51,9 @@ class Mc(McBase):
         return self._layers.layer_index(z)
 
     # -- packing -----------------------------------------------------------------
+    def _scattering_pfs(self):
+        return [item.pf for item in list(self._layers)[1:-1]]
+
     def _pack_medium(self):
         if type(self._layers[1].pf) is not self._obj_types['pf']:
             raise ValueError('The scattering phase function kind/type must not '

@@ -234,7 +234,7 @@ class UniformBeam(Source):
 class UniformFiber(Source):
     """Optical fiber with uniform emission within the NA (mcsource/fiber.py)."""
     cu_type = 'xo::SrcUniformFiber'
-    cu_refill_lanes = 6     # long launch path: launch jointly (mcsim._refill_lanes)
+    cu_refill_lanes = 8     # waiting lanes that trigger a service round (mcsim._refill_lanes)
     _update_keys = ('fiber', 'position', 'direction')
 
     @staticmethod

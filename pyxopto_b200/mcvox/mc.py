@@ -62,6 +62,9 @@ class Mc(McBase):
         return self._materials[material_index]
 
     # -- packing -----------------------------------------------------------------
+    def _scattering_pfs(self):
+        return [item.pf for item in list(self._materials)]
+
     def _pack_medium(self):
         if type(self._materials[0].pf) is not self._obj_types['pf']:
             raise ValueError('The scattering phase function kind/type must not '
