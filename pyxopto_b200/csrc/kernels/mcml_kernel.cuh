@@ -248,13 +248,16 @@ McKernel(
 	acc.priv = reinterpret_cast<u32 *>(xo_smem) + off_words;
 	acc.priv_len = priv_len;
 	acc.zero_private();
-	acc.win = acc.priv + 2*priv_len;
+	// 16 bytes in front of the window hold the constants of the deposits that
+	// miss it (XoFluence::Far, one LDS.128 relative to the window address)
+	const u32 far_words = (off_words + 2u*priv_len + 3u) & ~3u;
+	acc.win = reinterpret_cast<u32 *>(xo_smem) + far_words + 4u;
 	acc.bind();
 	const u32 win_len = window.ext0*window.ext1*window.ext2;
 	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
 #if !XO_DETERMINISTIC
 	// per-warp launch queue: 32 slots of {pos, weight | dir, packet | layer, trace count}
-	off_words += 2*priv_len + win_len;
+	off_words = far_words + 4u + win_len;
 	off_words = (off_words + 3u) & ~3u;
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;
@@ -268,7 +271,11 @@ McKernel(
 	// constants of the fluence deposit, pinned in registers by a round trip through
 	// shared memory (XoFluence::Prep)
 	__shared__ typename XoFluence::Prep sh_flu_prep;
-	if (threadIdx.x == 0) sh_flu_prep = fluence.prepare(window);
+	if (threadIdx.x == 0) {
+		sh_flu_prep = fluence.prepare(window);
+		if (sizeof(typename XoFluence::Far) == 16)
+			*reinterpret_cast<typename XoFluence::Far *>(acc.win - 4) = fluence.prepare_far(window);
+	}
 #endif
 	__syncthreads();
 

@@ -272,6 +272,13 @@ struct Accu {
 		u32 old = atoms_add(win_s + 4u*local, w);
 		return old + w < old;
 	}
+	// the 16 bytes in front of the window (constants of the deposits that miss it)
+	__device__ __forceinline__ uint4 load_far() const {
+		uint4 q;
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+-16];"
+			: "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(win_s));
+		return q;
+	}
 	__device__ __forceinline__ void carry_global(u32 index) const {
 		atomicAdd(global + index, 1ull << 32);
 	}

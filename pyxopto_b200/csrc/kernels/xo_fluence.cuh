@@ -17,7 +17,9 @@ struct FluNone {
 	__device__ __forceinline__ void deposit_fixed(const Accu &, const FluWindow &, const P3 &, u32, float) const {}
 	__device__ __forceinline__ float fixed_scale(float) const { return 0.0f; }
 	struct Prep { };
+	struct Far { };
 	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
 	__device__ __forceinline__ void deposit_prep(const Accu &, const Prep &, const FluWindow &, const P3 &, u32, float) const {}
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 };
@@ -74,7 +76,9 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 	// the same predicate for every non-NaN f: negative f floors to a negative
 	// integer (huge as unsigned), f >= n converts to >= n or saturates.
 	struct Prep { };
+	struct Far { };
 	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
 	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
 		deposit_fixed(acc, win, pos, wfix, opl);
 	}
@@ -116,6 +120,10 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 	// into the index offsets: l = floor(x*inv_d + b) is the window-local index,
 	// floor(f - n) == floor(f) - n for the integer n.
 	struct Prep { float cx, cy, inv_dr, br, inv_dz, bz; u32 ext0, ext1; };
+	// constants of the (rare, divergent) deposit outside the window, read from
+	// shared memory with one LDS.128 (16 bytes in front of the window): grid cells left of / below the window
+	// origin, row length, flat index of the window origin
+	struct __align__(16) Far { u32 rem0, rem1, n_r, base; };
 	__device__ __forceinline__ Prep prepare(const FluWindow &win) const {
 		Prep p;
 		p.cx = center.x; p.cy = center.y; p.inv_dr = inv_dr; p.inv_dz = inv_dz;
@@ -123,6 +131,12 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 		p.bz = -center.z*inv_dz - (float)win.org1;
 		p.ext0 = win.ext0; p.ext1 = win.ext1;
 		return p;
+	}
+	__device__ __forceinline__ Far prepare_far(const FluWindow &win) const {
+		Far f;
+		f.rem0 = n_r - win.org0; f.rem1 = n_z - win.org1;
+		f.n_r = n_r; f.base = offset + win.org1*n_r + win.org0;
+		return f;
 	}
 	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &p, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
 		if (!XO_FLU_WINDOW) { deposit_fixed(acc, win, pos, wfix, opl); return; }
@@ -134,8 +148,9 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 			if (acc.add_window(lz*p.ext0 + lr, wfix))
 				acc.carry_global(offset + (lz + win.org1)*n_r + lr + win.org0);
 		} else {
-			u32 ir = lr + win.org0, iz = lz + win.org1;
-			if (ir < n_r && iz < n_z) acc.add_global(offset + iz*n_r + ir, wfix);
+			const uint4 q = acc.load_far();
+			Far f; f.rem0 = q.x; f.rem1 = q.y; f.n_r = q.z; f.base = q.w;
+			if (lr < f.rem0 && lz < f.rem1) acc.add_global(lz*f.n_r + lr + f.base, wfix);
 		}
 	}
 	// deposit of a weight that is already in fixed point (throughput loops fold
@@ -170,7 +185,9 @@ struct FluXyzt {                    // mcfluence/fluencet.py:57-63
 	static constexpr bool needs_opl = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
+	struct Far { };
 	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
 	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
 		deposit_fixed(acc, win, pos, wfix, opl);
 	}
@@ -200,7 +217,9 @@ struct FluRzt {                     // mcfluence/fluencerzt.py:54-66
 	static constexpr bool needs_opl = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
+	struct Far { };
 	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
 	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
 		deposit_fixed(acc, win, pos, wfix, opl);
 	}
@@ -231,7 +250,9 @@ struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
 	static constexpr bool needs_opl = false;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
+	struct Far { };
 	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
 	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
 		deposit_fixed(acc, win, pos, wfix, opl);
 	}

@@ -341,6 +341,7 @@ class McBase(CuWorker):
         if lut_len:
             words += (lut_len + 3) & ~3
         words += 2*priv_len
+        words = ((words + 3) & ~3) + 4      # 16 aligned bytes in front of the fluence window
         return words*4 + 16, lut_len, priv_len
 
     def _trace_tails_unread(self) -> bool:

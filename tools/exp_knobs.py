@@ -11,7 +11,7 @@ for spec in sys.argv[3].split(';'):
         k, v = kv.split('=')
         if k == 'wgsize': kw['wgsize'] = int(v)
         elif k.startswith('D'): sim._cl_build_options.append('-%s=%s' % (k, v))
-        else: setattr(sim, k, int(v))
+        else: setattr(sim, k, float(v) if '.' in v else int(v))
     sim.run(10000, download=False, **kw)
     best = 1e9
     for i in range(3):
