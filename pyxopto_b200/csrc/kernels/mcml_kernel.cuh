@@ -45,17 +45,13 @@
 #include "xo_fluence.cuh"
 #include "xo_surface.cuh"
 #include "mcml_sources.cuh"
+#include "mcml_layer.cuh"
 
 #ifndef XO_USE_RMAX
 #define XO_USE_RMAX 1
 #endif
 
 namespace xo {
-
-struct MlLayer {                    // mcml/mclayer/layer.py:57-69
-	float thickness, top, bottom, n, cc_top, cc_bottom, mus, mua, inv_mut, mua_inv_mut;
-	XoPf pf;
-};
 
 // Per-layer records of the throughput body, derived once per CTA when the medium
 // is staged in shared memory.  `hot`, `pf` (+ `aux`) are exactly the register
@@ -93,13 +89,6 @@ typedef TraceNone XoTrace;
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetTop::needs_opl || XoDetBottom::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
-
-struct MlCtx {
-	const MlLayer *layers;          // shared memory
-	static constexpr bool has_specular = XoDetSpecular::active;
-	__device__ __forceinline__ float layer_n(int i) const { return layers[i].n; }
-	__device__ __forceinline__ float layer_cc_bottom(int i) const { return layers[i].cc_bottom; }
-};
 
 // Fresnel / Snell at a layer interface (mcml.template.c:80-203), reference
 // operation order.  Returns the event flag and updates dir / layer index.  A
@@ -283,7 +272,7 @@ McKernel(
 	Rng rng;
 	rng.x = rng_state_x[gid];
 	rng.a = rng_state_a[gid];
-	MlCtx ctx; ctx.layers = sh_layers;
+	MlCtx ctx; ctx.layers = sh_layers; ctx.num_layers = (i32)num_layers;
 #if XO_USE_RMAX
 	const P3 src_pos = source.origin();
 	const float rmax2 = rmax*rmax;

@@ -1,0 +1,83 @@
+// xo_clcompat_glue.cuh -- bodies of the user-plugin adapters (xo_clcompat_slots.cuh).
+//
+// Included after the fragments' implementations: each adapter builds a McSim
+// facade around the kernel's register state, calls the user's function and copies
+// the results back.  Everything inlines; the facade never reaches memory.
+#pragma once
+#include "xo_clcompat_slots.cuh"
+
+namespace xo {
+
+__device__ __forceinline__ void clc_sim_init(McSim &sim, Rng *rng) {
+	sim.rng = rng;
+	sim.pf = nullptr; sim.source = nullptr;
+	sim.det_top = nullptr; sim.det_bottom = nullptr; sim.det_specular = nullptr;
+	sim.layers = nullptr; sim.num_layers = 0;
+	sim.fp_lut_array = nullptr;
+	sim.accumulator_buffer = nullptr;
+	sim.state.position = P3{ 0.0f, 0.0f, 0.0f };
+	sim.state.direction = P3{ 0.0f, 0.0f, 1.0f };
+	sim.state.weight = 1.0f;
+	sim.state.layer_index = 1;
+	sim.state.photon_index = 0;
+	sim.state.optical_pathlength = 0.0f;
+	sim.spec_dir = P3{ 0.0f, 0.0f, -1.0f };
+	sim.spec_weight = 0.0f;
+}
+
+#if XO_USER_PF
+__device__ __forceinline__ float PfUser::sample(Rng &rng, const float *lut, float *azimuth) const {
+	McSim sim;
+	clc_sim_init(sim, &rng);
+	sim.pf = &p;
+	sim.fp_lut_array = lut;
+	return mcsim_pf_sample_angles(&sim, azimuth);
+}
+#endif
+
+#if XO_USER_SOURCE
+template <class Ctx>
+__device__ __forceinline__ void SrcUser::launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+	McSim sim;
+	clc_sim_init(sim, &rng);
+	sim.source = &s;
+	sim.layers = ctx.layers;
+	sim.num_layers = ctx.num_layers;
+	mcsim_launch(&sim);
+	L.pos = sim.state.position;
+	L.dir = sim.state.direction;
+	L.weight = sim.state.weight;
+	L.layer = sim.state.layer_index;
+	L.spec_dir = sim.spec_dir;
+	L.spec_weight = sim.spec_weight;
+}
+#endif
+
+#define XO_CLC_DETECTOR_BODY(slot, fn) \
+	McSim sim; \
+	Rng none = { 0ull, 0u }; \
+	clc_sim_init(sim, &none); \
+	sim.slot = &d; \
+	sim.accumulator_buffer = acc.global; \
+	sim.state.position = pos; sim.state.direction = dir; \
+	sim.state.weight = w; sim.state.optical_pathlength = opl; \
+	mc_point3f_t pos_ = pos, dir_ = dir; \
+	fn(&sim, &pos_, &dir_, w);
+
+#if XO_USER_DET_TOP
+__device__ __forceinline__ void DetUserTop::deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+	XO_CLC_DETECTOR_BODY(det_top, mcsim_top_detector_deposit)
+}
+#endif
+#if XO_USER_DET_BOTTOM
+__device__ __forceinline__ void DetUserBottom::deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+	XO_CLC_DETECTOR_BODY(det_bottom, mcsim_bottom_detector_deposit)
+}
+#endif
+#if XO_USER_DET_SPECULAR
+__device__ __forceinline__ void DetUserSpecular::deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+	XO_CLC_DETECTOR_BODY(det_specular, mcsim_specular_detector_deposit)
+}
+#endif
+
+}  // namespace xo

@@ -1,0 +1,83 @@
+// xo_clcompat_slots.cuh -- plugin slots filled by user-written OpenCL-C fragments.
+//
+// Included after the fragments' declarations (`struct McPf {...}` etc.).  Each
+// adapter wraps the user's packed struct in the interface the CUDA kernels bind
+// their plugin slots to (xo_pf.cuh, mcml_sources.cuh, xo_detectors.cuh); the
+// method bodies follow in xo_clcompat_glue.cuh, after the fragments'
+// implementations.  XO_USER_* (0/1) are written by the host for the slots whose
+// plugin object carries `cl_implementation` text instead of a `cu_type`.
+#pragma once
+#include "xo_clcompat.cuh"
+#include "xo_pf.cuh"
+#include "xo_detectors.cuh"
+
+#ifndef XO_USER_PF
+#define XO_USER_PF 0
+#endif
+#ifndef XO_USER_SOURCE
+#define XO_USER_SOURCE 0
+#endif
+#ifndef XO_USER_DET_TOP
+#define XO_USER_DET_TOP 0
+#endif
+#ifndef XO_USER_DET_BOTTOM
+#define XO_USER_DET_BOTTOM 0
+#endif
+#ifndef XO_USER_DET_SPECULAR
+#define XO_USER_DET_SPECULAR 0
+#endif
+
+namespace xo {
+
+struct Launch;
+
+#if XO_USER_PF
+// scattering phase function: `inline mc_fp_t mcsim_pf_sample_angles(McSim *, mc_fp_t *azimuth)`
+struct PfUser {
+	McPf p;
+	static constexpr bool uses_lut = true;      // the pool is staged whenever the plugin appended a table
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const;
+	typedef PfPlainFast<PfUser> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+#endif
+
+#if XO_USER_SOURCE
+// packet source: `inline void mcsim_launch(McSim *)`; the struct must have a
+// `position` member (the origin of the rmax sphere, mcml.template.c:759)
+struct SrcUser {
+	McSource s;
+	__device__ __forceinline__ P3 origin() const { return s.position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const;
+};
+#endif
+
+// surface detectors: `inline void mcsim_<loc>_detector_deposit(McSim *,
+// mc_point3f_t const *pos, mc_point3f_t const *dir, mc_fp_t weight)`
+#if XO_USER_DET_TOP
+struct DetUserTop {
+	McTopDetector d;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;
+};
+#endif
+#if XO_USER_DET_BOTTOM
+struct DetUserBottom {
+	McBottomDetector d;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;
+};
+#endif
+#if XO_USER_DET_SPECULAR
+struct DetUserSpecular {
+	McSpecularDetector d;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;
+};
+#endif
+
+}  // namespace xo

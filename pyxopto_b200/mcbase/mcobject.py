@@ -5,7 +5,7 @@ compile-time options (``cl_options``) and - instead of the reference's OpenCL-C
 text (``cl_declaration`` / ``cl_implementation``) - the name of the hand-written
 CUDA struct that implements it in ``csrc/kernels`` (``cu_type``).  Objects that
 still carry OpenCL-C fragments (user plugins) are compiled through
-``cl_compat.cuh``.
+``csrc/kernels/xo_clcompat*.cuh`` (mcbase/mcsim.py `_user_fragments`).
 """
 
 

@@ -28,6 +28,16 @@ PRIVATE_BINS_MAX = 4096          # detector bins privatised per CTA (32 KB)
 LUT_SHARED_MAX_BYTES = 64*1024   # pf lookup tables staged in shared memory
 
 
+def _fragment(obj, attr, mc) -> str:
+    """OpenCL-C text of a plugin attribute that is a string or a callable(mc)."""
+    frag = getattr(obj, attr, None)
+    if frag is None:
+        return ''
+    if callable(frag):
+        frag = frag(mc)
+    return str(frag or '')
+
+
 def _c_float(v: float) -> str:
     v = float(np.float32(v))
     if np.isinf(v):
@@ -195,16 +205,46 @@ class McBase(CuWorker):
             '#define XO_MIN_BLOCKS {}'.format(int(min_blocks)),
         ]
         lines += self._extra_defines(opts)
+        bindings = self._plugin_bindings()
+        user = self._user_fragments(bindings)
+        if user:
+            # compile-time options as the macros OpenCL-C fragments test (#if MC_USE_...)
+            for key in sorted(opts):
+                if key.startswith('MC_') and isinstance(opts[key], (bool, int, np.integer)):
+                    lines.append('#define {} {}'.format(key, int(opts[key])))
+            lines += ['#define {} 1'.format(self._USER_ADAPTERS[name][1]) for name, _ in user]
         lines += ['#include "xo_core.cuh"', '#include "xo_pf.cuh"',
                   '#include "xo_detectors.cuh"', '#include "xo_fluence.cuh"']
         lines += self._extra_includes()
+        if user:
+            lines.append('#include "xo_clcompat.cuh"')
+            for name, obj in user:
+                lines.append('// ---- declarations of the user plugin bound to {} ({})'.format(
+                    name, type(obj).__name__))
+                lines.append(_fragment(obj, 'cl_declaration', self))
+            lines.append('#include "xo_clcompat_slots.cuh"')
         checks = []
-        for name, cu_type, cl_type in self._plugin_bindings():
+        user_names = {name for name, _ in user}
+        for name, cu_type, cl_type in bindings:
+            if name in user_names:
+                cu_type = self._USER_ADAPTERS[name][0]
             lines.append('typedef {} {};'.format(cu_type, name))
             if cl_type is not None:
                 checks.append('static_assert(sizeof({}) == {}, "{} layout differs from '
                               'the packed host struct");'.format(
                                   name, ctypes.sizeof(cl_type), name))
+        if user:
+            if self.clcompat_geometry_header:
+                lines.append('#include "{}"'.format(self.clcompat_geometry_header))
+            for name, obj in user:
+                lines.append('// ---- implementation of the user plugin bound to {}'.format(name))
+                if name == 'XoSource':
+                    # a launch only *requests* the specular deposit (xo_clcompat.cuh)
+                    lines.append('#define mcsim_specular_detector_deposit XO_CLC_SPECULAR_REQUEST')
+                lines.append(_fragment(obj, 'cl_implementation', self))
+                if name == 'XoSource':
+                    lines.append('#undef mcsim_specular_detector_deposit')
+            lines.append('#include "xo_clcompat_glue.cuh"')
         lines.append('#include "{}"'.format(self.kernel_header))
         lines += checks
         lines += self._extra_checks()
@@ -212,6 +252,42 @@ class McBase(CuWorker):
 
     def _extra_defines(self, opts):
         return []
+
+    # -- user-written plugins (OpenCL-C fragments, csrc/kernels/xo_clcompat*.cuh) --
+    # slot typedef -> (adapter struct, flag macro)
+    _USER_ADAPTERS = {
+        'XoPf': ('xo::PfUser', 'XO_USER_PF'),
+        'XoSource': ('xo::SrcUser', 'XO_USER_SOURCE'),
+        'XoDetTop': ('xo::DetUserTop', 'XO_USER_DET_TOP'),
+        'XoDetBottom': ('xo::DetUserBottom', 'XO_USER_DET_BOTTOM'),
+        'XoDetSpecular': ('xo::DetUserSpecular', 'XO_USER_DET_SPECULAR'),
+    }
+    user_plugin_slots = ('XoPf',)        # slots of this geometry that take fragments
+    clcompat_geometry_header = None
+
+    def _plugin_objects(self) -> dict:
+        """{slot typedef name: plugin object} for the slots that may hold a
+        user-written plugin."""
+        return {}
+
+    def _user_fragments(self, bindings):
+        """[(slot, object)] of the plugins that have no hand-written CUDA struct
+        (``cu_type`` is None) but carry the reference's OpenCL-C fragment protocol
+        (``cl_declaration`` / ``cl_implementation``, mcobject.py:29-170)."""
+        objs = self._plugin_objects()
+        out = []
+        for name, cu_type, _ in bindings:
+            if cu_type is not None:
+                continue
+            obj = objs.get(name)
+            if obj is None or not hasattr(obj, 'cl_implementation') or \
+                    name not in self.user_plugin_slots:
+                raise NotImplementedError(
+                    'The plugin bound to {} ({}) has neither a CUDA implementation '
+                    '(cu_type) nor OpenCL-C fragments this geometry can compile.'.format(
+                        name, type(obj).__name__ if obj is not None else None))
+            out.append((name, obj))
+        return out
 
     def _scattering_pfs(self):
         """Phase functions of the layers / materials a packet can scatter in."""
@@ -287,6 +363,7 @@ class McBase(CuWorker):
         device (used by ``__graft_entry__.build`` and the CPU test-suite)."""
         self._pack(nphotons)
         src = self.kernel_source(block, min_blocks)
+        self._last_src = src
         return compile_kernel(src, self.deterministic, arch=arch,
                               extra_options=self._cl_build_options)
 

@@ -49,6 +49,9 @@ class Mc(McBase):
         return self._layers.layer_index(r)
 
     # -- packing -----------------------------------------------------------------
+    def _plugin_objects(self):
+        return {'XoPf': self._layers[1].pf}
+
     def _scattering_pfs(self):
         return [item.pf for item in list(self._layers)[1:]]
 

@@ -87,6 +87,16 @@ class Mc(McBase):
             out.append(('XoFluence', 'xo::FluNone', None))
         return out
 
+    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular')
+    clcompat_geometry_header = 'xo_clcompat_mcml.cuh'
+
+    def _plugin_objects(self):
+        dets = self._detectors
+        return {'XoPf': self._layers[1].pf, 'XoSource': self._source,
+                'XoDetTop': dets.top if dets is not None else None,
+                'XoDetBottom': dets.bottom if dets is not None else None,
+                'XoDetSpecular': dets.specular if dets is not None else None}
+
     def _surface_bindings(self):
         layouts = self._surface if self._surface is not None else mcsurface.SurfaceLayouts()
         return [(name, lay.fetch_cu_type(self), lay.fetch_cl_type(self))

@@ -62,6 +62,9 @@ class Mc(McBase):
         return self._materials[material_index]
 
     # -- packing -----------------------------------------------------------------
+    def _plugin_objects(self):
+        return {'XoPf': self._materials[0].pf}
+
     def _scattering_pfs(self):
         return [item.pf for item in list(self._materials)]
 

@@ -496,3 +496,56 @@ def make_sv(mc, name):
 
 
 SV_CASES = ('mcml_lut_iso_radialpl_trace', 'mcvox_line_mhg_trace', 'mccyl_gk_ubeam_fiz_trace')
+
+
+# ---------------------------------------------------------------------------
+# user-written plugins (OpenCL-C fragments, tests/user_plugins.py)
+def mcml_user_plugins(mc, **kw):
+    """Phase function, source and top detector written by a *user* against the
+    reference's kernel API; bottom / specular detectors built in."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=up.user_radial(mc, Axis(0, 10e-3, 100)),
+        bottom=mc.mcdetector.Radial(Axis(0, 10e-3, 100), cosmin=0.5),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, up.user_hg(mc, 0.8)), up.user_pencil(mc), det,
+                 rnginit=424242, **kw), dict(rmax=20e-3)
+
+
+def mcml_user_plugins_native(mc, **kw):
+    """The same simulation with the built-in Hg / Line / Radial plugins: its
+    results must equal those of ``mcml_user_plugins`` bit for bit."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(Axis(0, 10e-3, 100)),
+        bottom=mc.mcdetector.Radial(Axis(0, 10e-3, 100), cosmin=0.5),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det,
+                 rnginit=424242, **kw), dict(rmax=20e-3)
+
+
+def mcml_user_cubic(mc, **kw):
+    """A phase function the reference does not ship (p ~ 1 + cos^2), user-written,
+    with a user-written bottom and specular detector around built-in plugins."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(Axis(0, 10e-3, 100)),
+        bottom=up.user_radial(mc, Axis(0, 10e-3, 50), cosmin=0.3),
+        specular=up.user_radial(mc, Axis(0, 1e-3, 4)))
+    return mc.Mc(_layers(mc, up.user_cubic(mc, 1.0)), mc.mcsource.Line(), det,
+                 rnginit=515151, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
+ALL_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
+GEOMETRY['mcml_user_plugins_native'] = 'mcml'
+GOLDEN_RUN['mcml_user_plugins_native'] = (3000, 16)
+# cases with user fragments: golden vectors come from the reference kernel
+# executing the same fragments; there is no C restatement of user code, so the
+# oracle pins them through the equivalent built-in case (value) where one exists
+USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_user_cubic}
+USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None}
+USER_GEOMETRY = {name: 'mcml' for name in USER_CASES}
+USER_RUN = {'mcml_user_plugins': (3000, 16), 'mcml_user_cubic': (3000, 16)}

@@ -38,14 +38,15 @@ def main(argv):
     import cases
     from refkernel import RefKernel
     import importlib
-    names = argv or list(cases.ALL_CASES)
+    names = argv or (list(cases.ALL_CASES) + list(cases.USER_CASES))
     for name in names:
-        geom = cases.GEOMETRY[name]
+        geom = cases.GEOMETRY.get(name) or cases.USER_GEOMETRY[name]
         mc = importlib.import_module('xopto.{}.mc'.format(geom))
-        sim, attrs = cases.ALL_CASES[name](mc, cl_devices=mc.cl.Context())
+        make = cases.ALL_CASES.get(name) or cases.USER_CASES[name]
+        sim, attrs = make(mc, cl_devices=mc.cl.Context())
         for k, v in attrs.items():
             setattr(sim, k, v)
-        n, t = cases.GOLDEN_RUN[name]
+        n, t = cases.GOLDEN_RUN.get(name) or cases.USER_RUN[name]
         rk = RefKernel(sim, geom, 'golden_' + name)
         res = rk.run(n, t)
         out = {'packed_' + k: np.frombuffer(v, np.uint8) for k, v in rk.packed_bytes().items()}

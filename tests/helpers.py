@@ -15,9 +15,11 @@ def golden(name: str):
 
 def build_sim(name: str, **kw):
     """Case ``name`` built with the pyxopto_b200 host mirror."""
-    geom = cases.GEOMETRY.get(name) or cases.UNPINNED_GEOMETRY[name]
+    geom = cases.GEOMETRY.get(name) or cases.UNPINNED_GEOMETRY.get(name) or \
+        cases.USER_GEOMETRY[name]
     mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
-    make = cases.ALL_CASES.get(name) or cases.UNPINNED_CASES[name]
+    make = cases.ALL_CASES.get(name) or cases.UNPINNED_CASES.get(name) or \
+        cases.USER_CASES[name]
     sim, attrs = make(mc, **kw)
     for k, v in attrs.items():
         setattr(sim, k, v)
@@ -26,7 +28,7 @@ def build_sim(name: str, **kw):
 
 def run_size(name: str):
     """(packets, work-items) of the static block schedule of a case."""
-    return cases.GOLDEN_RUN.get(name) or cases.UNPINNED_RUN[name]
+    return cases.GOLDEN_RUN.get(name) or cases.UNPINNED_RUN.get(name) or cases.USER_RUN[name]
 
 
 def packed_bytes(sim) -> dict:

@@ -11,7 +11,7 @@ import pytest
 
 import cases
 import xo_oracle
-from helpers import build_sim, run_size
+from helpers import build_sim, golden, run_size
 
 pytestmark = pytest.mark.gpu
 
@@ -405,3 +405,53 @@ def test_device_trace_filter_equals_host_filter(name):
     assert sim_h.run_report['sv_rows_resident'] is False
     assert np.array_equal(sv_d.data, sv_h.data) and sv_d.weight == sv_h.weight
     assert sv_d.data.sum() > 0
+
+
+# ---------------------------------------------------------------------------
+# user-written plugins: OpenCL-C fragments compiled through xo_clcompat*.cuh
+def _raw_run(name, n, threads=256, block=64, deterministic=True):
+    sim = (_det_sim(name)[0] if deterministic else build_sim(name)[0])
+    kw = dict(maxthreads=threads, wgsize=block) if deterministic else {}
+    sim.run(n, download=False, **kw)
+    accu, ints, floats = sim.download_raw()
+    return sim, accu, sim.download_seeds()[:threads]
+
+
+def test_user_fragments_equal_builtins_bit_exact():
+    """A user-written phase function, source and detector (tests/user_plugins.py)
+    that restate Hg / Line / Radial: deterministic mode must give the very
+    accumulators and MWC states of the built-in CUDA plugins (which the oracle
+    pins, test_deterministic_mode_bit_exact[mcml_user_plugins_native])."""
+    n = 4*run_size('mcml_user_plugins')[0]
+    sim_u, accu_u, x_u = _raw_run('mcml_user_plugins', n)
+    sim_n, accu_n, x_n = _raw_run('mcml_user_plugins_native', n)
+    assert 'xo_clcompat.cuh' in sim_u._last_src and 'xo_clcompat' not in sim_n._last_src
+    assert accu_u.sum() > 0
+    assert np.array_equal(accu_u, accu_n)
+    assert np.array_equal(x_u, x_n)
+    assert sim_u.run_report['threads'] == sim_n.run_report['threads']
+
+
+@pytest.mark.parametrize('name', sorted(cases.USER_CASES))
+def test_user_fragments_match_reference_kernel(name):
+    """The same fragments executed by the reference's own kernel (golden vectors,
+    libm math, static schedule): deterministic mode here differs at ulp level only
+    (same criterion as test_portable_math_is_statistically_the_reference), and the
+    throughput mode agrees within 4 sigma per detector."""
+    g = golden(name)
+    n, t = run_size(name)
+    sim, accu, _ = _raw_run(name, n, threads=t, block=t)
+    a, b = float(accu.sum()), float(g['accu'].sum())
+    assert abs(a - b) <= max(1e-3*b, 2*(n/t)**0.5*0x7FFFFF)
+    same = np.count_nonzero(accu == g['accu'])/g['accu'].size
+    assert same > 0.9
+    # throughput mode, more packets, against the golden run scaled
+    n_fast = 200000
+    sim_f, accu_f, _ = _raw_run(name, n_fast, deterministic=False)
+    K = 0x7FFFFF
+    for det in sim_f.detectors:
+        for al in sim_f.cl_rw_accumulator_allocator.allocations(det):
+            tot_gpu = accu_f[al.offset:al.offset + al.size].sum()/K/n_fast
+            tot_ref = g['accu'][al.offset:al.offset + al.size].sum()/K/n
+            sigma = np.sqrt(max(tot_ref, 1e-6)*(1.0/n + 1.0/n_fast))*np.sqrt(2)
+            assert abs(tot_gpu - tot_ref) <= 4*sigma + 1e-5, (type(det).__name__, tot_gpu, tot_ref)

@@ -1,0 +1,288 @@
+"""User-written plugins: OpenCL-C fragments against the reference's kernel API.
+
+These classes follow the reference's plugin protocol (``cl_type`` /
+``cl_declaration`` / ``cl_implementation`` / ``cl_options`` / ``cl_pack``,
+xopto/mcbase/mcobject.py:29-170) and carry *no* ``cu_type``: what a user of
+PyXOpto who wrote their own phase function, source or detector has.  Each factory
+takes the simulator module (``xopto.mcml.mc`` or ``pyxopto_b200.mcml.mc``) and
+derives the class from that package's base classes, so the very same fragment
+text runs through the reference's OpenCL-C kernel (golden vectors, this container
+only) and through ``csrc/kernels/xo_clcompat*.cuh`` here.
+
+The fragment text is written for this test-suite (it is not reference code).
+``UserHg`` / ``UserPencil`` / ``UserRadial`` restate the arithmetic of Hg, Line at
+normal incidence and Radial, so the results must equal those of the built-ins
+bit for bit; ``UserCubic`` is a phase function the reference does not ship.
+"""
+import functools
+
+import numpy as np
+
+
+def _cltypes(mc):
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase import cltypes
+    else:
+        from pyxopto_b200.cl import cltypes
+    return cltypes
+
+
+@functools.lru_cache(maxsize=None)
+def _user_hg_class(mc):
+    cltypes = _cltypes(mc)
+
+    class UserHg(mc.mcpf.PfBase):
+        """Henyey-Greenstein, user-written."""
+        @staticmethod
+        def cl_type(mc_):
+            class ClUserHg(cltypes.Structure):
+                _fields_ = [('g', mc_.types.mc_fp_t)]
+            return ClUserHg
+
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McPf{ mc_fp_t g; };\n' \
+                   'void dbg_print_pf(const McPf *pf);\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_pf(const McPf *pf) {
+	dbg_print("user-written Hg:");
+	dbg_print_float(INDENT "g:", pf->g);
+};
+
+inline mc_fp_t mcsim_pf_sample_angles(McSim *mcsim, mc_fp_t *azimuth){
+	__mc_pf_mem const McPf *pf = mcsim_current_pf(mcsim);
+	mc_fp_t g = pf->g;
+	mc_fp_t xi, ratio, cos_theta;
+
+	*azimuth = FP_2PI*mcsim_random(mcsim);
+	xi = mcsim_random(mcsim);
+	ratio = mc_fdiv(FP_1 - g*g, FP_1 + g*(FP_2*xi - FP_1));
+	cos_theta = mc_fdiv(FP_1 + g*g - ratio*ratio, FP_2*g);
+	if (g == FP_0)
+		cos_theta = FP_1 - FP_2*mcsim_random(mcsim);
+
+	return mc_fmax(mc_fmin(cos_theta, FP_1), -FP_1);
+};
+'''
+
+        def __init__(self, g):
+            super().__init__()
+            self.g = float(g)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            target.g = self.g
+            return target
+
+        def todict(self):
+            return {'type': 'UserHg', 'g': self.g}
+
+    return UserHg
+
+
+def user_hg(mc, g):
+    return _user_hg_class(mc)(g)
+
+
+@functools.lru_cache(maxsize=None)
+def _user_cubic_class(mc):
+    """p(cos t) ~ 1 + s cos^2 t (s = 1: Rayleigh), sampled by solving the cubic
+    CDF with Cardano's formula - exercises mc_cbrt / mc_sqrt / mc_fclip."""
+    cltypes = _cltypes(mc)
+
+    class UserCubic(mc.mcpf.PfBase):
+        @staticmethod
+        def cl_type(mc_):
+            class ClUserCubic(cltypes.Structure):
+                _fields_ = [('s', mc_.types.mc_fp_t), ('inv_s', mc_.types.mc_fp_t)]
+            return ClUserCubic
+
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McPf{ mc_fp_t s; mc_fp_t inv_s; };\n' \
+                   'void dbg_print_pf(const McPf *pf);\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            # CDF: (mu + s mu^3/3 + 1 + s/3) / (2 + 2s/3) = xi
+            #  ->  mu^3 + (3/s) mu - (3/s)(2 xi - 1)(1 + s/3) = 0   (depressed cubic)
+            return '''
+void dbg_print_pf(const McPf *pf) {
+	dbg_print("user-written cubic pf:");
+	dbg_print_float(INDENT "s:", pf->s);
+};
+
+inline mc_fp_t mcsim_pf_sample_angles(McSim *mcsim, mc_fp_t *azimuth){
+	mc_fp_t s = mcsim_current_pf(mcsim)->s;
+	mc_fp_t inv_s = mcsim_current_pf(mcsim)->inv_s;
+	mc_fp_t xi, p, q, d, mu;
+
+	*azimuth = FP_2PI*mcsim_random(mcsim);
+	xi = mcsim_random(mcsim);
+	if (s == FP_0)
+		return FP_1 - FP_2*xi;
+	p = inv_s;                                          /* (3/s)/3 */
+	q = FP_0p5*FP_LITERAL(3.0)*inv_s*(FP_2*xi - FP_1)*(FP_1 + s*FP_LITERAL(0.3333333333));
+	d = mc_sqrt(q*q + p*p*p);
+	mu = mc_cbrt(q + d) + mc_cbrt(q - d);
+	return mc_fclip(mu, -FP_1, FP_1);
+};
+'''
+
+        def __init__(self, strength):
+            super().__init__()
+            self.s = float(strength)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            target.s = self.s
+            target.inv_s = 1.0/self.s if self.s != 0.0 else 0.0
+            return target
+
+        def todict(self):
+            return {'type': 'UserCubic', 'strength': self.s}
+
+    return UserCubic
+
+
+def user_cubic(mc, strength=1.0):
+    return _user_cubic_class(mc)(strength)
+
+
+@functools.lru_cache(maxsize=None)
+def _user_pencil_class(mc):
+    """Pencil beam at normal incidence; specular reflectance packed by the host."""
+    cltypes = _cltypes(mc)
+
+    class UserPencil(mc.mcsource.Source):
+        @staticmethod
+        def cl_type(mc_):
+            T = mc_.types
+            class ClUserPencil(cltypes.Structure):
+                _fields_ = [('position', T.mc_point3f_t), ('reflectance', T.mc_fp_t)]
+            return ClUserPencil
+
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McSource{ mc_point3f_t position; mc_fp_t reflectance; };\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_source(__mc_source_mem const McSource *src){
+	dbg_print("user-written pencil beam:");
+	dbg_print_point3f(INDENT "position:", &src->position);
+};
+
+inline void mcsim_launch(McSim *mcsim){
+	__mc_source_mem const McSource *src = mcsim_source(mcsim);
+	mc_point3f_t down = {FP_0, FP_0, FP_1};
+
+	mcsim_set_position(mcsim, &src->position);
+	mcsim_set_direction(mcsim, &down);
+	mcsim_set_weight(mcsim, FP_1 - src->reflectance);
+	#if MC_USE_SPECULAR_DETECTOR
+	{
+		mc_point3f_t up = {FP_0, FP_0, -FP_1};
+		mcsim_specular_detector_deposit(
+			mcsim, mcsim_position(mcsim), &up, src->reflectance);
+	}
+	#endif
+	mcsim_set_current_layer_index(mcsim, 1);
+};
+'''
+
+        def __init__(self, x, y):
+            super().__init__()
+            self.position = np.array([x, y, 0.0])
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            n1, n2 = float(mc_.layer(0).n), float(mc_.layer(1).n)
+            target.position.fromarray(self.position)
+            target.reflectance = ((n1 - n2)/(n1 + n2))**2
+            return target, None, None
+
+        def todict(self):
+            return {'type': 'UserPencil', 'x': float(self.position[0]),
+                    'y': float(self.position[1])}
+
+    return UserPencil
+
+
+def user_pencil(mc, x=0.0, y=0.0):
+    return _user_pencil_class(mc)(x, y)
+
+
+@functools.lru_cache(maxsize=None)
+def _user_radial_class(mc):
+    """Concentric-ring detector around the z axis (the arithmetic of Radial)."""
+    cltypes = _cltypes(mc)
+
+    class UserRadial(mc.mcdetector.Detector):
+        def cl_type(self, mc_):
+            T = mc_.types
+            class ClUserRadial(cltypes.Structure):
+                _fields_ = [('r_min', T.mc_fp_t), ('inv_dr', T.mc_fp_t),
+                            ('cos_min', T.mc_fp_t), ('n', T.mc_size_t),
+                            ('offset', T.mc_size_t)]
+            return ClUserRadial
+
+        def cl_declaration(self, mc_):
+            Loc = self.location.capitalize()
+            return 'struct MC_STRUCT_ATTRIBUTES Mc{}Detector{{ mc_fp_t r_min; mc_fp_t inv_dr; ' \
+                   'mc_fp_t cos_min; mc_size_t n; mc_size_t offset; }};\n'.format(Loc)
+
+        def cl_implementation(self, mc_):
+            loc = self.location
+            Loc = loc.capitalize()
+            return '''
+void dbg_print_{loc}_detector(__mc_detector_mem const Mc{Loc}Detector *det){{
+	dbg_print("user-written ring detector:");
+	dbg_print_size_t(INDENT "n:", det->n);
+}};
+
+inline void mcsim_{loc}_detector_deposit(
+		McSim *mcsim, mc_point3f_t const *pos, mc_point3f_t const *dir, mc_fp_t weight){{
+	__global mc_accu_t *address;
+	__mc_detector_mem const struct Mc{Loc}Detector *det = mcsim_{loc}_detector(mcsim);
+	mc_fp_t r = mc_sqrt(pos->x*pos->x + pos->y*pos->y);
+	mc_int_t ring = mc_clip(mc_int((r - det->r_min)*det->inv_dr), 0, (mc_int_t)det->n - 1);
+	uint32_t ui32w = weight_to_int(weight)*(det->cos_min <= mc_fabs(dir->z));
+
+	address = mcsim_accumulator_buffer_ex(mcsim, det->offset + ring);
+	if (ui32w > 0)
+		accumulator_deposit(address, ui32w);
+}};
+'''.format(loc=loc, Loc=Loc)
+
+        def __init__(self, axis, cosmin):
+            super().__init__(np.zeros((axis.n,)), 0)
+            self._axis = axis
+            self._cosmin = float(cosmin)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            allocation = mc_.cl_allocate_rw_accumulator_buffer(self, self.shape)
+            target.offset = allocation.offset
+            target.r_min = self._axis.start
+            target.inv_dr = 1.0/self._axis.step
+            target.cos_min = self._cosmin
+            target.n = self._axis.n
+            return target
+
+        def todict(self):
+            return {'type': 'UserRadial'}
+
+    return UserRadial
+
+
+def user_radial(mc, axis, cosmin=0.0):
+    return _user_radial_class(mc)(axis, cosmin)
