@@ -157,7 +157,7 @@ McKernel(
 
 	const u32 gid = blockIdx.x*blockDim.x + threadIdx.x;
 	Rng rng;
-	rng.x = rng_state_x[gid];
+	rng.load(rng_state_x[gid]);
 	rng.a = rng_state_a[gid];
 	CylCtx ctx; ctx.layers = sh_layers; ctx.num_layers = (i32)num_layers;
 	const P3 src_pos = source.origin();
@@ -325,7 +325,7 @@ McKernel(
 				}
 			}
 		}
-		rng_state_x[gid] = rng.x;
+		rng_state_x[gid] = rng.state();
 	}
 #undef XO_LAUNCH_PACKET
 	if (started) atomicAdd(num_kernels, 1u);

@@ -270,7 +270,7 @@ McKernel(
 
 	const u32 gid = blockIdx.x*blockDim.x + threadIdx.x;
 	Rng rng;
-	rng.x = rng_state_x[gid];
+	rng.load(rng_state_x[gid]);
 	rng.a = rng_state_a[gid];
 	MlCtx ctx; ctx.layers = sh_layers; ctx.num_layers = (i32)num_layers;
 #if XO_USE_RMAX
@@ -506,6 +506,13 @@ McKernel(
 #define XO_LOTTERY() do { if (weight < XO_WEIGHT_MIN) done = true; } while (0)
 #endif
 
+	// a lane may take a new packet (or retire) only after the staged trace events of
+	// its previous packet have left for memory (the flush reads `packet`)
+#if XO_TRACE && XO_TRACE_STAGED
+#define XO_NEEDS_PACKET() (state == ST_DEAD && !stg_pending)
+#else
+#define XO_NEEDS_PACKET() (state == ST_DEAD)
+#endif
 	for (;;) {
 #if XO_TRACE && XO_TRACE_STAGED
 		// ---- flush completed trace lines: 8 lanes write one 128-byte line ------------
@@ -593,7 +600,7 @@ McKernel(
 				XO_END_TRIP();
 			}
 			// ---- new packets for the lanes that need one -----------------------------------
-			u32 dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
+			u32 dead_mask = __ballot_sync(0xffffffffu, XO_NEEDS_PACKET());
 			while (dead_mask != 0u) {
 				if (q_count == 0u) {
 					if (q_dry) break;
@@ -622,7 +629,7 @@ McKernel(
 					q_count = n_new;
 					if (n_new == 0u) break;
 				}
-				if (state == ST_DEAD) {
+				if (XO_NEEDS_PACKET()) {
 					const u32 rank = (u32)__popc(dead_mask & lanemask_lt);
 					if (rank < q_count) {
 						const u32 slot = q_count - 1u - rank;
@@ -643,11 +650,11 @@ McKernel(
 				if (n_dead <= q_count) { q_count -= n_dead; break; }
 				// the queue ran out before every waiting lane had a packet: refill, go on
 				q_count = 0u;
-				dead_mask = __ballot_sync(0xffffffffu, state == ST_DEAD);
+				dead_mask = __ballot_sync(0xffffffffu, XO_NEEDS_PACKET());
 			}
 			if (q_dry && q_count == 0u) {
 				// packet budget exhausted: the lanes still waiting for a packet retire
-				if (state == ST_DEAD) state = ST_DRY;
+				if (XO_NEEDS_PACKET()) state = ST_DRY;
 				const u32 n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
 				if (n_dry == 32u) break;
 				thr_eff = refill < 32u - n_dry ? refill : 32u - n_dry;
@@ -734,17 +741,18 @@ McKernel(
 		XO_END_TRIP();
 	}
 #undef XO_LOAD_LAYER
+#undef XO_NEEDS_PACKET
 #undef XO_END_TRIP
 #undef XO_LOTTERY
 	// every lane drew from its stream (queue refills), whether or not it ever
 	// carried a packet: all states go back
-	rng_state_x[gid] = rng.x;
+	rng_state_x[gid] = rng.state();
 #endif  // XO_DETERMINISTIC
 #undef XO_RMAX_TEST
 #undef XO_TRACE_TRIP
 	if (started) {
 #if XO_DETERMINISTIC
-		rng_state_x[gid] = rng.x;
+		rng_state_x[gid] = rng.state();
 #endif
 		atomicAdd(num_kernels, 1u);
 	}

@@ -368,5 +368,5 @@
 #undef XO_END_TRIP
 	// every lane drew from its stream (queue refills), whether or not it ever
 	// carried a packet: all states go back
-	rng_state_x[gid] = rng.x;
+	rng_state_x[gid] = rng.state();
 }

@@ -193,7 +193,7 @@ McKernel(
 	const u32 gid = blockIdx.x*blockDim.x + threadIdx.x;
 	const u32 nthreads = gridDim.x*blockDim.x;
 	Rng rng;
-	rng.x = rng_state_x[gid];
+	rng.load(rng_state_x[gid]);
 	rng.a = rng_state_a[gid];
 	const VoxCfg &cfg = voxel_cfg;
 	VoxCtx ctx(cfg, sh_mat, voxels);
@@ -400,7 +400,7 @@ McKernel(
 				}
 			}
 		}
-		rng_state_x[gid] = rng.x;
+		rng_state_x[gid] = rng.state();
 	}
 #undef XO_LAUNCH_PACKET
 #endif  // XO_VOX_DDA

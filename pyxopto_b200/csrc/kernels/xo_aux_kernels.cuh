@@ -9,7 +9,7 @@
 
 extern "C" __global__ void RngKernel(xo::u64 x, xo::u32 a, xo::u32 n, float *buffer) {
 	if (blockIdx.x*blockDim.x + threadIdx.x == 0) {
-		xo::Rng rng; rng.x = x; rng.a = a;
+		xo::Rng rng; rng.load(x); rng.a = a;
 		for (xo::u32 i = 0; i < n; ++i) buffer[i] = rng.next();
 	}
 }

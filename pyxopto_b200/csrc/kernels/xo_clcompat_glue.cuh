@@ -55,7 +55,7 @@ __device__ __forceinline__ void SrcUser::launch(Rng &rng, const Ctx &ctx, Launch
 
 #define XO_CLC_DETECTOR_BODY(slot, fn) \
 	McSim sim; \
-	Rng none = { 0ull, 0u }; \
+	Rng none; none.load(0ull); none.a = 0u; \
 	clc_sim_init(sim, &none); \
 	sim.slot = &d; \
 	sim.accumulator_buffer = acc.global; \

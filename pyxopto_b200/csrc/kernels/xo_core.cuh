@@ -78,16 +78,24 @@ __device__ __forceinline__ u32 f2u(float x) { return __float2uint_rz(x); }
 //   x <- lo32(x)*a + hi32(x);  u = RN(float(lo32(x))) / RN(float(0xFFFFFFFF)) = RN(float(lo32 x))*2^-32
 // (the divisor rounds to 2^32, so the IEEE division is an exact scaling).
 struct Rng {
+#if XO_DETERMINISTIC
 	u64 x;
 	u32 a;
-	// one step of the recurrence as IMAD.WIDE.U32 + IADD3 + IADD3.X (the plain C
-	// expression compiles to twice as many instructions: the compiler
-	// materialises the zero-extended carry word as a register pair)
-	__device__ __forceinline__ void step() {
-#if XO_DETERMINISTIC
-		x = (u64)(u32)x*(u64)a + (x >> 32);
+	__device__ __forceinline__ void load(u64 v) { x = v; }
+	__device__ __forceinline__ u64 state() const { return x; }
+	__device__ __forceinline__ u32 low() const { return (u32)x; }
+	__device__ __forceinline__ void step() { x = (u64)(u32)x*(u64)a + (x >> 32); }
 #else
-		u32 lo = (u32)x, hi = (u32)(x >> 32);
+	// the two state words as independent 32-bit registers, stepped in place: one
+	// step is IMAD.WIDE.U32 + IADD3 + IADD3.X (the plain C expression on a u64
+	// compiles to twice as many instructions: the compiler materialises the
+	// zero-extended carry word as a register pair)
+	u32 lo, hi;
+	u32 a;
+	__device__ __forceinline__ void load(u64 v) { lo = (u32)v; hi = (u32)(v >> 32); }
+	__device__ __forceinline__ u64 state() const { return ((u64)hi << 32) | lo; }
+	__device__ __forceinline__ u32 low() const { return lo; }
+	__device__ __forceinline__ void step() {
 		asm("{\n\t"
 			".reg .u64 p;\n\t"
 			".reg .u32 pl, ph;\n\t"
@@ -96,18 +104,17 @@ struct Rng {
 			"add.cc.u32 %0, pl, %1;\n\t"
 			"addc.u32 %1, ph, 0;\n\t"
 			"}" : "+r"(lo), "+r"(hi) : "r"(a));
-		x = ((u64)hi << 32) | lo;
-#endif
 	}
+#endif
 	__device__ __forceinline__ float next() {
 		step();
-		return __uint2float_rn((u32)x)*2.3283064365386963e-10f;
+		return __uint2float_rn(low())*2.3283064365386963e-10f;
 	}
 	// the same draw before the 2^-32 scaling, RN(float(lo32 x)) in [0, 2^32]:
 	// throughput-mode callers fold the scale into their own constants
 	__device__ __forceinline__ float next_raw() {
 		step();
-		return __uint2float_rn((u32)x);
+		return __uint2float_rn(low());
 	}
 };
 #define XO_RNG_SCALE 2.3283064365386963e-10f

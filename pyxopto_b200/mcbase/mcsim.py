@@ -319,7 +319,17 @@ class McBase(CuWorker):
     # with a long launch path amortise it over more lanes
     refill_lanes = None
     default_refill_lanes = 1
-    min_blocks = 1                   # __launch_bounds__ second argument
+    min_blocks = None                # __launch_bounds__ second argument (None: automatic)
+
+    def _min_blocks(self, block: int) -> int:
+        if self.min_blocks is not None:
+            return int(self.min_blocks)
+        # the staged full-trace kernel needs 76 KB of shared memory per 256-thread
+        # CTA: three CTAs per SM fit if the compiler stays below 80 registers
+        # (measured C4: 3.94 ms at 83 registers / 2 CTAs, 3.38 ms at 72 / 3 CTAs)
+        if self._trace_staged() and block <= 256:
+            return 3
+        return 1
     chunk_max = 16
 
     def _refill_lanes(self) -> int:
@@ -474,7 +484,7 @@ class McBase(CuWorker):
             block = self.fluence_block
         else:
             block = DEFAULT_BLOCK
-        src = self.kernel_source(block=block, min_blocks=int(self.min_blocks))
+        src = self.kernel_source(block=block, min_blocks=self._min_blocks(block))
         self._last_src = src
         if exportsrc:
             with open(exportsrc, 'w') as f:
