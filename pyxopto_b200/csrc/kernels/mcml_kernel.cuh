@@ -465,10 +465,10 @@ McKernel(
 #undef XO_LAUNCH_PACKET
 #else
 	// ======== throughput loop ======================================================
-	// Lane states.  RUN: a packet is in flight.  BND_*: the packet sits on the
-	// top / bottom interface of its layer, interface physics pending.  DEAD:
+	// Lane states.  RUN: a packet is in flight.  BND: the step of the packet ends
+	// on the top / bottom interface of its layer, interface physics pending.  DEAD:
 	// needs a packet from the warp's launch queue.  DRY: no packets left.
-	enum : u32 { ST_RUN = 0, ST_BND_TOP = 1, ST_BND_BOTTOM = 2, ST_DEAD = 3, ST_DRY = 4 };
+	enum : u32 { ST_RUN = 0, ST_DRY = 1, ST_BND = 2, ST_DEAD = 3 };   // waiting: >= ST_BND
 	const u32 lane = threadIdx.x & 31u;
 	const u32 lanemask_lt = (1u << lane) - 1u;
 	u32 state = ST_DEAD;
@@ -547,11 +547,12 @@ McKernel(
 		// run jointly, in this order -- a packet that leaves the medium in the
 		// interface handler is replaced in the same round.  The rare, long paths run
 		// with several lanes instead of 1-2, and the common trip pays one VOTE.
-		const u32 wait_mask = __ballot_sync(0xffffffffu, state - 1u < 3u);
+		const u32 wait_mask = __ballot_sync(0xffffffffu, state >= ST_BND);
 		if (__builtin_expect((u32)__popc(wait_mask) >= thr_eff, 0)) {
 			// ---- interface physics ----------------------------------------------------
-			if (state - 1u < 2u) {
-				const bool up = (state == ST_BND_TOP);
+			if (state == ST_BND) {
+				// (a packet reaches the top interface moving up, the bottom one moving down)
+				const bool up = dir.z < 0.0f;
 				bool done = false;
 #if XO_METHOD != 2
 				{   // move onto the interface (mcml.template.c:541-582)
@@ -670,11 +671,10 @@ McKernel(
 		++iterations;
 		float step = fminf(fmaf(FastMath::lg2(rng.next_raw()), c_hot.step_k, c_hot.step_b), XO_FLT_MAX);
 		const float zs = fmaf(step, dir.z, pos.z);
-		const bool hit_top = zs < c_hot.top;
-		const bool hit = hit_top || zs >= c_hot.bottom;
+		const bool hit = !(zs >= c_hot.top && zs < c_hot.bottom);
 #if XO_METHOD == 2
 		if (hit) {
-			const float zb = hit_top ? c_hot.top : c_hot.bottom;
+			const float zb = (zs < c_hot.top) ? c_hot.top : c_hot.bottom;
 			if (dir.z != 0.0f) step = (zb - pos.z)*FastMath::rcp_approx(dir.z);
 			pos.z = zb;
 		} else {
@@ -696,14 +696,14 @@ McKernel(
 			}
 		}
 		if (hit) {
-			state = hit_top ? ST_BND_TOP : ST_BND_BOTTOM;
+			state = ST_BND;
 			continue;
 		}
 #else
-		if (hit) {
+		if (__builtin_expect(hit, 0)) {
 			// the move onto the interface (one division) is part of the deferred
 			// interface handling: the packet stays where it is until then
-			state = hit_top ? ST_BND_TOP : ST_BND_BOTTOM;
+			state = ST_BND;
 			continue;
 		}
 		pos.z = zs;
