@@ -87,6 +87,9 @@ typedef struct { p3f direction; float x_min, inv_dx, y_min, inv_dy, cos_min;
 	uint32_t n_x, n_y, offset; } det_cartesian;
 typedef struct { m3f T; p2f position; float core_r_squared, core_spacing, cos_min;
 	uint32_t offset; } det_six;
+/* mcdetector/probe/lineararray.py:58-66 */
+typedef struct { m3f T; p2f first_position, delta_position; float core_r_squared, cos_min;
+	uint32_t offset; } det_linarray;
 typedef struct { p3f direction; p2f position; float r_min, inv_dr, pl_min, inv_dpl, cos_min;
 	uint32_t n_r, n_pl, offset; int32_t r_log_scale, pl_log_scale; } det_radialpl;
 typedef struct { p3f direction; float cos_min, pl_min, inv_dpl;
@@ -434,6 +437,8 @@ enum { LOC_TOP = 0, LOC_BOTTOM = 1, LOC_SPECULAR = 2 };
 static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, float weight) {
 	const xo_oracle_job *j = s->job;
 	const char *base = (const char *)j->detectors + j->det_offset[loc];
+	const int32_t param = j->det_param[loc];
+	(void)param;
 	switch (j->det_kind[loc]) {
 	case XO_DET_TOTAL: {                               /* mcdetector/total.py:86-110 */
 		const det_total *d = (const det_total *)base;
@@ -490,6 +495,49 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		float pz = T.a31*dir->x + T.a32*dir->y + T.a33*dir->z;
 		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(pz));
 		if (w > 0) accu_deposit(s, d->offset + fiber_index, w);
+		break;
+	}
+	case XO_DET_LINEARARRAY: {                         /* mcdetector/probe/lineararray.py:105-167 */
+		const det_linarray *d = (const det_linarray *)base;
+		uint32_t n = (uint32_t)param, fiber_index = n;
+		float fiber_x = d->first_position.x, fiber_y = d->first_position.y;
+		p3f mc_pos, dp; float dx, dy, r2;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = pos->x - fiber_x; mc_pos.y = pos->y - fiber_y; mc_pos.z = FP_0;
+			m3f T = d->T;
+			transform3(&T, &mc_pos, &dp);
+			dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= d->core_r_squared) { fiber_index = index; break; }
+			fiber_x += d->delta_position.x;
+			fiber_y += d->delta_position.y;
+		}
+		if (fiber_index >= n) return;
+		float pz = d->T.a31*dir->x + d->T.a32*dir->y + d->T.a33*dir->z;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(pz));
+		if (w > 0) accu_deposit(s, d->offset + fiber_index, w);
+		break;
+	}
+	case XO_DET_FIBERARRAY: {                          /* mcdetector/probe/fiberarray.py:101-160 */
+		/* packed: m3f T[n]; p2f core_position[n]; float core_r_squared[n], cos_min[n]; u32 offset */
+		uint32_t n = (uint32_t)param, fiber_index = n;
+		const m3f *Ts = (const m3f *)base;
+		const p2f *cp = (const p2f *)(Ts + n);
+		const float *r2s = (const float *)(cp + n);
+		const float *cmin = r2s + n;
+		uint32_t offset = *(const uint32_t *)(cmin + n);
+		p3f mc_pos, dp; float dx, dy, r2;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = pos->x - cp[index].x; mc_pos.y = pos->y - cp[index].y; mc_pos.z = FP_0;
+			m3f T = Ts[index];
+			transform3(&T, &mc_pos, &dp);
+			dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= r2s[index]) { fiber_index = index; break; }
+		}
+		if (fiber_index >= n) return;
+		const m3f *Tf = &Ts[fiber_index];
+		float pz = Tf->a31*dir->x + Tf->a32*dir->y + Tf->a33*dir->z;
+		uint32_t w = weight_to_u32(weight, cmin[fiber_index] <= fabsf(pz));
+		if (w > 0) accu_deposit(s, offset + fiber_index, w);
 		break;
 	}
 	case XO_DET_RADIALPL: {                            /* mcdetector/radialpl.py:138-180 */

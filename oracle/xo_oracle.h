@@ -26,7 +26,8 @@ enum {
 	XO_DET_NONE = 0, XO_DET_TOTAL = 1, XO_DET_RADIAL = 2, XO_DET_CARTESIAN = 3,
 	XO_DET_SIXAROUNDONE = 4, XO_DET_RADIALPL = 5, XO_DET_TOTALPL = 6,
 	XO_DET_SYMMETRICX = 7, XO_DET_FIZ = 8, XO_DET_CARTESIANPL = 9,
-	XO_DET_SIXAROUNDONEPL = 10, XO_DET_TOTAL_CYL = 11
+	XO_DET_SIXAROUNDONEPL = 10, XO_DET_TOTAL_CYL = 11, XO_DET_LINEARARRAY = 12,
+	XO_DET_FIBERARRAY = 13
 };
 enum {
 	XO_FLU_NONE = 0, XO_FLU_XYZ = 1, XO_FLU_RZ = 2, XO_FLU_XYZT = 3,
@@ -48,6 +49,7 @@ typedef struct xo_oracle_job {
 	int32_t src_kind;
 	int32_t det_kind[3];       /* top, bottom, specular */
 	int32_t det_offset[3];     /* byte offsets inside the packed McDetectors */
+	int32_t det_param[3];      /* compile-time parameter of the plugin text (fiber count) */
 	int32_t fluence_kind;
 	int32_t fluence_rate;      /* MC_FLUENCE_MODE_RATE */
 	int32_t trace_flags;       /* MC_USE_TRACE value */

@@ -30,7 +30,8 @@ SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
             'IsotropicPoint': 4, 'UniformBeam': 5}
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
-            'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10}
+            'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10,
+            'LinearArray': 12, 'FiberArray': 13}
 DET_KIND_TOTAL_CYL = 11
 SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
              'SixAroundOne': 2}
@@ -46,6 +47,7 @@ class Job(ctypes.Structure):
         ('pf_kind', ctypes.c_int32), ('pf_size', ctypes.c_int32),
         ('src_kind', ctypes.c_int32),
         ('det_kind', ctypes.c_int32*3), ('det_offset', ctypes.c_int32*3),
+        ('det_param', ctypes.c_int32*3),
         ('fluence_kind', ctypes.c_int32), ('fluence_rate', ctypes.c_int32),
         ('trace_flags', ctypes.c_int32), ('use_events', ctypes.c_int32),
         ('track_opl', ctypes.c_int32),
@@ -171,7 +173,7 @@ def describe(mc_obj, geometry: str) -> dict:
              layers=_raw(P[layers_key]), source=_raw(P['source']),
              src_kind=SRC_KIND[_name(mc_obj.source)])
     dets = mc_obj.detectors
-    det_kind, det_off = [0, 0, 0], [0, 0, 0]
+    det_kind, det_off, det_par = [0, 0, 0], [0, 0, 0], [0, 0, 0]
     if dets is not None:
         dstruct = type(P['detectors'])
         # mccyl: `outer` takes the slot of `top`, there is no `bottom`
@@ -185,8 +187,9 @@ def describe(mc_obj, geometry: str) -> dict:
             if geometry == 'mccyl' and det_kind[i] == DET_KIND['Total']:
                 det_kind[i] = DET_KIND_TOTAL_CYL
             det_off[i] = getattr(dstruct, loc).offset
+            det_par[i] = int(getattr(det, 'n', 0) or 0) if det_kind[i] in (12, 13) else 0
         d['detectors'] = _raw(P['detectors'])
-    d['det_kind'], d['det_offset'] = det_kind, det_off
+    d['det_kind'], d['det_offset'], d['det_param'] = det_kind, det_off, det_par
     surf = getattr(mc_obj, 'surface', None)
     d['surf_kind'], d['surf_offset'] = [0, 0], [0, 0]
     if surf is not None and geometry == 'mcml':
@@ -250,6 +253,7 @@ def run(desc: dict, nphotons: int, nthreads: int, rng_x: np.ndarray,
     for i in range(3):
         job.det_kind[i] = desc['det_kind'][i]
         job.det_offset[i] = desc['det_offset'][i]
+        job.det_param[i] = desc.get('det_param', [0, 0, 0])[i]
     job.fluence_kind = desc.get('fluence_kind', 0)
     job.fluence_rate = desc.get('fluence_rate', 0)
     job.trace_flags = desc.get('trace_flags', 0)

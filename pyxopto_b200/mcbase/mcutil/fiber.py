@@ -1,4 +1,6 @@
-"""Optical fiber description (mirror of ``xopto/mcbase/mcutil/fiber.py`` MultimodeFiber)."""
+"""Optical fiber description (mirror of ``xopto/mcbase/mcutil/fiber.py`` MultimodeFiber,
+FiberLayout)."""
+import numpy as np
 
 
 class MultimodeFiber:
@@ -36,3 +38,54 @@ class MultimodeFiber:
     def __repr__(self):
         return 'MultimodeFiber(dcore={}, dcladding={}, ncore={}, na={})'.format(
             self.dcore, self.dcladding, self.ncore, self.na)
+
+
+class FiberLayout:
+    """A fiber placed at ``position`` (x, y[, z]) and tilted into ``direction``
+    (mcutil/fiber.py:384-470)."""
+    def __init__(self, fiber, position=(0.0, 0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        if isinstance(fiber, FiberLayout):
+            o = fiber
+            fiber, position, direction = o.fiber, o.position, o.direction
+        self._fiber = fiber
+        self._position = np.zeros((3,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self.position = position
+        self.direction = direction
+
+    def _set_fiber(self, fiber):
+        self._fiber = fiber
+
+    fiber = property(lambda self: self._fiber, _set_fiber)
+
+    def _set_position(self, value):
+        value = np.asarray(value, dtype=np.float64).reshape(-1)
+        if value.size < 3:
+            self._position[:value.size] = value
+        else:
+            self._position[:] = value[:3]
+
+    position = property(lambda self: self._position, _set_position)
+
+    def _set_direction(self, direction):
+        self._direction[:] = direction
+        norm = np.linalg.norm(self._direction)
+        if norm == 0.0:
+            raise ValueError('Direction vector norm/length must not be 0!')
+        self._direction *= 1.0/norm
+
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def todict(self) -> dict:
+        return {'type': 'FiberLayout', 'fiber': self._fiber.todict(),
+                'position': self._position.tolist(), 'direction': self._direction.tolist()}
+
+    @classmethod
+    def fromdict(cls, data: dict):
+        data = dict(data)
+        data.pop('type', None)
+        return cls(MultimodeFiber.fromdict(data.pop('fiber')), **data)
+
+    def __repr__(self):
+        return 'FiberLayout(fiber={}, position=({}, {}, {}), direction=({}, {}, {}))'.format(
+            self._fiber, *self._position, *self._direction)

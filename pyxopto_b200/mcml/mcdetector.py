@@ -12,7 +12,7 @@ from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import geometry
 from ..mcbase.mcutil.axis import Axis, RadialAxis, SymmetricAxis  # noqa: F401
-from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
+from ..mcbase.mcutil.fiber import MultimodeFiber, FiberLayout  # noqa: F401
 
 NONE, TOP, BOTTOM, SPECULAR = 'none', 'top', 'bottom', 'specular'
 
@@ -313,6 +313,190 @@ class SixAroundOne(Detector):
         return {'type': 'SixAroundOne', 'fiber': self._fiber.todict(),
                 'spacing': self._spacing, 'position': self._position.tolist(),
                 'direction': self._direction.tolist()}
+
+
+class LinearArray(Detector):
+    """Linear array of ``n`` equally spaced fibers (probe/lineararray.py); raw[i] is
+    fiber i, counted along ``orientation``.  ``n`` is a compile-time feature."""
+    def cu_type(self, mc):
+        return 'xo::DetLinearArray<{}>'.format(self._n)
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClLinearArray(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t),
+                        ('first_position', T.mc_point2f_t),
+                        ('delta_position', T.mc_point2f_t),
+                        ('core_r_squared', T.mc_fp_t), ('cos_min', T.mc_fp_t),
+                        ('offset', T.mc_size_t)]
+        return ClLinearArray
+
+    def __init__(self, fiber, n: int = 1, spacing: float = None, orientation=(1.0, 0.0),
+                 position=(0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        if isinstance(fiber, LinearArray):
+            o = fiber
+            fiber, n, spacing = o.fiber, o.n, o.spacing
+            orientation, position, direction = o.orientation, o.position, o.direction
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            n = max(int(n), 1)
+            raw, nphotons = np.zeros((n,)), 0
+            if spacing is None:
+                spacing = fiber.dcladding
+        super().__init__(raw, nphotons)
+        self._fiber = fiber
+        self._n = max(int(n), 1)
+        self._spacing = float(spacing)
+        self._orientation = np.array((1.0, 0.0))
+        self._position = np.zeros((2,))
+        self.orientation = orientation
+        self.position = position
+        self.direction = direction
+
+    def _set_fiber(self, fiber):
+        self._fiber = fiber
+
+    fiber = property(lambda self: self._fiber, _set_fiber)
+    n = property(lambda self: self._n)
+
+    def _set_spacing(self, v):
+        self._spacing = float(v)
+
+    spacing = property(lambda self: self._spacing, _set_spacing)
+
+    def _set_orientation(self, o):
+        self._orientation[:] = o
+        norm = np.linalg.norm(self._orientation)
+        if norm == 0.0:
+            raise ValueError('Orientation vector norm/length must not be 0!')
+        self._orientation *= 1.0/norm
+
+    orientation = property(lambda self: self._orientation, _set_orientation)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+
+    def check(self):
+        if self._spacing < self._fiber.dcore:
+            raise ValueError('Spacing between the optical fibers is smaller '
+                             'than the diameter of the fiber core!')
+        return True
+
+    def fiber_position(self, index: int) -> Tuple[float, float]:
+        if index >= self._n or index < -self._n:
+            raise IndexError('The fiber index is out of valid range!')
+        left = self._position - self._orientation*self._spacing*(self._n - 1)*0.5
+        return tuple(left + self._spacing*self._orientation*int(index))
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        adir = self._direction[0], self._direction[1], abs(self._direction[2])
+        target.transformation.fromarray(geometry.transform_base(adir, (0.0, 0.0, 1.0)))
+        target.core_r_squared = 0.25*self._fiber.dcore**2
+        target.cos_min = (1.0 - (self._fiber.na/self._fiber.ncore)**2)**0.5
+        target.first_position.fromarray(self.fiber_position(0))
+        target.delta_position.fromarray(self._orientation*self._spacing)
+        return target
+
+    def todict(self):
+        return {'type': 'LinearArray', 'fiber': self._fiber.todict(), 'n': self._n,
+                'orientation': self._orientation.tolist(), 'spacing': self._spacing,
+                'position': self._position.tolist(), 'direction': self._direction.tolist()}
+
+    @staticmethod
+    def fromdict(data):
+        data = dict(data)
+        if data.pop('type') != 'LinearArray':
+            raise TypeError('Expected a "LinearArray" type!')
+        return LinearArray(MultimodeFiber.fromdict(data.pop('fiber')), **data)
+
+
+class FiberArray(Detector):
+    """Array of individually placed / tilted fibers (probe/fiberarray.py); raw[i] is
+    fiber i of the list.  The number of fibers is a compile-time feature."""
+    def cu_type(self, mc):
+        return 'xo::DetFiberArray<{}>'.format(len(self._fibers))
+
+    def cl_type(self, mc):
+        T = mc.types
+        n = self.n
+        class ClFiberArray(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t*n),
+                        ('core_position', T.mc_point2f_t*n),
+                        ('core_r_squared', T.mc_fp_t*n), ('cos_min', T.mc_fp_t*n),
+                        ('offset', T.mc_size_t)]
+        return ClFiberArray
+
+    def __init__(self, fibers):
+        if isinstance(fibers, FiberArray):
+            o = fibers
+            fibers, raw, nphotons = o.fibers, np.copy(o.raw), o.nphotons
+        else:
+            fibers = list(fibers)
+            raw, nphotons = np.zeros((len(fibers),)), 0
+        super().__init__(raw, nphotons)
+        self._fibers = fibers
+
+    def _set_fibers(self, fibers):
+        if len(self._fibers) != len(fibers):
+            raise ValueError('The number of optical fibers must not change!')
+        if type(self._fibers[0]) != type(fibers[0]):
+            raise TypeError('The type of optical fibers must not change!')
+        self._fibers[:] = fibers
+
+    fibers = property(lambda self: self._fibers, _set_fibers)
+    n = property(lambda self: len(self._fibers))
+
+    def __len__(self):
+        return len(self._fibers)
+
+    def __iter__(self):
+        return iter(self._fibers)
+
+    def __getitem__(self, what):
+        return self._fibers[what]
+
+    def check(self):
+        for a in self._fibers:
+            for b in self._fibers:
+                if a is not b:
+                    d = np.linalg.norm(a.position - b.position)
+                    if d < max(a.fiber.dcladding, b.fiber.dcladding):
+                        raise ValueError('Some of the fibers in the detector array overlap!')
+        return True
+
+    def fiber_position(self, index: int) -> Tuple[float, float]:
+        n = len(self._fibers)
+        if index >= n or index < -n:
+            raise IndexError('The fiber index is out of valid range!')
+        return tuple(self._fibers[index].position[:2])
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        for index, cfg in enumerate(self._fibers):
+            adir = cfg.direction[0], cfg.direction[1], abs(cfg.direction[2])
+            target.transformation[index].fromarray(
+                geometry.transform_base(adir, (0.0, 0.0, 1.0)))
+            target.core_position[index].fromarray(cfg.position)
+            target.core_r_squared[index] = 0.25*cfg.fiber.dcore**2
+            target.cos_min[index] = (1.0 - (cfg.fiber.na/cfg.fiber.ncore)**2)**0.5
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        return target
+
+    def todict(self):
+        return {'type': 'FiberArray', 'fibers': [f.todict() for f in self._fibers]}
+
+    @staticmethod
+    def fromdict(data):
+        data = dict(data)
+        if data.pop('type') != 'FiberArray':
+            raise TypeError('Expected a "FiberArray" type!')
+        return FiberArray([FiberLayout.fromdict(f) for f in data.pop('fibers')])
 
 
 class RadialPl(Detector):

@@ -549,3 +549,56 @@ USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_us
 USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None}
 USER_GEOMETRY = {name: 'mcml' for name in USER_CASES}
 USER_RUN = {'mcml_user_plugins': (3000, 16), 'mcml_user_cubic': (3000, 16)}
+
+
+# ---------------------------------------------------------------------------
+# fiber-array probes (mcdetector/probe/lineararray.py, fiberarray.py)
+def _fiber_layout(mc, fib, position, direction=(0.0, 0.0, 1.0)):
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcml.mcutil import fiber as fiberutil
+        return fiberutil.FiberLayout(fib, position, direction)
+    return mc.mcdetector.FiberLayout(fib, position, direction)
+
+
+def mcml_hg_fiber_lineararray(mc, **kw):
+    """UniformFiber source under a tilted 5-fiber linear array (top) and a
+    3-fiber array along y (bottom)."""
+    fib = _fiber(mc)
+    tilt = (np.sin(np.deg2rad(8.0)), 0.0, np.cos(np.deg2rad(8.0)))
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.LinearArray(fib, 5, spacing=250e-6, direction=tilt,
+                                      position=(0.1e-3, 0.0)),
+        bottom=mc.mcdetector.LinearArray(fib, 3, orientation=(0.0, 1.0)),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.UniformFiber(fib), det,
+                 rnginit=737373, **kw), dict(rmax=20e-3)
+
+
+def mcml_mhg_line_fiberarray(mc, **kw):
+    """Line source, individually placed and tilted fibers of two kinds (top),
+    a two-fiber array at the bottom."""
+    fib = _fiber(mc)
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcml.mcutil import fiber as fiberutil
+        big = fiberutil.MultimodeFiber(400e-6, 440e-6, 1.462, 0.37)
+    else:
+        big = mc.mcsource.MultimodeFiber(400e-6, 440e-6, 1.462, 0.37)
+    tilt = (0.0, np.sin(np.deg2rad(-10.0)), np.cos(np.deg2rad(-10.0)))
+    top = mc.mcdetector.FiberArray([
+        _fiber_layout(mc, fib, (0.0, 0.0, 0.0)),
+        _fiber_layout(mc, big, (0.5e-3, 0.0, 0.0), tilt),
+        _fiber_layout(mc, fib, (-0.3e-3, 0.3e-3, 0.0)),
+        _fiber_layout(mc, big, (0.0, -0.6e-3, 0.0))])
+    bottom = mc.mcdetector.FiberArray([
+        _fiber_layout(mc, big, (0.0, 0.0, 0.0)), _fiber_layout(mc, big, (0.6e-3, 0.0, 0.0))])
+    det = mc.mcdetector.Detectors(top=top, bottom=bottom)
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.7, 0.8)), mc.mcsource.Line(), det,
+                 rnginit=848484, **kw), dict(rmax=20e-3)
+
+
+for _name, _fn in (('mcml_hg_fiber_lineararray', mcml_hg_fiber_lineararray),
+                   ('mcml_mhg_line_fiberarray', mcml_mhg_line_fiberarray)):
+    MCML_CASES[_name] = _fn
+    ALL_CASES[_name] = _fn
+    GEOMETRY[_name] = 'mcml'
+    GOLDEN_RUN[_name] = (4000, 16)
