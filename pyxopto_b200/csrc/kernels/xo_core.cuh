@@ -200,6 +200,7 @@ __device__ __forceinline__ bool fresnel_axis_fast(float n12, float cc, float &dn
 // Rotates `d` by polar cosine ct and azimuth fi, then renormalises (the
 // reference always renormalises in single precision, mcbase.template.c:1551).
 __device__ __forceinline__ void scatter_direction(P3 &d, float ct, float fi) {
+#if XO_DETERMINISTIC
 	float sf, cf;
 	float st = M::sqrt(1.0f - ct*ct);
 	M::sincos(fi, &sf, &cf);
@@ -210,26 +211,34 @@ __device__ __forceinline__ void scatter_direction(P3 &d, float ct, float fi) {
 		d.y = stsf;
 		d.z = copysignf(ct, d.z*ct);
 	} else {
-#if XO_DETERMINISTIC
 		float k = M::sqrt(1.0f - d.z*d.z);
 		d.x = M::div(stcf*px*d.z - stsf*d.y, k) + px*ct;
 		d.y = M::div(stcf*d.y*d.z + stsf*px, k) + d.y*ct;
 		d.z = (-stcf)*k + d.z*ct;
-#else
-		float k2 = 1.0f - d.z*d.z;
-		float ik = rsqrtf(k2);
-		float nx = (stcf*px*d.z - stsf*d.y)*ik + px*ct;
-		float ny = (stcf*d.y*d.z + stsf*px)*ik + d.y*ct;
-		d.z = d.z*ct - stcf*(k2*ik);
-		d.x = nx; d.y = ny;
-#endif
 	}
-#if XO_DETERMINISTIC
 	float k = M::div(1.0f, M::sqrt(d.x*d.x + d.y*d.y + d.z*d.z));
-#else
-	float k = rsqrtf(d.x*d.x + d.y*d.y + d.z*d.z);
-#endif
 	d.x *= k; d.y *= k; d.z *= k;
+#else
+	// branch-free: the general rotation with 1 - dz^2 kept away from zero, the
+	// |dz| >= 1 case of the reference selected afterwards (three selects instead
+	// of a divergent region)
+	float sf, cf;
+	float st = M::sqrt(1.0f - ct*ct);
+	M::sincos(fi, &sf, &cf);
+	const float stcf = st*cf, stsf = st*sf;
+	const float px = d.x, py = d.y, pz = d.z;
+	const bool polar = fabsf(pz) >= 1.0f;
+	const float k2 = fmaxf(fmaf(-pz, pz, 1.0f), 1e-30f);
+	const float ik = rsqrtf(k2);
+	float nx = (stcf*px*pz - stsf*py)*ik + px*ct;
+	float ny = (stcf*py*pz + stsf*px)*ik + py*ct;
+	float nz = pz*ct - stcf*(k2*ik);
+	nx = polar ? stcf : nx;
+	ny = polar ? stsf : ny;
+	nz = polar ? copysignf(ct, pz*ct) : nz;
+	const float k = rsqrtf(nx*nx + ny*ny + nz*nz);
+	d.x = nx*k; d.y = ny*k; d.z = nz*k;
+#endif
 }
 
 // ---- accumulators ------------------------------------------------------------
