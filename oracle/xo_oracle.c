@@ -90,6 +90,9 @@ typedef struct { m3f T; p2f position; float core_r_squared, core_spacing, cos_mi
 /* mcdetector/probe/lineararray.py:58-66 */
 typedef struct { m3f T; p2f first_position, delta_position; float core_r_squared, cos_min;
 	uint32_t offset; } det_linarray;
+/* mcdetector/probe/lineararraypl.py:66-78 */
+typedef struct { m3f T; p2f first_position, delta_position; float core_r_squared, cos_min,
+	pl_min, inv_dpl; uint32_t n_pl, offset; int32_t pl_log_scale; } det_linarraypl;
 typedef struct { p3f direction; p2f position; float r_min, inv_dr, pl_min, inv_dpl, cos_min;
 	uint32_t n_r, n_pl, offset; int32_t r_log_scale, pl_log_scale; } det_radialpl;
 typedef struct { p3f direction; float cos_min, pl_min, inv_dpl;
@@ -538,6 +541,61 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		float pz = Tf->a31*dir->x + Tf->a32*dir->y + Tf->a33*dir->z;
 		uint32_t w = weight_to_u32(weight, cmin[fiber_index] <= fabsf(pz));
 		if (w > 0) accu_deposit(s, offset + fiber_index, w);
+		break;
+	}
+	case XO_DET_LINEARARRAYPL: {                       /* mcdetector/probe/lineararraypl.py:118-190 */
+		const det_linarraypl *d = (const det_linarraypl *)base;
+		uint32_t n = (uint32_t)param, fiber_index = n;
+		float fiber_x = d->first_position.x, fiber_y = d->first_position.y;
+		p3f mc_pos, dp; float dx, dy, r2;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = pos->x - fiber_x; mc_pos.y = pos->y - fiber_y; mc_pos.z = FP_0;
+			m3f T = d->T;
+			transform3(&T, &mc_pos, &dp);
+			dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= d->core_r_squared) { fiber_index = index; break; }
+			fiber_x += d->delta_position.x;
+			fiber_y += d->delta_position.y;
+		}
+		if (fiber_index >= n) return;
+		float pl = s->opl;
+		if (d->pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		int32_t pl_index = (int32_t)((pl - d->pl_min)*d->inv_dpl);
+		pl_index = iclip(pl_index, 0, (int32_t)d->n_pl - 1);
+		float pz = d->T.a31*dir->x + d->T.a32*dir->y + d->T.a33*dir->z;
+		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(pz));
+		if (w > 0) accu_deposit(s, d->offset + (size_t)pl_index*n + fiber_index, w);
+		break;
+	}
+	case XO_DET_FIBERARRAYPL: {                        /* mcdetector/probe/fiberarraypl.py:110-185 */
+		/* packed: m3f T[n]; p2f core_position[n]; float core_r_squared[n], cos_min[n];
+		 * float pl_min, inv_dpl; u32 n_pl, offset; i32 pl_log_scale */
+		uint32_t n = (uint32_t)param, fiber_index = n;
+		const m3f *Ts = (const m3f *)base;
+		const p2f *cp = (const p2f *)(Ts + n);
+		const float *r2s = (const float *)(cp + n);
+		const float *cmin = r2s + n;
+		const float *tail = cmin + n;
+		float pl_min = tail[0], inv_dpl = tail[1];
+		uint32_t n_pl = ((const uint32_t *)tail)[2], offset = ((const uint32_t *)tail)[3];
+		int32_t pl_log_scale = ((const int32_t *)tail)[4];
+		p3f mc_pos, dp; float dx, dy, r2;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = pos->x - cp[index].x; mc_pos.y = pos->y - cp[index].y; mc_pos.z = FP_0;
+			m3f T = Ts[index];
+			transform3(&T, &mc_pos, &dp);
+			dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= r2s[index]) { fiber_index = index; break; }
+		}
+		if (fiber_index >= n) return;
+		float pl = s->opl;
+		if (pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		int32_t pl_index = (int32_t)((pl - pl_min)*inv_dpl);
+		pl_index = iclip(pl_index, 0, (int32_t)n_pl - 1);
+		const m3f *Tf = &Ts[fiber_index];
+		float pz = Tf->a31*dir->x + Tf->a32*dir->y + Tf->a33*dir->z;
+		uint32_t w = weight_to_u32(weight, cmin[fiber_index] <= fabsf(pz));
+		if (w > 0) accu_deposit(s, offset + (size_t)pl_index*n + fiber_index, w);
 		break;
 	}
 	case XO_DET_RADIALPL: {                            /* mcdetector/radialpl.py:138-180 */

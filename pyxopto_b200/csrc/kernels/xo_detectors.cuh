@@ -133,6 +133,61 @@ struct DetFiberArray {
 	}
 };
 
+// path-length resolved fiber arrays (probe/lineararraypl.py, fiberarraypl.py):
+// bins indexed [pl][fiber]
+__device__ __forceinline__ u32 pl_bin(float opl, float pl_min, float inv_dpl, u32 n_pl, i32 log_scale) {
+	float pl = opl;
+	if (log_scale) pl = M::log(fmaxf(pl, XO_FP_PLMIN));
+	return (u32)clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
+}
+
+template <int N>
+struct DetLinearArrayPl {
+	M3 T; P2 first_position, delta_position; float core_r_squared, cos_min, pl_min, inv_dpl;
+	u32 n_pl, offset; i32 pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		u32 fiber = N;
+		float fx = first_position.x, fy = first_position.y;
+#pragma unroll 1
+		for (u32 i = 0; i < (u32)N; ++i) {
+			P3 p = { pos.x - fx, pos.y - fy, 0.0f };
+			P3 q = transform3(T, p);
+			if (q.x*q.x + q.y*q.y <= core_r_squared) { fiber = i; break; }
+			fx += delta_position.x;
+			fy += delta_position.y;
+		}
+		if (fiber >= (u32)N) return;
+		u32 pi = pl_bin(opl, pl_min, inv_dpl, n_pl, pl_log_scale);
+		float pz = T.a31*dir.x + T.a32*dir.y + T.a33*dir.z;
+		u32 iw = weight_u32(w, cos_min <= fabsf(pz));
+		if (iw > 0) acc.add(offset + pi*(u32)N + fiber, iw);
+	}
+};
+
+template <int N>
+struct DetFiberArrayPl {
+	M3 T[N]; P2 core_position[N]; float core_r_squared[N], cos_min[N]; float pl_min, inv_dpl;
+	u32 n_pl, offset; i32 pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		u32 fiber = N;
+#pragma unroll 1
+		for (u32 i = 0; i < (u32)N; ++i) {
+			P3 p = { pos.x - core_position[i].x, pos.y - core_position[i].y, 0.0f };
+			P3 q = transform3(T[i], p);
+			if (q.x*q.x + q.y*q.y <= core_r_squared[i]) { fiber = i; break; }
+		}
+		if (fiber >= (u32)N) return;
+		u32 pi = pl_bin(opl, pl_min, inv_dpl, n_pl, pl_log_scale);
+		float pz = T[fiber].a31*dir.x + T[fiber].a32*dir.y + T[fiber].a33*dir.z;
+		u32 iw = weight_u32(w, cos_min[fiber] <= fabsf(pz));
+		if (iw > 0) acc.add(offset + pi*(u32)N + fiber, iw);
+	}
+};
+
 struct DetRadialPl {                // mcdetector/radialpl.py
 	P3 direction; P2 position; float r_min, inv_dr, pl_min, inv_dpl, cos_min;
 	u32 n_r, n_pl, offset; i32 r_log_scale, pl_log_scale;

@@ -15,7 +15,7 @@ import numpy as np
 
 from ..cl import clinfo, clrng, cltypes            # noqa: F401
 from ..mcbase import mcoptions, mctypes, mcobject  # noqa: F401
-from ..mcbase import mcsv                         # noqa: F401
+from ..mcbase import mcsv, mcprogress                         # noqa: F401
 from ..mcbase import mcpf, mcfluence, mctrace      # noqa: F401
 from ..mcbase.mcobject import McObject             # noqa: F401
 from ..mcbase.mcsim import McBase

@@ -499,6 +499,119 @@ class FiberArray(Detector):
         return FiberArray([FiberLayout.fromdict(f) for f in data.pop('fibers')])
 
 
+class LinearArrayPl(LinearArray):
+    """LinearArray resolved by optical path length; raw indexed [pl, fiber]
+    (probe/lineararraypl.py)."""
+    def cu_type(self, mc):
+        return 'xo::DetLinearArrayPl<{}>'.format(self._n)
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClLinearArrayPl(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t),
+                        ('first_position', T.mc_point2f_t),
+                        ('delta_position', T.mc_point2f_t),
+                        ('core_r_squared', T.mc_fp_t), ('cos_min', T.mc_fp_t),
+                        ('pl_min', T.mc_fp_t), ('inv_dpl', T.mc_fp_t),
+                        ('n_pl', T.mc_size_t), ('offset', T.mc_size_t),
+                        ('pl_log_scale', T.mc_int_t)]
+        return ClLinearArrayPl
+
+    def cl_options(self, mc):
+        return [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    def __init__(self, fiber, n: int = 1, spacing: float = None, plaxis=None,
+                 orientation=(1.0, 0.0), position=(0.0, 0.0), direction=(0.0, 0.0, 1.0)):
+        if isinstance(fiber, LinearArrayPl):
+            o = fiber
+            super().__init__(o.fiber, o.n, o.spacing, o.orientation, o.position, o.direction)
+            plaxis = type(o.plaxis)(o.plaxis)
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            super().__init__(fiber, n, spacing, orientation, position, direction)
+            if plaxis is None:
+                plaxis = Axis(0.0, 1.0, 1)
+            raw, nphotons = np.zeros((plaxis.n, self._n)), 0
+        self._raw_data, self._nphotons = raw, int(nphotons)
+        self._pl_axis = plaxis
+
+    plaxis = property(lambda self: self._pl_axis)
+    pl = property(lambda self: self._pl_axis.centers)
+    pledges = property(lambda self: self._pl_axis.edges)
+    npl = property(lambda self: self._pl_axis.n)
+
+    def cl_pack(self, mc, target=None):
+        target = super().cl_pack(mc, target)
+        target.pl_min, target.inv_dpl = self._pl_axis.scaled_start, _inv_step(self._pl_axis)
+        target.pl_log_scale, target.n_pl = self._pl_axis.logscale, self._pl_axis.n
+        return target
+
+    def todict(self):
+        d = super().todict()
+        d.update(type='LinearArrayPl', pl_axis=self._pl_axis.todict())
+        return d
+
+    @staticmethod
+    def fromdict(data):
+        data = dict(data)
+        if data.pop('type') != 'LinearArrayPl':
+            raise TypeError('Expected a "LinearArrayPl" type!')
+        pl = dict(data.pop('pl_axis'))
+        pl.pop('type', None)
+        return LinearArrayPl(MultimodeFiber.fromdict(data.pop('fiber')), plaxis=Axis(**pl), **data)
+
+
+class FiberArrayPl(FiberArray):
+    """FiberArray resolved by optical path length; raw indexed [pl, fiber]
+    (probe/fiberarraypl.py)."""
+    def cu_type(self, mc):
+        return 'xo::DetFiberArrayPl<{}>'.format(len(self._fibers))
+
+    def cl_type(self, mc):
+        T = mc.types
+        n = self.n
+        class ClFiberArrayPl(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t*n),
+                        ('core_position', T.mc_point2f_t*n),
+                        ('core_r_squared', T.mc_fp_t*n), ('cos_min', T.mc_fp_t*n),
+                        ('pl_min', T.mc_fp_t), ('inv_dpl', T.mc_fp_t),
+                        ('n_pl', T.mc_size_t), ('offset', T.mc_size_t),
+                        ('pl_log_scale', T.mc_int_t)]
+        return ClFiberArrayPl
+
+    def cl_options(self, mc):
+        return [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    def __init__(self, fibers, plaxis=None):
+        if isinstance(fibers, FiberArrayPl):
+            o = fibers
+            super().__init__(o.fibers)
+            plaxis = type(o.plaxis)(o.plaxis)
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            super().__init__(fibers)
+            if plaxis is None:
+                plaxis = Axis(0.0, 1.0, 1)
+            raw, nphotons = np.zeros((plaxis.n, len(self._fibers))), 0
+        self._raw_data, self._nphotons = raw, int(nphotons)
+        self._pl_axis = plaxis
+
+    plaxis = property(lambda self: self._pl_axis)
+    pl = property(lambda self: self._pl_axis.centers)
+    pledges = property(lambda self: self._pl_axis.edges)
+    npl = property(lambda self: self._pl_axis.n)
+
+    def cl_pack(self, mc, target=None):
+        target = super().cl_pack(mc, target)
+        target.pl_min, target.inv_dpl = self._pl_axis.scaled_start, _inv_step(self._pl_axis)
+        target.pl_log_scale, target.n_pl = self._pl_axis.logscale, self._pl_axis.n
+        return target
+
+    def todict(self):
+        return {'type': 'FiberArrayPl', 'fibers': [f.todict() for f in self._fibers],
+                'pl_axis': self._pl_axis.todict()}
+
+
 class RadialPl(Detector):
     """Radial x optical-path-length histogram; raw indexed [pl, r] (radialpl.py)."""
     cu_type = 'xo::DetRadialPl'

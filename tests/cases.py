@@ -602,3 +602,24 @@ for _name, _fn in (('mcml_hg_fiber_lineararray', mcml_hg_fiber_lineararray),
     ALL_CASES[_name] = _fn
     GEOMETRY[_name] = 'mcml'
     GOLDEN_RUN[_name] = (4000, 16)
+
+
+def mcml_hg_fiber_arrays_pl(mc, **kw):
+    """Path-length resolved fiber arrays: LinearArrayPl (top, log path-length
+    axis) and FiberArrayPl (bottom)."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    top = mc.mcdetector.LinearArrayPl(fib, 4, spacing=300e-6,
+                                      plaxis=Axis(1e-4, 1e-1, 12, logscale=True))
+    bottom = mc.mcdetector.FiberArrayPl(
+        [_fiber_layout(mc, fib, (0.0, 0.0, 0.0)), _fiber_layout(mc, fib, (0.4e-3, 0.1e-3, 0.0)),
+         _fiber_layout(mc, fib, (-0.4e-3, 0.0, 0.0))], plaxis=Axis(0.0, 30e-3, 15))
+    det = mc.mcdetector.Detectors(top=top, bottom=bottom, specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.9)), mc.mcsource.UniformFiber(fib), det,
+                 rnginit=959595, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hg_fiber_arrays_pl'] = mcml_hg_fiber_arrays_pl
+ALL_CASES['mcml_hg_fiber_arrays_pl'] = mcml_hg_fiber_arrays_pl
+GEOMETRY['mcml_hg_fiber_arrays_pl'] = 'mcml'
+GOLDEN_RUN['mcml_hg_fiber_arrays_pl'] = (6000, 16)
