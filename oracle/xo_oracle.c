@@ -78,6 +78,7 @@ typedef struct { m3f T; p3f position, direction; float radius, cos_min, n; } src
 typedef struct { m3f T; p3f position, direction; p2f radius; float reflectance; } src_ubeam_ml; /* mcsource/uniformbeam.py:36-47 */
 typedef struct { p3f position; uint32_t layer_index; } src_isopoint;
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip; } src_gauss_vox;  /* mcvox/mcsource/gaussianbeam.py:71-77 */
+typedef struct { p3f position; int32_t vx, vy, vz; } src_isovoxel;                    /* mcvox/mcsource/voxel.py:44-47 */
 typedef struct { p3f position; } src_isopoint_vox;                                  /* mcvox/mcsource/point.py:44-46 */
 
 typedef struct { p3f direction; float cos_min; uint32_t offset; } det_total;
@@ -118,6 +119,9 @@ typedef struct { p3f center; float t_min, inv_dr, inv_dz, inv_dt;
 	uint32_t n_r, n_z, n_t, offset; int32_t k; } flu_rzt;       /* mcfluence/fluencerzt.py:54 */
 typedef struct { p2f center; float r_min, fi_min, z_min, inv_dr, inv_dfi, inv_dz;
 	uint32_t n_r, n_fi, n_z, offset; int32_t k; } flu_cyl;       /* mcfluence/fluencecyl.py:56 */
+
+typedef struct { p2f center; float r_min, fi_min, z_min, t_min, inv_dr, inv_dfi, inv_dz, inv_dt;
+	uint32_t n_r, n_fi, n_z, n_t, offset; int32_t k; } flu_cylt;  /* mcfluence/fluencecylt.py:79 */
 
 typedef struct { int32_t max_events; uint32_t data_off, count_off, event_mask; } trace_cfg;
 
@@ -804,6 +808,24 @@ static void fluence_deposit_at(sim_t *s, const p3f *pos, float weight, float mua
 		}
 		break;
 	}
+	case XO_FLU_CYLT: {                                /* mcfluence/fluencecylt.py:151-204 */
+		const flu_cylt *f = (const flu_cylt *)j->fluence;
+		float dx = pos->x - f->center.x, dy = pos->y - f->center.y;
+		float r = m_sqrt(dx*dx + dy*dy);
+		float fi = m_atan2(s, dy, dx) + FP_PI;
+		float dt = s->opl*FP_INV_C - f->t_min;
+		float fr = (r - f->r_min)*f->inv_dr, fz = (pos->z - f->z_min)*f->inv_dz;
+		float ffi = (fi - f->fi_min)*f->inv_dfi, ft = dt*f->inv_dt;
+		if (fr >= 0 && fz >= 0 && ffi >= 0 && ft >= 0 && fr < f->n_r && fz < f->n_z &&
+				ffi < f->n_fi && ft < f->n_t) {
+			uint32_t ir = (uint32_t)fr, iz = (uint32_t)fz, ifi = (uint32_t)ffi, it = (uint32_t)ft;
+			uint32_t index = ((iz*f->n_fi + ifi)*f->n_r + ir)*f->n_t + it;
+			if (j->fluence_rate) weight *= (mua != FP_0) ? m_div(FP_1, mua) : FP_0;
+			uint32_t w = (uint32_t)(weight*f->k + FP_0p5);
+			accu_deposit(s, f->offset + index, w);
+		}
+		break;
+	}
 	default: break;
 	}
 }
@@ -945,6 +967,41 @@ static void launch_mcml(sim_t *s) {
 		s->layer_index = 1;
 		break;
 	}
+	case XO_SRC_LAMBERTIANFIBER: {                     /* mcsource/fiber.py:567-632 */
+		const src_ufiber *src = (const src_ufiber *)j->source;    /* cos_min slot holds na */
+		float sin_fi, cos_fi, sin_theta, cos_theta; p3f pt_src, pt_mc;
+		float r = m_sqrt(sim_random(s))*src->radius;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		pt_src.x = r*cos_fi; pt_src.y = r*sin_fi; pt_src.z = FP_0;
+		m3f T = src->T;
+		transform3(&T, &pt_src, &pt_mc);
+		float k = m_div(FP_0 - pt_mc.z, src->direction.z);
+		pt_mc.x += k*src->direction.x;
+		pt_mc.y += k*src->direction.y;
+		pt_mc.z = FP_0;
+		s->pos.x = src->position.x + pt_mc.x;
+		s->pos.y = src->position.y + pt_mc.y;
+		s->pos.z = FP_0;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		sin_theta = m_sqrt(sim_random(s))*src->cos_min;
+		sin_theta = m_div(sin_theta, src->n);
+		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+		pt_src.x = cos_fi*sin_theta; pt_src.y = sin_fi*sin_theta; pt_src.z = cos_theta;
+		p3f direction;
+		transform3(&T, &pt_src, &direction);
+		float cc = cos_critical(src->n, medium_n(j, 1));
+		p3f normal = { FP_0, FP_0, FP_1 };
+		p3f refracted = direction;
+		if (pt_mc.z > cc)             /* never true: pt_mc.z == 0 */
+			refract3(&pt_mc, &normal, src->n, medium_n(j, 1), &refracted);
+		s->dir = refracted;
+		float specular_r = reflectance(src->n, medium_n(j, 1), direction.z, cc);
+		s->weight = FP_1 - specular_r;
+		if (j->det_kind[LOC_SPECULAR])
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &direction, specular_r);
+		s->layer_index = 1;
+		break;
+	}
 	case XO_SRC_ISOTROPICPOINT: {                      /* mcsource/point.py:76-135 */
 		const src_isopoint *src = (const src_isopoint *)j->source;
 		float sin_fi, cos_fi, sin_theta, cos_theta, specular_r = FP_0;
@@ -987,6 +1044,7 @@ static inline p3f source_position(const xo_oracle_job *j) {
 	switch (j->src_kind) {
 		case XO_SRC_GAUSSIANBEAM: off = sizeof(m3f); break;
 		case XO_SRC_UNIFORMFIBER: off = sizeof(m3f); break;
+		case XO_SRC_LAMBERTIANFIBER: off = sizeof(m3f); break;
 		case XO_SRC_UNIFORMBEAM: off = sizeof(m3f); break;
 		default: off = 0; break;
 	}

@@ -20,7 +20,8 @@ enum { XO_PF_HG = 1, XO_PF_MHG = 2, XO_PF_GK = 3, XO_PF_LUT = 4, XO_PF_HG2 = 5,
 	XO_PF_GK2 = 6, XO_PF_MGK = 7, XO_PF_PC = 8, XO_PF_MPC = 9 };
 enum {
 	XO_SRC_LINE = 1, XO_SRC_GAUSSIANBEAM = 2, XO_SRC_UNIFORMFIBER = 3,
-	XO_SRC_ISOTROPICPOINT = 4, XO_SRC_UNIFORMBEAM = 5
+	XO_SRC_ISOTROPICPOINT = 4, XO_SRC_UNIFORMBEAM = 5, XO_SRC_LAMBERTIANFIBER = 6,
+	XO_SRC_ISOTROPICVOXEL = 7
 };
 enum {
 	XO_DET_NONE = 0, XO_DET_TOTAL = 1, XO_DET_RADIAL = 2, XO_DET_CARTESIAN = 3,
@@ -31,7 +32,7 @@ enum {
 };
 enum {
 	XO_FLU_NONE = 0, XO_FLU_XYZ = 1, XO_FLU_RZ = 2, XO_FLU_XYZT = 3,
-	XO_FLU_RZT = 4, XO_FLU_CYL = 5
+	XO_FLU_RZT = 4, XO_FLU_CYL = 5, XO_FLU_CYLT = 6
 };
 enum { XO_SURF_NONE = 0, XO_SURF_LAMBERTIAN = 1, XO_SURF_SIXAROUNDONE = 2 };
 enum { XO_TRACE_NONE = 0, XO_TRACE_START = 1, XO_TRACE_END = 2, XO_TRACE_ALL = 7 };

@@ -27,7 +27,8 @@ MATH_LIBM, MATH_PORTABLE = 0, 1
 PF_KIND = {'Hg': 1, 'MHg': 2, 'Gk': 3, 'Lut': 4, 'LutEx': 4, 'Hg2': 5, 'Gk2': 6,
            'MGk': 7, 'Pc': 8, 'MPc': 9}
 SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
-            'IsotropicPoint': 4, 'UniformBeam': 5}
+            'IsotropicPoint': 4, 'UniformBeam': 5, 'LambertianFiber': 6,
+            'IsotropicVoxel': 7}
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
             'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10,
@@ -36,7 +37,7 @@ DET_KIND_TOTAL_CYL = 11
 SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
              'SixAroundOne': 2}
 FLU_KIND = {'NoneType': 0, 'Fluence': 1, 'FluenceRz': 2, 'Fluencet': 3,
-            'FluenceRzt': 4, 'FluenceCyl': 5}
+            'FluenceRzt': 4, 'FluenceCyl': 5, 'FluenceCylt': 6}
 
 
 class Job(ctypes.Structure):
@@ -206,7 +207,7 @@ def describe(mc_obj, geometry: str) -> dict:
         d['fluence_rate'] = int(flu.mode == 'fluence')
     tr = mc_obj.trace
     track_opl = any(k in (5, 6, 9, 10, 14, 15) for k in det_kind) or \
-        d['fluence_kind'] in (3, 4)
+        d['fluence_kind'] in (3, 4, 6)
     if tr is not None:
         d['trace'] = _raw(P['trace'])
         d['trace_flags'] = int(tr.options)

@@ -179,4 +179,27 @@ struct VoxSrcIsotropicPoint {       // mcvox/mcsource/point.py:44-46
 	}
 };
 
+// mcvox/mcsource/voxel.py:31-110: a uniformly random point of one voxel, isotropic
+// direction, no surface passage (weight 1, nothing for the specular detector)
+struct VoxSrcIsotropicVoxel {
+	P3 position; i32 vx, vy, vz;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		const float lim = 1.0f - 1.1920928955078125e-07f;      // FP_1 - FP_EPS
+		L.pos.x = ((float)vx + fminf(rng.next(), lim))*ctx.cfg.size.x + ctx.cfg.top_left.x;
+		L.pos.y = ((float)vy + fminf(rng.next(), lim))*ctx.cfg.size.y + ctx.cfg.top_left.y;
+		L.pos.z = ((float)vz + fminf(rng.next(), lim))*ctx.cfg.size.z + ctx.cfg.top_left.z;
+		float sf, cf;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 1.0f - 2.0f*rng.next();
+		float st = M::sqrt(1.0f - ct*ct);
+		L.dir.x = cf*st; L.dir.y = sf*st; L.dir.z = ct;
+		L.weight = 1.0f;
+		L.spec_dir = L.dir;
+		L.spec_weight = 0.0f;
+	}
+};
+
 }  // namespace xo

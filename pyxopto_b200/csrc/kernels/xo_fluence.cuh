@@ -275,6 +275,38 @@ struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
 	}
 };
 
+struct FluCylt {                    // mcfluence/fluencecylt.py:79-95
+	P2 center; float r_min, fi_min, z_min, t_min, inv_dr, inv_dfi, inv_dz, inv_dt;
+	u32 n_r, n_fi, n_z, n_t, offset; i32 k;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
+	struct Prep { };
+	struct Far { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
+	__device__ __forceinline__ void deposit_prep(const Accu &acc, const Prep &, const FluWindow &win, const P3 &pos, u32 wfix, float opl) const {
+		deposit_fixed(acc, win, pos, wfix, opl);
+	}
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &win, const P3 &pos, float w, float mua, float opl) const {
+		deposit_fixed(acc, win, pos, fluence_weight(w, mua, k), opl);
+	}
+	__device__ __forceinline__ float fixed_scale(float mua) const { return fluence_scale(mua, k); }
+	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &, const P3 &pos, u32 wfix, float opl) const {
+		float dx = pos.x - center.x, dy = pos.y - center.y;
+		float r = M::sqrt(dx*dx + dy*dy);
+		float fi = M::atan2(dy, dx) + 3.141592653589793f;
+		float dt = opl*XO_FP_INV_C - t_min;
+		float fr = (r - r_min)*inv_dr, fz = (pos.z - z_min)*inv_dz;
+		float ffi = (fi - fi_min)*inv_dfi, ft = dt*inv_dt;
+		if (fr >= 0.0f && fz >= 0.0f && ffi >= 0.0f && ft >= 0.0f &&
+				fr < (float)n_r && fz < (float)n_z && ffi < (float)n_fi && ft < (float)n_t) {
+			u32 index = ((f2u(fz)*n_fi + f2u(ffi))*n_r + f2u(fr))*n_t + f2u(ft);
+			acc.add_global(offset + index, wfix);
+		}
+	}
+};
+
 // ---- trace ------------------------------------------------------------------
 #ifndef XO_TRACE
 #define XO_TRACE 0

@@ -404,6 +404,62 @@ class FluenceCyl(_FluenceBase):
                 'center': self._center.tolist()}
 
 
+class FluenceCylt(FluenceCyl):
+    """Time-resolved cylindrical grid; raw shape (n_z, n_fi, n_r, n_t)
+    (mcfluence/fluencecylt.py).  Time = optical path length / c."""
+    cu_type = 'xo::FluCylt'
+    _extra_options = [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClFluenceCylt(cltypes.Structure):
+            _fields_ = [('center', T.mc_point2f_t), ('r_min', T.mc_fp_t),
+                        ('fi_min', T.mc_fp_t), ('z_min', T.mc_fp_t), ('t_min', T.mc_fp_t),
+                        ('inv_dr', T.mc_fp_t), ('inv_dfi', T.mc_fp_t), ('inv_dz', T.mc_fp_t),
+                        ('inv_dt', T.mc_fp_t),
+                        ('n_r', T.mc_size_t), ('n_fi', T.mc_size_t), ('n_z', T.mc_size_t),
+                        ('n_t', T.mc_size_t), ('offset', T.mc_size_t), ('k', T.mc_int_t)]
+        return ClFluenceCylt
+
+    def __init__(self, raxis=None, fiaxis: Axis = None, zaxis: Axis = None,
+                 taxis: Axis = None, center: Tuple[float, float] = (0.0, 0.0),
+                 mode: str = 'deposition'):
+        if isinstance(raxis, FluenceCylt):
+            taxis = Axis(raxis.taxis)
+        taxis = Axis(0.0, 1.0, 1) if taxis is None else taxis
+        if taxis.logscale:
+            raise ValueError('FluenceCylt does not support logarithmic axes!')
+        self._t_axis = taxis
+        super().__init__(raxis, fiaxis, zaxis, center, mode)
+
+    shape = property(lambda self: (self._z_axis.n, self._fi_axis.n, self._r_axis.n,
+                                   self._t_axis.n))
+    taxis = property(lambda self: self._t_axis)
+    t = property(lambda self: self._t_axis.centers)
+    dt = property(lambda self: abs(self._t_axis.step))
+
+    @property
+    def data(self):
+        r = self._r_axis.edges
+        k = 1.0/(self.nphotons*(r[1:]**2 - r[:-1]**2)*abs(self._fi_axis.step) *
+                 abs(self._z_axis.step)*self.dt)
+        k.shape = (1, 1, k.size, 1)
+        return self._data*k
+
+    def cl_pack(self, mc, target=None):
+        target = super().cl_pack(mc, target)
+        target.t_min = self._t_axis.start
+        target.inv_dt = 1.0/self._t_axis.step
+        target.n_t = self._t_axis.n
+        return target
+
+    def todict(self):
+        d = super().todict()
+        d.update(type='FluenceCylt', taxis=self._t_axis.todict())
+        return d
+
+
 class Fluencet(_FluenceBase):
     """Time-resolved x-y-z-t grid; raw shape (nz, ny, nx, nt) (mcfluence/fluencet.py).
     Time = optical path length / c, so the kernel tracks the optical path length."""

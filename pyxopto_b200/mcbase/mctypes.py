@@ -14,9 +14,10 @@ from ..cl import cltypes
 
 class _Vec(cltypes.Structure):
     def fromarray(self, array):
-        flat = np.asarray(array, dtype=np.float64).ravel()
-        for (name, _), value in zip(self._fields_, flat):
-            setattr(self, name, value)
+        flat = np.asarray(array).ravel()
+        for (name, ctype), value in zip(self._fields_, flat):
+            integer = ctype not in (ctypes.c_float, ctypes.c_double)
+            setattr(self, name, int(value) if integer else float(value))
         return self
 
     def toarray(self) -> np.ndarray:

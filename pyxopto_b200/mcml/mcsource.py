@@ -292,6 +292,32 @@ class UniformFiber(Source):
                 'direction': self._direction.tolist(), 'type': type(self).__name__}
 
 
+class LambertianFiber(UniformFiber):
+    """Optical fiber emitting a lambertian beam within the NA (mcsource/fiber.py:499-688)."""
+    cu_type = 'xo::SrcLambertianFiber'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClLambertianFiber(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('na', T.mc_fp_t), ('n', T.mc_fp_t)]
+        return ClLambertianFiber
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.n = self._fiber.ncore
+        target.na = self._fiber.na
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+
 class IsotropicPoint(Source):
     """Isotropic point source above or inside the sample (mcsource/point.py)."""
     cu_type = 'xo::SrcIsotropicPoint'

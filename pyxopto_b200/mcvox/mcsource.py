@@ -261,3 +261,39 @@ class IsotropicPoint(Source):
 
     def todict(self):
         return {'position': self._position.tolist(), 'type': type(self).__name__}
+
+
+class IsotropicVoxel(Source):
+    """Isotropic emission from random points of one voxel (mcvox/mcsource/voxel.py:31-193)."""
+    cu_type = 'xo::VoxSrcIsotropicVoxel'
+    cu_refill_lanes = 6
+    _update_keys = ('voxel',)
+
+    @staticmethod
+    def cl_type(mc):
+        class ClIsotropicVoxel(cltypes.Structure):
+            _fields_ = [('position', mc.types.mc_point3f_t), ('voxel', mc.types.mc_point3_t)]
+        return ClIsotropicVoxel
+
+    def __init__(self, voxel=(0, 0, 0)):
+        super().__init__()
+        self._voxel = np.zeros((3,), dtype=np.int32)
+        self.voxel = voxel
+
+    def _set_voxel(self, voxel):
+        self._voxel[:] = voxel
+
+    voxel = property(lambda self: self._voxel, _set_voxel, None,
+                     'Source voxel indices (ind_x, ind_y, ind_z).')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        if not mc.voxels.isvalid(self._voxel):
+            raise ValueError('Voxel index ({}, {}, {}) is not valid!'.format(*self._voxel))
+        target.voxel.fromarray(self._voxel)
+        target.position.fromarray(mc.voxels.center(self._voxel))
+        return target, None, None
+
+    def todict(self):
+        return {'voxel': self._voxel.tolist(), 'type': type(self).__name__}

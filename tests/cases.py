@@ -623,3 +623,59 @@ MCML_CASES['mcml_hg_fiber_arrays_pl'] = mcml_hg_fiber_arrays_pl
 ALL_CASES['mcml_hg_fiber_arrays_pl'] = mcml_hg_fiber_arrays_pl
 GEOMETRY['mcml_hg_fiber_arrays_pl'] = 'mcml'
 GOLDEN_RUN['mcml_hg_fiber_arrays_pl'] = (6000, 16)
+
+
+def mcml_hg_fiber_fluencecylt(mc, **kw):
+    """Time-resolved cylindrical deposition grid (FluenceCylt)."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceCylt(Axis(0, 2e-3, 10), Axis(0, 2*np.pi, 6), Axis(0, 3e-3, 15),
+                                   Axis(0, 40e-12, 8), center=(0.05e-3, -0.05e-3))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)),
+                 mc.mcsource.UniformFiber(fib, position=(0.1e-3, 0, 0), direction=(0.2, 0.1, 1)),
+                 det, fluence=flu, rnginit=80808, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hg_fiber_fluencecylt'] = mcml_hg_fiber_fluencecylt
+ALL_CASES['mcml_hg_fiber_fluencecylt'] = mcml_hg_fiber_fluencecylt
+GEOMETRY['mcml_hg_fiber_fluencecylt'] = 'mcml'
+GOLDEN_RUN['mcml_hg_fiber_fluencecylt'] = (2000, 16)
+
+
+def mcml_mhg_lambertianfiber_radial(mc, **kw):
+    """Tilted LambertianFiber source (mcsource/fiber.py:499), radial detectors."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 50)),
+                                  bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.8, 0.7)),
+                 mc.mcsource.LambertianFiber(fib, position=(0.2e-3, -0.1e-3, 0),
+                                             direction=(0.1, -0.2, 1)),
+                 det, rnginit=171717, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_mhg_lambertianfiber_radial'] = mcml_mhg_lambertianfiber_radial
+ALL_CASES['mcml_mhg_lambertianfiber_radial'] = mcml_mhg_lambertianfiber_radial
+GEOMETRY['mcml_mhg_lambertianfiber_radial'] = 'mcml'
+GOLDEN_RUN['mcml_mhg_lambertianfiber_radial'] = (3000, 16)
+
+
+def mcvox_isovoxel_fluence(mc, **kw):
+    """IsotropicVoxel source inside the vessel (mcvox/mcsource/voxel.py), deposition
+    grid and radial / total detectors."""
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc)
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(A(0, 0.4e-3, 20)), bottom=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg), mc.mcsource.IsotropicVoxel((13, 9, 12)),
+                detectors=det, fluence=flu, rnginit=363636, **kw)
+    return _fill_skin_vessel(sim), dict(rmax=25e-3)
+
+
+MCVOX_CASES['mcvox_isovoxel_fluence'] = mcvox_isovoxel_fluence
+ALL_CASES['mcvox_isovoxel_fluence'] = mcvox_isovoxel_fluence
+GEOMETRY['mcvox_isovoxel_fluence'] = 'mcvox'
+GOLDEN_RUN['mcvox_isovoxel_fluence'] = (2000, 16)

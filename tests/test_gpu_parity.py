@@ -90,7 +90,10 @@ def test_deterministic_mode_bit_exact(name):
                                   'mcml_gk_fiber_six_flu', 'mcml_surface_six_lambert',
                                   'mcml_surface_lambert_top', 'mcvox_gauss_fluence',
                                   'mccyl_hg_line_fiz', 'mccyl_mhg_gauss_total_flurz',
-                                  'mccyl_hg_isopoint_outside'])
+                                  'mccyl_hg_isopoint_outside', 'mcvox_isovoxel_fluence',
+                                  'mcml_mhg_lambertianfiber_radial', 'mcml_hg_fiber_lineararray',
+                                  'mcml_mhg_line_fiberarray', 'mcml_hg_fiber_arrays_pl',
+                                  'mcml_hg_fiber_fluencecylt'])
 def test_throughput_mode_statistics(name):
     """Fast mode vs oracle (libm, different schedule): totals within 4 sigma."""
     sim, geom, _ = build_sim(name)
