@@ -164,7 +164,19 @@ static inline float rng_next(uint64_t *x, uint32_t a) {
 	*x = (*x & 0xFFFFFFFFull)*a + (*x >> 32);
 	return (float)(uint32_t)*x / (float)0xFFFFFFFFu;
 }
-static inline float sim_random(sim_t *s) { return rng_next(&s->rng_x, s->rng_a); }
+/* MC_USE_ENHANCED_RNG (mcbase.template.c:1577-1586): two steps, 64 random bits,
+ * (float)u64 / (float)0xFFFFFFFFFFFFFFFF (the divisor rounds to 2^64) */
+static inline float rng_next_enhanced(uint64_t *x, uint32_t a) {
+	*x = (*x & 0xFFFFFFFFull)*a + (*x >> 32);
+	uint32_t high = (uint32_t)*x;
+	*x = (*x & 0xFFFFFFFFull)*a + (*x >> 32);
+	uint32_t low = (uint32_t)*x;
+	return (float)((((uint64_t)high) << 32) + low) / (float)0xFFFFFFFFFFFFFFFFull;
+}
+static inline float sim_random(sim_t *s) {
+	return s->job->enhanced_rng ? rng_next_enhanced(&s->rng_x, s->rng_a)
+		: rng_next(&s->rng_x, s->rng_a);
+}
 
 void xo_oracle_rng_test(uint64_t x, uint32_t a, uint32_t n, float *out) {
 	for (uint32_t i = 0; i < n; ++i) out[i] = rng_next(&x, a);

@@ -58,6 +58,7 @@ typedef struct xo_oracle_job {
 	int32_t track_opl;         /* MC_TRACK_OPTICAL_PATHLENGTH */
 	int32_t surf_kind[2];      /* top, bottom surface layout (mcml) */
 	int32_t surf_offset[2];    /* byte offsets inside the packed McSurfaceLayouts */
+	int32_t enhanced_rng;      /* MC_USE_ENHANCED_RNG: two MWC steps per draw (mcbase.template.c:1577-1586) */
 
 	/* run-time kernel arguments (mcml.template.c:346-376, mcvox.template.c:548) */
 	uint32_t num_packets;

@@ -53,6 +53,7 @@ class Job(ctypes.Structure):
         ('trace_flags', ctypes.c_int32), ('use_events', ctypes.c_int32),
         ('track_opl', ctypes.c_int32),
         ('surf_kind', ctypes.c_int32*2), ('surf_offset', ctypes.c_int32*2),
+        ('enhanced_rng', ctypes.c_int32),
         ('num_packets', ctypes.c_uint32), ('num_threads', ctypes.c_uint32),
         ('rmax', ctypes.c_float), ('num_layers', ctypes.c_uint32),
         ('layers', ctypes.c_void_p), ('voxel_cfg', ctypes.c_void_p),
@@ -191,6 +192,8 @@ def describe(mc_obj, geometry: str) -> dict:
             det_par[i] = int(getattr(det, 'n', 0) or 0) if det_kind[i] in (12, 13, 14, 15) else 0
         d['detectors'] = _raw(P['detectors'])
     d['det_kind'], d['det_offset'], d['det_param'] = det_kind, det_off, det_par
+    if hasattr(mc_obj, 'resolved_options'):
+        d['enhanced_rng'] = int(bool(mc_obj.resolved_options().get('MC_USE_ENHANCED_RNG', False)))
     surf = getattr(mc_obj, 'surface', None)
     d['surf_kind'], d['surf_offset'] = [0, 0], [0, 0]
     if surf is not None and geometry == 'mcml':
@@ -260,6 +263,7 @@ def run(desc: dict, nphotons: int, nthreads: int, rng_x: np.ndarray,
     job.trace_flags = desc.get('trace_flags', 0)
     job.use_events = desc.get('use_events', 0)
     job.track_opl = desc.get('track_opl', 0)
+    job.enhanced_rng = int(desc.get('enhanced_rng', 0))
     job.num_packets = int(nphotons)
     job.num_threads = int(nthreads)
     job.rmax = np.float32(desc['rmax'])

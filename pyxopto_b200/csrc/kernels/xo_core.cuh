@@ -73,6 +73,10 @@ __device__ __forceinline__ float signf(float x) { return (x >= 0.0f) ? 1.0f : -1
 __device__ __forceinline__ i32 f2i(float x) { return __float2int_rz(x); }
 __device__ __forceinline__ u32 f2u(float x) { return __float2uint_rz(x); }
 
+#ifndef XO_ENHANCED_RNG
+#define XO_ENHANCED_RNG 0
+#endif
+
 // ---- RNG: 64-bit multiply-with-carry, state in registers -------------------
 // Same recurrence and float mapping as fp_random_single (mcbase.template.c:1576):
 //   x <- lo32(x)*a + hi32(x);  u = RN(float(lo32(x))) / RN(float(0xFFFFFFFF)) = RN(float(lo32 x))*2^-32
@@ -106,6 +110,17 @@ struct Rng {
 			"}" : "+r"(lo), "+r"(hi) : "r"(a));
 	}
 #endif
+#if XO_ENHANCED_RNG
+	// MC_USE_ENHANCED_RNG (mcbase.template.c:1577-1586): two steps per draw,
+	// u = RN(float(u64)) * 2^-64 (the reference's divisor rounds to 2^64)
+	__device__ __forceinline__ float next() {
+		step();
+		const u32 high = low();
+		step();
+		return __ull2float_rn(((u64)high << 32) + low())*5.421010862427522e-20f;
+	}
+	__device__ __forceinline__ float next_raw() { return next()*4294967296.0f; }
+#else
 	__device__ __forceinline__ float next() {
 		step();
 		return __uint2float_rn(low())*2.3283064365386963e-10f;
@@ -116,6 +131,7 @@ struct Rng {
 		step();
 		return __uint2float_rn(low());
 	}
+#endif
 };
 #define XO_RNG_SCALE 2.3283064365386963e-10f
 

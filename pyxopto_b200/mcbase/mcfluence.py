@@ -46,7 +46,7 @@ class _FluenceBase(McObject):
     def update_data(self, mc, data, nphotons, **kwargs):
         accumulators = data[np.dtype(mc.types.np_accu)]
         if self._data is not None:
-            self._data.flat += accumulators[0]*(1.0/self.k)
+            self._data += np.reshape(accumulators[0], self._data.shape)*(1.0/self.k)
             self._nphotons += nphotons
         else:
             self._data = accumulators[0]*(1.0/self.k)

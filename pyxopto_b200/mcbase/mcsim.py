@@ -178,15 +178,16 @@ class McBase(CuWorker):
     def kernel_source(self, block: int = DEFAULT_BLOCK, min_blocks: int = 1) -> str:
         """The CUDA translation unit for the current plugin set / options."""
         opts = self.resolved_options()
-        if opts.get('MC_USE_ENHANCED_RNG') or opts.get('MC_USE_DOUBLE_PRECISION'):
-            raise NotImplementedError('Enhanced RNG / double precision kernels '
-                                      'are not part of the accelerated path.')
+        if opts.get('MC_USE_DOUBLE_PRECISION'):
+            raise NotImplementedError('Double precision kernels are not part of the '
+                                      'accelerated path.')
         trace_flags = int(opts.get('MC_USE_TRACE', 0))
         lines = [
             '// generated by pyxopto_b200 ({})'.format(self.geometry),
             '#define XO_DETERMINISTIC {}'.format(int(bool(opts.get('XO_DETERMINISTIC', False)))),
             '#define XO_METHOD {}'.format(int(opts.get('MC_METHOD', 0))),
             '#define XO_USE_LOTTERY {}'.format(int(bool(opts.get('MC_USE_LOTTERY', True)))),
+            '#define XO_ENHANCED_RNG {}'.format(int(bool(opts.get('MC_USE_ENHANCED_RNG', False)))),
             '#define XO_WEIGHT_MIN {}'.format(_c_float(opts.get('MC_PACKET_WEIGHT_MIN', 1e-4))),
             '#define XO_LOTTERY_CHANCE {}'.format(
                 _c_float(opts.get('MC_PACKET_LOTTERY_CHANCE', 0.1))),
@@ -385,6 +386,7 @@ class McBase(CuWorker):
         return tuple(float(v) for v in np.asarray(pos, dtype=np.float64).reshape(-1)[:3])
 
     fluence_window_bytes = None      # None: automatic
+    max_batch = 0xFFFFFFFF           # packets per kernel launch (32-bit device counter)
     fluence_block = FLUENCE_BLOCK
 
     def _window_enabled(self) -> bool:
@@ -466,10 +468,28 @@ class McBase(CuWorker):
         result objects like the reference (mc.py:730-1018); with ``out`` the new
         data are accumulated into the given previous results."""
         nphotons = int(nphotons)
-        if nphotons > self._types.mc_cnt_max or nphotons > 0xFFFFFFFF:
+        if nphotons > self._types.mc_cnt_max:
             raise ValueError('Maximum number of photon packets that can be '
                              'simulated in a single run is limited to {:,d}!'.format(
-                                 min(self._types.mc_cnt_max, 0xFFFFFFFF)))
+                                 self._types.mc_cnt_max))
+        if nphotons > self.max_batch:
+            # 64-bit packet counter family (McDataTypesSingleCnt64): the device
+            # counter stays 32 bits wide, the host runs the budget in batches that
+            # continue the MWC streams and accumulates the results (`out=`); the
+            # integer accumulators make the sum exact
+            if self._trace is not None:
+                raise ValueError('A traced run is limited to {:,d} packets!'.format(self.max_batch))
+            if not (download and synchronize):
+                raise ValueError('Runs of more than {:,d} packets need download=True, '
+                                 'synchronize=True'.format(self.max_batch))
+            remaining, results = nphotons, out
+            while remaining > 0:
+                batch = min(remaining, self.max_batch)
+                results = self.run(batch, out=results, wgsize=wgsize, maxthreads=maxthreads,
+                                   copyseeds=copyseeds, exportsrc=exportsrc, verbose=verbose)
+                remaining -= batch
+            self._run_report['items'] = nphotons
+            return results
         t0 = time.perf_counter()
         self._ensure_device()
         self._device_trace = None        # rows of the previous run are overwritten

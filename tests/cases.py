@@ -679,3 +679,21 @@ MCVOX_CASES['mcvox_isovoxel_fluence'] = mcvox_isovoxel_fluence
 ALL_CASES['mcvox_isovoxel_fluence'] = mcvox_isovoxel_fluence
 GEOMETRY['mcvox_isovoxel_fluence'] = 'mcvox'
 GOLDEN_RUN['mcvox_isovoxel_fluence'] = (2000, 16)
+
+
+def mcml_mhg_gauss_enhanced_rng(mc, **kw):
+    """MC_USE_ENHANCED_RNG: two MWC steps (64 random bits) per uniform draw."""
+    Axis = mc.mcdetector.Axis
+    opts = list(kw.pop('options', None) or []) + [mc.mcoptions.McUseEnhancedRng.on]
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 50)),
+                                  bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceRz(Axis(0, 2e-3, 20), Axis(0, 3e-3, 30))
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.8, 0.9)), mc.mcsource.GaussianBeam(100e-6), det,
+                 fluence=flu, rnginit=191919, options=opts, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_mhg_gauss_enhanced_rng'] = mcml_mhg_gauss_enhanced_rng
+ALL_CASES['mcml_mhg_gauss_enhanced_rng'] = mcml_mhg_gauss_enhanced_rng
+GEOMETRY['mcml_mhg_gauss_enhanced_rng'] = 'mcml'
+GOLDEN_RUN['mcml_mhg_gauss_enhanced_rng'] = (2000, 16)

@@ -16,9 +16,9 @@ from helpers import build_sim, golden, run_size
 pytestmark = pytest.mark.gpu
 
 
-def _det_sim(name):
+def _det_sim(name, **kw):
     from pyxopto_b200.mcbase import mcoptions
-    return build_sim(name, options=[mcoptions.McDeterministic.on])
+    return build_sim(name, options=[mcoptions.McDeterministic.on], **kw)
 
 
 def test_library_sees_a_b200():
@@ -458,3 +458,25 @@ def test_user_fragments_match_reference_kernel(name):
             tot_ref = g['accu'][al.offset:al.offset + al.size].sum()/K/n
             sigma = np.sqrt(max(tot_ref, 1e-6)*(1.0/n + 1.0/n_fast))*np.sqrt(2)
             assert abs(tot_gpu - tot_ref) <= 4*sigma + 1e-5, (type(det).__name__, tot_gpu, tot_ref)
+
+
+def test_runs_above_the_device_counter_are_batched_exactly():
+    """McDataTypesSingleCnt64: a budget above ``max_batch`` is run in batches that
+    continue the MWC streams; in deterministic mode the accumulated result equals
+    the sum of the same batches run one by one (integer accumulators), and the
+    enhanced (two-step) RNG takes part."""
+    from pyxopto_b200.mcbase import mctypes
+    a = _det_sim('mcml_mhg_gauss_enhanced_rng', types=mctypes.McDataTypesSingleCnt64)[0]
+    b = _det_sim('mcml_mhg_gauss_enhanced_rng', types=mctypes.McDataTypesSingleCnt64)[0]
+    a.max_batch = 3000
+    kw = dict(maxthreads=256, wgsize=64)
+    _, flu_a, det_a = a.run(8000, **kw)            # 3000 + 3000 + 2000
+    out = None
+    for n in (3000, 3000, 2000):
+        out = b.run(n, out=out, **kw)
+    _, flu_b, det_b = out
+    assert det_a.top.nphotons == 8000 and flu_a.nphotons == 8000
+    assert np.array_equal(det_a.top.raw, det_b.top.raw) and det_a.top.raw.sum() > 0
+    assert np.array_equal(flu_a.raw, flu_b.raw) and flu_a.raw.sum() > 0
+    with pytest.raises(ValueError):
+        _det_sim('mcml_mhg_gauss_enhanced_rng')[0].run(2**33)
