@@ -340,6 +340,18 @@ def main():
             'sfu': {'achieved': achieved_sfu/1e9, 'peak': sfu_peak/1e9,
                     'frac': achieved_sfu/sfu_peak},
             'atomics_per_s': (iter_per_launch/(k_ms*1e-3) if config == 'c2_skin' else None),
+            # accumulator ("atomic") roofline, SURVEY 8d: deposits per second against
+            # the rate measured with tools/atomic_probe.cu on B200 (shared-memory
+            # window of C2: > 1.2e12 /s; RED.E.ADD.64 to a 65 MB grid in L2, uniform:
+            # 1.8e11 /s); deposits per iteration = 1 (C2, AW) / 0.15 (C3, oracle statistics)
+            'atomic': ({'achieved': iter_per_launch/(k_ms*1e-3), 'peak': 1.2e12,
+                        'frac': iter_per_launch/(k_ms*1e-3)/1.2e12,
+                        'unit': 'deposits/s', 'path': 'shared-memory window (ATOMS lo/hi), 2.5 % RED.E.ADD.64'}
+                       if config == 'c2_skin' else
+                       {'achieved': 0.15*iter_per_launch/(k_ms*1e-3), 'peak': 1.8e11,
+                        'frac': 0.15*iter_per_launch/(k_ms*1e-3)/1.8e11,
+                        'unit': 'deposits/s', 'path': 'RED.E.ADD.64 to L2'}
+                       if config == 'c3_vox' else None),
             'peak_source': 'sm_max_mhz of MEASURED_PEAKS.json ({}) x {} SMs x {} FP32 lanes; '
                            'hbm is not the bound of this path (working set < 2 MB)'.format(
                                peaks_src, sms, FP32_LANES_PER_SM),
