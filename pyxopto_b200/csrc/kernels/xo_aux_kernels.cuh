@@ -31,3 +31,13 @@ extern "C" __global__ void MathProbe(int fn, xo::u32 n, const float *in0, const 
 		case 7: out0[i] = M::div(a, b); break;
 	}
 }
+
+// AccuScale: out[i] = (double)accu[i] * inv_k -- the host's `update_data`
+// (mcfluence/fluence.py:368-376: raw += accumulators*(1/k), float64) evaluated on
+// the device for large grids; same IEEE operations (u64 -> binary64 round to
+// nearest, one binary64 multiply), so the result is bit-identical to NumPy's.
+extern "C" __global__ void AccuScale(const xo::u64 *accu, double *out, xo::u64 n, double inv_k) {
+	const xo::u64 stride = (xo::u64)gridDim.x*blockDim.x;
+	for (xo::u64 i = (xo::u64)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride)
+		out[i] = __dmul_rn(__ull2double_rn(accu[i]), inv_k);
+}

@@ -53,6 +53,17 @@ class _FluenceBase(McObject):
             self._data.shape = self.shape
             self._nphotons = nphotons
 
+    def update_scaled(self, scaled: np.ndarray, nphotons: int):
+        """``update_data`` with the conversion ``accumulators*(1/k)`` already done
+        (bit-identically) on the device: ``scaled`` is a float64 array that the
+        caller may reuse afterwards."""
+        if self._data is not None:
+            self._data += np.reshape(scaled, self._data.shape)
+            self._nphotons += nphotons
+        else:
+            self._data = np.array(scaled, dtype=np.float64).reshape(self.shape)
+            self._nphotons = nphotons
+
     def cu_window(self, mc, max_bins: int, focus):
         """(org0, org1, org2, ext0, ext1, ext2): block of grid cells around the
         point ``focus`` (source position) that each CTA accumulates in shared

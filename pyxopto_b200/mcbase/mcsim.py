@@ -617,8 +617,12 @@ class McBase(CuWorker):
         if self._fluence is not None:
             fluence_res = out_fluence if out_fluence is not None \
                 else type(self._fluence)(self._fluence)
-            data = self._download_allocations(self._fluence, nphotons)
-            fluence_res.update_data(self, data, nphotons=nphotons)
+            scaled = self._download_scaled_fluence(fluence_res)
+            if scaled is not None:
+                fluence_res.update_scaled(scaled, nphotons)
+            else:
+                data = self._download_allocations(self._fluence, nphotons)
+                fluence_res.update_data(self, data, nphotons=nphotons)
         if self._detectors is not None:
             detectors_res = out_detectors if out_detectors is not None \
                 else type(self._detectors)(self._detectors)
@@ -627,6 +631,42 @@ class McBase(CuWorker):
                 if data:
                     detectors_res.update_data(self, res, data, nphotons=nphotons)
         return trace_res, fluence_res, detectors_res
+
+    # grids of at least this many cells are converted to float64 on the device
+    # (AccuScale): the host then only copies the page-locked result
+    SCALE_ON_DEVICE_MIN = 1 << 20
+
+    def _download_scaled_fluence(self, result):
+        """float64 ``accumulators*(1/k)`` of the fluence grid computed on the device
+        (bit-identical to ``update_data``'s NumPy expression), or None when the
+        plugin does not use the stock conversion / the grid is small."""
+        from . import mcfluence, rngkernel
+        from ..cu import abi
+        flu = self._fluence
+        if type(result).update_data is not mcfluence._FluenceBase.update_data or \
+                not hasattr(result, 'update_scaled'):
+            return None
+        allocs = self.cl_rw_accumulator_allocator.allocations(flu)
+        if len(allocs) != 1 or allocs[0].size < self.SCALE_ON_DEVICE_MIN or \
+                not allocs[0].download:
+            return None
+        a = allocs[0]
+        mod = rngkernel._aux_module(self, True)
+        out = self._buffer('accu_scaled', a.size*8)
+        src = self._cl_buffers[self._rw_name('accumulator')]
+        grid = 4*self._ctx.info['multiprocessor_count']
+        mod.kernel('AccuScale').launch(
+            self._stream, grid, 512,
+            [(src, a.offset*8), out, np.uint64(a.size), np.float64(1.0/result.k)])
+        key = ('accu_scaled', a.size)
+        host = self._pinned_downloads.get(key)
+        if host is None:
+            if len(self._pinned_downloads) >= 4:
+                self._pinned_downloads.clear()
+            host = abi.pinned_empty(self._ctx, (a.size,), np.float64)
+            self._pinned_downloads[key] = host
+        out.download(self._stream, host)
+        return host
 
     # -- device-side trace filter (SURVEY 8f-1) ------------------------------------
     # True: a Trace with a Filter is filtered and compacted on the device and

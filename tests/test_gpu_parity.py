@@ -480,3 +480,20 @@ def test_runs_above_the_device_counter_are_batched_exactly():
     assert np.array_equal(flu_a.raw, flu_b.raw) and flu_a.raw.sum() > 0
     with pytest.raises(ValueError):
         _det_sim('mcml_mhg_gauss_enhanced_rng')[0].run(2**33)
+
+
+def test_device_side_grid_conversion_is_bit_identical():
+    """Large fluence grids are converted to float64 on the device (AccuScale)
+    instead of by ``update_data`` on the host: same IEEE operations, same bits;
+    accumulation with ``out=`` included."""
+    def run(on_device):
+        sim = _det_sim('mcvox_gauss_fluence')[0]
+        sim.SCALE_ON_DEVICE_MIN = 1 if on_device else 1 << 62
+        kw = dict(maxthreads=256, wgsize=64)
+        res = sim.run(3000, **kw)
+        res = sim.run(2000, out=res, **kw)
+        return res[1]
+    a, b = run(True), run(False)
+    assert a.nphotons == b.nphotons == 5000
+    assert a.raw.sum() > 0 and a.raw.dtype == np.float64 and a.raw.shape == b.raw.shape
+    assert np.array_equal(a.raw, b.raw)

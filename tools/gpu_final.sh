@@ -11,7 +11,7 @@ for c in c2_skin c1_slab c3_vox c5_cyl c4_trace; do
   timeout 900 python bench.py --config $c --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_$c.json 2> gpurun_out/bench_$c.err
   tail -c 600 gpurun_out/${TAG}_bench_$c.json; tail -2 gpurun_out/bench_$c.err
 done
-timeout 900 python bench.py --config c5_slab --sweep 64 --packets 1e6 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_c5_sweep64.json 2> gpurun_out/bench_c5_sweep.err
+timeout 900 python bench.py --config c5_slab --sweep 64 --packets 1e7 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench_c5_sweep64.json 2> gpurun_out/bench_c5_sweep.err
 tail -c 400 gpurun_out/${TAG}_bench_c5_sweep64.json
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref_c2_skin.json 2>&1; tail -c 500 gpurun_out/${TAG}_bench_ref_c2_skin.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench_c2_skin.csv \
