@@ -1073,6 +1073,13 @@ typedef struct { m3f T; p2f position; float core_spacing;
 	float core_r_squared, core_n, core_cc;
 	float cutout_r_squared, cutout_n, cutout_cc;
 	float probe_r_squared, probe_reflectivity; } surf_six;
+/* mcsurface/probe/lineararray.py:44-64 */
+typedef struct { m3f T; float c11, c12, c21, c22; p2f position, first_position, delta_position;
+	float core_spacing;
+	float cladding_r_squared, cladding_n, cladding_cc;
+	float core_r_squared, core_n, core_cc;
+	float cutout_width_half, cutout_height_half, cutout_n, cutout_cc;
+	float probe_r_squared, probe_reflectivity; } surf_linarray;
 enum { SURF_CONTINUE = 0, SURF_REFLECTED = 1 };
 
 static int surf_six_fiber(const surf_six *l, float r2, float *n2, float *cc) {
@@ -1128,6 +1135,44 @@ static int surface_layout_handler(sim_t *s, int which, float *n2, float *cc) {
 		if (surf_six_fiber(l, r2, n2, cc)) return SURF_CONTINUE;
 		dx = rel.x; dy = rel.y; r2 = dx*dx + dy*dy;
 		if (r2 <= l->cutout_r_squared) { *n2 = l->cutout_n; *cc = l->cutout_cc; return SURF_CONTINUE; }
+		if (r2 <= l->probe_r_squared) {
+			s->dir.z = -s->dir.z;
+			s->weight = s->weight*l->probe_reflectivity;
+			return SURF_REFLECTED;
+		}
+		return SURF_CONTINUE;
+	}
+	case XO_SURF_LINEARARRAY: {                        /* mcsurface/probe/lineararray.py:152-228 */
+		const surf_linarray *l = (const surf_linarray *)base;
+		uint32_t n = (uint32_t)j->surf_param[which];
+		float dx, dy, r2;
+		p3f mc_pos = { FP_0, FP_0, FP_0 }, lp;
+		float fiber_x = l->first_position.x, fiber_y = l->first_position.y;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = s->pos.x - fiber_x; mc_pos.y = s->pos.y - fiber_y; mc_pos.z = FP_0;
+			m3f T = l->T;
+			transform3(&T, &mc_pos, &lp);
+			dx = lp.x; dy = lp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= l->cladding_r_squared) {
+				if (r2 <= l->core_r_squared) { *n2 = l->core_n; *cc = l->core_cc; return SURF_CONTINUE; }
+				*n2 = l->cladding_n; *cc = l->cladding_cc;
+				return SURF_CONTINUE;
+			}
+			fiber_x += l->delta_position.x;
+			fiber_y += l->delta_position.y;
+		}
+		/* the cut-out of the probe, in the frame of the array */
+		{
+			float cx = s->pos.x - l->position.x, cy = s->pos.y - l->position.y;
+			float ox = l->c11*cx + l->c12*cy, oy = l->c21*cx + l->c22*cy;
+			dx = fabsf(ox); dy = fabsf(oy);
+			if (dx <= l->cutout_width_half && dy < l->cutout_height_half) {
+				*n2 = l->cutout_n; *cc = l->cutout_cc;
+				return SURF_CONTINUE;
+			}
+		}
+		/* the probe tip: relative to the LAST fiber (mc_pos survives the loop) */
+		dx = mc_pos.x; dy = mc_pos.y; r2 = dx*dx + dy*dy;
 		if (r2 <= l->probe_r_squared) {
 			s->dir.z = -s->dir.z;
 			s->weight = s->weight*l->probe_reflectivity;

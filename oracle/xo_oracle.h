@@ -34,7 +34,8 @@ enum {
 	XO_FLU_NONE = 0, XO_FLU_XYZ = 1, XO_FLU_RZ = 2, XO_FLU_XYZT = 3,
 	XO_FLU_RZT = 4, XO_FLU_CYL = 5, XO_FLU_CYLT = 6
 };
-enum { XO_SURF_NONE = 0, XO_SURF_LAMBERTIAN = 1, XO_SURF_SIXAROUNDONE = 2 };
+enum { XO_SURF_NONE = 0, XO_SURF_LAMBERTIAN = 1, XO_SURF_SIXAROUNDONE = 2,
+	XO_SURF_LINEARARRAY = 3 };
 enum { XO_TRACE_NONE = 0, XO_TRACE_START = 1, XO_TRACE_END = 2, XO_TRACE_ALL = 7 };
 
 typedef struct xo_oracle_job {
@@ -58,6 +59,7 @@ typedef struct xo_oracle_job {
 	int32_t track_opl;         /* MC_TRACK_OPTICAL_PATHLENGTH */
 	int32_t surf_kind[2];      /* top, bottom surface layout (mcml) */
 	int32_t surf_offset[2];    /* byte offsets inside the packed McSurfaceLayouts */
+	int32_t surf_param[2];     /* compile-time parameter of the layout text (fiber count) */
 	int32_t enhanced_rng;      /* MC_USE_ENHANCED_RNG: two MWC steps per draw (mcbase.template.c:1577-1586) */
 
 	/* run-time kernel arguments (mcml.template.c:346-376, mcvox.template.c:548) */

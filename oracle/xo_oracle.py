@@ -35,7 +35,7 @@ DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'LinearArray': 12, 'FiberArray': 13, 'LinearArrayPl': 14, 'FiberArrayPl': 15}
 DET_KIND_TOTAL_CYL = 11
 SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
-             'SixAroundOne': 2}
+             'SixAroundOne': 2, 'LinearArray': 3}
 FLU_KIND = {'NoneType': 0, 'Fluence': 1, 'FluenceRz': 2, 'Fluencet': 3,
             'FluenceRzt': 4, 'FluenceCyl': 5, 'FluenceCylt': 6}
 
@@ -53,7 +53,7 @@ class Job(ctypes.Structure):
         ('trace_flags', ctypes.c_int32), ('use_events', ctypes.c_int32),
         ('track_opl', ctypes.c_int32),
         ('surf_kind', ctypes.c_int32*2), ('surf_offset', ctypes.c_int32*2),
-        ('enhanced_rng', ctypes.c_int32),
+        ('surf_param', ctypes.c_int32*2), ('enhanced_rng', ctypes.c_int32),
         ('num_packets', ctypes.c_uint32), ('num_threads', ctypes.c_uint32),
         ('rmax', ctypes.c_float), ('num_layers', ctypes.c_uint32),
         ('layers', ctypes.c_void_p), ('voxel_cfg', ctypes.c_void_p),
@@ -201,6 +201,8 @@ def describe(mc_obj, geometry: str) -> dict:
         sstruct = type(packed)
         for i, loc in enumerate(('top', 'bottom')):
             d['surf_kind'][i] = SURF_KIND[_name(getattr(surf, loc))]
+            d.setdefault('surf_param', [0, 0])[i] = int(getattr(getattr(surf, loc), 'n', 0) or 0) \
+                if d['surf_kind'][i] == 3 else 0
             d['surf_offset'][i] = getattr(sstruct, loc).offset
         d['surface'] = _raw(packed)
     flu = mc_obj.fluence
@@ -277,6 +279,7 @@ def run(desc: dict, nphotons: int, nthreads: int, rng_x: np.ndarray,
     for i in range(2):
         job.surf_kind[i] = desc.get('surf_kind', [0, 0])[i]
         job.surf_offset[i] = desc.get('surf_offset', [0, 0])[i]
+        job.surf_param[i] = desc.get('surf_param', [0, 0])[i]
     if desc['geometry'] == 'mcvox':
         job.voxel_cfg = buf(desc['voxel_cfg'])
         vox = np.ascontiguousarray(desc['voxels'], np.int32)

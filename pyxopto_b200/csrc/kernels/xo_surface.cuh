@@ -93,6 +93,51 @@ struct SurfSixAroundOne {           // mcsurface/probe/sixaroundone.py
 	}
 };
 
+// mcsurface/probe/lineararray.py:150-230: N fibers in a row, rectangular cut-out,
+// reflective probe tip.  The tip test uses the position relative to the *last*
+// fiber (the loop variable of the reference survives the loop), kept as is.
+template <int N>
+struct SurfLinearArray {
+	M3 T; float c11, c12, c21, c22; P2 position, first_position, delta_position;
+	float core_spacing;
+	float cladding_r_squared, cladding_n, cladding_cc;
+	float core_r_squared, core_n, core_cc;
+	float cutout_width_half, cutout_height_half, cutout_n, cutout_cc;
+	float probe_r_squared, probe_reflectivity;
+	static constexpr bool active = true;
+	__device__ __forceinline__ int handle(Rng &rng, const P3 &pos, P3 &dir, float &weight,
+			float *n2, float *cc) const {
+		(void)rng;
+		float fx = first_position.x, fy = first_position.y;
+		P3 p = { 0.0f, 0.0f, 0.0f };
+#pragma unroll 1
+		for (u32 i = 0; i < (u32)N; ++i) {
+			p.x = pos.x - fx; p.y = pos.y - fy; p.z = 0.0f;
+			P3 q = transform3(T, p);
+			float r2 = q.x*q.x + q.y*q.y;
+			if (r2 <= cladding_r_squared) {
+				if (r2 <= core_r_squared) { *n2 = core_n; *cc = core_cc; }
+				else { *n2 = cladding_n; *cc = cladding_cc; }
+				return SURF_CONTINUE;
+			}
+			fx += delta_position.x;
+			fy += delta_position.y;
+		}
+		float cx = pos.x - position.x, cy = pos.y - position.y;
+		float dx = fabsf(c11*cx + c12*cy), dy = fabsf(c21*cx + c22*cy);
+		if (dx <= cutout_width_half && dy < cutout_height_half) {
+			*n2 = cutout_n; *cc = cutout_cc;
+			return SURF_CONTINUE;
+		}
+		if (p.x*p.x + p.y*p.y <= probe_r_squared) {
+			dir.z = -dir.z;
+			weight = weight*probe_reflectivity;
+			return SURF_REFLECTED;
+		}
+		return SURF_CONTINUE;
+	}
+};
+
 template <class Top, class Bottom>
 struct SurfaceLayouts {             // mcsurface/base.py:258-263
 	Top top;

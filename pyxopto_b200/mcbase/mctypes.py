@@ -78,6 +78,7 @@ class McDataTypesSingle:
     mc_point4s_t = _vec('mc_point4s_t', ctypes.c_uint32, 'xyzw')
     mc_matrix3f_t = type('mc_matrix3f_t', (_Matrix3,),
                          {'_fields_': [(f, ctypes.c_float) for f in _M3_FIELDS]})
+    mc_matrix2f_t = _vec('mc_matrix2f_t', ctypes.c_float, ['a_11', 'a_12', 'a_21', 'a_22'])
 
     @classmethod
     def cl_options(cls, *_):

@@ -18,3 +18,16 @@ def rotation_matrix(a, b) -> np.ndarray:
 
 def transform_base(vfrom, vto) -> np.ndarray:
     return rotation_matrix(vfrom, vto)
+
+
+def rotation_matrix_2d(a, b) -> np.ndarray:
+    """2 x 2 rotation of unit vector a onto b as the reference computes it
+    (mcutil/geometry.py:33-60): the sine is taken as +sqrt(1 - cos^2), i.e. the
+    rotation is always counter-clockwise by the angle between the vectors."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    a = a/np.linalg.norm(a)
+    b = b/np.linalg.norm(b)
+    cos_theta = np.dot(a, b)
+    sin_theta = np.sqrt(1.0 - cos_theta**2)
+    return np.array([[cos_theta, -sin_theta], [sin_theta, cos_theta]])

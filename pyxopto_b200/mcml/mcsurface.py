@@ -253,6 +253,152 @@ class SixAroundOne(SurfaceLayoutBase):
                                     self._reflectivity, self._cutout, self._cutout_n)
 
 
+class LinearArray(SurfaceLayoutBase):
+    """Linear array of ``n`` fibers in a stainless-steel probe pressed against the
+    surface (mcsurface/probe/lineararray.py): cores, claddings, an optional
+    rectangular filled cut-out and the reflective probe tip.  ``n`` is a
+    compile-time feature."""
+    def cu_type(self, mc):
+        return 'xo::SurfLinearArray<{}>'.format(self._n)
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClLinearArray(cltypes.Structure):
+            _fields_ = [
+                ('transformation', T.mc_matrix3f_t),
+                ('cutout_transformation', T.mc_matrix2f_t),
+                ('position', T.mc_point2f_t), ('first_position', T.mc_point2f_t),
+                ('delta_position', T.mc_point2f_t), ('core_spacing', T.mc_fp_t),
+                ('cladding_r_squared', T.mc_fp_t), ('cladding_n', T.mc_fp_t),
+                ('cladding_cos_critical', T.mc_fp_t),
+                ('core_r_squared', T.mc_fp_t), ('core_n', T.mc_fp_t),
+                ('core_cos_critical', T.mc_fp_t),
+                ('cutout_width_half', T.mc_fp_t), ('cutout_height_half', T.mc_fp_t),
+                ('cutout_n', T.mc_fp_t), ('cutout_cos_critical', T.mc_fp_t),
+                ('probe_r_squared', T.mc_fp_t), ('probe_reflectivity', T.mc_fp_t)]
+        return ClLinearArray
+
+    def __init__(self, fiber, n: int = 1, spacing: float = None,
+                 orientation: Tuple[float, float] = (1.0, 0.0), diameter: float = 0.0,
+                 reflectivity: float = 1.0, cutout: Tuple[float, float] = (0.0, 0.0),
+                 cutoutn: float = 1.0, position: Tuple[float, float] = (0.0, 0.0),
+                 direction: Tuple[float, float, float] = (0.0, 0.0, 1.0)):
+        super().__init__()
+        if isinstance(fiber, LinearArray):
+            o = fiber
+            fiber, n, spacing, orientation = o.fiber, o.n, o.spacing, o.orientation
+            diameter, reflectivity, cutout, cutoutn = o.diameter, o.reflectivity, o.cutout, o.cutoutn
+            position, direction = o.position, o.direction
+        elif spacing is None:
+            spacing = fiber.dcladding
+        self._fiber = fiber
+        self._n = max(int(n), 1)
+        self._cutout = np.zeros((2,))
+        self._orientation = np.array((1.0, 0.0))
+        self._position = np.zeros((2,))
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self.spacing, self.diameter, self.reflectivity = spacing, diameter, reflectivity
+        self.cutout, self.cutoutn = cutout, cutoutn
+        self.orientation, self.position, self.direction = orientation, position, direction
+
+    def _set_fiber(self, fiber):
+        self._fiber = fiber
+
+    fiber = property(lambda self: self._fiber, _set_fiber)
+    n = property(lambda self: self._n)
+
+    def _set_spacing(self, v):
+        self._spacing = float(v)
+
+    spacing = property(lambda self: self._spacing, _set_spacing)
+
+    def _set_diameter(self, v):
+        self._diameter = max(float(v), 0.0)
+
+    diameter = property(lambda self: self._diameter, _set_diameter)
+
+    def _set_reflectivity(self, v):
+        self._reflectivity = min(max(float(v), 0.0), 1.0)
+
+    reflectivity = property(lambda self: self._reflectivity, _set_reflectivity)
+
+    def _set_orientation(self, o):
+        self._orientation[:] = o
+        norm = np.linalg.norm(self._orientation)
+        if norm == 0.0:
+            raise ValueError('Orientation vector norm/length must not be 0!')
+        self._orientation *= 1.0/norm
+
+    orientation = property(lambda self: self._orientation, _set_orientation)
+
+    def _set_cutout(self, c):
+        self._cutout[:] = np.maximum(0.0, c)
+
+    cutout = property(lambda self: self._cutout, _set_cutout, None,
+                      'Size (width, height) of the cut-out that accommodates the fibers.')
+
+    def _set_cutoutn(self, v):
+        self._cutout_n = max(float(v), 1.0)
+
+    cutoutn = property(lambda self: self._cutout_n, _set_cutoutn)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+
+    def _set_direction(self, d):
+        self._direction[:] = d
+        norm = np.linalg.norm(self._direction)
+        if norm == 0.0:
+            raise ValueError('Direction vector norm/length must not be 0!')
+        self._direction *= 1.0/norm
+
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def fiber_position(self, index: int) -> Tuple[float, float]:
+        if index >= self._n or index < -self._n:
+            raise IndexError('The fiber index is out of valid range!')
+        left = self._position - self._orientation*self._spacing*(self._n - 1)*0.5
+        return tuple(left + self._spacing*self._orientation*int(index))
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        adir = self._direction[0], self._direction[1], abs(self._direction[2])
+        n_sample = mc.layers[1].n if self.location == TOP else mc.layers[-2].n
+        target.transformation.fromarray(geometry.transform_base(adir, (0.0, 0.0, 1.0)))
+        target.position.fromarray(self._position)
+        target.first_position.fromarray(self.fiber_position(0))
+        target.delta_position.fromarray(self._orientation*self._spacing)
+        target.core_r_squared = 0.25*self._fiber.dcore**2
+        target.core_n = self._fiber.ncore
+        target.core_cos_critical = boundary.cos_critical(n_sample, self._fiber.ncore)
+        target.cladding_r_squared = 0.25*self._fiber.dcladding**2
+        target.cladding_n = self._fiber.ncladding
+        target.cladding_cos_critical = boundary.cos_critical(n_sample, self._fiber.ncladding)
+        target.probe_r_squared = 0.25*self._diameter**2
+        target.probe_reflectivity = self._reflectivity
+        target.cutout_transformation.fromarray(
+            geometry.rotation_matrix_2d(self._orientation, [1.0, 0.0]))
+        target.cutout_width_half = self._cutout[0]*0.5
+        target.cutout_height_half = self._cutout[1]*0.5
+        target.cutout_n = self._cutout_n
+        target.cutout_cos_critical = boundary.cos_critical(n_sample, self._cutout_n)
+        return target
+
+    def todict(self):
+        return {'type': 'LinearArray', 'fiber': self._fiber.todict(), 'n': self._n,
+                'spacing': self._spacing, 'orientation': self._orientation.tolist(),
+                'diameter': self._diameter, 'reflectivity': self._reflectivity,
+                'cutout': self._cutout.tolist(), 'cutoutn': self._cutout_n,
+                'position': self._position.tolist(), 'direction': self._direction.tolist()}
+
+    def __repr__(self):
+        return 'LinearArray(fiber={}, n={}, spacing={}, diameter={})'.format(
+            self._fiber, self._n, self._spacing, self._diameter)
+
+
 class SurfaceLayouts(McObject):
     """Container {top, bottom} (mcsurface/base.py:235-426)."""
 

@@ -697,3 +697,38 @@ MCML_CASES['mcml_mhg_gauss_enhanced_rng'] = mcml_mhg_gauss_enhanced_rng
 ALL_CASES['mcml_mhg_gauss_enhanced_rng'] = mcml_mhg_gauss_enhanced_rng
 GEOMETRY['mcml_mhg_gauss_enhanced_rng'] = 'mcml'
 GOLDEN_RUN['mcml_mhg_gauss_enhanced_rng'] = (2000, 16)
+
+
+def mcml_surface_lineararray(mc, **kw):
+    """Linear fiber-array probe on both surfaces (mcml/mcsurface/probe/lineararray.py):
+    cores / claddings, a rectangular filled cut-out and the reflective tip on top
+    (tilted, rotated array), a plain array without cut-out at the bottom; the
+    matching LinearArray detectors collect the light."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    L = mc.mclayer.Layer
+    pf = mc.mcpf.Hg(0.8)
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=0.3e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=0.4e-3, n=1.4, mua=0.5e2, mus=50e2, pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf)])
+    orient = (np.cos(np.deg2rad(30.0)), np.sin(np.deg2rad(30.0)))
+    surf = mc.mcsurface.SurfaceLayouts(
+        top=mc.mcsurface.LinearArray(fib, 3, spacing=260e-6, orientation=orient, diameter=2.5e-3,
+                                     reflectivity=0.55, cutout=(1.0e-3, 0.4e-3), cutoutn=1.6,
+                                     position=(30e-6, -20e-6), direction=(0.04, 0.0, 1.0)),
+        bottom=mc.mcsurface.LinearArray(fib, 2, diameter=1.5e-3, reflectivity=0.8))
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.LinearArray(fib, 3, spacing=260e-6, orientation=orient,
+                                      position=(30e-6, -20e-6), direction=(0.04, 0.0, 1.0)),
+        bottom=mc.mcdetector.LinearArray(fib, 2), specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceRz(Axis(0, 2e-3, 40), Axis(0, 0.7e-3, 35))
+    return mc.Mc(layers, mc.mcsource.UniformFiber(fib), det, fluence=flu, surface=surf,
+                 rnginit=13579, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_surface_lineararray'] = mcml_surface_lineararray
+ALL_CASES['mcml_surface_lineararray'] = mcml_surface_lineararray
+GEOMETRY['mcml_surface_lineararray'] = 'mcml'
+GOLDEN_RUN['mcml_surface_lineararray'] = (4000, 16)
