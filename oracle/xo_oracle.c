@@ -1180,6 +1180,36 @@ static int surface_layout_handler(sim_t *s, int which, float *n2, float *cc) {
 		}
 		return SURF_CONTINUE;
 	}
+	case XO_SURF_FIBERARRAY: {                         /* mcsurface/probe/fiberarray.py:133-183 */
+		/* packed: m3f T[n]; p2f fiber_position[n]; float cladding_r2[n], cladding_n[n],
+		 * cladding_cc[n], core_r2[n], core_n[n], core_cc[n]; p2f probe_position;
+		 * float probe_r_squared, probe_reflectivity */
+		uint32_t n = (uint32_t)j->surf_param[which];
+		const m3f *Ts = (const m3f *)base;
+		const p2f *fp = (const p2f *)(Ts + n);
+		const float *clad_r2 = (const float *)(fp + n), *clad_n = clad_r2 + n, *clad_cc = clad_n + n;
+		const float *core_r2 = clad_cc + n, *core_n = core_r2 + n, *core_cc = core_n + n;
+		const float *tail = core_cc + n;   /* probe_position.x, .y, probe_r_squared, reflectivity */
+		float dx, dy, r2; p3f mc_pos, lp;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = s->pos.x - fp[index].x; mc_pos.y = s->pos.y - fp[index].y; mc_pos.z = FP_0;
+			m3f T = Ts[index];
+			transform3(&T, &mc_pos, &lp);
+			dx = lp.x; dy = lp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= clad_r2[index]) {
+				if (r2 <= core_r2[index]) { *n2 = core_n[index]; *cc = core_cc[index]; return SURF_CONTINUE; }
+				*n2 = clad_n[index]; *cc = clad_cc[index];
+				return SURF_CONTINUE;
+			}
+		}
+		dx = s->pos.x - tail[0]; dy = s->pos.y - tail[1]; r2 = dx*dx + dy*dy;
+		if (r2 <= tail[2]) {
+			s->dir.z = -s->dir.z;
+			s->weight = s->weight*tail[3];
+			return SURF_REFLECTED;
+		}
+		return SURF_CONTINUE;
+	}
 	}
 	return SURF_CONTINUE;
 }

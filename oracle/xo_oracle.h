@@ -35,7 +35,7 @@ enum {
 	XO_FLU_RZT = 4, XO_FLU_CYL = 5, XO_FLU_CYLT = 6
 };
 enum { XO_SURF_NONE = 0, XO_SURF_LAMBERTIAN = 1, XO_SURF_SIXAROUNDONE = 2,
-	XO_SURF_LINEARARRAY = 3 };
+	XO_SURF_LINEARARRAY = 3, XO_SURF_FIBERARRAY = 4 };
 enum { XO_TRACE_NONE = 0, XO_TRACE_START = 1, XO_TRACE_END = 2, XO_TRACE_ALL = 7 };
 
 typedef struct xo_oracle_job {

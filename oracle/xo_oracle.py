@@ -35,7 +35,7 @@ DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'LinearArray': 12, 'FiberArray': 13, 'LinearArrayPl': 14, 'FiberArrayPl': 15}
 DET_KIND_TOTAL_CYL = 11
 SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
-             'SixAroundOne': 2, 'LinearArray': 3}
+             'SixAroundOne': 2, 'LinearArray': 3, 'FiberArray': 4}
 FLU_KIND = {'NoneType': 0, 'Fluence': 1, 'FluenceRz': 2, 'Fluencet': 3,
             'FluenceRzt': 4, 'FluenceCyl': 5, 'FluenceCylt': 6}
 
@@ -202,7 +202,7 @@ def describe(mc_obj, geometry: str) -> dict:
         for i, loc in enumerate(('top', 'bottom')):
             d['surf_kind'][i] = SURF_KIND[_name(getattr(surf, loc))]
             d.setdefault('surf_param', [0, 0])[i] = int(getattr(getattr(surf, loc), 'n', 0) or 0) \
-                if d['surf_kind'][i] == 3 else 0
+                if d['surf_kind'][i] in (3, 4) else 0
             d['surf_offset'][i] = getattr(sstruct, loc).offset
         d['surface'] = _raw(packed)
     flu = mc_obj.fluence

@@ -138,6 +138,39 @@ struct SurfLinearArray {
 	}
 };
 
+// mcsurface/probe/fiberarray.py:130-185: N individually placed / tilted fibers and
+// the probe tip around `probe_position`
+template <int N>
+struct SurfFiberArray {
+	M3 T[N]; P2 fiber_position[N];
+	float cladding_r_squared[N], cladding_n[N], cladding_cc[N];
+	float core_r_squared[N], core_n[N], core_cc[N];
+	P2 probe_position; float probe_r_squared, probe_reflectivity;
+	static constexpr bool active = true;
+	__device__ __forceinline__ int handle(Rng &rng, const P3 &pos, P3 &dir, float &weight,
+			float *n2, float *cc) const {
+		(void)rng;
+#pragma unroll 1
+		for (u32 i = 0; i < (u32)N; ++i) {
+			P3 p = { pos.x - fiber_position[i].x, pos.y - fiber_position[i].y, 0.0f };
+			P3 q = transform3(T[i], p);
+			float r2 = q.x*q.x + q.y*q.y;
+			if (r2 <= cladding_r_squared[i]) {
+				if (r2 <= core_r_squared[i]) { *n2 = core_n[i]; *cc = core_cc[i]; }
+				else { *n2 = cladding_n[i]; *cc = cladding_cc[i]; }
+				return SURF_CONTINUE;
+			}
+		}
+		float dx = pos.x - probe_position.x, dy = pos.y - probe_position.y;
+		if (dx*dx + dy*dy <= probe_r_squared) {
+			dir.z = -dir.z;
+			weight = weight*probe_reflectivity;
+			return SURF_REFLECTED;
+		}
+		return SURF_CONTINUE;
+	}
+};
+
 template <class Top, class Bottom>
 struct SurfaceLayouts {             // mcsurface/base.py:258-263
 	Top top;

@@ -15,7 +15,7 @@ import numpy as np
 from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import boundary, geometry
-from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
+from ..mcbase.mcutil.fiber import MultimodeFiber, FiberLayout  # noqa: F401
 
 TOP = 'top'
 BOTTOM = 'bottom'
@@ -397,6 +397,93 @@ class LinearArray(SurfaceLayoutBase):
     def __repr__(self):
         return 'LinearArray(fiber={}, n={}, spacing={}, diameter={})'.format(
             self._fiber, self._n, self._spacing, self._diameter)
+
+
+class FiberArray(SurfaceLayoutBase):
+    """Individually placed / tilted fibers in a stainless-steel probe
+    (mcsurface/probe/fiberarray.py).  The number of fibers is a compile-time
+    feature.  Quirk kept: the reference packs the tip reflectivity into an
+    attribute that is not a struct field (``target.probe_reflectivity`` while the
+    field is called ``reflectivity``, fiberarray.py:81,381), so the kernel always
+    sees 0 - a packet that hits the tip loses all its weight."""
+    def cu_type(self, mc):
+        return 'xo::SurfFiberArray<{}>'.format(len(self._fibers))
+
+    def cl_type(self, mc):
+        T = mc.types
+        n = self.n
+        class ClFiberArray(cltypes.Structure):
+            _fields_ = [
+                ('transformation', T.mc_matrix3f_t*n), ('fiber_position', T.mc_point2f_t*n),
+                ('cladding_r_squared', T.mc_fp_t*n), ('cladding_n', T.mc_fp_t*n),
+                ('cladding_cos_critical', T.mc_fp_t*n),
+                ('core_r_squared', T.mc_fp_t*n), ('core_n', T.mc_fp_t*n),
+                ('core_cos_critical', T.mc_fp_t*n),
+                ('probe_position', T.mc_point2f_t), ('probe_r_squared', T.mc_fp_t),
+                ('reflectivity', T.mc_fp_t)]
+        return ClFiberArray
+
+    def __init__(self, fibers, diameter: float = 0.0, reflectivity: float = 0.0,
+                 position: Tuple[float, float] = (0.0, 0.0)):
+        super().__init__()
+        if isinstance(fibers, FiberArray):
+            o = fibers
+            fibers, diameter, reflectivity, position = o.fibers, o.diameter, o.reflectivity, o.position
+        self._fibers = list(fibers)
+        self._position = np.zeros((2,))
+        self.diameter, self.reflectivity, self.position = diameter, reflectivity, position
+
+    def _set_fibers(self, fibers):
+        if len(self._fibers) != len(fibers):
+            raise ValueError('The number of optical fibers must not change!')
+        self._fibers[:] = fibers
+
+    fibers = property(lambda self: self._fibers, _set_fibers)
+    n = property(lambda self: len(self._fibers))
+
+    def _set_diameter(self, v):
+        self._diameter = max(float(v), 0.0)
+
+    diameter = property(lambda self: self._diameter, _set_diameter)
+
+    def _set_reflectivity(self, v):
+        self._reflectivity = min(max(float(v), 0.0), 1.0)
+
+    reflectivity = property(lambda self: self._reflectivity, _set_reflectivity)
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        n_sample = mc.layers[1].n if self.location == TOP else mc.layers[-2].n
+        for index, cfg in enumerate(self._fibers):
+            adir = cfg.direction[0], cfg.direction[1], abs(cfg.direction[2])
+            target.transformation[index].fromarray(
+                geometry.transform_base(adir, (0.0, 0.0, 1.0)))
+            target.fiber_position[index].fromarray(cfg.position)
+            target.cladding_r_squared[index] = 0.25*cfg.fiber.dcladding**2
+            target.cladding_n[index] = cfg.fiber.ncladding
+            target.cladding_cos_critical[index] = boundary.cos_critical(
+                n_sample, cfg.fiber.ncladding)
+            target.core_r_squared[index] = 0.25*cfg.fiber.dcore**2
+            target.core_n[index] = cfg.fiber.ncore
+            target.core_cos_critical[index] = boundary.cos_critical(n_sample, cfg.fiber.ncore)
+        target.probe_position.fromarray(self._position)
+        target.probe_r_squared = 0.25*self._diameter**2
+        # (the struct field `reflectivity` stays 0, see the class docstring)
+        return target
+
+    def todict(self):
+        return {'type': 'FiberArray', 'fibers': [f.todict() for f in self._fibers],
+                'diameter': self._diameter, 'reflectivity': self._reflectivity,
+                'position': self._position.tolist()}
+
+    def __repr__(self):
+        return 'FiberArray(fibers={}, diameter={})'.format(self._fibers, self._diameter)
 
 
 class SurfaceLayouts(McObject):

@@ -732,3 +732,40 @@ MCML_CASES['mcml_surface_lineararray'] = mcml_surface_lineararray
 ALL_CASES['mcml_surface_lineararray'] = mcml_surface_lineararray
 GEOMETRY['mcml_surface_lineararray'] = 'mcml'
 GOLDEN_RUN['mcml_surface_lineararray'] = (4000, 16)
+
+
+def mcml_surface_fiberarray(mc, **kw):
+    """FiberArray probe layout on top (two fiber kinds, one tilted), matching
+    FiberArray detector; the tip reflectivity never reaches the reference kernel
+    (see pyxopto_b200.mcml.mcsurface.FiberArray), so the tip absorbs."""
+    Axis = mc.mcdetector.Axis
+    fib = _fiber(mc)
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcml.mcutil import fiber as fiberutil
+        big = fiberutil.MultimodeFiber(400e-6, 440e-6, 1.462, 0.37)
+    else:
+        big = mc.mcsource.MultimodeFiber(400e-6, 440e-6, 1.462, 0.37)
+    L = mc.mclayer.Layer
+    pf = mc.mcpf.Hg(0.8)
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=0.3e-3, n=1.33, mua=1e2, mus=100e2, pf=pf),
+        L(d=0.4e-3, n=1.4, mua=0.5e2, mus=50e2, pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf)])
+    tilt = (0.0, np.sin(np.deg2rad(-10.0)), np.cos(np.deg2rad(-10.0)))
+    fibers = [_fiber_layout(mc, fib, (0.0, 0.0, 0.0)),
+              _fiber_layout(mc, big, (0.5e-3, 0.0, 0.0), tilt),
+              _fiber_layout(mc, fib, (-0.3e-3, 0.3e-3, 0.0))]
+    surf = mc.mcsurface.SurfaceLayouts(
+        top=mc.mcsurface.FiberArray(fibers, diameter=2e-3, reflectivity=0.7,
+                                    position=(0.1e-3, 0.05e-3)))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.FiberArray(fibers),
+                                  bottom=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    return mc.Mc(layers, mc.mcsource.UniformFiber(fib), det, surface=surf,
+                 rnginit=97531, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_surface_fiberarray'] = mcml_surface_fiberarray
+ALL_CASES['mcml_surface_fiberarray'] = mcml_surface_fiberarray
+GEOMETRY['mcml_surface_fiberarray'] = 'mcml'
+GOLDEN_RUN['mcml_surface_fiberarray'] = (4000, 16)
