@@ -17,6 +17,7 @@ import time
 import numpy as np
 
 from . import mcoptions, mctypes
+from . import mcsv as mcsv_module
 from .mcworker import CuWorker, compile_kernel
 
 DEFAULT_BLOCK = 256
@@ -640,8 +641,7 @@ class McBase(CuWorker):
         """float64 ``accumulators*(1/k)`` of the fluence grid computed on the device
         (bit-identical to ``update_data``'s NumPy expression), or None when the
         plugin does not use the stock conversion / the grid is small."""
-        from . import mcfluence, rngkernel
-        from ..cu import abi
+        from . import mcfluence
         flu = self._fluence
         if type(result).update_data is not mcfluence._FluenceBase.update_data or \
                 not hasattr(result, 'update_scaled'):
@@ -650,14 +650,19 @@ class McBase(CuWorker):
         if len(allocs) != 1 or allocs[0].size < self.SCALE_ON_DEVICE_MIN or \
                 not allocs[0].download:
             return None
-        a = allocs[0]
+        src = self._cl_buffers[self._rw_name('accumulator')]
+        return self._scale_on_device(src, allocs[0], 1.0/result.k)
+
+    def _scale_on_device(self, src, a, inv_k: float) -> np.ndarray:
+        """Page-locked float64 array ``accu[a]*inv_k`` computed by AccuScale."""
+        from . import rngkernel
+        from ..cu import abi
         mod = rngkernel._aux_module(self, True)
         out = self._buffer('accu_scaled', a.size*8)
-        src = self._cl_buffers[self._rw_name('accumulator')]
         grid = 4*self._ctx.info['multiprocessor_count']
         mod.kernel('AccuScale').launch(
             self._stream, grid, 512,
-            [(src, a.offset*8), out, np.uint64(a.size), np.float64(1.0/result.k)])
+            [(src, a.offset*8), out, np.uint64(a.size), np.float64(inv_k)])
         key = ('accu_scaled', a.size)
         host = self._pinned_downloads.get(key)
         if host is None:
@@ -813,10 +818,18 @@ class McBase(CuWorker):
         cbuf.download(self._stream, counters)
         tbuf.download(self._stream, total)
         accus = []
-        for a in (self.cl_rw_accumulator_allocator.allocations(sv) if download else ()):
-            host = self._download_host_array('accumulator', a)
-            abuf.download(self._stream, host, offset=a.offset*8)
-            accus.append(host)
+        allocs = self.cl_rw_accumulator_allocator.allocations(sv) if download else ()
+        if len(allocs) == 1 and allocs[0].size >= self.SCALE_ON_DEVICE_MIN and \
+                type(sv).update_data is mcsv_module.SamplingVolume.update_data:
+            # large grid: the float64 conversion of update_data runs on the device
+            # (AccuScale, bit-identical), the host copies the page-locked result
+            scaled = self._scale_on_device(abuf, allocs[0], 1.0/(sv.k*sv._multiplier(self)))
+            sv.update_scaled(scaled, total_weight=total[0])
+        else:
+            for a in allocs:
+                host = self._download_host_array('accumulator', a)
+                abuf.download(self._stream, host, offset=a.offset*8)
+                accus.append(host)
         if accus:
             sv.update_data(self, accumulators=accus, nphotons=nphotons,
                            total_weight=total[0])

@@ -79,6 +79,16 @@ class SamplingVolume(McObject):
             self._data = new_data*(1.0/(self.k*multiplier))
             self._weight = float(total_weight)/self._k
 
+    def update_scaled(self, scaled, total_weight):
+        """``update_data`` with ``accumulators*(1/(k*multiplier))`` already computed
+        (bit-identically) on the device; ``scaled`` may be reused by the caller."""
+        if self._data is not None:
+            self._data += np.reshape(scaled, self.shape)
+            self._weight += float(total_weight)/self._k
+        else:
+            self._data = np.array(scaled, dtype=np.float64).reshape(self.shape)
+            self._weight = float(total_weight)/self._k
+
     def cl_pack(self, mc, target=None):
         if target is None:
             target = self.cl_type(mc)()

@@ -498,3 +498,21 @@ def test_device_side_grid_conversion_is_bit_identical():
     assert a.nphotons == b.nphotons == 5000
     assert a.raw.sum() > 0 and a.raw.dtype == np.float64 and a.raw.shape == b.raw.shape
     assert np.array_equal(a.raw, b.raw)
+
+
+def test_device_side_sampling_volume_conversion_is_bit_identical():
+    """The same for the sampling-volume grid (config 4: 200^3 voxels, 64 MB)."""
+    name = 'mcml_lut_iso_radialpl_trace'
+    out = []
+    for on_device in (True, False):
+        sim, geom, mc = _det_sim(name)
+        sim.SCALE_ON_DEVICE_MIN = 1 if on_device else 1 << 62
+        n = run_size(name)[0]
+        trace, _, _ = sim.run(n, maxthreads=256, wgsize=64)
+        sv = cases.make_sv(mc, name)
+        sim.sampling_volume(trace, sv)
+        sim.sampling_volume(trace, sv)             # accumulates into the same object
+        out.append(sv)
+    a, b = out
+    assert a.data.sum() > 0 and a.weight == b.weight
+    assert np.array_equal(a.data, b.data)
