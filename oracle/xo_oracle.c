@@ -450,6 +450,21 @@ static float pf_sample_angles(sim_t *s, float *azimuth) {
 	return FP_1;
 }
 
+/* ---- linear lookup tables: mcbase.template.h:2494-2548 ---------------------- */
+typedef struct { float first, inv_span; uint32_t n, offset; } fp_lut_t;
+typedef struct { fp_lut_t lut; p3f direction; uint32_t offset; } det_totallut;   /* total.py:262-266 */
+/* fp_linear_lut_sample: rounded first index, fractional weight, untouched when
+ * the position is outside the table */
+static inline void fp_lut_sample(const float *buffer, const fp_lut_t *lut, float where, float *value) {
+	float fp_index = (where - lut->first)*lut->inv_span*(lut->n - 1);
+	if (fp_index >= FP_0 && fp_index <= lut->n - 1) {
+		uint32_t index1 = (uint32_t)(fp_index + FP_0p5);
+		float w2 = fp_index - floorf(fp_index);
+		uint32_t index2 = (uint32_t)iclip((int32_t)(index1 + 1), 0, (int32_t)(lut->n - 1));
+		*value = buffer[lut->offset + index1]*(FP_1 - w2) + buffer[lut->offset + index2]*w2;
+	}
+}
+
 /* ---- detectors ------------------------------------------------------------- */
 enum { LOC_TOP = 0, LOC_BOTTOM = 1, LOC_SPECULAR = 2 };
 
@@ -463,6 +478,15 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		const det_total *d = (const det_total *)base;
 		p3f dd = d->direction;
 		uint32_t w = weight_to_u32(weight, d->cos_min <= fabsf(dot3(dir, &dd)));
+		if (w > 0) accu_deposit(s, d->offset, w);
+		break;
+	}
+	case XO_DET_TOTALLUT: {                            /* mcdetector/total.py:290-326 */
+		const det_totallut *d = (const det_totallut *)base;
+		float sensitivity = FP_0;
+		p3f dd = d->direction;
+		fp_lut_sample(j->fp_lut, &d->lut, fabsf(dot3(dir, &dd)), &sensitivity);
+		uint32_t w = (uint32_t)(weight*sensitivity*ACCU_K + FP_0p5);
 		if (w > 0) accu_deposit(s, d->offset, w);
 		break;
 	}

@@ -140,7 +140,7 @@ McKernel(
 	u32 off_words = (layer_words + 3u) & ~3u;
 	float *sh_lut = reinterpret_cast<float *>(xo_smem) + off_words;
 	const float *lut = fp_lut;
-	if (XoPf::uses_lut && lut_len) {
+	if (lut_len) {      // staged for the pf and the *Lut plugins
 		for (u32 i = threadIdx.x; i < lut_len; i += blockDim.x) sh_lut[i] = fp_lut[i];
 		lut = sh_lut;
 		off_words += (lut_len + 3u) & ~3u;
@@ -152,6 +152,7 @@ McKernel(
 	acc.zero_private();
 	acc.win = acc.priv + 2*priv_len;
 	acc.bind();
+	acc.lut = lut;
 	for (u32 i = threadIdx.x; i < window.ext0*window.ext1*window.ext2; i += blockDim.x) acc.win[i] = 0;
 	__syncthreads();
 

@@ -227,7 +227,7 @@ McKernel(
 #endif
 	float *sh_lut = reinterpret_cast<float *>(xo_smem) + off_words;
 	const float *lut = fp_lut;
-	if (XoPf::uses_lut && lut_len) {
+	if (lut_len) {      // staged for the pf and the *Lut plugins
 		for (u32 i = threadIdx.x; i < lut_len; i += blockDim.x) sh_lut[i] = fp_lut[i];
 		lut = sh_lut;
 		off_words += (lut_len + 3u) & ~3u;
@@ -242,6 +242,7 @@ McKernel(
 	const u32 far_words = (off_words + 2u*priv_len + 3u) & ~3u;
 	acc.win = reinterpret_cast<u32 *>(xo_smem) + far_words + 4u;
 	acc.bind();
+	acc.lut = lut;
 	const u32 win_len = window.ext0*window.ext1*window.ext2;
 	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
 #if !XO_DETERMINISTIC

@@ -166,7 +166,7 @@ McKernel(
 #endif
 	float *sh_lut = reinterpret_cast<float *>(xo_smem) + off_words;
 	const float *lut = fp_lut;
-	if (XoPf::uses_lut && lut_len) {
+	if (lut_len) {      // staged for the pf and the *Lut plugins
 		for (u32 i = threadIdx.x; i < lut_len; i += blockDim.x) sh_lut[i] = fp_lut[i];
 		lut = sh_lut;
 		off_words += (lut_len + 3u) & ~3u;
@@ -178,6 +178,7 @@ McKernel(
 	acc.zero_private();
 	acc.win = acc.priv + 2*priv_len;
 	acc.bind();
+	acc.lut = lut;
 	const u32 win_len = window.ext0*window.ext1*window.ext2;
 	for (u32 i = threadIdx.x; i < win_len; i += blockDim.x) acc.win[i] = 0;
 #if XO_VOX_DDA

@@ -99,7 +99,7 @@ struct mc_rectf_t { mc_point2f_t top_left; mc_fp_t width, height; };
 struct mc_circf_t { mc_point2f_t center; mc_fp_t r; };
 
 // lookup-table descriptor (mcbase.template.h:2494-2503)
-struct mc_fp_lut_t { mc_fp_t first, inv_span; mc_size_t n, offset; };
+typedef xo::FpLut mc_fp_lut_t;
 
 // ---- constants ---------------------------------------------------------------------------
 #define FP_LITERAL(x) x##f
@@ -293,17 +293,16 @@ __device__ __forceinline__ void scatter_direction(mc_point3f_t *dir, mc_fp_t cos
 }
 
 // ---- lookup tables -------------------------------------------------------------------------------
-// linear interpolation in a table of the float pool (mcbase.template.h:2505-2560)
+// linear interpolation in a table of the float pool, with the reference's
+// semantics (mcbase.template.h:2507-2548, see xo::lut_sample): the first index is
+// *rounded*, the weight is the fractional part, the value is written only when
+// the position falls inside the table
 __device__ __forceinline__ void fp_linear_lut_rel_sample(const mc_fp_t *lut_array, const mc_fp_lut_t *lut, mc_fp_t rel, mc_fp_t *value) {
-	mc_fp_t fi = rel*(mc_fp_t)(lut->n - 1);
-	fi = mc_fclip(fi, FP_0, (mc_fp_t)(lut->n - 1));
-	mc_size_t i1 = mc_uint(fi);
-	mc_size_t i2 = i1 + 1 < lut->n ? i1 + 1 : lut->n - 1;
-	mc_fp_t w2 = fi - (mc_fp_t)i1;
-	*value = lut_array[lut->offset + i1]*(FP_1 - w2) + lut_array[lut->offset + i2]*w2;
+	xo::lut_sample_index(lut_array, lut->n, lut->offset, rel*(mc_fp_t)(lut->n - 1), false, value);
 }
 __device__ __forceinline__ void fp_linear_lut_sample(const mc_fp_t *lut_array, const mc_fp_lut_t *lut, mc_fp_t x, mc_fp_t *value) {
-	fp_linear_lut_rel_sample(lut_array, lut, (x - lut->first)*lut->inv_span, value);
+	xo::lut_sample_index(lut_array, lut->n, lut->offset,
+		(x - lut->first)*lut->inv_span*(mc_fp_t)(lut->n - 1), true, value);
 }
 
 // ---- debugging hooks: compiled out ---------------------------------------------------------------

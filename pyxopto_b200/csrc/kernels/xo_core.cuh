@@ -257,6 +257,28 @@ __device__ __forceinline__ void scatter_direction(P3 &d, float ct, float fi) {
 #endif
 }
 
+// ---- linear lookup tables in the float pool --------------------------------------
+// descriptor mc_fp_lut_t (mcbase.template.h:2494-2503) and the sampling macros
+// fp_linear_lut_(rel_)sample (:2507-2548), restated with their quirks: the first
+// index is the *rounded* position, the interpolation weight its fractional part,
+// and `value` is left untouched when the position falls outside the table.
+struct FpLut { float first, inv_span; u32 n, offset; };
+__device__ __forceinline__ void lut_sample_index(const float *pool, u32 n, u32 offset,
+		float fp_index, bool range_on_position, float *value) {
+	const u32 i1 = f2u(fp_index + 0.5f);
+	const bool inside = range_on_position ? (fp_index >= 0.0f && fp_index <= (float)(n - 1))
+		: (i1 < n);
+	if (inside) {
+		const float w2 = fp_index - floorf(fp_index);
+		const i32 nxt = (i32)i1 + 1;
+		const u32 i2 = (u32)clipi(nxt, 0, (i32)n - 1);
+		*value = pool[offset + i1]*(1.0f - w2) + pool[offset + i2]*w2;
+	}
+}
+__device__ __forceinline__ void lut_sample(const float *pool, const FpLut &lut, float x, float *value) {
+	lut_sample_index(pool, lut.n, lut.offset, (x - lut.first)*lut.inv_span*(float)(lut.n - 1), true, value);
+}
+
 // ---- accumulators ------------------------------------------------------------
 // The flat accumulator buffer holds detector bins first (pack order) and the
 // fluence grid after them.  Bins [0, priv_len) are privatised per CTA in shared
@@ -291,6 +313,7 @@ struct Accu {
 	u32 priv_len;
 	u32 *win;         // shared memory, ext0*ext1*ext2 words (0 extents: no window)
 	u32 priv_s, win_s;  // shared-space addresses of priv / win (set by bind())
+	const float *lut;   // float lookup-table pool (shared-memory copy if staged): *Lut plugins
 	// (the empty asm keeps both addresses in registers: the compiler otherwise
 	// rematerialises them from SR_CgaCtaId and the kernel parameters before every
 	// atomic, 7 instructions per deposit)

@@ -28,6 +28,22 @@ struct DetTotal {                   // mcdetector/total.py
 	}
 };
 
+// mcdetector/total.py:240-330 TotalLut: the weight is scaled by an angular
+// sensitivity looked up (linear table in the float pool) at |cos| of the
+// incidence angle against the detector direction
+struct DetTotalLut {
+	FpLut lut; P3 direction; u32 offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		(void)pos;
+		float sensitivity = 0.0f;
+		lut_sample(acc.lut, lut, fabsf(dot3(dir, direction)), &sensitivity);
+		u32 iw = weight_u32(w*sensitivity, true);
+		if (iw > 0) acc.add(offset, iw);
+	}
+};
+
 struct DetRadial {                  // mcdetector/radial.py
 	P3 direction; P2 position; float r_min, inv_dr, cos_min; u32 n, offset; i32 log_scale;
 	static constexpr bool active = true;

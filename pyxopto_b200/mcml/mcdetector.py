@@ -13,6 +13,7 @@ from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import geometry
 from ..mcbase.mcutil.axis import Axis, RadialAxis, SymmetricAxis  # noqa: F401
 from ..mcbase.mcutil.fiber import MultimodeFiber, FiberLayout  # noqa: F401
+from ..mcbase.mcutil.lut import CollectionLut, LinearLut  # noqa: F401
 
 NONE, TOP, BOTTOM, SPECULAR = 'none', 'top', 'bottom', 'specular'
 
@@ -129,6 +130,49 @@ class Total(Detector):
 
     def todict(self):
         return {'type': 'Total', 'cosmin': self._cosmin,
+                'direction': self._direction.tolist()}
+
+
+class TotalLut(Detector):
+    """Total reflectance / transmittance weighted by an angular sensitivity table
+    (total.py:240-460)."""
+    cu_type = 'xo::DetTotalLut'
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClTotalLut(cltypes.Structure):
+            _fields_ = [('lut', CollectionLut.cl_type(mc)), ('direction', T.mc_point3f_t),
+                        ('offset', T.mc_size_t)]
+        return ClTotalLut
+
+    def __init__(self, lut, direction=(0.0, 0.0, 1.0)):
+        if isinstance(lut, TotalLut):
+            o = lut
+            lut, direction = o.lut, o.direction
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            raw, nphotons = np.zeros((1,)), 0
+        super().__init__(raw, nphotons)
+        self.lut = lut
+        self.direction = direction
+
+    def _set_lut(self, lut):
+        if not isinstance(lut, CollectionLut):
+            raise TypeError('The lookup table must be an instance of CollectionLut!')
+        self._lut = lut
+
+    lut = property(lambda self: self._lut, _set_lut)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        target.lut = self._lut.cl_pack(mc, target.lut)
+        target.direction.fromarray(self._direction)
+        return target
+
+    def todict(self):
+        return {'type': 'TotalLut', 'lut': self._lut.todict(),
                 'direction': self._direction.tolist()}
 
 

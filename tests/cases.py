@@ -769,3 +769,29 @@ MCML_CASES['mcml_surface_fiberarray'] = mcml_surface_fiberarray
 ALL_CASES['mcml_surface_fiberarray'] = mcml_surface_fiberarray
 GEOMETRY['mcml_surface_fiberarray'] = 'mcml'
 GOLDEN_RUN['mcml_surface_fiberarray'] = (4000, 16)
+
+
+def mcml_hg_line_totallut(mc, **kw):
+    """TotalLut detectors: angular sensitivity tables in the float lookup-table pool
+    (mcdetector/total.py:240, mcutil/lut.py CollectionLut).  The reference's
+    TotalLut does not switch MC_USE_FP_LUT on itself, so its kernel only builds
+    next to another table user - here the Lut phase function."""
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase.mcutil.lut import CollectionLut
+    else:
+        CollectionLut = mc.mcdetector.CollectionLut
+    ct = np.linspace(0.0, 1.0, 21)
+    top = mc.mcdetector.TotalLut(CollectionLut(ct**2, ct, n=100))
+    bottom = mc.mcdetector.TotalLut(CollectionLut(np.sqrt(np.linspace(0.2, 1.0, 9)),
+                                                  np.linspace(0.2, 1.0, 9), n=33),
+                                    direction=(0.1, 0.0, 1.0))
+    det = mc.mcdetector.Detectors(top=top, bottom=bottom, specular=mc.mcdetector.Total())
+    params, lut = _hg_lut()
+    return mc.Mc(_layers(mc, mc.mcpf.Lut(params, lut)), mc.mcsource.Line(), det,
+                 rnginit=262626, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hg_line_totallut'] = mcml_hg_line_totallut
+ALL_CASES['mcml_hg_line_totallut'] = mcml_hg_line_totallut
+GEOMETRY['mcml_hg_line_totallut'] = 'mcml'
+GOLDEN_RUN['mcml_hg_line_totallut'] = (3000, 16)
