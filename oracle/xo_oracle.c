@@ -465,6 +465,18 @@ static inline void fp_lut_sample(const float *buffer, const fp_lut_t *lut, float
 	}
 }
 
+typedef struct { m3f T; p3f position, direction; float radius, n; fp_lut_t lut; } src_ufiberlut;  /* mcsource/fiber.py:719-727 */
+/* fp_linear_lut_rel_sample (mcbase.template.h:2517-2527) */
+static inline void fp_lut_rel_sample(const float *buffer, const fp_lut_t *lut, float where, float *value) {
+	float fp_index = where*(lut->n - 1);
+	uint32_t index1 = (uint32_t)(fp_index + FP_0p5);
+	if (index1 < lut->n) {
+		float w2 = fp_index - floorf(fp_index);
+		uint32_t index2 = (uint32_t)iclip((int32_t)(index1 + 1), 0, (int32_t)(lut->n - 1));
+		*value = buffer[lut->offset + index1]*(FP_1 - w2) + buffer[lut->offset + index2]*w2;
+	}
+}
+
 /* ---- detectors ------------------------------------------------------------- */
 enum { LOC_TOP = 0, LOC_BOTTOM = 1, LOC_SPECULAR = 2 };
 
@@ -1038,6 +1050,42 @@ static void launch_mcml(sim_t *s) {
 		s->layer_index = 1;
 		break;
 	}
+	case XO_SRC_UNIFORMFIBERLUT: {                     /* mcsource/fiber.py:766-830 */
+		const src_ufiberlut *src = (const src_ufiberlut *)j->source;
+		float sin_fi, cos_fi, sin_theta, cos_theta = FP_0; p3f pt_src, pt_mc;
+		float r = m_sqrt(sim_random(s))*src->radius;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		pt_src.x = r*cos_fi; pt_src.y = r*sin_fi; pt_src.z = FP_0;
+		m3f T = src->T;
+		transform3(&T, &pt_src, &pt_mc);
+		float k = m_div(FP_0 - pt_mc.z, src->direction.z);
+		pt_mc.x += k*src->direction.x;
+		pt_mc.y += k*src->direction.y;
+		pt_mc.z = FP_0;
+		s->pos.x = src->position.x + pt_mc.x;
+		s->pos.y = src->position.y + pt_mc.y;
+		s->pos.z = FP_0;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		fp_lut_rel_sample(j->fp_lut, &src->lut, sim_random(s), &cos_theta);
+		sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+		sin_theta = m_div(sin_theta, src->n);
+		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+		pt_src.x = cos_fi*sin_theta; pt_src.y = sin_fi*sin_theta; pt_src.z = cos_theta;
+		p3f direction;
+		transform3(&T, &pt_src, &direction);
+		float cc = cos_critical(src->n, medium_n(j, 1));
+		p3f normal = { FP_0, FP_0, FP_1 };
+		p3f refracted = direction;
+		if (direction.z > cc)
+			refract3(&direction, &normal, src->n, medium_n(j, 1), &refracted);
+		s->dir = refracted;
+		float specular_r = reflectance(src->n, medium_n(j, 1), direction.z, cc);
+		s->weight = FP_1 - specular_r;
+		if (j->det_kind[LOC_SPECULAR])
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &direction, specular_r);
+		s->layer_index = 1;
+		break;
+	}
 	case XO_SRC_ISOTROPICPOINT: {                      /* mcsource/point.py:76-135 */
 		const src_isopoint *src = (const src_isopoint *)j->source;
 		float sin_fi, cos_fi, sin_theta, cos_theta, specular_r = FP_0;
@@ -1081,6 +1129,7 @@ static inline p3f source_position(const xo_oracle_job *j) {
 		case XO_SRC_GAUSSIANBEAM: off = sizeof(m3f); break;
 		case XO_SRC_UNIFORMFIBER: off = sizeof(m3f); break;
 		case XO_SRC_LAMBERTIANFIBER: off = sizeof(m3f); break;
+		case XO_SRC_UNIFORMFIBERLUT: off = sizeof(m3f); break;
 		case XO_SRC_UNIFORMBEAM: off = sizeof(m3f); break;
 		default: off = 0; break;
 	}

@@ -273,7 +273,7 @@ McKernel(
 	Rng rng;
 	rng.load(rng_state_x[gid]);
 	rng.a = rng_state_a[gid];
-	MlCtx ctx; ctx.layers = sh_layers; ctx.num_layers = (i32)num_layers;
+	MlCtx ctx; ctx.layers = sh_layers; ctx.num_layers = (i32)num_layers; ctx.lut = lut;
 #if XO_USE_RMAX
 	const P3 src_pos = source.origin();
 	const float rmax2 = rmax*rmax;

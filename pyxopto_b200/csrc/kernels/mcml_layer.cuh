@@ -16,6 +16,7 @@ struct MlLayer {                    // mcml/mclayer/layer.py:57-69
 struct MlCtx {
 	const MlLayer *layers;          // shared memory
 	i32 num_layers;
+	const float *lut;               // float lookup-table pool (*Lut sources)
 	static constexpr bool has_specular = XoDetSpecular::active;
 	__device__ __forceinline__ float layer_n(int i) const { return layers[i].n; }
 	__device__ __forceinline__ float layer_cc_bottom(int i) const { return layers[i].cc_bottom; }

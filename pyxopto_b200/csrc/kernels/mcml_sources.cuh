@@ -164,6 +164,44 @@ struct SrcLambertianFiber {         // mcsource/fiber.py:537-545, launch :567-63
 	}
 };
 
+struct SrcUniformFiberLut {         // mcsource/fiber.py:719-727, launch :766-830
+	M3 T; P3 position, direction; float radius, n; FpLut lut;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf;
+		float r = M::sqrt(rng.next())*radius;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		P3 ps = { r*cf, r*sf, 0.0f };
+		P3 pm = transform3(T, ps);
+		float k = M::div(0.0f - pm.z, direction.z);
+		pm.x += k*direction.x;
+		pm.y += k*direction.y;
+		L.pos.x = position.x + pm.x;
+		L.pos.y = position.y + pm.y;
+		L.pos.z = 0.0f;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		// emission cosine from the table (sampled with a uniform number)
+		float ct = 0.0f;
+		lut_sample_index(ctx.lut, lut.n, lut.offset, rng.next()*(float)(lut.n - 1), false, &ct);
+		float st = M::sqrt(1.0f - ct*ct);
+		st = M::div(st, n);
+		ct = M::sqrt(1.0f - st*st);
+		P3 ds = { cf*st, sf*st, ct };
+		P3 d = transform3(T, ds);
+		float n1 = ctx.layer_n(1);
+		float cc = cos_critical(n, n1);
+		// this source tests the *direction* against the critical cosine: refracted
+		P3 normal = { 0.0f, 0.0f, 1.0f };
+		L.dir = (d.z > cc) ? refract3(d, normal, n, n1) : d;
+		float rs = reflectance(n, n1, d.z, cc);
+		L.weight = 1.0f - rs;
+		L.spec_dir = d;
+		L.spec_weight = rs;
+		L.layer = 1;
+	}
+};
+
 struct SrcIsotropicPoint {          // mcsource/point.py:46-49
 	P3 position; u32 layer_index;
 	__device__ __forceinline__ P3 origin() const { return position; }

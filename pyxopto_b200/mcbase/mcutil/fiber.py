@@ -40,6 +40,47 @@ class MultimodeFiber:
             self.dcore, self.dcladding, self.ncore, self.na)
 
 
+class MultimodeFiberLut:
+    """Multimode fiber with tabulated emission / collection characteristics
+    (mcutil/fiber.py:224-382)."""
+    compute_na = staticmethod(MultimodeFiber.compute_na)
+    compute_ncladding = staticmethod(MultimodeFiber.compute_ncladding)
+
+    def __init__(self, dcore: float, dcladding: float, ncore: float, ncladding: float = None,
+                 emission=None, collection=None):
+        from .lut import CollectionLut, EmissionLut
+        self.dcore = float(dcore)
+        self.dcladding = float(dcladding)
+        self.ncore = float(ncore)
+        self._ncladding = self.ncore if ncladding is None else float(ncladding)
+        if isinstance(emission, str):
+            emission = EmissionLut.fromfile(emission)
+        elif isinstance(emission, np.ndarray):
+            emission = EmissionLut(emission)
+        if isinstance(collection, str):
+            collection = CollectionLut.fromfile(collection)
+        self._emission_lut = emission
+        self._collection_lut = collection
+
+    def validate(self):
+        if self.dcore > self.dcladding:
+            raise ValueError('Fiber core diameter must be smaller than the fiber '
+                             'cladding diameter!')
+
+    ncladding = property(lambda self: self._ncladding)
+    emission = property(lambda self: self._emission_lut)
+    collection = property(lambda self: self._collection_lut)
+
+    def todict(self) -> dict:
+        return {'dcore': self.dcore, 'dcladding': self.dcladding, 'ncore': self.ncore,
+                'emission': self._emission_lut, 'collection': self._collection_lut,
+                'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'MultimodeFiberLut(dcore={:f}, dcladding={:f}, ncore={:f})'.format(
+            self.dcore, self.dcladding, self.ncore)
+
+
 class FiberLayout:
     """A fiber placed at ``position`` (x, y[, z]) and tilted into ``direction``
     (mcutil/fiber.py:384-470)."""

@@ -131,3 +131,48 @@ class CollectionLut(LinearLut):
             costheta = np.asarray(costheta)
         ct = np.linspace(costheta.min(), costheta.max(), n)
         super().__init__(interp1d(costheta, sensitivity)(ct), ct[0], ct[-1])
+
+
+class EmissionLut(LinearLut):
+    """Table for sampling the emission-angle cosine of a source with the given
+    angular radiance (azimuthal symmetry): sampled with a uniform random number
+    from [0, 1] (mcutil/lut.py:240-325; CDF by Simpson's rule or adaptive
+    quadrature)."""
+    def __init__(self, radiance, costheta=None, n: int = 2000, npts: int = 10000,
+                 meth: str = 'simps'):
+        if isinstance(radiance, (str, EmissionLut)):
+            super().__init__(radiance)
+            return
+        from scipy.interpolate import interp1d
+        lut_random = np.linspace(0.0, 1.0, n)
+        radiance = np.asarray(radiance, dtype=np.float64)
+        if costheta is None:
+            costheta = np.linspace(0.0, 1.0, radiance.size)
+        else:
+            costheta = np.asarray(costheta, dtype=np.float64)
+        if radiance.size != costheta.size:
+            raise ValueError('The sizes of the radiance and costheta array must be equal!')
+        radiance_f = interp1d(costheta, radiance*np.sqrt(1.0 - costheta**2))
+        ct_range = costheta.min(), costheta.max()
+        if meth == 'simps':
+            npts = max(int((max(2*n, npts)//2))*2 + 1, 3)
+            ct = np.linspace(ct_range[0], ct_range[1], max(n, npts))
+            cdf = np.zeros([int(ct.size//2) + 1])
+            radiance_ct = radiance_f(ct)
+            dx = (ct[-1] - ct[0])/(ct.size - 1)
+            cdf[1:] = dx/3.0*(
+                radiance_ct[:-2:2] + 4.0*radiance_ct[1:-1:2] + radiance_ct[2::2])
+            cdf = cdf.cumsum()
+            cdf /= cdf[-1]
+            lut = interp1d(cdf, ct[::2])(lut_random)
+        elif meth == 'quad':
+            from scipy.integrate import quad
+            ct = np.linspace(ct_range[0], ct_range[1], max(n, npts))
+            cdf = np.zeros_like(ct)
+            for index, ct_item in enumerate(ct):
+                cdf[index] = quad(radiance_f, ct_range[0], ct_item)[0]
+            cdf /= cdf[-1]
+            lut = interp1d(cdf, ct)(lut_random)
+        else:
+            raise ValueError('Unknown integration method "{}"!'.format(meth))
+        super().__init__(lut, 0.0, 1.0)

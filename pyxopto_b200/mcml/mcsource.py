@@ -7,7 +7,8 @@ import numpy as np
 from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import boundary, geometry
-from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
+from ..mcbase.mcutil.fiber import MultimodeFiber, MultimodeFiberLut  # noqa: F401
+from ..mcbase.mcutil.lut import EmissionLut, LinearLut  # noqa: F401
 
 
 class Source(McObject):
@@ -315,6 +316,39 @@ class LambertianFiber(UniformFiber):
         target.position.fromarray(self._position)
         target.direction.fromarray(self._direction)
         target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+
+class UniformFiberLut(UniformFiber):
+    """Optical fiber with a tabulated angular emission characteristic
+    (mcsource/fiber.py:690-1017): the emission cosine comes from an EmissionLut in
+    the float pool; unlike UniformFiber the direction *is* refracted into the
+    sample."""
+    cu_type = 'xo::SrcUniformFiberLut'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformFiberLut(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('n', T.mc_fp_t), ('lut', LinearLut.cl_type(mc))]
+        return ClUniformFiberLut
+
+    @staticmethod
+    def cl_options(mc):
+        return [('MC_USE_FP_LUT', True)]
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius = self._fiber.dcore*0.5
+        target.n = self._fiber.ncore
+        self._fiber.emission.cl_pack(mc, target.lut)
         return target, None, None
 
 

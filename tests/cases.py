@@ -795,3 +795,31 @@ MCML_CASES['mcml_hg_line_totallut'] = mcml_hg_line_totallut
 ALL_CASES['mcml_hg_line_totallut'] = mcml_hg_line_totallut
 GEOMETRY['mcml_hg_line_totallut'] = 'mcml'
 GOLDEN_RUN['mcml_hg_line_totallut'] = (3000, 16)
+
+
+def mcml_lut_ufiberlut_totallut(mc, **kw):
+    """UniformFiberLut source (tabulated emission, refracted into the sample) under a
+    tilted TotalLut detector (mcsource/fiber.py:690, mcutil/lut.py EmissionLut)."""
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase.mcutil.lut import CollectionLut, EmissionLut
+        from xopto.mcml.mcutil.fiber import MultimodeFiberLut
+    else:
+        CollectionLut, EmissionLut = mc.mcdetector.CollectionLut, mc.mcsource.EmissionLut
+        MultimodeFiberLut = mc.mcsource.MultimodeFiberLut
+    ct = np.linspace(np.cos(np.deg2rad(25.0)), 1.0, 40)
+    emission = EmissionLut(np.exp(-((1.0 - ct)/0.03)**2), ct, n=200, npts=2000)
+    fib = MultimodeFiberLut(200e-6, 220e-6, 1.462, None, emission=emission)
+    cs = np.linspace(0.0, 1.0, 11)
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.TotalLut(CollectionLut(cs, cs, n=64), direction=(0.0, 0.1, 1.0)),
+        bottom=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    params, lut = _hg_lut()
+    return mc.Mc(_layers(mc, mc.mcpf.Lut(params, lut)),
+                 mc.mcsource.UniformFiberLut(fib, position=(0.1e-3, 0, 0), direction=(0.15, 0.0, 1)),
+                 det, rnginit=383838, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_lut_ufiberlut_totallut'] = mcml_lut_ufiberlut_totallut
+ALL_CASES['mcml_lut_ufiberlut_totallut'] = mcml_lut_ufiberlut_totallut
+GEOMETRY['mcml_lut_ufiberlut_totallut'] = 'mcml'
+GOLDEN_RUN['mcml_lut_ufiberlut_totallut'] = (3000, 16)
