@@ -136,7 +136,8 @@ def main():
         'c3_vox': 'mcvox 201^3 voxel 2-layer skin + blood vessel (5 um voxels), '
                   'GaussianBeam sigma 50 um, Fluence deposition grid',
         'c4_trace': 'mcml slab, RadialPl 100x300 (path-length resolved) + Trace maxlen 512 of every '
-                    'packet + device filter + sampling_volume 200^3',
+                    'packet + device filter + sampling_volume 200^3 (e2e: the accepted rows feed '
+                    'sampling_volume on the device; the host receives detectors, counts and the grid)',
         'c5_slab': 'mcml semi-infinite n=1.337 under air, (mua, musr) sweep point(s), g=0.8, '
                    'Line + Radial 500, rmax 25 mm',
         'c5_cyl': 'mccyl single cylinder r=5 mm n=1.337 mua=1/cm mus=100/cm g=0.8, '

@@ -13,6 +13,7 @@ in-tree by content hash.
 """
 import ctypes
 import time
+import weakref
 
 import numpy as np
 
@@ -597,11 +598,19 @@ class McBase(CuWorker):
         if self._trace is not None:
             trace_res = out_trace if out_trace is not None else type(self._trace)(self._trace)
             if self._trace.filter is not None and self.device_trace_filter:
-                n_sel, rows, n_dropped = self.filter_trace_on_device(nphotons)
+                lazy = out_trace is None and self.lazy_trace_rows
+                n_sel, rows, n_dropped = self.filter_trace_on_device(
+                    nphotons, download=not lazy)
                 data = {np.dtype(self._types.np_float): [rows],
                         np.dtype(self._types.np_int): [n_sel]}
                 trace_res.update_data(self, data, nphotons=nphotons, prefiltered=True,
                                       n_dropped=n_dropped)
+                if lazy:
+                    # the accepted rows (16 KB each at maxlen 512) stay on the device
+                    # until somebody reads `trace.data`
+                    trace_res._set_lazy_rows(self._lazy_rows_loader(
+                        (n_sel.size, int(self._trace.maxlen)), rows.dtype))
+                    self._lazy_trace = weakref.ref(trace_res)
             else:
                 data = self._download_allocations(self._trace, nphotons)
                 trace_res.update_data(self, data, nphotons=nphotons)
@@ -680,6 +689,29 @@ class McBase(CuWorker):
     device_trace_filter = True
     _FILTER_SRC = '#include "xo_trace_kernels.cuh"\n'
 
+    # True: the rows accepted by the device-side filter are downloaded when the
+    # result's `data` is first read (or before the device buffer is reused)
+    lazy_trace_rows = True
+    _lazy_trace = None
+
+    def _lazy_rows_loader(self, shape, dtype):
+        buf, stream = self._device_trace['floats'], self._stream
+
+        def load():
+            rows = np.empty(shape, dtype=dtype)
+            if rows.size:
+                buf.download(stream, rows)
+            return rows
+        return load
+
+    def _materialize_lazy_trace(self):
+        """Download the rows of an outstanding lazy Trace result (called before
+        the compact-row buffer is overwritten)."""
+        ref, self._lazy_trace = self._lazy_trace, None
+        res = ref() if ref is not None else None
+        if res is not None and res.rows_on_device_only:
+            res.data                                   # noqa: B018  (triggers the download)
+
     def filter_trace_on_device(self, nphotons: int, download: bool = True):
         """Evaluate ``self.trace.filter`` on the trace rows of the last run where
         they are, compact the accepted rows in packet order and return
@@ -687,6 +719,7 @@ class McBase(CuWorker):
         With ``download=False`` only the counts are read back and the compact
         rows stay on the device for ``sampling_volume``."""
         from ..cu import abi
+        self._materialize_lazy_trace()
         trace = self._trace
         tp = self._packed['trace']
         nphotons = int(nphotons)
@@ -721,11 +754,13 @@ class McBase(CuWorker):
         self._run_report['filter_ms'] = ev0.elapsed_ms(ev1)
         self._run_report['filter_accepted'] = n_sel
         n_host = np.zeros((n_sel,), dtype=self._types.np_int)
-        rows = np.zeros((n_sel, maxlen), dtype=trace.dtype(self))
+        # (TraceCompact writes whole rows including their zero tails: no zero fill)
+        rows = np.empty((n_sel, maxlen) if download else (0, maxlen), dtype=trace.dtype(self))
         if n_sel:
             obuf_i.download(self._stream, n_host)
             if download:
                 obuf_f.download(self._stream, rows)
+
         self._device_trace = dict(n=n_sel, maxlen=maxlen, ints=obuf_i, floats=obuf_f)
         return n_host, rows, n_dropped
 

@@ -242,6 +242,23 @@ class Trace(McObject):
 
     filter = property(lambda self: self._filter, _set_filter)
 
+    # The rows of a device-filtered run may still be on the device only: `_data`
+    # then fetches them on first access (Mc.run installs `_lazy_rows`; the
+    # simulator materialises an outstanding result before it reuses the buffer).
+    # A result that is only handed to Mc.sampling_volume never downloads its rows.
+    def _get_rows(self):
+        loader = self.__dict__.get('_lazy_rows')
+        if loader is not None:
+            self.__dict__['_lazy_rows'] = None
+            self.__dict__['_rows'] = loader()
+        return self.__dict__.get('_rows')
+
+    def _set_rows(self, rows):
+        self.__dict__['_lazy_rows'] = None
+        self.__dict__['_rows'] = rows
+
+    _data = property(_get_rows, _set_rows)
+
     # token of the device-resident copy of the rows (set by Mc.run, dropped as
     # soon as the host arrays are replaced): lets Mc.sampling_volume skip the
     # re-upload of rows that never left the device
@@ -250,6 +267,15 @@ class Trace(McObject):
     def _set_data(self, d):
         self._data = d
         self._device_token = None
+
+    def _set_lazy_rows(self, loader):
+        """Rows that are fetched from the device on first access of ``data``."""
+        self.__dict__['_rows'] = None
+        self.__dict__['_lazy_rows'] = loader
+
+    rows_on_device_only = property(
+        lambda self: self.__dict__.get('_lazy_rows') is not None, None, None,
+        'True while the rows of this result have not been downloaded yet.')
 
     def _set_n(self, n):
         self._n = n

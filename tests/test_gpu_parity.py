@@ -517,3 +517,28 @@ def test_device_side_sampling_volume_conversion_is_bit_identical():
     a, b = out
     assert a.data.sum() > 0 and a.weight == b.weight
     assert np.array_equal(a.data, b.data)
+
+
+def test_lazy_trace_rows_equal_eager_rows():
+    """Rows accepted by the device-side filter are fetched when ``trace.data`` is
+    first read; a result that is still outstanding when the next run reuses the
+    device buffer is materialised first.  Same rows as the eager download."""
+    name = 'mcml_lut_iso_radialpl_trace'
+    n = run_size(name)[0]*4
+    out = {}
+    for lazy in (True, False):
+        sim, geom, mc = _det_sim(name)
+        sim.trace.filter = _filters(mc)[name]
+        sim.lazy_trace_rows = lazy
+        kw = dict(maxthreads=256, wgsize=64)
+        t1 = sim.run(n, **kw)[0]
+        assert t1.rows_on_device_only == lazy
+        t2 = sim.run(n, **kw)[0]              # reuses the compact-row buffer
+        assert not t1.rows_on_device_only     # ... after t1 was materialised
+        sv = cases.make_sv(mc, name)
+        sim.sampling_volume(t2, sv)           # consumes the device-resident rows
+        assert t2.rows_on_device_only == lazy
+        out[lazy] = (t1.data.copy(), t1.n.copy(), t2.data.copy(), t2.n.copy(), sv.data.copy())
+    for a, b in zip(out[True], out[False]):
+        assert a.shape == b.shape and a.size > 0
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
