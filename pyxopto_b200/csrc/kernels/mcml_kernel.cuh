@@ -6,26 +6,27 @@
 // machine mapping:
 //   * one packet per thread, regenerated in place until the packet budget is
 //     exhausted, packet state entirely in registers;
-//   * warp launch queue (throughput mode): new packets are not launched by the
-//     lane that needs one.  When the queue of a warp is empty, all 32 lanes run
-//     the source code together (one atomic claims 32 packet indices) and park
-//     the launched packets in a per-warp shared-memory queue; a lane whose packet
-//     terminated pops one (3 LDS).  The long launch path therefore always runs
-//     with full warps instead of the 1-2 lanes that happen to need a packet;
-//   * deferred interface physics (throughput mode): a lane that hits a layer
-//     interface parks in a BND state and idles until at least `refill` lanes of
-//     its warp wait there (or nothing else runs); then they run Fresnel /
-//     detector deposit / reload of the layer constants together;
+//   * lane state machine (throughput mode): RUN / BND (step ends on an interface)
+//     / DEAD (needs a packet) / DRY.  The common trip pays one VOTE; a *service
+//     round* fires when `refill` lanes of the warp wait (or every lane that still
+//     has work waits) and runs, jointly for the waiting lanes: the interface
+//     physics (move onto the interface, Fresnel, detector deposit, reload of the
+//     layer constants), then the refill of the warp's launch queue (all 32 lanes
+//     run the source code together, one atomic claims 32 packet indices, the
+//     launched packets park in shared memory), then the pops.  The rare, long
+//     paths therefore run with several lanes instead of the 1-2 that happen to
+//     need them;
 //   * layer table (+ derived per-layer constants + pf lookup tables) staged once
 //     per CTA in shared memory; the constants of the *current* layer are cached
 //     in registers and reloaded only when the packet changes layer;
 //   * plugin parameter structs are __grid_constant__ kernel parameters;
-//   * detector bins privatised per CTA in shared memory (Accu), fluence through
-//     RED.E.ADD.64;
+//   * detector bins privatised per CTA in shared memory (Accu); fluence grids
+//     through a CTA-private window in shared memory (32-bit partial sums, exact
+//     64-bit totals) and RED.E.ADD.64 for the cells outside it;
 //   * packet scheduling: deterministic mode = static block schedule (work-item t
 //     owns packets [base_t, base_t+n_t)), a legal outcome of the reference's
 //     racing atomic counter (mcml.template.c:460,790); throughput mode = the
-//     same counter, but claimed in chunks of `chunk` packets per atomic.
+//     same counter, claimed 32 packets at a time by a warp (launch queue).
 //
 // Two loops share prologue and epilogue: the deterministic loop evaluates the
 // reference's expressions in the reference's order with DetMath, each work-item
@@ -184,8 +185,8 @@ McKernel(
 	xo::u32 lut_len,            // floats of fp_lut staged in shared memory (0: read global)
 	xo::u32 priv_len,           // accumulator bins privatised per CTA
 	const __grid_constant__ xo::FluWindow window,   // fluence cells privatised per CTA
-	xo::u32 chunk,              // throughput mode: lanes per warp waiting for a packet that trigger a pop
-	xo::u32 refill)             // lanes per warp waiting at an interface that trigger its joint handling
+	xo::u32 chunk,              // (unused by this kernel: packets are claimed 32 at a time per warp)
+	xo::u32 refill)             // throughput mode: waiting lanes per warp that trigger a service round
 {
 	using namespace xo;
 	extern __shared__ __align__(16) unsigned char xo_smem[];

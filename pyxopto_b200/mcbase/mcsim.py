@@ -318,8 +318,8 @@ class McBase(CuWorker):
         """False when the rmax test can never fire (compiled out of the loop)."""
         return bool(np.isfinite(np.float32(self._rmax)))
 
-    # idle lanes per warp that trigger a joint launch (throughput mode); sources
-    # with a long launch path amortise it over more lanes
+    # waiting lanes per warp (interface pending / packet needed) that trigger a
+    # service round of the throughput loops; None: the source's / geometry's default
     refill_lanes = None
     default_refill_lanes = 1
     min_blocks = None                # __launch_bounds__ second argument (None: automatic)
