@@ -125,7 +125,8 @@ McKernel(
 	xo::u32 lut_len,
 	xo::u32 priv_len,
 	const __grid_constant__ xo::FluWindow window,
-	xo::u32 chunk)
+	xo::u32 chunk,
+	xo::u32 refill)             // throughput mode: waiting lanes per warp that trigger a service round
 {
 	using namespace xo;
 	extern __shared__ __align__(16) unsigned char xo_smem[];
@@ -166,6 +167,180 @@ McKernel(
 	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
 	(void)tcfg;
 
+#if !XO_DETERMINISTIC
+	// ======== throughput loop =====================================================
+	// Lane states as in mcml_kernel.cuh: RUN / BND_IN, BND_OUT (the step ended on the
+	// inner / outer cylinder of the layer, interface physics pending) / DEAD (needs a
+	// packet) / DRY.  One VOTE per trip; a service round runs the interface physics
+	// (Fresnel against the radial normal, detector deposit), the packet claims and
+	// the launches jointly once `refill` lanes wait.
+	enum : u32 { ST_RUN = 0, ST_DRY = 1, ST_BND_IN = 2, ST_BND_OUT = 3, ST_DEAD = 4 };
+	bool started = false;
+	u32 iterations = 0;
+	{
+		P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
+		float weight = 0.0f;
+		i32 layer = 1;
+		float opl = 0.0f;
+		u32 packet = 0, trace_count = 0, flags = 0;
+		(void)opl; (void)packet; (void)trace_count; (void)flags;
+		u32 state = ST_DEAD;
+		u32 pk_next = 0, pk_end = 0;
+		bool budget_dry = false;
+		u32 thr_eff = refill < 1u ? 1u : (refill > 32u ? 32u : refill);
+
+#define XO_CYL_END_TRIP() do { \
+		{ \
+			float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
+			if (ex_*ex_ + ey_*ey_ + ez_*ez_ > rmax2 || weight <= 0.0f) { done = true; flags |= EV_ESCAPED; } \
+		} \
+		if (XO_TRACE) { \
+			flags |= done ? EV_TERMINATED : 0u; \
+			if (XO_TRACE == XO_TRACE_ALL || ((XO_TRACE & XO_TRACE_END) && done)) { \
+				if (trace_event(tcfg, float_buffer, packet, trace_count, flags, \
+						pos, dir, weight, opl)) ++trace_count; \
+			} \
+			if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
+		} \
+		flags = 0; \
+		state = done ? ST_DEAD : ST_RUN; \
+	} while (0)
+
+		for (;;) {
+			const u32 wait_mask = __ballot_sync(0xffffffffu, state >= ST_BND_IN);
+			if (__builtin_expect((u32)__popc(wait_mask) >= thr_eff, 0)) {
+				// ---- interface physics ---------------------------------------------
+				if (state == ST_BND_IN || state == ST_BND_OUT) {
+					const i32 next_layer = layer + (state == ST_BND_IN ? 1 : -1);
+					bool done = false;
+					u32 bf = cyl_boundary(sh_layers[layer], sh_layers[next_layer], pos, dir,
+						layer, next_layer, rng);
+					flags |= bf | EV_BOUNDARY_HIT;
+					if (!(layer > 0 && layer < (i32)num_layers)) {
+						if (layer <= 0 && XoDetOuter::active)
+							detectors.outer.deposit(acc, pos, dir, weight, opl);
+						done = true;
+					}
+					{   // direction sanity check (mccyl.template.c:928-934)
+						float len = M::sqrt(dir.x*dir.x + dir.y*dir.y + dir.z*dir.z);
+						if (fabsf(len - 1.0f) > 10.0f*XO_FP_EPS) done = true;
+					}
+					XO_CYL_END_TRIP();
+				}
+				// ---- new packets ------------------------------------------------------
+				if (state == ST_DEAD) {
+					if (pk_next >= pk_end && !budget_dry) {
+						pk_next = atomicAdd(num_packets_done, chunk);
+						pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
+						if (pk_next >= num_packets) { pk_end = pk_next; budget_dry = true; }
+					}
+					if (pk_next < pk_end) {
+						Launch L_;
+						packet = pk_next++;
+						source.launch(rng, ctx, L_);
+						pos = L_.pos; dir = L_.dir; weight = L_.weight; layer = L_.layer;
+						if (XoDetSpecular::active)
+							detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
+						trace_count = 0;
+						opl = 0.0f;
+						flags = EV_LAUNCH;
+						if (XO_TRACE & XO_TRACE_START) {
+							if (trace_event(tcfg, float_buffer, packet, trace_count, flags,
+									pos, dir, weight, opl)) ++trace_count;
+						}
+						state = ST_RUN;
+						started = true;
+					} else {
+						state = ST_DRY;
+					}
+				}
+				const u32 n_dry = (u32)__popc(__ballot_sync(0xffffffffu, state == ST_DRY));
+				if (n_dry == 32u) break;
+				thr_eff = refill < 32u - n_dry ? refill : 32u - n_dry;
+				if (thr_eff < 1u) thr_eff = 1u;
+			}
+			if (state != ST_RUN) continue;
+
+			// ---- one step of the packet ------------------------------------------------
+			const CylLayer &L = sh_layers[layer];
+			++iterations;
+			float step = -M::log(rng.next())*L.inv_mut;
+			step = fminf(step, XO_FLT_MAX);
+			bool hit = false, inwards = false;
+			if (dir.x != 0.0f || dir.y != 0.0f) {
+				// distance to the inner / outer cylinder of the layer
+				// (mccyl.template.c:147-209): a d^2 + b d + c - r^2 = 0
+				float a = dir.x*dir.x + dir.y*dir.y;
+				float b = 2.0f*(pos.x*dir.x + pos.y*dir.y);
+				float c = pos.x*pos.x + pos.y*pos.y;
+				float d_inner = XO_INF, d_outer = XO_INF;
+				float inv_2a = M::div(1.0f, 2.0f*a);
+				float D = b*b - 4.0f*a*(c - L.r_inner*L.r_inner);
+				if (L.r_inner > 0.0f && D > 0.0f) {
+					D = M::sqrt(D);
+					float d1 = (-b - D)*inv_2a;
+					float d2 = (-b + D)*inv_2a;
+					d_inner = (d2 > 2.0f*XO_FP_EPS) ? fmaxf(d1, 0.0f) : XO_INF;
+				}
+				D = b*b - 4.0f*a*(c - L.r_outer*L.r_outer);
+				if (D >= 0.0f) {
+					D = M::sqrt(D);
+					float d2 = (-b + D)*inv_2a;
+					d_outer = fmaxf(d2, 0.0f);
+				}
+				float d = fminf(d_outer, d_inner);
+				hit = step > d;
+				inwards = d_inner <= d_outer;
+				step = fminf(d, step);
+			}
+			pos.x = pos.x + dir.x*step;
+			pos.y = pos.y + dir.y*step;
+			pos.z = pos.z + dir.z*step;
+			if (XO_NEEDS_OPL) opl += L.n*step;
+			if (hit) {
+				state = inwards ? ST_BND_IN : ST_BND_OUT;
+				continue;
+			}
+			bool done = false;
+#if XO_METHOD == 1
+			if (rng.next() < L.mua_inv_mut) {
+				float deposit = weight;
+				done = true;
+				weight -= deposit;
+				flags |= EV_ABSORPTION;
+				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+			} else {
+				float fi, ct = L.pf.sample(rng, lut, &fi);
+				scatter_direction(dir, ct, fi);
+				flags |= EV_SCATTERING;
+			}
+#else
+			{
+				float deposit = weight*L.mua_inv_mut;
+				weight -= deposit;
+				flags |= EV_ABSORPTION;
+				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+			}
+			float fi, ct = L.pf.sample(rng, lut, &fi);
+			scatter_direction(dir, ct, fi);
+			flags |= EV_SCATTERING;
+			if (weight < XO_WEIGHT_MIN) {
+#if XO_USE_LOTTERY
+				if (rng.next() > XO_LOTTERY_CHANCE) done = true;
+				else weight = M::div(weight, XO_LOTTERY_CHANCE);
+#else
+				done = true;
+#endif
+			}
+#endif
+			XO_CYL_END_TRIP();
+		}
+#undef XO_CYL_END_TRIP
+		rng_state_x[gid] = rng.state();
+	}
+#else
+	// ======== deterministic loop: reference expressions, reference order =========
+	(void)refill;
 	u32 pk_next, pk_end;
 #if XO_DETERMINISTIC
 	static_quota(num_packets, gridDim.x*blockDim.x, gid, &pk_next, &pk_end);
@@ -329,6 +504,7 @@ McKernel(
 		rng_state_x[gid] = rng.state();
 	}
 #undef XO_LAUNCH_PACKET
+#endif  // XO_DETERMINISTIC
 	if (started) atomicAdd(num_kernels, 1u);
 	{
 		const u32 mask = __activemask();

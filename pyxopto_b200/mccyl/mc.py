@@ -25,6 +25,7 @@ from . import mclayer, mcsource, mcdetector        # noqa: F401
 class Mc(McBase):
     kernel_header = 'mccyl_kernel.cuh'
     geometry = 'mccyl'
+    default_refill_lanes = 4         # waiting lanes per warp that trigger a service round
 
     def __init__(self, layers, source, detectors=None, trace=None, fluence=None,
                  surface=None, types=mctypes.McDataTypesSingle, options=None,
@@ -131,4 +132,5 @@ class Mc(McBase):
             dets,
             bufs['lut'], bufs['ints'], bufs['floats'], bufs['accu'],
             np.uint32(lut_len), np.uint32(priv_len), window, np.uint32(max(chunk, 1)),
+            np.uint32(max(refill, 1)),
         ]
