@@ -44,6 +44,15 @@ struct CylLayer {                   // mccyl/mclayer/layer.py:119-130
 	XoPf pf;
 };
 
+// Per-layer records of the throughput loop, derived once per CTA when the medium
+// is staged in shared memory; the record of the *current* layer is cached in
+// registers (cf. MlFastLayer in mcml_kernel.cuh).
+struct __align__(16) CylHot { float ri2, ro2, step_k, step_b; };
+	// squared radii; step = lg2(raw draw)*step_k + step_b = -ln(u)/mut
+struct __align__(16) CylAbs { float absorb, mua, n, pad; };
+struct __align__(16) CylPfFast { XoPf::Fast v; };
+struct CylFastLayer { CylHot hot; CylAbs abs; CylPfFast pf; };
+
 typedef CylDetectors<XoDetOuter, XoDetSpecular> XoDetectors;
 #if XO_TRACE
 typedef TraceCfg XoTrace;
@@ -139,6 +148,20 @@ McKernel(
 		for (u32 i = threadIdx.x; i < layer_words; i += blockDim.x) dst[i] = src[i];
 	}
 	u32 off_words = (layer_words + 3u) & ~3u;
+#if !XO_DETERMINISTIC
+	CylFastLayer *sh_fast = reinterpret_cast<CylFastLayer *>(reinterpret_cast<u32 *>(xo_smem) + off_words);
+	for (u32 i = threadIdx.x; i < num_layers; i += blockDim.x) {
+		const CylLayer &Lg = layers[i];
+		CylFastLayer F;
+		F.hot.ri2 = Lg.r_inner*Lg.r_inner; F.hot.ro2 = Lg.r_outer*Lg.r_outer;
+		F.hot.step_k = -0.6931471805599453f*Lg.inv_mut;
+		F.hot.step_b = -32.0f*F.hot.step_k;
+		F.abs.absorb = Lg.mua_inv_mut; F.abs.mua = Lg.mua; F.abs.n = Lg.n; F.abs.pad = 0.0f;
+		Lg.pf.prepare(F.pf.v);
+		sh_fast[i] = F;
+	}
+	off_words += num_layers*(u32)(sizeof(CylFastLayer)/4);
+#endif
 	float *sh_lut = reinterpret_cast<float *>(xo_smem) + off_words;
 	const float *lut = fp_lut;
 	if (lut_len) {      // staged for the pf and the *Lut plugins
@@ -188,6 +211,13 @@ McKernel(
 		u32 pk_next = 0, pk_end = 0;
 		bool budget_dry = false;
 		u32 thr_eff = refill < 1u ? 1u : (refill > 32u ? 32u : refill);
+		CylHot c_hot = { 0.0f, 0.0f, 0.0f, 0.0f };
+		CylAbs c_abs = { 0.0f, 0.0f, 1.0f, 0.0f };
+		XoPf::Fast c_pf;
+#define XO_CYL_LOAD_LAYER(idx) do { \
+		const CylFastLayer &F_ = sh_fast[idx]; \
+		c_hot = F_.hot; c_abs = F_.abs; c_pf = F_.pf.v; \
+	} while (0)
 
 #define XO_CYL_END_TRIP() do { \
 		{ \
@@ -220,6 +250,8 @@ McKernel(
 						if (layer <= 0 && XoDetOuter::active)
 							detectors.outer.deposit(acc, pos, dir, weight, opl);
 						done = true;
+					} else {
+						XO_CYL_LOAD_LAYER(layer);
 					}
 					{   // direction sanity check (mccyl.template.c:928-934)
 						float len = M::sqrt(dir.x*dir.x + dir.y*dir.y + dir.z*dir.z);
@@ -248,6 +280,7 @@ McKernel(
 							if (trace_event(tcfg, float_buffer, packet, trace_count, flags,
 									pos, dir, weight, opl)) ++trace_count;
 						}
+						if (layer > 0 && layer < (i32)num_layers) XO_CYL_LOAD_LAYER(layer);
 						state = ST_RUN;
 						started = true;
 					} else {
@@ -262,72 +295,70 @@ McKernel(
 			if (state != ST_RUN) continue;
 
 			// ---- one step of the packet ------------------------------------------------
-			const CylLayer &L = sh_layers[layer];
 			++iterations;
-			float step = -M::log(rng.next())*L.inv_mut;
-			step = fminf(step, XO_FLT_MAX);
+			float step = fminf(fmaf(FastMath::lg2(rng.next_raw()), c_hot.step_k, c_hot.step_b), XO_FLT_MAX);
 			bool hit = false, inwards = false;
 			if (dir.x != 0.0f || dir.y != 0.0f) {
 				// distance to the inner / outer cylinder of the layer
-				// (mccyl.template.c:147-209): a d^2 + b d + c - r^2 = 0
-				float a = dir.x*dir.x + dir.y*dir.y;
-				float b = 2.0f*(pos.x*dir.x + pos.y*dir.y);
-				float c = pos.x*pos.x + pos.y*pos.y;
+				// (mccyl.template.c:147-209) from the half-b form of the quadratic:
+				// a d^2 + 2 hb d + (c - r^2) = 0,  d = (-hb +- sqrt(hb^2 - a (c - r^2)))/a
+				const float a = fmaf(dir.x, dir.x, dir.y*dir.y);
+				const float hb = fmaf(pos.x, dir.x, pos.y*dir.y);
+				const float c = fmaf(pos.x, pos.x, pos.y*pos.y);
+				const float inv_a = FastMath::rcp_approx(a);
 				float d_inner = XO_INF, d_outer = XO_INF;
-				float inv_2a = M::div(1.0f, 2.0f*a);
-				float D = b*b - 4.0f*a*(c - L.r_inner*L.r_inner);
-				if (L.r_inner > 0.0f && D > 0.0f) {
-					D = M::sqrt(D);
-					float d1 = (-b - D)*inv_2a;
-					float d2 = (-b + D)*inv_2a;
+				float D = fmaf(hb, hb, -a*(c - c_hot.ri2));
+				if (c_hot.ri2 > 0.0f && D > 0.0f) {
+					D = FastMath::sqrt(D);
+					const float d1 = (-hb - D)*inv_a;
+					const float d2 = (D - hb)*inv_a;
 					d_inner = (d2 > 2.0f*XO_FP_EPS) ? fmaxf(d1, 0.0f) : XO_INF;
 				}
-				D = b*b - 4.0f*a*(c - L.r_outer*L.r_outer);
+				D = fmaf(hb, hb, -a*(c - c_hot.ro2));
 				if (D >= 0.0f) {
-					D = M::sqrt(D);
-					float d2 = (-b + D)*inv_2a;
-					d_outer = fmaxf(d2, 0.0f);
+					D = FastMath::sqrt(D);
+					d_outer = fmaxf((D - hb)*inv_a, 0.0f);
 				}
-				float d = fminf(d_outer, d_inner);
+				const float d = fminf(d_outer, d_inner);
 				hit = step > d;
 				inwards = d_inner <= d_outer;
 				step = fminf(d, step);
 			}
-			pos.x = pos.x + dir.x*step;
-			pos.y = pos.y + dir.y*step;
-			pos.z = pos.z + dir.z*step;
-			if (XO_NEEDS_OPL) opl += L.n*step;
-			if (hit) {
+			pos.x = fmaf(dir.x, step, pos.x);
+			pos.y = fmaf(dir.y, step, pos.y);
+			pos.z = fmaf(dir.z, step, pos.z);
+			if (XO_NEEDS_OPL) opl = fmaf(c_abs.n, step, opl);
+			if (__builtin_expect(hit, 0)) {
 				state = inwards ? ST_BND_IN : ST_BND_OUT;
 				continue;
 			}
 			bool done = false;
 #if XO_METHOD == 1
-			if (rng.next() < L.mua_inv_mut) {
+			if (rng.next() < c_abs.absorb) {
 				float deposit = weight;
 				done = true;
 				weight -= deposit;
 				flags |= EV_ABSORPTION;
-				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_abs.mua, opl);
 			} else {
-				float fi, ct = L.pf.sample(rng, lut, &fi);
+				float fi, ct = c_pf.sample(rng, lut, &fi);
 				scatter_direction(dir, ct, fi);
 				flags |= EV_SCATTERING;
 			}
 #else
 			{
-				float deposit = weight*L.mua_inv_mut;
+				float deposit = weight*c_abs.absorb;
 				weight -= deposit;
 				flags |= EV_ABSORPTION;
-				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_abs.mua, opl);
 			}
-			float fi, ct = L.pf.sample(rng, lut, &fi);
+			float fi, ct = c_pf.sample(rng, lut, &fi);
 			scatter_direction(dir, ct, fi);
 			flags |= EV_SCATTERING;
 			if (weight < XO_WEIGHT_MIN) {
 #if XO_USE_LOTTERY
-				if (rng.next() > XO_LOTTERY_CHANCE) done = true;
-				else weight = M::div(weight, XO_LOTTERY_CHANCE);
+				if (rng.next_raw() > XO_LOTTERY_CHANCE*4294967296.0f) done = true;
+				else weight *= (1.0f/XO_LOTTERY_CHANCE);
 #else
 				done = true;
 #endif
@@ -336,6 +367,7 @@ McKernel(
 			XO_CYL_END_TRIP();
 		}
 #undef XO_CYL_END_TRIP
+#undef XO_CYL_LOAD_LAYER
 		rng_state_x[gid] = rng.state();
 	}
 #else

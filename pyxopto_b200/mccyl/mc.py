@@ -63,7 +63,9 @@ class Mc(McBase):
         self._packed['layers'] = self._layers.cl_pack(self, self._packed.get('layers'))
 
     def _medium_bytes(self) -> int:
-        return len(cltypes.raw_bytes(self._packed['layers']))
+        # packed layers + the per-layer derived constants the throughput kernel
+        # appends (xo::CylFastLayer, <= 96 B per layer)
+        return len(cltypes.raw_bytes(self._packed['layers'])) + 96*len(self._layers) + 32
 
     def _upload_medium(self):
         self.cl_r_buffer('layers', self._packed['layers'])
