@@ -453,6 +453,8 @@ static float pf_sample_angles(sim_t *s, float *azimuth) {
 /* ---- linear lookup tables: mcbase.template.h:2494-2548 ---------------------- */
 typedef struct { float first, inv_span; uint32_t n, offset; } fp_lut_t;
 typedef struct { fp_lut_t lut; p3f direction; uint32_t offset; } det_totallut;   /* total.py:262-266 */
+typedef struct { fp_lut_t lut; p3f direction; float pl_min, inv_dpl; uint32_t n_pl, offset;
+	int32_t pl_log_scale; } det_totallutpl;                                      /* totalpl.py:340-348 */
 /* fp_linear_lut_sample: rounded first index, fractional weight, untouched when
  * the position is outside the table */
 static inline void fp_lut_sample(const float *buffer, const fp_lut_t *lut, float where, float *value) {
@@ -500,6 +502,19 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		fp_lut_sample(j->fp_lut, &d->lut, fabsf(dot3(dir, &dd)), &sensitivity);
 		uint32_t w = (uint32_t)(weight*sensitivity*ACCU_K + FP_0p5);
 		if (w > 0) accu_deposit(s, d->offset, w);
+		break;
+	}
+	case XO_DET_TOTALLUTPL: {                          /* mcdetector/totalpl.py:380-415 */
+		const det_totallutpl *d = (const det_totallutpl *)base;
+		float pl = s->opl;
+		if (d->pl_log_scale) pl = m_log(s, fmaxf(pl, FP_PLMIN));
+		int32_t pl_index = (int32_t)((pl - d->pl_min)*d->inv_dpl);
+		pl_index = iclip(pl_index, 0, (int32_t)d->n_pl - 1);
+		float sensitivity = FP_0;
+		p3f dd = d->direction;
+		fp_lut_sample(j->fp_lut, &d->lut, fabsf(dot3(dir, &dd)), &sensitivity);
+		uint32_t w = (uint32_t)(weight*sensitivity*ACCU_K + FP_0p5);
+		if (w > 0) accu_deposit(s, d->offset + (uint32_t)pl_index, w);
 		break;
 	}
 	case XO_DET_RADIAL: {                              /* mcdetector/radial.py:117-150 */

@@ -32,7 +32,7 @@ SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
             'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10,
-            'LinearArray': 12, 'FiberArray': 13, 'LinearArrayPl': 14, 'FiberArrayPl': 15, 'TotalLut': 16}
+            'LinearArray': 12, 'FiberArray': 13, 'LinearArrayPl': 14, 'FiberArrayPl': 15, 'TotalLut': 16, 'TotalLutPl': 17}
 DET_KIND_TOTAL_CYL = 11
 SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
              'SixAroundOne': 2, 'LinearArray': 3, 'FiberArray': 4}
@@ -211,7 +211,7 @@ def describe(mc_obj, geometry: str) -> dict:
         d['fluence'] = _raw(P['fluence'])
         d['fluence_rate'] = int(flu.mode == 'fluence')
     tr = mc_obj.trace
-    track_opl = any(k in (5, 6, 9, 10, 14, 15) for k in det_kind) or \
+    track_opl = any(k in (5, 6, 9, 10, 14, 15, 17) for k in det_kind) or \
         d['fluence_kind'] in (3, 4, 6)
     if tr is not None:
         d['trace'] = _raw(P['trace'])

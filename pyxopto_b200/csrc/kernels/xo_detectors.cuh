@@ -157,6 +157,20 @@ __device__ __forceinline__ u32 pl_bin(float opl, float pl_min, float inv_dpl, u3
 	return (u32)clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
 }
 
+struct DetTotalLutPl {              // mcdetector/totalpl.py:315-420
+	FpLut lut; P3 direction; float pl_min, inv_dpl; u32 n_pl, offset; i32 pl_log_scale;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+		(void)pos;
+		u32 pi = pl_bin(opl, pl_min, inv_dpl, n_pl, pl_log_scale);
+		float sensitivity = 0.0f;
+		lut_sample(acc.lut, lut, fabsf(dot3(dir, direction)), &sensitivity);
+		u32 iw = weight_u32(w*sensitivity, true);
+		if (iw > 0) acc.add(offset + pi, iw);
+	}
+};
+
 template <int N>
 struct DetLinearArrayPl {
 	M3 T; P2 first_position, delta_position; float core_r_squared, cos_min, pl_min, inv_dpl;

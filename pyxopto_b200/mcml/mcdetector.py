@@ -176,6 +176,52 @@ class TotalLut(Detector):
                 'direction': self._direction.tolist()}
 
 
+class TotalLutPl(TotalLut):
+    """TotalLut resolved by optical path length (totalpl.py:315-611)."""
+    cu_type = 'xo::DetTotalLutPl'
+
+    def cl_type(self, mc):
+        T = mc.types
+        class ClTotalLutPl(cltypes.Structure):
+            _fields_ = [('lut', CollectionLut.cl_type(mc)), ('direction', T.mc_point3f_t),
+                        ('pl_min', T.mc_fp_t), ('inv_dpl', T.mc_fp_t),
+                        ('n_pl', T.mc_size_t), ('offset', T.mc_size_t),
+                        ('pl_log_scale', T.mc_int_t)]
+        return ClTotalLutPl
+
+    def cl_options(self, mc):
+        return [('MC_TRACK_OPTICAL_PATHLENGTH', True)]
+
+    def __init__(self, lut, plaxis=None, direction=(0.0, 0.0, 1.0)):
+        if isinstance(lut, TotalLutPl):
+            o = lut
+            super().__init__(o.lut, o.direction)
+            plaxis = type(o.plaxis)(o.plaxis)
+            raw, nphotons = np.copy(o.raw), o.nphotons
+        else:
+            super().__init__(lut, direction)
+            if plaxis is None:
+                plaxis = Axis(0.0, 1.0, 1)
+            raw, nphotons = np.zeros((plaxis.n,)), 0
+        self._raw_data, self._nphotons = raw, int(nphotons)
+        self._pl_axis = plaxis
+
+    plaxis = property(lambda self: self._pl_axis)
+    pl = property(lambda self: self._pl_axis.centers)
+    pledges = property(lambda self: self._pl_axis.edges)
+    npl = property(lambda self: self._pl_axis.n)
+
+    def cl_pack(self, mc, target=None):
+        target = super().cl_pack(mc, target)
+        target.pl_min, target.inv_dpl = self._pl_axis.scaled_start, _inv_step(self._pl_axis)
+        target.pl_log_scale, target.n_pl = self._pl_axis.logscale, self._pl_axis.n
+        return target
+
+    def todict(self):
+        return {'type': 'TotalLutPl', 'lut': self._lut.todict(),
+                'plaxis': self._pl_axis.todict(), 'direction': self._direction.tolist()}
+
+
 class Radial(Detector):
     cu_type = 'xo::DetRadial'
 

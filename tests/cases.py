@@ -782,9 +782,10 @@ def mcml_hg_line_totallut(mc, **kw):
         CollectionLut = mc.mcdetector.CollectionLut
     ct = np.linspace(0.0, 1.0, 21)
     top = mc.mcdetector.TotalLut(CollectionLut(ct**2, ct, n=100))
-    bottom = mc.mcdetector.TotalLut(CollectionLut(np.sqrt(np.linspace(0.2, 1.0, 9)),
-                                                  np.linspace(0.2, 1.0, 9), n=33),
-                                    direction=(0.1, 0.0, 1.0))
+    bottom = mc.mcdetector.TotalLutPl(CollectionLut(np.sqrt(np.linspace(0.2, 1.0, 9)),
+                                                    np.linspace(0.2, 1.0, 9), n=33),
+                                      plaxis=mc.mcdetector.Axis(0.0, 40e-3, 800),
+                                      direction=(0.1, 0.0, 1.0))
     det = mc.mcdetector.Detectors(top=top, bottom=bottom, specular=mc.mcdetector.Total())
     params, lut = _hg_lut()
     return mc.Mc(_layers(mc, mc.mcpf.Lut(params, lut)), mc.mcsource.Line(), det,

@@ -43,7 +43,10 @@ def test_portable_math_is_statistically_the_reference(name):
     n = cases.GOLDEN_RUN[name][0]
     assert abs(a - b) <= max(1e-3*b, 2*(n/t)**0.5*0x7FFFFF)
     if g['accu'].size >= 20:      # bin-wise identity is meaningless for 2 totals
-        same = np.count_nonzero(res['accu'] == g['accu'])/g['accu'].size
+        # (bins of detectors that scale the weight by a continuous sensitivity, e.g.
+        # TotalLut, differ by a few counts of ~1e7 when a cosine moves by one ulp)
+        a64, b64 = res['accu'].astype(np.int64), g['accu'].astype(np.int64)
+        same = np.count_nonzero(np.abs(a64 - b64) <= np.maximum(4, b64//1000000))/b64.size
         assert same > 0.9
 
 
