@@ -517,6 +517,31 @@ static void detector_deposit(sim_t *s, int loc, const p3f *pos, const p3f *dir, 
 		if (w > 0) accu_deposit(s, d->offset + (uint32_t)pl_index, w);
 		break;
 	}
+	case XO_DET_FIBERLUTARRAY: {                       /* mcdetector/probe/fiberlutarray.py:100-170 */
+		/* packed: m3f T[n]; p2f core_position[n]; float core_r_squared[n]; fp_lut_t lut[n]; u32 offset */
+		uint32_t n = (uint32_t)param, fiber_index = n;
+		const m3f *Ts = (const m3f *)base;
+		const p2f *cp = (const p2f *)(Ts + n);
+		const float *r2s = (const float *)(cp + n);
+		const fp_lut_t *luts = (const fp_lut_t *)(r2s + n);
+		uint32_t offset = *(const uint32_t *)(luts + n);
+		p3f mc_pos, dp; float dx, dy, r2;
+		for (uint32_t index = 0; index < n; ++index) {
+			mc_pos.x = pos->x - cp[index].x; mc_pos.y = pos->y - cp[index].y; mc_pos.z = FP_0;
+			m3f T = Ts[index];
+			transform3(&T, &mc_pos, &dp);
+			dx = dp.x; dy = dp.y; r2 = dx*dx + dy*dy;
+			if (r2 <= r2s[index]) { fiber_index = index; break; }
+		}
+		if (fiber_index >= n) return;
+		const m3f *Tf = &Ts[fiber_index];
+		float pz = Tf->a31*dir->x + Tf->a32*dir->y + Tf->a33*dir->z;
+		float sensitivity = FP_0;
+		fp_lut_sample(j->fp_lut, &luts[fiber_index], fabsf(pz), &sensitivity);
+		uint32_t w = (uint32_t)(weight*sensitivity*ACCU_K + FP_0p5);
+		if (w > 0) accu_deposit(s, offset + fiber_index, w);
+		break;
+	}
 	case XO_DET_RADIAL: {                              /* mcdetector/radial.py:117-150 */
 		const det_radial *d = (const det_radial *)base;
 		float dx = pos->x - d->position.x, dy = pos->y - d->position.y;

@@ -29,7 +29,8 @@ enum {
 	XO_DET_SYMMETRICX = 7, XO_DET_FIZ = 8, XO_DET_CARTESIANPL = 9,
 	XO_DET_SIXAROUNDONEPL = 10, XO_DET_TOTAL_CYL = 11, XO_DET_LINEARARRAY = 12,
 	XO_DET_FIBERARRAY = 13, XO_DET_LINEARARRAYPL = 14, XO_DET_FIBERARRAYPL = 15,
-	XO_DET_TOTALLUT = 16, XO_DET_TOTALLUTPL = 17
+	XO_DET_TOTALLUT = 16, XO_DET_TOTALLUTPL = 17,
+	XO_DET_FIBERLUTARRAY = 18
 };
 enum {
 	XO_FLU_NONE = 0, XO_FLU_XYZ = 1, XO_FLU_RZ = 2, XO_FLU_XYZT = 3,

@@ -32,7 +32,8 @@ SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
             'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10,
-            'LinearArray': 12, 'FiberArray': 13, 'LinearArrayPl': 14, 'FiberArrayPl': 15, 'TotalLut': 16, 'TotalLutPl': 17}
+            'LinearArray': 12, 'FiberArray': 13, 'LinearArrayPl': 14, 'FiberArrayPl': 15, 'TotalLut': 16, 'TotalLutPl': 17,
+            'FiberLutArray': 18}
 DET_KIND_TOTAL_CYL = 11
 SURF_KIND = {'NoneType': 0, 'SurfaceLayoutDefault': 0, 'LambertianReflector': 1,
              'SixAroundOne': 2, 'LinearArray': 3, 'FiberArray': 4}
@@ -189,7 +190,7 @@ def describe(mc_obj, geometry: str) -> dict:
             if geometry == 'mccyl' and det_kind[i] == DET_KIND['Total']:
                 det_kind[i] = DET_KIND_TOTAL_CYL
             det_off[i] = getattr(dstruct, loc).offset
-            det_par[i] = int(getattr(det, 'n', 0) or 0) if det_kind[i] in (12, 13, 14, 15) else 0
+            det_par[i] = int(getattr(det, 'n', 0) or 0) if det_kind[i] in (12, 13, 14, 15, 18) else 0
         d['detectors'] = _raw(P['detectors'])
     d['det_kind'], d['det_offset'], d['det_param'] = det_kind, det_off, det_par
     if hasattr(mc_obj, 'resolved_options'):

@@ -157,6 +157,30 @@ __device__ __forceinline__ u32 pl_bin(float opl, float pl_min, float inv_dpl, u3
 	return (u32)clipi(f2i((pl - pl_min)*inv_dpl), 0, (i32)(n_pl - 1));
 }
 
+// mcdetector/probe/fiberlutarray.py: N fibers, each with its own tabulated
+// collection sensitivity (sampled at |cos| in the fiber's frame)
+template <int N>
+struct DetFiberLutArray {
+	M3 T[N]; P2 core_position[N]; float core_r_squared[N]; FpLut lut[N]; u32 offset;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float) const {
+		u32 fiber = N;
+#pragma unroll 1
+		for (u32 i = 0; i < (u32)N; ++i) {
+			P3 p = { pos.x - core_position[i].x, pos.y - core_position[i].y, 0.0f };
+			P3 q = transform3(T[i], p);
+			if (q.x*q.x + q.y*q.y <= core_r_squared[i]) { fiber = i; break; }
+		}
+		if (fiber >= (u32)N) return;
+		float pz = T[fiber].a31*dir.x + T[fiber].a32*dir.y + T[fiber].a33*dir.z;
+		float sensitivity = 0.0f;
+		lut_sample(acc.lut, lut[fiber], fabsf(pz), &sensitivity);
+		u32 iw = weight_u32(w*sensitivity, true);
+		if (iw > 0) acc.add(offset + fiber, iw);
+	}
+};
+
 struct DetTotalLutPl {              // mcdetector/totalpl.py:315-420
 	FpLut lut; P3 direction; float pl_min, inv_dpl; u32 n_pl, offset; i32 pl_log_scale;
 	static constexpr bool active = true;

@@ -702,6 +702,43 @@ class FiberArrayPl(FiberArray):
                 'pl_axis': self._pl_axis.todict()}
 
 
+class FiberLutArray(FiberArray):
+    """Array of fibers (``MultimodeFiberLut``) with tabulated collection
+    sensitivity (probe/fiberlutarray.py)."""
+    def cu_type(self, mc):
+        return 'xo::DetFiberLutArray<{}>'.format(len(self._fibers))
+
+    def cl_type(self, mc):
+        T = mc.types
+        n = self.n
+        class ClFiberLutArray(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t*n),
+                        ('core_position', T.mc_point2f_t*n),
+                        ('core_r_squared', T.mc_fp_t*n),
+                        ('lut', CollectionLut.cl_type(mc)*n),
+                        ('offset', T.mc_size_t)]
+        return ClFiberLutArray
+
+    def cl_options(self, mc):
+        return [('MC_USE_FP_LUT', True)]
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        for index, cfg in enumerate(self._fibers):
+            adir = cfg.direction[0], cfg.direction[1], abs(cfg.direction[2])
+            target.transformation[index].fromarray(
+                geometry.transform_base(adir, (0.0, 0.0, 1.0)))
+            target.core_position[index].fromarray(cfg.position)
+            target.core_r_squared[index] = 0.25*cfg.fiber.dcore**2
+            cfg.fiber.collection.cl_pack(mc, target.lut[index])
+        target.offset = mc.cl_allocate_rw_accumulator_buffer(self, self.shape).offset
+        return target
+
+    def todict(self):
+        return {'type': 'FiberLutArray', 'fibers': [f.todict() for f in self._fibers]}
+
+
 class RadialPl(Detector):
     """Radial x optical-path-length histogram; raw indexed [pl, r] (radialpl.py)."""
     cu_type = 'xo::DetRadialPl'

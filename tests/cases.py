@@ -824,3 +824,33 @@ MCML_CASES['mcml_lut_ufiberlut_totallut'] = mcml_lut_ufiberlut_totallut
 ALL_CASES['mcml_lut_ufiberlut_totallut'] = mcml_lut_ufiberlut_totallut
 GEOMETRY['mcml_lut_ufiberlut_totallut'] = 'mcml'
 GOLDEN_RUN['mcml_lut_ufiberlut_totallut'] = (3000, 16)
+
+
+def mcml_hg_line_fiberlutarray(mc, **kw):
+    """FiberLutArray detector: fibers with tabulated collection sensitivity
+    (mcdetector/probe/fiberlutarray.py)."""
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase.mcutil.lut import CollectionLut
+        from xopto.mcml.mcutil.fiber import MultimodeFiberLut
+    else:
+        CollectionLut = mc.mcdetector.CollectionLut
+        MultimodeFiberLut = mc.mcsource.MultimodeFiberLut
+    cs = np.linspace(0.5, 1.0, 26)
+    fa = MultimodeFiberLut(400e-6, 440e-6, 1.462, None,
+                           collection=CollectionLut((cs - 0.5)*2.0, cs, n=50))
+    fb = MultimodeFiberLut(600e-6, 660e-6, 1.462, None,
+                           collection=CollectionLut(np.sqrt(cs), cs, n=80))
+    tilt = (np.sin(np.deg2rad(6.0)), 0.0, np.cos(np.deg2rad(6.0)))
+    top = mc.mcdetector.FiberLutArray([
+        _fiber_layout(mc, fa, (0.3e-3, 0.0, 0.0)),
+        _fiber_layout(mc, fb, (-0.5e-3, 0.2e-3, 0.0), tilt),
+        _fiber_layout(mc, fa, (0.0, -0.6e-3, 0.0))])
+    det = mc.mcdetector.Detectors(top=top, bottom=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det,
+                 rnginit=484848, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hg_line_fiberlutarray'] = mcml_hg_line_fiberlutarray
+ALL_CASES['mcml_hg_line_fiberlutarray'] = mcml_hg_line_fiberlutarray
+GEOMETRY['mcml_hg_line_fiberlutarray'] = 'mcml'
+GOLDEN_RUN['mcml_hg_line_fiberlutarray'] = (4000, 16)
