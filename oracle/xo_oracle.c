@@ -77,6 +77,8 @@ typedef struct { m3f T; p3f position, direction; p2f sigma; float clip, reflecta
 typedef struct { m3f T; p3f position, direction; float radius, cos_min, n; } src_ufiber;
 typedef struct { m3f T; p3f position, direction; p2f radius; float reflectance; } src_ubeam_ml; /* mcsource/uniformbeam.py:36-47 */
 typedef struct { p3f position; uint32_t layer_index; } src_isopoint;
+/* mcsource/rectangular.py:56-63 (cos_min) / :343-350 (na) */
+typedef struct { p3f position; p2f size; float n, cos_critical, aperture; uint32_t layer_index; } src_rect;
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip; } src_gauss_vox;  /* mcvox/mcsource/gaussianbeam.py:71-77 */
 typedef struct { p3f position; int32_t vx, vy, vz; } src_isovoxel;                    /* mcvox/mcsource/voxel.py:44-47 */
 typedef struct { p3f position; } src_isopoint_vox;                                  /* mcvox/mcsource/point.py:44-46 */
@@ -252,6 +254,27 @@ static inline void reflect3(const p3f *p, const p3f *n, p3f *r) {
 	float p_n_2 = FP_2*dot3(p, n);
 	r->x = p->x - n->x*p_n_2; r->y = p->y - n->y*p_n_2; r->z = p->z - n->z*p_n_2;
 }
+/* mcbase.template.c:1303-1348 */
+static inline float reflectance_cos2(float n1, float n2, float cos2) {
+	float Rp, Rs, R = FP_1, n1_d_n2, sin1, sin2, cos1, n_cos1, n_cos2;
+	cos2 = fabsf(cos2);
+	if (n1 == n2) return FP_0;
+	sin2 = m_sqrt(FP_1 - cos2*cos2);
+	if (cos2 >= FP_COS_0) sin2 = FP_0;
+	sin1 = m_div(n2, n1)*sin2;
+	if (sin1 < FP_1) {
+		cos1 = m_sqrt(FP_1 - sin1*sin1);
+		n1_d_n2 = m_div(n1, n2);
+		n_cos1 = n1_d_n2*cos1;
+		n_cos2 = n1_d_n2*cos2;
+		Rs = m_div(n_cos1 - cos2, n_cos1 + cos2); Rs *= Rs;
+		Rp = m_div(n_cos2 - cos1, n_cos2 + cos1); Rp *= Rp;
+		R = FP_0p5*(Rp + Rs);
+		if (cos1 <= FP_COS_90 || sin2 == FP_1) return FP_1;
+	}
+	return R;
+}
+
 static inline void refract3(const p3f *p, const p3f *n, float n1, float n2, p3f *r) {
 	float cos1 = dot3(p, n);
 	float n1_d_n2 = m_div(n1, n2);
@@ -1124,6 +1147,29 @@ static void launch_mcml(sim_t *s) {
 		if (j->det_kind[LOC_SPECULAR])
 			detector_deposit(s, LOC_SPECULAR, &s->pos, &direction, specular_r);
 		s->layer_index = 1;
+		break;
+	}
+	case XO_SRC_UNIFORMRECTANGULAR:                    /* mcsource/rectangular.py:91-146 */
+	case XO_SRC_LAMBERTIANRECTANGULAR: {               /* mcsource/rectangular.py:376-430 */
+		const src_rect *src = (const src_rect *)j->source;
+		float sin_fi, cos_fi, sin_theta, cos_theta;
+		s->pos.x = src->position.x + (sim_random(s) - FP_0p5)*src->size.x;
+		s->pos.y = src->position.y + (sim_random(s) - FP_0p5)*src->size.y;
+		s->pos.z = src->position.z;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		if (j->src_kind == XO_SRC_LAMBERTIANRECTANGULAR) {
+			sin_theta = m_sqrt(sim_random(s))*src->aperture;
+		} else {
+			cos_theta = FP_1 - sim_random(s)*(FP_1 - src->aperture);
+			sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+		}
+		sin_theta = m_div(sin_theta, medium_n(j, (int32_t)src->layer_index));
+		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+		s->dir.x = cos_fi*sin_theta; s->dir.y = sin_fi*sin_theta; s->dir.z = cos_theta;
+		float r = reflectance_cos2(src->n, medium_n(j, (int32_t)src->layer_index), cos_theta);
+		s->weight = FP_1 - r;
+		/* (the specular branch of the reference does not compile: no such case) */
+		s->layer_index = (int32_t)src->layer_index;
 		break;
 	}
 	case XO_SRC_ISOTROPICPOINT: {                      /* mcsource/point.py:76-135 */

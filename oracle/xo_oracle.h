@@ -21,7 +21,8 @@ enum { XO_PF_HG = 1, XO_PF_MHG = 2, XO_PF_GK = 3, XO_PF_LUT = 4, XO_PF_HG2 = 5,
 enum {
 	XO_SRC_LINE = 1, XO_SRC_GAUSSIANBEAM = 2, XO_SRC_UNIFORMFIBER = 3,
 	XO_SRC_ISOTROPICPOINT = 4, XO_SRC_UNIFORMBEAM = 5, XO_SRC_LAMBERTIANFIBER = 6,
-	XO_SRC_ISOTROPICVOXEL = 7, XO_SRC_UNIFORMFIBERLUT = 8
+	XO_SRC_ISOTROPICVOXEL = 7, XO_SRC_UNIFORMFIBERLUT = 8,
+	XO_SRC_UNIFORMRECTANGULAR = 9, XO_SRC_LAMBERTIANRECTANGULAR = 10
 };
 enum {
 	XO_DET_NONE = 0, XO_DET_TOTAL = 1, XO_DET_RADIAL = 2, XO_DET_CARTESIAN = 3,

@@ -202,6 +202,42 @@ struct SrcUniformFiberLut {         // mcsource/fiber.py:719-727, launch :766-83
 	}
 };
 
+// mcsource/rectangular.py:32-315 / :317-528: rectangular emitter at the surface or
+// inside a layer; emission cosine uniform within the NA (Uniform) or sin = sqrt(u)
+// NA (Lambertian), adjusted to the refractive index of the layer.  (The
+// reference's specular branch names a struct field that does not exist, so these
+// sources only build without a specular detector; the host refuses otherwise.)
+template <bool LAMBERTIAN>
+struct SrcRectangular {
+	P3 position; P2 size; float n, cos_critical, aperture; u32 layer_index;
+		// aperture: cos_min (uniform) or na (lambertian)
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf, st, ct;
+		L.pos.x = position.x + (rng.next() - 0.5f)*size.x;
+		L.pos.y = position.y + (rng.next() - 0.5f)*size.y;
+		L.pos.z = position.z;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		if (LAMBERTIAN) {
+			st = M::sqrt(rng.next())*aperture;
+		} else {
+			ct = 1.0f - rng.next()*(1.0f - aperture);
+			st = M::sqrt(1.0f - ct*ct);
+		}
+		const float n_layer = ctx.layer_n((int)layer_index);
+		st = M::div(st, n_layer);
+		ct = M::sqrt(1.0f - st*st);
+		L.dir.x = cf*st; L.dir.y = sf*st; L.dir.z = ct;
+		L.weight = 1.0f - reflectance_cos2(n, n_layer, ct);
+		L.spec_dir = L.dir;
+		L.spec_weight = 0.0f;
+		L.layer = (i32)layer_index;
+	}
+};
+typedef SrcRectangular<false> SrcUniformRectangular;
+typedef SrcRectangular<true> SrcLambertianRectangular;
+
 struct SrcIsotropicPoint {          // mcsource/point.py:46-49
 	P3 position; u32 layer_index;
 	__device__ __forceinline__ P3 origin() const { return position; }

@@ -160,6 +160,27 @@ __device__ inline float reflectance(float n1, float n2, float cos1, float cc) {
 	return R;
 }
 
+// unpolarised Fresnel reflectance from the cosine on the *far* side of the
+// interface (mcbase.template.c:1303-1348 reflectance_cos2)
+__device__ inline float reflectance_cos2(float n1, float n2, float cos2) {
+	float R = 1.0f;
+	cos2 = fabsf(cos2);
+	if (n1 == n2) return 0.0f;
+	float sin2 = M::sqrt(1.0f - cos2*cos2);
+	if (cos2 >= 1.0f) sin2 = 0.0f;
+	float sin1 = M::div(n2, n1)*sin2;
+	if (sin1 < 1.0f) {
+		float cos1 = M::sqrt(1.0f - sin1*sin1);
+		float n12 = M::div(n1, n2);
+		float nc1 = n12*cos1, nc2 = n12*cos2;
+		float Rs = M::div(nc1 - cos2, nc1 + cos2); Rs *= Rs;
+		float Rp = M::div(nc2 - cos1, nc2 + cos1); Rp *= Rp;
+		R = 0.5f*(Rp + Rs);
+		if (cos1 <= 0.0f || sin2 == 1.0f) return 1.0f;
+	}
+	return R;
+}
+
 __device__ __forceinline__ P3 reflect3(const P3 &p, const P3 &n) {
 	float k = 2.0f*dot3(p, n);
 	P3 r = { p.x - n.x*k, p.y - n.y*k, p.z - n.z*k };

@@ -352,6 +352,80 @@ class UniformFiberLut(UniformFiber):
         return target, None, None
 
 
+class UniformRectangular(Source):
+    """Rectangular emitter (width x height) with uniform emission within the NA, at
+    the top surface or inside a layer (mcsource/rectangular.py:32-315).  As in the
+    reference the kernel cannot be built together with a specular detector."""
+    cu_type = 'xo::SrcUniformRectangular'
+    cu_refill_lanes = 4
+    _update_keys = ('width', 'height', 'n', 'na', 'position')
+    _aperture_field = 'cos_min'
+
+    @classmethod
+    def cl_type(cls, mc):
+        T = mc.types
+        class ClRectangular(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('size', T.mc_point2f_t),
+                        ('n', T.mc_fp_t), ('cos_critical', T.mc_fp_t),
+                        (cls._aperture_field, T.mc_fp_t), ('layer_index', T.mc_size_t)]
+        return ClRectangular
+
+    def __init__(self, width: float, height: float, n: float, na: float,
+                 position=(0.0, 0.0, 0.0)):
+        super().__init__()
+        self._width, self._height = float(width), float(height)
+        self._n, self._na = float(n), float(na)
+        self._position = np.zeros((3,))
+        self.position = position
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    position = property(lambda self: self._position, _set_position)
+    width = property(lambda self: self._width, lambda self, v: setattr(self, '_width', float(v)))
+    height = property(lambda self: self._height, lambda self, v: setattr(self, '_height', float(v)))
+    n = property(lambda self: self._n, lambda self, v: setattr(self, '_n', float(v)))
+    na = property(lambda self: self._na, lambda self, v: setattr(self, '_na', float(v)))
+
+    def _aperture(self) -> float:
+        return (1 - (self._na)**2)**0.5
+
+    def cl_pack(self, mc, target=None):
+        if mc.detectors is not None and type(mc.detectors.specular).__name__ != 'DetectorDefault':
+            raise NotImplementedError(
+                'Rectangular sources cannot be combined with a specular detector (the '
+                'reference kernel does not build: rectangular.py:140 names a missing field).')
+        if target is None:
+            target = self.cl_type(mc)()
+        if self._position[2] <= 0.0:
+            position = (self._position[0], self._position[1], 0.0)
+            layer_index = 1
+        else:
+            position = self._position
+            layer_index = mc.layer_index(self._position[2])
+        target.position.fromarray(position)
+        target.size.fromarray([self._width, self._height])
+        target.n = self._n
+        target.cos_critical = boundary.cos_critical(self._n, mc.layers[layer_index].n)
+        setattr(target, self._aperture_field, self._aperture())
+        target.layer_index = layer_index
+        return target, None, None
+
+    def todict(self):
+        return {'width': self._width, 'height': self._height, 'n': self._n, 'na': self._na,
+                'position': self._position.tolist(), 'type': type(self).__name__}
+
+
+class LambertianRectangular(UniformRectangular):
+    """Rectangular emitter with lambertian emission within the NA
+    (mcsource/rectangular.py:317-528)."""
+    cu_type = 'xo::SrcLambertianRectangular'
+    _aperture_field = 'na'
+
+    def _aperture(self) -> float:
+        return self._na
+
+
 class IsotropicPoint(Source):
     """Isotropic point source above or inside the sample (mcsource/point.py)."""
     cu_type = 'xo::SrcIsotropicPoint'

@@ -854,3 +854,33 @@ MCML_CASES['mcml_hg_line_fiberlutarray'] = mcml_hg_line_fiberlutarray
 ALL_CASES['mcml_hg_line_fiberlutarray'] = mcml_hg_line_fiberlutarray
 GEOMETRY['mcml_hg_line_fiberlutarray'] = 'mcml'
 GOLDEN_RUN['mcml_hg_line_fiberlutarray'] = (4000, 16)
+
+
+def mcml_mhg_rect_uniform(mc, **kw):
+    """UniformRectangular source on the surface (mcsource/rectangular.py:32)."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Cartesian(Axis(-2e-3, 2e-3, 20)),
+                                  bottom=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.8, 0.9)),
+                 mc.mcsource.UniformRectangular(1e-3, 0.5e-3, 1.45, 0.4, position=(0.1e-3, 0, 0)),
+                 det, rnginit=575757, **kw), dict(rmax=20e-3)
+
+
+def mcml_hg_rect_lambertian_inside(mc, **kw):
+    """LambertianRectangular source buried in the second sample layer."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 50)),
+                                  bottom=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceRz(Axis(0, 2e-3, 20), Axis(0, 3e-3, 30))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)),
+                 mc.mcsource.LambertianRectangular(0.4e-3, 0.8e-3, 1.6, 0.5,
+                                                   position=(0, -0.1e-3, 1.5e-3)),
+                 det, fluence=flu, rnginit=676767, **kw), dict(rmax=20e-3)
+
+
+for _name, _fn in (('mcml_mhg_rect_uniform', mcml_mhg_rect_uniform),
+                   ('mcml_hg_rect_lambertian_inside', mcml_hg_rect_lambertian_inside)):
+    MCML_CASES[_name] = _fn
+    ALL_CASES[_name] = _fn
+    GEOMETRY[_name] = 'mcml'
+    GOLDEN_RUN[_name] = (3000, 16)
