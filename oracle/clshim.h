@@ -75,9 +75,12 @@ static inline float xo_ref_sincos(float x, float *c) { *c = cosf(x); return sinf
 #define native_rsqrt(x)  (1.0f/sqrtf(x))
 #define native_powr      powf
 #define native_divide(a, b) ((a)/(b))
-#define clamp(x, lo, hi) ((x) < (lo) ? (lo) : ((x) > (hi) ? (hi) : (x)))
-#define min(a, b)        ((a) < (b) ? (a) : (b))
-#define max(a, b)        ((a) > (b) ? (a) : (b))
+/* OpenCL's min / max / clamp are functions: every argument is evaluated once
+ * (mcvox/mcsource/voxel.py draws a random number inside mc_min(...)) */
+#define clamp(x, lo, hi) ({ __typeof__(x) x_ = (x); __typeof__(lo) lo_ = (lo); __typeof__(hi) hi_ = (hi); \
+	x_ < lo_ ? lo_ : (x_ > hi_ ? hi_ : x_); })
+#define min(a, b)        ({ __typeof__(a) a_ = (a); __typeof__(b) b_ = (b); a_ < b_ ? a_ : b_; })
+#define max(a, b)        ({ __typeof__(a) a_ = (a); __typeof__(b) b_ = (b); a_ > b_ ? a_ : b_; })
 
 /* OpenCL math built-ins are overloaded on float; the rendered text uses the
  * bare names with float arguments. */

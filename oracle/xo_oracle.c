@@ -80,6 +80,7 @@ typedef struct { p3f position; uint32_t layer_index; } src_isopoint;
 /* mcsource/rectangular.py:56-63 (cos_min) / :343-350 (na) */
 typedef struct { p3f position; p2f size; float n, cos_critical, aperture; uint32_t layer_index; } src_rect;
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip; } src_gauss_vox;  /* mcvox/mcsource/gaussianbeam.py:71-77 */
+typedef struct { p3f position; uint32_t n, offset; } src_isovoxels;                    /* mcvox/mcsource/voxel.py:205-209 */
 typedef struct { p3f position; int32_t vx, vy, vz; } src_isovoxel;                    /* mcvox/mcsource/voxel.py:44-47 */
 typedef struct { p3f position; } src_isopoint_vox;                                  /* mcvox/mcsource/point.py:44-46 */
 

@@ -59,6 +59,7 @@ struct VoxCtx {
 	const VoxCfg &cfg;
 	const VoxMaterial *materials;   // shared memory
 	const i32 *voxels;              // global, read-only
+	const float *lut = nullptr;     // float lookup-table pool (IsotropicVoxels)
 	static constexpr bool has_specular = XoDetSpecular::active;
 	__device__ __forceinline__ VoxCtx(const VoxCfg &c, const VoxMaterial *m, const i32 *v)
 		: cfg(c), materials(m), voxels(v) {}
@@ -198,6 +199,7 @@ McKernel(
 	rng.a = rng_state_a[gid];
 	const VoxCfg &cfg = voxel_cfg;
 	VoxCtx ctx(cfg, sh_mat, voxels);
+	ctx.lut = lut;
 	const P3 src_pos = source.origin();
 	const float rmax2 = rmax*rmax;
 

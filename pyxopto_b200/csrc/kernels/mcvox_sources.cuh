@@ -202,4 +202,31 @@ struct VoxSrcIsotropicVoxel {
 	}
 };
 
+// mcvox/mcsource/voxel.py:195-300: one of `n` source voxels is drawn uniformly, its
+// weight and (float) indices come from the float pool (4 floats per voxel)
+struct VoxSrcIsotropicVoxels {
+	P3 position; u32 n, offset;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		i32 pick = f2i(rng.next()*(float)n);
+		if (pick > (i32)(n - 1u)) pick = (i32)(n - 1u);
+		const float *entry = ctx.lut + offset + (u32)pick*4u;
+		const float w = entry[0], vx = entry[1], vy = entry[2], vz = entry[3];
+		const float lim = 1.0f - 1.1920928955078125e-07f;      // FP_1 - FP_EPS
+		L.pos.x = (vx + fminf(rng.next(), lim))*ctx.cfg.size.x + ctx.cfg.top_left.x;
+		L.pos.y = (vy + fminf(rng.next(), lim))*ctx.cfg.size.y + ctx.cfg.top_left.y;
+		L.pos.z = (vz + fminf(rng.next(), lim))*ctx.cfg.size.z + ctx.cfg.top_left.z;
+		float sf, cf;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 1.0f - 2.0f*rng.next();
+		float st = M::sqrt(1.0f - ct*ct);
+		L.dir.x = cf*st; L.dir.y = sf*st; L.dir.z = ct;
+		L.weight = w;
+		L.spec_dir = L.dir;
+		L.spec_weight = 0.0f;
+	}
+};
+
 }  // namespace xo

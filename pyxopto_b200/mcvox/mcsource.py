@@ -297,3 +297,80 @@ class IsotropicVoxel(Source):
 
     def todict(self):
         return {'voxel': self._voxel.tolist(), 'type': type(self).__name__}
+
+
+class IsotropicVoxels(Source):
+    """Isotropic emission from a set of voxels with individual weights
+    (mcvox/mcsource/voxel.py:195-420); the table (weight, x, y, z per voxel) lives in
+    the simulator's float lookup-table pool."""
+    cu_type = 'xo::VoxSrcIsotropicVoxels'
+    cu_refill_lanes = 6
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClIsotropicVoxels(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('n', T.mc_size_t),
+                        ('offset', T.mc_size_t)]
+        return ClIsotropicVoxels
+
+    @staticmethod
+    def cl_options(mc):
+        return [('MC_USE_FP_LUT', True)]
+
+    def __init__(self, voxels, weights=None):
+        super().__init__()
+        voxels = np.asarray(voxels)
+        if voxels.shape[-1] != 3:
+            raise ValueError('Shape of the voxel array must be (n, 3)!')
+        self._data = None
+        self.voxels = voxels
+        if weights is not None:
+            weights = np.asarray(weights)
+            if weights.size != self._data.shape[0]:
+                raise ValueError('The size of array with voxel weights/intensities '
+                                 'does not match the array of voxel indices!')
+            self._data[:, 0] = np.clip(weights, 0.0, 1.0)
+
+    def _set_voxels(self, voxels):
+        voxels = np.asarray(voxels)
+        if voxels.ndim > 2 or voxels.shape[-1] != 3:
+            raise ValueError('Shape of the voxel array must be (n, 3)!')
+        if voxels.ndim == 1:
+            voxels = voxels.reshape(1, 3)
+        if self._data is None or self._data.shape[0] != voxels.shape[0]:
+            dtype = self._data.dtype if self._data is not None else None
+            self._data = np.ones((voxels.shape[0], 4), dtype=dtype)
+        self._data[:, 1:] = voxels
+
+    voxels = property(lambda self: self._data[:, 1:], _set_voxels)
+
+    def _set_weights(self, weights):
+        self._data[:, 0] = np.clip(weights, 0.0, 1.0)
+
+    weights = property(lambda self: self._data[:, 0], _set_weights)
+
+    def update(self, other):
+        if isinstance(other, IsotropicVoxels):
+            self.voxels, self.weights = other.voxels, other.weights
+        elif isinstance(other, dict):
+            self.voxels = other.get('voxels', self.voxels)
+            self.weights = other.get('weights', self.weights)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        for voxel in self.voxels:
+            if not mc.voxels.isvalid(voxel):
+                raise ValueError('Voxel index ({}, {}, {}) is not valid!'.format(*voxel))
+        if self._data.dtype != mc.types.np_float:
+            self._data = self._data.astype(mc.types.np_float)
+        entry = mc.append_r_lut(np.reshape(self._data, (self._data.size,)))
+        target.position.fromarray(mc.voxels.center(np.mean(self.voxels, 0)))
+        target.n = self._data.shape[0]
+        target.offset = entry.offset
+        return target, None, None
+
+    def todict(self):
+        return {'voxels': self.voxels.tolist(), 'weights': self.weights.tolist(),
+                'type': type(self).__name__}

@@ -884,3 +884,24 @@ for _name, _fn in (('mcml_mhg_rect_uniform', mcml_mhg_rect_uniform),
     ALL_CASES[_name] = _fn
     GEOMETRY[_name] = 'mcml'
     GOLDEN_RUN[_name] = (3000, 16)
+
+
+def mcvox_isovoxels_total(mc, **kw):
+    """IsotropicVoxels source: a weighted set of emitting voxels kept in the float
+    lookup-table pool (mcvox/mcsource/voxel.py:195)."""
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc)
+    voxels = np.array([[12, 10, 14], [13, 10, 14], [12, 11, 13], [5, 4, 3], [20, 15, 25]])
+    weights = np.array([1.0, 0.5, 0.25, 0.8, 0.1])
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Radial(A(0, 0.4e-3, 20)), bottom=mc.mcdetector.Total())
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg), mc.mcsource.IsotropicVoxels(voxels, weights),
+                detectors=det, fluence=flu, rnginit=787878, **kw)
+    return _fill_skin_vessel(sim), dict(rmax=25e-3)
+
+
+MCVOX_CASES['mcvox_isovoxels_total'] = mcvox_isovoxels_total
+ALL_CASES['mcvox_isovoxels_total'] = mcvox_isovoxels_total
+GEOMETRY['mcvox_isovoxels_total'] = 'mcvox'
+GOLDEN_RUN['mcvox_isovoxels_total'] = (2000, 16)
