@@ -70,7 +70,8 @@ typedef struct { float g1, g2, b; } pf_hg2;                  /* mcpf/hg2.py:58 *
 typedef struct { pf_gk gk_1, gk_2; float b; } pf_gk2;        /* mcpf/gk2.py:61 */
 typedef struct { float g, a, beta, inv_a, a1, a2; } pf_mgk;  /* mcpf/mgk.py:64 */
 typedef struct { float n; } pf_pc;                           /* mcpf/pc.py:50 */
-typedef struct { float n, beta; } pf_mpc;                    /* mcpf/mpc.py:54 */
+typedef struct { float n, beta; } pf_mpc;
+typedef struct { p3f direction; float g, p; } pf_hgdir;      /* mcpf/hgdir.py:62-66 */                    /* mcpf/mpc.py:54 */
 
 typedef struct { p3f position, dir_medium, dir_sample, dir_reflected; float reflectance; } src_line;
 typedef struct { m3f T; p3f position, direction; p2f sigma; float clip, reflectance; } src_gauss_ml;
@@ -1428,6 +1429,20 @@ static uint32_t boundary_mcml(sim_t *s, int32_t next_index) {
 }
 
 static inline void sim_scatter(sim_t *s) {               /* mcml.template.c:277-290 */
+	if (s->job->pf_kind == XO_PF_HGDIR) {                /* MC_PF_SAMPLE_DIRECTION: mcpf/hgdir.py:95-118 */
+		const pf_hgdir *pf = (const pf_hgdir *)current_pf(s);
+		float g = pf->g, k, cos_theta;
+		p3f out_dir;
+		k = m_div(FP_1 - g*g, FP_1 + g*(FP_2*sim_random(s) - FP_1));
+		cos_theta = m_div(FP_1 + g*g - k*k, FP_2*g);
+		if (g == FP_0) cos_theta = FP_1 - FP_2*sim_random(s);
+		cos_theta = fmaxf(fminf(cos_theta, FP_1), -FP_1);
+		out_dir = (sim_random(s) < pf->p) ? pf->direction : s->dir;
+		cos_theta = (dot3(&s->dir, &out_dir) < FP_0) ? -cos_theta : cos_theta;
+		scatter_direction(s, &out_dir, cos_theta, FP_2PI*sim_random(s));
+		s->dir = out_dir;
+		return;
+	}
 	float fi, cos_theta = pf_sample_angles(s, &fi);
 	scatter_direction(s, &s->dir, cos_theta, fi);
 }

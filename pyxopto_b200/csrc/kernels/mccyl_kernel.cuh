@@ -341,8 +341,7 @@ McKernel(
 				flags |= EV_ABSORPTION;
 				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_abs.mua, opl);
 			} else {
-				float fi, ct = c_pf.sample(rng, lut, &fi);
-				scatter_direction(dir, ct, fi);
+				pf_scatter(c_pf, rng, lut, dir);
 				flags |= EV_SCATTERING;
 			}
 #else
@@ -352,8 +351,7 @@ McKernel(
 				flags |= EV_ABSORPTION;
 				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_abs.mua, opl);
 			}
-			float fi, ct = c_pf.sample(rng, lut, &fi);
-			scatter_direction(dir, ct, fi);
+			pf_scatter(c_pf, rng, lut, dir);
 			flags |= EV_SCATTERING;
 			if (weight < XO_WEIGHT_MIN) {
 #if XO_USE_LOTTERY
@@ -468,8 +466,7 @@ McKernel(
 					flags |= EV_ABSORPTION;
 					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
 				} else {
-					float fi, ct = L.pf.sample(rng, lut, &fi);
-					scatter_direction(dir, ct, fi);
+					pf_scatter(L.pf, rng, lut, dir);
 					flags |= EV_SCATTERING;
 				}
 #else
@@ -479,8 +476,7 @@ McKernel(
 					flags |= EV_ABSORPTION;
 					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
 				}
-				float fi, ct = L.pf.sample(rng, lut, &fi);
-				scatter_direction(dir, ct, fi);
+				pf_scatter(L.pf, rng, lut, dir);
 				flags |= EV_SCATTERING;
 				if (weight < XO_WEIGHT_MIN) {
 #if XO_USE_LOTTERY

@@ -423,8 +423,7 @@ McKernel(
 					flags |= EV_ABSORPTION;
 					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
 				} else {
-					float fi, ct = L.pf.sample(rng, lut, &fi);
-					scatter_direction(dir, ct, fi);
+					pf_scatter(L.pf, rng, lut, dir);
 					flags |= EV_SCATTERING;
 				}
 #else
@@ -436,8 +435,7 @@ McKernel(
 					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
 				}
 #endif
-				float fi, ct = L.pf.sample(rng, lut, &fi);
-				scatter_direction(dir, ct, fi);
+				pf_scatter(L.pf, rng, lut, dir);
 				flags |= EV_SCATTERING;
 #endif
 			}
@@ -722,8 +720,7 @@ McKernel(
 			flags |= EV_ABSORPTION;
 			if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_abs.mua, opl);
 		} else {
-			float fi, ct = c_pf.sample(rng, lut, &fi);
-			scatter_direction(dir, ct, fi);
+			pf_scatter(c_pf, rng, lut, dir);
 			flags |= EV_SCATTERING;
 		}
 #else
@@ -735,8 +732,7 @@ McKernel(
 			if (XoFluence::active) fluence.deposit_prep(acc, flu_prep, window, pos, wfix, opl);
 		}
 #endif
-		float fi, ct = c_pf.sample(rng, lut, &fi);
-		scatter_direction(dir, ct, fi);
+		pf_scatter(c_pf, rng, lut, dir);
 		flags |= EV_SCATTERING;
 		XO_LOTTERY();
 #endif

@@ -226,8 +226,7 @@
 				flags |= EV_ABSORPTION;
 				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
 			} else {
-				float fi, ct = c_pf.sample(rng, lut, &fi);
-				scatter_direction(dir, ct, fi);
+				pf_scatter(c_pf, rng, lut, dir);
 				flags |= EV_SCATTERING;
 			}
 #else
@@ -237,8 +236,7 @@
 				flags |= EV_ABSORPTION;
 				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
 			}
-			float fi, ct = c_pf.sample(rng, lut, &fi);
-			scatter_direction(dir, ct, fi);
+			pf_scatter(c_pf, rng, lut, dir);
 			flags |= EV_SCATTERING;
 			if (weight < XO_WEIGHT_MIN) {
 #if XO_USE_LOTTERY

@@ -343,8 +343,7 @@ McKernel(
 					done = true;
 					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua, opl);
 				} else {
-					float fi, ct = Mt.pf.sample(rng, lut, &fi);
-					scatter_direction(dir, ct, fi);
+					pf_scatter(Mt.pf, rng, lut, dir);
 					flags |= EV_SCATTERING;
 				}
 #else
@@ -356,8 +355,7 @@ McKernel(
 					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua, opl);
 				}
 #endif
-				float fi, ct = Mt.pf.sample(rng, lut, &fi);
-				scatter_direction(dir, ct, fi);
+				pf_scatter(Mt.pf, rng, lut, dir);
 				flags |= EV_SCATTERING;
 #endif
 			}

@@ -259,4 +259,58 @@ struct PfLut {                      // mcpf/lut.py:78-85
 	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
 };
 
+// ---- direction-sampling phase functions (MC_PF_SAMPLE_DIRECTION) -----------------
+// A phase function may produce the new direction itself instead of (cos theta,
+// azimuth) (mcml.template.c:277-290 mcsim_scatter).  `samples_direction` marks it;
+// every scattering site of the kernels goes through pf_scatter().
+template <class Pf, class = void>
+struct pf_samples_direction { static constexpr bool value = false; };
+template <class Pf>
+struct pf_samples_direction<Pf, decltype((void)Pf::samples_direction)> {
+	static constexpr bool value = Pf::samples_direction;
+};
+
+template <class Pf>
+__device__ __forceinline__ void pf_scatter(const Pf &pf, Rng &rng, const float *lut, P3 &dir) {
+	if constexpr (pf_samples_direction<Pf>::value) {
+		pf.sample_dir(rng, lut, dir);
+	} else {
+		float fi, ct = pf.sample(rng, lut, &fi);
+		scatter_direction(dir, ct, fi);
+	}
+}
+
+// prepared form of a direction-sampling phase function (nothing to precompute)
+template <class Pf>
+struct PfDirFast {
+	Pf pf;
+	static constexpr bool samples_direction = true;
+	__device__ __forceinline__ void sample_dir(Rng &rng, const float *lut, P3 &dir) const { pf.sample_dir(rng, lut, dir); }
+	__device__ __forceinline__ float sample(Rng &, const float *, float *azimuth) const { *azimuth = 0.0f; return 1.0f; }
+};
+
+// mcpf/hgdir.py:60-120: Henyey-Greenstein deflection measured from a preferred
+// direction with probability p, from the current direction otherwise (draw
+// order: polar [, isotropic extra], the choice, azimuth)
+struct PfHgDir {
+	P3 direction; float g, p;
+	static constexpr bool uses_lut = false;
+	static constexpr bool samples_direction = true;
+	__device__ __forceinline__ void sample_dir(Rng &rng, const float *lut, P3 &dir) const {
+		(void)lut;
+		float k = M::div(1.0f - g*g, 1.0f + g*(2.0f*rng.next() - 1.0f));
+		float ct = M::div(1.0f + g*g - k*k, 2.0f*g);
+		if (g == 0.0f) ct = 1.0f - 2.0f*rng.next();
+		ct = fmaxf(fminf(ct, 1.0f), -1.0f);
+		P3 out = (rng.next() < p) ? direction : dir;
+		ct = (dot3(dir, out) < 0.0f) ? -ct : ct;
+		scatter_direction(out, ct, XO_FP_2PI*rng.next());
+		dir = out;
+	}
+	// (sample() is never used; present so that generic code compiles)
+	__device__ __forceinline__ float sample(Rng &, const float *, float *azimuth) const { *azimuth = 0.0f; return 1.0f; }
+	typedef PfDirFast<PfHgDir> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
 }  // namespace xo

@@ -50,6 +50,59 @@ class Hg(PfBase):
         return 'Hg(g={})'.format(self._g)
 
 
+class HgDir(PfBase):
+    """Henyey-Greenstein with a preferred scattering direction (mcpf/hgdir.py): with
+    probability ``p`` the deflection is measured from ``direction`` instead of the
+    packet's direction.  Samples the new direction itself
+    (``MC_PF_SAMPLE_DIRECTION``)."""
+    cu_type = 'xo::PfHgDir'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClHgDir(cltypes.Structure):
+            _fields_ = [('direction', T.mc_point3f_t), ('g', T.mc_fp_t), ('p', T.mc_fp_t)]
+        return ClHgDir
+
+    @staticmethod
+    def cl_options(mc):
+        return [('MC_PF_SAMPLE_DIRECTION', True)]
+
+    def __init__(self, g: float, direction=(0.0, 0.0, 1.0), p: float = 1.0):
+        super().__init__()
+        self._direction = np.array((0.0, 0.0, 1.0))
+        self.g, self.p, self.direction = g, p, direction
+
+    def _set_g(self, g):
+        self._g = min(max(float(g), -1.0), 1.0)
+
+    def _set_p(self, p):
+        self._p = min(max(float(p), 0.0), 1.0)
+
+    def _set_direction(self, d):
+        self._direction[:] = d
+        norm = np.linalg.norm(self._direction)
+        if norm == 0.0:
+            raise ValueError('Direction vector norm/length must not be 0!')
+        self._direction *= 1.0/norm
+
+    g = property(lambda self: self._g, _set_g)
+    p = property(lambda self: self._p, _set_p)
+    direction = property(lambda self: self._direction, _set_direction)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        target.g = self._g
+        target.p = self._p
+        target.direction.fromarray(self._direction)
+        return target
+
+    def todict(self):
+        return {'g': self._g, 'p': self._p, 'direction': self._direction.tolist(),
+                'type': type(self).__name__}
+
+
 class MHg(PfBase):
     """Modified Henyey-Greenstein (mcpf/mhg.py)."""
     cu_type = 'xo::PfMHg'

@@ -905,3 +905,21 @@ MCVOX_CASES['mcvox_isovoxels_total'] = mcvox_isovoxels_total
 ALL_CASES['mcvox_isovoxels_total'] = mcvox_isovoxels_total
 GEOMETRY['mcvox_isovoxels_total'] = 'mcvox'
 GOLDEN_RUN['mcvox_isovoxels_total'] = (2000, 16)
+
+
+def mcml_hgdir_line_radial(mc, **kw):
+    """HgDir: a phase function that samples the new direction itself
+    (MC_PF_SAMPLE_DIRECTION, mcpf/hgdir.py)."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 100)),
+                                  bottom=mc.mcdetector.Cartesian(Axis(-3e-3, 3e-3, 30)),
+                                  specular=mc.mcdetector.Total())
+    pf = mc.mcpf.HgDir(0.8, direction=(0.6, 0.0, 0.8), p=0.3)
+    return mc.Mc(_layers(mc, pf), mc.mcsource.Line(), det,
+                 rnginit=898989, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hgdir_line_radial'] = mcml_hgdir_line_radial
+ALL_CASES['mcml_hgdir_line_radial'] = mcml_hgdir_line_radial
+GEOMETRY['mcml_hgdir_line_radial'] = 'mcml'
+GOLDEN_RUN['mcml_hgdir_line_radial'] = (3000, 16)
