@@ -493,6 +493,11 @@ static inline void fp_lut_sample(const float *buffer, const fp_lut_t *lut, float
 }
 
 typedef struct { m3f T; p3f position, direction; float radius, n; fp_lut_t lut; } src_ufiberlut;  /* mcsource/fiber.py:719-727 */
+/* mcsource/fiberni.py:210-215 (aperture = cos_min), :453-458 (aperture = na), :611-616 */
+typedef struct { p3f position; float radius, aperture, n; } src_fiberni;
+typedef struct { p3f position; float radius, n; fp_lut_t lut; } src_fiberlutni;
+/* mcsource/rectangular.py:553-561 */
+typedef struct { p3f position; p2f size; float n, cos_critical; fp_lut_t lut; uint32_t layer_index; } src_rectlut;
 /* fp_linear_lut_rel_sample (mcbase.template.h:2517-2527) */
 static inline void fp_lut_rel_sample(const float *buffer, const fp_lut_t *lut, float where, float *value) {
 	float fp_index = where*(lut->n - 1);
@@ -1151,6 +1156,44 @@ static void launch_mcml(sim_t *s) {
 		s->layer_index = 1;
 		break;
 	}
+	case XO_SRC_UNIFORMFIBERNI:                        /* mcsource/fiberni.py:242-293 */
+	case XO_SRC_LAMBERTIANFIBERNI:                     /* mcsource/fiberni.py:489-534 */
+	case XO_SRC_UNIFORMFIBERLUTNI: {                   /* mcsource/fiberni.py:642-696 */
+		const src_fiberni *src = (const src_fiberni *)j->source;
+		const src_fiberlutni *srcl = (const src_fiberlutni *)j->source;
+		const int is_lut = j->src_kind == XO_SRC_UNIFORMFIBERLUTNI;
+		const float n_core = is_lut ? srcl->n : src->n;
+		float sin_fi, cos_fi, sin_theta, cos_theta = FP_0;
+		float r = m_sqrt(sim_random(s))*src->radius;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		s->pos.x = src->position.x + r*cos_fi;
+		s->pos.y = src->position.y + r*sin_fi;
+		s->pos.z = FP_0;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		if (is_lut) {
+			fp_lut_rel_sample(j->fp_lut, &srcl->lut, sim_random(s), &cos_theta);
+			sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+		} else if (j->src_kind == XO_SRC_LAMBERTIANFIBERNI) {
+			sin_theta = m_sqrt(sim_random(s))*src->aperture;
+		} else {
+			cos_theta = FP_1 - sim_random(s)*(FP_1 - src->aperture);
+			sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
+		}
+		/* emission angle adjusted to the refractive index of the sample */
+		sin_theta = m_div(sin_theta, medium_n(j, 1));
+		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+		s->dir.x = cos_fi*sin_theta; s->dir.y = sin_fi*sin_theta; s->dir.z = cos_theta;
+		r = reflectance_cos2(n_core, medium_n(j, 1), cos_theta);
+		s->weight = FP_1 - r;
+		if (j->det_kind[LOC_SPECULAR]) {
+			p3f dir_in = { s->dir.x, s->dir.y, -s->dir.z }, dir;
+			p3f normal = { FP_0, FP_0, -FP_1 };
+			refract3(&dir_in, &normal, medium_n(j, 1), n_core, &dir);
+			detector_deposit(s, LOC_SPECULAR, &s->pos, &dir, r);
+		}
+		s->layer_index = 1;
+		break;
+	}
 	case XO_SRC_UNIFORMRECTANGULAR:                    /* mcsource/rectangular.py:91-146 */
 	case XO_SRC_LAMBERTIANRECTANGULAR: {               /* mcsource/rectangular.py:376-430 */
 		const src_rect *src = (const src_rect *)j->source;
@@ -1166,6 +1209,24 @@ static void launch_mcml(sim_t *s) {
 			sin_theta = m_sqrt(FP_1 - cos_theta*cos_theta);
 		}
 		sin_theta = m_div(sin_theta, medium_n(j, (int32_t)src->layer_index));
+		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
+		s->dir.x = cos_fi*sin_theta; s->dir.y = sin_fi*sin_theta; s->dir.z = cos_theta;
+		float r = reflectance_cos2(src->n, medium_n(j, (int32_t)src->layer_index), cos_theta);
+		s->weight = FP_1 - r;
+		/* (the specular branch of the reference does not compile: no such case) */
+		s->layer_index = (int32_t)src->layer_index;
+		break;
+	}
+	case XO_SRC_UNIFORMRECTANGULARLUT: {               /* mcsource/rectangular.py:600-660 */
+		const src_rectlut *src = (const src_rectlut *)j->source;
+		float sin_fi, cos_fi, sin_theta, cos_theta = FP_0;
+		s->pos.x = src->position.x + (sim_random(s) - FP_0p5)*src->size.x;
+		s->pos.y = src->position.y + (sim_random(s) - FP_0p5)*src->size.y;
+		s->pos.z = src->position.z;
+		m_sincos(s, sim_random(s)*FP_2PI, &sin_fi, &cos_fi);
+		fp_lut_rel_sample(j->fp_lut, &src->lut, sim_random(s), &cos_theta);
+		sin_theta = m_div(m_sqrt(FP_1 - cos_theta*cos_theta),
+			medium_n(j, (int32_t)src->layer_index));
 		cos_theta = m_sqrt(FP_1 - sin_theta*sin_theta);
 		s->dir.x = cos_fi*sin_theta; s->dir.y = sin_fi*sin_theta; s->dir.z = cos_theta;
 		float r = reflectance_cos2(src->n, medium_n(j, (int32_t)src->layer_index), cos_theta);

@@ -23,7 +23,9 @@ enum {
 	XO_SRC_ISOTROPICPOINT = 4, XO_SRC_UNIFORMBEAM = 5, XO_SRC_LAMBERTIANFIBER = 6,
 	XO_SRC_ISOTROPICVOXEL = 7, XO_SRC_UNIFORMFIBERLUT = 8,
 	XO_SRC_UNIFORMRECTANGULAR = 9, XO_SRC_LAMBERTIANRECTANGULAR = 10,
-	XO_SRC_ISOTROPICVOXELS = 11
+	XO_SRC_ISOTROPICVOXELS = 11,
+	XO_SRC_UNIFORMFIBERNI = 12, XO_SRC_LAMBERTIANFIBERNI = 13, XO_SRC_UNIFORMFIBERLUTNI = 14,
+	XO_SRC_UNIFORMRECTANGULARLUT = 15
 };
 enum {
 	XO_DET_NONE = 0, XO_DET_TOTAL = 1, XO_DET_RADIAL = 2, XO_DET_CARTESIAN = 3,

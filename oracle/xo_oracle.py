@@ -30,7 +30,8 @@ SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
             'IsotropicPoint': 4, 'UniformBeam': 5, 'LambertianFiber': 6,
             'IsotropicVoxel': 7, 'UniformFiberLut': 8,
             'UniformRectangular': 9, 'LambertianRectangular': 10,
-            'IsotropicVoxels': 11}
+            'IsotropicVoxels': 11, 'UniformFiberNI': 12, 'LambertianFiberNI': 13,
+            'UniformFiberLutNI': 14, 'UniformRectangularLut': 15}
 DET_KIND = {'NoneType': 0, 'DetectorDefault': 0, 'Total': 1, 'Radial': 2,
             'Cartesian': 3, 'SixAroundOne': 4, 'RadialPl': 5, 'TotalPl': 6,
             'SymmetricX': 7, 'FiZ': 8, 'CartesianPl': 9, 'SixAroundOnePl': 10,

@@ -202,6 +202,71 @@ struct SrcUniformFiberLut {         // mcsource/fiber.py:719-727, launch :766-83
 	}
 };
 
+// mcsource/fiberni.py:180-296 / :422-535 / :581-698: fibers at normal incidence
+// (no transformation).  APERTURE 0: emission cosine uniform within the NA
+// (`aperture` = cos_min), 1: lambertian, sin = sqrt(u) NA (`aperture` = na).  The
+// emission angle is adjusted to the refractive index of the first sample layer
+// and the weight loses reflectance_cos2(n_core, n_layer, cos); the specular
+// detector sees the direction refracted back into the fiber core.
+template <class Ctx>
+__device__ __forceinline__ void fiberni_finish(const Ctx &ctx, float n, float sf, float cf,
+		float st, Launch &L) {
+	const float n1 = ctx.layer_n(1);
+	st = M::div(st, n1);
+	const float ct = M::sqrt(1.0f - st*st);
+	L.dir.x = cf*st; L.dir.y = sf*st; L.dir.z = ct;
+	const float r = reflectance_cos2(n, n1, ct);
+	L.weight = 1.0f - r;
+	P3 dir_in = { L.dir.x, L.dir.y, -L.dir.z };
+	P3 normal = { 0.0f, 0.0f, -1.0f };
+	L.spec_dir = refract3(dir_in, normal, n1, n);
+	L.spec_weight = r;
+	L.layer = 1;
+}
+
+template <bool LAMBERTIAN>
+struct SrcFiberNI {
+	P3 position; float radius, aperture, n;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf, st;
+		float r = M::sqrt(rng.next())*radius;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		L.pos.x = position.x + r*cf;
+		L.pos.y = position.y + r*sf;
+		L.pos.z = 0.0f;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		if (LAMBERTIAN) {
+			st = M::sqrt(rng.next())*aperture;
+		} else {
+			float ct = 1.0f - rng.next()*(1.0f - aperture);
+			st = M::sqrt(1.0f - ct*ct);
+		}
+		fiberni_finish(ctx, n, sf, cf, st, L);
+	}
+};
+typedef SrcFiberNI<false> SrcUniformFiberNI;
+typedef SrcFiberNI<true> SrcLambertianFiberNI;
+
+struct SrcUniformFiberLutNI {       // mcsource/fiberni.py:611-616, launch :642-696
+	P3 position; float radius, n; FpLut lut;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf;
+		float r = M::sqrt(rng.next())*radius;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		L.pos.x = position.x + r*cf;
+		L.pos.y = position.y + r*sf;
+		L.pos.z = 0.0f;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 0.0f;
+		lut_sample_index(ctx.lut, lut.n, lut.offset, rng.next()*(float)(lut.n - 1), false, &ct);
+		fiberni_finish(ctx, n, sf, cf, M::sqrt(1.0f - ct*ct), L);
+	}
+};
+
 // mcsource/rectangular.py:32-315 / :317-528: rectangular emitter at the surface or
 // inside a layer; emission cosine uniform within the NA (Uniform) or sin = sqrt(u)
 // NA (Lambertian), adjusted to the refractive index of the layer.  (The
@@ -237,6 +302,32 @@ struct SrcRectangular {
 };
 typedef SrcRectangular<false> SrcUniformRectangular;
 typedef SrcRectangular<true> SrcLambertianRectangular;
+
+// mcsource/rectangular.py:530-854: rectangular emitter with a tabulated emission
+// cosine (EmissionLut in the float pool, sampled with a uniform number).  Like the
+// other rectangular sources its specular branch names a missing field.
+struct SrcUniformRectangularLut {
+	P3 position; P2 size; float n, cos_critical; FpLut lut; u32 layer_index;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const {
+		float sf, cf;
+		L.pos.x = position.x + (rng.next() - 0.5f)*size.x;
+		L.pos.y = position.y + (rng.next() - 0.5f)*size.y;
+		L.pos.z = position.z;
+		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float ct = 0.0f;
+		lut_sample_index(ctx.lut, lut.n, lut.offset, rng.next()*(float)(lut.n - 1), false, &ct);
+		const float n_layer = ctx.layer_n((int)layer_index);
+		const float st = M::div(M::sqrt(1.0f - ct*ct), n_layer);
+		ct = M::sqrt(1.0f - st*st);
+		L.dir.x = cf*st; L.dir.y = sf*st; L.dir.z = ct;
+		L.weight = 1.0f - reflectance_cos2(n, n_layer, ct);
+		L.spec_dir = L.dir;
+		L.spec_weight = 0.0f;
+		L.layer = (i32)layer_index;
+	}
+};
 
 struct SrcIsotropicPoint {          // mcsource/point.py:46-49
 	P3 position; u32 layer_index;

@@ -1,5 +1,5 @@
 """Photon packet sources of the planar simulator (mirror of ``xopto/mcml/mcsource``:
-Line, GaussianBeam, UniformFiber, IsotropicPoint)."""
+Line, GaussianBeam, UniformBeam, the fiber and rectangular sources, IsotropicPoint)."""
 from typing import Tuple
 
 import numpy as np
@@ -352,6 +352,120 @@ class UniformFiberLut(UniformFiber):
         return target, None, None
 
 
+class UniformFiberNI(Source):
+    """Optical fiber at normal incidence with uniform emission within the NA
+    (mcsource/fiberni.py:180-419): no transformation, emission angle adjusted to
+    the refractive index of the first sample layer."""
+    cu_type = 'xo::SrcUniformFiberNI'
+    cu_refill_lanes = 8
+    _update_keys = ('fiber', 'position')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformFiberNI(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('cos_min', T.mc_fp_t), ('n', T.mc_fp_t)]
+        return ClUniformFiberNI
+
+    def __init__(self, fiber: MultimodeFiber, position=(0.0, 0.0, 0.0)):
+        super().__init__()
+        self._fiber = fiber
+        self._position = np.zeros((3,))
+        self.position = position
+
+    def _set_fiber(self, f):
+        self._fiber = f
+
+    def _set_position(self, p):
+        self._position[:] = p
+        self._position[2] = 0.0
+
+    fiber = property(lambda self: self._fiber, _set_fiber)
+    position = property(lambda self: self._position, _set_position)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.n = self._fiber.ncore
+        target.cos_min = (1.0 - self._fiber.na**2)**0.5
+        target.position.fromarray(self._position)
+        target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+    def todict(self):
+        return {'fiber': self._fiber.todict(), 'position': self._position.tolist(),
+                'type': type(self).__name__}
+
+    @classmethod
+    def fromdict(cls, data):
+        data = dict(data)
+        data.pop('type', None)
+        fiber = data.pop('fiber')
+        if isinstance(fiber, dict):
+            kind = MultimodeFiberLut if 'emission' in fiber or 'collection' in fiber \
+                else MultimodeFiber
+            fiber = kind.fromdict(fiber)
+        return cls(fiber, **data)
+
+    def __str__(self):
+        return '{} # id 0x{:>08X}.'.format(self.__repr__(), id(self))
+
+    def __repr__(self):
+        return '{}(fiber={}, position=({}, {}, {}))'.format(
+            type(self).__name__, self._fiber, *self._position)
+
+
+class LambertianFiberNI(UniformFiberNI):
+    """Optical fiber at normal incidence emitting a lambertian beam within the NA
+    (mcsource/fiberni.py:422-578)."""
+    cu_type = 'xo::SrcLambertianFiberNI'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClLambertianFiberNI(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('na', T.mc_fp_t), ('n', T.mc_fp_t)]
+        return ClLambertianFiberNI
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.n = self._fiber.ncore
+        target.na = self._fiber.na
+        target.position.fromarray(self._position)
+        target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+
+class UniformFiberLutNI(UniformFiberNI):
+    """Optical fiber at normal incidence with a tabulated angular emission
+    characteristic (mcsource/fiberni.py:581-836; EmissionLut in the float pool)."""
+    cu_type = 'xo::SrcUniformFiberLutNI'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformFiberLutNI(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('n', T.mc_fp_t), ('lut', LinearLut.cl_type(mc))]
+        return ClUniformFiberLutNI
+
+    @staticmethod
+    def cl_options(mc):
+        return [('MC_USE_FP_LUT', True)]
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.position.fromarray(self._position)
+        target.radius = self._fiber.dcore*0.5
+        target.n = self._fiber.ncore
+        self._fiber.emission.cl_pack(mc, target.lut)
+        return target, None, None
+
+
 class UniformRectangular(Source):
     """Rectangular emitter (width x height) with uniform emission within the NA, at
     the top surface or inside a layer (mcsource/rectangular.py:32-315).  As in the
@@ -424,6 +538,76 @@ class LambertianRectangular(UniformRectangular):
 
     def _aperture(self) -> float:
         return self._na
+
+
+class UniformRectangularLut(Source):
+    """Rectangular emitter with a tabulated angular emission characteristic
+    (mcsource/rectangular.py:530-854): the emission cosine (valid for air) is
+    sampled from an EmissionLut in the float pool and adjusted to the refractive
+    index of the layer that holds the source."""
+    cu_type = 'xo::SrcUniformRectangularLut'
+    cu_refill_lanes = 4
+    _update_keys = ('lut', 'width', 'height', 'n', 'position')
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformRectangularLut(cltypes.Structure):
+            _fields_ = [('position', T.mc_point3f_t), ('size', T.mc_point2f_t),
+                        ('n', T.mc_fp_t), ('cos_critical', T.mc_fp_t),
+                        ('lut', EmissionLut.cl_type(mc)), ('layer_index', T.mc_size_t)]
+        return ClUniformRectangularLut
+
+    @staticmethod
+    def cl_options(mc):
+        return [('MC_USE_FP_LUT', True)]
+
+    def __init__(self, lut: EmissionLut, width: float, height: float, n: float,
+                 position=(0.0, 0.0, 0.0)):
+        super().__init__()
+        self._lut = lut
+        self._width, self._height = float(width), float(height)
+        self._n = max(1.0, float(n))
+        self._position = np.zeros((3,))
+        self.position = position
+
+    def _set_position(self, p):
+        self._position[:] = p
+
+    def _set_lut(self, lut):
+        self._lut = lut
+
+    position = property(lambda self: self._position, _set_position)
+    lut = property(lambda self: self._lut, _set_lut)
+    width = property(lambda self: self._width, lambda self, v: setattr(self, '_width', float(v)))
+    height = property(lambda self: self._height, lambda self, v: setattr(self, '_height', float(v)))
+    n = property(lambda self: self._n, lambda self, v: setattr(self, '_n', max(1.0, float(v))))
+
+    def cl_pack(self, mc, target=None):
+        if mc.detectors is not None and type(mc.detectors.specular).__name__ != 'DetectorDefault':
+            raise NotImplementedError(
+                'Rectangular sources cannot be combined with a specular detector (the '
+                'reference kernel does not build: rectangular.py:650 names a missing field).')
+        if target is None:
+            target = self.cl_type(mc)()
+        if self._position[2] <= 0.0:
+            position = (self._position[0], self._position[1], 0.0)
+            layer_index = 1
+        else:
+            position = self._position
+            layer_index = mc.layer_index(self._position[2])
+        self._lut.cl_pack(mc, target.lut)
+        target.position.fromarray(position)
+        target.size.fromarray([self._width, self._height])
+        target.n = self._n
+        target.cos_critical = boundary.cos_critical(self._n, mc.layers[layer_index].n)
+        target.layer_index = layer_index
+        return target, None, None
+
+    def todict(self):
+        return {'lut': self._lut.todict(), 'width': self._width, 'height': self._height,
+                'n': self._n, 'position': self._position.tolist(),
+                'type': type(self).__name__}
 
 
 class IsotropicPoint(Source):

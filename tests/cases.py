@@ -923,3 +923,81 @@ MCML_CASES['mcml_hgdir_line_radial'] = mcml_hgdir_line_radial
 ALL_CASES['mcml_hgdir_line_radial'] = mcml_hgdir_line_radial
 GEOMETRY['mcml_hgdir_line_radial'] = 'mcml'
 GOLDEN_RUN['mcml_hgdir_line_radial'] = (3000, 16)
+
+
+def mcml_hg_ufiberni_radial(mc, **kw):
+    """UniformFiberNI source (normal incidence, mcsource/fiberni.py:180) with a specular
+    detector that sees the direction refracted back into the core."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 100)),
+                                  bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Radial(Axis(0, 0.2e-3, 20), cosmin=0.98))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)),
+                 mc.mcsource.UniformFiberNI(_fiber(mc), position=(0.05e-3, -0.02e-3, 0)),
+                 det, rnginit=919191, **kw), dict(rmax=20e-3)
+
+
+def mcml_mhg_lfiberni_cart(mc, **kw):
+    """LambertianFiberNI source (mcsource/fiberni.py:422)."""
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Cartesian(Axis(-2e-3, 2e-3, 20)),
+                                  bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.FluenceRz(Axis(0, 2e-3, 20), Axis(0, 3e-3, 30))
+    return mc.Mc(_layers(mc, mc.mcpf.MHg(0.8, 0.9)),
+                 mc.mcsource.LambertianFiberNI(_fiber(mc), position=(-0.1e-3, 0, 0)),
+                 det, fluence=flu, rnginit=929292, **kw), dict(rmax=20e-3)
+
+
+def mcml_hg_ufiberlutni_total(mc, **kw):
+    """UniformFiberLutNI source: tabulated emission at normal incidence
+    (mcsource/fiberni.py:581)."""
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase.mcutil.lut import EmissionLut
+        from xopto.mcml.mcutil.fiber import MultimodeFiberLut
+    else:
+        EmissionLut = mc.mcsource.EmissionLut
+        MultimodeFiberLut = mc.mcsource.MultimodeFiberLut
+    ct = np.linspace(np.cos(np.deg2rad(20.0)), 1.0, 30)
+    emission = EmissionLut(np.exp(-((1.0 - ct)/0.02)**2), ct, n=150, npts=2000)
+    fib = MultimodeFiberLut(200e-6, 220e-6, 1.462, None, emission=emission)
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 50)),
+                                  bottom=mc.mcdetector.Total(),
+                                  specular=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)),
+                 mc.mcsource.UniformFiberLutNI(fib, position=(0, 0.1e-3, 0)),
+                 det, rnginit=939393, **kw), dict(rmax=20e-3)
+
+
+for _name, _fn in (('mcml_hg_ufiberni_radial', mcml_hg_ufiberni_radial),
+                   ('mcml_mhg_lfiberni_cart', mcml_mhg_lfiberni_cart),
+                   ('mcml_hg_ufiberlutni_total', mcml_hg_ufiberlutni_total)):
+    MCML_CASES[_name] = _fn
+    ALL_CASES[_name] = _fn
+    GEOMETRY[_name] = 'mcml'
+    GOLDEN_RUN[_name] = (3000, 16)
+
+
+def mcml_hg_rectlut_inside(mc, **kw):
+    """UniformRectangularLut source buried in the second layer: tabulated emission
+    (mcsource/rectangular.py:530)."""
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase.mcutil.lut import EmissionLut
+    else:
+        EmissionLut = mc.mcsource.EmissionLut
+    ct = np.linspace(np.cos(np.deg2rad(40.0)), 1.0, 50)
+    emission = EmissionLut(ct**2, ct, n=300, npts=2000)
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 5e-3, 50)),
+                                  bottom=mc.mcdetector.Cartesian(Axis(-2e-3, 2e-3, 10)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)),
+                 mc.mcsource.UniformRectangularLut(emission, 0.6e-3, 0.3e-3, 1.55,
+                                                   position=(0.1e-3, 0, 1.2e-3)),
+                 det, rnginit=949494, **kw), dict(rmax=20e-3)
+
+
+MCML_CASES['mcml_hg_rectlut_inside'] = mcml_hg_rectlut_inside
+ALL_CASES['mcml_hg_rectlut_inside'] = mcml_hg_rectlut_inside
+GEOMETRY['mcml_hg_rectlut_inside'] = 'mcml'
+GOLDEN_RUN['mcml_hg_rectlut_inside'] = (3000, 16)

@@ -97,7 +97,9 @@ def test_deterministic_mode_bit_exact(name):
                                   'mcml_surface_fiberarray', 'mcml_hg_line_totallut',
                                   'mcml_lut_ufiberlut_totallut', 'mcml_hg_line_fiberlutarray',
                                   'mcml_mhg_rect_uniform', 'mcml_hg_rect_lambertian_inside',
-                                  'mcvox_isovoxels_total', 'mcml_hgdir_line_radial'])
+                                  'mcvox_isovoxels_total', 'mcml_hgdir_line_radial',
+                                  'mcml_hg_ufiberni_radial', 'mcml_mhg_lfiberni_cart',
+                                  'mcml_hg_ufiberlutni_total', 'mcml_hg_rectlut_inside'])
 def test_throughput_mode_statistics(name):
     """Fast mode vs oracle (libm, different schedule): totals within 4 sigma."""
     sim, geom, _ = build_sim(name)

@@ -42,7 +42,12 @@ def test_portable_math_is_statistically_the_reference(name):
     a, b = float(res['accu'].sum()), float(g['accu'].sum())
     n = cases.GOLDEN_RUN[name][0]
     assert abs(a - b) <= max(1e-3*b, 2*(n/t)**0.5*0x7FFFFF)
-    if g['accu'].size >= 20:      # bin-wise identity is meaningless for 2 totals
+    # a work-item whose stream position shifted spreads its remaining packets over
+    # all bins: at most a couple of the work-items may do so, and the bin-wise
+    # identity below is checked for runs where none did
+    diverged = t - int(np.count_nonzero(res['rng_x'][:t] == g['rng_x_after']))
+    assert diverged <= 2
+    if g['accu'].size >= 20 and diverged == 0:   # (meaningless for 2 totals)
         # (bins of detectors that scale the weight by a continuous sensitivity, e.g.
         # TotalLut, differ by a few counts of ~1e7 when a cosine moves by one ulp)
         a64, b64 = res['accu'].astype(np.int64), g['accu'].astype(np.int64)
