@@ -90,41 +90,84 @@ struct VoxSrcUniformBeam {          // mcvox/mcsource/uniformbeam.py:36-44
 	}
 };
 
-struct VoxSrcUniformFiber {         // mcvox/mcsource/fiber.py (UniformFiber)
+// mcvox/mcsource/fiber.py: the three fiber sources share everything but the sampling
+// of the emission angle.  `st` is the sine of the polar angle in air; the packet
+// leaves the core at st / n, enters the box where the fiber axis meets it and is
+// refracted into the material of the entry voxel.
+template <class Ctx>
+__device__ __forceinline__ void vox_fiber_emit(const Ctx &ctx, const M3 &T, const P3 &position,
+		const P3 &direction, float n, const P3 &pm, float sf, float cf, float st, Launch &L) {
+	float rs = 0.0f;
+	st = M::div(st, n);             // emission angle inside the fibre core
+	const float ct = M::sqrt(1.0f - st*st);
+	P3 pd = { cf*st, sf*st, ct };
+	P3 packet_dir = transform3(T, pd);
+	P3 sd = { direction.x, direction.y, direction.z };
+	if (ctx.box_contains(pm)) { sd.x = -sd.x; sd.y = -sd.y; sd.z = -sd.z; }
+	P3 refracted = packet_dir, p = position, isect, normal;
+	if (ctx.box_intersect(pm, sd, &isect, &normal)) {
+		normal.x = -normal.x; normal.y = -normal.y; normal.z = -normal.z;
+		p = isect;
+		rs = vox_enter_n(ctx, isect, normal, packet_dir, &refracted, n);
+	} else {
+		p = ctx.cfg.top_left;
+		rs = 1.0f;
+	}
+	L.pos = p;
+	L.dir = refracted;
+	L.spec_dir = packet_dir;
+	L.spec_weight = rs;
+	L.weight = 1.0f - rs;
+}
+
+// core position (2 draws) and azimuth of the emission direction (1 draw)
+__device__ __forceinline__ P3 vox_fiber_core_point(Rng &rng, const M3 &T, const P3 &position,
+		float radius, float *sf, float *cf) {
+	float r = M::sqrt(rng.next())*radius;
+	M::sincos(rng.next()*XO_FP_2PI, sf, cf);
+	P3 ps = { r*(*cf), r*(*sf), 0.0f };
+	P3 pm = transform3(T, ps);
+	pm.x += position.x; pm.y += position.y; pm.z += position.z;
+	M::sincos(rng.next()*XO_FP_2PI, sf, cf);
+	return pm;
+}
+
+struct VoxSrcUniformFiber {         // mcvox/mcsource/fiber.py:178-521 (UniformFiber)
 	M3 T; P3 position, direction; float radius, cos_min, n;
 	__device__ __forceinline__ P3 origin() const { return position; }
 	template <class Ctx>
 	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
 		(void)prev_pos;
-		float sf, cf, rs = 0.0f;
-		float r = M::sqrt(rng.next())*radius;
-		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
-		P3 ps = { r*cf, r*sf, 0.0f };
-		P3 pm = transform3(T, ps);
-		pm.x += position.x; pm.y += position.y; pm.z += position.z;
-		M::sincos(rng.next()*XO_FP_2PI, &sf, &cf);
+		float sf, cf;
+		P3 pm = vox_fiber_core_point(rng, T, position, radius, &sf, &cf);
 		float ct = 1.0f - rng.next()*(1.0f - cos_min);
-		float st = M::sqrt(1.0f - ct*ct);
-		st = M::div(st, n);             // emission angle inside the fibre core
-		ct = M::sqrt(1.0f - st*st);
-		P3 pd = { cf*st, sf*st, ct };
-		P3 packet_dir = transform3(T, pd);
-		P3 sd = { direction.x, direction.y, direction.z };
-		if (ctx.box_contains(pm)) { sd.x = -sd.x; sd.y = -sd.y; sd.z = -sd.z; }
-		P3 refracted = packet_dir, p = position, isect, normal;
-		if (ctx.box_intersect(pm, sd, &isect, &normal)) {
-			normal.x = -normal.x; normal.y = -normal.y; normal.z = -normal.z;
-			p = isect;
-			rs = vox_enter_n(ctx, isect, normal, packet_dir, &refracted, n);
-		} else {
-			p = ctx.cfg.top_left;
-			rs = 1.0f;
-		}
-		L.pos = p;
-		L.dir = refracted;
-		L.spec_dir = packet_dir;
-		L.spec_weight = rs;
-		L.weight = 1.0f - rs;
+		vox_fiber_emit(ctx, T, position, direction, n, pm, sf, cf, M::sqrt(1.0f - ct*ct), L);
+	}
+};
+
+struct VoxSrcLambertianFiber {      // mcvox/mcsource/fiber.py:523-745 (sin = sqrt(u) NA)
+	M3 T; P3 position, direction; float radius, na, n;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		float sf, cf;
+		P3 pm = vox_fiber_core_point(rng, T, position, radius, &sf, &cf);
+		vox_fiber_emit(ctx, T, position, direction, n, pm, sf, cf, M::sqrt(rng.next())*na, L);
+	}
+};
+
+struct VoxSrcUniformFiberLut {      // mcvox/mcsource/fiber.py:747- (tabulated emission cosine)
+	M3 T; P3 position, direction; float radius, n; FpLut lut;
+	__device__ __forceinline__ P3 origin() const { return position; }
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+		(void)prev_pos;
+		float sf, cf;
+		P3 pm = vox_fiber_core_point(rng, T, position, radius, &sf, &cf);
+		float ct = 0.0f;
+		lut_sample_index(ctx.lut, lut.n, lut.offset, rng.next()*(float)(lut.n - 1), false, &ct);
+		vox_fiber_emit(ctx, T, position, direction, n, pm, sf, cf, M::sqrt(1.0f - ct*ct), L);
 	}
 };
 

@@ -1,11 +1,13 @@
 """Photon packet sources of the voxelised simulator (mirror of
-``xopto/mcvox/mcsource``: Line, GaussianBeam, IsotropicPoint)."""
+``xopto/mcvox/mcsource``: Line, GaussianBeam, UniformBeam, the fiber sources,
+IsotropicPoint, IsotropicVoxel(s))."""
 import numpy as np
 
 from ..cl import cltypes
 from ..mcbase.mcutil import boundary, geometry
 from ..mcml.mcsource import Source, _unit
-from ..mcbase.mcutil.fiber import MultimodeFiber  # noqa: F401
+from ..mcbase.mcutil.fiber import MultimodeFiber, MultimodeFiberLut  # noqa: F401
+from ..mcbase.mcutil.lut import EmissionLut, LinearLut  # noqa: F401
 
 
 class Line(Source):
@@ -229,6 +231,65 @@ class UniformFiber(Source):
     def todict(self):
         return {'fiber': self._fiber.todict(), 'position': self._position.tolist(),
                 'direction': self._direction.tolist(), 'type': type(self).__name__}
+
+
+class LambertianFiber(UniformFiber):
+    """Multimode fibre emitting a lambertian beam within its NA
+    (mcvox/mcsource/fiber.py:523-745)."""
+    cu_type = 'xo::VoxSrcLambertianFiber'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClLambertianFiber(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('na', T.mc_fp_t), ('n', T.mc_fp_t)]
+        return ClLambertianFiber
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.n = self._fiber.ncore
+        target.na = self._fiber.na
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius = self._fiber.dcore*0.5
+        return target, None, None
+
+
+class UniformFiberLut(UniformFiber):
+    """Multimode fibre with a tabulated angular emission characteristic
+    (mcvox/mcsource/fiber.py:747-): the emission cosine (valid for air) is sampled
+    from the fibre's EmissionLut in the float pool."""
+    cu_type = 'xo::VoxSrcUniformFiberLut'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClUniformFiberLut(cltypes.Structure):
+            _fields_ = [('transformation', T.mc_matrix3f_t), ('position', T.mc_point3f_t),
+                        ('direction', T.mc_point3f_t), ('radius', T.mc_fp_t),
+                        ('n', T.mc_fp_t), ('lut', LinearLut.cl_type(mc))]
+        return ClUniformFiberLut
+
+    @staticmethod
+    def cl_options(mc):
+        return [('MC_USE_FP_LUT', True)]
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.cl_type(mc)()
+        target.transformation.fromarray(
+            geometry.transform_base((0.0, 0.0, 1.0), self._direction))
+        target.position.fromarray(self._position)
+        target.direction.fromarray(self._direction)
+        target.radius = self._fiber.dcore*0.5
+        target.n = self._fiber.ncore
+        self._fiber.emission.cl_pack(mc, target.lut)
+        return target, None, None
 
 
 class IsotropicPoint(Source):

@@ -1001,3 +1001,46 @@ MCML_CASES['mcml_hg_rectlut_inside'] = mcml_hg_rectlut_inside
 ALL_CASES['mcml_hg_rectlut_inside'] = mcml_hg_rectlut_inside
 GEOMETRY['mcml_hg_rectlut_inside'] = 'mcml'
 GOLDEN_RUN['mcml_hg_rectlut_inside'] = (3000, 16)
+
+
+def mcvox_lfiber_radial(mc, **kw):
+    """mcvox LambertianFiber tilted against the top surface (mcvox/mcsource/fiber.py:523)."""
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc, n=(20, 20, 16))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(A(0, 0.4e-3, 20)),
+                                  bottom=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg),
+                mc.mcsource.LambertianFiber(_fiber(mc), position=(-5e-6, 10e-6, 0.0),
+                                            direction=(0.1, 0.0, 1.0)),
+                detectors=det, rnginit=959595, **kw)
+    return _fill_skin_vessel(sim, center=200e-6, radius=60e-6), dict(rmax=5e-3)
+
+
+def mcvox_ufiberlut_fluence(mc, **kw):
+    """mcvox UniformFiberLut: tabulated emission + deposition grid
+    (mcvox/mcsource/fiber.py:747)."""
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcbase.mcutil.lut import EmissionLut
+        from xopto.mcvox.mcutil.fiber import MultimodeFiberLut
+    else:
+        EmissionLut = mc.mcsource.EmissionLut
+        MultimodeFiberLut = mc.mcsource.MultimodeFiberLut
+    ct = np.linspace(np.cos(np.deg2rad(25.0)), 1.0, 40)
+    emission = EmissionLut(np.exp(-((1.0 - ct)/0.03)**2), ct, n=200, npts=2000)
+    fib = MultimodeFiberLut(200e-6, 220e-6, 1.462, None, emission=emission)
+    vox = _vox_grid(mc, n=(20, 20, 16))
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), specular=mc.mcdetector.Total())
+    sim = mc.Mc(vox, _vox_materials(mc, mc.mcpf.Hg),
+                mc.mcsource.UniformFiberLut(fib, position=(5e-6, -5e-6, 0.0),
+                                            direction=(0.0, 0.1, 1.0)),
+                detectors=det, fluence=flu, rnginit=969696, **kw)
+    return _fill_skin_vessel(sim, center=200e-6, radius=60e-6), dict(rmax=5e-3)
+
+
+for _name, _fn in (('mcvox_lfiber_radial', mcvox_lfiber_radial),
+                   ('mcvox_ufiberlut_fluence', mcvox_ufiberlut_fluence)):
+    MCVOX_CASES[_name] = _fn
+    ALL_CASES[_name] = _fn
+    GEOMETRY[_name] = 'mcvox'
+    GOLDEN_RUN[_name] = (1500, 16)

@@ -99,7 +99,8 @@ def test_deterministic_mode_bit_exact(name):
                                   'mcml_mhg_rect_uniform', 'mcml_hg_rect_lambertian_inside',
                                   'mcvox_isovoxels_total', 'mcml_hgdir_line_radial',
                                   'mcml_hg_ufiberni_radial', 'mcml_mhg_lfiberni_cart',
-                                  'mcml_hg_ufiberlutni_total', 'mcml_hg_rectlut_inside'])
+                                  'mcml_hg_ufiberlutni_total', 'mcml_hg_rectlut_inside',
+                                  'mcvox_lfiber_radial', 'mcvox_ufiberlut_fluence'])
 def test_throughput_mode_statistics(name):
     """Fast mode vs oracle (libm, different schedule): totals within 4 sigma."""
     sim, geom, _ = build_sim(name)
