@@ -94,17 +94,26 @@ class ClockSampler:
                 'reasons': sorted(reasons)}
 
 
-def cpu_reference_run(config: str, sample_packets: int, threads: int):
+def cpu_reference_run(config: str, sample_packets: int, threads: int, variant: str = None):
     """The reference's own kernel (oracle/_ref, built here from the rendered
-    reference text) or, when that .so is absent, the oracle port, on host cores
-    with the dynamic schedule.  Returns (packets/s, kind, seconds)."""
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import importlib
+    reference text, on inputs packed by the reference's host layer) or, when that
+    build is absent, the oracle port, on host cores with the dynamic schedule.
+    Returns (packets/s, kind, seconds, compiler flags).  Imports nothing of
+    pyxopto_b200 when the reference build is present."""
+    oracle_dir = os.path.join(ROOT, 'oracle')
+    if oracle_dir not in sys.path:
+        sys.path.insert(0, oracle_dir)
     import refbench
-    geom = benchcfg.GEOMETRY[config]
-    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
-    sim = benchcfg.CONFIGS[config](mc)
-    return refbench.run(sim, geom, config, sample_packets, threads)
+    return refbench.run(config, benchcfg.GEOMETRY[config], sample_packets, threads, variant)
+
+
+def cpu_reference_variant(config: str, pilot: int, threads: int):
+    """The faster usable build of the reference kernel (IEEE or -ffast-math)."""
+    oracle_dir = os.path.join(ROOT, 'oracle')
+    if oracle_dir not in sys.path:
+        sys.path.insert(0, oracle_dir)
+    import refbench
+    return refbench.fastest_variant(config, benchcfg.GEOMETRY[config], pilot, threads)[0]
 
 
 def main():
@@ -150,9 +159,10 @@ def main():
             return 0
         sample = int(args.cpu_sample or {'c2_skin': 3e5, 'c3_vox': 2e4, 'c4_trace': 2e4}.get(config, 5e4))
         times = []
-        kind = 'port'
+        kind, flags = 'port', ''
+        variant = cpu_reference_variant(config, max(sample//4, 1000), ncores)
         for i in range(args.warmup + args.steps):
-            pps, kind, secs = cpu_reference_run(config, sample, ncores)
+            pps, kind, secs, flags = cpu_reference_run(config, sample, ncores, variant)
             if i >= args.warmup:
                 times.append(secs)
         total = sum(times)
@@ -165,7 +175,7 @@ def main():
             'config': {'workload': workload, 'packets_per_step': sample,
                        'schedule': 'dynamic atomic packet counter, one work-item per host thread'},
             'cpu_baseline': {'value': value, 'unit': 'packets/s', 'cores': ncores,
-                             'kind': kind,
+                             'kind': kind, 'flags': flags,
                              'sample': '{} packets per step, {} timed steps'.format(sample, len(times))},
             'e2e': {'value': value, 'unit': 'packets/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
@@ -376,16 +386,18 @@ def main():
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             try:
+                variant = None
                 if args.cpu_sample:
                     sample = int(args.cpu_sample)
                 else:
                     # pilot run, then a sample sized for ~12 s of CPU work
                     pilot = int({'c4_trace': 5e3}.get(config, 5e4))
-                    pps0, _, _ = cpu_reference_run(config, pilot, ncores)
+                    variant = cpu_reference_variant(config, pilot, ncores)
+                    pps0 = cpu_reference_run(config, pilot, ncores, variant)[0]
                     sample = int(min(max(pps0*12.0, pilot), 2e8 if config != 'c4_trace' else 1e5))
-                pps, kind, secs = cpu_reference_run(config, sample, ncores)
+                pps, kind, secs, flags = cpu_reference_run(config, sample, ncores, variant)
                 cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
-                                'kind': kind,
+                                'kind': kind, 'flags': flags,
                                 'sample': '{} packets of the same workload in {:.1f} s'.format(
                                     sample, secs)}
             except Exception as exc:    # the baseline must never take the bench down

@@ -263,7 +263,7 @@ McKernel(
 				if (state == ST_DEAD) {
 					if (pk_next >= pk_end && !budget_dry) {
 						pk_next = atomicAdd(num_packets_done, chunk);
-						pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
+						pk_end = (pk_next < num_packets && num_packets - pk_next > chunk) ? pk_next + chunk : num_packets;
 						if (pk_next >= num_packets) { pk_end = pk_next; budget_dry = true; }
 					}
 					if (pk_next < pk_end) {
@@ -377,7 +377,7 @@ McKernel(
 	(void)chunk;
 #else
 	pk_next = atomicAdd(num_packets_done, chunk);
-	pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
+	pk_end = (pk_next < num_packets && num_packets - pk_next > chunk) ? pk_next + chunk : num_packets;
 	if (pk_next >= num_packets) pk_end = pk_next;
 #endif
 	bool started = false;
@@ -517,7 +517,7 @@ McKernel(
 #if !XO_DETERMINISTIC
 				if (pk_next >= pk_end) {
 					pk_next = atomicAdd(num_packets_done, chunk);
-					pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
+					pk_end = (pk_next < num_packets && num_packets - pk_next > chunk) ? pk_next + chunk : num_packets;
 					if (pk_next >= num_packets) pk_end = pk_next;
 				}
 #endif

@@ -216,7 +216,7 @@ McKernel(
 #else
 	(void)nthreads;
 	pk_next = atomicAdd(num_packets_done, chunk);
-	pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
+	pk_end = (pk_next < num_packets && num_packets - pk_next > chunk) ? pk_next + chunk : num_packets;
 	if (pk_next >= num_packets) pk_end = pk_next;
 #endif
 
@@ -389,7 +389,7 @@ McKernel(
 #if !XO_DETERMINISTIC
 				if (pk_next >= pk_end) {
 					pk_next = atomicAdd(num_packets_done, chunk);
-					pk_end = pk_next + chunk < num_packets ? pk_next + chunk : num_packets;
+					pk_end = (pk_next < num_packets && num_packets - pk_next > chunk) ? pk_next + chunk : num_packets;
 					if (pk_next >= num_packets) pk_end = pk_next;
 				}
 #endif

@@ -388,7 +388,12 @@ class McBase(CuWorker):
         return tuple(float(v) for v in np.asarray(pos, dtype=np.float64).reshape(-1)[:3])
 
     fluence_window_bytes = None      # None: automatic
-    max_batch = 0xFFFFFFFF           # packets per kernel launch (32-bit device counter)
+    # packets per kernel launch: the device packet counter is 32 bits wide and every
+    # thread claims at most one more chunk (<= chunk_max packets, mcml / mcvox
+    # throughput loops: one per lane) after the budget is exhausted, so the counter
+    # ends at most max_threads*chunk_max (< 2^24) above the budget and must not wrap
+    max_batch = 0xFFFFFFFF - (1 << 24)
+    _packet_counter_start = 0
     fluence_block = FLUENCE_BLOCK
 
     def _window_enabled(self) -> bool:
@@ -518,6 +523,10 @@ class McBase(CuWorker):
         # uploads (mc.py:840-884)
         self._upload_seeds(copy=False)
         counters = np.zeros(4, dtype=np.uint32)   # done, kernels, iterations (u64)
+        # (test hook: a throughput-mode launch that starts with the packet counter
+        # at S simulates the packets [S, nphotons) - exercises the top of the
+        # 32-bit counter range without simulating 4e9 packets)
+        counters[0] = self._packet_counter_start
         cbuf = self.cl_r_buffer(self._counters_name(), counters)
         self._upload_medium()
         if len(self._float_lut):

@@ -489,6 +489,38 @@ def test_runs_above_the_device_counter_are_batched_exactly():
         _det_sim('mcml_mhg_gauss_enhanced_rng')[0].run(2**33)
 
 
+@pytest.mark.parametrize('name', ['mcml_c1_slab', 'mcvox_gauss_fluence', 'mccyl_hg_line_fiz',
+                                  'mcvox_ubeam_radial'])
+def test_packet_counter_does_not_wrap_at_the_top_of_its_range(name):
+    """A throughput-mode launch of ``max_batch`` packets whose device counter
+    starts 20 000 below the budget: the claims of the last chunks (and the one
+    extra claim of every thread after exhaustion) must neither wrap the 32-bit
+    counter nor drop the tail chunk - the kernel ends, the counter stays above
+    the budget and exactly 20 000 packets are simulated (all-bin total within
+    5 sigma of a plain 20 000-packet run)."""
+    n = 20000
+    ref_sim, _, _ = build_sim(name)
+    top, _, _ = build_sim(name)
+    ref_sim.run(n, download=False)
+    a_ref = ref_sim.download_raw()[0].astype(np.float64)
+    top._packet_counter_start = top.max_batch - n
+    top.run(top.max_batch, download=False)
+    cnt = np.zeros(4, np.uint32)
+    top._cl_buffers[top._counters_name()].download(top._stream, cnt)
+    assert top.max_batch <= int(cnt[0]) <= 0xFFFFFFFF
+    assert int(cnt[0]) - top.max_batch <= top.run_report['launched_threads']*top.chunk_max
+    a_top = top.download_raw()[0].astype(np.float64)
+    K = 0x7FFFFF
+    owners = [d for d in (top.detectors or ())] + ([top.fluence] if top.fluence else [])
+    for owner in owners:
+        scale = float(owner.k) if owner is top.fluence else K
+        for al in top.cl_rw_accumulator_allocator.allocations(owner):
+            t_top = a_top[al.offset:al.offset + al.size].sum()/scale/n
+            t_ref = a_ref[al.offset:al.offset + al.size].sum()/scale/n
+            sigma = np.sqrt(max(t_ref, 1e-6)/n)*2
+            assert abs(t_top - t_ref) <= 5*sigma + 1e-5, (type(owner).__name__, t_top, t_ref)
+
+
 def test_device_side_grid_conversion_is_bit_identical():
     """Large fluence grids are converted to float64 on the device (AccuScale)
     instead of by ``update_data`` on the host: same IEEE operations, same bits;
