@@ -1044,3 +1044,32 @@ for _name, _fn in (('mcvox_lfiber_radial', mcvox_lfiber_radial),
     ALL_CASES[_name] = _fn
     GEOMETRY[_name] = 'mcvox'
     GOLDEN_RUN[_name] = (1500, 16)
+
+
+# ---- the bench configurations (benchcfg.py) at their real size -----------------
+# BASELINE.json's configs themselves under the oracle: C2's 5-entry stack with the
+# 250 x 500 FluenceRz grid, C3 at 201^3 (compact uint8 map / power-of-two strides /
+# 4 GB-window addressing of the CUDA path), C4's maxlen-512 trace, the C5 points.
+# (packets, work-items) of the golden run with the reference kernel:
+BENCH_RUN = {'c1_slab': (2000, 16), 'c2_skin': (3000, 16), 'c3_vox': (1000, 16),
+             'c4_trace': (96, 16), 'c5_cyl': (1000, 16), 'c5_slab': (1000, 16)}
+
+
+def bench_case(name):
+    """Case function ``f(mc, **kw) -> (sim, attrs)`` of bench configuration ``name``."""
+    import benchcfg
+
+    def make(mc, **kw):
+        return benchcfg.CONFIGS[name](mc, **kw), {}
+    return make
+
+
+def bench_geometry(name):
+    import benchcfg
+    return benchcfg.GEOMETRY[name]
+
+
+# ---- per-packet trajectories against the reference kernel -----------------------
+# packets = work-items (one packet per MWC stream) of tests/golden/traj_<case>.npz
+TRAJ_RUN = {'mcml_lut_iso_radialpl_trace': 512, 'mcvox_line_mhg_trace': 512,
+            'mccyl_gk_ubeam_fiz_trace': 512, 'c4_trace': 192}
