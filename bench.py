@@ -116,96 +116,103 @@ def cpu_reference_variant(config: str, pilot: int, threads: int):
     return refbench.fastest_variant(config, benchcfg.GEOMETRY[config], pilot, threads)[0]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--config', default='c2_skin', choices=sorted(benchcfg.CONFIGS))
-    ap.add_argument('--packets', type=float, default=None,
-                    help='packets per GPU per step (default 1.25e8 for c2_skin)')
-    ap.add_argument('--cpu-sample', type=float, default=None)
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--sweep', type=int, default=0,
-                    help='c5_slab only: configurations per step, run as a pipelined sweep')
-    args = ap.parse_args()
+METRIC_NAMES = {'c2_skin': 'mcml 5-layer skin', 'c3_vox': 'mcvox 201^3 fluence',
+                'validate_uniformfiber': "reference's validate.SingleLayerUniformFiberRadial "
+                                         'performance suite, 400 x 1e7 packets'}
+WORKLOADS = {
+    'c2_skin': 'mcml 5-layer skin (Skin3 @550nm), UniformFiber + SixAroundOne, '
+               'MHg(beta=0.9), FluenceRz 250x500',
+    'c1_slab': 'mcml single slab mua=1/cm mus=100/cm g=0.8 n=1.33, Line + Radial',
+    'c3_vox': 'mcvox 201^3 voxel 2-layer skin + blood vessel (5 um voxels), '
+              'GaussianBeam sigma 50 um, Fluence deposition grid',
+    'c4_trace': 'mcml slab, RadialPl 100x300 (path-length resolved) + Trace maxlen 512 of every '
+                'packet + device filter + sampling_volume 200^3 (e2e: the accepted rows feed '
+                'sampling_volume on the device; the host receives detectors, counts and the grid)',
+    'c4_trace_vox': 'mcvox 201^3 skin + vessel, Line source, Trace maxlen 512 of every packet + '
+                    'device filter + sampling_volume 200^3',
+    'c5_slab': 'mcml semi-infinite n=1.337 under air, (mua, musr) sweep point(s), g=0.8, '
+               'Line + Radial 500, rmax 25 mm',
+    'c5_cyl': 'mccyl single cylinder r=5 mm n=1.337 mua=1/cm mus=100/cm g=0.8, '
+              'Line + FiZ 64x100',
+    'validate_uniformfiber': 'mcml 8 mm layer n=1.33 Hg(0.85) under n=1.452, UniformFiberNI(200 um, '
+                             'NA 0.22) + Radial(RadialAxis 340 x 5 um, cosmin), rmax 5 mm; sweep of '
+                             '20 x 20 (mua, musr) points x 1e7 packets '
+                             '(xopto/mcml/test/validate.py:348-445, test/performance.py)',
+}
+DEFAULT_PACKETS = {'c2_skin': 1.25e8, 'c3_vox': 1e8, 'c4_trace': 1e6, 'c4_trace_vox': 2e5}
+TRACE_CONFIGS = ('c4_trace', 'c4_trace_vox')
 
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    ncores = os.cpu_count() or 1
-    config = args.config
-    metric = 'photon packets/s ({})'.format(
-        {'c2_skin': 'mcml 5-layer skin', 'c3_vox': 'mcvox 201^3 fluence'}.get(config, config))
-    workload = {
-        'c2_skin': 'mcml 5-layer skin (Skin3 @550nm), UniformFiber + SixAroundOne, '
-                   'MHg(beta=0.9), FluenceRz 250x500',
-        'c1_slab': 'mcml single slab mua=1/cm mus=100/cm g=0.8 n=1.33, Line + Radial',
-        'c3_vox': 'mcvox 201^3 voxel 2-layer skin + blood vessel (5 um voxels), '
-                  'GaussianBeam sigma 50 um, Fluence deposition grid',
-        'c4_trace': 'mcml slab, RadialPl 100x300 (path-length resolved) + Trace maxlen 512 of every '
-                    'packet + device filter + sampling_volume 200^3 (e2e: the accepted rows feed '
-                    'sampling_volume on the device; the host receives detectors, counts and the grid)',
-        'c5_slab': 'mcml semi-infinite n=1.337 under air, (mua, musr) sweep point(s), g=0.8, '
-                   'Line + Radial 500, rmax 25 mm',
-        'c5_cyl': 'mccyl single cylinder r=5 mm n=1.337 mua=1/cm mus=100/cm g=0.8, '
-                  'Line + FiZ 64x100',
-    }.get(config, config)
 
-    # ---------------- reference arm: the reference kernel on host cores --------
-    if args.impl == 'reference':
-        if rank != 0:
-            return 0
-        sample = int(args.cpu_sample or {'c2_skin': 3e5, 'c3_vox': 2e4, 'c4_trace': 2e4}.get(config, 5e4))
-        times = []
-        kind, flags = 'port', ''
-        variant = cpu_reference_variant(config, max(sample//4, 1000), ncores)
-        for i in range(args.warmup + args.steps):
-            pps, kind, secs, flags = cpu_reference_run(config, sample, ncores, variant)
-            if i >= args.warmup:
-                times.append(secs)
-        total = sum(times)
-        value = sample*len(times)/total
-        line = {
-            'impl': 'reference', 'metric': metric, 'value': value, 'unit': 'packets/s',
-            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3*total/len(times), 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload, 'packets_per_step': sample,
-                       'schedule': 'dynamic atomic packet counter, one work-item per host thread'},
-            'cpu_baseline': {'value': value, 'unit': 'packets/s', 'cores': ncores,
-                             'kind': kind, 'flags': flags,
-                             'sample': '{} packets per step, {} timed steps'.format(sample, len(times))},
-            'e2e': {'value': value, 'unit': 'packets/s', 'h2d_bytes_per_step': 0,
-                    'd2h_bytes_per_step': 0},
-            'gpu_launches': 0,
-        }
-        print(json.dumps(line))
-        return 0
+def atomic_peaks():
+    """Measured accumulator-path rates (tools/atomic_probe.cu run on a B200, output
+    committed as profiles/atomic_probe_r02.json): deposits/s of the shared-memory
+    lo/hi window (ATOMS) and of RED.E.ADD.64 into a 201^3 grid in L2 (uniform)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'atomic_probe_r02.json')) as f:
+            res = json.load(f)['results']
+        atoms = max(r['G_deposits_per_s'] for r in res
+                    if r['path'] == 'atoms_lohi' and r['bins'] >= 4096 and not r['peaked'])
+        red = max(r['G_deposits_per_s'] for r in res
+                  if r['path'] == 'redg64' and r['bins'] == 8120601 and not r['peaked'])
+        return atoms*1e9, red*1e9, 'profiles/atomic_probe_r02.json'
+    except (OSError, ValueError, KeyError):
+        return 1.2e12, 1.8e11, 'constants (probe output not found)'
 
-    # ---------------- native arm --------------------------------------------------
+
+def reference_arm(config, args, ncores):
+    sample = int(args.cpu_sample or {'c2_skin': 3e5, 'c3_vox': 2e4, 'c4_trace': 2e4,
+                                     'c4_trace_vox': 1e4}.get(config, 5e4))
+    times = []
+    kind, flags = 'port', ''
+    variant = cpu_reference_variant(config, max(sample//4, 1000), ncores)
+    for i in range(args.warmup + args.steps):
+        pps, kind, secs, flags = cpu_reference_run(config, sample, ncores, variant)
+        if i >= args.warmup:
+            times.append(secs)
+    total = sum(times)
+    value = sample*len(times)/total
+    return {
+        'impl': 'reference',
+        'metric': 'photon packets/s ({})'.format(METRIC_NAMES.get(config, config)),
+        'value': value, 'unit': 'packets/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3*total/len(times), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOADS.get(config, config), 'packets_per_step': sample,
+                   'schedule': 'dynamic atomic packet counter, one work-item per host thread',
+                   'inputs': 'structs / LUTs / seeds packed by the reference host layer '
+                             '(oracle/_ref/inputs_{}.npz)'.format(config)},
+        'cpu_baseline': {'value': value, 'unit': 'packets/s', 'cores': ncores,
+                         'kind': kind, 'flags': flags,
+                         'sample': '{} packets per step, {} timed steps'.format(sample, len(times))},
+        'e2e': {'value': value, 'unit': 'packets/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+
+
+def native_arm(config, args, env, cpu_baseline_wanted=True):
+    """One bench line (dict, rank 0; None elsewhere) of ``config``."""
     import importlib
-    dist = None
-    torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
     from pyxopto_b200.cu import abi
+    from pyxopto_b200 import parallel
+    rank, world, local_rank = env['rank'], env['world'], env['local_rank']
+    torch, dist = env.get('torch'), env.get('dist')
+    ncores = os.cpu_count() or 1
     geom = benchcfg.GEOMETRY[config]
     mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
-    packets = int(args.packets or {'c2_skin': 1.25e8, 'c3_vox': 1e8,
-                                   'c4_trace': 1e6}.get(config, 1e7))
-    from pyxopto_b200 import parallel as _par
-    sim = benchcfg.CONFIGS[config](mc, rnginit=_par.seed_for_rank(benchcfg.RNGINIT, rank),
+    packets = int(args.packets or DEFAULT_PACKETS.get(config, 1e7))
+    sim = benchcfg.CONFIGS[config](mc, rnginit=parallel.seed_for_rank(benchcfg.RNGINIT, rank),
                                    cl_devices=local_rank)
-
-    if world > 1:
-        from pyxopto_b200 import parallel
-        sim._reduce_hook = parallel.NcclAccumulatorReducer(local_rank)
+    n_sweep = int(args.sweep)
+    if config == 'validate_uniformfiber' and not n_sweep:
+        n_sweep = 400
+    reducer = None
+    if world > 1 and not n_sweep:
+        # packets sharded over the ranks: one all-reduce of the accumulators per step,
+        # stream-ordered on the engine's stream
+        reducer = parallel.NcclAccumulatorReducer(local_rank)
+        sim._reduce_hook = reducer
 
     def barrier():
         sim._stream.synchronize()
@@ -216,7 +223,10 @@ def main():
     # one step of the configuration, device-resident (`value`) and through the
     # public API with host results (`e2e`)
     sv_ms = []
-    if config == 'c4_trace':
+    launches_per_step = 1
+    if config in TRACE_CONFIGS:
+        launches_per_step = 5
+
         def step_device():
             sim.run(packets, download=False)
             rr = dict(sim.run_report)
@@ -229,13 +239,21 @@ def main():
             trace, fluence, detectors = sim.run(packets)
             sv = sim.sampling_volume(trace, benchcfg.c4_sampling_volume(mc))
             return detectors, fluence, float(sv.data.sum())
-    elif config == 'c5_slab' and args.sweep:
-        # config 5 as it is meant to be run: a pipelined sweep over (mua, musr)
+    elif n_sweep:
+        # a pipelined sweep over (mua, musr): configurations dealt round-robin to the
+        # ranks, no collective on the data path, one gather of the rows in e2e
         from pyxopto_b200 import mcsweep
-        grid_cfgs = benchcfg.c5_grid()
-        stride = max(len(grid_cfgs)//args.sweep, 1)
-        sweep_cfgs = grid_cfgs[::stride][:args.sweep]
-        sweep = mcsweep.Sweep(sim)
+        grid_cfgs = benchcfg.validate_grid() if config == 'validate_uniformfiber' \
+            else benchcfg.c5_grid()
+        total_cfgs = n_sweep*world
+        if total_cfgs >= len(grid_cfgs):
+            reps = (total_cfgs + len(grid_cfgs) - 1)//len(grid_cfgs)
+            sweep_cfgs = (grid_cfgs*reps)[:total_cfgs]
+        else:
+            stride = max(len(grid_cfgs)//total_cfgs, 1)
+            sweep_cfgs = grid_cfgs[::stride][:total_cfgs]
+        sweep = mcsweep.Sweep(sim, rank, world)
+        launches_per_step = n_sweep
         ev_a, ev_b = abi.Event(sim.cl_context), abi.Event(sim.cl_context)
 
         def step_device():
@@ -251,20 +269,29 @@ def main():
 
         def step_e2e():
             idx, rows = sweep.run(sweep_cfgs, packets)
-            refl = sweep.detector(rows, sim.detectors.top, packets)
-            return None, None, float(refl.sum())
+            if world > 1:
+                rows = sweep.gather(idx, rows, len(sweep_cfgs))
+            refl = sweep.detector(rows, sim.detectors.top if geom != 'mccyl'
+                                  else sim.detectors.outer, packets)
+            return None, None, float(np.sum(refl))
     else:
         def step_device():
             sim.run(packets, download=False)
             return sim.run_report
 
         def step_e2e():
-            trace, fluence, detectors = sim.run(packets)
+            if world > 1:
+                # the root rank receives the reduced results; the others only simulate
+                trace, fluence, detectors = parallel.run_sharded(
+                    sim, packets*world, rank, world, reducer=reducer, root=0)
+            else:
+                trace, fluence, detectors = sim.run(packets)
             return detectors, fluence, 0.0
 
     # warm-up (also builds/loads the kernel)
     for _ in range(max(args.warmup, 1)):
         step_device()
+    step_e2e()
     barrier()
 
     # ---- device-resident loop: `value` -------------------------------------------
@@ -290,7 +317,7 @@ def main():
     # ---- end-to-end loop through the public API: `e2e` ----------------------------
     barrier()
     t2 = time.perf_counter()
-    h2d = d2h = 0
+    checksum = 0.0
     for _ in range(args.steps):
         detectors, fluence, extra = step_e2e()
         checksum = sum(float(d.raw.sum()) for d in (detectors or ()) if hasattr(d, 'raw')) + \
@@ -302,7 +329,9 @@ def main():
     P = sim._packed
     h2d = sum(len(cltypes.raw_bytes(P[k])) for k in P if P[k] is not None) + 16
     d2h = int(sim.cl_rw_accumulator_allocator.size)*8 + 16
-    if config == 'c4_trace':
+    if n_sweep:
+        h2d, d2h = h2d*n_sweep, d2h*n_sweep
+    if config in TRACE_CONFIGS:
         # accepted trace rows + their counts, then the sampling-volume grid
         d2h += int(sim.run_report.get('filter_accepted', 0))*(32*int(sim.trace.maxlen) + 4)
 
@@ -311,128 +340,194 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         loop_s, e2e_s, loop_ms_events = [float(v) for v in t.tolist()]
 
-    per_step = packets*(args.sweep if (config == 'c5_slab' and args.sweep) else 1)
+    per_step = packets*max(n_sweep, 1)
     total_packets = per_step*world*args.steps
     value = total_packets/loop_s
     e2e_value = total_packets/e2e_s
+    if rank != 0:
+        return None
 
-    if rank == 0:
-        peaks, peaks_src = measured_peaks()
-        sm_mhz_max = float(peaks.get('sm_max_mhz', 1965.0))
-        info = sim.cl_context.info
-        sms = info['multiprocessor_count']
-        issue_peak = sms*FP32_LANES_PER_SM*sm_mhz_max*1e6     # thread-instr/s
-        sfu_peak = sms*SFU_LANES_PER_SM*sm_mhz_max*1e6
-        alu_ops, sfu_ops = benchcfg.OPS_PER_ITERATION[config]
-        k_ms = float(np.mean(kernel_ms))
-        iter_per_launch = float(np.mean(iters))
-        achieved = iter_per_launch*(alu_ops + sfu_ops)/(k_ms*1e-3)
-        achieved_sfu = iter_per_launch*sfu_ops/(k_ms*1e-3)
-        # DRAM bytes of the kernel from the committed ncu capture (per launch, at the
-        # capture's launch size; the working set of this path lives in L2)
-        traffic, traffic_note = None, None
+    peaks, peaks_src = measured_peaks()
+    sm_mhz_max = float(peaks.get('sm_max_mhz', 1965.0))
+    info = sim.cl_context.info
+    sms = info['multiprocessor_count']
+    issue_peak = sms*FP32_LANES_PER_SM*sm_mhz_max*1e6     # thread-instr/s
+    sfu_peak = sms*SFU_LANES_PER_SM*sm_mhz_max*1e6
+    alu_ops, sfu_ops = benchcfg.OPS_PER_ITERATION[config]
+    k_ms = float(np.mean(kernel_ms))
+    iter_per_launch = float(np.mean(iters))
+    achieved = iter_per_launch*(alu_ops + sfu_ops)/(k_ms*1e-3)
+    achieved_sfu = iter_per_launch*sfu_ops/(k_ms*1e-3)
+    # DRAM bytes of the kernel from the committed ncu capture (per launch, at the
+    # capture's launch size; the working set of this path lives in L2)
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            tr = json.load(f).get(config)
+        if tr:
+            traffic = tr['dram_bytes']
+            traffic_note = 'dram read+write bytes of one McKernel launch of {:.0e} packets ' \
+                           '({})'.format(tr['launch_packets'], tr['capture'])
+    except (OSError, ValueError, KeyError):
+        pass
+    atoms_peak, red_peak, atomic_src = atomic_peaks()
+    dep_rate = iter_per_launch/(k_ms*1e-3)
+    roofline = {
+        'bound': 'issue', 'achieved': achieved/1e9, 'peak': issue_peak/1e9,
+        'unit': 'G thread-instr/s', 'frac': achieved/issue_peak,
+        'traffic': traffic, 'traffic_note': traffic_note,
+        'kernel': 'McKernel', 'kernel_ms': k_ms,
+        'iterations_per_launch': iter_per_launch,
+        'iterations_per_packet': iter_per_launch/per_step,
+        'algorithmic_ops_per_iteration': {'alu_fma': alu_ops, 'mufu': sfu_ops},
+        'sfu': {'achieved': achieved_sfu/1e9, 'peak': sfu_peak/1e9,
+                'frac': achieved_sfu/sfu_peak},
+        # accumulator ("atomic") roofline, SURVEY 8d: deposits per second against
+        # the rates measured with tools/atomic_probe.cu on B200; deposits per
+        # iteration = 1 (C2, AW) / 0.15 (C3, oracle statistics)
+        'atomic': ({'achieved': dep_rate, 'peak': atoms_peak, 'frac': dep_rate/atoms_peak,
+                    'unit': 'deposits/s', 'peak_source': atomic_src,
+                    'path': 'shared-memory window (ATOMS lo/hi), 2.5 % RED.E.ADD.64'}
+                   if config == 'c2_skin' else
+                   {'achieved': 0.15*dep_rate, 'peak': red_peak, 'frac': 0.15*dep_rate/red_peak,
+                    'unit': 'deposits/s', 'peak_source': atomic_src,
+                    'path': 'RED.E.ADD.64 to L2'}
+                   if config == 'c3_vox' else None),
+        'peak_source': 'sm_max_mhz of MEASURED_PEAKS.json ({}) x {} SMs x {} FP32 lanes; '
+                       'hbm is not the bound of this path (working set < 2 MB / L2-resident)'.format(
+                           peaks_src, sms, FP32_LANES_PER_SM),
+        'kernel_share_of_step': k_ms*args.steps/(loop_ms_events if loop_ms_events > 0 else 1),
+    }
+    if config in TRACE_CONFIGS:
+        # the trace stream binds this configuration: one 32 B event record per
+        # loop iteration, written once
+        hbm_peak = float(peaks.get('hbm_gbs', peaks.get('hbm_gbps', 6650.0)))
+        bytes_per_launch = iter_per_launch*benchcfg.TRACE_BYTES_PER_ITERATION
+        roofline.update({
+            'bound': 'hbm', 'achieved': bytes_per_launch/(k_ms*1e-3)/1e9,
+            'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': bytes_per_launch/(k_ms*1e-3)/1e9/hbm_peak,
+            'algorithmic_bytes_per_iteration': benchcfg.TRACE_BYTES_PER_ITERATION,
+            'issue': {'achieved': achieved/1e9, 'peak': issue_peak/1e9,
+                      'frac': achieved/issue_peak},
+            'filter_plus_sampling_volume_ms': float(np.mean(sv_ms)) if sv_ms else None,
+            'peak_source': 'hbm_gbs of MEASURED_PEAKS.json ({})'.format(peaks_src),
+        })
+    cpu_baseline = None
+    if cpu_baseline_wanted and not args.no_cpu_baseline and world == 1:
         try:
-            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
-                tr = json.load(f).get(config)
-            if tr:
-                traffic = tr['dram_bytes']
-                traffic_note = 'dram read+write bytes of one McKernel launch of {:.0e} packets ' \
-                               '({})'.format(tr['launch_packets'], tr['capture'])
-        except (OSError, ValueError, KeyError):
-            pass
-        roofline = {
-            'bound': 'issue', 'achieved': achieved/1e9, 'peak': issue_peak/1e9,
-            'unit': 'G thread-instr/s', 'frac': achieved/issue_peak,
-            'traffic': traffic, 'traffic_note': traffic_note,
-            'kernel': 'McKernel', 'kernel_ms': k_ms,
-            'iterations_per_launch': iter_per_launch,
-            'iterations_per_packet': iter_per_launch/per_step,
-            'algorithmic_ops_per_iteration': {'alu_fma': alu_ops, 'mufu': sfu_ops},
-            'sfu': {'achieved': achieved_sfu/1e9, 'peak': sfu_peak/1e9,
-                    'frac': achieved_sfu/sfu_peak},
-            'atomics_per_s': (iter_per_launch/(k_ms*1e-3) if config == 'c2_skin' else None),
-            # accumulator ("atomic") roofline, SURVEY 8d: deposits per second against
-            # the rate measured with tools/atomic_probe.cu on B200 (shared-memory
-            # window of C2: > 1.2e12 /s; RED.E.ADD.64 to a 65 MB grid in L2, uniform:
-            # 1.8e11 /s); deposits per iteration = 1 (C2, AW) / 0.15 (C3, oracle statistics)
-            'atomic': ({'achieved': iter_per_launch/(k_ms*1e-3), 'peak': 1.2e12,
-                        'frac': iter_per_launch/(k_ms*1e-3)/1.2e12,
-                        'unit': 'deposits/s', 'path': 'shared-memory window (ATOMS lo/hi), 2.5 % RED.E.ADD.64'}
-                       if config == 'c2_skin' else
-                       {'achieved': 0.15*iter_per_launch/(k_ms*1e-3), 'peak': 1.8e11,
-                        'frac': 0.15*iter_per_launch/(k_ms*1e-3)/1.8e11,
-                        'unit': 'deposits/s', 'path': 'RED.E.ADD.64 to L2'}
-                       if config == 'c3_vox' else None),
-            'peak_source': 'sm_max_mhz of MEASURED_PEAKS.json ({}) x {} SMs x {} FP32 lanes; '
-                           'hbm is not the bound of this path (working set < 2 MB)'.format(
-                               peaks_src, sms, FP32_LANES_PER_SM),
-            'kernel_share_of_step': k_ms*args.steps/(loop_ms_events if loop_ms_events > 0 else 1),
-        }
-        if config == 'c4_trace':
-            # the trace stream binds this configuration: one 32 B event record per
-            # loop iteration, written once
-            hbm_peak = float(peaks.get('hbm_gbs', peaks.get('hbm_gbps', 6650.0)))
-            bytes_per_launch = iter_per_launch*benchcfg.TRACE_BYTES_PER_ITERATION
-            roofline.update({
-                'bound': 'hbm', 'achieved': bytes_per_launch/(k_ms*1e-3)/1e9,
-                'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': bytes_per_launch/(k_ms*1e-3)/1e9/hbm_peak,
-                'algorithmic_bytes_per_iteration': benchcfg.TRACE_BYTES_PER_ITERATION,
-                'issue': {'achieved': achieved/1e9, 'peak': issue_peak/1e9,
-                          'frac': achieved/issue_peak},
-                'filter_plus_sampling_volume_ms': float(np.mean(sv_ms)) if sv_ms else None,
-                'peak_source': 'hbm_gbs of MEASURED_PEAKS.json ({})'.format(peaks_src),
-            })
-        cpu_baseline = None
-        if not args.no_cpu_baseline and world == 1:
-            try:
-                variant = None
-                if args.cpu_sample:
-                    sample = int(args.cpu_sample)
-                else:
-                    # pilot run, then a sample sized for ~12 s of CPU work
-                    pilot = int({'c4_trace': 5e3}.get(config, 5e4))
-                    variant = cpu_reference_variant(config, pilot, ncores)
-                    pps0 = cpu_reference_run(config, pilot, ncores, variant)[0]
-                    sample = int(min(max(pps0*12.0, pilot), 2e8 if config != 'c4_trace' else 1e5))
-                pps, kind, secs, flags = cpu_reference_run(config, sample, ncores, variant)
-                cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
-                                'kind': kind, 'flags': flags,
-                                'sample': '{} packets of the same workload in {:.1f} s'.format(
-                                    sample, secs)}
-            except Exception as exc:    # the baseline must never take the bench down
-                cpu_baseline = {'value': None, 'unit': 'packets/s', 'cores': ncores,
-                                'kind': 'port', 'sample': 'failed: {!r}'.format(exc)}
-        rr = sim.run_report
-        line = {
-            'metric': metric, 'value': value, 'unit': 'packets/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3*loop_s/args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {
-                'workload': workload, 'packets_per_gpu_per_step': per_step,
-                'global_packets_per_step': per_step*world,
-                'sweep_configs_per_step': args.sweep or None,
-                'parallelism': 'packets sharded over {} GPU(s), disjoint MWC seed sets'
-                               '{}'.format(world, ', 1 NCCL all-reduce of the uint64 '
-                                           'accumulators per step' if world > 1 else ''),
-                'mode': 'throughput (MUFU math, dynamic chunked packet counter)',
-                'l2': 'inputs are < 2 MB of constants; every step re-zeroes and rewrites '
-                      'the accumulator grid, no cached outputs are reused',
-                'grid': rr['grid'], 'block': rr['block'],
-                'registers': rr.get('kernel_attributes', {}).get('num_regs'),
-            },
-            'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'packets/s', 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3*e2e_s/args.steps,
-                    'checksum': checksum},
-            'gpu_launches': args.steps*(5 if config == 'c4_trace' else max(args.sweep, 1)),
-            'roofline': roofline,
-            'cpu_baseline': cpu_baseline,
-        }
+            variant = None
+            if args.cpu_sample:
+                sample = int(args.cpu_sample)
+            else:
+                # pilot run, then a sample sized for ~12 s of CPU work
+                pilot = int(5e3 if config in TRACE_CONFIGS else 5e4)
+                variant = cpu_reference_variant(config, pilot, ncores)
+                pps0 = cpu_reference_run(config, pilot, ncores, variant)[0]
+                sample = int(min(max(pps0*12.0, pilot), 1e5 if config in TRACE_CONFIGS else 2e8))
+            pps, kind, secs, flags = cpu_reference_run(config, sample, ncores, variant)
+            cpu_baseline = {'value': pps, 'unit': 'packets/s', 'cores': ncores,
+                            'kind': kind, 'flags': flags,
+                            'sample': '{} packets of the same workload in {:.1f} s'.format(
+                                sample, secs)}
+        except Exception as exc:    # the baseline must never take the bench down
+            cpu_baseline = {'value': None, 'unit': 'packets/s', 'cores': ncores,
+                            'kind': 'port', 'sample': 'failed: {!r}'.format(exc)}
+    rr = sim.run_report
+    vs_baseline = None
+    if config == 'validate_uniformfiber' and n_sweep == 400 and packets == 10**7:
+        # the one number the reference publishes for this path: 400 x 1e7 packets in
+        # 5.7 s on an RTX A6000 (test/performance.py:134-135) - end to end
+        vs_baseline = e2e_value/world/benchcfg.VALIDATE_PUBLISHED_PACKETS_PER_S
+    line = {
+        'metric': 'photon packets/s ({})'.format(METRIC_NAMES.get(config, config)),
+        'value': value, 'unit': 'packets/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3*loop_s/args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': vs_baseline, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {
+            'workload': WORKLOADS.get(config, config), 'packets_per_gpu_per_step': per_step,
+            'global_packets_per_step': per_step*world,
+            'sweep_configs_per_gpu_per_step': n_sweep or None,
+            'parallelism': ('{} configurations per GPU dealt round-robin over {} GPU(s), no '
+                            'collective on the data path'.format(n_sweep, world) if n_sweep else
+                            'packets sharded over {} GPU(s), disjoint MWC seed sets{}'.format(
+                                world, ', 1 stream-ordered NCCL all-reduce of the uint64 '
+                                'accumulators per step' if world > 1 else '')),
+            'mode': 'throughput (MUFU math, dynamic chunked packet counter)',
+            'l2': 'inputs are < 2 MB of constants; every step re-zeroes and rewrites '
+                  'the accumulator grid, no cached outputs are reused',
+            'grid': rr['grid'], 'block': rr['block'],
+            'registers': rr.get('kernel_attributes', {}).get('num_regs'),
+        },
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'packets/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3*e2e_s/args.steps,
+                'checksum': checksum,
+                'results_on': 'rank 0 (NCCL-reduced accumulators)' if world > 1 else 'host'},
+        'gpu_launches': args.steps*launches_per_step,
+        'roofline': roofline,
+        'cpu_baseline': cpu_baseline,
+    }
+    if config == 'validate_uniformfiber':
+        line['suite_seconds'] = {'device': loop_s/args.steps, 'e2e': e2e_s/args.steps,
+                                 'published_rtx_a6000': benchcfg.VALIDATE_PUBLISHED_SECONDS}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--config', default=None, choices=sorted(benchcfg.CONFIGS))
+    ap.add_argument('--packets', type=float, default=None,
+                    help='packets per GPU per step (default 1.25e8 for c2_skin)')
+    ap.add_argument('--cpu-sample', type=float, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='default run only: skip the mcvox 201^3 block')
+    ap.add_argument('--sweep', type=int, default=0,
+                    help='c5_slab / c5_cyl / validate_uniformfiber: configurations per GPU '
+                         'per step, run as a pipelined sweep')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    ncores = os.cpu_count() or 1
+    # BASELINE.json's metric names two workloads: "mcml skin, mcvox 201^3 fluence".
+    # Without --config the line is the mcml skin measurement and carries the mcvox
+    # one, measured the same way in the same run, as `secondary`.
+    default_run = args.config is None
+    config = args.config or 'c2_skin'
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        line = reference_arm(config, args, ncores)
+        if default_run and not args.no_secondary:
+            line['secondary'] = reference_arm('c3_vox', args, ncores)
+        print(json.dumps(line))
+        return 0
+
+    env = {'rank': rank, 'world': world, 'local_rank': local_rank}
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        env.update(torch=torch, dist=dist)
+    line = native_arm(config, args, env)
+    if default_run and not args.no_secondary:
+        second = native_arm('c3_vox', args, env)
+        if line is not None:
+            line['secondary'] = second
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        env['dist'].destroy_process_group()
     return 0
 
 

@@ -202,3 +202,54 @@ CONFIGS['c5_slab'] = c5_slab
 GEOMETRY['c5_slab'] = 'mcml'
 PACKETS['c5_slab'] = 10**7
 OPS_PER_ITERATION['c5_slab'] = (85, 11)
+
+
+# ---- the reference's own acceptance / performance workload ----------------------
+# xopto/mcml/test/validate.py:348-445 (SingleLayerUniformFiberRadial) is the workload
+# behind every number printed by test/performance.py:116-162: one 8 mm layer (n 1.33,
+# Hg g 0.85) under a fiber-glass half-space (n 1.452), UniformFiberNI(200 um, NA 0.22),
+# Radial(RadialAxis(0, 1.7 mm, 340), cosmin = cos(asin(NA/ncore))), rmax 5 mm, and a
+# 20 x 20 grid mua in linspace(1, 2500, 20) 1/m x musr in linspace(500, 6000, 20) 1/m
+# with 1e7 packets each.  Parameters are the ones stored in the reference's
+# test/reference/cuda_singlelayer_uniformfiber.pkl (tests/golden/validate_vectors.npz).
+VALIDATE_G = 0.85
+VALIDATE_NCORE = 1.452
+VALIDATE_NA = 0.22
+
+
+def validate_uniformfiber(mc, rnginit=RNGINIT, mua=1.0, musr=500.0, **kw):
+    L = mc.mclayer.Layer
+    g = VALIDATE_G
+    layers = mc.mclayer.Layers([
+        L(d=float('inf'), n=VALIDATE_NCORE, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(g)),
+        L(d=8e-3, n=1.33, mua=mua, mus=musr/(1.0 - g), pf=mc.mcpf.Hg(g)),
+        L(d=float('inf'), n=1.33, mua=0.0, mus=0.0, pf=mc.mcpf.Hg(g))])
+    if mc.__name__.startswith('xopto'):
+        from xopto.mcml.mcutil import fiber as fiberutil
+        fib = fiberutil.MultimodeFiber(200e-6, 200e-6, VALIDATE_NCORE, VALIDATE_NA)
+    else:
+        fib = mc.mcsource.MultimodeFiber(200e-6, 200e-6, VALIDATE_NCORE, VALIDATE_NA)
+    cosmin = float(np.cos(np.arcsin(VALIDATE_NA/VALIDATE_NCORE)))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(
+        mc.mcdetector.RadialAxis(0.0, 1.7e-3, 340), cosmin=cosmin))
+    sim = mc.Mc(layers, mc.mcsource.UniformFiberNI(fib), det, rnginit=rnginit, **kw)
+    sim.rmax = 5e-3
+    return sim
+
+
+def validate_grid(n_mua=20, n_musr=20, g=VALIDATE_G, layer=1):
+    """The 400 (mua, musr) points of the acceptance suite as Sweep descriptors
+    (mua-major, musr fastest: np.meshgrid(..., indexing='ij') of validate.py:413)."""
+    return [{layer: {'mua': float(mua), 'mus': float(musr/(1.0 - g))}}
+            for mua in np.linspace(1.0, 2500.0, n_mua)
+            for musr in np.linspace(500.0, 6000.0, n_musr)]
+
+
+CONFIGS['validate_uniformfiber'] = validate_uniformfiber
+GEOMETRY['validate_uniformfiber'] = 'mcml'
+PACKETS['validate_uniformfiber'] = 10**7
+OPS_PER_ITERATION['validate_uniformfiber'] = (85, 11)
+# published by the reference for exactly this workload (test/performance.py:134-135):
+# 400 x 1e7 packets in 5.7 s on an NVIDIA RTX A6000 (OpenCL)
+VALIDATE_PUBLISHED_SECONDS = 5.7
+VALIDATE_PUBLISHED_PACKETS_PER_S = 400*1e7/5.7
