@@ -17,3 +17,16 @@ DATA_PATH = os.path.join(ROOT_PATH, 'data')
 KERNEL_CACHE_PATH = os.environ.get(
     'PYXOPTO_B200_KCACHE', os.path.join(ROOT_PATH, '_kcache'))
 VERBOSE = bool(int(os.environ.get('PYXOPTO_VERBOSE', '0')))
+
+# user directories of the reference (xopto/__init__.py:58-140): scripts write
+# exported kernel sources / temporary files there
+USER_PATH = os.environ.get('PYXOPTO_USER_PATH', os.path.join(os.path.expanduser('~'), '.xopto'))
+USER_DATA_PATH = os.path.join(USER_PATH, 'data')
+USER_BIN_PATH = os.path.join(USER_PATH, 'bin')
+USER_TMP_PATH = os.path.join(USER_PATH, 'tmp')
+
+
+def make_user_dirs():
+    """Creates the user directories (xopto/__init__.py:128)."""
+    for path in (USER_DATA_PATH, USER_BIN_PATH, USER_TMP_PATH):
+        os.makedirs(path, exist_ok=True)

@@ -1,2 +1,21 @@
 """Voxelised Monte Carlo simulator - mirror of ``xopto.mcvox``."""
 from . import mc  # noqa: F401
+
+
+# ---- the reference's subpackage layout -------------------------------------------
+# xopto.mcvox exposes its plugin families as subpackages (xopto.mcvox.mcoptions,
+# .mcpf, .mcfluence, .mctrace, .mcutil.fiber ...).  The same import statements work
+# here: the shared modules of pyxopto_b200.mcbase / pyxopto_b200.cl are registered
+# under this package's name.
+import sys as _sys
+from ..cl import clinfo, clrng, cltypes                      # noqa: E402,F401
+from ..mcbase import (mcobject, mcoptions, mctypes, mcpf, mcfluence, mctrace,  # noqa: E402,F401
+                      mcsv, mcprogress, mcmaterial, mcutil)
+from ..mcml import mcdetector                              # noqa: E402,F401
+import importlib as _importlib                                 # noqa: E402
+mcoptions = _importlib.import_module(__name__ + '.mcoptions')  # shared options + McMaterialMemory
+for _name in ('clinfo', 'clrng', 'cltypes', 'mcobject', 'mcoptions', 'mctypes', 'mcpf', 'mcfluence', 'mctrace', 'mcsv', 'mcprogress', 'mcmaterial', 'mcutil', 'mcdetector'):
+    _sys.modules.setdefault(__name__ + '.' + _name, globals()[_name])
+for _name in ('axis', 'boundary', 'buffer', 'fiber', 'geometry', 'lut'):
+    _sys.modules.setdefault(__name__ + '.mcutil.' + _name, getattr(mcutil, _name))
+del _name

@@ -12,7 +12,8 @@ import ctypes
 import numpy as np
 
 from ..cl import clinfo, clrng, cltypes            # noqa: F401
-from ..mcbase import mcoptions, mctypes, mcobject  # noqa: F401
+from ..mcbase import mctypes, mcobject             # noqa: F401
+from . import mcoptions                            # noqa: F401  (shared + McMaterialMemory)
 from ..mcbase import mcsv, mcprogress                         # noqa: F401
 from ..mcbase import mcpf, mcfluence, mctrace, mcmaterial  # noqa: F401
 from ..mcbase.mcobject import McObject             # noqa: F401
