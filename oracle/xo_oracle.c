@@ -53,6 +53,12 @@ typedef struct {
 	float thickness, top, bottom, n, cc_top, cc_bottom, mus, mua, inv_mut, mua_inv_mut;
 	/* McPf follows */
 } ml_layer;
+/* mcml/mclayer/layer.py:412-424 (AnisotropicLayer): same head, tensors instead of
+ * the scalar coefficients */
+typedef struct {
+	float thickness, top, bottom, n, cc_top, cc_bottom;
+	m3f mus, mua, mut;
+} ml_aniso_layer;
 /* mccyl/mclayer/layer.py:119-130 */
 typedef struct {
 	float r_inner, r_outer, n, cc_inner, cc_outer, mus, mua, inv_mut, mua_inv_mut;
@@ -318,7 +324,8 @@ static void scatter_direction(const sim_t *s, p3f *dir, float cos_theta, float f
 /* ---- layer / material access --------------------------------------------- */
 static inline size_t layer_stride(const xo_oracle_job *j) {
 	switch (j->geometry) {
-		case XO_GEOM_MCML: return sizeof(ml_layer) + (size_t)j->pf_size;
+		case XO_GEOM_MCML: return (j->anisotropic ? sizeof(ml_aniso_layer) : sizeof(ml_layer)) +
+			(size_t)j->pf_size;
 		case XO_GEOM_MCCYL: return sizeof(cyl_layer) + (size_t)j->pf_size;
 		default: return sizeof(vox_material) + (size_t)j->pf_size;
 	}
@@ -356,6 +363,33 @@ static inline void medium_props(const sim_t *s, float *mus, float *mua,
 		default: { const vox_material *l = vox_material_at(j, s->layer_index);
 			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
 	}
+}
+
+/* mcbase.template.h:2227-2230 tensor3f_project: p T p' */
+static inline float tensor_project(const m3f *T, const p3f *p) {
+	return p->x*(T->a11*p->x + T->a12*p->y + T->a13*p->z) +
+		p->y*(T->a21*p->x + T->a22*p->y + T->a23*p->z) +
+		p->z*(T->a31*p->x + T->a32*p->y + T->a33*p->z);
+}
+/* optical properties of an mcml layer along the propagation direction:
+ * mclayer/layer.py:153-216 (Layer: packed scalars) and :497-551 (AnisotropicLayer:
+ * projected tensors, mc_layer_inv_mut / mc_layer_mua_inv_mut) */
+static inline float ml_mus(const sim_t *s, const ml_layer *L) {
+	return s->job->anisotropic ? tensor_project(&((const ml_aniso_layer *)L)->mus, &s->dir) : L->mus;
+}
+static inline float ml_mua(const sim_t *s, const ml_layer *L) {
+	return s->job->anisotropic ? tensor_project(&((const ml_aniso_layer *)L)->mua, &s->dir) : L->mua;
+}
+static inline float ml_inv_mut(const sim_t *s, const ml_layer *L) {
+	if (!s->job->anisotropic) return L->inv_mut;
+	float mut = tensor_project(&((const ml_aniso_layer *)L)->mut, &s->dir);
+	return (mut != FP_0) ? m_div(FP_1, mut) : INFINITY;
+}
+static inline float ml_mua_inv_mut(const sim_t *s, const ml_layer *L) {
+	if (!s->job->anisotropic) return L->mua_inv_mut;
+	float mua = tensor_project(&((const ml_aniso_layer *)L)->mua, &s->dir);
+	float mut = tensor_project(&((const ml_aniso_layer *)L)->mut, &s->dir);
+	return (mua != FP_0) ? ((mut != FP_0) ? m_div(mua, mut) : INFINITY) : FP_0;
 }
 
 /* ---- phase functions ------------------------------------------------------- */
@@ -1556,9 +1590,9 @@ static void workitem_mcml(sim_t *s, quota_t *q) {
 		const ml_layer *L = ml_layer_at(j, s->layer_index);
 		s->iterations++;
 		if (j->method == XO_METHOD_MBL)
-			step = m_div(-m_log(s, sim_random(s)), L->mus);
+			step = m_div(-m_log(s, sim_random(s)), ml_mus(s, L));
 		else
-			step = -m_log(s, sim_random(s))*L->inv_mut;
+			step = -m_log(s, sim_random(s))*ml_inv_mut(s, L);
 		step = fminf(step, FLT_MAX);
 		next_index = s->layer_index;
 		if (s->pos.z + step*s->dir.z < L->top) {
@@ -1577,7 +1611,7 @@ static void workitem_mcml(sim_t *s, quota_t *q) {
 		if (s->layer_index > next_index) s->pos.z = L->top;
 
 		if (j->method == XO_METHOD_MBL) {              /* mcml.template.c:584-666 */
-			float mua = L->mua;
+			float mua = ml_mua(s, L);
 			float deposit_fraction = FP_1 - m_exp(s, -mua*step);
 			deposit = deposit_fraction*s->weight;
 			s->weight -= deposit;
@@ -1587,7 +1621,7 @@ static void workitem_mcml(sim_t *s, quota_t *q) {
 					step - m_div(-m_log(s, FP_1 - sim_random(s)*deposit_fraction), mua) : FP_0;
 				p3f dp = { s->pos.x - step_back*s->dir.x, s->pos.y - step_back*s->dir.y,
 					s->pos.z - step_back*s->dir.z };
-				fluence_deposit_weight(s, &dp, deposit, L->mua);
+				fluence_deposit_weight(s, &dp, deposit, mua);
 			}
 		}
 
@@ -1610,21 +1644,21 @@ static void workitem_mcml(sim_t *s, quota_t *q) {
 			lottery(s, &done);
 		} else if (j->method == XO_METHOD_AR) {        /* mcml.template.c:705-721 */
 			L = ml_layer_at(j, s->layer_index);
-			if (sim_random(s) < L->mua_inv_mut) {
+			if (sim_random(s) < ml_mua_inv_mut(s, L)) {
 				deposit = s->weight;
 				done = 1;
 				s->weight -= deposit;
 				s->event_flags |= EV_ABSORPTION;
-				fluence_deposit_weight(s, &s->pos, deposit, L->mua);
+				fluence_deposit_weight(s, &s->pos, deposit, ml_mua(s, L));
 			} else {
 				sim_scatter(s);
 				s->event_flags |= EV_SCATTERING;
 			}
 		} else {                                       /* AW, mcml.template.c:722-754 */
-			deposit = s->weight*L->mua_inv_mut;
+			deposit = s->weight*ml_mua_inv_mut(s, L);
 			s->weight -= deposit;
 			s->event_flags |= EV_ABSORPTION;
-			fluence_deposit_weight(s, &s->pos, deposit, L->mua);
+			fluence_deposit_weight(s, &s->pos, deposit, ml_mua(s, L));
 			sim_scatter(s);
 			s->event_flags |= EV_SCATTERING;
 			lottery(s, &done);

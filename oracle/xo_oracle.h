@@ -67,6 +67,7 @@ typedef struct xo_oracle_job {
 	int32_t surf_offset[2];    /* byte offsets inside the packed McSurfaceLayouts */
 	int32_t surf_param[2];     /* compile-time parameter of the layout text (fiber count) */
 	int32_t enhanced_rng;      /* MC_USE_ENHANCED_RNG: two MWC steps per draw (mcbase.template.c:1577-1586) */
+	int32_t anisotropic;       /* layers / materials carry mus, mua, mut tensors (AnisotropicLayer / AnisotropicMaterial) */
 
 	/* run-time kernel arguments (mcml.template.c:346-376, mcvox.template.c:548) */
 	uint32_t num_packets;

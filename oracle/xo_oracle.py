@@ -58,6 +58,7 @@ class Job(ctypes.Structure):
         ('track_opl', ctypes.c_int32),
         ('surf_kind', ctypes.c_int32*2), ('surf_offset', ctypes.c_int32*2),
         ('surf_param', ctypes.c_int32*2), ('enhanced_rng', ctypes.c_int32),
+        ('anisotropic', ctypes.c_int32),
         ('num_packets', ctypes.c_uint32), ('num_threads', ctypes.c_uint32),
         ('rmax', ctypes.c_float), ('num_layers', ctypes.c_uint32),
         ('layers', ctypes.c_void_p), ('voxel_cfg', ctypes.c_void_p),
@@ -174,7 +175,8 @@ def describe(mc_obj, geometry: str) -> dict:
         pf = media[1].pf
         layers_key, n_media = 'layers', len(media)
     pf_type = pf.fetch_cl_type(mc_obj) if hasattr(pf, 'fetch_cl_type') else pf.cl_type(mc_obj)
-    d = dict(geometry=geometry, pf_kind=PF_KIND[_name(pf)],
+    aniso = int(_name(media[1 if geometry != 'mcvox' else 0]).startswith('Anisotropic'))
+    d = dict(anisotropic=aniso, geometry=geometry, pf_kind=PF_KIND[_name(pf)],
              pf_size=ctypes.sizeof(pf_type), num_layers=n_media,
              layers=_raw(P[layers_key]), source=_raw(P['source']),
              src_kind=SRC_KIND[_name(mc_obj.source)])
@@ -270,6 +272,7 @@ def run(desc: dict, nphotons: int, nthreads: int, rng_x: np.ndarray,
     job.use_events = desc.get('use_events', 0)
     job.track_opl = desc.get('track_opl', 0)
     job.enhanced_rng = int(desc.get('enhanced_rng', 0))
+    job.anisotropic = int(desc.get('anisotropic', 0))
     job.num_packets = int(nphotons)
     job.num_threads = int(nthreads)
     job.rmax = np.float32(desc['rmax'])

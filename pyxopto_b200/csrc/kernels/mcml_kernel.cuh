@@ -51,6 +51,9 @@
 #ifndef XO_USE_RMAX
 #define XO_USE_RMAX 1
 #endif
+#ifndef XO_DEPOSIT_MAGIC
+#define XO_DEPOSIT_MAGIC 0
+#endif
 
 namespace xo {
 
@@ -77,16 +80,6 @@ typedef TraceCfg XoTrace;
 #else
 typedef TraceNone XoTrace;
 #endif
-
-// Throughput mode with a full trace (one 32-byte event per loop trip and lane):
-// events are staged per lane in shared memory and leave as whole 128-byte lines
-// (4 events), 8 lanes per line -- written directly, every STG.128 of a warp
-// touches 32 different 16 KB-strided rows (32 LSU wavefronts per instruction,
-// measured 1.9 TB/s of the 6.5 TB/s the trace stream could use).
-#ifndef XO_TRACE_STAGED
-#define XO_TRACE_STAGED 0
-#endif
-#define XO_STAGE_F4_PER_WARP 264        // 8 float4 columns x (32 lanes + 1 pad)
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetTop::needs_opl || XoDetBottom::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
@@ -206,6 +199,11 @@ McKernel(
 		const MlLayer &Lg = layers[i];
 		MlFastLayer F;
 		F.hot.top = Lg.top; F.hot.bottom = Lg.bottom;
+#if XO_ANISO
+		// direction dependent: derived per flight segment (XO_DIR_CONSTS below)
+		F.hot.step_k = 0.0f; F.hot.step_b = 0.0f;
+		F.abs.absorb = 0.0f; F.abs.survive = 1.0f; F.abs.dep_k = 0.0f; F.abs.mua = 0.0f;
+#else
 #if XO_METHOD == 2
 		F.hot.step_k = -0.6931471805599453f/Lg.mus;
 #else
@@ -215,6 +213,7 @@ McKernel(
 		F.abs.absorb = Lg.mua_inv_mut; F.abs.survive = 1.0f - Lg.mua_inv_mut;
 		F.abs.dep_k = Lg.mua_inv_mut*fluence.fixed_scale(Lg.mua);
 		F.abs.mua = Lg.mua;
+#endif
 		F.aux.n = Lg.n; F.aux.pad0 = 0.0f; F.aux.pad1 = 0.0f; F.aux.pad2 = 0.0f;
 		float n_up = (i > 0) ? layers[i - 1].n : Lg.n;
 		float n_dn = (i + 1 < num_layers) ? layers[i + 1].n : Lg.n;
@@ -253,12 +252,6 @@ McKernel(
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;
 	u32 *q_l = reinterpret_cast<u32 *>(xo_smem) + off_words + blockDim.x*8u + (threadIdx.x & ~31u);
-#if XO_TRACE_STAGED
-	off_words += blockDim.x*9u;
-	off_words = (off_words + 3u) & ~3u;
-	float4 *stage = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) +
-		(threadIdx.x >> 5)*XO_STAGE_F4_PER_WARP;
-#endif
 	// constants of the fluence deposit, pinned in registers by a round trip through
 	// shared memory (XoFluence::Prep)
 	__shared__ typename XoFluence::Prep sh_flu_prep;
@@ -302,27 +295,7 @@ McKernel(
 #else
 #define XO_RMAX_TEST() do { } while (0)
 #endif
-#if XO_TRACE && XO_TRACE_STAGED && !XO_DETERMINISTIC
-	// staged events of this lane: 4-bit slot mask within the line `stg_line`
-	u32 stg_mask = 0, stg_line = 0;
-	bool stg_pending = false;
-#define XO_TRACE_TRIP() do { \
-		flags |= done ? EV_TERMINATED : 0u; \
-		{ \
-			const u32 last_ = (u32)tcfg.max_events - 1u; \
-			const u32 slot_ = trace_count < last_ ? trace_count : last_; \
-			const u32 col_ = (slot_ & 3u)*2u; \
-			stage[col_*33u + (threadIdx.x & 31u)] = make_float4(pos.x, pos.y, pos.z, dir.x); \
-			stage[(col_ + 1u)*33u + (threadIdx.x & 31u)] = make_float4(dir.y, dir.z, weight, opl); \
-			stg_mask |= 1u << (slot_ & 3u); \
-			stg_line = slot_ >> 2; \
-			++trace_count; \
-			const u32 next_ = trace_count < last_ ? trace_count : last_; \
-			stg_pending = done || (next_ >> 2) != stg_line; \
-		} \
-		if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
-	} while (0)
-#elif XO_TRACE
+#if XO_TRACE
 #define XO_TRACE_TRIP() do { \
 		flags |= done ? EV_TERMINATED : 0u; \
 		if (XO_TRACE == XO_TRACE_ALL || ((XO_TRACE & XO_TRACE_END) && done)) { \
@@ -366,9 +339,9 @@ McKernel(
 			float step;
 			++iterations;
 #if XO_METHOD == 2
-			step = M::div(-M::log(rng.next()), L.mus);
+			step = M::div(-M::log(rng.next()), L.mus_at(dir));
 #else
-			step = -M::log(rng.next())*L.inv_mut;
+			step = -M::log(rng.next())*L.inv_mut_at(dir);
 #endif
 			step = fminf(step, XO_FLT_MAX);
 			i32 next_layer = layer;
@@ -389,7 +362,7 @@ McKernel(
 			if (layer > next_layer) pos.z = top;
 #if XO_METHOD == 2
 			{   // microscopic Beer-Lambert (mcml.template.c:584-666)
-				float mua = L.mua;
+				float mua = L.mua_at(dir);
 				float frac = 1.0f - M::exp(-mua*step);
 				float deposit = frac*weight;
 				weight -= deposit;
@@ -416,12 +389,12 @@ McKernel(
 			} else {
 #if XO_METHOD == 1
 				// albedo rejection (mcml.template.c:705-721)
-				if (rng.next() < L.mua_inv_mut) {
+				if (rng.next() < L.mua_inv_mut_at(dir)) {
 					float deposit = weight;
 					done = true;
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
-					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua_at(dir), opl);
 				} else {
 					pf_scatter(L.pf, rng, lut, dir);
 					flags |= EV_SCATTERING;
@@ -429,10 +402,10 @@ McKernel(
 #else
 #if XO_METHOD == 0
 				{   // albedo weight (mcml.template.c:722-731)
-					float deposit = weight*L.mua_inv_mut;
+					float deposit = weight*L.mua_inv_mut_at(dir);
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
-					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua_at(dir), opl);
 				}
 #endif
 				pf_scatter(L.pf, rng, lut, dir);
@@ -484,10 +457,30 @@ McKernel(
 	(void)c_aux;
 	const typename XoFluence::Prep flu_prep = sh_flu_prep;
 	(void)flu_prep;
+#if XO_ANISO
+	// anisotropic layers: the step / absorption constants belong to a (layer, direction)
+	// pair and are rederived whenever either changes (launch, interface, scattering)
+#define XO_DIR_CONSTS() do { \
+		const MlLayer &L_ = sh_layers[layer]; \
+		const float mut_ = tensor_project(L_.mut_t, dir), mua_ = tensor_project(L_.mua_t, dir); \
+		const float inv_ = (mut_ != 0.0f) ? FastMath::rcp_approx(mut_) : XO_INF; \
+		c_hot.step_k = (XO_METHOD == 2) ? \
+			-0.6931471805599453f*FastMath::rcp_approx(tensor_project(L_.mus_t, dir)) : \
+			-0.6931471805599453f*inv_; \
+		c_hot.step_b = -32.0f*c_hot.step_k; \
+		c_abs.absorb = (mua_ != 0.0f) ? mua_*inv_ : 0.0f; \
+		c_abs.survive = 1.0f - c_abs.absorb; \
+		c_abs.dep_k = c_abs.absorb*fluence.fixed_scale(mua_); \
+		c_abs.mua = mua_; \
+	} while (0)
+#else
+#define XO_DIR_CONSTS() do { } while (0)
+#endif
 #define XO_LOAD_LAYER(idx) do { \
 		const MlFastLayer &F_ = sh_fast[idx]; \
 		c_hot = F_.hot; c_abs = F_.abs; c_pf = F_.pf.v; \
 		if (XO_NEEDS_OPL) c_aux = F_.aux; \
+		XO_DIR_CONSTS(); \
 	} while (0)
 #define XO_END_TRIP() do { \
 		XO_RMAX_TEST(); \
@@ -506,40 +499,8 @@ McKernel(
 #define XO_LOTTERY() do { if (weight < XO_WEIGHT_MIN) done = true; } while (0)
 #endif
 
-	// a lane may take a new packet (or retire) only after the staged trace events of
-	// its previous packet have left for memory (the flush reads `packet`)
-#if XO_TRACE && XO_TRACE_STAGED
-#define XO_NEEDS_PACKET() (state == ST_DEAD && !stg_pending)
-#else
 #define XO_NEEDS_PACKET() (state == ST_DEAD)
-#endif
 	for (;;) {
-#if XO_TRACE && XO_TRACE_STAGED
-		// ---- flush completed trace lines: 8 lanes write one 128-byte line ------------
-		{
-			u32 pend = __ballot_sync(0xffffffffu, stg_pending);
-			while (pend != 0u) {
-				// the four lowest pending lanes, one per group of 8 lanes
-				const u32 p0 = pend, p1 = p0 & (p0 - 1u), p2 = p1 & (p1 - 1u), p3 = p2 & (p2 - 1u);
-				const u32 grp = (threadIdx.x >> 3) & 3u;
-				const u32 sel = grp == 0u ? p0 : (grp == 1u ? p1 : (grp == 2u ? p2 : p3));
-				const bool have = sel != 0u;
-				const u32 src = have ? (u32)__ffs((int)sel) - 1u : 0u;
-				const u32 s_mask = __shfl_sync(0xffffffffu, stg_mask, src);
-				const u32 s_line = __shfl_sync(0xffffffffu, stg_line, src);
-				const u32 s_packet = __shfl_sync(0xffffffffu, packet, src);
-				const u32 k = threadIdx.x & 7u;         // float4 of the line; event slot k >> 1
-				if (have && ((s_mask >> (k >> 1)) & 1u)) {
-					float4 *line = reinterpret_cast<float4 *>(float_buffer + tcfg.data_off) +
-						((u64)s_packet*(u64)tcfg.max_events + (u64)s_line*4u)*2u;
-					line[k] = stage[k*33u + src];
-				}
-				pend = p3 & (p3 - 1u);
-			}
-			if (stg_pending) { stg_mask = 0; stg_pending = false; }
-			__syncwarp();
-		}
-#endif
 		// ---- service round ------------------------------------------------------------
 		// One vote per trip.  Lanes waiting at an interface (BND_*) or for a new packet
 		// (DEAD) idle until `refill` lanes of the warp wait (or every lane that still
@@ -594,6 +555,8 @@ McKernel(
 					} else {
 						XO_LOAD_LAYER(layer);
 					}
+				} else {
+					XO_DIR_CONSTS();                // reflected: new direction, same layer
 				}
 #if XO_METHOD == 2
 				XO_LOTTERY();                   // MBL: lottery after every step
@@ -661,15 +624,17 @@ McKernel(
 				thr_eff = refill < 32u - n_dry ? refill : 32u - n_dry;
 			}
 		}
-#if XO_TRACE && XO_TRACE_STAGED
-		// a completed trace line is flushed (loop top) before the lane records again
-		if (stg_pending) continue;
-#endif
 		if (state != ST_RUN) continue;
 
 		// ---- one step of the packet ----------------------------------------------------
 		++iterations;
+#if XO_METHOD == 2
 		float step = fminf(fmaf(FastMath::lg2(rng.next_raw()), c_hot.step_k, c_hot.step_b), XO_FLT_MAX);
+#else
+		// (no clamp to FLT_MAX: an infinite step (draw == 0) always "hits" - z +- inf
+		// or NaN fails the in-layer test - and the hit path recomputes the step)
+		const float step = fmaf(FastMath::lg2(rng.next_raw()), c_hot.step_k, c_hot.step_b);
+#endif
 		const float zs = fmaf(step, dir.z, pos.z);
 		const bool hit = !(zs >= c_hot.top && zs < c_hot.bottom);
 #if XO_METHOD == 2
@@ -722,11 +687,19 @@ McKernel(
 		} else {
 			pf_scatter(c_pf, rng, lut, dir);
 			flags |= EV_SCATTERING;
+			XO_DIR_CONSTS();
 		}
 #else
 #if XO_METHOD == 0
-		{   // albedo weight: the deposit leaves as fixed point in one FFMA + F2I
+		{   // albedo weight: the deposit leaves as fixed point in one FFMA + LOP3
+#if XO_DEPOSIT_MAGIC
+			// round(w*dep_k) from the mantissa of w*dep_k + 2^23 (the host guarantees
+			// w*dep_k < 2^23 - 1): no F2I on the XU pipe.  Round-to-nearest-even
+			// instead of the reference's floor(x + 0.5): differs only on exact ties.
+			const u32 wfix = __float_as_uint(fmaf(weight, c_abs.dep_k, 8388608.0f)) & 0x7fffffu;
+#else
 			const u32 wfix = f2u(fmaf(weight, c_abs.dep_k, 0.5f));
+#endif
 			weight *= c_abs.survive;
 			flags |= EV_ABSORPTION;
 			if (XoFluence::active) fluence.deposit_prep(acc, flu_prep, window, pos, wfix, opl);
@@ -734,11 +707,13 @@ McKernel(
 #endif
 		pf_scatter(c_pf, rng, lut, dir);
 		flags |= EV_SCATTERING;
+		XO_DIR_CONSTS();
 		XO_LOTTERY();
 #endif
 		XO_END_TRIP();
 	}
 #undef XO_LOAD_LAYER
+#undef XO_DIR_CONSTS
 #undef XO_NEEDS_PACKET
 #undef XO_END_TRIP
 #undef XO_LOTTERY

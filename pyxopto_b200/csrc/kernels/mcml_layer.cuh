@@ -8,10 +8,45 @@
 
 namespace xo {
 
+#ifndef XO_ANISO
+#define XO_ANISO 0
+#endif
+
+// p T p' (mcbase.template.h:2227-2230), the reference's association
+__device__ __forceinline__ float tensor_project(const M3 &T, const P3 &p) {
+	return p.x*(T.a11*p.x + T.a12*p.y + T.a13*p.z) +
+		p.y*(T.a21*p.x + T.a22*p.y + T.a23*p.z) +
+		p.z*(T.a31*p.x + T.a32*p.y + T.a33*p.z);
+}
+
+#if XO_ANISO
+// AnisotropicLayer (mcml/mclayer/layer.py:412-424): the coefficients seen by a packet
+// are the tensors projected on its propagation direction (:497-551)
+struct MlLayer {
+	float thickness, top, bottom, n, cc_top, cc_bottom;
+	M3 mus_t, mua_t, mut_t;
+	XoPf pf;
+	__device__ __forceinline__ float mus_at(const P3 &d) const { return tensor_project(mus_t, d); }
+	__device__ __forceinline__ float mua_at(const P3 &d) const { return tensor_project(mua_t, d); }
+	__device__ __forceinline__ float inv_mut_at(const P3 &d) const {
+		const float mut = tensor_project(mut_t, d);
+		return (mut != 0.0f) ? M::div(1.0f, mut) : XO_INF;
+	}
+	__device__ __forceinline__ float mua_inv_mut_at(const P3 &d) const {
+		const float mua = tensor_project(mua_t, d), mut = tensor_project(mut_t, d);
+		return (mua != 0.0f) ? ((mut != 0.0f) ? M::div(mua, mut) : XO_INF) : 0.0f;
+	}
+};
+#else
 struct MlLayer {                    // mcml/mclayer/layer.py:57-69
 	float thickness, top, bottom, n, cc_top, cc_bottom, mus, mua, inv_mut, mua_inv_mut;
 	XoPf pf;
+	__device__ __forceinline__ float mus_at(const P3 &) const { return mus; }
+	__device__ __forceinline__ float mua_at(const P3 &) const { return mua; }
+	__device__ __forceinline__ float inv_mut_at(const P3 &) const { return inv_mut; }
+	__device__ __forceinline__ float mua_inv_mut_at(const P3 &) const { return mua_inv_mut; }
 };
+#endif
 
 struct MlCtx {
 	const MlLayer *layers;          // shared memory

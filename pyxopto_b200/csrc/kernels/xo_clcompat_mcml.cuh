@@ -23,8 +23,16 @@ typedef xo::MlLayer McLayer;
 #define mc_layer_n(player) ((player)->n)
 #define mc_layer_cc_top(player) ((player)->cc_top)
 #define mc_layer_cc_bottom(player) ((player)->cc_bottom)
+#if XO_ANISO
+#define mc_layer_mus(player, pdir) ((player)->mus_at(*(pdir)))
+#define mc_layer_mua(player, pdir) ((player)->mua_at(*(pdir)))
+#define mc_layer_mut(player, pdir) (xo::tensor_project((player)->mut_t, *(pdir)))
+#define mc_layer_inv_mut(player, pdir) ((player)->inv_mut_at(*(pdir)))
+#define mc_layer_mua_inv_mut(player, pdir) ((player)->mua_inv_mut_at(*(pdir)))
+#else
 #define mc_layer_mus(player, ...) ((player)->mus)
 #define mc_layer_mua(player, ...) ((player)->mua)
 #define mc_layer_mut(player, ...) ((player)->mua + (player)->mus)
 #define mc_layer_inv_mut(player, ...) ((player)->inv_mut)
 #define mc_layer_mua_inv_mut(player, ...) ((player)->mua_inv_mut)
+#endif

@@ -70,6 +70,9 @@ __device__ __forceinline__ i32 clipi(i32 x, i32 lo, i32 hi) { return x < lo ? lo
 __device__ __forceinline__ float signf(float x) { return (x >= 0.0f) ? 1.0f : -1.0f; }
 // C float->int conversion of the reference (convert_int / (uint32_t) casts):
 // CUDA's cvt.rzi saturates where C is undefined; identical on every reachable value.
+// floor(x) for |x| < 2^22 on the FMA pipe: bits(x + 1.5 * 2^23, rounded down) - bits(1.5 * 2^23)
+#define XO_FLOOR_MAGIC 12582912.0f
+#define XO_FLOOR_MAGIC_BITS 0x4B400000u
 __device__ __forceinline__ i32 f2i(float x) { return __float2int_rz(x); }
 __device__ __forceinline__ u32 f2u(float x) { return __float2uint_rz(x); }
 
@@ -273,6 +276,10 @@ __device__ __forceinline__ void scatter_direction(P3 &d, float ct, float fi) {
 	nx = polar ? stcf : nx;
 	ny = polar ? stsf : ny;
 	nz = polar ? copysignf(ct, pz*ct) : nz;
+	// renormalisation (the reference always renormalises).  A Newton step 1.5 - 0.5 s
+	// in place of the MUFU.RSQ is NOT enough: within ~1e-6 of the poles 1 - pz^2 loses
+	// all its digits and the rotated vector is off by O(1) (a handful of events per
+	// 1e7 leave with |dir| - 1 > 1e-4; measured with the trace consistency tests)
 	const float k = rsqrtf(nx*nx + ny*ny + nz*nz);
 	d.x = nx*k; d.y = ny*k; d.z = nz*k;
 #endif

@@ -127,7 +127,7 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 	__device__ __forceinline__ Prep prepare(const FluWindow &win) const {
 		Prep p;
 		p.cx = center.x; p.cy = center.y; p.inv_dr = inv_dr; p.inv_dz = inv_dz;
-		p.br = -(float)win.org0;
+		p.br = XO_FLOOR_MAGIC - (float)win.org0;      // exact: both are integers
 		p.bz = -center.z*inv_dz - (float)win.org1;
 		p.ext0 = win.ext0; p.ext1 = win.ext1;
 		return p;
@@ -142,8 +142,13 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 		if (!XO_FLU_WINDOW) { deposit_fixed(acc, win, pos, wfix, opl); return; }
 		float dx = pos.x - p.cx, dy = pos.y - p.cy;
 		float r = FastMath::sqrt(fmaf(dx, dx, dy*dy));
-		u32 lr = (u32)__float2int_rd(fmaf(r, p.inv_dr, p.br));
-		u32 lz = (u32)__float2int_rd(fmaf(pos.z, p.inv_dz, p.bz));
+		// floor without the conversion unit (F2I shares the XU pipe with MUFU, the
+		// busiest pipe of this loop): adding 1.5 * 2^23 with round-down leaves
+		// floor(x) in the low mantissa bits for |x| < 2^22, and the bit pattern is
+		// monotonic in x beyond that, so the unsigned window test still rejects
+		// every out-of-range / NaN coordinate (p.br carries the 1.5 * 2^23)
+		u32 lr = __float_as_uint(__fmaf_rd(r, p.inv_dr, p.br)) - XO_FLOOR_MAGIC_BITS;
+		u32 lz = __float_as_uint(__fadd_rd(fmaf(pos.z, p.inv_dz, p.bz), XO_FLOOR_MAGIC)) - XO_FLOOR_MAGIC_BITS;
 		if (lr < p.ext0 && lz < p.ext1) {
 			if (acc.add_window(lz*p.ext0 + lr, wfix))
 				acc.carry_global(offset + (lz + win.org1)*n_r + lr + win.org0);
@@ -335,7 +340,21 @@ __device__ __forceinline__ bool trace_event(const TraceCfg &t, float *fbuf, u32 
 	i32 slot = (i32)count < t.max_events - 1 ? (i32)count : t.max_events - 1;
 	u32 p = (u32)slot*8u + packet*(u32)t.max_events*8u + t.data_off;
 	float *dst = fbuf + p;
-#if XO_TRACE_ALIGNED
+#if XO_TRACE_ALIGNED == 2
+	// 32-byte aligned rows: the event is exactly one DRAM sector and leaves with ONE
+	// 256-bit store (STG.E.256, sm_100+).  Measured on B200 with one 16 KB-strided
+	// row per thread (tools/trace_store_probe.cu, profiles/trace_store_probe_r02.json):
+	// 3.3-4.4 TB/s against 2.2 TB/s for two STG.128 and 3.0-4.2 TB/s for 128-byte
+	// lines assembled by 8 lanes in shared memory (the round-1 path, ~100 extra
+	// warp-instructions per trip); a per-lane cp.async.bulk serialises (UBLKCP takes
+	// uniform registers: one lane at a time).  Parking the event in registers and storing
+	// it one trip later (so that the warp does not wait behind the store until the LSU
+	// has read the operands, 46 % of the stall samples) changed nothing: 2.75 vs 2.69 ms
+	// per 1e6 packets of C4 - the SM's store path itself (~16 B/clk) is the limit.
+	asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+		:: "l"(dst), "f"(pos.x), "f"(pos.y), "f"(pos.z), "f"(dir.x), "f"(dir.y),
+		   "f"(dir.z), "f"(w), "f"(opl) : "memory");
+#elif XO_TRACE_ALIGNED
 	float4 *d4 = reinterpret_cast<float4 *>(dst);
 	d4[0] = make_float4(pos.x, pos.y, pos.z, dir.x);
 	d4[1] = make_float4(dir.y, dir.z, w, opl);

@@ -100,18 +100,23 @@ struct PfMHg {                      // mcpf/mhg.py:52-58
 		return clipf(ct, -1.0f, 1.0f);
 	}
 	struct Fast {
-		HgFast hg;
+		// One draw serves the branch choice AND the polar angle: given f <= beta the
+		// draw f/beta is uniform again (and (f - beta)/(1 - beta) given f > beta), so
+		// the two affine maps are folded into the constants of the two samplers -
+		// the same distribution as the reference's three draws with two (one MWC
+		// step, one int->float conversion and the divergent third draw less).
+		// Both branches are evaluated and selected: nearly every warp would take
+		// both sides of a branch.
+		HgFast hg;                  // d1 carries 1/beta
 		float beta_raw;             // beta * 2^32 (compared against the raw draw)
+		float rl_k, rl_b;           // Rayleigh-like part: ct = cbrt(f*rl_k + rl_b)
 		__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
 			(void)lut;
-			// both branches consume the same third draw: evaluate both (8 + 6
-			// instructions) and select, instead of a divergent branch that
-			// nearly every warp would take both ways
 			*azimuth = rng.next_raw()*(XO_FP_2PI*2.3283064365386963e-10f);
-			const bool use_hg = rng.next_raw() <= beta_raw;
 			const float f = rng.next_raw();
+			const bool use_hg = f <= beta_raw;
 			float ct_hg = hg.polar(f, rng, use_hg);
-			float ct_rl = FastMath::cbrt(fmaf(f, 2.0f*2.3283064365386963e-10f, -1.0f));
+			float ct_rl = FastMath::cbrt(fmaf(f, rl_k, rl_b));
 			float ct = use_hg ? ct_hg : ct_rl;
 			return fmaxf(fminf(ct, 1.0f), -1.0f);
 		}
@@ -119,6 +124,11 @@ struct PfMHg {                      // mcpf/mhg.py:52-58
 	__device__ __forceinline__ void prepare(Fast &f) const {
 		f.hg.prepare(g);
 		f.beta_raw = beta*4294967296.0f;
+		if (beta > 0.0f) f.hg.d1 = f.hg.d1/beta;
+		// 2 (f 2^-32 - beta)/(1 - beta) - 1
+		const float w = (beta < 1.0f) ? 1.0f/(1.0f - beta) : 0.0f;
+		f.rl_k = 2.0f*2.3283064365386963e-10f*w;
+		f.rl_b = -2.0f*beta*w - 1.0f;
 	}
 };
 

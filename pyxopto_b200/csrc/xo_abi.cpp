@@ -122,15 +122,35 @@ std::once_flag g_rtc_once;
 std::string g_rtc_error;
 
 void load_nvrtc() {
+	// The newest NVRTC in reach wins: a host process may already have mapped an older
+	// libnvrtc.so.12 under the same soname (PyTorch bundles the one of its own CUDA
+	// build), and the kernels use PTX of the toolkit this library was built against
+	// (256-bit global stores need PTX ISA 8.8).  Absolute paths are separate objects
+	// for the dynamic loader, so every candidate is opened and asked for its version.
 	std::vector<std::string> names;
 	if (const char *env = getenv("XOPTO_NVRTC")) names.push_back(env);
-	names.push_back("libnvrtc.so.12");
+	for (const char *var : {"CUDA_HOME", "CUDA_PATH"})
+		if (const char *home = getenv(var)) names.push_back(std::string(home) + "/lib64/libnvrtc.so.12");
 	names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
-	names.push_back("libnvrtc.so");
+	names.push_back("/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12");
 	names.push_back("/usr/local/cuda/lib64/libnvrtc.so");
-	for (auto &n : names) {
-		g_rtc.handle = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
-		if (g_rtc.handle) break;
+	names.push_back("libnvrtc.so.12");
+	names.push_back("libnvrtc.so");
+	int best = -1;
+	for (size_t i = 0; i < names.size(); ++i) {
+		void *h = dlopen(names[i].c_str(), RTLD_NOW | RTLD_LOCAL);
+		if (!h) continue;
+		int major = 0, minor = 0;
+		auto version = reinterpret_cast<decltype(&::nvrtcVersion)>(dlsym(h, "nvrtcVersion"));
+		const int v = (version && version(&major, &minor) == NVRTC_SUCCESS) ? major*1000 + minor : 0;
+		if (i == 0 && getenv("XOPTO_NVRTC")) { g_rtc.handle = h; break; }   // explicit choice
+		if (v > best) {
+			if (g_rtc.handle) dlclose(g_rtc.handle);
+			g_rtc.handle = h;
+			best = v;
+		} else {
+			dlclose(h);
+		}
 	}
 	if (!g_rtc.handle) {
 		g_rtc_error = "NVRTC library libnvrtc.so.12 not found";

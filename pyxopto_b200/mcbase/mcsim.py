@@ -12,6 +12,7 @@ the geometry kernel header.  NVRTC compiles it for sm_100a; cubins are cached
 in-tree by content hash.
 """
 import ctypes
+import os
 import time
 import weakref
 
@@ -200,10 +201,10 @@ class McBase(CuWorker):
             '#define XO_FLUENCE_RATE {}'.format(
                 int(bool(opts.get('MC_FLUENCE_MODE_RATE', False)))),
             '#define XO_TRACE_ALIGNED {}'.format(int(self._trace_aligned())),
-            '#define XO_TRACE_STAGED {}'.format(int(self._trace_staged(opts))),
             '#define XO_USE_RMAX {}'.format(int(self._rmax_needed())),
             '#define XO_FLU_WINDOW {}'.format(int(self._window_enabled())),
             '#define XO_PF_G0 {}'.format(int(self._pf_isotropic_possible())),
+            '#define XO_DEPOSIT_MAGIC {}'.format(int(self._deposit_magic(opts))),
             '#define XO_BLOCK {}'.format(int(block)),
             '#define XO_MIN_BLOCKS {}'.format(int(min_blocks)),
         ]
@@ -314,6 +315,18 @@ class McBase(CuWorker):
                 return True
         return False
 
+    def _deposit_magic(self, opts) -> bool:
+        """True when every fluence deposit of the throughput loop is below 2^23 - 1
+        in fixed point (weight <= 1, deposition mode, k <= 0x7FFFFF): the kernel then
+        converts with one FFMA + LOP3 instead of the conversion unit."""
+        flu = self._fluence
+        if flu is None or opts.get('MC_FLUENCE_MODE_RATE', False):
+            return False
+        wmin = float(opts.get('MC_PACKET_WEIGHT_MIN', 1e-4))
+        chance = float(opts.get('MC_PACKET_LOTTERY_CHANCE', 0.1))
+        return int(getattr(flu, 'k', 1 << 30)) <= 0x7FFFFF and wmin <= chance and \
+            getattr(self._source, 'cu_type', None) is not None
+
     def _rmax_needed(self) -> bool:
         """False when the rmax test can never fire (compiled out of the loop)."""
         return bool(np.isfinite(np.float32(self._rmax)))
@@ -327,10 +340,11 @@ class McBase(CuWorker):
     def _min_blocks(self, block: int) -> int:
         if self.min_blocks is not None:
             return int(self.min_blocks)
-        # the staged full-trace kernel needs 76 KB of shared memory per 256-thread
-        # CTA: three CTAs per SM fit if the compiler stays below 80 registers
-        # (measured C4: 3.94 ms at 83 registers / 2 CTAs, 3.38 ms at 72 / 3 CTAs)
-        if self._trace_staged() and block <= 256:
+        # a full trace is a store stream (one 32-byte event per trip and lane): more
+        # resident warps keep more stores in flight (measured C4, 1e6 packets: 2.69 ms
+        # at 3 CTAs of 256 / 70 registers, 2.85 ms at 4 / 64, 2.95 ms at 2 / 76)
+        if self.geometry == 'mcml' and self._trace is not None and block <= 256 and \
+                not self.deterministic:
             return 3
         return 1
     chunk_max = 16
@@ -346,21 +360,16 @@ class McBase(CuWorker):
     def _extra_checks(self):
         return []
 
-    def _trace_aligned(self) -> bool:
+    def _trace_aligned(self) -> int:
+        """Alignment class of the trace rows in the float buffer: 2 = 32 bytes (an
+        event leaves with one 256-bit store), 1 = 16 bytes (two 128-bit stores),
+        0 = scalar stores."""
         tr = self._packed.get('trace')
-        return self._trace is not None and tr is not None and \
-            tr.data_buffer_offset % 4 == 0
-
-    def _trace_staged(self, opts=None) -> bool:
-        """Full traces of the layered throughput kernel leave through a
-        shared-memory stage as whole 128-byte lines (mcml_kernel.cuh)."""
-        opts = self.resolved_options() if opts is None else opts
-        return (self.geometry == 'mcml' and self._trace is not None and
-                int(opts.get('MC_USE_TRACE', 0)) == 7 and
-                not opts.get('XO_DETERMINISTIC', False) and
-                not opts.get('MC_USE_EVENTS', False) and
-                self._trace_aligned() and int(self._trace.maxlen) % 4 == 0 and
-                int(self._trace.maxlen) >= 4)
+        if self._trace is None or tr is None:
+            return 0
+        off = int(tr.data_buffer_offset)
+        wide = os.environ.get('XOPTO_TRACE_STORE', '256') == '256'     # developer knob
+        return 2 if (off % 8 == 0 and wide) else (1 if off % 4 == 0 else 0)
 
     def export_src(self, filename: str = None, nphotons: int = 1) -> str:
         self._pack(nphotons)
@@ -539,8 +548,6 @@ class McBase(CuWorker):
         ibuf = self._rw_flat_buffer('int')
         shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
         queue_bytes = 0 if deterministic else 36*block + 16   # per-warp launch queues
-        if self._trace_staged():
-            queue_bytes += (block//32)*264*16 + 16            # per-warp trace stage
         window = self._fluence_window(block, shared + queue_bytes)
         shared += 4*int(window[3])*int(window[4])*int(window[5]) + queue_bytes
         grid, block = self.launch_geometry(kernel, block, shared, maxthreads)
@@ -774,6 +781,45 @@ class McBase(CuWorker):
         return n_host, rows, n_dropped
 
     # -- sampling volume (config 4) ----------------------------------------------
+    # True: the integer grid of a SamplingVolume object stays on the device across
+    # ``sampling_volume`` calls (exact 64-bit sums) and is converted / downloaded when
+    # the object's ``data`` is read; False: the reference's flow, one conversion and
+    # one download of the whole grid per call (mc.py:1183-1213).
+    lazy_sampling_volume = False
+    _sv_resident = None              # (weakref to the SamplingVolume, grid cells)
+
+    def _sv_resident_buffer(self, sv, cells: int):
+        """Device grid that accumulates for ``sv``; another object's pending grid is
+        collected first, a fresh grid starts at zero."""
+        cur = self._sv_resident
+        owner = cur[0]() if cur is not None else None
+        if owner is not sv or cur[1] != cells:
+            if owner is not None:
+                owner._materialize()
+            self._sv_resident = None
+        buf = self._buffer('sv_resident', cells*8)
+        if self._sv_resident is None:
+            buf.fill(self._stream, 0, np.uint32, count=cells*2)
+            self._sv_resident = (weakref.ref(sv), cells)
+        return buf
+
+    def _sv_loader(self, cells: int):
+        """Loader handed to the SamplingVolume: converts the resident grid on the
+        device (AccuScale), copies it to the host and restarts the grid at zero."""
+        def load(sv):
+            cur = self._sv_resident
+            if cur is None or cur[0]() is not sv:
+                return
+            buf = self._cl_buffers['sv_resident']
+            whole = type('A', (), {'offset': 0, 'size': cells})
+            scaled = self._scale_on_device(buf, whole, 1.0/(sv.k*sv._multiplier(self)))
+            if sv._data is not None:
+                sv._data += np.reshape(scaled, sv.shape)
+            else:
+                sv._data = np.array(scaled, dtype=np.float64).reshape(sv.shape)
+            self._sv_resident = None
+        return load
+
     _SV_SRC = '#define XO_DETERMINISTIC {det}\n#include "xo_sv_kernel.cuh"\n'
 
     def _pack_sampling_volume(self, trace, sv, nphotons: int):
@@ -817,7 +863,16 @@ class McBase(CuWorker):
         cbuf = self.cl_r_buffer('counters', counters)
         total = np.zeros(1, dtype=np.uint64)
         tbuf = self.cl_r_buffer('sv_total_weight', total)
-        abuf = self._rw_flat_buffer('accumulator')
+        sv_allocs = self.cl_rw_accumulator_allocator.allocations(sv)
+        lazy = bool(self.lazy_sampling_volume and download and len(sv_allocs) == 1 and
+                    int(sv_allocs[0].offset) == 0 and hasattr(sv, '_set_pending') and
+                    type(sv).update_data is mcsv_module.SamplingVolume.update_data)
+        if lazy:
+            # the kernel adds onto the grid that stays on the device for `sv`
+            cells = int(sv_allocs[0].size)
+            abuf = self._sv_resident_buffer(sv, cells)
+        else:
+            abuf = self._rw_flat_buffer('accumulator')
         itemsize = np.dtype(self._types.np_float).itemsize
         dev = getattr(self, '_device_trace', None)
         resident = bool(
@@ -862,7 +917,10 @@ class McBase(CuWorker):
         cbuf.download(self._stream, counters)
         tbuf.download(self._stream, total)
         accus = []
-        allocs = self.cl_rw_accumulator_allocator.allocations(sv) if download else ()
+        allocs = sv_allocs if (download and not lazy) else ()
+        if lazy:
+            sv.add_weight(total[0])
+            sv._set_pending(self._sv_loader(cells))
         if len(allocs) == 1 and allocs[0].size >= self.SCALE_ON_DEVICE_MIN and \
                 type(sv).update_data is mcsv_module.SamplingVolume.update_data:
             # large grid: the float64 conversion of update_data runs on the device

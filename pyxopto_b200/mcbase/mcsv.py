@@ -27,7 +27,7 @@ class SamplingVolume(McObject):
         if isinstance(xaxis, SamplingVolume):
             sv = xaxis
             xaxis, yaxis, zaxis = Axis(sv.xaxis), Axis(sv.yaxis), Axis(sv.zaxis)
-            if sv.data is not None:
+            if sv.data is not None:         # (reading `data` collects a device-resident grid)
                 data = np.copy(sv.data)
             weight = sv.weight
         self._x_axis, self._y_axis, self._z_axis = xaxis, yaxis, zaxis
@@ -46,18 +46,38 @@ class SamplingVolume(McObject):
     zaxis = property(lambda self: self._z_axis)
     k = property(lambda self: self._k)
 
+    # Device-resident accumulation (``Mc.lazy_sampling_volume``): the simulator keeps
+    # the integer grid of this object on the device across ``sampling_volume`` calls
+    # and hands over a loader; the grid comes to the host (converted once, from the
+    # exact integer sum) when ``data`` is read.
+    _pending = None
+
+    def _set_pending(self, loader):
+        self._pending = loader
+
+    def _materialize(self):
+        loader, self._pending = self._pending, None
+        if loader is not None:
+            loader(self)
+
+    def _get_data(self):
+        self._materialize()
+        return self._data
+
     def _set_data(self, data):
+        self._materialize()
         self._data = data
 
     def _set_weight(self, w):
         self._weight = w
 
-    data = property(lambda self: self._data, _set_data, None,
+    data = property(_get_data, _set_data, None,
                     'Raw sampling volume accumulator data if any.')
     weight = property(lambda self: self._weight, _set_weight, None,
                       'Total weight of the accumulated photon packets.')
 
     def clear(self):
+        self._materialize()
         if self._data is not None:
             self._data.fill(0)
 
@@ -84,10 +104,12 @@ class SamplingVolume(McObject):
         (bit-identically) on the device; ``scaled`` may be reused by the caller."""
         if self._data is not None:
             self._data += np.reshape(scaled, self.shape)
-            self._weight += float(total_weight)/self._k
         else:
             self._data = np.array(scaled, dtype=np.float64).reshape(self.shape)
-            self._weight = float(total_weight)/self._k
+        self.add_weight(total_weight)
+
+    def add_weight(self, total_weight):
+        self._weight = (self._weight or 0.0) + float(total_weight)/self._k
 
     def cl_pack(self, mc, target=None):
         if target is None:

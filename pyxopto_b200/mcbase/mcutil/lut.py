@@ -116,63 +116,78 @@ class LinearLut(McObject):
         np.savez_compressed(filename, **self.todict(False))
 
 
+def _resample(x, y, xq):
+    """Piecewise-linear resampling ``y(x) -> y(xq)`` (``x`` ascending or descending,
+    ``xq`` inside its range).  The segment is chosen with a left-sided search and
+    evaluated in the slope form ``y0 + (xq - x0)*(y1 - y0)/(x1 - x0)``, which is the
+    arithmetic scipy's ``interp1d`` performs - the reference builds its tables with
+    it (mcutil/lut.py:285-362), and the packed float pool has to match to the bit."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    xq = np.asarray(xq, dtype=np.float64)
+    if x.size > 1 and x[0] > x[-1]:
+        x, y = x[::-1], y[::-1]
+    if xq.size and (xq.min() < x[0] or xq.max() > x[-1]):
+        raise ValueError('A value in x_new is outside of the interpolation range.')
+    hi = np.clip(np.searchsorted(x, xq), 1, x.size - 1)
+    lo = hi - 1
+    return (y[hi] - y[lo])/(x[hi] - x[lo])*(xq - x[lo]) + y[lo]
+
+
+def _cosine_axis(costheta, size: int) -> np.ndarray:
+    if costheta is None:
+        return np.linspace(0.0, 1.0, size)
+    return np.asarray(costheta, dtype=np.float64)
+
+
 class CollectionLut(LinearLut):
-    """Angular sensitivity of a detector as a function of the incidence-angle
-    cosine, resampled to ``n`` uniformly spaced cosines (mcutil/lut.py:327-362)."""
+    """Angular sensitivity of a detector over the cosine of the incidence angle,
+    tabulated at ``n`` equidistant cosines (counterpart of mcutil/lut.py:327-362)."""
     def __init__(self, sensitivity, costheta=None, n: int = 1000):
         if isinstance(sensitivity, (str, CollectionLut)):
             super().__init__(sensitivity)
             return
-        from scipy.interpolate import interp1d
-        sensitivity = np.asarray(sensitivity, dtype=np.float64)
-        if costheta is None:
-            costheta = np.linspace(0.0, 1.0, sensitivity.size)
-        else:
-            costheta = np.asarray(costheta)
-        ct = np.linspace(costheta.min(), costheta.max(), n)
-        super().__init__(interp1d(costheta, sensitivity)(ct), ct[0], ct[-1])
+        values = np.asarray(sensitivity, dtype=np.float64)
+        axis = _cosine_axis(costheta, values.size)
+        grid = np.linspace(axis.min(), axis.max(), n)
+        super().__init__(_resample(axis, values, grid), grid[0], grid[-1])
 
 
 class EmissionLut(LinearLut):
-    """Table for sampling the emission-angle cosine of a source with the given
-    angular radiance (azimuthal symmetry): sampled with a uniform random number
-    from [0, 1] (mcutil/lut.py:240-325; CDF by Simpson's rule or adaptive
-    quadrature)."""
+    """Inverse-CDF table of a source's emission-angle cosine for an azimuthally
+    symmetric angular radiance: entry ``u*(n - 1)`` of the table is the cosine at
+    which the cumulative emitted power reaches the fraction ``u`` (counterpart of
+    mcutil/lut.py:240-325).  The power density over the cosine is
+    ``radiance*sin(theta)``; its running integral is taken panel by panel with
+    Simpson's rule on an odd number of equidistant nodes (``meth='simps'``) or
+    with adaptive quadrature from the lower limit (``meth='quad'``)."""
     def __init__(self, radiance, costheta=None, n: int = 2000, npts: int = 10000,
                  meth: str = 'simps'):
         if isinstance(radiance, (str, EmissionLut)):
             super().__init__(radiance)
             return
-        from scipy.interpolate import interp1d
-        lut_random = np.linspace(0.0, 1.0, n)
-        radiance = np.asarray(radiance, dtype=np.float64)
-        if costheta is None:
-            costheta = np.linspace(0.0, 1.0, radiance.size)
-        else:
-            costheta = np.asarray(costheta, dtype=np.float64)
-        if radiance.size != costheta.size:
-            raise ValueError('The sizes of the radiance and costheta array must be equal!')
-        radiance_f = interp1d(costheta, radiance*np.sqrt(1.0 - costheta**2))
-        ct_range = costheta.min(), costheta.max()
-        if meth == 'simps':
-            npts = max(int((max(2*n, npts)//2))*2 + 1, 3)
-            ct = np.linspace(ct_range[0], ct_range[1], max(n, npts))
-            cdf = np.zeros([int(ct.size//2) + 1])
-            radiance_ct = radiance_f(ct)
-            dx = (ct[-1] - ct[0])/(ct.size - 1)
-            cdf[1:] = dx/3.0*(
-                radiance_ct[:-2:2] + 4.0*radiance_ct[1:-1:2] + radiance_ct[2::2])
-            cdf = cdf.cumsum()
-            cdf /= cdf[-1]
-            lut = interp1d(cdf, ct[::2])(lut_random)
-        elif meth == 'quad':
-            from scipy.integrate import quad
-            ct = np.linspace(ct_range[0], ct_range[1], max(n, npts))
-            cdf = np.zeros_like(ct)
-            for index, ct_item in enumerate(ct):
-                cdf[index] = quad(radiance_f, ct_range[0], ct_item)[0]
-            cdf /= cdf[-1]
-            lut = interp1d(cdf, ct)(lut_random)
-        else:
+        if meth not in ('simps', 'quad'):
             raise ValueError('Unknown integration method "{}"!'.format(meth))
-        super().__init__(lut, 0.0, 1.0)
+        values = np.asarray(radiance, dtype=np.float64)
+        axis = _cosine_axis(costheta, values.size)
+        if values.size != axis.size:
+            raise ValueError('The sizes of the radiance and costheta array must be equal!')
+        density = values*np.sqrt(1.0 - axis**2)
+        lower, upper = axis.min(), axis.max()
+        fractions = np.linspace(0.0, 1.0, n)
+        if meth == 'simps':
+            nodes = max(n, max(2*(max(2*n, npts)//2) + 1, 3))
+            ct = np.linspace(lower, upper, nodes)
+            f = _resample(axis, density, ct)
+            h = (ct[-1] - ct[0])/(ct.size - 1)
+            # one Simpson panel per pair of intervals; the CDF lives on the even nodes
+            panels = h/3.0*(f[:-2:2] + 4.0*f[1:-1:2] + f[2::2])
+            cdf = np.concatenate(([0.0], panels)).cumsum()
+            knots = ct[::2]
+        else:
+            from scipy.integrate import quad
+            knots = np.linspace(lower, upper, max(n, npts))
+            cdf = np.array([quad(lambda c: float(_resample(axis, density, c)), lower, c)[0]
+                            for c in knots])
+        cdf /= cdf[-1]
+        super().__init__(_resample(cdf, knots, fractions), 0.0, 1.0)

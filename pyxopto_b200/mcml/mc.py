@@ -73,6 +73,10 @@ class Mc(McBase):
         self.cl_r_buffer('layers', self._packed['layers'])
 
     # -- translation unit ----------------------------------------------------------
+    def _extra_defines(self, opts):
+        aniso = isinstance(self._layers[1], mclayer.AnisotropicLayer)
+        return ['#define XO_ANISO {}'.format(int(aniso))]
+
     def _plugin_bindings(self):
         pf = self._layers[1].pf
         out = [('XoPf', pf.fetch_cu_type(self), pf.fetch_cl_type(self)),

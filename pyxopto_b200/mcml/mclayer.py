@@ -1,4 +1,6 @@
 """Layer stack of the planar simulator (mirror of ``xopto/mcml/mclayer/layer.py``)."""
+import numpy as np
+
 from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import boundary
@@ -58,6 +60,97 @@ class Layer(McObject):
             self.d, self.n, self.mua, self.mus, self.pf)
 
 
+def _tensor(value) -> np.ndarray:
+    """3 x 3 tensor from a scalar (isotropic), 3 diagonal elements or a full
+    matrix (layer.py:662-708)."""
+    t = np.zeros((3, 3))
+    if isinstance(value, (float, int)):
+        t[0, 0] = t[1, 1] = t[2, 2] = value
+    else:
+        value = np.asarray(value, dtype=float)
+        if value.size == 3:
+            t[0, 0], t[1, 1], t[2, 2] = value.ravel()
+        else:
+            t[:] = value
+    return t
+
+
+class AnisotropicLayer(McObject):
+    """Layer with direction-dependent absorption / scattering coefficients: the
+    kernel projects the 3 x 3 tensors on the propagation direction, ``mu(dir) =
+    dir^T T dir`` (layer.py:391-790, mcbase.template.h:2227-2230)."""
+    cu_type = 'xo::MlAnisoLayer'
+
+    @staticmethod
+    def layer_type(mc, pf_type):
+        T = mc.types
+        class ClAnisotropicLayer(cltypes.Structure):
+            _fields_ = [
+                ('thickness', T.mc_fp_t), ('top', T.mc_fp_t), ('bottom', T.mc_fp_t),
+                ('n', T.mc_fp_t), ('cos_critical_top', T.mc_fp_t),
+                ('cos_critical_bottom', T.mc_fp_t), ('mus', T.mc_matrix3f_t),
+                ('mua', T.mc_matrix3f_t), ('mut', T.mc_matrix3f_t), ('pf', pf_type)]
+        return ClAnisotropicLayer
+
+    def cl_type(self, mc):
+        return self.layer_type(mc, self.pf.fetch_cl_type(mc))
+
+    def __init__(self, d: float, n: float, mua, mus, pf):
+        super().__init__()
+        self.d, self.n = float(d), float(n)
+        self._mua, self._mus = _tensor(mua), _tensor(mus)
+        self._pf = pf
+
+    def _set_mua(self, mua):
+        self._mua = _tensor(mua)
+
+    def _set_mus(self, mus):
+        self._mus = _tensor(mus)
+
+    mua = property(lambda self: self._mua, _set_mua, None,
+                   'Absorption coefficient tensor (3x3) of the layer (1/m).')
+    mus = property(lambda self: self._mus, _set_mus, None,
+                   'Scattering coefficient tensor (3x3) of the layer (1/m).')
+
+    def _set_pf(self, pf):
+        if type(self._pf) is not type(pf):
+            raise ValueError('The scattering phase function type '
+                             'of the layer must not change!')
+        self._pf = pf
+
+    pf = property(lambda self: self._pf, _set_pf, None, 'Phase function object.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        target.thickness, target.n = self.d, self.n
+        target.mua.fromarray(self._mua)
+        target.mus.fromarray(self._mus)
+        target.mut.fromarray(self._mua + self._mus)
+        self.pf.cl_pack(mc, target.pf)
+        return target
+
+    def todict(self):
+        return {'d': self.d, 'n': self.n, 'mua': self._mua, 'mus': self._mus,
+                'pf': self.pf.todict(), 'type': type(self).__name__}
+
+    @classmethod
+    def fromdict(cls, data: dict):
+        from ..mcbase import mcpf
+        data = dict(data)
+        if data.pop('type') != 'AnisotropicLayer':
+            raise ValueError('Cannot create an AnisotropicLayer instance from the data!')
+        pf_data = data.pop('pf')
+        if not hasattr(mcpf, pf_data['type']):
+            raise TypeError('Scattering phase function "{}" not implemented'.format(
+                pf_data['type']))
+        return cls(pf=getattr(mcpf, pf_data['type']).fromdict(pf_data), **data)
+
+    def __repr__(self):
+        return 'AnisotropicLayer(d={}, n={}, mua={}, mus={}, pf={})'.format(
+            self.d, self.n, self._mua, self._mus, self.pf)
+
+
 class Layers(McObject):
     """Stack of layers; the first and last describe the surrounding medium."""
 
@@ -73,6 +166,15 @@ class Layers(McObject):
         if any(type(l.pf) is not pf_type for l in self._layers):
             raise ValueError('All the layers must use the same scattering '
                              'phase function model!')
+        layer_type = type(self._layers[0])
+        for l in self._layers:
+            if not isinstance(l, (Layer, AnisotropicLayer)):
+                raise TypeError('All the sample layers must be instances of Layer or '
+                                'AnisotropicLayer but found {:s}!'.format(type(l).__name__))
+            if type(l) is not layer_type:
+                raise TypeError('All the sample layers must use the same type!'
+                                'Found {} and {}!'.format(layer_type.__name__,
+                                                          type(l).__name__))
 
     def cl_type(self, mc):
         return self._layers[0].fetch_cl_type(mc)*len(self._layers)

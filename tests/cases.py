@@ -1073,3 +1073,30 @@ def bench_geometry(name):
 # packets = work-items (one packet per MWC stream) of tests/golden/traj_<case>.npz
 TRAJ_RUN = {'mcml_lut_iso_radialpl_trace': 512, 'mcvox_line_mhg_trace': 512,
             'mccyl_gk_ubeam_fiz_trace': 512, 'c4_trace': 192}
+
+
+# ---------------------------------------------------------------------------
+# anisotropic layers (mcml/mclayer/layer.py:391-790): absorption / scattering tensors
+# projected on the propagation direction
+def mcml_aniso_line_cart_flu(mc, **kw):
+    Axis = mc.mcdetector.Axis
+    L = mc.mclayer.AnisotropicLayer
+    pf = mc.mcpf.Hg(0.8)
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=1e-3, n=1.33, mua=[1e2, 2e2, 0.5e2],
+          mus=np.array([[100e2, 10e2, 0.0], [10e2, 60e2, 5e2], [0.0, 5e2, 150e2]]), pf=pf),
+        L(d=2e-3, n=1.4, mua=0.5e2, mus=[50e2, 80e2, 30e2], pf=pf),
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf)])
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.Cartesian(Axis(-2e-3, 2e-3, 40)), bottom=mc.mcdetector.Total(),
+        specular=mc.mcdetector.Total())
+    flu = mc.mcfluence.Fluence(Axis(-1e-3, 1e-3, 20), Axis(-1e-3, 1e-3, 20),
+                               Axis(0, 3e-3, 30), mode='deposition')
+    return mc.Mc(layers, mc.mcsource.Line((0.0, 0.0, 0.0), (0.2, 0.1, 1.0)), det,
+                 fluence=flu, rnginit=99, **kw), dict(rmax=20e-3)
+
+
+ALL_CASES['mcml_aniso_line_cart_flu'] = mcml_aniso_line_cart_flu
+GEOMETRY['mcml_aniso_line_cart_flu'] = 'mcml'
+GOLDEN_RUN['mcml_aniso_line_cart_flu'] = (2000, 16)

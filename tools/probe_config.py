@@ -1,4 +1,5 @@
-"""Developer timing probe: python tools/qb.py config n [wgsize]"""
+"""Developer timing probe of one bench configuration (also the process ncu profiles,
+tools/gpu_ncu.sh): python tools/probe_config.py config n [wgsize]"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import benchcfg
@@ -6,6 +7,10 @@ import importlib
 name = sys.argv[1]; n = int(float(sys.argv[2]))
 kw = {'wgsize': int(sys.argv[3])} if len(sys.argv) > 3 else {}
 mc = importlib.import_module("pyxopto_b200.%s.mc" % benchcfg.GEOMETRY[name]); sim = benchcfg.CONFIGS[name](mc)
+if os.environ.get('XO_REFILL'):
+    sim.refill_lanes = int(os.environ['XO_REFILL'])
+if os.environ.get('XO_MIN_BLOCKS'):
+    sim.min_blocks = int(os.environ['XO_MIN_BLOCKS'])
 sim.run(10000, download=False, **kw)
 for i in range(3):
     sim.run(n, download=False, **kw)
