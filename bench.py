@@ -233,7 +233,7 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
             sim.run(packets, download=False)
             rr = dict(sim.run_report)
             sim.filter_trace_on_device(packets, download=False)
-            sim.sampling_volume(None, benchcfg.c4_sampling_volume(mc), download=False)
+            sim.sampling_volume(None, benchcfg.SAMPLING_VOLUMES[config](mc), download=False)
             sv_ms.append(sim.run_report['sv_kernel_ms'] + sim.run_report['filter_ms'])
             return rr
 
@@ -243,7 +243,7 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
         # sums) and reaches the host once, when `sv.data` is read after the last batch
         # (inside the timed region, see `finish_e2e`)
         sim.lazy_sampling_volume = True
-        sv_acc = [benchcfg.c4_sampling_volume(mc)]
+        sv_acc = [benchcfg.SAMPLING_VOLUMES[config](mc)]
 
         trace_d2h = {}
 
@@ -257,10 +257,10 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
 
         def finish_e2e():
             total = float(sv_acc[0].data.sum())
-            sv_acc[0] = benchcfg.c4_sampling_volume(mc)
+            sv_acc[0] = benchcfg.SAMPLING_VOLUMES[config](mc)
             return total
     elif n_sweep:
-        # a pipelined sweep over (mua, musr): configurations dealt round-robin to the
+        # a pipelined sweep over (mua, musr): configurations dealt by a fixed pseudo-random permutation to the
         # ranks, no collective on the data path, one gather of the rows in e2e
         from pyxopto_b200 import mcsweep
         grid_cfgs = benchcfg.validate_grid() if config == 'validate_uniformfiber' \
@@ -475,7 +475,7 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
             'workload': WORKLOADS.get(config, config), 'packets_per_gpu_per_step': per_step,
             'global_packets_per_step': per_step*world,
             'sweep_configs_per_gpu_per_step': n_sweep or None,
-            'parallelism': ('{} configurations per GPU dealt round-robin over {} GPU(s), no '
+            'parallelism': ('{} configurations per GPU dealt by a fixed permutation over {} GPU(s), no '
                             'collective on the data path'.format(n_sweep, world) if n_sweep else
                             'packets sharded over {} GPU(s), disjoint MWC seed sets{}'.format(
                                 world, ', 1 stream-ordered NCCL all-reduce of the uint64 '

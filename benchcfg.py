@@ -175,6 +175,42 @@ OPS_PER_ITERATION['c4_trace'] = (91, 11)
 TRACE_BYTES_PER_ITERATION = 32
 
 
+def c4_trace_vox(mc, rnginit=RNGINIT, maxlen=512, **kw):
+    """BASELINE configs[3] on the voxel geometry ("time-resolved mcml/mcvox"): the C3
+    medium (201^3 voxels of 5 um, 2-layer skin + vessel), Line source, path-length
+    resolved RadialPl reflectance, full Trace of every packet (maxlen 512, one event
+    per loop trip = voxel crossing or interaction, like the reference) with a
+    terminal-event filter (top surface, 100-400 um from the source, within 30 deg of
+    the normal), then ``sampling_volume`` on a 200^3 grid over the voxel box."""
+    sim = c3_vox(mc, rnginit=rnginit, **kw)
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.RadialPl(Axis(0.0, 0.5e-3, 100), plaxis=Axis(0.0, 0.03, 300)))
+    flt = mc.mctrace.Filter(z=(-float('inf'), 0.0), r=(100e-6, 400e-6, (0.0, 0.0)),
+                            pz=(-1.0, -float(np.cos(np.deg2rad(30.0)))))
+    tr = mc.mctrace.Trace(maxlen=maxlen, options=mc.mctrace.Trace.TRACE_ALL, plon=True,
+                          filter=flt)
+    vox, mats = sim.voxels, sim.materials
+    material = np.array(sim.voxels.material, copy=True)
+    sim2 = mc.Mc(vox, mats, mc.mcsource.Line(), det, trace=tr, rnginit=rnginit, **kw)
+    sim2.rmax = 25e-3
+    sim2.voxels.material[:] = material
+    return sim2
+
+
+def c4_sampling_volume_vox(mc):
+    A = mc.mcsv.Axis
+    half = 201/2*5e-6
+    return mc.mcsv.SamplingVolume(A(-half, half, 200), A(-half, half, 200), A(0.0, 2*half, 200))
+
+
+CONFIGS['c4_trace_vox'] = c4_trace_vox
+GEOMETRY['c4_trace_vox'] = 'mcvox'
+PACKETS['c4_trace_vox'] = 2*10**5
+OPS_PER_ITERATION['c4_trace_vox'] = (83, 5.5)
+SAMPLING_VOLUMES = {'c4_trace': c4_sampling_volume, 'c4_trace_vox': c4_sampling_volume_vox}
+
+
 def c5_slab(mc, rnginit=RNGINIT, mua=1e2, musr=20e2, **kw):
     """BASELINE configs[4], mcml variant: semi-infinite water
     (n = 1.337) under air, Line source, Radial(0..5 mm, 500 bins) reflectance,

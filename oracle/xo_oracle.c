@@ -63,8 +63,15 @@ typedef struct {
 typedef struct {
 	float r_inner, r_outer, n, cc_inner, cc_outer, mus, mua, inv_mut, mua_inv_mut;
 } cyl_layer;
+/* mccyl/mclayer/layer.py:477-491 (AnisotropicLayer) */
+typedef struct {
+	float r_inner, r_outer, n, cc_inner, cc_outer;
+	m3f mus, mua, mut;
+} cyl_aniso_layer;
 /* mcbase/mcmaterial.py:52-62 */
 typedef struct { float n, mus, mua, inv_mut, mua_inv_mut; } vox_material;
+/* mcbase/mcmaterial.py:330-341 (AnisotropicMaterial) */
+typedef struct { float n; m3f mus, mua, mut; } vox_aniso_material;
 /* mcvox/mcgeometry/voxel.py:96-121 */
 typedef struct { p3f top_left, bottom_right, size; int32_t nx, ny, nz; } vox_cfg;
 
@@ -326,8 +333,10 @@ static inline size_t layer_stride(const xo_oracle_job *j) {
 	switch (j->geometry) {
 		case XO_GEOM_MCML: return (j->anisotropic ? sizeof(ml_aniso_layer) : sizeof(ml_layer)) +
 			(size_t)j->pf_size;
-		case XO_GEOM_MCCYL: return sizeof(cyl_layer) + (size_t)j->pf_size;
-		default: return sizeof(vox_material) + (size_t)j->pf_size;
+		case XO_GEOM_MCCYL: return (j->anisotropic ? sizeof(cyl_aniso_layer) : sizeof(cyl_layer)) +
+			(size_t)j->pf_size;
+		default: return (j->anisotropic ? sizeof(vox_aniso_material) : sizeof(vox_material)) +
+			(size_t)j->pf_size;
 	}
 }
 static inline const ml_layer *ml_layer_at(const xo_oracle_job *j, int32_t i) {
@@ -352,45 +361,59 @@ static inline float medium_n(const xo_oracle_job *j, int32_t i) {
 		default: return vox_material_at(j, i)->n;
 	}
 }
-static inline void medium_props(const sim_t *s, float *mus, float *mua,
-		float *inv_mut, float *mua_inv_mut, float *n) {
-	const xo_oracle_job *j = s->job;
-	switch (j->geometry) {
-		case XO_GEOM_MCML: { const ml_layer *l = ml_layer_at(j, s->layer_index);
-			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
-		case XO_GEOM_MCCYL: { const cyl_layer *l = cyl_layer_at(j, s->layer_index);
-			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
-		default: { const vox_material *l = vox_material_at(j, s->layer_index);
-			*mus = l->mus; *mua = l->mua; *inv_mut = l->inv_mut; *mua_inv_mut = l->mua_inv_mut; *n = l->n; break; }
-	}
-}
-
 /* mcbase.template.h:2227-2230 tensor3f_project: p T p' */
 static inline float tensor_project(const m3f *T, const p3f *p) {
 	return p->x*(T->a11*p->x + T->a12*p->y + T->a13*p->z) +
 		p->y*(T->a21*p->x + T->a22*p->y + T->a23*p->z) +
 		p->z*(T->a31*p->x + T->a32*p->y + T->a33*p->z);
 }
-/* optical properties of an mcml layer along the propagation direction:
- * mclayer/layer.py:153-216 (Layer: packed scalars) and :497-551 (AnisotropicLayer:
- * projected tensors, mc_layer_inv_mut / mc_layer_mua_inv_mut) */
-static inline float ml_mus(const sim_t *s, const ml_layer *L) {
-	return s->job->anisotropic ? tensor_project(&((const ml_aniso_layer *)L)->mus, &s->dir) : L->mus;
+/* Optical properties of the current medium along the propagation direction.  Isotropic
+ * media: the packed scalars (mclayer/layer.py:153-216, mcmaterial.py:94-134); anisotropic
+ * media: the projected tensors with the reference's guards (mc_layer_inv_mut /
+ * mc_layer_mua_inv_mut, mclayer/layer.py:497-551; mc_material_*, mcmaterial.py:390-455) */
+typedef struct { float mus, mua, inv_mut, mua_inv_mut; } medium_scalars;
+static inline void aniso_tensors(const sim_t *s, const void *medium,
+		const m3f **mus, const m3f **mua, const m3f **mut) {
+	switch (s->job->geometry) {
+		case XO_GEOM_MCML: { const ml_aniso_layer *L = (const ml_aniso_layer *)medium;
+			*mus = &L->mus; *mua = &L->mua; *mut = &L->mut; break; }
+		case XO_GEOM_MCCYL: { const cyl_aniso_layer *L = (const cyl_aniso_layer *)medium;
+			*mus = &L->mus; *mua = &L->mua; *mut = &L->mut; break; }
+		default: { const vox_aniso_material *M = (const vox_aniso_material *)medium;
+			*mus = &M->mus; *mua = &M->mua; *mut = &M->mut; break; }
+	}
 }
-static inline float ml_mua(const sim_t *s, const ml_layer *L) {
-	return s->job->anisotropic ? tensor_project(&((const ml_aniso_layer *)L)->mua, &s->dir) : L->mua;
+static inline float aniso_mus(const sim_t *s, const void *medium) {
+	const m3f *mus, *mua, *mut; aniso_tensors(s, medium, &mus, &mua, &mut);
+	return tensor_project(mus, &s->dir);
 }
-static inline float ml_inv_mut(const sim_t *s, const ml_layer *L) {
-	if (!s->job->anisotropic) return L->inv_mut;
-	float mut = tensor_project(&((const ml_aniso_layer *)L)->mut, &s->dir);
-	return (mut != FP_0) ? m_div(FP_1, mut) : INFINITY;
+static inline float aniso_mua(const sim_t *s, const void *medium) {
+	const m3f *mus, *mua, *mut; aniso_tensors(s, medium, &mus, &mua, &mut);
+	return tensor_project(mua, &s->dir);
 }
-static inline float ml_mua_inv_mut(const sim_t *s, const ml_layer *L) {
-	if (!s->job->anisotropic) return L->mua_inv_mut;
-	float mua = tensor_project(&((const ml_aniso_layer *)L)->mua, &s->dir);
-	float mut = tensor_project(&((const ml_aniso_layer *)L)->mut, &s->dir);
-	return (mua != FP_0) ? ((mut != FP_0) ? m_div(mua, mut) : INFINITY) : FP_0;
+static inline float aniso_inv_mut(const sim_t *s, const void *medium) {
+	const m3f *mus, *mua, *mut; aniso_tensors(s, medium, &mus, &mua, &mut);
+	float m = tensor_project(mut, &s->dir);
+	return (m != FP_0) ? m_div(FP_1, m) : INFINITY;
 }
+static inline float aniso_mua_inv_mut(const sim_t *s, const void *medium) {
+	const m3f *mus, *mua, *mut; aniso_tensors(s, medium, &mus, &mua, &mut);
+	float a = tensor_project(mua, &s->dir);
+	float m = tensor_project(mut, &s->dir);
+	return (a != FP_0) ? ((m != FP_0) ? m_div(a, m) : INFINITY) : FP_0;
+}
+#define MEDIUM_ACCESSORS(prefix, type) \
+	static inline float prefix##_mus(const sim_t *s, const type *L) { \
+		return s->job->anisotropic ? aniso_mus(s, L) : L->mus; } \
+	static inline float prefix##_mua(const sim_t *s, const type *L) { \
+		return s->job->anisotropic ? aniso_mua(s, L) : L->mua; } \
+	static inline float prefix##_inv_mut(const sim_t *s, const type *L) { \
+		return s->job->anisotropic ? aniso_inv_mut(s, L) : L->inv_mut; } \
+	static inline float prefix##_mua_inv_mut(const sim_t *s, const type *L) { \
+		return s->job->anisotropic ? aniso_mua_inv_mut(s, L) : L->mua_inv_mut; }
+MEDIUM_ACCESSORS(ml, ml_layer)
+MEDIUM_ACCESSORS(cyl, cyl_layer)
+MEDIUM_ACCESSORS(vox, vox_material)
 
 /* ---- phase functions ------------------------------------------------------- */
 static float pf_sample_angles(sim_t *s, float *azimuth) {

@@ -39,10 +39,37 @@
 
 namespace xo {
 
+#ifndef XO_ANISO
+#define XO_ANISO 0
+#endif
+#if XO_ANISO
+// AnisotropicLayer (mccyl/mclayer/layer.py:477-491): coefficient tensors projected on
+// the propagation direction
+struct CylLayer {
+	float r_inner, r_outer, n, cc_inner, cc_outer;
+	M3 mus_t, mua_t, mut_t;
+	XoPf pf;
+	__device__ __forceinline__ float mus_at(const P3 &d) const { return tensor_project(mus_t, d); }
+	__device__ __forceinline__ float mua_at(const P3 &d) const { return tensor_project(mua_t, d); }
+	__device__ __forceinline__ float inv_mut_at(const P3 &d) const {
+		const float mut = tensor_project(mut_t, d);
+		return (mut != 0.0f) ? M::div(1.0f, mut) : XO_INF;
+	}
+	__device__ __forceinline__ float mua_inv_mut_at(const P3 &d) const {
+		const float mua = tensor_project(mua_t, d), mut = tensor_project(mut_t, d);
+		return (mua != 0.0f) ? ((mut != 0.0f) ? M::div(mua, mut) : XO_INF) : 0.0f;
+	}
+};
+#else
 struct CylLayer {                   // mccyl/mclayer/layer.py:119-130
 	float r_inner, r_outer, n, cc_inner, cc_outer, mus, mua, inv_mut, mua_inv_mut;
 	XoPf pf;
+	__device__ __forceinline__ float mus_at(const P3 &) const { return mus; }
+	__device__ __forceinline__ float mua_at(const P3 &) const { return mua; }
+	__device__ __forceinline__ float inv_mut_at(const P3 &) const { return inv_mut; }
+	__device__ __forceinline__ float mua_inv_mut_at(const P3 &) const { return mua_inv_mut; }
 };
+#endif
 
 // Per-layer records of the throughput loop, derived once per CTA when the medium
 // is staged in shared memory; the record of the *current* layer is cached in
@@ -154,9 +181,15 @@ McKernel(
 		const CylLayer &Lg = layers[i];
 		CylFastLayer F;
 		F.hot.ri2 = Lg.r_inner*Lg.r_inner; F.hot.ro2 = Lg.r_outer*Lg.r_outer;
+#if XO_ANISO
+		F.hot.step_k = 0.0f; F.hot.step_b = 0.0f;       // per direction (XO_DIR_CONSTS)
+		F.abs.absorb = 0.0f; F.abs.mua = 0.0f;
+#else
 		F.hot.step_k = -0.6931471805599453f*Lg.inv_mut;
 		F.hot.step_b = -32.0f*F.hot.step_k;
-		F.abs.absorb = Lg.mua_inv_mut; F.abs.mua = Lg.mua; F.abs.n = Lg.n; F.abs.pad = 0.0f;
+		F.abs.absorb = Lg.mua_inv_mut; F.abs.mua = Lg.mua;
+#endif
+		F.abs.n = Lg.n; F.abs.pad = 0.0f;
 		Lg.pf.prepare(F.pf.v);
 		sh_fast[i] = F;
 	}
@@ -214,9 +247,24 @@ McKernel(
 		CylHot c_hot = { 0.0f, 0.0f, 0.0f, 0.0f };
 		CylAbs c_abs = { 0.0f, 0.0f, 1.0f, 0.0f };
 		XoPf::Fast c_pf;
+#if XO_ANISO
+	// anisotropic layers: step / absorption constants of a (layer, direction) pair
+#define XO_DIR_CONSTS() do { \
+		const CylLayer &L_ = sh_layers[layer]; \
+		const float mut_ = tensor_project(L_.mut_t, dir), mua_ = tensor_project(L_.mua_t, dir); \
+		const float inv_ = (mut_ != 0.0f) ? FastMath::rcp_approx(mut_) : XO_INF; \
+		c_hot.step_k = -0.6931471805599453f*inv_; \
+		c_hot.step_b = -32.0f*c_hot.step_k; \
+		c_abs.absorb = (mua_ != 0.0f) ? mua_*inv_ : 0.0f; \
+		c_abs.mua = mua_; \
+	} while (0)
+#else
+#define XO_DIR_CONSTS() do { } while (0)
+#endif
 #define XO_CYL_LOAD_LAYER(idx) do { \
 		const CylFastLayer &F_ = sh_fast[idx]; \
 		c_hot = F_.hot; c_abs = F_.abs; c_pf = F_.pf.v; \
+		XO_DIR_CONSTS(); \
 	} while (0)
 
 #define XO_CYL_END_TRIP() do { \
@@ -343,6 +391,7 @@ McKernel(
 			} else {
 				pf_scatter(c_pf, rng, lut, dir);
 				flags |= EV_SCATTERING;
+				XO_DIR_CONSTS();
 			}
 #else
 			{
@@ -353,6 +402,7 @@ McKernel(
 			}
 			pf_scatter(c_pf, rng, lut, dir);
 			flags |= EV_SCATTERING;
+			XO_DIR_CONSTS();
 			if (weight < XO_WEIGHT_MIN) {
 #if XO_USE_LOTTERY
 				if (rng.next_raw() > XO_LOTTERY_CHANCE*4294967296.0f) done = true;
@@ -366,6 +416,7 @@ McKernel(
 		}
 #undef XO_CYL_END_TRIP
 #undef XO_CYL_LOAD_LAYER
+#undef XO_DIR_CONSTS
 		rng_state_x[gid] = rng.state();
 	}
 #else
@@ -416,7 +467,7 @@ McKernel(
 #endif
 			const CylLayer &L = sh_layers[layer];
 			++iterations;
-			float step = -M::log(rng.next())*L.inv_mut;
+			float step = -M::log(rng.next())*L.inv_mut_at(dir);
 			step = fminf(step, XO_FLT_MAX);
 			i32 next_layer = layer;
 			if (dir.x != 0.0f || dir.y != 0.0f) {
@@ -459,22 +510,22 @@ McKernel(
 				}
 			} else {
 #if XO_METHOD == 1
-				if (rng.next() < L.mua_inv_mut) {
+				if (rng.next() < L.mua_inv_mut_at(dir)) {
 					float deposit = weight;
 					done = true;
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
-					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua_at(dir), opl);
 				} else {
 					pf_scatter(L.pf, rng, lut, dir);
 					flags |= EV_SCATTERING;
 				}
 #else
 				{
-					float deposit = weight*L.mua_inv_mut;
+					float deposit = weight*L.mua_inv_mut_at(dir);
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
-					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, L.mua_at(dir), opl);
 				}
 				pf_scatter(L.pf, rng, lut, dir);
 				flags |= EV_SCATTERING;

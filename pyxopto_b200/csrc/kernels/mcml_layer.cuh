@@ -12,13 +12,6 @@ namespace xo {
 #define XO_ANISO 0
 #endif
 
-// p T p' (mcbase.template.h:2227-2230), the reference's association
-__device__ __forceinline__ float tensor_project(const M3 &T, const P3 &p) {
-	return p.x*(T.a11*p.x + T.a12*p.y + T.a13*p.z) +
-		p.y*(T.a21*p.x + T.a22*p.y + T.a23*p.z) +
-		p.z*(T.a31*p.x + T.a32*p.y + T.a33*p.z);
-}
-
 #if XO_ANISO
 // AnisotropicLayer (mcml/mclayer/layer.py:412-424): the coefficients seen by a packet
 // are the tensors projected on its propagation direction (:497-551)

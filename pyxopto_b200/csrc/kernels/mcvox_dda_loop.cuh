@@ -73,6 +73,20 @@
 	VoxHot c_hot = { 0.0f, 0.0f, 0.0f, 1.0f };
 	XoPf::Fast c_pf;
 #define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
+#if XO_ANISO
+	// anisotropic materials: step / absorption constants of a ray = the tensors projected
+	// on its direction, derived when the ray is set up
+#define XO_DIR_CONSTS() do { \
+		const VoxMaterial &M_ = sh_mat[mat]; \
+		const float mut_ = tensor_project(M_.mut_t, dir), mua_ = tensor_project(M_.mua_t, dir); \
+		const float inv_ = (mut_ != 0.0f) ? FastMath::rcp_approx(mut_) : XO_INF; \
+		c_hot.step_k = -0.6931471805599453f*inv_; \
+		c_hot.absorb = (mua_ != 0.0f) ? mua_*inv_ : 0.0f; \
+		c_hot.mua = mua_; \
+	} while (0)
+#else
+#define XO_DIR_CONSTS() do { } while (0)
+#endif
 #define XO_VOXEL(lo) ((u32)__ldg(reinterpret_cast<const unsigned char *>(((u64)vbase_hi << 32) | (u64)(lo))))
 #if XO_USE_RMAX
 #define XO_RMAX_TEST() do { \
@@ -252,6 +266,7 @@
 
 		// ---- new ray from `pos` along `dir` in voxel (ix, iy, iz) -----------------------
 		if (state == ST_SETUP) {
+			XO_DIR_CONSTS();
 			const float rx = FastMath::rcp_approx(dir.x), ry = FastMath::rcp_approx(dir.y),
 				rz = FastMath::rcp_approx(dir.z);
 			const bool fx = dir.x >= 0.0f, fy = dir.y >= 0.0f, fz = dir.z >= 0.0f;
@@ -360,6 +375,7 @@
 		}
 	}
 #undef XO_LOAD_MAT
+#undef XO_DIR_CONSTS
 #undef XO_VOXEL
 #undef XO_RMAX_TEST
 #undef XO_TRACE_TRIP

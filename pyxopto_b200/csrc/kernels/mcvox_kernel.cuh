@@ -18,10 +18,37 @@
 
 namespace xo {
 
+#ifndef XO_ANISO
+#define XO_ANISO 0
+#endif
+#if XO_ANISO
+// AnisotropicMaterial (mcbase/mcmaterial.py:330-341): coefficient tensors projected on
+// the propagation direction (:390-455)
+struct VoxMaterial {
+	float n;
+	M3 mus_t, mua_t, mut_t;
+	XoPf pf;
+	__device__ __forceinline__ float mus_at(const P3 &d) const { return tensor_project(mus_t, d); }
+	__device__ __forceinline__ float mua_at(const P3 &d) const { return tensor_project(mua_t, d); }
+	__device__ __forceinline__ float inv_mut_at(const P3 &d) const {
+		const float mut = tensor_project(mut_t, d);
+		return (mut != 0.0f) ? M::div(1.0f, mut) : XO_INF;
+	}
+	__device__ __forceinline__ float mua_inv_mut_at(const P3 &d) const {
+		const float mua = tensor_project(mua_t, d), mut = tensor_project(mut_t, d);
+		return (mua != 0.0f) ? ((mut != 0.0f) ? M::div(mua, mut) : XO_INF) : 0.0f;
+	}
+};
+#else
 struct VoxMaterial {                // mcbase/mcmaterial.py:52-62
 	float n, mus, mua, inv_mut, mua_inv_mut;
 	XoPf pf;
+	__device__ __forceinline__ float mus_at(const P3 &) const { return mus; }
+	__device__ __forceinline__ float mua_at(const P3 &) const { return mua; }
+	__device__ __forceinline__ float inv_mut_at(const P3 &) const { return inv_mut; }
+	__device__ __forceinline__ float mua_inv_mut_at(const P3 &) const { return mua_inv_mut; }
 };
+#endif
 struct VoxCfg {                     // mcvox/mcgeometry/voxel.py:96-121
 	P3 top_left, bottom_right, size;
 	i32 nx, ny, nz;
@@ -156,9 +183,13 @@ McKernel(
 	for (u32 i = threadIdx.x; i < num_materials; i += blockDim.x) {
 		const VoxMaterial &Mg = materials[i];
 		VoxFastMat F;
+#if XO_ANISO
+		F.hot.step_k = 0.0f; F.hot.absorb = 0.0f; F.hot.mua = 0.0f;   // per ray (XO_DIR_CONSTS)
+#else
 		F.hot.step_k = -0.6931471805599453f*Mg.inv_mut;
 		F.hot.absorb = Mg.mua_inv_mut;
 		F.hot.mua = Mg.mua;
+#endif
 		F.hot.n = Mg.n;
 		Mg.pf.prepare(F.pf.v);
 		sh_fast[i] = F;
@@ -253,9 +284,9 @@ McKernel(
 			++iterations;
 			float step;
 #if XO_METHOD == 2
-			step = M::div(-M::log(rng.next()), Mt.mus);
+			step = M::div(-M::log(rng.next()), Mt.mus_at(dir));
 #else
-			step = -M::log(rng.next())*Mt.inv_mut;
+			step = -M::log(rng.next())*Mt.inv_mut_at(dir);
 #endif
 			step = fminf(step, XO_FLT_MAX);
 			// distances to the exit faces of the current voxel (mcvox.template.c:173-196)
@@ -274,7 +305,7 @@ McKernel(
 
 #if XO_METHOD == 2
 			{
-				float mua = Mt.mua;
+				float mua = Mt.mua_at(dir);
 				float frac = 1.0f - M::exp(-mua*d_ok);
 				float deposit = frac*weight;
 				weight -= deposit;
@@ -336,12 +367,12 @@ McKernel(
 				}
 			} else {
 #if XO_METHOD == 1
-				if (rng.next() < Mt.mua_inv_mut) {
+				if (rng.next() < Mt.mua_inv_mut_at(dir)) {
 					float deposit = weight;
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
 					done = true;
-					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua_at(dir), opl);
 				} else {
 					pf_scatter(Mt.pf, rng, lut, dir);
 					flags |= EV_SCATTERING;
@@ -349,10 +380,10 @@ McKernel(
 #else
 #if XO_METHOD == 0
 				{
-					float deposit = weight*Mt.mua_inv_mut;
+					float deposit = weight*Mt.mua_inv_mut_at(dir);
 					weight -= deposit;
 					flags |= EV_ABSORPTION;
-					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua, opl);
+					if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, Mt.mua_at(dir), opl);
 				}
 #endif
 				pf_scatter(Mt.pf, rng, lut, dir);

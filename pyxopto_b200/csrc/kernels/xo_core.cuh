@@ -58,6 +58,13 @@ __device__ __forceinline__ float dot3(const P3 &a, const P3 &b) {
 	return a.x*b.x + a.y*b.y + a.z*b.z;
 #endif
 }
+// p T p' (mcbase.template.h:2227-2230), the reference's association
+__device__ __forceinline__ float tensor_project(const M3 &T, const P3 &p) {
+	return p.x*(T.a11*p.x + T.a12*p.y + T.a13*p.z) +
+		p.y*(T.a21*p.x + T.a22*p.y + T.a23*p.z) +
+		p.z*(T.a31*p.x + T.a32*p.y + T.a33*p.z);
+}
+
 __device__ __forceinline__ P3 transform3(const M3 &m, const P3 &v) {
 	P3 r;
 	r.x = m.a11*v.x + m.a12*v.y + m.a13*v.z;

@@ -79,6 +79,10 @@ class Mc(McBase):
             out.append((Name, det.fetch_cu_type(self), det.fetch_cl_type(self)))
         return out
 
+    def _extra_defines(self, opts):
+        aniso = isinstance(self._layers[1], mclayer.AnisotropicLayer)
+        return ['#define XO_ANISO {}'.format(int(aniso))]
+
     def _plugin_bindings(self):
         pf = self._layers[1].pf
         out = [('XoPf', pf.fetch_cu_type(self), pf.fetch_cl_type(self)),

@@ -7,6 +7,7 @@ from typing import Tuple
 from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import boundary
+from ..mcbase.mcmaterial import optical_tensor as _tensor
 
 
 def ray_cylinder_intersection(r: float, pos, dir) -> Tuple[float, float]:
@@ -74,6 +75,69 @@ class Layer(McObject):
             self.d, self.n, self.mua, self.mus, self.pf)
 
 
+class AnisotropicLayer(McObject):
+    """Concentric layer with absorption / scattering tensors projected on the
+    propagation direction (layer.py:455-760)."""
+    cu_type = 'xo::CylLayer'
+
+    @staticmethod
+    def layer_type(mc, pf_type):
+        T = mc.types
+        class ClAnisotropicLayer(cltypes.Structure):
+            _fields_ = [
+                ('r_inner', T.mc_fp_t), ('r_outer', T.mc_fp_t), ('n', T.mc_fp_t),
+                ('cos_critical_inner', T.mc_fp_t), ('cos_critical_outer', T.mc_fp_t),
+                ('mus', T.mc_matrix3f_t), ('mua', T.mc_matrix3f_t),
+                ('mut', T.mc_matrix3f_t), ('pf', pf_type)]
+        return ClAnisotropicLayer
+
+    def cl_type(self, mc):
+        return self.layer_type(mc, self.pf.fetch_cl_type(mc))
+
+    def __init__(self, d: float, n: float, mua, mus, pf):
+        super().__init__()
+        self.d, self.n = float(d), float(n)
+        self._mua, self._mus = _tensor(mua), _tensor(mus)
+        self._pf = pf
+
+    def _set_mua(self, mua):
+        self._mua = _tensor(mua)
+
+    def _set_mus(self, mus):
+        self._mus = _tensor(mus)
+
+    mua = property(lambda self: self._mua, _set_mua, None,
+                   'Absorption coefficient tensor (3x3) of the layer (1/m).')
+    mus = property(lambda self: self._mus, _set_mus, None,
+                   'Scattering coefficient tensor (3x3) of the layer (1/m).')
+
+    def _set_pf(self, pf):
+        if type(self._pf) is not type(pf):
+            raise ValueError('The scattering phase function type '
+                             'of the layer must not change!')
+        self._pf = pf
+
+    pf = property(lambda self: self._pf, _set_pf, None, 'Phase function object.')
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        target.n = self.n
+        target.mua.fromarray(self._mua)
+        target.mus.fromarray(self._mus)
+        target.mut.fromarray(self._mua + self._mus)
+        self.pf.cl_pack(mc, target.pf)
+        return target
+
+    def todict(self):
+        return {'d': self.d, 'n': self.n, 'mua': self._mua.tolist(), 'mus': self._mus.tolist(),
+                'pf': self.pf.todict(), 'type': 'AnisotropicLayer'}
+
+    def __repr__(self):
+        return 'AnisotropicLayer(d={}, n={}, mua={}, mus={}, pf={})'.format(
+            self.d, self.n, self._mua, self._mus, self.pf)
+
+
 class Layers(McObject):
     def __init__(self, layers):
         super().__init__()
@@ -87,10 +151,13 @@ class Layers(McObject):
             raise ValueError('At least two layers are required, '
                              'but got only {:d}!'.format(len(self._layers)))
         pf_type = type(self._layers[1].pf)
+        layer_type = type(self._layers[0])
         for layer in self._layers:
-            if not isinstance(layer, Layer):
-                raise TypeError('All layers must be instances of Layer '
+            if not isinstance(layer, (Layer, AnisotropicLayer)):
+                raise TypeError('All layers must be instances of Layer or AnisotropicLayer '
                                 'but found {:s}!'.format(type(layer).__name__))
+            if type(layer) is not layer_type:
+                raise TypeError('All the sample layers must use the same type!')
             if type(layer.pf) is not pf_type:
                 raise TypeError('All the sample layer must use the same scattering '
                                 'phase function model!')

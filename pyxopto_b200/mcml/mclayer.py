@@ -1,9 +1,8 @@
 """Layer stack of the planar simulator (mirror of ``xopto/mcml/mclayer/layer.py``)."""
-import numpy as np
-
 from ..cl import cltypes
 from ..mcbase.mcobject import McObject
 from ..mcbase.mcutil import boundary
+from ..mcbase.mcmaterial import optical_tensor as _tensor
 
 
 class Layer(McObject):
@@ -58,21 +57,6 @@ class Layer(McObject):
     def __repr__(self):
         return 'Layer(d={}, n={}, mua={}, mus={}, pf={})'.format(
             self.d, self.n, self.mua, self.mus, self.pf)
-
-
-def _tensor(value) -> np.ndarray:
-    """3 x 3 tensor from a scalar (isotropic), 3 diagonal elements or a full
-    matrix (layer.py:662-708)."""
-    t = np.zeros((3, 3))
-    if isinstance(value, (float, int)):
-        t[0, 0] = t[1, 1] = t[2, 2] = value
-    else:
-        value = np.asarray(value, dtype=float)
-        if value.size == 3:
-            t[0, 0], t[1, 1], t[2, 2] = value.ravel()
-        else:
-            t[:] = value
-    return t
 
 
 class AnisotropicLayer(McObject):

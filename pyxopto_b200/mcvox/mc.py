@@ -122,7 +122,9 @@ class Mc(McBase):
         return len(self._materials) <= self.VOX_SENTINEL and sum(self._vox_pack_bits()) <= 31
 
     def _extra_defines(self, opts):
-        return ['#define XO_VOX_PACKED {}'.format(int(self._vox_packed()))]
+        aniso = isinstance(self._materials[0], mcmaterial.AnisotropicMaterial)
+        return ['#define XO_VOX_PACKED {}'.format(int(self._vox_packed())),
+                '#define XO_ANISO {}'.format(int(aniso))]
 
     def _upload_medium(self):
         self.cl_r_buffer('materials', self._packed['materials'])

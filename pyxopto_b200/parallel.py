@@ -103,7 +103,7 @@ class NcclAccumulatorReducer:
         return t
 
     def _stream(self, sim):
-        native = sim._stream.native()
+        native = sim._stream.native
         ext = self._streams.get(native)
         if ext is None:
             ext = self.torch.cuda.ExternalStream(native, device=self.device)

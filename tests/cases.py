@@ -1100,3 +1100,54 @@ def mcml_aniso_line_cart_flu(mc, **kw):
 ALL_CASES['mcml_aniso_line_cart_flu'] = mcml_aniso_line_cart_flu
 GEOMETRY['mcml_aniso_line_cart_flu'] = 'mcml'
 GOLDEN_RUN['mcml_aniso_line_cart_flu'] = (2000, 16)
+
+
+def mcvox_aniso_gauss_fluence(mc, **kw):
+    """AnisotropicMaterial (mcbase/mcmaterial.py:310-655) in the voxel geometry."""
+    A = mc.mcgeometry.Axis
+    vox = mc.mcgeometry.Voxels(A(-300e-6, 300e-6, 24), A(-250e-6, 250e-6, 20), A(0.0, 700e-6, 28))
+    M = mc.mcmaterial.AnisotropicMaterial
+    pf = mc.mcpf.Hg(0.8)
+    mats = mc.mcmaterial.Materials([
+        M(n=1.0, mua=0.0, mus=0.0, pf=pf),
+        M(n=1.33, mua=[20e2, 10e2, 5e2],
+          mus=np.array([[300e2, 20e2, 0.0], [20e2, 200e2, 10e2], [0.0, 10e2, 400e2]]), pf=pf),
+        M(n=1.4, mua=8e2, mus=[150e2, 250e2, 100e2], pf=pf)])
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), bottom=mc.mcdetector.Total())
+    sim = mc.Mc(vox, mats, mc.mcsource.GaussianBeam(40e-6), det, fluence=flu,
+                rnginit=4711, **kw)
+    z, y, x = sim.voxels.meshgrid()
+    m = sim.voxels.material
+    m[z <= 200e-6] = 1
+    m[z > 200e-6] = 2
+    m[(x**2 + (z - 350e-6)**2) <= (90e-6)**2] = 1
+    return sim, dict(rmax=5e-3)
+
+
+def mccyl_aniso_line_fiz(mc, **kw):
+    """AnisotropicLayer (mccyl/mclayer/layer.py:455-760) in the cylindrical geometry."""
+    Axis = mc.mcdetector.Axis
+    # (the reference's mccyl.mclayer package does not re-export the class)
+    L = getattr(mc.mclayer, 'AnisotropicLayer', None) or mc.mclayer.layer.AnisotropicLayer
+    pf = mc.mcpf.Hg(0.8)
+    layers = mc.mclayer.Layers([
+        L(d=0.0, n=1.0, mua=0.0, mus=0.0, pf=pf),
+        L(d=6e-3, n=1.33, mua=[1e2, 2e2, 0.5e2],
+          mus=np.array([[100e2, 10e2, 0.0], [10e2, 60e2, 5e2], [0.0, 5e2, 150e2]]), pf=pf),
+        L(d=3e-3, n=1.4, mua=0.5e2, mus=[50e2, 80e2, 30e2], pf=pf)])
+    det = mc.mcdetector.Detectors(
+        outer=mc.mcdetector.FiZ(Axis(-np.pi, np.pi, 16), Axis(-4e-3, 4e-3, 20)),
+        specular=mc.mcdetector.Total())
+    return mc.Mc(layers, mc.mcsource.Line((-8e-3, 0.3e-3, 0.0), (1.0, 0.05, 0.1)), det,
+                 rnginit=1357, **kw), dict(rmax=20e-3)
+
+
+ALL_CASES['mcvox_aniso_gauss_fluence'] = mcvox_aniso_gauss_fluence
+GEOMETRY['mcvox_aniso_gauss_fluence'] = 'mcvox'
+GOLDEN_RUN['mcvox_aniso_gauss_fluence'] = (2000, 16)
+# the reference's mccyl Layers.check() rejects its own AnisotropicLayer
+# (mccyl/mclayer/layer.py:938-941), so no golden vector can exist: CUDA vs oracle only
+UNPINNED_CASES['mccyl_aniso_line_fiz'] = mccyl_aniso_line_fiz
+UNPINNED_GEOMETRY['mccyl_aniso_line_fiz'] = 'mccyl'
+UNPINNED_RUN['mccyl_aniso_line_fiz'] = (1500, 16)

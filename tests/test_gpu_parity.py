@@ -421,6 +421,41 @@ def test_device_trace_filter_equals_host_filter(name):
     assert sv_d.data.sum() > 0
 
 
+@pytest.mark.parametrize('config', ['c4_trace', 'c4_trace_vox'])
+def test_sampling_volume_accumulates_on_the_device(config):
+    """``Mc.lazy_sampling_volume``: one SamplingVolume fed by several batches keeps its
+    integer grid on the device and comes to the host when ``data`` is read.  The
+    result equals the reference flow (one conversion + download per call, summed in
+    float64 on the host) to rounding, the total weight exactly; the grid restarts at
+    zero afterwards."""
+    import importlib
+    import benchcfg
+    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(benchcfg.GEOMETRY[config]))
+    from pyxopto_b200.mcbase import mcoptions
+    n = 20000 if config == 'c4_trace' else 8000
+    results = []
+    for lazy in (True, False):
+        # (deterministic mode: both simulators trace exactly the same packets)
+        sim = benchcfg.CONFIGS[config](mc, maxlen=128, options=[mcoptions.McDeterministic.on])
+        sim.lazy_sampling_volume = lazy
+        sv = benchcfg.SAMPLING_VOLUMES[config](mc)
+        for _ in range(3):
+            trace, _, det = sim.run(n, maxthreads=2048, wgsize=64)
+            assert trace.nphotons > 0
+            out = sim.sampling_volume(trace, sv)
+            assert out is sv
+            assert (sv._pending is not None) == lazy
+        results.append((sim, sv, sv.weight, np.array(sv.data, copy=True)))
+    (sim_l, sv_l, w_l, d_l), (sim_e, sv_e, w_e, d_e) = results
+    assert sv_l._pending is None and sim_l._sv_resident is None
+    assert w_l == w_e and d_l.sum() > 0
+    assert np.allclose(d_l, d_e, rtol=1e-12, atol=0.0)
+    # a second study with the same object continues from the collected data
+    trace, _, _ = sim_l.run(n, maxthreads=2048, wgsize=64)
+    sim_l.sampling_volume(trace, sv_l)
+    assert sv_l.data.sum() > d_l.sum()
+
+
 # ---------------------------------------------------------------------------
 # user-written plugins: OpenCL-C fragments compiled through xo_clcompat*.cuh
 def _raw_run(name, n, threads=256, block=64, deterministic=True):

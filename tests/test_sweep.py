@@ -1,4 +1,4 @@
-"""Config-5 sweeps (pyxopto_b200/mcsweep.py): static round-robin partition (CPU)
+"""Config-5 sweeps (pyxopto_b200/mcsweep.py): static pseudo-random partition (CPU)
 and, on the GPU, the pipelined sweep against one blocking ``Mc.run`` per
 configuration."""
 import numpy as np
@@ -7,7 +7,7 @@ import pytest
 from pyxopto_b200 import mcsweep
 
 
-def test_partition_round_robin_is_disjoint_and_covering():
+def test_partition_is_disjoint_and_covering():
     for n in (0, 1, 7, 4096):
         for world in (1, 2, 3, 8):
             seen = np.concatenate([mcsweep.partition(n, world, r) for r in range(world)])
