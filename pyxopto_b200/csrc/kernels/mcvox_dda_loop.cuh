@@ -28,6 +28,16 @@
 //     it, leaving the grid is a "material change" to the sentinel, and the few
 //     hundred KB around the beam stay L1-resident (the int32 map of the
 //     reference layout is 4x larger and every lookup went to L2).
+//   * every cell of the compact map also carries the CLEARANCE of its voxel: the
+//     chessboard distance (in voxels, capped at 255) to the nearest voxel of another
+//     material or outside the grid.  A flight whose extent along every axis stays
+//     below clearance - 1 voxels cannot leave the material, whatever the start point
+//     inside the voxel: it skips the walk altogether (no DDA set-up, no per-voxel
+//     lookups) and goes straight to its interaction; the loop-trip count of the
+//     reference is restored as the Manhattan distance between the start and the end
+//     voxel (a straight ray is monotone on every axis).  Half of the voxels of the
+//     201^3 skin + vessel model have a clearance above 10 voxels, the mean free path
+//     is 5.4.  Disabled for full traces (one event per crossing is the product there).
 //   * new packets come from a per-warp launch queue filled by all 32 lanes
 //     together (as in mcml_kernel.cuh).
 //   * rmax: the reference tests |pos - source| > rmax after every trip.  A ray
@@ -35,7 +45,8 @@
 //     so the test of a crossing is one compare (compiled out by the host when
 //     the voxel box lies inside the sphere).
 {
-	enum : u32 { ST_RUN = 0, ST_SCAT = 1, ST_BND = 2, ST_SETUP = 3, ST_DEAD = 4, ST_DRY = 5 };
+	enum : u32 { ST_RUN = 0, ST_SCAT = 1, ST_BND = 2, ST_SETUP = 3, ST_DEAD = 4, ST_DRY = 5, ST_FAR = 6 };
+#define XO_VOX_CLEARANCE (XO_TRACE != XO_TRACE_ALL)
 	const u32 lane = threadIdx.x & 31u;
 	const u32 lanemask_lt = (1u << lane) - 1u;
 	const u32 vox_bxy = vox_bx + vox_by;
@@ -53,7 +64,8 @@
 	(void)opl; (void)packet; (void)trace_count; (void)flags;
 	// ray: voxel walk state
 	// The walk keeps the low address word of the current voxel in the compact
-	// map, vlo = lo32(voxels8) + packed index (x+2) | (y+2) << bx | (z+2) << bxy
+	// map (16-bit cells: material | clearance << 8),
+	// vlo = lo32(voxels8) + 2*packed index, packed index = (x+2) | (y+2) << bx | (z+2) << bxy
 	// (two voxels of padding: the speculative second crossing of a trip may look
 	// one voxel beyond the sentinel layer);
 	// the host guarantees that the map does not straddle a 4 GB boundary, so a
@@ -61,7 +73,10 @@
 	const u32 vbase_lo = (u32)reinterpret_cast<u64>(voxels8);
 	const u32 vbase_hi = (u32)(reinterpret_cast<u64>(voxels8) >> 32);
 	u32 vlo = vbase_lo;
-	i32 stx = 1, sty = 1, stz = 1;  // address increment per crossing on each axis
+	u32 dcur = 1;                   // clearance of the current voxel
+	i32 stx = 2, sty = 2, stz = 2;  // address increment per crossing on each axis
+	const float inv_sx = 1.0f/cfg.size.x, inv_sy = 1.0f/cfg.size.y, inv_sz = 1.0f/cfg.size.z;
+	(void)dcur; (void)inv_sx; (void)inv_sy; (void)inv_sz;
 	i32 last_d = 0;                 // increment of the last crossing (names its axis)
 	u32 mat = 0;
 	float tmx = 0.0f, tmy = 0.0f, tmz = 0.0f, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
@@ -87,7 +102,8 @@
 #else
 #define XO_DIR_CONSTS() do { } while (0)
 #endif
-#define XO_VOXEL(lo) ((u32)__ldg(reinterpret_cast<const unsigned char *>(((u64)vbase_hi << 32) | (u64)(lo))))
+#define XO_VOXEL(lo) ((u32)__ldg(reinterpret_cast<const unsigned short *>(((u64)vbase_hi << 32) | (u64)(lo))))
+#define XO_PACK_VOXEL(ix_, iy_, iz_) (vbase_lo + 2u*((u32)((ix_) + 2) | ((u32)((iy_) + 2) << vox_bx) | ((u32)((iz_) + 2) << vox_bxy)))
 #if XO_USE_RMAX
 #define XO_RMAX_TEST() do { \
 		float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
@@ -141,6 +157,15 @@
 					q_a[lane] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
 					q_b[lane] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, __uint_as_float(base + lane));
 					q_l[lane] = tc;
+					{   // voxel under the launch point (mcvox.template.c:206-220), kept inside
+						// the grid; found here by the whole warp, not by the 1-2 lanes of a pop
+						i32 ix, iy, iz;
+						ctx.position_to_voxel(L_.pos, &ix, &iy, &iz);
+						ix = clipi(ix, 0, cfg.nx - 1);
+						iy = clipi(iy, 0, cfg.ny - 1);
+						iz = clipi(iz, 0, cfg.nz - 1);
+						q_v[lane] = XO_PACK_VOXEL(ix, iy, iz);
+					}
 				}
 				__syncwarp();
 				q_count = n_new;
@@ -153,15 +178,8 @@
 					trace_count = q_l[slot];
 					pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
 					dir.x = b.x; dir.y = b.y; dir.z = b.z; packet = __float_as_uint(b.w);
-					// voxel under the launch point (mcvox.template.c:206-220), kept
-					// inside the grid
-					i32 ix, iy, iz;
-					ctx.position_to_voxel(pos, &ix, &iy, &iz);
-					ix = clipi(ix, 0, cfg.nx - 1);
-					iy = clipi(iy, 0, cfg.ny - 1);
-					iz = clipi(iz, 0, cfg.nz - 1);
-					vlo = vbase_lo + ((u32)(ix + 2) | ((u32)(iy + 2) << vox_bx) | ((u32)(iz + 2) << vox_bxy));
-					mat = XO_VOXEL(vlo);
+					vlo = q_v[slot];
+					{ const u32 cell = XO_VOXEL(vlo); mat = cell & 0xffu; dcur = cell >> 8; }
 					XO_LOAD_MAT(mat);
 					opl = 0.0f;
 					flags = EV_LAUNCH;
@@ -190,8 +208,9 @@
 			pos.y = fmaf(dir.y, t_evt, pos.y);
 			pos.z = fmaf(dir.z, t_evt, pos.z);
 			if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_evt, opl);
-			const u32 entered = XO_VOXEL(vlo);
+			const u32 entered = XO_VOXEL(vlo) & 0xffu;
 			const bool escaping = (entered == XO_VOX_SENTINEL);
+			dcur = 1;               // on a face between materials / of the grid
 			const u32 next_mat = escaping ? 0u : entered;
 			const float n1 = c_hot.n, n2 = sh_fast[next_mat].hot.n;
 			bool through = true;
@@ -206,7 +225,7 @@
 			flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 			if (through) {
 				if (escaping) {
-					const i32 iz = (i32)((vlo - vbase_lo) >> vox_bxy) - 2;
+					const i32 iz = (i32)(((vlo - vbase_lo) >> 1) >> vox_bxy) - 2;
 					if (iz < 0) {
 						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
 					} else if (iz >= cfg.nz) {
@@ -225,13 +244,36 @@
 		}
 
 		// ---- interaction: absorb, scatter, lottery (mcvox.template.c:925-981) -------
-		if (state == ST_SCAT) {
+		if (state == ST_SCAT || state == ST_FAR) {
 			bool done = false;
 			++iterations;
 			pos.x = fmaf(dir.x, t_s, pos.x);
 			pos.y = fmaf(dir.y, t_s, pos.y);
 			pos.z = fmaf(dir.z, t_s, pos.z);
 			if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_s, opl);
+#if XO_VOX_CLEARANCE
+			u32 mat_here = mat;
+			if (state == ST_FAR) {
+				// the flight skipped the walk: voxel of the interaction point from the
+				// position, loop trips of the reference = faces crossed on the way
+				const u32 idx0 = (vlo - vbase_lo) >> 1;
+				i32 ix = __float2int_rd((pos.x - cfg.top_left.x)*inv_sx);
+				i32 iy = __float2int_rd((pos.y - cfg.top_left.y)*inv_sy);
+				i32 iz = __float2int_rd((pos.z - cfg.top_left.z)*inv_sz);
+				ix = clipi(ix, 0, cfg.nx - 1);
+				iy = clipi(iy, 0, cfg.ny - 1);
+				iz = clipi(iz, 0, cfg.nz - 1);
+				iterations += (u32)(abs(ix - ((i32)(idx0 & vox_mx) - 2)) +
+					abs(iy - ((i32)((idx0 >> vox_bx) & vox_my) - 2)) +
+					abs(iz - ((i32)(idx0 >> vox_bxy) - 2)));
+				vlo = XO_PACK_VOXEL(ix, iy, iz);
+				const u32 cell = XO_VOXEL(vlo);
+				dcur = cell >> 8;
+				// (a rounding of the end point across a face of the clearance box can
+				// land in another material: adopted after this interaction)
+				if ((cell & 0xffu) != XO_VOX_SENTINEL) mat_here = cell & 0xffu;
+			}
+#endif
 #if XO_METHOD == 1
 			if (rng.next() < c_hot.absorb) {
 				float deposit = weight;
@@ -248,7 +290,15 @@
 				float deposit = weight*c_hot.absorb;
 				weight -= deposit;
 				flags |= EV_ABSORPTION;
+#if XO_FLU_VOXGRID
+				{   // the fluence grid is the voxel grid: the cell is the voxel of the walk
+					const u32 idx = (vlo - vbase_lo) >> 1;
+					fluence.deposit_cell(acc, (idx & vox_mx) - 2u, ((idx >> vox_bx) & vox_my) - 2u,
+						(idx >> vox_bxy) - 2u, fluence_weight(deposit, c_hot.mua, fluence.k));
+				}
+#else
 				if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
+#endif
 			}
 			pf_scatter(c_pf, rng, lut, dir);
 			flags |= EV_SCATTERING;
@@ -261,30 +311,15 @@
 #endif
 			}
 #endif
+#if XO_VOX_CLEARANCE
+			if (mat_here != mat) { mat = mat_here; XO_LOAD_MAT(mat); }
+#endif
 			XO_END_TRIP();
 		}
 
 		// ---- new ray from `pos` along `dir` in voxel (ix, iy, iz) -----------------------
 		if (state == ST_SETUP) {
 			XO_DIR_CONSTS();
-			const float rx = FastMath::rcp_approx(dir.x), ry = FastMath::rcp_approx(dir.y),
-				rz = FastMath::rcp_approx(dir.z);
-			const bool fx = dir.x >= 0.0f, fy = dir.y >= 0.0f, fz = dir.z >= 0.0f;
-			stx = fx ? 1 : -1;
-			sty = (fy ? 1 : -1) << vox_bx;
-			stz = (fz ? 1 : -1) << vox_bxy;
-			// exit faces of the current voxel (mcvox.template.c:173-196); the packed
-			// index holds coordinate + 2
-			const u32 idx = vlo - vbase_lo;
-			const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 1 : 2)), cfg.size.x, cfg.top_left.x);
-			const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 1 : 2)), cfg.size.y, cfg.top_left.y);
-			const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 1 : 2)), cfg.size.z, cfg.top_left.z);
-			tmx = (dir.x != 0.0f) ? fmaxf((facex - pos.x)*rx, 0.0f) : XO_INF;
-			tmy = (dir.y != 0.0f) ? fmaxf((facey - pos.y)*ry, 0.0f) : XO_INF;
-			tmz = (dir.z != 0.0f) ? fmaxf((facez - pos.z)*rz, 0.0f) : XO_INF;
-			tdx = cfg.size.x*fabsf(rx);
-			tdy = cfg.size.y*fabsf(ry);
-			tdz = cfg.size.z*fabsf(rz);
 			t_s = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
 #if XO_USE_RMAX
 			{   // parameter at which the ray leaves the rmax sphere around the source
@@ -295,6 +330,36 @@
 			}
 #endif
 			state = ST_RUN;
+#if XO_VOX_CLEARANCE
+			{   // extent of the flight in voxels along its longest axis against the clearance
+				const float ext = t_s*fmaxf(fabsf(dir.x)*inv_sx, fmaxf(fabsf(dir.y)*inv_sy, fabsf(dir.z)*inv_sz));
+				bool far = ext < (float)dcur - 1.0f;
+#if XO_USE_RMAX
+				far = far && t_s <= t_rmax;
+#endif
+				if (far) state = ST_FAR;
+			}
+#endif
+			if (state == ST_RUN) {
+				const float rx = FastMath::rcp_approx(dir.x), ry = FastMath::rcp_approx(dir.y),
+					rz = FastMath::rcp_approx(dir.z);
+				const bool fx = dir.x >= 0.0f, fy = dir.y >= 0.0f, fz = dir.z >= 0.0f;
+				stx = fx ? 2 : -2;
+				sty = (fy ? 2 : -2) << vox_bx;
+				stz = (fz ? 2 : -2) << vox_bxy;
+				// exit faces of the current voxel (mcvox.template.c:173-196); the packed
+				// index holds coordinate + 2
+				const u32 idx = (vlo - vbase_lo) >> 1;
+				const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 1 : 2)), cfg.size.x, cfg.top_left.x);
+				const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 1 : 2)), cfg.size.y, cfg.top_left.y);
+				const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 1 : 2)), cfg.size.z, cfg.top_left.z);
+				tmx = (dir.x != 0.0f) ? fmaxf((facex - pos.x)*rx, 0.0f) : XO_INF;
+				tmy = (dir.y != 0.0f) ? fmaxf((facey - pos.y)*ry, 0.0f) : XO_INF;
+				tmz = (dir.z != 0.0f) ? fmaxf((facez - pos.z)*rz, 0.0f) : XO_INF;
+				tdx = cfg.size.x*fabsf(rx);
+				tdy = cfg.size.y*fabsf(ry);
+				tdz = cfg.size.z*fabsf(rz);
+			}
 		}
 
 		// ---- voxel walk: lanes in RUN state cross faces until enough lanes wait ------
@@ -319,7 +384,8 @@
 					if (pz) tmz += tdz;
 					last_d = px ? stx : (py ? sty : stz);
 					vlo += (u32)last_d;
-					u32 m_a = XO_VOXEL(vlo);
+					const u32 cell_a = XO_VOXEL(vlo);
+					u32 m_a = cell_a & 0xffu;
 					// second crossing, speculative
 					const float tmin_b = fminf(tmx, fminf(tmy, tmz));
 					const bool ok_b = tmin_b < t_s;
@@ -328,8 +394,10 @@
 					const bool qz = !qx && !qy;
 					const i32 d_b = qx ? stx : (qy ? sty : stz);
 					const u32 vlo_b = vlo + (u32)d_b;
-					u32 m_b = mat;
-					if (ok_b) m_b = XO_VOXEL(vlo_b);
+					u32 cell_b = 0x100u | mat;
+					if (ok_b) cell_b = XO_VOXEL(vlo_b);
+					u32 m_b = cell_b & 0xffu;
+					dcur = cell_a >> 8;
 #if XO_USE_RMAX
 					// first face beyond rmax: handled as an event
 					if (tmin_a > t_rmax) m_a = ~0u;
@@ -346,9 +414,32 @@
 #else
 #define XO_TRACE_CROSSING(tmin_) do { } while (0)
 #endif
+#if XO_VOX_SAME_N
+					// Equal refractive indices everywhere: a face between two materials is
+					// no interface event, only the attenuation changes.  The remaining
+					// optical depth of the flight is still Exp(1) distributed (memoryless),
+					// so the free path is rescaled to the new material instead of stopping
+					// the ray for a fresh draw (what the reference does, statistically the
+					// same; the grid face and rmax stay events).
+#define XO_MATERIAL_CHANGE(m_, tmin_) do { \
+						const float k_old_ = c_hot.step_k; \
+						XO_LOAD_MAT(m_); \
+						mat = (m_); \
+						t_s = fmaf(t_s - (tmin_), c_hot.step_k*FastMath::rcp_approx(k_old_), (tmin_)); \
+					} while (0)
+#define XO_IS_PLAIN_CHANGE(m_) ((m_) < XO_VOX_SENTINEL && c_hot.step_k > -XO_FLT_MAX && t_s < XO_FLT_MAX)
+#else
+#define XO_MATERIAL_CHANGE(m_, tmin_) do { } while (0)
+#define XO_IS_PLAIN_CHANGE(m_) false
+#endif
 					if (m_a != mat) {
-						state = ST_BND;
-						t_evt = tmin_a;
+						if (XO_IS_PLAIN_CHANGE(m_a)) {
+							XO_TRACE_CROSSING(tmin_a);
+							XO_MATERIAL_CHANGE(m_a, tmin_a);
+						} else {
+							state = ST_BND;
+							t_evt = tmin_a;
+						}
 					} else {
 						XO_TRACE_CROSSING(tmin_a);      // the reference records every loop trip
 						if (!ok_b) {
@@ -360,15 +451,23 @@
 							if (qz) tmz += tdz;
 							vlo = vlo_b;
 							last_d = d_b;
+							dcur = cell_b >> 8;
 							if (m_b != mat) {
-								state = ST_BND;
-								t_evt = tmin_b;
+								if (XO_IS_PLAIN_CHANGE(m_b)) {
+									XO_TRACE_CROSSING(tmin_b);
+									XO_MATERIAL_CHANGE(m_b, tmin_b);
+								} else {
+									state = ST_BND;
+									t_evt = tmin_b;
+								}
 							} else {
 								XO_TRACE_CROSSING(tmin_b);
 							}
 						}
 					}
 #undef XO_TRACE_CROSSING
+#undef XO_MATERIAL_CHANGE
+#undef XO_IS_PLAIN_CHANGE
 				}
 			}
 			if ((u32)__popc(__ballot_sync(0xffffffffu, state != ST_RUN)) >= wake) break;
@@ -377,6 +476,8 @@
 #undef XO_LOAD_MAT
 #undef XO_DIR_CONSTS
 #undef XO_VOXEL
+#undef XO_PACK_VOXEL
+#undef XO_VOX_CLEARANCE
 #undef XO_RMAX_TEST
 #undef XO_TRACE_TRIP
 #undef XO_END_TRIP

@@ -163,8 +163,8 @@ McKernel(
 	const __grid_constant__ xo::FluWindow window,
 	xo::u32 chunk,
 	xo::u32 refill,             // throughput mode: waiting lanes per warp that trigger their joint handling
-	const unsigned char *voxels8,   // throughput mode: padded uint8 material map (mcvox/mc.py)
-	xo::u32 vox_bx,             // ... its index = (x+1) | (y+1) << vox_bx | (z+1) << (vox_bx + vox_by)
+	const unsigned char *voxels8,   // throughput mode: padded compact map, 16-bit cells material | clearance << 8 (mcvox/mc.py)
+	xo::u32 vox_bx,             // ... its index = (x+2) | (y+2) << vox_bx | (z+2) << (vox_bx + vox_by)
 	xo::u32 vox_by)
 {
 	using namespace xo;
@@ -220,6 +220,7 @@ McKernel(
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;
 	u32 *q_l = reinterpret_cast<u32 *>(xo_smem) + off_words + blockDim.x*8u + (threadIdx.x & ~31u);
+	u32 *q_v = q_l + blockDim.x;    // voxel (low address word of the compact map) of the launch point
 #endif
 	__syncthreads();
 

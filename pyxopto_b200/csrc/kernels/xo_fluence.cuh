@@ -106,6 +106,11 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 		u32 ly = t % win.ext1, lz = t/win.ext1;
 		return offset + ((lz + win.org2)*ny + (ly + win.org1))*nx + lx + win.org0;
 	}
+	// deposit into a cell whose (in-range) indices the caller already knows (mcvox
+	// throughput loop with the fluence grid on the voxel grid)
+	__device__ __forceinline__ void deposit_cell(const Accu &acc, u32 ix, u32 iy, u32 iz, u32 wfix) const {
+		acc.add_global(offset + (iz*ny + iy)*nx + ix, wfix);
+	}
 };
 
 struct FluRz {                      // mcfluence/fluencerz.py:64-72

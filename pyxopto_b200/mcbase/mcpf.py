@@ -113,10 +113,16 @@ class MHg(PfBase):
             _fields_ = [('g', mc.types.mc_fp_t), ('beta', mc.types.mc_fp_t)]
         return ClMHg
 
-    def __init__(self, g: float, beta: float):
+    def __init__(self, g: float, b: float = None, beta: float = None):
+        # (the reference names the Rayleigh fraction ``b``, mhg.py:112; ``beta`` is the
+        # name of the packed field)
         super().__init__()
+        if b is None:
+            b = beta
+        if b is None:
+            raise TypeError("MHg() missing 1 required positional argument: 'b'")
         self.g = g
-        self.beta = beta
+        self.beta = b
 
     def _set_g(self, g):
         self._g = min(max(float(g), -1.0), 1.0)
@@ -126,6 +132,7 @@ class MHg(PfBase):
 
     g = property(lambda self: self._g, _set_g)
     beta = property(lambda self: self._beta, _set_beta)
+    b = property(lambda self: self._beta, _set_beta)
 
     def cl_pack(self, mc, target=None):
         if target is None:
@@ -135,10 +142,10 @@ class MHg(PfBase):
         return target
 
     def todict(self):
-        return {'g': self._g, 'beta': self._beta, 'type': type(self).__name__}
+        return {'g': self._g, 'b': self._beta, 'type': type(self).__name__}
 
     def __repr__(self):
-        return 'MHg(g={}, beta={})'.format(self._g, self._beta)
+        return 'MHg(g={}, b={})'.format(self._g, self._beta)
 
 
 class Gk(PfBase):

@@ -80,6 +80,11 @@ class McBase(CuWorker):
             raise NotImplementedError(
                 'Surface layouts are only part of the accelerated path of the '
                 'layered simulator (mcml).')
+        # plugin objects built with the reference package are rebuilt with this
+        # package's classes from their own description (pyxopto_b200/adopt.py)
+        from ..adopt import adopt
+        source, detectors, trace, fluence, surface = (
+            adopt(obj, self.geometry) for obj in (source, detectors, trace, fluence, surface))
         self._surface = surface
         self._source = source
         self._detectors = detectors
@@ -402,6 +407,7 @@ class McBase(CuWorker):
     # throughput loops: one per lane) after the budget is exhausted, so the counter
     # ends at most max_threads*chunk_max (< 2^24) above the budget and must not wrap
     max_batch = 0xFFFFFFFF - (1 << 24)
+    _keep_accumulators = False       # batches of one run: do not re-zero the accumulators
     _packet_counter_start = 0
     fluence_block = FLUENCE_BLOCK
 
@@ -491,20 +497,33 @@ class McBase(CuWorker):
         if nphotons > self.max_batch:
             # 64-bit packet counter family (McDataTypesSingleCnt64): the device
             # counter stays 32 bits wide, the host runs the budget in batches that
-            # continue the MWC streams and accumulates the results (`out=`); the
-            # integer accumulators make the sum exact
+            # continue the MWC streams.  The batches accumulate where they are: the
+            # 64-bit integer accumulators stay on the device from batch to batch
+            # (exact sums) and come to the host once, after the last one
             if self._trace is not None:
                 raise ValueError('A traced run is limited to {:,d} packets!'.format(self.max_batch))
             if not (download and synchronize):
                 raise ValueError('Runs of more than {:,d} packets need download=True, '
                                  'synchronize=True'.format(self.max_batch))
-            remaining, results = nphotons, out
-            while remaining > 0:
-                batch = min(remaining, self.max_batch)
-                results = self.run(batch, out=results, wgsize=wgsize, maxthreads=maxthreads,
-                                   copyseeds=copyseeds, exportsrc=exportsrc, verbose=verbose)
-                remaining -= batch
-            self._run_report['items'] = nphotons
+            remaining = nphotons
+            kernel_ms = iterations = 0
+            hook = self._reduce_hook
+            try:
+                while remaining > 0:
+                    batch = min(remaining, self.max_batch)
+                    # (multi-GPU: the ranks combine their totals once, after the last batch)
+                    self._reduce_hook = hook if batch == remaining else None
+                    self.run(batch, wgsize=wgsize, maxthreads=maxthreads, copyseeds=copyseeds,
+                             exportsrc=exportsrc, verbose=verbose, download=False)
+                    kernel_ms += self._run_report['kernel_ms']
+                    iterations += self._run_report['iterations']
+                    remaining -= batch
+                    self._keep_accumulators = True      # the next batch adds on top
+            finally:
+                self._keep_accumulators = False
+                self._reduce_hook = hook
+            results = self._collect_results(nphotons, out)
+            self._run_report.update(items=nphotons, kernel_ms=kernel_ms, iterations=iterations)
             return results
         t0 = time.perf_counter()
         self._ensure_device()
@@ -543,11 +562,11 @@ class McBase(CuWorker):
         else:
             lut_host = np.zeros(4, np.float32)
         lbuf = self.cl_r_buffer('fp_lut', lut_host)
-        abuf = self._rw_flat_buffer('accumulator')
+        abuf = self._rw_flat_buffer('accumulator', fill=not self._keep_accumulators)
         fbuf = self._rw_flat_buffer('float', fill=not self._trace_tails_unread())
         ibuf = self._rw_flat_buffer('int')
         shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
-        queue_bytes = 0 if deterministic else 36*block + 16   # per-warp launch queues
+        queue_bytes = 0 if deterministic else 40*block + 16   # per-warp launch queues
         window = self._fluence_window(block, shared + queue_bytes)
         shared += 4*int(window[3])*int(window[4])*int(window[5]) + queue_bytes
         grid, block = self.launch_geometry(kernel, block, shared, maxthreads)

@@ -144,7 +144,7 @@ class CollectionLut(LinearLut):
     """Angular sensitivity of a detector over the cosine of the incidence angle,
     tabulated at ``n`` equidistant cosines (counterpart of mcutil/lut.py:327-362)."""
     def __init__(self, sensitivity, costheta=None, n: int = 1000):
-        if isinstance(sensitivity, (str, CollectionLut)):
+        if isinstance(sensitivity, (str, LinearLut)):
             super().__init__(sensitivity)
             return
         values = np.asarray(sensitivity, dtype=np.float64)
@@ -163,7 +163,7 @@ class EmissionLut(LinearLut):
     with adaptive quadrature from the lower limit (``meth='quad'``)."""
     def __init__(self, radiance, costheta=None, n: int = 2000, npts: int = 10000,
                  meth: str = 'simps'):
-        if isinstance(radiance, (str, EmissionLut)):
+        if isinstance(radiance, (str, LinearLut)):
             super().__init__(radiance)
             return
         if meth not in ('simps', 'quad'):

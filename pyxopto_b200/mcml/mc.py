@@ -36,8 +36,10 @@ class Mc(McBase):
                          surface=surface, types=types, options=options,
                          rnginit=rnginit, cl_devices=cl_devices,
                          cl_build_options=cl_build_options, cl_profiling=cl_profiling)
+        from ..adopt import adopt
+        layers = adopt(layers, self.geometry)
         if not isinstance(layers, mclayer.Layers):
-            layers = mclayer.Layers(layers)
+            layers = mclayer.Layers([adopt(item, self.geometry) for item in layers])
         self._layers = layers
         self._obj_types['layer'] = type(layers[1])
         self._obj_types['pf'] = type(layers[1].pf)

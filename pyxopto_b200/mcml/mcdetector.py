@@ -157,6 +157,8 @@ class TotalLut(Detector):
         self.direction = direction
 
     def _set_lut(self, lut):
+        if isinstance(lut, LinearLut) and not isinstance(lut, CollectionLut):
+            lut = CollectionLut(lut)        # (a deserialised table: lut.py:209-214 drops the subclass)
         if not isinstance(lut, CollectionLut):
             raise TypeError('The lookup table must be an instance of CollectionLut!')
         self._lut = lut

@@ -39,8 +39,10 @@ class Mc(McBase):
                          surface=surface, types=types, options=options,
                          rnginit=rnginit, cl_devices=cl_devices,
                          cl_build_options=cl_build_options, cl_profiling=cl_profiling)
+        from ..adopt import adopt
+        voxels, materials = adopt(voxels, self.geometry), adopt(materials, self.geometry)
         if not isinstance(materials, mcmaterial.Materials):
-            materials = mcmaterial.Materials(materials)
+            materials = mcmaterial.Materials([adopt(item, self.geometry) for item in materials])
         self._voxels = voxels
         self._materials = materials
         self._voxels.data(self)            # allocate the material-index array
@@ -83,8 +85,12 @@ class Mc(McBase):
         return len(cltypes.raw_bytes(self._packed['materials'])) + \
             64*len(self._materials) + 32
 
-    # waiting lanes per warp that trigger their joint handling (throughput loop)
-    wait_lanes = 16
+    # waiting lanes per warp that trigger their joint handling (throughput loop).
+    # Measured on C3 (201^3, ms per 1e8 packets) with the clearance map, where 68 % of
+    # the flights skip the voxel walk and wait for their interaction right away:
+    # 16: 121.2, 20: 113.4, 22: 112.2, 24: 112.8, 26: 116.4, 28: 124.3, 32: 187.1
+    # (before the clearance map the optimum was 16: 129.6)
+    wait_lanes = 22
 
     def _refill_lanes(self) -> int:
         if self.refill_lanes is not None:
@@ -118,13 +124,52 @@ class Mc(McBase):
         nz, ny, nx = self._voxels.shape
         return tuple(int(n + 3).bit_length() for n in (nx, ny, nz))
 
+    @staticmethod
+    def _clearance(mat: np.ndarray) -> np.ndarray:
+        """Chessboard distance (voxels, 1 ... 255) of every voxel to the nearest voxel
+        of another material or outside the grid: all voxels closer than that - in the
+        maximum norm - hold the same material.  The throughput loop lets a flight that
+        is shorter than the clearance skip the voxel walk (mcvox_dda_loop.cuh)."""
+        from scipy import ndimage
+        padded = np.full(tuple(n + 2 for n in mat.shape), -1, dtype=np.int32)
+        padded[1:-1, 1:-1, 1:-1] = mat
+        dist = np.zeros(padded.shape, dtype=np.int32)
+        for m in np.unique(mat):
+            dist += ndimage.distance_transform_cdt(padded == m, metric='chessboard')
+        return np.clip(dist[1:-1, 1:-1, 1:-1], 1, 255).astype(np.uint8)
+
     def _vox_packed(self) -> bool:
         return len(self._materials) <= self.VOX_SENTINEL and sum(self._vox_pack_bits()) <= 31
+
+    def _same_refractive_index(self) -> bool:
+        """True when every material (the surrounding medium included) packs the same
+        refractive index: a face between two materials then never reflects or
+        refracts, and the throughput loop treats it as a change of the attenuation
+        along the ray instead of an interface event."""
+        ns = {float(np.float32(m.n)) for m in self._materials}
+        return len(ns) == 1
+
+    def _fluence_on_voxel_grid(self) -> bool:
+        """True when the fluence plugin is the plain ``Fluence`` accumulator on exactly
+        the voxel grid: the cell of a deposit is then the voxel the walk is in."""
+        flu = self._fluence
+        if flu is None or type(flu) is not mcfluence.Fluence:
+            return False
+        v = self._voxels
+        for fa, va in ((flu.xaxis, v.xaxis), (flu.yaxis, v.yaxis), (flu.zaxis, v.zaxis)):
+            if (np.float32(fa.start), np.float32(fa.stop), int(fa.n)) != \
+                    (np.float32(va.start), np.float32(va.stop), int(va.n)) or \
+                    getattr(fa, 'logscale', False):
+                return False
+        return True
 
     def _extra_defines(self, opts):
         aniso = isinstance(self._materials[0], mcmaterial.AnisotropicMaterial)
         return ['#define XO_VOX_PACKED {}'.format(int(self._vox_packed())),
-                '#define XO_ANISO {}'.format(int(aniso))]
+                '#define XO_ANISO {}'.format(int(aniso)),
+                '#define XO_VOX_SAME_N {}'.format(
+                    int(self._same_refractive_index() and not aniso)),
+                '#define XO_FLU_VOXGRID {}'.format(int(self._fluence_on_voxel_grid()))]
 
     def _upload_medium(self):
         self.cl_r_buffer('materials', self._packed['materials'])
@@ -134,12 +179,13 @@ class Mc(McBase):
             if self._vox_packed():
                 bx, by, bz = self._vox_pack_bits()
                 nz, ny, nx = self._voxels.shape
-                packed = np.full((1 << bz, 1 << by, 1 << bx), self.VOX_SENTINEL, np.uint8)
                 mat = data.reshape(nz, ny, nx)
                 if mat.size and (mat.min() < 0 or mat.max() >= len(self._materials)):
                     raise ValueError('Voxel material indices must be in [0, {})!'.format(
                         len(self._materials)))
-                packed[2:nz + 2, 2:ny + 2, 2:nx + 2] = mat
+                packed = np.full((1 << bz, 1 << by, 1 << bx), self.VOX_SENTINEL, np.uint16)
+                packed[2:nz + 2, 2:ny + 2, 2:nx + 2] = \
+                    mat.astype(np.uint16) | (self._clearance(mat).astype(np.uint16) << 8)
                 # the voxel walk steps the low address word only: the map must not
                 # straddle a 4 GB boundary (re-allocate in the unlikely case it does)
                 parked = []
