@@ -22,7 +22,10 @@ import numpy as np
 
 
 def _is_native(obj) -> bool:
-    return type(obj).__module__.split('.')[0] == __name__.split('.')[0]
+    """True for everything that is not an object of the reference package: this
+    package's own classes and user-written plugin classes (which carry their own
+    kernel fragments and are bound as they are, mcsim._user_fragments)."""
+    return type(obj).__module__.split('.')[0] != 'xopto'
 
 
 def _search_path(geometry: str, context=None):
