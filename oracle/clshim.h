@@ -63,6 +63,21 @@ static inline ulong atom_add(volatile ulong *p, ulong v) {
 #define convert_int(x)   ((int)(x))
 #define convert_uint(x)  ((uint)(x))
 
+/* (with -DXO_REF_DOUBLE the rendered kernel computes in binary64: the bare OpenCL math
+ * names then are libm's double functions as they stand) */
+#ifdef XO_REF_DOUBLE
+static inline double xo_ref_sincos(double x, double *c) { *c = cos(x); return sin(x); }
+#define sincos(x, pc)    xo_ref_sincos((x), (pc))
+#define rsqrt(x)         (1.0/sqrt(x))
+#define powr(x, y)       pow((x), (y))
+#define native_sin       sin
+#define native_cos       cos
+#define native_log       log
+#define native_exp       exp
+#define native_sqrt      sqrt
+#define native_rsqrt(x)  (1.0/sqrt(x))
+#define native_powr      pow
+#else
 static inline float xo_ref_sincos(float x, float *c) { *c = cosf(x); return sinf(x); }
 #define sincos(x, pc)    xo_ref_sincos((x), (pc))
 #define rsqrt(x)         (1.0f/sqrtf(x))
@@ -74,6 +89,7 @@ static inline float xo_ref_sincos(float x, float *c) { *c = cosf(x); return sinf
 #define native_sqrt      sqrtf
 #define native_rsqrt(x)  (1.0f/sqrtf(x))
 #define native_powr      powf
+#endif
 #define native_divide(a, b) ((a)/(b))
 /* OpenCL's min / max / clamp are functions: every argument is evaluated once
  * (mcvox/mcsource/voxel.py draws a random number inside mc_min(...)) */
@@ -84,6 +100,7 @@ static inline float xo_ref_sincos(float x, float *c) { *c = cosf(x); return sinf
 
 /* OpenCL math built-ins are overloaded on float; the rendered text uses the
  * bare names with float arguments. */
+#ifndef XO_REF_DOUBLE
 #define sin sinf
 #define cos cosf
 #define tan tanf
@@ -105,4 +122,5 @@ static inline float xo_ref_sincos(float x, float *c) { *c = cosf(x); return sinf
 #define pow powf
 #define fmod fmodf
 #define round roundf
+#endif
 #endif

@@ -25,11 +25,18 @@ _Thread_local size_t xo_ref_global_id;
 #define XO_REF_GEOMETRY 0
 #endif
 
+/* floating-point type of the rendered kernel: -DXO_REF_DOUBLE for McDataTypesDouble */
+#ifdef XO_REF_DOUBLE
+typedef double xo_ref_fp;
+#else
+typedef float xo_ref_fp;
+#endif
+
 typedef struct {
 	uint32_t num_packets;
 	uint32_t *num_packets_done;
 	uint32_t *num_kernels;
-	float rmax;
+	double rmax;                /* converted to the kernel's precision at the call */
 	uint64_t *rng_x;
 	const uint32_t *rng_a;
 	/* geometry: mcml/mccyl: g0=num_layers(u32 by value), g1=layers
@@ -37,34 +44,34 @@ typedef struct {
 	uint32_t g0;
 	const void *g1, *g2, *g3;
 	const void *source, *surface, *trace, *fluence, *detectors;
-	const float *fp_lut;
+	const xo_ref_fp *fp_lut;
 	int32_t *int_buffer;
-	float *float_buffer;
+	xo_ref_fp *float_buffer;
 	uint64_t *accumulator_buffer;
 	/* trace row strides (0 when no trace): floats per packet, ints per packet */
 	uint64_t trace_float_stride, trace_int_stride;
 } xo_ref_args;
 
 #if XO_REF_GEOMETRY == 1
-void McKernel(uint32_t, uint32_t *, uint32_t *, float, uint64_t *, const uint32_t *,
+void McKernel(uint32_t, uint32_t *, uint32_t *, xo_ref_fp, uint64_t *, const uint32_t *,
 	const void *, const void *, uint32_t, const void *,
-	const void *, const void *, const void *, const void *, const void *, const float *,
-	int32_t *, float *, uint64_t *);
+	const void *, const void *, const void *, const void *, const void *, const xo_ref_fp *,
+	int32_t *, xo_ref_fp *, uint64_t *);
 static void call_kernel(const xo_ref_args *a, uint32_t n, uint32_t *done,
-		int32_t *ibuf, float *fbuf) {
-	McKernel(n, done, a->num_kernels, a->rmax, a->rng_x, a->rng_a,
+		int32_t *ibuf, xo_ref_fp *fbuf) {
+	McKernel(n, done, a->num_kernels, (xo_ref_fp)a->rmax, a->rng_x, a->rng_a,
 		a->g1, a->g2, a->g0, a->g3,
 		a->source, a->surface, a->trace, a->fluence, a->detectors, a->fp_lut,
 		ibuf, fbuf, a->accumulator_buffer);
 }
 #else
-void McKernel(uint32_t, uint32_t *, uint32_t *, float, uint64_t *, const uint32_t *,
+void McKernel(uint32_t, uint32_t *, uint32_t *, xo_ref_fp, uint64_t *, const uint32_t *,
 	uint32_t, const void *,
-	const void *, const void *, const void *, const void *, const void *, const float *,
-	int32_t *, float *, uint64_t *);
+	const void *, const void *, const void *, const void *, const void *, const xo_ref_fp *,
+	int32_t *, xo_ref_fp *, uint64_t *);
 static void call_kernel(const xo_ref_args *a, uint32_t n, uint32_t *done,
-		int32_t *ibuf, float *fbuf) {
-	McKernel(n, done, a->num_kernels, a->rmax, a->rng_x, a->rng_a,
+		int32_t *ibuf, xo_ref_fp *fbuf) {
+	McKernel(n, done, a->num_kernels, (xo_ref_fp)a->rmax, a->rng_x, a->rng_a,
 		a->g0, a->g1,
 		a->source, a->surface, a->trace, a->fluence, a->detectors, a->fp_lut,
 		ibuf, fbuf, a->accumulator_buffer);
@@ -140,9 +147,9 @@ void xo_ref_run_dynamic_items(const xo_ref_args *a, uint32_t nthreads, uint32_t 
 /* the reference's SamplingVolume kernel (mcsv.template.c:236), one work-item:
  * no random numbers, integer accumulation -> schedule independent */
 void SamplingVolume(uint32_t, uint32_t *, uint32_t *, const void *, const void *,
-	uint64_t *, int32_t *, float *, uint64_t *);
+	uint64_t *, int32_t *, xo_ref_fp *, uint64_t *);
 void xo_ref_run_sv(uint32_t npackets, const void *trace, const void *sv,
-		uint64_t *total_weight, int32_t *ibuf, float *fbuf, uint64_t *abuf) {
+		uint64_t *total_weight, int32_t *ibuf, xo_ref_fp *fbuf, uint64_t *abuf) {
 	uint32_t processed = 0, kernels = 0;
 	xo_ref_global_id = 0;
 	SamplingVolume(npackets, &processed, &kernels, trace, sv, total_weight, ibuf, fbuf, abuf);

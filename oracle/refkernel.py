@@ -32,7 +32,7 @@ class XoRefArgs(ctypes.Structure):
         ('num_packets', ctypes.c_uint32),
         ('num_packets_done', ctypes.c_void_p),
         ('num_kernels', ctypes.c_void_p),
-        ('rmax', ctypes.c_float),
+        ('rmax', ctypes.c_double),      # passed on in the kernel's precision (ref_driver.c)
         ('rng_x', ctypes.c_void_p),
         ('rng_a', ctypes.c_void_p),
         ('g0', ctypes.c_uint32),
@@ -109,6 +109,12 @@ class RefKernel:
         self.outdir = outdir
         self._lib = None
         self._src_hash = None
+        # precision of the rendered kernel (McDataTypesDouble: binary64 buffers, and the
+        # cl_khr_fp64 macro an OpenCL compiler would predefine)
+        self.np_float = np.dtype(getattr(mc_obj.types, 'np_float', 'float32'))
+        if self.np_float.itemsize == 8:
+            self.cflags = list(CFLAGS_EXACT if cflags is None else cflags) + \
+                ['-DXO_REF_DOUBLE', '-Dcl_khr_fp64=1']
 
     # -- reference host side ------------------------------------------------
     def pack(self, nphotons: int):
@@ -141,8 +147,8 @@ class RefKernel:
     def fp_lut(self) -> np.ndarray:
         mgr = self.mc.float_r_lut_manager
         if len(mgr) == 0:
-            return np.zeros(1, np.float32)
-        return np.ascontiguousarray(mgr.pack_into(None), dtype=np.float32)
+            return np.zeros(1, self.np_float)
+        return np.ascontiguousarray(mgr.pack_into(None), dtype=self.np_float)
 
     # -- run ------------------------------------------------------------------
     def run(self, nphotons: int, nthreads: int, schedule: str = 'static',
@@ -153,7 +159,7 @@ class RefKernel:
         nphotons = int(nphotons)
         accu = np.zeros(max(int(m.cl_rw_accumulator_allocator.size), 1), np.uint64)
         ints = np.zeros(max(int(m.cl_rw_int_allocator.size), 1), np.int32)
-        floats = np.zeros(max(int(m.cl_rw_float_allocator.size), 1), np.float32)
+        floats = np.zeros(max(int(m.cl_rw_float_allocator.size), 1), self.np_float)
         lut = self.fp_lut()
         done = np.zeros(1, np.uint32)
         nk = np.zeros(1, np.uint32)
@@ -165,7 +171,7 @@ class RefKernel:
         args.num_packets = nphotons
         args.num_packets_done = done.ctypes.data
         args.num_kernels = nk.ctypes.data
-        args.rmax = np.float32(m.rmax)
+        args.rmax = float(self.np_float.type(m.rmax))
         args.rng_x = x.ctypes.data
         args.rng_a = a.ctypes.data
         keep = []
@@ -213,10 +219,10 @@ class RefKernel:
         sp = sv.cl_pack(m, None)
         accu = np.zeros(max(int(m.cl_rw_accumulator_allocator.size), 1), np.uint64)
         ibuf = np.zeros(max(int(m.cl_rw_int_allocator.size), 1), np.int32)
-        fbuf = np.zeros(max(int(m.cl_rw_float_allocator.size), 1), np.float32)
+        fbuf = np.zeros(max(int(m.cl_rw_float_allocator.size), 1), self.np_float)
         _, do, co, _ = np.frombuffer(bytes(memoryview(tp).cast('B')), np.uint32)[:4].tolist()
         ibuf[co:co + n] = trace_n
-        flat = np.asarray(trace_data, np.float32).reshape(-1)
+        flat = np.asarray(trace_data, self.np_float).reshape(-1)
         fbuf[do:do + flat.size] = flat
         total = np.zeros(1, np.uint64)
         fn = self._lib.xo_ref_run_sv

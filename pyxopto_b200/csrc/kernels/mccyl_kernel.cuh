@@ -89,7 +89,6 @@ typedef TraceNone XoTrace;
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetOuter::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
-#define XO_FP_EPS 1.1920929e-07f
 #define XO_CYL_MAX_STEPS 1000000
 
 struct CylCtx {

@@ -700,9 +700,12 @@ McKernel(
 #else
 			const u32 wfix = f2u(fmaf(weight, c_abs.dep_k, 0.5f));
 #endif
+			if (XoFluence::active && !XoFluence::fixed_point)     // user-written fragment
+				fluence.deposit(acc, window, pos, weight*c_abs.absorb, c_abs.mua, opl);
 			weight *= c_abs.survive;
 			flags |= EV_ABSORPTION;
-			if (XoFluence::active) fluence.deposit_prep(acc, flu_prep, window, pos, wfix, opl);
+			if (XoFluence::active && XoFluence::fixed_point)
+				fluence.deposit_prep(acc, flu_prep, window, pos, wfix, opl);
 		}
 #endif
 		pf_scatter(c_pf, rng, lut, dir);

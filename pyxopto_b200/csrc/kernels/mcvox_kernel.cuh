@@ -63,7 +63,6 @@ typedef TraceNone XoTrace;
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetTop::needs_opl || XoDetBottom::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
-#define XO_FP_EPS 1.1920929e-07f
 
 // Throughput mode (albedo weight / albedo rejection) runs the DDA formulation
 // below; deterministic mode and microscopic Beer-Lambert keep the reference's

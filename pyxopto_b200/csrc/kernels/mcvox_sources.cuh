@@ -230,7 +230,7 @@ struct VoxSrcIsotropicVoxel {
 	template <class Ctx>
 	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
 		(void)prev_pos;
-		const float lim = 1.0f - 1.1920928955078125e-07f;      // FP_1 - FP_EPS
+		const float lim = 1.0f - XO_FP_EPS;      // FP_1 - FP_EPS
 		L.pos.x = ((float)vx + fminf(rng.next(), lim))*ctx.cfg.size.x + ctx.cfg.top_left.x;
 		L.pos.y = ((float)vy + fminf(rng.next(), lim))*ctx.cfg.size.y + ctx.cfg.top_left.y;
 		L.pos.z = ((float)vz + fminf(rng.next(), lim))*ctx.cfg.size.z + ctx.cfg.top_left.z;
@@ -257,7 +257,7 @@ struct VoxSrcIsotropicVoxels {
 		if (pick > (i32)(n - 1u)) pick = (i32)(n - 1u);
 		const float *entry = ctx.lut + offset + (u32)pick*4u;
 		const float w = entry[0], vx = entry[1], vy = entry[2], vz = entry[3];
-		const float lim = 1.0f - 1.1920928955078125e-07f;      // FP_1 - FP_EPS
+		const float lim = 1.0f - XO_FP_EPS;      // FP_1 - FP_EPS
 		L.pos.x = (vx + fminf(rng.next(), lim))*ctx.cfg.size.x + ctx.cfg.top_left.x;
 		L.pos.y = (vy + fminf(rng.next(), lim))*ctx.cfg.size.y + ctx.cfg.top_left.y;
 		L.pos.z = (vz + fminf(rng.next(), lim))*ctx.cfg.size.z + ctx.cfg.top_left.z;

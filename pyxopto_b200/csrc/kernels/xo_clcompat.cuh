@@ -338,7 +338,7 @@ struct McSimState {
 struct McSim {
 	McSimState state;
 	xo::Rng *rng;
-	const void *pf, *source, *det_top, *det_bottom, *det_specular, *layers;
+	const void *pf, *source, *det_top, *det_bottom, *det_specular, *layers, *fluence;
 	mc_int_t num_layers;
 	const mc_fp_t *fp_lut_array;
 	mc_accu_t *accumulator_buffer;
@@ -388,6 +388,12 @@ struct McSim {
 #define mcsim_top_detector(psim) (static_cast<const McTopDetector *>((psim)->det_top))
 #define mcsim_bottom_detector(psim) (static_cast<const McBottomDetector *>((psim)->det_bottom))
 #define mcsim_specular_detector(psim) (static_cast<const McSpecularDetector *>((psim)->det_specular))
+#define mcsim_fluence(psim) (static_cast<const McFluence *>((psim)->fluence))
+// low-level deposit of a fluence fragment (mcml.template.c:229-240): one 64-bit RED to
+// the accumulator at `offset`
+#define mcsim_fluence_weight_deposit_ll(psim, offset, weight) \
+	atomicAdd(reinterpret_cast<unsigned long long *>((psim)->accumulator_buffer + (offset)), \
+		(unsigned long long)(uint32_t)(weight))
 // `mcsim_specular_detector_deposit(psim, ppos, pdir, w)` is two things in the
 // reference: the function a specular-detector fragment defines and the call a
 // source fragment makes from mcsim_launch.  The host wraps *source* fragments in

@@ -12,7 +12,7 @@ __device__ __forceinline__ void clc_sim_init(McSim &sim, Rng *rng) {
 	sim.rng = rng;
 	sim.pf = nullptr; sim.source = nullptr;
 	sim.det_top = nullptr; sim.det_bottom = nullptr; sim.det_specular = nullptr;
-	sim.layers = nullptr; sim.num_layers = 0;
+	sim.layers = nullptr; sim.num_layers = 0; sim.fluence = nullptr;
 	sim.fp_lut_array = nullptr;
 	sim.accumulator_buffer = nullptr;
 	sim.state.position = P3{ 0.0f, 0.0f, 0.0f };
@@ -50,6 +50,25 @@ __device__ __forceinline__ void SrcUser::launch(Rng &rng, const Ctx &ctx, Launch
 	L.layer = sim.state.layer_index;
 	L.spec_dir = sim.spec_dir;
 	L.spec_weight = sim.spec_weight;
+}
+#endif
+
+#if XO_USER_FLUENCE
+__device__ __forceinline__ void FluUser::deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float opl) const {
+	McSim sim;
+	Rng none; none.load(0ull); none.a = 0u;
+	clc_sim_init(sim, &none);
+	sim.fluence = &f;
+	sim.accumulator_buffer = acc.global;
+	sim.state.position = pos;
+	sim.state.weight = w; sim.state.optical_pathlength = opl;
+	mc_point3f_t pos_ = pos;
+#if XO_FLUENCE_RATE
+	mcsim_fluence_deposit_at(&sim, &pos_, w, mua);
+#else
+	(void)mua;
+	mcsim_fluence_deposit_at(&sim, &pos_, w);
+#endif
 }
 #endif
 

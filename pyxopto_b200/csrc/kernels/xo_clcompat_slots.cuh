@@ -27,9 +27,34 @@
 #define XO_USER_DET_SPECULAR 0
 #endif
 
+#ifndef XO_USER_FLUENCE
+#define XO_USER_FLUENCE 0
+#endif
+
 namespace xo {
 
 struct Launch;
+
+#if XO_USER_FLUENCE
+// fluence / deposition accumulator: `inline void mcsim_fluence_deposit_at(McSim *,
+// mc_point3f_t const *position, mc_fp_t weight[, mc_fp_t mua])` (the mua argument with
+// MC_FLUENCE_MODE_RATE, mcfluence/fluence.py:103-108); the fragment deposits with
+// mcsim_fluence_weight_deposit_ll
+struct FluUser {
+	McFluence f;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = true;     // (the facade carries the optical path length)
+	static constexpr bool fixed_point = false;  // the fragment converts the weight itself
+	struct Prep { };
+	struct Far { };
+	__device__ __forceinline__ Prep prepare(const FluWindow &) const { return Prep(); }
+	__device__ __forceinline__ Far prepare_far(const FluWindow &) const { return Far(); }
+	__device__ __forceinline__ float fixed_scale(float) const { return 1.0f; }
+	__device__ __forceinline__ void deposit(const Accu &acc, const FluWindow &, const P3 &pos, float w, float mua, float opl) const;
+	__device__ __forceinline__ void deposit_prep(const Accu &, const Prep &, const FluWindow &, const P3 &, u32, float) const { }
+	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0u; }
+};
+#endif
 
 #if XO_USER_PF
 // scattering phase function: `inline mc_fp_t mcsim_pf_sample_angles(McSim *, mc_fp_t *azimuth)`

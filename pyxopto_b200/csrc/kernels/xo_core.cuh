@@ -31,12 +31,19 @@ typedef DetMath M;
 typedef FastMath M;
 #endif
 
-#define XO_FP_2PI 6.283185307179586f
-#define XO_FP_COS_30 0.8660254037844386f
-#define XO_FP_INV_C 3.3356409519815204e-09f
-#define XO_FP_RMIN 1e-12f
-#define XO_FP_PLMIN 1e-12f
+#define XO_FP_2PI XO_FP(6.283185307179586)
+#define XO_FP_PI XO_FP(3.141592653589793)
+#define XO_FP_COS_30 XO_FP(0.8660254037844386)
+#define XO_FP_INV_C XO_FP(3.3356409519815204e-09)
+#define XO_FP_RMIN XO_FP(1e-12)
+#define XO_FP_PLMIN XO_FP(1e-12)
 #define XO_ACCU_K 8388607.0f
+// machine epsilon of the kernels' floating-point type (FP_EPS, mcbase.template.h:457-470)
+#if XO_DOUBLE
+#define XO_FP_EPS 2.220446049250313e-16
+#else
+#define XO_FP_EPS 1.1920929e-07f
+#endif
 
 // event flags (values as in mcbase.template.h:664-681 so Trace event masks mean the same)
 enum : u32 {
@@ -120,7 +127,21 @@ struct Rng {
 			"}" : "+r"(lo), "+r"(hi) : "r"(a));
 	}
 #endif
+#if XO_DOUBLE
+	// fp_random_double (mcbase.template.c:1610-1628): the divisor 0xFFFFFFFF is exact in
+	// binary64 (a true division); the enhanced one, 2^64 - 1, rounds to 2^64
+	__device__ __forceinline__ double next() {
+		step();
 #if XO_ENHANCED_RNG
+		const u32 high = low();
+		step();
+		return __ull2double_rn(((u64)high << 32) + low())*5.421010862427522e-20;
+#else
+		return __ddiv_rn(__uint2double_rn(low()), 4294967295.0);
+#endif
+	}
+	__device__ __forceinline__ double next_raw() { return next()*4294967296.0; }
+#elif XO_ENHANCED_RNG
 	// MC_USE_ENHANCED_RNG (mcbase.template.c:1577-1586): two steps per draw,
 	// u = RN(float(u64)) * 2^-64 (the reference's divisor rounds to 2^64)
 	__device__ __forceinline__ float next() {

@@ -13,6 +13,7 @@ struct FluNone {
 	i32 dummy;
 	static constexpr bool active = false;
 	static constexpr bool needs_opl = false;
+	static constexpr bool fixed_point = true;
 	__device__ __forceinline__ void deposit(const Accu &, const FluWindow &, const P3 &, float, float, float) const {}
 	__device__ __forceinline__ void deposit_fixed(const Accu &, const FluWindow &, const P3 &, u32, float) const {}
 	__device__ __forceinline__ float fixed_scale(float) const { return 0.0f; }
@@ -71,6 +72,7 @@ struct FluXyz {                     // mcfluence/fluence.py:57-63
 	P3 inv_step, top_left; u32 nx, ny, nz, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
+	static constexpr bool fixed_point = true;
 	// The reference tests 0 <= f < n in floating point and then truncates
 	// (fluence.py:103-143).  floor-conversion + one unsigned compare per axis is
 	// the same predicate for every non-NaN f: negative f floors to a negative
@@ -117,6 +119,7 @@ struct FluRz {                      // mcfluence/fluencerz.py:64-72
 	P3 center; float inv_dr, inv_dz; u32 n_r, n_z, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
+	static constexpr bool fixed_point = true;
 	// bounds test in the integer domain, see FluXyz::deposit (fluencerz.py:112-160)
 	// Throughput loops: the grid constants in the form the deposit uses them, held
 	// in registers for the whole kernel (the kernel passes them through shared
@@ -193,6 +196,7 @@ struct FluXyzt {                    // mcfluence/fluencet.py:57-63
 	float inv_step[4], top_left[4]; u32 shape[4]; u32 offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = true;
+	static constexpr bool fixed_point = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
 	struct Far { };
@@ -225,6 +229,7 @@ struct FluRzt {                     // mcfluence/fluencerzt.py:54-66
 	P3 center; float t_min, inv_dr, inv_dz, inv_dt; u32 n_r, n_z, n_t, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = true;
+	static constexpr bool fixed_point = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
 	struct Far { };
@@ -258,6 +263,7 @@ struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
 	u32 n_r, n_fi, n_z, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
+	static constexpr bool fixed_point = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
 	struct Far { };
@@ -275,7 +281,7 @@ struct FluCyl {                     // mcfluence/fluencecyl.py:56-70
 	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &, const P3 &pos, u32 wfix, float) const {
 		float dx = pos.x - center.x, dy = pos.y - center.y;
 		float r = M::sqrt(dx*dx + dy*dy);
-		float fi = M::atan2(dy, dx) + 3.141592653589793f;
+		float fi = M::atan2(dy, dx) + XO_FP_PI;
 		float fr = (r - r_min)*inv_dr, fz = (pos.z - z_min)*inv_dz, ffi = (fi - fi_min)*inv_dfi;
 		if (fr >= 0.0f && fz >= 0.0f && ffi >= 0.0f &&
 				fr < (float)n_r && fz < (float)n_z && ffi < (float)n_fi) {
@@ -290,6 +296,7 @@ struct FluCylt {                    // mcfluence/fluencecylt.py:79-95
 	u32 n_r, n_fi, n_z, n_t, offset; i32 k;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = true;
+	static constexpr bool fixed_point = true;
 	__device__ __forceinline__ u32 window_index(const FluWindow &, u32) const { return 0; }
 	struct Prep { };
 	struct Far { };
@@ -305,7 +312,7 @@ struct FluCylt {                    // mcfluence/fluencecylt.py:79-95
 	__device__ __forceinline__ void deposit_fixed(const Accu &acc, const FluWindow &, const P3 &pos, u32 wfix, float opl) const {
 		float dx = pos.x - center.x, dy = pos.y - center.y;
 		float r = M::sqrt(dx*dx + dy*dy);
-		float fi = M::atan2(dy, dx) + 3.141592653589793f;
+		float fi = M::atan2(dy, dx) + XO_FP_PI;
 		float dt = opl*XO_FP_INV_C - t_min;
 		float fr = (r - r_min)*inv_dr, fz = (pos.z - z_min)*inv_dz;
 		float ffi = (fi - fi_min)*inv_dfi, ft = dt*inv_dt;

@@ -15,6 +15,16 @@
 //    within 1 ulp of glibc/OpenCL built-ins.
 #pragma once
 
+#ifndef XO_DOUBLE
+#define XO_DOUBLE 0
+#endif
+// literal in the kernels' floating-point type
+#if XO_DOUBLE
+#define XO_FP(x) x
+#include "xo_math_double.cuh"
+#else
+#define XO_FP(x) x##f
+
 namespace xo {
 
 #define XO_INF __int_as_float(0x7f800000)
@@ -262,3 +272,5 @@ struct DetMath {
 };
 
 }  // namespace xo
+
+#endif  // !XO_DOUBLE

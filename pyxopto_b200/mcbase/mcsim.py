@@ -126,7 +126,12 @@ class McBase(CuWorker):
         return lists
 
     def resolved_options(self) -> dict:
-        return mcoptions.resolve_cl_options(*self._plugin_option_lists())
+        opts = mcoptions.resolve_cl_options(*self._plugin_option_lists())
+        if opts.get('MC_USE_DOUBLE_PRECISION'):
+            # binary64 runs use the reference-structured loops only (static schedule,
+            # reference expression order, no contraction): csrc/kernels/xo_math_double.cuh
+            opts['XO_DETERMINISTIC'] = True
+        return opts
 
     @property
     def deterministic(self) -> bool:
@@ -186,12 +191,10 @@ class McBase(CuWorker):
     def kernel_source(self, block: int = DEFAULT_BLOCK, min_blocks: int = 1) -> str:
         """The CUDA translation unit for the current plugin set / options."""
         opts = self.resolved_options()
-        if opts.get('MC_USE_DOUBLE_PRECISION'):
-            raise NotImplementedError('Double precision kernels are not part of the '
-                                      'accelerated path.')
         trace_flags = int(opts.get('MC_USE_TRACE', 0))
         lines = [
             '// generated by pyxopto_b200 ({})'.format(self.geometry),
+            '#define XO_DOUBLE {}'.format(int(bool(opts.get('MC_USE_DOUBLE_PRECISION', False)))),
             '#define XO_DETERMINISTIC {}'.format(int(bool(opts.get('XO_DETERMINISTIC', False)))),
             '#define XO_METHOD {}'.format(int(opts.get('MC_METHOD', 0))),
             '#define XO_USE_LOTTERY {}'.format(int(bool(opts.get('MC_USE_LOTTERY', True)))),
@@ -239,9 +242,14 @@ class McBase(CuWorker):
                 cu_type = self._USER_ADAPTERS[name][0]
             lines.append('typedef {} {};'.format(cu_type, name))
             if cl_type is not None:
+                size = ctypes.sizeof(cl_type)
+                if opts.get('MC_USE_DOUBLE_PRECISION') and size % 8:
+                    # a host struct declared with _pack_ = 1 (mccyl FiZ) has no tail
+                    # padding; the device struct is naturally aligned - the member
+                    # offsets agree and the enclosing struct is checked as a whole
+                    size += 8 - size % 8
                 checks.append('static_assert(sizeof({}) == {}, "{} layout differs from '
-                              'the packed host struct");'.format(
-                                  name, ctypes.sizeof(cl_type), name))
+                              'the packed host struct");'.format(name, size, name))
         if user:
             if self.clcompat_geometry_header:
                 lines.append('#include "{}"'.format(self.clcompat_geometry_header))
@@ -270,6 +278,7 @@ class McBase(CuWorker):
         'XoDetTop': ('xo::DetUserTop', 'XO_USER_DET_TOP'),
         'XoDetBottom': ('xo::DetUserBottom', 'XO_USER_DET_BOTTOM'),
         'XoDetSpecular': ('xo::DetUserSpecular', 'XO_USER_DET_SPECULAR'),
+        'XoFluence': ('xo::FluUser', 'XO_USER_FLUENCE'),
     }
     user_plugin_slots = ('XoPf',)        # slots of this geometry that take fragments
     clcompat_geometry_header = None
@@ -325,7 +334,8 @@ class McBase(CuWorker):
         in fixed point (weight <= 1, deposition mode, k <= 0x7FFFFF): the kernel then
         converts with one FFMA + LOP3 instead of the conversion unit."""
         flu = self._fluence
-        if flu is None or opts.get('MC_FLUENCE_MODE_RATE', False):
+        if flu is None or opts.get('MC_FLUENCE_MODE_RATE', False) or \
+                getattr(flu, 'cu_type', None) is None:
             return False
         wmin = float(opts.get('MC_PACKET_WEIGHT_MIN', 1e-4))
         chance = float(opts.get('MC_PACKET_LOTTERY_CHANCE', 0.1))
@@ -373,6 +383,8 @@ class McBase(CuWorker):
         if self._trace is None or tr is None:
             return 0
         off = int(tr.data_buffer_offset)
+        if np.dtype(self._types.np_float).itemsize != 4:
+            return 0                    # binary64 events: plain stores
         wide = os.environ.get('XOPTO_TRACE_STORE', '256') == '256'     # developer knob
         return 2 if (off % 8 == 0 and wide) else (1 if off % 4 == 0 else 0)
 

@@ -4,6 +4,10 @@ The photon-packet kernels of this engine compute in fp32 with 32-bit integers /
 size_t and 64-bit fixed-point accumulators - the reference's default family
 ``McDataTypesSingle``.  ``McDataTypesSingleCnt64`` only widens the host-side
 packet counter bookkeeping (runs above 2**32-1 packets are split in batches).
+``McDataTypesDouble`` / ``McDataTypesDoubleCnt64`` (mctypes.py:647-748,991-1044)
+switch ``mc_fp_t`` to binary64: packed structs, trace rows and lookup tables carry
+doubles and the kernels are compiled with ``XO_DOUBLE`` (reference expression order,
+IEEE double arithmetic, CUDA's double-precision elementary functions).
 """
 import ctypes
 
@@ -90,6 +94,35 @@ class McDataTypesSingle:
 
 
 class McDataTypesSingleCnt64(McDataTypesSingle):
+    """As above; the host splits runs of more than 2**32-1 packets in batches."""
+    np_cnt = np.uint64
+    mc_cnt_max = 0xFFFFFFFFFFFFFFFF
+
+
+class McDataTypesDouble(McDataTypesSingle):
+    """fp64 / int32 / 32-bit size_t / 32-bit packet counter / 64-bit accumulators."""
+    mc_fp_t = ctypes.c_double
+    np_float = np.float64
+    mc_fp_maxint = 0xFFFFFFFFFFFFF          # 52 bits (McDouble.mc_fp_maxint)
+    eps = float(np.finfo(np.float64).eps)
+
+    mc_point2f_t = _vec('mc_point2f_t', ctypes.c_double, 'xy')
+    mc_point3f_t = _vec('mc_point3f_t', ctypes.c_double, 'xyz')
+    mc_point4f_t = _vec('mc_point4f_t', ctypes.c_double, 'xyzw')
+    mc_matrix3f_t = type('mc_matrix3f_t', (_Matrix3,),
+                         {'_fields_': [(f, ctypes.c_double) for f in _M3_FIELDS]})
+    mc_matrix2f_t = _vec('mc_matrix2f_t', ctypes.c_double, ['a_11', 'a_12', 'a_21', 'a_22'])
+
+    @classmethod
+    def cl_options(cls, *_):
+        return [('MC_USE_DOUBLE_PRECISION', True),
+                ('MC_USE_64_BIT_SIZE_T', False), ('MC_USE_64_BIT_INTEGER', False),
+                ('MC_USE_64_BIT_PACKET_COUNTER', False),
+                ('MC_USE_64_BIT_ACCUMULATORS', True),
+                ('MC_INT_ACCUMULATOR_K', cls.mc_accu_k)]
+
+
+class McDataTypesDoubleCnt64(McDataTypesDouble):
     """As above; the host splits runs of more than 2**32-1 packets in batches."""
     np_cnt = np.uint64
     mc_cnt_max = 0xFFFFFFFFFFFFFFFF

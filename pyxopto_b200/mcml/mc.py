@@ -93,7 +93,8 @@ class Mc(McBase):
             out.append(('XoFluence', 'xo::FluNone', None))
         return out
 
-    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular')
+    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular',
+                         'XoFluence')
     clcompat_geometry_header = 'xo_clcompat_mcml.cuh'
 
     def _plugin_objects(self):
@@ -101,7 +102,8 @@ class Mc(McBase):
         return {'XoPf': self._layers[1].pf, 'XoSource': self._source,
                 'XoDetTop': dets.top if dets is not None else None,
                 'XoDetBottom': dets.bottom if dets is not None else None,
-                'XoDetSpecular': dets.specular if dets is not None else None}
+                'XoDetSpecular': dets.specular if dets is not None else None,
+                'XoFluence': self._fluence}
 
     def _surface_bindings(self):
         layouts = self._surface if self._surface is not None else mcsurface.SurfaceLayouts()

@@ -538,6 +538,17 @@ def mcml_user_cubic(mc, **kw):
                  rnginit=515151, **kw), dict(rmax=20e-3)
 
 
+def mcml_user_fluence(mc, **kw):
+    """A fluence accumulator written by a user (1-D deposition profile over depth)
+    around built-in plugins."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), bottom=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det,
+                 fluence=up.user_depth(mc, Axis(0.0, 3e-3, 60)),
+                 rnginit=616161, **kw), dict(rmax=20e-3)
+
+
 MCML_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
 ALL_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
 GEOMETRY['mcml_user_plugins_native'] = 'mcml'
@@ -545,10 +556,13 @@ GOLDEN_RUN['mcml_user_plugins_native'] = (3000, 16)
 # cases with user fragments: golden vectors come from the reference kernel
 # executing the same fragments; there is no C restatement of user code, so the
 # oracle pins them through the equivalent built-in case (value) where one exists
-USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_user_cubic}
-USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None}
+USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_user_cubic,
+              'mcml_user_fluence': mcml_user_fluence}
+USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None,
+                   'mcml_user_fluence': None}
 USER_GEOMETRY = {name: 'mcml' for name in USER_CASES}
-USER_RUN = {'mcml_user_plugins': (3000, 16), 'mcml_user_cubic': (3000, 16)}
+USER_RUN = {'mcml_user_plugins': (3000, 16), 'mcml_user_cubic': (3000, 16),
+            'mcml_user_fluence': (3000, 16)}
 
 
 # ---------------------------------------------------------------------------
@@ -1151,3 +1165,37 @@ GOLDEN_RUN['mcvox_aniso_gauss_fluence'] = (2000, 16)
 UNPINNED_CASES['mccyl_aniso_line_fiz'] = mccyl_aniso_line_fiz
 UNPINNED_GEOMETRY['mccyl_aniso_line_fiz'] = 'mccyl'
 UNPINNED_RUN['mccyl_aniso_line_fiz'] = (1500, 16)
+
+
+# ---------------------------------------------------------------------------
+# binary64 kernels (McDataTypesDouble, mcbase/mctypes.py:647-748,991-1044).  No C
+# restatement exists for this family: the golden vectors (the reference kernel rendered
+# in double precision, libm) pin the CUDA path directly.
+def _double(mc):
+    return mc.mctypes.McDataTypesDouble
+
+
+def mcml_double_mhg_gauss_cart_flurz(mc, **kw):
+    return mcml_mhg_gauss_cart_flurz(mc, types=_double(mc), **kw)
+
+
+def mcml_double_lut_iso_radialpl_trace(mc, **kw):
+    return mcml_lut_iso_radialpl_trace(mc, types=_double(mc), **kw)
+
+
+def mcvox_double_gauss_fluence(mc, **kw):
+    return mcvox_gauss_fluence(mc, types=_double(mc), **kw)
+
+
+def mccyl_double_hg_line_fiz(mc, **kw):
+    return mccyl_hg_line_fiz(mc, types=_double(mc), **kw)
+
+
+DOUBLE_CASES = {
+    'mcml_double_mhg_gauss_cart_flurz': mcml_double_mhg_gauss_cart_flurz,
+    'mcml_double_lut_iso_radialpl_trace': mcml_double_lut_iso_radialpl_trace,
+    'mcvox_double_gauss_fluence': mcvox_double_gauss_fluence,
+    'mccyl_double_hg_line_fiz': mccyl_double_hg_line_fiz,
+}
+DOUBLE_GEOMETRY = {name: name.split('_')[0] for name in DOUBLE_CASES}
+DOUBLE_RUN = {name: (1500, 16) for name in DOUBLE_CASES}

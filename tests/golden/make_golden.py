@@ -106,15 +106,17 @@ def main(argv):
     import cases
     from refkernel import RefKernel
     import importlib
-    names = argv or (list(cases.ALL_CASES) + list(cases.USER_CASES))
+    names = argv or (list(cases.ALL_CASES) + list(cases.USER_CASES) + list(cases.DOUBLE_CASES))
     for name in names:
-        geom = cases.GEOMETRY.get(name) or cases.USER_GEOMETRY[name]
+        geom = cases.GEOMETRY.get(name) or cases.USER_GEOMETRY.get(name) or \
+            cases.DOUBLE_GEOMETRY[name]
         mc = importlib.import_module('xopto.{}.mc'.format(geom))
-        make = cases.ALL_CASES.get(name) or cases.USER_CASES[name]
+        make = cases.ALL_CASES.get(name) or cases.USER_CASES.get(name) or \
+            cases.DOUBLE_CASES[name]
         sim, attrs = make(mc, cl_devices=mc.cl.Context())
         for k, v in attrs.items():
             setattr(sim, k, v)
-        n, t = cases.GOLDEN_RUN.get(name) or cases.USER_RUN[name]
+        n, t = cases.GOLDEN_RUN.get(name) or cases.USER_RUN.get(name) or cases.DOUBLE_RUN[name]
         rk = RefKernel(sim, geom, 'golden_' + name)
         res = rk.run(n, t)
         out = {'packed_' + k: np.frombuffer(v, np.uint8) for k, v in rk.packed_bytes().items()}

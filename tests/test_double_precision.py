@@ -1,0 +1,92 @@
+"""Binary64 kernels (``McDataTypesDouble``, xopto/mcbase/mctypes.py:647-748,991-1044).
+
+Golden vectors: the REFERENCE kernel rendered in double precision and compiled for
+the CPU (oracle/refkernel.py with -DXO_REF_DOUBLE; generated in the container that
+holds the reference).  The CUDA kernels are compiled with XO_DOUBLE: the same text in
+binary64, reference expression and draw order, static block schedule.
+
+CPU: packed structs byte-identical to the reference's double-precision packing, the
+translation units compile for sm_100a.  GPU: accumulators, trace rows and advanced MWC
+states against the golden vectors - IEEE operations are identical, CUDA's and glibc's
+``log`` / ``sincos`` / ``cbrt`` may differ in the last place of a double, which moves a
+fixed-point deposit by one unit at most once in ~1e9 deposits and a branch never in
+practice: integer buffers are expected (and required) to be equal, float rows to 1e-12.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+import cases
+from helpers import golden, packed_bytes
+
+
+def _sim(name, **kw):
+    geom = cases.DOUBLE_GEOMETRY[name]
+    mc = importlib.import_module('pyxopto_b200.{}.mc'.format(geom))
+    sim, attrs = cases.DOUBLE_CASES[name](mc, **kw)
+    for k, v in attrs.items():
+        setattr(sim, k, v)
+    return sim, geom, mc
+
+
+@pytest.mark.parametrize('name', sorted(cases.DOUBLE_CASES))
+def test_double_structs_pack_like_the_reference(name):
+    sim, _, _ = _sim(name)
+    g = golden(name)
+    sim._pack(int(g['nphotons']))
+    mine = packed_bytes(sim)
+    keys = [k for k in g.files if k.startswith('packed_')]
+    assert keys
+    for key in keys:
+        assert mine[key[len('packed_'):]] == g[key].tobytes(), key
+    if len(sim._float_lut):
+        lut = sim._float_lut.pack_into(None)
+        assert lut.dtype == np.float64 and g['lut'].dtype == np.float64
+        assert np.array_equal(lut[:g['lut'].size], g['lut'][:lut.size])
+    assert np.array_equal(sim.rng_seeds_x[:int(g['nthreads'])], g['rng_x0'])
+
+
+@pytest.mark.parametrize('name', sorted(cases.DOUBLE_CASES))
+def test_double_kernels_compile_for_sm100a(name):
+    sim, _, _ = _sim(name)
+    cubin, log, _ = sim.compile(1000, block=64)
+    assert len(cubin) > 10000
+    src = sim._last_src
+    assert '#define XO_DOUBLE 1' in src and '#define XO_DETERMINISTIC 1' in src
+    assert sim.deterministic        # binary64 runs use the reference-structured loops
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(cases.DOUBLE_CASES))
+def test_double_precision_against_the_reference_kernel(name):
+    sim, geom, _ = _sim(name)
+    g = golden(name)
+    n, t = int(g['nphotons']), int(g['nthreads'])
+    sim.run(n, maxthreads=t, wgsize=t, download=False)
+    assert sim.run_report['launched_threads'] == t
+    accu, ints, floats = sim.download_raw()
+    assert floats.dtype == np.float64
+    assert accu.sum() > 0
+    assert np.array_equal(accu, g['accu'])
+    assert np.array_equal(ints, g['ints'])
+    assert np.array_equal(sim.download_seeds()[:t], g['rng_x_after'])
+    assert np.allclose(floats, g['floats'], rtol=1e-12, atol=1e-18)
+    assert sim.run_report['threads'] == int(g['num_kernels'])
+
+
+@pytest.mark.gpu
+def test_double_results_come_back_in_reference_units():
+    sim, _, _ = _sim('mcml_double_mhg_gauss_cart_flurz')
+    trace, fluence, detectors = sim.run(20000)
+    assert fluence.raw.dtype == np.float64 and detectors.top.raw.sum() > 0
+    single = importlib.import_module('pyxopto_b200.mcml.mc')
+    ref, attrs = cases.mcml_mhg_gauss_cart_flurz(single)
+    for k, v in attrs.items():
+        setattr(ref, k, v)
+    _, flu32, det32 = ref.run(20000)
+    # the two precisions are the same physics (different draws): totals within 5 sigma
+    a, b = detectors.top.raw.sum()/20000, det32.top.raw.sum()/20000
+    assert abs(a - b) < 5*np.sqrt(2*b/20000)
+    a, b = fluence.raw.sum()/20000, flu32.raw.sum()/20000
+    assert abs(a - b) < 5*np.sqrt(2*b/20000)

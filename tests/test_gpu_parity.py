@@ -498,7 +498,7 @@ def test_user_fragments_match_reference_kernel(name):
     n_fast = 200000
     sim_f, accu_f, _ = _raw_run(name, n_fast, deterministic=False)
     K = 0x7FFFFF
-    for det in sim_f.detectors:
+    for det in list(sim_f.detectors) + ([sim_f.fluence] if sim_f.fluence is not None else []):
         for al in sim_f.cl_rw_accumulator_allocator.allocations(det):
             tot_gpu = accu_f[al.offset:al.offset + al.size].sum()/K/n_fast
             tot_ref = g['accu'][al.offset:al.offset + al.size].sum()/K/n

@@ -49,8 +49,9 @@ def test_pipelined_sweep_equals_one_run_per_configuration():
     assert (total > 0.01).all() and (total < 1.0).all()
     # more absorption -> less diffuse reflectance at fixed scattering
     assert total[0] > total[3] > total[6]
-    # rank 1 of 2 simulates the odd configurations
+    # rank 1 of 2 simulates its share of the fixed permutation
     sweep2 = mcsweep.Sweep(_sweep_sim()[0], rank=1, world=2)
     idx2, rows2 = sweep2.run(configs, n, maxthreads=1024, wgsize=64)
-    assert idx2.tolist() == list(range(1, len(configs), 2))
+    assert idx2.tolist() == mcsweep.partition(len(configs), 2, 1).tolist()
+    assert 0 < len(idx2) < len(configs)
     assert rows2.shape == (len(idx2), rows.shape[1])

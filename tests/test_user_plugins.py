@@ -40,7 +40,7 @@ def test_user_structs_pack_like_the_reference(name):
     sim._pack(run_size(name)[0])
     g = golden(name)
     mine = packed_bytes(sim)
-    for key in ('layers', 'source', 'detectors'):
+    for key in ('layers', 'source', 'detectors') + (('fluence',) if 'packed_fluence' in g.files else ()):
         assert mine[key] == g['packed_' + key].tobytes(), key
 
 
@@ -54,7 +54,12 @@ def test_user_fragments_compile_for_sm100a(name, deterministic):
     assert len(cubin) > 10000
     assert 'error' not in log.lower()
     src = sim._last_src
-    assert '#include "xo_clcompat.cuh"' in src and 'mcsim_pf_sample_angles' in src
+    assert '#include "xo_clcompat.cuh"' in src
+    if name == 'mcml_user_fluence':
+        assert 'mcsim_fluence_deposit_at' in src and 'typedef xo::FluUser XoFluence;' in src
+        assert 'typedef xo::PfHg XoPf;' in src
+        return
+    assert 'mcsim_pf_sample_angles' in src
     # built-in slots stay hand-written CUDA
     assert ('typedef xo::SrcLine XoSource;' in src) == (name == 'mcml_user_cubic')
 

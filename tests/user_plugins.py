@@ -286,3 +286,86 @@ inline void mcsim_{loc}_detector_deposit(
 
 def user_radial(mc, axis, cosmin=0.0):
     return _user_radial_class(mc)(axis, cosmin)
+
+
+@functools.lru_cache(maxsize=None)
+def _user_depth_class(mc):
+    """Deposited weight per depth slice - a fluence plugin a user wrote: 1-D, its
+    own packed struct, its own result conversion."""
+    cltypes = _cltypes(mc)
+
+    class UserDepth(mc.McObject):
+        @staticmethod
+        def cl_type(mc_):
+            T = mc_.types
+            class ClUserDepth(cltypes.Structure):
+                _fields_ = [('z_min', T.mc_fp_t), ('inv_dz', T.mc_fp_t),
+                            ('n', T.mc_size_t), ('offset', T.mc_size_t), ('k', T.mc_int_t)]
+            return ClUserDepth
+
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McFluence{ mc_fp_t z_min; mc_fp_t inv_dz; ' \
+                   'mc_size_t n; mc_size_t offset; mc_int_t k; };\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_fluence(__mc_fluence_mem const McFluence *fluence){
+	dbg_print("user-written depth profile:");
+	dbg_print_size_t(INDENT "n:", fluence->n);
+};
+
+inline void mcsim_fluence_deposit_at(
+		McSim *mcsim, mc_point3f_t const *position, mc_fp_t weight){
+	__mc_fluence_mem McFluence const *fluence = mcsim_fluence(mcsim);
+	mc_fp_t indexf = (position->z - fluence->z_min)*fluence->inv_dz;
+	if (indexf >= FP_0 && indexf < fluence->n){
+		mc_size_t index = mc_uint(indexf);
+		uint32_t ui32w = (uint32_t)(weight*fluence->k + FP_0p5);
+		mcsim_fluence_weight_deposit_ll(mcsim, fluence->offset + index, ui32w);
+	};
+};
+'''
+
+        def cl_options(self, mc_):
+            return [('MC_USE_FLUENCE', True), ('MC_FLUENCE_MODE_RATE', False)]
+
+        def __init__(self, zaxis, k=0x7FFFFF):
+            super().__init__()
+            if isinstance(zaxis, UserDepth):
+                other = zaxis
+                zaxis, k = other._axis, other._k
+            self._axis, self._k = zaxis, int(k)
+            self._raw = np.zeros((zaxis.n,))
+            self._nphotons = 0
+
+        raw = property(lambda self: self._raw)
+        nphotons = property(lambda self: self._nphotons)
+        k = property(lambda self: self._k)
+        shape = property(lambda self: (self._axis.n,))
+        mode = 'deposition'
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            allocation = mc_.cl_allocate_rw_accumulator_buffer(self, self.shape)
+            target.offset = allocation.offset
+            target.z_min = self._axis.start
+            target.inv_dz = 1.0/self._axis.step
+            target.n = self._axis.n
+            target.k = self._k
+            return target
+
+        def update_data(self, mc_, accumulators, nphotons, **kwargs):
+            self._raw += np.reshape(accumulators[0], self.shape)*(1.0/self._k)
+            self._nphotons += int(nphotons)
+
+        def todict(self):
+            return {'type': 'UserDepth'}
+
+    return UserDepth
+
+
+def user_depth(mc, zaxis):
+    return _user_depth_class(mc)(zaxis)
