@@ -41,7 +41,13 @@ def _fragment(obj, attr, mc) -> str:
     return str(frag or '')
 
 
-def _c_float(v: float) -> str:
+def _c_float(v: float, double: bool = False) -> str:
+    """Literal in the kernels' floating-point type (FP_LITERAL of the reference)."""
+    if double:
+        v = float(v)
+        if np.isinf(v):
+            return 'XO_INF' if v > 0 else '(-XO_INF)'
+        return repr(v)
     v = float(np.float32(v))
     if np.isinf(v):
         return '__int_as_float(0x7f800000)' if v > 0 else '__int_as_float(0xff800000)'
@@ -192,6 +198,7 @@ class McBase(CuWorker):
         """The CUDA translation unit for the current plugin set / options."""
         opts = self.resolved_options()
         trace_flags = int(opts.get('MC_USE_TRACE', 0))
+        is_double = bool(opts.get('MC_USE_DOUBLE_PRECISION', False))
         lines = [
             '// generated by pyxopto_b200 ({})'.format(self.geometry),
             '#define XO_DOUBLE {}'.format(int(bool(opts.get('MC_USE_DOUBLE_PRECISION', False)))),
@@ -199,9 +206,10 @@ class McBase(CuWorker):
             '#define XO_METHOD {}'.format(int(opts.get('MC_METHOD', 0))),
             '#define XO_USE_LOTTERY {}'.format(int(bool(opts.get('MC_USE_LOTTERY', True)))),
             '#define XO_ENHANCED_RNG {}'.format(int(bool(opts.get('MC_USE_ENHANCED_RNG', False)))),
-            '#define XO_WEIGHT_MIN {}'.format(_c_float(opts.get('MC_PACKET_WEIGHT_MIN', 1e-4))),
+            '#define XO_WEIGHT_MIN {}'.format(
+                _c_float(opts.get('MC_PACKET_WEIGHT_MIN', 1e-4), is_double)),
             '#define XO_LOTTERY_CHANCE {}'.format(
-                _c_float(opts.get('MC_PACKET_LOTTERY_CHANCE', 0.1))),
+                _c_float(opts.get('MC_PACKET_LOTTERY_CHANCE', 0.1), is_double)),
             '#define XO_TRACE {}'.format(trace_flags),
             '#define XO_USE_EVENTS {}'.format(int(bool(opts.get('MC_USE_EVENTS', False)))),
             '#define XO_TRACK_OPL {}'.format(
@@ -451,7 +459,10 @@ class McBase(CuWorker):
     def _shared_layout(self, medium_bytes: int):
         """(dynamic shared bytes, lut floats staged, private bins)."""
         lut_len = 0
-        if len(self._float_lut) and self._float_lut.size*4 <= LUT_SHARED_MAX_BYTES:
+        if len(self._float_lut) and self._float_lut.size*4 <= LUT_SHARED_MAX_BYTES and \
+                np.dtype(self._types.np_float).itemsize == 4:
+            # (binary64 tables are read from global memory: the shared-memory layout of
+            # the kernels counts 4-byte words)
             lut_len = self._float_lut.size
         priv_len = 0
         if self._detectors is not None:
@@ -570,9 +581,9 @@ class McBase(CuWorker):
         cbuf = self.cl_r_buffer(self._counters_name(), counters)
         self._upload_medium()
         if len(self._float_lut):
-            lut_host = self._float_lut.pack_into(None).astype(np.float32)
+            lut_host = self._float_lut.pack_into(None).astype(self._types.np_float)
         else:
-            lut_host = np.zeros(4, np.float32)
+            lut_host = np.zeros(4, self._types.np_float)
         lbuf = self.cl_r_buffer('fp_lut', lut_host)
         abuf = self._rw_flat_buffer('accumulator', fill=not self._keep_accumulators)
         fbuf = self._rw_flat_buffer('float', fill=not self._trace_tails_unread())

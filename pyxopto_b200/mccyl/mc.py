@@ -130,7 +130,7 @@ class Mc(McBase):
             np.uint32(nphotons),
             (bufs['counters'], 0),            # num_packets_done
             (bufs['counters'], 4),            # num_kernels
-            np.float32(self._rmax),
+            self._types.np_float(self._rmax),
             bufs['rng_x'], bufs['rng_a'],
             np.uint32(len(self._layers)),
             self._cl_buffers['layers'],

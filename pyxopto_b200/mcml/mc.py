@@ -140,7 +140,7 @@ class Mc(McBase):
             T.np_cnt(nphotons) if T.np_cnt is np.uint32 else np.uint32(nphotons),
             (bufs['counters'], 0),            # num_packets_done
             (bufs['counters'], 4),            # num_kernels
-            np.float32(self._rmax),
+            self._types.np_float(self._rmax),
             bufs['rng_x'], bufs['rng_a'],
             np.uint32(len(self._layers)),
             self._cl_buffers['layers'],

@@ -242,7 +242,7 @@ class Mc(McBase):
         return [
             np.uint32(nphotons),
             (bufs['counters'], 0), (bufs['counters'], 4),
-            np.float32(self._rmax),
+            self._types.np_float(self._rmax),
             bufs['rng_x'], bufs['rng_a'],
             self._packed['voxels'],
             self._cl_buffers['voxel_data'],
