@@ -273,12 +273,16 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
             stride = max(len(grid_cfgs)//total_cfgs, 1)
             sweep_cfgs = grid_cfgs[::stride][:total_cfgs]
         sweep = mcsweep.Sweep(sim, rank, world)
+        # N > 1: a short pilot (2000 packets per configuration, the ranks pilot disjoint
+        # slices, one all-reduce of the loop-trip counts; outside the timed region, like
+        # the kernel build) lets the configurations be dealt longest-first
+        sweep_costs = sweep.pilot_costs(sweep_cfgs) if world > 1 else None
         launches_per_step = n_sweep
         ev_a, ev_b = abi.Event(sim.cl_context), abi.Event(sim.cl_context)
 
         def step_device():
             ev_a.record(sim._stream)
-            sweep.run(sweep_cfgs, packets)
+            sweep.run(sweep_cfgs, packets, costs=sweep_costs)
             ev_b.record(sim._stream)
             sim._stream.synchronize()
             rr = dict(sim.run_report)
@@ -288,7 +292,7 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
             return rr
 
         def step_e2e():
-            idx, rows = sweep.run(sweep_cfgs, packets)
+            idx, rows = sweep.run(sweep_cfgs, packets, costs=sweep_costs)
             if world > 1:
                 rows = sweep.gather(idx, rows, len(sweep_cfgs))
             refl = sweep.detector(rows, sim.detectors.top if geom != 'mccyl'
@@ -475,7 +479,7 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
             'workload': WORKLOADS.get(config, config), 'packets_per_gpu_per_step': per_step,
             'global_packets_per_step': per_step*world,
             'sweep_configs_per_gpu_per_step': n_sweep or None,
-            'parallelism': ('{} configurations per GPU dealt by a fixed permutation over {} GPU(s), no '
+            'parallelism': ('{} configurations per GPU dealt longest-first by pilot cost over {} GPU(s), no '
                             'collective on the data path'.format(n_sweep, world) if n_sweep else
                             'packets sharded over {} GPU(s), disjoint MWC seed sets{}'.format(
                                 world, ', 1 stream-ordered NCCL all-reduce of the uint64 '

@@ -36,6 +36,29 @@ def partition(n_configs: int, world: int, rank: int) -> np.ndarray:
     return np.sort(perm[rank::world]).astype(np.int64)
 
 
+def balanced_partition(costs, world: int, rank: int) -> np.ndarray:
+    """Indices (ascending) of ``rank`` for configurations of known relative cost:
+    longest-processing-time-first onto the least loaded rank, ties by index - the
+    same deterministic assignment on every rank; every rank gets the same number of
+    configurations (+-1), as ``gather()`` expects."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n, world = costs.size, int(world)
+    if world <= 1:
+        return np.arange(n, dtype=np.int64)
+    order = np.lexsort((np.arange(n), -costs))           # descending cost, stable
+    load = np.zeros(world)
+    count = np.zeros(world, dtype=np.int64)
+    cap = (n + world - 1)//world
+    owner = np.empty(n, dtype=np.int64)
+    for i in order:
+        free = np.flatnonzero(count < cap)
+        r = free[np.argmin(load[free])]
+        owner[i] = r
+        load[r] += costs[i]
+        count[r] += 1
+    return np.flatnonzero(owner == int(rank)).astype(np.int64)
+
+
 class Sweep:
     def __init__(self, sim, rank: int = 0, world: int = 1):
         """``sim``: a ``pyxopto_b200`` simulator (any geometry) whose plugin
@@ -44,9 +67,38 @@ class Sweep:
         self.sim = sim
         self.rank, self.world = int(rank), int(world)
         self.report = {}
+        self._mine = None           # assignment of the last run (gather() reuses it)
+
+    def pilot_costs(self, configs, nphotons: int = 2000, apply=None) -> np.ndarray:
+        """Relative cost of every configuration: loop trips of a short pilot run.
+        The ranks pilot disjoint slices and exchange the counts with one all-gather
+        (no exchange at world = 1).  The pilot packets are not part of any result."""
+        n = len(configs)
+        mine = np.arange(self.rank, n, self.world, dtype=np.int64)
+        saved_rank, saved_world = self.rank, self.world
+        try:
+            # (run this rank's slice through the ordinary pipelined path)
+            self._forced = mine
+            self.run(configs, nphotons, apply=apply)
+        finally:
+            self._forced = None
+            self.rank, self.world = saved_rank, saved_world
+        local = np.zeros(n, dtype=np.float64)
+        local[mine] = self.report['iterations'].astype(np.float64)
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            dev = torch.device('cuda', torch.cuda.current_device()) \
+                if dist.get_backend() == 'nccl' else torch.device('cpu')
+            t = torch.from_numpy(local).to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            local = t.cpu().numpy()
+        return local
+
+    _forced = None
 
     def run(self, configs, nphotons: int, apply=None, wgsize: int = None,
-            maxthreads: int = None):
+            maxthreads: int = None, costs=None):
         """Simulate ``nphotons`` packets for every configuration of this rank.
 
         ``configs``: sequence of configuration descriptors; ``apply(sim, cfg)``
@@ -56,11 +108,21 @@ class Sweep:
         Returns ``(indices, accumulators)``: the global indices of this rank's
         configurations and a ``uint64[len(indices), accumulator size]`` array of
         raw fixed-point accumulators (detector bins first, fluence after, pack
-        order) - ``Sweep.detector(...)`` converts rows to reference units."""
+        order) - ``Sweep.detector(...)`` converts rows to reference units.
+
+        ``costs``: relative cost per configuration (e.g. ``pilot_costs``): the
+        configurations are then dealt longest-first onto the least loaded rank
+        instead of by the fixed permutation."""
         from .cu import abi
         sim = self.sim
         apply = apply or _apply_layer_updates
-        mine = partition(len(configs), self.world, self.rank)
+        if self._forced is not None:
+            mine = self._forced
+        elif costs is not None:
+            mine = balanced_partition(costs, self.world, self.rank)
+        else:
+            mine = partition(len(configs), self.world, self.rank)
+        self._mine = (len(configs), None if costs is None else np.array(costs, copy=True))
         nphotons = int(nphotons)
         sim._ensure_device()
         t0 = time.perf_counter()
@@ -128,8 +190,11 @@ class Sweep:
         out = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(out, t)
         full = np.zeros((int(n_configs), width), np.uint64)
+        costs = self._mine[1] if self._mine is not None and self._mine[0] == int(n_configs) \
+            else None
         for r in range(self.world):
-            idx = partition(n_configs, self.world, r)
+            idx = partition(n_configs, self.world, r) if costs is None \
+                else balanced_partition(costs, self.world, r)
             full[idx] = out[r].cpu().numpy().view(np.uint64)[:idx.size]
         return full
 

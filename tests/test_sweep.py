@@ -16,6 +16,23 @@ def test_partition_is_disjoint_and_covering():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_partition_is_disjoint_covering_and_balanced():
+    rng = np.random.default_rng(3)
+    for n in (1, 9, 4096):
+        costs = rng.lognormal(0.0, 0.7, n)
+        for world in (1, 2, 8):
+            parts = [mcsweep.balanced_partition(costs, world, r) for r in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            sizes = [p.size for p in parts]
+            assert max(sizes) - min(sizes) <= 1
+            if n == 4096 and world == 8:
+                loads = np.array([costs[p].sum() for p in parts])
+                assert loads.max()/loads.mean() - 1.0 < 1e-3
+                perm = np.array([costs[mcsweep.partition(n, world, r)].sum()
+                                 for r in range(world)])
+                assert loads.max() < perm.max()
+
+
 def _configs():
     g = 0.8
     return [{1: {'mua': float(mua), 'mus': float(musr/(1.0 - g))}}
@@ -55,3 +72,26 @@ def test_pipelined_sweep_equals_one_run_per_configuration():
     assert idx2.tolist() == mcsweep.partition(len(configs), 2, 1).tolist()
     assert 0 < len(idx2) < len(configs)
     assert rows2.shape == (len(idx2), rows.shape[1])
+
+
+@pytest.mark.gpu
+def test_pilot_costs_and_balanced_deal():
+    """The pilot run reports loop trips per configuration (more scattering = more
+    trips); dealing by those costs changes which rank simulates what, not the rows."""
+    n = 20000
+    configs = _configs()
+    sweep = mcsweep.Sweep(_sweep_sim()[0])
+    costs = sweep.pilot_costs(configs, 1000)
+    assert costs.shape == (len(configs),) and (costs > 0).all()
+    assert costs.max() > 1.2*costs.min()        # the grid points differ in cost
+    # (fresh simulators: consecutive runs of one simulator continue its MWC streams)
+    idx_a, rows_a = mcsweep.Sweep(_sweep_sim()[0]).run(configs, n, maxthreads=1024, wgsize=64)
+    idx_b, rows_b = mcsweep.Sweep(_sweep_sim()[0]).run(configs, n, maxthreads=1024, wgsize=64,
+                                                       costs=costs)
+    assert idx_a.tolist() == idx_b.tolist()
+    assert np.array_equal(rows_a, rows_b)
+    # two ranks: the shares are disjoint, covering and follow the costs
+    parts = [mcsweep.Sweep(_sweep_sim()[0], rank=r, world=2) for r in range(2)]
+    got = [p.run(configs, n, maxthreads=1024, wgsize=64, costs=costs)[0] for p in parts]
+    assert sorted(np.concatenate(got).tolist()) == list(range(len(configs)))
+    assert got[0].tolist() == mcsweep.balanced_partition(costs, 2, 0).tolist()
