@@ -77,8 +77,10 @@ struct CylLayer {                   // mccyl/mclayer/layer.py:119-130
 struct __align__(16) CylHot { float ri2, ro2, step_k, step_b; };
 	// squared radii; step = lg2(raw draw)*step_k + step_b = -ln(u)/mut
 struct __align__(16) CylAbs { float absorb, mua, n, pad; };
+struct __align__(16) CylGeo { float ri, ro, pad0, pad1; };
+	// radii for the radial-clearance test (ri = -inf for the innermost layer: no inner surface)
 struct __align__(16) CylPfFast { XoPf::Fast v; };
-struct CylFastLayer { CylHot hot; CylAbs abs; CylPfFast pf; };
+struct CylFastLayer { CylHot hot; CylAbs abs; CylGeo geo; CylPfFast pf; };
 
 typedef CylDetectors<XoDetOuter, XoDetSpecular> XoDetectors;
 #if XO_TRACE
@@ -189,6 +191,8 @@ McKernel(
 		F.abs.absorb = Lg.mua_inv_mut; F.abs.mua = Lg.mua;
 #endif
 		F.abs.n = Lg.n; F.abs.pad = 0.0f;
+		F.geo.ri = (Lg.r_inner > 0.0f) ? Lg.r_inner : -XO_INF; F.geo.ro = Lg.r_outer;
+		F.geo.pad0 = 0.0f; F.geo.pad1 = 0.0f;
 		Lg.pf.prepare(F.pf.v);
 		sh_fast[i] = F;
 	}
@@ -245,6 +249,7 @@ McKernel(
 		u32 thr_eff = refill < 1u ? 1u : (refill > 32u ? 32u : refill);
 		CylHot c_hot = { 0.0f, 0.0f, 0.0f, 0.0f };
 		CylAbs c_abs = { 0.0f, 0.0f, 1.0f, 0.0f };
+		CylGeo c_geo = { 0.0f, 0.0f, 0.0f, 0.0f };
 		XoPf::Fast c_pf;
 #if XO_ANISO
 	// anisotropic layers: step / absorption constants of a (layer, direction) pair
@@ -262,7 +267,7 @@ McKernel(
 #endif
 #define XO_CYL_LOAD_LAYER(idx) do { \
 		const CylFastLayer &F_ = sh_fast[idx]; \
-		c_hot = F_.hot; c_abs = F_.abs; c_pf = F_.pf.v; \
+		c_hot = F_.hot; c_abs = F_.abs; c_geo = F_.geo; c_pf = F_.pf.v; \
 		XO_DIR_CONSTS(); \
 	} while (0)
 
@@ -345,7 +350,15 @@ McKernel(
 			++iterations;
 			float step = fminf(fmaf(FastMath::lg2(rng.next_raw()), c_hot.step_k, c_hot.step_b), XO_FLT_MAX);
 			bool hit = false, inwards = false;
-			if (dir.x != 0.0f || dir.y != 0.0f) {
+			// Radial clearance: a packet at radius r cannot reach a surface of its layer
+			// within a path shorter than min(ro - r, r - ri), whatever its direction - the
+			// ray / cylinder quadratic (2 square roots, 1 reciprocal, ~25 FMA / compares)
+			// is evaluated only for the steps that are longer than that (one square root
+			// and 5 FMA / compares otherwise; in a 5 mm cylinder with a 0.1 mm free path
+			// nearly every step).  A pure geometric bound: no statistical change.
+			const float r_now = FastMath::sqrt(fmaf(pos.x, pos.x, pos.y*pos.y));
+			const float room = fminf(c_geo.ro - r_now, r_now - c_geo.ri);
+			if (!(step < 0.9999f*room) && (dir.x != 0.0f || dir.y != 0.0f)) {
 				// distance to the inner / outer cylinder of the layer
 				// (mccyl.template.c:147-209) from the half-b form of the quadratic:
 				// a d^2 + 2 hb d + (c - r^2) = 0,  d = (-hb +- sqrt(hb^2 - a (c - r^2)))/a

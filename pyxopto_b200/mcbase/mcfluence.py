@@ -53,15 +53,17 @@ class _FluenceBase(McObject):
             self._data.shape = self.shape
             self._nphotons = nphotons
 
-    def update_scaled(self, scaled: np.ndarray, nphotons: int):
+    def update_scaled(self, scaled: np.ndarray, nphotons: int, owned: bool = False):
         """``update_data`` with the conversion ``accumulators*(1/k)`` already done
         (bit-identically) on the device: ``scaled`` is a float64 array that the
-        caller may reuse afterwards."""
+        caller may reuse afterwards - unless ``owned``: then a fresh result keeps the
+        array itself (no copy of a 65 MB grid)."""
         if self._data is not None:
             self._data += np.reshape(scaled, self._data.shape)
             self._nphotons += nphotons
         else:
-            self._data = np.array(scaled, dtype=np.float64).reshape(self.shape)
+            self._data = np.reshape(scaled, self.shape) if owned else \
+                np.array(scaled, dtype=np.float64).reshape(self.shape)
             self._nphotons = nphotons
 
     def cu_window(self, mc, max_bins: int, focus):

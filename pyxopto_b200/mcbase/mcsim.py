@@ -687,7 +687,10 @@ class McBase(CuWorker):
                 else type(self._fluence)(self._fluence)
             scaled = self._download_scaled_fluence(fluence_res)
             if scaled is not None:
-                fluence_res.update_scaled(scaled, nphotons)
+                owned = False
+                if isinstance(scaled, tuple):
+                    scaled, owned = scaled
+                fluence_res.update_scaled(scaled, nphotons, owned=owned)
             else:
                 data = self._download_allocations(self._fluence, nphotons)
                 fluence_res.update_data(self, data, nphotons=nphotons)
@@ -718,27 +721,62 @@ class McBase(CuWorker):
                 not allocs[0].download:
             return None
         src = self._cl_buffers[self._rw_name('accumulator')]
-        return self._scale_on_device(src, allocs[0], 1.0/result.k)
+        # a fresh result takes the converted grid as its own array
+        return self._scale_on_device(src, allocs[0], 1.0/result.k,
+                                     want_owned=result.raw is None)
 
-    def _scale_on_device(self, src, a, inv_k: float) -> np.ndarray:
-        """Page-locked float64 array ``accu[a]*inv_k`` computed by AccuScale."""
-        from . import rngkernel
+    # Page-locked float64 result buffers (grid conversions done on the device).  A
+    # result object may OWN such a buffer (no host copy, no first-touch page faults on
+    # 65 MB): the pool hands out views and reuses a buffer once nothing but the pool
+    # refers to it any more; at most RESULT_POOL buffers are kept per size.
+    RESULT_POOL = 3
+
+    def _pinned_result(self, size: int):
+        """(array, owned): a page-locked float64[size]; ``owned`` True when the caller
+        may keep it (a pool buffer that is free), False when it is the shared staging
+        array that the next conversion overwrites."""
+        import sys
         from ..cu import abi
+        pool = self._pinned_downloads.setdefault(('result_pool', size), [])
+        for buf in pool:
+            # (views of a view share the root array as their base: count its referrers -
+            # the pool's own array, the local name and the argument)
+            root = buf.base if buf.base is not None else buf
+            if sys.getrefcount(root) <= 3:
+                return buf.view(), True
+        if len(pool) < self.RESULT_POOL:
+            buf = abi.pinned_empty(self._ctx, (size,), np.float64)
+            pool.append(buf)
+            return buf.view(), True
+        key = ('accu_scaled', size)
+        host = self._pinned_downloads.get(key)
+        if host is None:
+            host = abi.pinned_empty(self._ctx, (size,), np.float64)
+            self._pinned_downloads[key] = host
+        return host, False
+
+    def _scale_on_device(self, src, a, inv_k: float, want_owned: bool = False):
+        """Page-locked float64 array ``accu[a]*inv_k`` computed by AccuScale (with
+        ``want_owned``: ``(array, owned)``, see ``_pinned_result``)."""
+        from . import rngkernel
         mod = rngkernel._aux_module(self, True)
         out = self._buffer('accu_scaled', a.size*8)
         grid = 4*self._ctx.info['multiprocessor_count']
         mod.kernel('AccuScale').launch(
             self._stream, grid, 512,
             [(src, a.offset*8), out, np.uint64(a.size), np.float64(inv_k)])
-        key = ('accu_scaled', a.size)
-        host = self._pinned_downloads.get(key)
-        if host is None:
-            if len(self._pinned_downloads) >= 4:
-                self._pinned_downloads.clear()
-            host = abi.pinned_empty(self._ctx, (a.size,), np.float64)
-            self._pinned_downloads[key] = host
+        if want_owned:
+            host, owned = self._pinned_result(int(a.size))
+        else:
+            key = ('accu_scaled', a.size)
+            host = self._pinned_downloads.get(key)
+            if host is None:
+                from ..cu import abi
+                host = abi.pinned_empty(self._ctx, (a.size,), np.float64)
+                self._pinned_downloads[key] = host
+            owned = False
         out.download(self._stream, host)
-        return host
+        return (host, owned) if want_owned else host
 
     # -- device-side trace filter (SURVEY 8f-1) ------------------------------------
     # True: a Trace with a Filter is filtered and compacted on the device and

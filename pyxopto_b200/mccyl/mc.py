@@ -66,8 +66,8 @@ class Mc(McBase):
 
     def _medium_bytes(self) -> int:
         # packed layers + the per-layer derived constants the throughput kernel
-        # appends (xo::CylFastLayer, <= 96 B per layer)
-        return len(cltypes.raw_bytes(self._packed['layers'])) + 96*len(self._layers) + 32
+        # appends (xo::CylFastLayer, <= 112 B per layer)
+        return len(cltypes.raw_bytes(self._packed['layers'])) + 112*len(self._layers) + 32
 
     def _upload_medium(self):
         self.cl_r_buffer('layers', self._packed['layers'])

@@ -623,3 +623,25 @@ def test_lazy_trace_rows_equal_eager_rows():
     for a, b in zip(out[True], out[False]):
         assert a.shape == b.shape and a.size > 0
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_large_fluence_results_own_their_pinned_grid():
+    """Grids converted on the device land in a pooled page-locked array that a fresh
+    result keeps without a copy; a later result must not alias an earlier one that is
+    still alive, and a released buffer is reused."""
+    sim = _det_sim('mcvox_gauss_fluence')[0]
+    sim.SCALE_ON_DEVICE_MIN = 1
+    kw = dict(maxthreads=256, wgsize=64)
+    _, flu_a, _ = sim.run(2000, **kw)
+    keep = np.array(flu_a.raw, copy=True)
+    _, flu_b, _ = sim.run(2000, **kw)
+    assert not np.shares_memory(flu_a.raw, flu_b.raw)
+    assert np.array_equal(flu_a.raw, keep) and flu_a.raw.sum() > 0
+    addr_a = flu_a.raw.__array_interface__['data'][0]
+    del flu_a
+    _, flu_c, _ = sim.run(2000, **kw)
+    _, flu_d, _ = sim.run(2000, **kw)
+    addrs = {f.raw.__array_interface__['data'][0] for f in (flu_b, flu_c, flu_d)}
+    assert len(addrs) == 3 and addr_a in addrs          # the released buffer came back
+    _, flu_e, _ = sim.run(2000, **kw)                   # pool exhausted: plain copy
+    assert not any(np.shares_memory(flu_e.raw, f.raw) for f in (flu_b, flu_c, flu_d))
