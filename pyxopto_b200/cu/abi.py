@@ -287,6 +287,10 @@ class Buffer:
         return v.value
 
     def upload(self, stream: Stream, host, offset: int = 0, blocking: bool = True):
+        if isinstance(host, (bytes, bytearray)):
+            # (a read-only array view keeps the bytes alive for the whole call; an
+            # asynchronous upload of a temporary object is the caller's business)
+            host = np.frombuffer(host, dtype=np.uint8)
         raw, nbytes = _host_ptr(host)
         check(lib().xo_copy_h2d(stream.handle, self.handle, offset, raw, nbytes,
                                 int(blocking)))
@@ -357,8 +361,8 @@ def _host_ptr(host):
             raise ValueError('host array must be C-contiguous')
         return host.ctypes.data, host.nbytes
     if isinstance(host, (bytes, bytearray)):
-        buf = (ctypes.c_char*len(host)).from_buffer_copy(host)
-        return ctypes.addressof(buf), len(host)
+        raise TypeError('pass bytes through numpy.frombuffer(): a temporary copy would be '
+                        'freed before the copy engine reads it')
     return ctypes.addressof(host), ctypes.sizeof(host)
 
 

@@ -488,6 +488,10 @@ class McBase(CuWorker):
         tr = self._trace
         if tr is None or tr.filter is None or not self.device_trace_filter:
             return False
+        if self.resolved_options().get('MC_USE_EVENTS', False):
+            # with an event mask a packet can record nothing at all: the filter then
+            # reads slot maxlen - 1 of its row (numpy's index -1), which must be zero
+            return False
         allocs = self._allocators['float'].allocations()
         return bool(allocs) and all(a.owner is tr for a in allocs)
 
