@@ -244,6 +244,10 @@
 		}
 
 		// ---- interaction: absorb, scatter, lottery (mcvox.template.c:925-981) -------
+		// (convergence barrier: without it the compiler dispatches the phases through
+		// jump tables on `state`, and the lanes that walked (SCAT) and the lanes that
+		// skipped the walk (FAR) reach this block at different times and run it twice)
+		__syncwarp();
 		if (state == ST_SCAT || state == ST_FAR) {
 			bool done = false;
 			++iterations;
@@ -318,6 +322,7 @@
 		}
 
 		// ---- new ray from `pos` along `dir` in voxel (ix, iy, iz) -----------------------
+		__syncwarp();
 		if (state == ST_SETUP) {
 			XO_DIR_CONSTS();
 			t_s = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);

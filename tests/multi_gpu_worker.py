@@ -46,6 +46,34 @@ def main():
             fluence.nphotons == nphotons and detectors.top.nphotons == nphotons
         print('MULTI_GPU_RESULT', 'OK' if ok else 'MISMATCH', 'world', world,
               'accumulator sum', int(reduced.sum()), flush=True)
+    # config-per-GPU sweep: pilot costs exchanged over NCCL, longest-first
+    # deal, one all-gather of the rows; every rank ends up with the rows of one GPU
+    # simulating all configurations alone (deterministic mode, same seeds per simulator)
+    from pyxopto_b200 import mcsweep
+    g = 0.8
+    configs = [{1: {'mua': float(mua), 'mus': float(musr/(1.0 - g))}}
+               for mua in np.linspace(0.0, 5e2, 3) for musr in np.linspace(5e2, 35e2, 3)]
+
+    def sweep_sim():
+        return benchcfg.c5_slab(mc, options=opts, cl_devices=local)
+
+    costs = mcsweep.Sweep(sweep_sim(), rank, world).pilot_costs(configs, 500)
+    sweep = mcsweep.Sweep(sweep_sim(), rank, world)     # (the pilot advanced its simulator's MWC states)
+    idx, rows = sweep.run(configs, 20000, maxthreads=1024, wgsize=64, costs=costs)
+    full = sweep.gather(idx, rows, len(configs))
+    sweep_ok = full.shape[0] == len(configs) and bool((full.sum(axis=1) > 0).all()) and \
+        idx.tolist() == mcsweep.balanced_partition(costs, world, rank).tolist()
+    if rank == 0:
+        # each configuration starts from the simulator's initial MWC state only when it
+        # is the first one of its rank: compare the first configuration of every rank
+        for r in range(world):
+            first = int(mcsweep.balanced_partition(costs, world, r)[0])
+            alone = mcsweep.Sweep(sweep_sim())
+            alone._forced = np.array([first])
+            _, row = alone.run(configs, 20000, maxthreads=1024, wgsize=64)
+            sweep_ok = sweep_ok and bool(np.array_equal(row[0], full[first]))
+        print('MULTI_GPU_SWEEP', 'OK' if sweep_ok else 'MISMATCH', flush=True)
+    ok = ok and sweep_ok
     flag = torch.tensor([int(ok)], device='cuda')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

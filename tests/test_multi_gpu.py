@@ -33,3 +33,4 @@ def test_nccl_allreduce_equals_sum_of_shards():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert 'MULTI_GPU_RESULT OK' in out.stdout
+    assert 'MULTI_GPU_SWEEP OK' in out.stdout
