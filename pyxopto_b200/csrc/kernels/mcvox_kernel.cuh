@@ -71,6 +71,9 @@ typedef TraceNone XoTrace;
 #define XO_VOX_PACKED 0
 #endif
 #define XO_VOX_DDA (!XO_DETERMINISTIC && XO_METHOD != 2 && XO_VOX_PACKED)
+#ifndef XO_VOX_POOL
+#define XO_VOX_POOL 0               // slots of the per-warp packet pool (0: lane-resident packets)
+#endif
 #define XO_VOX_SENTINEL 255
 
 // Per-material record of the throughput loop, derived once per CTA when the
@@ -216,10 +219,23 @@ McKernel(
 	// per-warp launch queue: 32 slots of {pos, weight | dir, packet | trace count}
 	off_words += 2*priv_len + win_len;
 	off_words = (off_words + 3u) & ~3u;
+#if XO_VOX_POOL
+	// per-warp packet pool (mcvox_pool_loop.cuh): XO_VOX_POOL slots of 4 x float4 + 1 float,
+	// one state byte per slot, 32 bytes of gather indices
+	const u32 pool_warps = blockDim.x >> 5, pool_warp = threadIdx.x >> 5;
+	float4 *P_A = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + pool_warp*XO_VOX_POOL;
+	float4 *P_B = P_A + pool_warps*XO_VOX_POOL;
+	float4 *P_C = P_B + pool_warps*XO_VOX_POOL;
+	float4 *P_D = P_C + pool_warps*XO_VOX_POOL;
+	float *P_E = reinterpret_cast<float *>(P_D + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
+	unsigned char *P_ST = reinterpret_cast<unsigned char *>(P_E + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
+	unsigned char *P_IDX = P_ST + (pool_warps - pool_warp)*XO_VOX_POOL + pool_warp*32u;
+#else
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;
 	u32 *q_l = reinterpret_cast<u32 *>(xo_smem) + off_words + blockDim.x*8u + (threadIdx.x & ~31u);
 	u32 *q_v = q_l + blockDim.x;    // voxel (low address word of the compact map) of the launch point
+#endif
 #endif
 	__syncthreads();
 
@@ -236,7 +252,9 @@ McKernel(
 
 	bool started = false;
 	u32 iterations = 0;
-#if XO_VOX_DDA
+#if XO_VOX_DDA && XO_VOX_POOL
+#include "mcvox_pool_loop.cuh"
+#elif XO_VOX_DDA
 #include "mcvox_dda_loop.cuh"
 #else
 	(void)refill; (void)voxels8; (void)vox_bx; (void)vox_by;

@@ -1,0 +1,448 @@
+// mcvox_pool_loop.cuh -- throughput loop of the voxel kernel with a per-warp packet
+// pool (body fragment, included inside McKernel of mcvox_kernel.cuh when XO_VOX_POOL).
+//
+// Same physics and the same ray formulation as mcvox_dda_loop.cuh (one ray per
+// flight, incremental voxel walk over the compact 16-bit map, clearance shortcut,
+// inline material change at equal refractive index; mcvox.template.c:667-1014), but
+// the packets do not live in the registers of "their" lane.  In the lane-resident loop
+// every phase - interaction, ray set-up, voxel walk, interface - runs with the lanes
+// that happen to be in that state: 22 / 5 / 12 / 1.3 of 32 on the 201^3 skin model
+// (profiles/r02s_*c3*).  Here a warp owns XO_VOX_POOL (64) packet slots in shared
+// memory; every round it takes a census of the slot states (one REDUX), picks the phase
+// with the most candidates, gathers up to 32 slots of that class by rank, loads exactly
+// the fields the phase needs, runs the phase with (nearly) full lanes - several passes
+// while enough lanes stay in the class - and stores the packets back:
+//
+//   INTERACT  slots NEW / RAY / SCAT / FAR: [voxel of the end point of a flight that
+//             skipped the walk] deposit, scattering, lottery, then the next free path
+//             and the clearance test -> FAR (again this phase) / DDA / EMPTY
+//   WALK      slots DDA (first: walk set-up) and RUN: two crossings per trip until fewer
+//             than XO_POOL_THR_W lanes still walk -> SCAT / BND / RUN
+//   BOUNDARY  slots BND: interface physics at a face between materials of different
+//             refractive index, or the face of the grid -> RAY / EMPTY
+//   LAUNCH    EMPTY slots, while the packet budget lasts -> NEW
+//
+// A slot is 17 words: A = pos | weight, B = dir | free path (or the event parameter of
+// a BND slot), C = next-face parameters | voxel address, D = per-voxel increments |
+// material, clearance, axis of the last crossing, direction signs; E = optical path
+// length.  The MWC stream belongs to the lane, not to the packet (throughput mode is
+// not stream-aligned with the reference anyway).
+//
+// Host conditions (mcvox/mc.py): compact map, throughput mode, albedo weight /
+// albedo rejection, no trace, isotropic materials, rmax test compiled out.
+{
+	enum : u32 { PS_EMPTY = 0, PS_NEW = 1, PS_RAY = 2, PS_SCAT = 3, PS_FAR = 4, PS_DDA = 5, PS_RUN = 6, PS_BND = 7 };
+	enum : u32 { PH_INTERACT = 0, PH_WALK = 1, PH_BOUNDARY = 2, PH_LAUNCH = 3 };
+#ifndef XO_POOL_THR_I
+#define XO_POOL_THR_I 20        // INTERACT repeats while this many lanes skip the walk again
+#endif
+#ifndef XO_POOL_THR_W
+#define XO_POOL_THR_W 16        // WALK goes on while this many lanes still walk
+#endif
+#ifndef XO_POOL_LAUNCH
+#define XO_POOL_LAUNCH 24       // EMPTY slots that trigger a LAUNCH
+#endif
+#ifndef XO_POOL_BND
+#define XO_POOL_BND 12          // BND slots that trigger a BOUNDARY phase
+#endif
+	static_assert(XO_VOX_POOL == 64, "the census reads two slots per lane");
+	constexpr u32 S = XO_VOX_POOL;
+	const u32 lane = threadIdx.x & 31u;
+	const u32 lanemask_lt = (1u << lane) - 1u;
+	const u32 vox_bxy = vox_bx + vox_by;
+	const u32 vox_mx = (1u << vox_bx) - 1u, vox_my = (1u << vox_by) - 1u;
+	(void)chunk; (void)nthreads; (void)refill; (void)rmax2; (void)src_pos; (void)int_buffer; (void)float_buffer;
+	const u32 vbase_lo = (u32)reinterpret_cast<u64>(voxels8);
+	const u32 vbase_hi = (u32)(reinterpret_cast<u64>(voxels8) >> 32);
+	const float inv_sx = 1.0f/cfg.size.x, inv_sy = 1.0f/cfg.size.y, inv_sz = 1.0f/cfg.size.z;
+#define XO_VOXEL(lo) ((u32)__ldg(reinterpret_cast<const unsigned short *>(((u64)vbase_hi << 32) | (u64)(lo))))
+#define XO_PACK_VOXEL(ix_, iy_, iz_) (vbase_lo + 2u*((u32)((ix_) + 2) | ((u32)((iy_) + 2) << vox_bx) | ((u32)((iz_) + 2) << vox_bxy)))
+#define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
+	// slots of this warp
+	P_ST[lane] = (unsigned char)PS_EMPTY;
+	P_ST[lane + 32u] = (unsigned char)PS_EMPTY;
+	P_A[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	P_A[lane + 32u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	__syncwarp();
+	bool dry = false;               // warp-uniform: the packet budget is exhausted
+
+	for (;;) {
+		// ---- census of the slot states: class counts in the bytes of one word ------------
+		u32 nI, nD, nW, nB, nE;
+		const u32 s0 = P_ST[lane], s1 = P_ST[lane + 32u];
+		{
+			const u32 w0 = s0 ? (1u << (8u*(max(s0, 4u) - 4u))) : 0u;
+			const u32 w1 = s1 ? (1u << (8u*(max(s1, 4u) - 4u))) : 0u;
+			const u32 cen = __reduce_add_sync(0xffffffffu, w0 + w1);
+			nI = cen & 0xffu; nD = (cen >> 8) & 0xffu; nW = (cen >> 16) & 0xffu; nB = cen >> 24;
+			nE = S - (nI + nD + nW + nB);
+		}
+		u32 phase;
+		if (!dry && nE >= XO_POOL_LAUNCH) phase = PH_LAUNCH;
+		else if (nE == S) break;
+		else if (nB >= XO_POOL_BND || (nB >= nI && nB >= nD + nW)) phase = PH_BOUNDARY;
+		else phase = (nI >= nD + nW) ? PH_INTERACT : PH_WALK;
+
+		// ---- gather up to 32 slots of the phase's class(es), first class first -----------
+		u32 slot = 0;
+		bool act;
+		{
+			u32 f0, f1, g0, g1;     // first / second class membership of the two own slots
+			if (phase == PH_INTERACT) {
+				f0 = (s0 >= PS_NEW && s0 <= PS_FAR); f1 = (s1 >= PS_NEW && s1 <= PS_FAR); g0 = g1 = 0u;
+			} else if (phase == PH_WALK) {
+				f0 = (s0 == PS_DDA); f1 = (s1 == PS_DDA); g0 = (s0 == PS_RUN); g1 = (s1 == PS_RUN);
+			} else if (phase == PH_BOUNDARY) {
+				f0 = (s0 == PS_BND); f1 = (s1 == PS_BND); g0 = g1 = 0u;
+			} else {
+				f0 = (s0 == PS_EMPTY); f1 = (s1 == PS_EMPTY); g0 = g1 = 0u;
+			}
+			const u32 mf0 = __ballot_sync(0xffffffffu, f0), mf1 = __ballot_sync(0xffffffffu, f1);
+			u32 n = (u32)__popc(mf0);
+			if (f0) P_IDX[__popc(mf0 & lanemask_lt)] = (unsigned char)lane;
+			u32 r = n + (u32)__popc(mf1 & lanemask_lt);
+			if (f1 && r < 32u) P_IDX[r] = (unsigned char)(lane + 32u);
+			n += (u32)__popc(mf1);
+			if (phase == PH_WALK) {
+				const u32 mg0 = __ballot_sync(0xffffffffu, g0), mg1 = __ballot_sync(0xffffffffu, g1);
+				r = n + (u32)__popc(mg0 & lanemask_lt);
+				if (g0 && r < 32u) P_IDX[r] = (unsigned char)lane;
+				n += (u32)__popc(mg0);
+				r = n + (u32)__popc(mg1 & lanemask_lt);
+				if (g1 && r < 32u) P_IDX[r] = (unsigned char)(lane + 32u);
+				n += (u32)__popc(mg1);
+			}
+			__syncwarp();
+			act = lane < n;         // (n may exceed 32: the rest waits for the next round)
+			if (act) slot = P_IDX[lane];
+			__syncwarp();
+		}
+
+		if (phase == PH_INTERACT) {
+			// ======== interaction + next free path (mcvox.template.c:925-981, 667-700) ========
+			u32 st = PS_EMPTY, vlo = vbase_lo, mat = 0, dcur = 1;
+			P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
+			float weight = 0.0f, t_s = 0.0f, opl = 0.0f;
+			(void)opl;
+			if (act) {
+				st = P_ST[slot];
+				const float4 a = P_A[slot], b = P_B[slot];
+				pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
+				dir.x = b.x; dir.y = b.y; dir.z = b.z; t_s = b.w;
+				vlo = __float_as_uint(P_C[slot].w);
+				const u32 misc = __float_as_uint(P_D[slot].w);
+				mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu;
+				if (XO_NEEDS_OPL) opl = P_E[slot];
+				if (st == PS_NEW) { const u32 cell = XO_VOXEL(vlo); mat = cell & 0xffu; dcur = cell >> 8; }
+			}
+			VoxHot c_hot;
+			XoPf::Fast c_pf;
+			XO_LOAD_MAT(mat);
+			for (;;) {
+				if (st == PS_SCAT || st == PS_FAR) {
+					bool done = false;
+					++iterations;
+					pos.x = fmaf(dir.x, t_s, pos.x);
+					pos.y = fmaf(dir.y, t_s, pos.y);
+					pos.z = fmaf(dir.z, t_s, pos.z);
+					if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_s, opl);
+					u32 mat_here = mat;
+					if (st == PS_FAR) {
+						// the flight skipped the walk: voxel of the interaction point from the
+						// position, loop trips of the reference = faces crossed on the way
+						const u32 idx0 = (vlo - vbase_lo) >> 1;
+						i32 ix = __float2int_rd((pos.x - cfg.top_left.x)*inv_sx);
+						i32 iy = __float2int_rd((pos.y - cfg.top_left.y)*inv_sy);
+						i32 iz = __float2int_rd((pos.z - cfg.top_left.z)*inv_sz);
+						ix = clipi(ix, 0, cfg.nx - 1);
+						iy = clipi(iy, 0, cfg.ny - 1);
+						iz = clipi(iz, 0, cfg.nz - 1);
+						iterations += (u32)(abs(ix - ((i32)(idx0 & vox_mx) - 2)) +
+							abs(iy - ((i32)((idx0 >> vox_bx) & vox_my) - 2)) +
+							abs(iz - ((i32)(idx0 >> vox_bxy) - 2)));
+						vlo = XO_PACK_VOXEL(ix, iy, iz);
+						const u32 cell = XO_VOXEL(vlo);
+						dcur = cell >> 8;
+						// (a rounding of the end point across a face of the clearance box can
+						// land in another material: adopted after this interaction)
+						if ((cell & 0xffu) != XO_VOX_SENTINEL) mat_here = cell & 0xffu;
+					}
+#if XO_METHOD == 1
+					if (rng.next() < c_hot.absorb) {
+						float deposit = weight;
+						done = true;
+						weight = 0.0f;
+						if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
+					} else {
+						pf_scatter(c_pf, rng, lut, dir);
+					}
+#else
+					{
+						float deposit = weight*c_hot.absorb;
+						weight -= deposit;
+#if XO_FLU_VOXGRID
+						{   // the fluence grid is the voxel grid: the cell is the voxel of the packet
+							const u32 idx = (vlo - vbase_lo) >> 1;
+							fluence.deposit_cell(acc, (idx & vox_mx) - 2u, ((idx >> vox_bx) & vox_my) - 2u,
+								(idx >> vox_bxy) - 2u, fluence_weight(deposit, c_hot.mua, fluence.k));
+						}
+#else
+						if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
+#endif
+					}
+					pf_scatter(c_pf, rng, lut, dir);
+					if (weight < XO_WEIGHT_MIN) {
+#if XO_USE_LOTTERY
+						if (rng.next_raw() > XO_LOTTERY_CHANCE*4294967296.0f) done = true;
+						else weight *= (1.0f/XO_LOTTERY_CHANCE);
+#else
+						done = true;
+#endif
+					}
+#endif
+					if (mat_here != mat) { mat = mat_here; XO_LOAD_MAT(mat); }
+					if (weight <= 0.0f) done = true;
+					st = done ? PS_EMPTY : PS_RAY;
+				}
+				if (st == PS_RAY || st == PS_NEW) {
+					t_s = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
+					// extent of the flight in voxels along its longest axis against the clearance
+					const float ext = t_s*fmaxf(fabsf(dir.x)*inv_sx, fmaxf(fabsf(dir.y)*inv_sy, fabsf(dir.z)*inv_sz));
+					st = (ext < (float)dcur - 1.0f) ? PS_FAR : PS_DDA;
+				}
+				if ((u32)__popc(__ballot_sync(0xffffffffu, st == PS_FAR)) < XO_POOL_THR_I) break;
+			}
+			if (act) {
+				P_A[slot] = make_float4(pos.x, pos.y, pos.z, weight);
+				P_B[slot] = make_float4(dir.x, dir.y, dir.z, t_s);
+				P_C[slot].w = __uint_as_float(vlo);
+				P_D[slot].w = __uint_as_float(mat | (dcur << 8));
+				if (XO_NEEDS_OPL) P_E[slot] = opl;
+				P_ST[slot] = (unsigned char)st;
+			}
+		} else if (phase == PH_WALK) {
+			// ======== walk set-up (DDA slots) and voxel walk =====================================
+			u32 st = PS_EMPTY, vlo = vbase_lo, mat = 0, dcur = 1, sg = 7u, axis = 0;
+			float tmx = XO_INF, tmy = XO_INF, tmz = XO_INF, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
+			float t_s = 0.0f, t_evt = 0.0f;
+			if (act) {
+				st = P_ST[slot];
+				const float4 b = P_B[slot];
+				t_s = b.w;
+				if (st == PS_DDA) {
+					const float4 a = P_A[slot];
+					vlo = __float_as_uint(P_C[slot].w);
+					const u32 misc = __float_as_uint(P_D[slot].w);
+					mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu;
+					const float rx = FastMath::rcp_approx(b.x), ry = FastMath::rcp_approx(b.y),
+						rz = FastMath::rcp_approx(b.z);
+					const bool fx = b.x >= 0.0f, fy = b.y >= 0.0f, fz = b.z >= 0.0f;
+					sg = (fx ? 1u : 0u) | (fy ? 2u : 0u) | (fz ? 4u : 0u);
+					// exit faces of the current voxel (mcvox.template.c:173-196); the packed
+					// index holds coordinate + 2
+					const u32 idx = (vlo - vbase_lo) >> 1;
+					const float facex = fmaf((float)((i32)(idx & vox_mx) - (fx ? 1 : 2)), cfg.size.x, cfg.top_left.x);
+					const float facey = fmaf((float)((i32)((idx >> vox_bx) & vox_my) - (fy ? 1 : 2)), cfg.size.y, cfg.top_left.y);
+					const float facez = fmaf((float)((i32)(idx >> vox_bxy) - (fz ? 1 : 2)), cfg.size.z, cfg.top_left.z);
+					tmx = (b.x != 0.0f) ? fmaxf((facex - a.x)*rx, 0.0f) : XO_INF;
+					tmy = (b.y != 0.0f) ? fmaxf((facey - a.y)*ry, 0.0f) : XO_INF;
+					tmz = (b.z != 0.0f) ? fmaxf((facez - a.z)*rz, 0.0f) : XO_INF;
+					tdx = cfg.size.x*fabsf(rx);
+					tdy = cfg.size.y*fabsf(ry);
+					tdz = cfg.size.z*fabsf(rz);
+					st = PS_RUN;
+				} else {
+					const float4 c = P_C[slot], d = P_D[slot];
+					tmx = c.x; tmy = c.y; tmz = c.z; vlo = __float_as_uint(c.w);
+					tdx = d.x; tdy = d.y; tdz = d.z;
+					const u32 misc = __float_as_uint(d.w);
+					mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu; sg = (misc >> 18) & 7u;
+				}
+			}
+			const i32 stx = (sg & 1u) ? 2 : -2;
+			const i32 sty = ((sg & 2u) ? 2 : -2) << vox_bx;
+			const i32 stz = ((sg & 4u) ? 2 : -2) << vox_bxy;
+			float step_k = sh_fast[mat].hot.step_k;
+			(void)step_k;
+			// Two crossings per trip; the lookup of the second one is issued before the first
+			// has returned, and committed only if the first one stayed inside the material.
+			for (;;) {
+				if (st == PS_RUN) {
+					const float tmin_a = fminf(tmx, fminf(tmy, tmz));
+					if (!(tmin_a < t_s)) {
+						st = PS_SCAT;
+					} else {
+						++iterations;
+						const bool px = (tmx == tmin_a);
+						const bool py = !px && (tmy == tmin_a);
+						const bool pz = !px && !py;
+						if (px) tmx += tdx;
+						if (py) tmy += tdy;
+						if (pz) tmz += tdz;
+						const i32 d_a = px ? stx : (py ? sty : stz);
+						const u32 ax_a = px ? 0u : (py ? 1u : 2u);
+						vlo += (u32)d_a;
+						const u32 cell_a = XO_VOXEL(vlo);
+						const u32 m_a = cell_a & 0xffu;
+						// second crossing, speculative
+						const float tmin_b = fminf(tmx, fminf(tmy, tmz));
+						const bool ok_b = tmin_b < t_s;
+						const bool qx = (tmx == tmin_b);
+						const bool qy = !qx && (tmy == tmin_b);
+						const bool qz = !qx && !qy;
+						const i32 d_b = qx ? stx : (qy ? sty : stz);
+						const u32 vlo_b = vlo + (u32)d_b;
+						u32 cell_b = 0x100u | mat;
+						if (ok_b) cell_b = XO_VOXEL(vlo_b);
+						const u32 m_b = cell_b & 0xffu;
+						dcur = cell_a >> 8;
+#if XO_VOX_SAME_N
+						// Equal refractive indices everywhere: a face between two materials is no
+						// interface event, only the attenuation changes; the remaining optical depth
+						// of the flight is still Exp(1) distributed, so the free path is rescaled to
+						// the new material (the grid face stays an event).
+#define XO_MATERIAL_CHANGE(m_, tmin_) do { \
+							const float k_new_ = sh_fast[m_].hot.step_k; \
+							t_s = fmaf(t_s - (tmin_), k_new_*FastMath::rcp_approx(step_k), (tmin_)); \
+							step_k = k_new_; \
+							mat = (m_); \
+						} while (0)
+#define XO_IS_PLAIN_CHANGE(m_) ((m_) < XO_VOX_SENTINEL && step_k > -XO_FLT_MAX && t_s < XO_FLT_MAX)
+#else
+#define XO_MATERIAL_CHANGE(m_, tmin_) do { } while (0)
+#define XO_IS_PLAIN_CHANGE(m_) false
+#endif
+						if (m_a != mat) {
+							if (XO_IS_PLAIN_CHANGE(m_a)) {
+								XO_MATERIAL_CHANGE(m_a, tmin_a);
+							} else {
+								st = PS_BND; t_evt = tmin_a; axis = ax_a;
+							}
+						} else if (!ok_b) {
+							st = PS_SCAT;
+						} else {
+							++iterations;
+							if (qx) tmx += tdx;
+							if (qy) tmy += tdy;
+							if (qz) tmz += tdz;
+							vlo = vlo_b;
+							dcur = cell_b >> 8;
+							if (m_b != mat) {
+								if (XO_IS_PLAIN_CHANGE(m_b)) {
+									XO_MATERIAL_CHANGE(m_b, tmin_b);
+								} else {
+									st = PS_BND; t_evt = tmin_b; axis = qx ? 0u : (qy ? 1u : 2u);
+								}
+							}
+						}
+#undef XO_MATERIAL_CHANGE
+#undef XO_IS_PLAIN_CHANGE
+					}
+				}
+				if ((u32)__popc(__ballot_sync(0xffffffffu, st == PS_RUN)) < XO_POOL_THR_W) break;
+			}
+			if (act) {
+				P_B[slot].w = (st == PS_BND) ? t_evt : t_s;
+				P_C[slot] = make_float4(tmx, tmy, tmz, __uint_as_float(vlo));
+				P_D[slot] = make_float4(tdx, tdy, tdz,
+					__uint_as_float(mat | (dcur << 8) | (axis << 16) | (sg << 18)));
+				P_ST[slot] = (unsigned char)st;
+			}
+		} else if (phase == PH_BOUNDARY) {
+			// ======== a face between materials of different refractive index, or the face of
+			// the grid (mcvox.template.c:275-388); the walk already moved the voxel address
+			// across the face, along `axis` =========================================================
+			if (act) {
+				const float4 a = P_A[slot], b = P_B[slot];
+				P3 pos = { a.x, a.y, a.z }, dir = { b.x, b.y, b.z };
+				float weight = a.w, opl = 0.0f;
+				const float t_evt = b.w;
+				u32 vlo = __float_as_uint(P_C[slot].w);
+				const u32 misc = __float_as_uint(P_D[slot].w);
+				u32 mat = misc & 0xffu;
+				const u32 axis = (misc >> 16) & 3u, sg = (misc >> 18) & 7u;
+				if (XO_NEEDS_OPL) opl = P_E[slot];
+				const VoxHot hot = sh_fast[mat].hot;
+				bool done = false;
+				pos.x = fmaf(dir.x, t_evt, pos.x);
+				pos.y = fmaf(dir.y, t_evt, pos.y);
+				pos.z = fmaf(dir.z, t_evt, pos.z);
+				if (XO_NEEDS_OPL) opl = fmaf(hot.n, t_evt, opl);
+				const u32 entered = XO_VOXEL(vlo) & 0xffu;
+				const bool escaping = (entered == XO_VOX_SENTINEL);
+				const u32 next_mat = escaping ? 0u : entered;
+				const float n1 = hot.n, n2 = sh_fast[next_mat].hot.n;
+				bool through = true;
+				if (n1 != n2) {
+					const float n12 = n1*FastMath::rcp_approx(n2);
+					const float n21 = n2*FastMath::rcp_approx(n1);
+					const float cc = (n1 > n2) ? FastMath::sqrt(fmaxf(fmaf(-n21, n21, 1.0f), 0.0f)) : 0.0f;
+					if (axis == 0u) through = fresnel_axis_fast(n12, cc, dir.x, dir.y, dir.z, rng);
+					else if (axis == 1u) through = fresnel_axis_fast(n12, cc, dir.y, dir.x, dir.z, rng);
+					else through = fresnel_axis_fast(n12, cc, dir.z, dir.x, dir.y, rng);
+				}
+				if (through) {
+					if (escaping) {
+						const i32 iz = (i32)(((vlo - vbase_lo) >> 1) >> vox_bxy) - 2;
+						if (iz < 0) {
+							if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
+						} else if (iz >= cfg.nz) {
+							if (XoDetBottom::active) detectors.bottom.deposit(acc, pos, dir, weight, opl);
+						}
+						done = true;
+					} else {
+						mat = next_mat;
+					}
+				} else {
+					// reflected: back into the voxel the packet came from
+					const i32 d = (axis == 0u) ? ((sg & 1u) ? 2 : -2) :
+						((axis == 1u) ? (((sg & 2u) ? 2 : -2) << vox_bx) : (((sg & 4u) ? 2 : -2) << vox_bxy));
+					vlo -= (u32)d;
+				}
+				if (weight <= 0.0f) done = true;
+				P_A[slot] = make_float4(pos.x, pos.y, pos.z, weight);
+				P_B[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+				P_C[slot].w = __uint_as_float(vlo);
+				P_D[slot].w = __uint_as_float(mat | (1u << 8));   // on a face: clearance 1
+				if (XO_NEEDS_OPL) P_E[slot] = opl;
+				P_ST[slot] = (unsigned char)(done ? PS_EMPTY : PS_RAY);
+			}
+		} else {
+			// ======== new packets into the EMPTY slots =============================================
+			const u32 want = (u32)__popc(__ballot_sync(0xffffffffu, act));
+			u32 base = 0;
+			if (lane == 0u) base = atomicAdd(num_packets_done, want);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			const u32 n_new = base < num_packets ?
+				(num_packets - base < want ? num_packets - base : want) : 0u;
+			dry = n_new < want;
+			if (lane < n_new) {
+				const float4 prev = P_A[slot];      // (last position of the packet that died here)
+				P3 prev_pos = { prev.x, prev.y, prev.z };
+				Launch L_;
+				source.launch(rng, ctx, prev_pos, L_);
+				if (XoDetSpecular::active && L_.spec_weight >= 0.0f)
+					detectors.specular.deposit(acc, L_.pos, L_.spec_dir, L_.spec_weight, 0.0f);
+				// voxel under the launch point (mcvox.template.c:206-220), kept inside the grid
+				i32 ix, iy, iz;
+				ctx.position_to_voxel(L_.pos, &ix, &iy, &iz);
+				ix = clipi(ix, 0, cfg.nx - 1);
+				iy = clipi(iy, 0, cfg.ny - 1);
+				iz = clipi(iz, 0, cfg.nz - 1);
+				P_A[slot] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
+				P_B[slot] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, 0.0f);
+				P_C[slot].w = __uint_as_float(XO_PACK_VOXEL(ix, iy, iz));
+				P_D[slot].w = __uint_as_float(0u);
+				if (XO_NEEDS_OPL) P_E[slot] = 0.0f;
+				P_ST[slot] = (unsigned char)PS_NEW;
+				started = true;
+			}
+		}
+		__syncwarp();
+	}
+#undef XO_LOAD_MAT
+#undef XO_VOXEL
+#undef XO_PACK_VOXEL
+	// every lane drew from its stream: all states go back
+	rng_state_x[gid] = rng.state();
+}

@@ -377,6 +377,11 @@ class McBase(CuWorker):
             return int(min(max(self.refill_lanes, 1), 32))
         return int(getattr(self._source, 'cu_refill_lanes', self.default_refill_lanes))
 
+    def _queue_bytes(self, block: int) -> int:
+        """Shared memory of the throughput loops behind the window: per-warp launch
+        queues (32 slots of 40 bytes)."""
+        return 40*block + 16
+
     def _extra_includes(self):
         return []
 
@@ -593,7 +598,7 @@ class McBase(CuWorker):
         fbuf = self._rw_flat_buffer('float', fill=not self._trace_tails_unread())
         ibuf = self._rw_flat_buffer('int')
         shared, lut_len, priv_len = self._shared_layout(self._medium_bytes())
-        queue_bytes = 0 if deterministic else 40*block + 16   # per-warp launch queues
+        queue_bytes = 0 if deterministic else self._queue_bytes(block)
         window = self._fluence_window(block, shared + queue_bytes)
         shared += 4*int(window[3])*int(window[4])*int(window[5]) + queue_bytes
         grid, block = self.launch_geometry(kernel, block, shared, maxthreads)

@@ -163,9 +163,36 @@ class Mc(McBase):
                 return False
         return True
 
+    # Per-warp packet pool of the throughput loop (csrc/kernels/mcvox_pool_loop.cuh): a warp
+    # owns 64 packet slots in shared memory and runs, every round, the phase most of them
+    # wait for.  0 keeps the packets in the registers of their lane (mcvox_dda_loop.cuh).
+    pool_slots = 64
+    pool_tuning = {}                 # XO_POOL_* thresholds (developer knob)
+
+    def _pool_slots(self, opts=None) -> int:
+        """Slots per warp, or 0 where the pool loop does not apply: it covers the compact
+        map in throughput mode with albedo weight / rejection, no trace, isotropic
+        materials and no reachable rmax sphere."""
+        opts = self.resolved_options() if opts is None else opts
+        if not self.pool_slots or self.deterministic or not self._vox_packed() or \
+                self._trace is not None or self._rmax_needed() or \
+                isinstance(self._materials[0], mcmaterial.AnisotropicMaterial) or \
+                opts.get('MC_METHOD', 0) not in (0, 1):
+            return 0
+        return int(self.pool_slots)
+
+    def _queue_bytes(self, block: int) -> int:
+        slots = self._pool_slots()
+        if slots:
+            # 4 x float4 + 1 float + 1 state byte per slot, 32 index bytes per warp
+            return (block//32)*(slots*69 + 32) + 32
+        return super()._queue_bytes(block)
+
     def _extra_defines(self, opts):
         aniso = isinstance(self._materials[0], mcmaterial.AnisotropicMaterial)
-        return ['#define XO_VOX_PACKED {}'.format(int(self._vox_packed())),
+        return ['#define XO_VOX_POOL {}'.format(self._pool_slots(opts))] + \
+            ['#define {} {}'.format(k, int(v)) for k, v in sorted(self.pool_tuning.items())] + \
+            ['#define XO_VOX_PACKED {}'.format(int(self._vox_packed())),
                 '#define XO_ANISO {}'.format(int(aniso)),
                 '#define XO_VOX_SAME_N {}'.format(
                     int(self._same_refractive_index() and not aniso)),

@@ -11,6 +11,11 @@ if os.environ.get('XO_REFILL'):
     sim.refill_lanes = int(os.environ['XO_REFILL'])
 if os.environ.get('XO_MIN_BLOCKS'):
     sim.min_blocks = int(os.environ['XO_MIN_BLOCKS'])
+if os.environ.get('XO_POOL_SLOTS'):
+    sim.pool_slots = int(os.environ['XO_POOL_SLOTS'])
+if any(k.startswith('XO_POOL_') and k != 'XO_POOL_SLOTS' for k in os.environ):
+    sim.pool_tuning = {k: int(v) for k, v in os.environ.items()
+                       if k.startswith('XO_POOL_') and k != 'XO_POOL_SLOTS'}
 sim.run(10000, download=False, **kw)
 for i in range(3):
     sim.run(n, download=False, **kw)
