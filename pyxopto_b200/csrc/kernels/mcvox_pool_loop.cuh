@@ -31,19 +31,20 @@
 // Host conditions (mcvox/mc.py): compact map, throughput mode, albedo weight /
 // albedo rejection, no trace, isotropic materials, rmax test compiled out.
 {
-	enum : u32 { PS_EMPTY = 0, PS_NEW = 1, PS_RAY = 2, PS_SCAT = 3, PS_FAR = 4, PS_DDA = 5, PS_RUN = 6, PS_BND = 7 };
+	// slot states: the class (INTERACT / WALK set-up / WALK / BOUNDARY) sits in bits 3-4
+	enum : u32 { PS_EMPTY = 0, PS_NEW = 1, PS_RAY = 2, PS_SCAT = 3, PS_FAR = 4, PS_DDA = 8, PS_RUN = 16, PS_BND = 24 };
 	enum : u32 { PH_INTERACT = 0, PH_WALK = 1, PH_BOUNDARY = 2, PH_LAUNCH = 3 };
 #ifndef XO_POOL_THR_I
-#define XO_POOL_THR_I 20        // INTERACT repeats while this many lanes skip the walk again
+#define XO_POOL_THR_I 16        // INTERACT repeats while this many lanes skip the walk again
 #endif
 #ifndef XO_POOL_THR_W
-#define XO_POOL_THR_W 16        // WALK goes on while this many lanes still walk
+#define XO_POOL_THR_W 12        // WALK goes on while this many lanes still walk
 #endif
 #ifndef XO_POOL_LAUNCH
-#define XO_POOL_LAUNCH 24       // EMPTY slots that trigger a LAUNCH
+#define XO_POOL_LAUNCH 16       // EMPTY slots that trigger a LAUNCH
 #endif
 #ifndef XO_POOL_BND
-#define XO_POOL_BND 12          // BND slots that trigger a BOUNDARY phase
+#define XO_POOL_BND 16          // BND slots that trigger a BOUNDARY phase
 #endif
 	static_assert(XO_VOX_POOL == 64, "the census reads two slots per lane");
 	constexpr u32 S = XO_VOX_POOL;
@@ -71,8 +72,8 @@
 		u32 nI, nD, nW, nB, nE;
 		const u32 s0 = P_ST[lane], s1 = P_ST[lane + 32u];
 		{
-			const u32 w0 = s0 ? (1u << (8u*(max(s0, 4u) - 4u))) : 0u;
-			const u32 w1 = s1 ? (1u << (8u*(max(s1, 4u) - 4u))) : 0u;
+			const u32 w0 = s0 ? (1u << (s0 & 24u)) : 0u;
+			const u32 w1 = s1 ? (1u << (s1 & 24u)) : 0u;
 			const u32 cen = __reduce_add_sync(0xffffffffu, w0 + w1);
 			nI = cen & 0xffu; nD = (cen >> 8) & 0xffu; nW = (cen >> 16) & 0xffu; nB = cen >> 24;
 			nE = S - (nI + nD + nW + nB);
@@ -87,16 +88,12 @@
 		u32 slot = 0;
 		bool act;
 		{
-			u32 f0, f1, g0, g1;     // first / second class membership of the two own slots
-			if (phase == PH_INTERACT) {
-				f0 = (s0 >= PS_NEW && s0 <= PS_FAR); f1 = (s1 >= PS_NEW && s1 <= PS_FAR); g0 = g1 = 0u;
-			} else if (phase == PH_WALK) {
-				f0 = (s0 == PS_DDA); f1 = (s1 == PS_DDA); g0 = (s0 == PS_RUN); g1 = (s1 == PS_RUN);
-			} else if (phase == PH_BOUNDARY) {
-				f0 = (s0 == PS_BND); f1 = (s1 == PS_BND); g0 = g1 = 0u;
-			} else {
-				f0 = (s0 == PS_EMPTY); f1 = (s1 == PS_EMPTY); g0 = g1 = 0u;
-			}
+			// class key of a slot: 0 / 8 / 16 / 24 as in the census, 32 = EMPTY; a phase takes
+			// its first class first (WALK: the slots that still need their walk set-up)
+			const u32 k0 = s0 ? (s0 & 24u) : 32u, k1 = s1 ? (s1 & 24u) : 32u;
+			const u32 key_f = (phase == PH_INTERACT) ? 0u : ((phase == PH_WALK) ? 8u :
+				((phase == PH_BOUNDARY) ? 24u : 32u));
+			const bool f0 = (k0 == key_f), f1 = (k1 == key_f);
 			const u32 mf0 = __ballot_sync(0xffffffffu, f0), mf1 = __ballot_sync(0xffffffffu, f1);
 			u32 n = (u32)__popc(mf0);
 			if (f0) P_IDX[__popc(mf0 & lanemask_lt)] = (unsigned char)lane;
@@ -104,6 +101,7 @@
 			if (f1 && r < 32u) P_IDX[r] = (unsigned char)(lane + 32u);
 			n += (u32)__popc(mf1);
 			if (phase == PH_WALK) {
+				const bool g0 = (k0 == 16u), g1 = (k1 == 16u);
 				const u32 mg0 = __ballot_sync(0xffffffffu, g0), mg1 = __ballot_sync(0xffffffffu, g1);
 				r = n + (u32)__popc(mg0 & lanemask_lt);
 				if (g0 && r < 32u) P_IDX[r] = (unsigned char)lane;
@@ -222,7 +220,8 @@
 			}
 		} else if (phase == PH_WALK) {
 			// ======== walk set-up (DDA slots) and voxel walk =====================================
-			u32 st = PS_EMPTY, vlo = vbase_lo, mat = 0, dcur = 1, sg = 7u, axis = 0;
+			u32 st = PS_EMPTY, vlo = vbase_lo, mat = 0, dcur = 1, sg = 7u;
+			i32 last_d = 0;
 			float tmx = XO_INF, tmy = XO_INF, tmz = XO_INF, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
 			float t_s = 0.0f, t_evt = 0.0f;
 			if (act) {
@@ -259,9 +258,11 @@
 					mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu; sg = (misc >> 18) & 7u;
 				}
 			}
-			const i32 stx = (sg & 1u) ? 2 : -2;
-			const i32 sty = ((sg & 2u) ? 2 : -2) << vox_bx;
-			const i32 stz = ((sg & 4u) ? 2 : -2) << vox_bxy;
+			// address increment per crossing on each axis (pinned in registers over the walk)
+			i32 stx = (sg & 1u) ? 2 : -2;
+			i32 sty = ((sg & 2u) ? 2 : -2) << vox_bx;
+			i32 stz = ((sg & 4u) ? 2 : -2) << vox_bxy;
+			asm volatile("" : "+r"(stx), "+r"(sty), "+r"(stz));
 			float step_k = sh_fast[mat].hot.step_k;
 			(void)step_k;
 			// Two crossings per trip; the lookup of the second one is issued before the first
@@ -280,7 +281,6 @@
 						if (py) tmy += tdy;
 						if (pz) tmz += tdz;
 						const i32 d_a = px ? stx : (py ? sty : stz);
-						const u32 ax_a = px ? 0u : (py ? 1u : 2u);
 						vlo += (u32)d_a;
 						const u32 cell_a = XO_VOXEL(vlo);
 						const u32 m_a = cell_a & 0xffu;
@@ -316,7 +316,7 @@
 							if (XO_IS_PLAIN_CHANGE(m_a)) {
 								XO_MATERIAL_CHANGE(m_a, tmin_a);
 							} else {
-								st = PS_BND; t_evt = tmin_a; axis = ax_a;
+								st = PS_BND; t_evt = tmin_a; last_d = d_a;
 							}
 						} else if (!ok_b) {
 							st = PS_SCAT;
@@ -331,7 +331,7 @@
 								if (XO_IS_PLAIN_CHANGE(m_b)) {
 									XO_MATERIAL_CHANGE(m_b, tmin_b);
 								} else {
-									st = PS_BND; t_evt = tmin_b; axis = qx ? 0u : (qy ? 1u : 2u);
+									st = PS_BND; t_evt = tmin_b; last_d = d_b;
 								}
 							}
 						}
@@ -342,6 +342,7 @@
 				if ((u32)__popc(__ballot_sync(0xffffffffu, st == PS_RUN)) < XO_POOL_THR_W) break;
 			}
 			if (act) {
+				const u32 axis = (last_d == stx) ? 0u : ((last_d == sty) ? 1u : 2u);
 				P_B[slot].w = (st == PS_BND) ? t_evt : t_s;
 				P_C[slot] = make_float4(tmx, tmy, tmz, __uint_as_float(vlo));
 				P_D[slot] = make_float4(tdx, tdy, tdz,
