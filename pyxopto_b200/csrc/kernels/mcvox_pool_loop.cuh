@@ -152,9 +152,9 @@
 						i32 ix = __float2int_rd((pos.x - cfg.top_left.x)*inv_sx);
 						i32 iy = __float2int_rd((pos.y - cfg.top_left.y)*inv_sy);
 						i32 iz = __float2int_rd((pos.z - cfg.top_left.z)*inv_sz);
-						ix = clipi(ix, 0, cfg.nx - 1);
-						iy = clipi(iy, 0, cfg.ny - 1);
-						iz = clipi(iz, 0, cfg.nz - 1);
+						ix = __vimin_s32_relu(ix, cfg.nx - 1);      // clip to [0, n - 1]: one VIMNMX.RELU
+						iy = __vimin_s32_relu(iy, cfg.ny - 1);
+						iz = __vimin_s32_relu(iz, cfg.nz - 1);
 						iterations += (u32)(abs(ix - ((i32)(idx0 & vox_mx) - 2)) +
 							abs(iy - ((i32)((idx0 >> vox_bx) & vox_my) - 2)) +
 							abs(iz - ((i32)(idx0 >> vox_bxy) - 2)));

@@ -377,6 +377,10 @@ class McBase(CuWorker):
             return int(min(max(self.refill_lanes, 1), 32))
         return int(getattr(self._source, 'cu_refill_lanes', self.default_refill_lanes))
 
+    def _loop_name(self) -> str:
+        """Which photon loop of the kernel header the launch ran (run_report['loop'])."""
+        return 'reference-structured' if self.deterministic else 'throughput'
+
     def _queue_bytes(self, block: int) -> int:
         """Shared memory of the throughput loops behind the window: per-warp launch
         queues (32 slots of 40 bytes)."""
@@ -649,7 +653,7 @@ class McBase(CuWorker):
             'launched_threads': nthreads, 'grid': grid, 'block': block,
             'shared_bytes': shared, 'private_bins': priv_len, 'lut_shared': lut_len,
             'chunk': chunk, 'refill': refill, 'fluence_window': [int(v) for v in window], 'items': nphotons, 'cache_hit': mod.cache_hit,
-            'kernel_attributes': kernel.attributes(),
+            'kernel_attributes': kernel.attributes(), 'loop': self._loop_name(),
         }
         if verbose:
             print('pyxopto_b200 run: build {:.3f} s, upload {:.3f} s, kernel {:.3f} ms, '

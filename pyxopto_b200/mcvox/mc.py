@@ -181,6 +181,12 @@ class Mc(McBase):
             return 0
         return int(self.pool_slots)
 
+    def _loop_name(self) -> str:
+        opts = self.resolved_options()
+        if self.deterministic or not self._vox_packed() or opts.get('MC_METHOD', 0) == 2:
+            return 'reference-structured'
+        return 'packet pool' if self._pool_slots(opts) else 'lane-resident rays'
+
     def _queue_bytes(self, block: int) -> int:
         slots = self._pool_slots()
         if slots:

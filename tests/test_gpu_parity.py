@@ -645,3 +645,56 @@ def test_large_fluence_results_own_their_pinned_grid():
     assert len(addrs) == 3 and addr_a in addrs          # the released buffer came back
     _, flu_e, _ = sim.run(2000, **kw)                   # pool exhausted: plain copy
     assert not any(np.shares_memory(flu_e.raw, f.raw) for f in (flu_b, flu_c, flu_d))
+
+
+@pytest.mark.parametrize('name', ['mcvox_gauss_fluence', 'mcvox_isopoint_fluencerate',
+                                  'mcvox_isovoxel_fluence', 'mcvox_ufiber_fluence',
+                                  'mcvox_gk2_line_total', 'mcvox_ubeam_radial'])
+def test_both_mcvox_throughput_loops_against_the_oracle(name):
+    """The packet-pool loop (mcvox_pool_loop.cuh, the default where it applies) and the
+    lane-resident loop (mcvox_dda_loop.cuh, ``pool_slots = 0``) are both pinned against the
+    oracle: totals within 4 sigma, every bin of the marginal fluence profiles and every
+    detector bin within 5 sigma; the two loops must also agree with each other."""
+    n = 300000
+    K = 0x7FFFFF
+    results = {}
+    for slots in (64, 0):
+        sim, geom, _ = build_sim(name)
+        sim.pool_slots = slots
+        sim.run(n, download=False)
+        assert sim.run_report['loop'] == ('packet pool' if slots else 'lane-resident rays')
+        results[slots] = sim.download_raw()[0]
+    desc = xo_oracle.describe(sim, geom)
+    ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
+                        math=xo_oracle.MATH_LIBM)['accu']
+
+    def check(a, b, scale, what, nsig):
+        a = a.astype(np.float64)/scale/n
+        b = b.astype(np.float64)/scale/n
+        sigma = np.sqrt(np.maximum(b, 1e-6)/n)*np.sqrt(2)
+        bad = np.abs(a - b) > nsig*sigma + 2e-5
+        assert not bad.any(), (what, np.flatnonzero(bad)[:5], a[bad][:5], b[bad][:5])
+
+    rate = bool(sim.resolved_options().get('MC_FLUENCE_MODE_RATE'))
+    for slots, other in ((64, ref), (0, ref), (64, results[0])):
+        accu = results[slots]
+        for det in sim.detectors or ():
+            for a in sim.cl_rw_accumulator_allocator.allocations(det):
+                sl = slice(a.offset, a.offset + a.size)
+                check(accu[sl].sum(keepdims=True), other[sl].sum(keepdims=True), K,
+                      (slots, type(det).__name__, 'total'), 4)
+                check(accu[sl], other[sl], K, (slots, type(det).__name__), 5)
+        flu = sim.fluence
+        if flu is None:
+            continue
+        for a in sim.cl_rw_accumulator_allocator.allocations(flu):
+            g = accu[a.offset:a.offset + a.size].reshape(a.shape)
+            c = other[a.offset:a.offset + a.size].reshape(a.shape)
+            k = float(flu.k)
+            if rate:
+                k *= 1.0/min(m.mua for m in sim.materials if m.mua > 0)
+            check(g.sum(keepdims=True).ravel(), c.sum(keepdims=True).ravel(), k,
+                  (slots, 'fluence total'), 4)
+            for axis in range(g.ndim):
+                rest = tuple(i for i in range(g.ndim) if i != axis)
+                check(g.sum(axis=rest), c.sum(axis=rest), k, (slots, 'fluence', axis), 5)

@@ -1,0 +1,62 @@
+"""Host-side decisions of the mcvox throughput path (no GPU): which photon loop a
+configuration compiles - the packet pool (mcvox_pool_loop.cuh), the lane-resident rays
+(mcvox_dda_loop.cuh) or the reference-structured loop - and the shared memory it asks for."""
+import numpy as np
+import pytest
+
+import benchcfg
+import cases
+from helpers import build_sim
+from pyxopto_b200.mcbase import mcoptions
+from pyxopto_b200.mcvox import mc as voxmc
+
+
+def _define(src: str, name: str) -> str:
+    for line in src.splitlines():
+        if line.startswith('#define {} '.format(name)):
+            return line.split()[2]
+    raise KeyError(name)
+
+
+def test_c3_compiles_the_packet_pool():
+    sim = benchcfg.c3_vox(voxmc, n=21)
+    sim._pack(1000)
+    assert sim._loop_name() == 'packet pool'
+    src = sim.kernel_source(block=1024)
+    assert _define(src, 'XO_VOX_POOL') == '64'
+    assert _define(src, 'XO_USE_RMAX') == '0'
+    # per warp: 64 slots of 17 words + 1 state byte, 32 bytes of gather indices
+    assert sim._queue_bytes(1024) == 32*(64*69 + 32) + 32
+    assert sim._queue_bytes(1024) + sim._shared_layout(sim._medium_bytes())[0] < 227*1024
+
+
+@pytest.mark.parametrize('change, loop', [
+    (lambda sim: setattr(sim, 'pool_slots', 0), 'lane-resident rays'),
+    (lambda sim: setattr(sim, 'rmax', 50e-6), 'lane-resident rays'),       # sphere inside the box
+    (lambda sim: sim._options.append(mcoptions.McMethod.mbl), 'reference-structured'),
+    (lambda sim: sim._options.append(mcoptions.McDeterministic.on), 'reference-structured'),
+    (lambda sim: sim._options.append(mcoptions.McMethod.ar), 'packet pool'),
+])
+def test_loop_selection(change, loop):
+    sim = benchcfg.c3_vox(voxmc, n=21)
+    change(sim)
+    sim._pack(1000)
+    assert sim._loop_name() == loop
+    src = sim.kernel_source(block=256)
+    assert (_define(src, 'XO_VOX_POOL') == '64') == (loop == 'packet pool')
+    if loop != 'packet pool':
+        assert sim._queue_bytes(256) == 40*256 + 16
+
+
+def test_a_trace_keeps_the_lane_resident_loop():
+    sim, geom, _ = build_sim('mcvox_line_mhg_trace')
+    sim._pack(600)
+    assert geom == 'mcvox' and sim._loop_name() == 'lane-resident rays'
+    assert _define(sim.kernel_source(block=64), 'XO_VOX_POOL') == '0'
+
+
+def test_pool_thresholds_reach_the_translation_unit():
+    sim = benchcfg.c3_vox(voxmc, n=21)
+    sim.pool_tuning = {'XO_POOL_THR_W': 10}
+    sim._pack(1000)
+    assert _define(sim.kernel_source(block=1024), 'XO_POOL_THR_W') == '10'
