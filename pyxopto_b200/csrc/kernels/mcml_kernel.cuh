@@ -96,11 +96,13 @@ __device__ __forceinline__ u32 ml_boundary(const MlLayer &cur, const MlLayer &nx
 	// surface layouts (mcml.template.c:100-126): may override n2 / cc at the
 	// point of incidence, or reflect the packet themselves
 	if (XoSurfTop::active && next_layer == 0) {
-		if (surface.top.handle(rng, pos, dir, weight, &n2, &cc) != SURF_CONTINUE)
-			return EV_REFLECTION;
+		const int r = surf_handle(surface.top, rng, pos, dir, weight, &n2, &cc, &cur - layer, num_layers, layer);
+		if (r == SURF_REFLECTED) return EV_REFLECTION;
+		if (r == SURF_REFRACTED) return EV_REFRACTION;
 	} else if (XoSurfBottom::active && next_layer == num_layers - 1) {
-		if (surface.bottom.handle(rng, pos, dir, weight, &n2, &cc) != SURF_CONTINUE)
-			return EV_REFLECTION;
+		const int r = surf_handle(surface.bottom, rng, pos, dir, weight, &n2, &cc, &cur - layer, num_layers, layer);
+		if (r == SURF_REFLECTED) return EV_REFLECTION;
+		if (r == SURF_REFRACTED) return EV_REFRACTION;
 	}
 	if (n1 == n2) { layer = next_layer; return EV_REFRACTION; }
 	dir.z = -dir.z;
@@ -534,18 +536,19 @@ McKernel(
 					// sample surface with a layout (mcml.template.c:100-126)
 					const float n_out = sh_layers[up ? 0 : (i32)num_layers - 1].n;
 					float n2 = n_out;
-					surf = up ? surface.top.handle(rng, pos, dir, weight, &n2, &cc)
-						: surface.bottom.handle(rng, pos, dir, weight, &n2, &cc);
+					surf = up ? surf_handle(surface.top, rng, pos, dir, weight, &n2, &cc, sh_layers, (i32)num_layers, layer)
+						: surf_handle(surface.bottom, rng, pos, dir, weight, &n2, &cc, sh_layers, (i32)num_layers, layer);
 					if (n2 != n_out) {
 						const float n1 = sh_layers[layer].n;
 						n12 = (n1 == n2) ? 1.0f : n1*FastMath::rcp_approx(n2);
 					}
 				}
-				if (surf != SURF_CONTINUE) through = false;
+				if (surf == SURF_REFLECTED) through = false;
+				else if (surf == SURF_REFRACTED) through = true;     // (a user-written layout moved the packet across)
 				else through = ml_boundary_fast(n12, cc, dir, rng);
 				flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 				if (through) {
-					layer += up ? -1 : 1;
+					if (surf != SURF_REFRACTED) layer += up ? -1 : 1;
 					if (layer <= 0) {
 						if (XoDetTop::active) detectors.top.deposit(acc, pos, dir, weight, opl);
 						done = true;

@@ -339,6 +339,7 @@ struct McSim {
 	McSimState state;
 	xo::Rng *rng;
 	const void *pf, *source, *det_top, *det_bottom, *det_specular, *layers, *fluence;
+	const void *surf_top, *surf_bottom;
 	mc_int_t num_layers;
 	const mc_fp_t *fp_lut_array;
 	mc_accu_t *accumulator_buffer;
@@ -385,6 +386,12 @@ struct McSim {
 #define mcsim_current_pf(psim) (static_cast<const McPf *>((psim)->pf))
 #define mcsim_current_layer_pf(psim) mcsim_current_pf(psim)
 #define mcsim_source(psim) (static_cast<const McSource *>((psim)->source))
+#define mcsim_top_surface_layout(psim) (static_cast<const McTopSurfaceLayout *>((psim)->surf_top))
+#define mcsim_bottom_surface_layout(psim) (static_cast<const McBottomSurfaceLayout *>((psim)->surf_bottom))
+// return values of mcsim_{top,bottom}_surface_layout_handler (mcml.template.h:262, 999-1001)
+#define MC_SURFACE_LAYOUT_CONTINUE (-1)
+#define MC_REFLECTED 1
+#define MC_REFRACTED 2
 #define mcsim_top_detector(psim) (static_cast<const McTopDetector *>((psim)->det_top))
 #define mcsim_bottom_detector(psim) (static_cast<const McBottomDetector *>((psim)->det_bottom))
 #define mcsim_specular_detector(psim) (static_cast<const McSpecularDetector *>((psim)->det_specular))

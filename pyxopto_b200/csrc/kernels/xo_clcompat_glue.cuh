@@ -13,6 +13,7 @@ __device__ __forceinline__ void clc_sim_init(McSim &sim, Rng *rng) {
 	sim.pf = nullptr; sim.source = nullptr;
 	sim.det_top = nullptr; sim.det_bottom = nullptr; sim.det_specular = nullptr;
 	sim.layers = nullptr; sim.num_layers = 0; sim.fluence = nullptr;
+	sim.surf_top = nullptr; sim.surf_bottom = nullptr;
 	sim.fp_lut_array = nullptr;
 	sim.accumulator_buffer = nullptr;
 	sim.state.position = P3{ 0.0f, 0.0f, 0.0f };
@@ -69,6 +70,31 @@ __device__ __forceinline__ void FluUser::deposit(const Accu &acc, const FluWindo
 	(void)mua;
 	mcsim_fluence_deposit_at(&sim, &pos_, w);
 #endif
+}
+#endif
+
+#define XO_CLC_SURFACE_BODY(slot, fn) \
+	McSim sim; \
+	clc_sim_init(sim, &rng); \
+	sim.slot = &s.l; \
+	sim.layers = layers; sim.num_layers = num_layers; \
+	sim.state.position = pos; sim.state.direction = dir; \
+	sim.state.weight = weight; sim.state.layer_index = layer; \
+	const int r_ = fn(&sim, n2, cc); \
+	if (r_ == MC_SURFACE_LAYOUT_CONTINUE) return SURF_CONTINUE; \
+	dir = sim.state.direction; weight = sim.state.weight; layer = sim.state.layer_index; \
+	return (r_ == MC_REFRACTED) ? SURF_REFRACTED : SURF_REFLECTED;
+
+#if XO_USER_SURF_TOP
+__device__ __forceinline__ int surf_handle(const SurfUserTop &s, Rng &rng, const P3 &pos, P3 &dir,
+		float &weight, float *n2, float *cc, const MlLayer *layers, i32 num_layers, i32 &layer) {
+	XO_CLC_SURFACE_BODY(surf_top, mcsim_top_surface_layout_handler)
+}
+#endif
+#if XO_USER_SURF_BOTTOM
+__device__ __forceinline__ int surf_handle(const SurfUserBottom &s, Rng &rng, const P3 &pos, P3 &dir,
+		float &weight, float *n2, float *cc, const MlLayer *layers, i32 num_layers, i32 &layer) {
+	XO_CLC_SURFACE_BODY(surf_bottom, mcsim_bottom_surface_layout_handler)
 }
 #endif
 

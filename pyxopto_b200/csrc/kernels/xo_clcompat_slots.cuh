@@ -30,6 +30,12 @@
 #ifndef XO_USER_FLUENCE
 #define XO_USER_FLUENCE 0
 #endif
+#ifndef XO_USER_SURF_TOP
+#define XO_USER_SURF_TOP 0
+#endif
+#ifndef XO_USER_SURF_BOTTOM
+#define XO_USER_SURF_BOTTOM 0
+#endif
 
 namespace xo {
 
@@ -103,6 +109,28 @@ struct DetUserSpecular {
 	static constexpr bool needs_opl = false;
 	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;
 };
+#endif
+
+// sample surface layouts (mcml): `inline int mcsim_<loc>_surface_layout_handler(McSim *,
+// mc_fp_t *n2, mc_fp_t *cc)` returning MC_SURFACE_LAYOUT_CONTINUE / MC_REFLECTED /
+// MC_REFRACTED (mcsurface/base.py:265-287, mcml.template.h:262-305); called through the
+// surf_handle overloads below instead of the `handle` of the hand-written layouts
+struct MlLayer;
+#if XO_USER_SURF_TOP
+struct SurfUserTop {
+	McTopSurfaceLayout l;
+	static constexpr bool active = true;
+};
+__device__ __forceinline__ int surf_handle(const SurfUserTop &s, Rng &rng, const P3 &pos, P3 &dir,
+	float &weight, float *n2, float *cc, const MlLayer *layers, i32 num_layers, i32 &layer);
+#endif
+#if XO_USER_SURF_BOTTOM
+struct SurfUserBottom {
+	McBottomSurfaceLayout l;
+	static constexpr bool active = true;
+};
+__device__ __forceinline__ int surf_handle(const SurfUserBottom &s, Rng &rng, const P3 &pos, P3 &dir,
+	float &weight, float *n2, float *cc, const MlLayer *layers, i32 num_layers, i32 &layer);
 #endif
 
 }  // namespace xo

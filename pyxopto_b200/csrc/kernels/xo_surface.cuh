@@ -9,12 +9,16 @@
 //     critical cosine cc of the medium behind the surface at the point of
 //     incidence (fibre core, cladding, cut-out), or
 //   * reflects the packet itself (direction, weight) and returns SURF_REFLECTED.
+// A user-written layout (OpenCL-C fragment, xo_clcompat_slots.cuh) may also move the packet
+// across the surface itself and return SURF_REFRACTED (it sets the layer index).
 #pragma once
 #include "xo_core.cuh"
 
 namespace xo {
 
-enum { SURF_CONTINUE = 0, SURF_REFLECTED = 1 };
+enum { SURF_CONTINUE = 0, SURF_REFLECTED = 1, SURF_REFRACTED = 2 };
+
+struct MlLayer;
 
 // absent layout: SurfaceLayoutDefault {int64 dummy} (mcsurface/base.py:124-152)
 struct SurfNone {
@@ -170,6 +174,16 @@ struct SurfFiberArray {
 		return SURF_CONTINUE;
 	}
 };
+
+// The kernels call a layout through this dispatcher: the hand-written layouts need the
+// packet only, the adapters of user-written fragments (non-template overloads in
+// xo_clcompat_slots.cuh) also hand the layer stack to the fragment's McSim facade.
+template <class S>
+__device__ __forceinline__ int surf_handle(const S &s, Rng &rng, const P3 &pos, P3 &dir,
+		float &weight, float *n2, float *cc, const MlLayer *layers, i32 num_layers, i32 &layer) {
+	(void)layers; (void)num_layers; (void)layer;
+	return s.handle(rng, pos, dir, weight, n2, cc);
+}
 
 template <class Top, class Bottom>
 struct SurfaceLayouts {             // mcsurface/base.py:258-263

@@ -287,6 +287,8 @@ class McBase(CuWorker):
         'XoDetBottom': ('xo::DetUserBottom', 'XO_USER_DET_BOTTOM'),
         'XoDetSpecular': ('xo::DetUserSpecular', 'XO_USER_DET_SPECULAR'),
         'XoFluence': ('xo::FluUser', 'XO_USER_FLUENCE'),
+        'XoSurfTop': ('xo::SurfUserTop', 'XO_USER_SURF_TOP'),
+        'XoSurfBottom': ('xo::SurfUserBottom', 'XO_USER_SURF_BOTTOM'),
     }
     user_plugin_slots = ('XoPf',)        # slots of this geometry that take fragments
     clcompat_geometry_header = None

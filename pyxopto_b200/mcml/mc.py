@@ -94,7 +94,7 @@ class Mc(McBase):
         return out
 
     user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular',
-                         'XoFluence')
+                         'XoFluence', 'XoSurfTop', 'XoSurfBottom')
     clcompat_geometry_header = 'xo_clcompat_mcml.cuh'
 
     def _plugin_objects(self):
@@ -103,7 +103,9 @@ class Mc(McBase):
                 'XoDetTop': dets.top if dets is not None else None,
                 'XoDetBottom': dets.bottom if dets is not None else None,
                 'XoDetSpecular': dets.specular if dets is not None else None,
-                'XoFluence': self._fluence}
+                'XoFluence': self._fluence,
+                'XoSurfTop': self._surface.top if self._surface is not None else None,
+                'XoSurfBottom': self._surface.bottom if self._surface is not None else None}
 
     def _surface_bindings(self):
         layouts = self._surface if self._surface is not None else mcsurface.SurfaceLayouts()

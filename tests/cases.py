@@ -549,6 +549,32 @@ def mcml_user_fluence(mc, **kw):
                  rnginit=616161, **kw), dict(rmax=20e-3)
 
 
+def mcml_user_surface_reflector(mc, **kw):
+    """A top surface layout written by a user (the arithmetic of LambertianReflector):
+    equals ``mcml_surface_lambert_top`` bit for bit."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    surf = mc.mcsurface.SurfaceLayouts(top=up.user_reflector(mc, 0.8, 0.0))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(),
+                                  bottom=mc.mcdetector.Radial(Axis(0, 5e-3, 50)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det, surface=surf,
+                 rnginit=13579, **kw), dict(rmax=20e-3)
+
+
+def mcml_user_surface_window(mc, **kw):
+    """A layout the reference does not ship, on both surfaces: anti-reflection window
+    (handler returns MC_REFRACTED), black ring (MC_REFLECTED with zero weight), glass
+    elsewhere (n2 / cc override, MC_SURFACE_LAYOUT_CONTINUE)."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    surf = mc.mcsurface.SurfaceLayouts(top=up.user_window(mc, 0.4e-3, 0.8e-3, 1.52),
+                                       bottom=up.user_window(mc, 1.0e-3, 1.5e-3, 1.45))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 4e-3, 80)),
+                                  bottom=mc.mcdetector.Radial(Axis(0, 4e-3, 80)))
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line(), det, surface=surf,
+                 rnginit=717171, **kw), dict(rmax=20e-3)
+
+
 MCML_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
 ALL_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
 GEOMETRY['mcml_user_plugins_native'] = 'mcml'
@@ -557,12 +583,15 @@ GOLDEN_RUN['mcml_user_plugins_native'] = (3000, 16)
 # executing the same fragments; there is no C restatement of user code, so the
 # oracle pins them through the equivalent built-in case (value) where one exists
 USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_user_cubic,
-              'mcml_user_fluence': mcml_user_fluence}
+              'mcml_user_fluence': mcml_user_fluence,
+              'mcml_user_surface_reflector': mcml_user_surface_reflector,
+              'mcml_user_surface_window': mcml_user_surface_window}
 USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None,
-                   'mcml_user_fluence': None}
+                   'mcml_user_fluence': None,
+                   'mcml_user_surface_reflector': 'mcml_surface_lambert_top',
+                   'mcml_user_surface_window': None}
 USER_GEOMETRY = {name: 'mcml' for name in USER_CASES}
-USER_RUN = {'mcml_user_plugins': (3000, 16), 'mcml_user_cubic': (3000, 16),
-            'mcml_user_fluence': (3000, 16)}
+USER_RUN = {name: (3000, 16) for name in USER_CASES}
 
 
 # ---------------------------------------------------------------------------

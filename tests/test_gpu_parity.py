@@ -466,14 +466,17 @@ def _raw_run(name, n, threads=256, block=64, deterministic=True):
     return sim, accu, sim.download_seeds()[:threads]
 
 
-def test_user_fragments_equal_builtins_bit_exact():
+@pytest.mark.parametrize('user, native', [('mcml_user_plugins', 'mcml_user_plugins_native'),
+                                          ('mcml_user_surface_reflector', 'mcml_surface_lambert_top')])
+def test_user_fragments_equal_builtins_bit_exact(user, native):
     """A user-written phase function, source and detector (tests/user_plugins.py)
-    that restate Hg / Line / Radial: deterministic mode must give the very
-    accumulators and MWC states of the built-in CUDA plugins (which the oracle
-    pins, test_deterministic_mode_bit_exact[mcml_user_plugins_native])."""
-    n = 4*run_size('mcml_user_plugins')[0]
-    sim_u, accu_u, x_u = _raw_run('mcml_user_plugins', n)
-    sim_n, accu_n, x_n = _raw_run('mcml_user_plugins_native', n)
+    that restate Hg / Line / Radial - and a user-written surface layout that restates
+    LambertianReflector: deterministic mode must give the very accumulators and MWC
+    states of the built-in CUDA plugins (which the oracle pins,
+    test_deterministic_mode_bit_exact[mcml_user_plugins_native / mcml_surface_lambert_top])."""
+    n = 4*run_size(user)[0]
+    sim_u, accu_u, x_u = _raw_run(user, n)
+    sim_n, accu_n, x_n = _raw_run(native, n)
     assert 'xo_clcompat.cuh' in sim_u._last_src and 'xo_clcompat' not in sim_n._last_src
     assert accu_u.sum() > 0
     assert np.array_equal(accu_u, accu_n)

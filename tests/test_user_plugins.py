@@ -21,8 +21,17 @@ def test_reference_runs_user_fragments_like_builtins():
     assert np.array_equal(gu['rng_x_after'], gn['rng_x_after'])
 
 
-def test_oracle_pins_user_fragments_through_equivalent_builtins():
-    name = 'mcml_user_plugins'
+def test_reference_runs_a_user_surface_layout_like_the_builtin():
+    """Golden vectors of the reference kernel: the user-written reflector == LambertianReflector."""
+    gu, gn = golden('mcml_user_surface_reflector'), golden('mcml_surface_lambert_top')
+    assert gu['accu'].sum() > 0
+    assert np.array_equal(gu['accu'], gn['accu'])
+    assert np.array_equal(gu['rng_x_after'], gn['rng_x_after'])
+    assert gu['packed_surface_layouts'].tobytes() == gn['packed_surface_layouts'].tobytes()
+
+
+@pytest.mark.parametrize('name', ['mcml_user_plugins', 'mcml_user_surface_reflector'])
+def test_oracle_pins_user_fragments_through_equivalent_builtins(name):
     eq = cases.USER_EQUIVALENT[name]
     sim, geom, _ = build_sim(eq)
     n, t = run_size(name)
@@ -40,7 +49,9 @@ def test_user_structs_pack_like_the_reference(name):
     sim._pack(run_size(name)[0])
     g = golden(name)
     mine = packed_bytes(sim)
-    for key in ('layers', 'source', 'detectors') + (('fluence',) if 'packed_fluence' in g.files else ()):
+    for key in ('layers', 'source', 'detectors') + \
+            (('fluence',) if 'packed_fluence' in g.files else ()) + \
+            (('surface_layouts',) if 'packed_surface_layouts' in g.files else ()):
         assert mine[key] == g['packed_' + key].tobytes(), key
 
 
@@ -58,6 +69,11 @@ def test_user_fragments_compile_for_sm100a(name, deterministic):
     if name == 'mcml_user_fluence':
         assert 'mcsim_fluence_deposit_at' in src and 'typedef xo::FluUser XoFluence;' in src
         assert 'typedef xo::PfHg XoPf;' in src
+        return
+    if name.startswith('mcml_user_surface'):
+        assert 'mcsim_top_surface_layout_handler' in src
+        assert 'typedef xo::SurfUserTop XoSurfTop;' in src and 'typedef xo::PfHg XoPf;' in src
+        assert ('typedef xo::SurfUserBottom XoSurfBottom;' in src) == (name.endswith('window'))
         return
     assert 'mcsim_pf_sample_angles' in src
     # built-in slots stay hand-written CUDA

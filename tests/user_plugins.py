@@ -369,3 +369,145 @@ inline void mcsim_fluence_deposit_at(
 
 def user_depth(mc, zaxis):
     return _user_depth_class(mc)(zaxis)
+
+
+# ---- sample surface layouts (mcml/mcsurface/base.py:265-287) --------------------------------
+@functools.lru_cache(maxsize=None)
+def _user_reflector_class(mc):
+    """Diffuse / specular reflector covering a whole sample surface (the arithmetic of
+    LambertianReflector), user-written."""
+    cltypes = _cltypes(mc)
+
+    class UserReflector(mc.mcsurface.SurfaceLayoutAny):
+        def cl_type(self, mc_):
+            T = mc_.types
+            class ClUserReflector(cltypes.Structure):
+                _fields_ = [('reflectance', T.mc_fp_t), ('specular', T.mc_fp_t)]
+            return ClUserReflector
+
+        def cl_declaration(self, mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES Mc{}SurfaceLayout{{ mc_fp_t reflectance; ' \
+                   'mc_fp_t specular; }};\n'.format(self.location.capitalize())
+
+        def cl_implementation(self, mc_):
+            loc = self.location
+            Loc = loc.capitalize()
+            return '''
+void dbg_print_{loc}_surface_layout(__mc_surface_mem const Mc{Loc}SurfaceLayout *layout){{
+	dbg_print("user-written reflector:");
+	dbg_print_float(INDENT "reflectance:", layout->reflectance);
+}};
+
+inline int mcsim_{loc}_surface_layout_handler(McSim *mcsim, mc_fp_t *n2, mc_fp_t *cc){{
+	__mc_surface_mem const struct Mc{Loc}SurfaceLayout *layout = mcsim_{loc}_surface_layout(mcsim);
+	mc_fp_t sin_fi, cos_fi, sin_theta, cos_theta;
+
+	if (mcsim_random(mcsim) > layout->specular){{
+		sin_theta = mc_sqrt(mcsim_random(mcsim));
+		cos_theta = mc_sqrt(FP_1 - sin_theta*sin_theta);
+		mc_sincos(mcsim_random(mcsim)*FP_2PI, &sin_fi, &cos_fi);
+		mcsim_set_direction_coordinates(mcsim, cos_fi*sin_theta, sin_fi*sin_theta,
+			mc_fsign(-mcsim_direction_z(mcsim))*cos_theta);
+	}} else {{
+		mcsim_reverse_direction_z(mcsim);
+	}};
+	mcsim_set_weight(mcsim, mcsim_weight(mcsim)*layout->reflectance);
+	return MC_REFLECTED;
+}};
+'''.format(loc=loc, Loc=Loc)
+
+        def __init__(self, reflectance, specular=0.0):
+            super().__init__()
+            self._reflectance, self._specular = float(reflectance), float(specular)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            target.reflectance = self._reflectance
+            target.specular = self._specular
+            return target
+
+        def todict(self):
+            return {'type': 'UserReflector', 'reflectance': self._reflectance,
+                    'specular': self._specular}
+
+    return UserReflector
+
+
+def user_reflector(mc, reflectance, specular=0.0):
+    return _user_reflector_class(mc)(reflectance, specular)
+
+
+@functools.lru_cache(maxsize=None)
+def _user_window_class(mc):
+    """A layout the reference does not ship: a disc of radius ``r`` around the z axis is an
+    ideally anti-reflection coated window (every packet passes, undeviated - the handler
+    moves the packet into the surrounding medium itself and returns MC_REFRACTED), a ring
+    up to ``r_black`` is a black absorber (the packet is reflected with zero weight), the rest
+    of the surface is a glass of refractive index ``n_glass`` (n2 / cc override, Fresnel by
+    the kernel)."""
+    cltypes = _cltypes(mc)
+
+    class UserWindow(mc.mcsurface.SurfaceLayoutAny):
+        def cl_type(self, mc_):
+            T = mc_.types
+            class ClUserWindow(cltypes.Structure):
+                _fields_ = [('r2_window', T.mc_fp_t), ('r2_black', T.mc_fp_t),
+                            ('n_glass', T.mc_fp_t)]
+            return ClUserWindow
+
+        def cl_declaration(self, mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES Mc{}SurfaceLayout{{ mc_fp_t r2_window; ' \
+                   'mc_fp_t r2_black; mc_fp_t n_glass; }};\n'.format(self.location.capitalize())
+
+        def cl_implementation(self, mc_):
+            loc = self.location
+            Loc = loc.capitalize()
+            outside = 'mcsim_top_layer_index(mcsim)' if loc == 'top' else \
+                'mcsim_bottom_layer_index(mcsim)'
+            return '''
+void dbg_print_{loc}_surface_layout(__mc_surface_mem const Mc{Loc}SurfaceLayout *layout){{
+	dbg_print("user-written window:");
+	dbg_print_float(INDENT "n_glass:", layout->n_glass);
+}};
+
+inline int mcsim_{loc}_surface_layout_handler(McSim *mcsim, mc_fp_t *n2, mc_fp_t *cc){{
+	__mc_surface_mem const struct Mc{Loc}SurfaceLayout *layout = mcsim_{loc}_surface_layout(mcsim);
+	mc_fp_t r2 = mcsim_position_r2(mcsim);
+
+	if (r2 <= layout->r2_window){{
+		mcsim_set_current_layer_index(mcsim, {outside});
+		return MC_REFRACTED;
+	}};
+	if (r2 <= layout->r2_black){{
+		mcsim_reverse_direction_z(mcsim);
+		mcsim_set_weight(mcsim, FP_0);
+		return MC_REFLECTED;
+	}};
+	*n2 = layout->n_glass;
+	*cc = cos_critical(mc_layer_n(mcsim_current_layer(mcsim)), layout->n_glass);
+	return MC_SURFACE_LAYOUT_CONTINUE;
+}};
+'''.format(loc=loc, Loc=Loc, outside=outside)
+
+        def __init__(self, r_window, r_black, n_glass):
+            super().__init__()
+            self._rw, self._rb, self._n = float(r_window), float(r_black), float(n_glass)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            target.r2_window = self._rw**2
+            target.r2_black = self._rb**2
+            target.n_glass = self._n
+            return target
+
+        def todict(self):
+            return {'type': 'UserWindow', 'r_window': self._rw, 'r_black': self._rb,
+                    'n_glass': self._n}
+
+    return UserWindow
+
+
+def user_window(mc, r_window, r_black, n_glass):
+    return _user_window_class(mc)(r_window, r_black, n_glass)
