@@ -915,7 +915,7 @@ class McBase(CuWorker):
             self._sv_resident = None
         return load
 
-    _SV_SRC = '#define XO_DETERMINISTIC {det}\n#include "xo_sv_kernel.cuh"\n'
+    _SV_SRC = '#define XO_DOUBLE {dbl}\n#define XO_DETERMINISTIC {det}\n#include "xo_sv_kernel.cuh"\n'
 
     def _pack_sampling_volume(self, trace, sv, nphotons: int):
         """Clears the allocators and packs the trace rows + the sampling volume
@@ -948,7 +948,8 @@ class McBase(CuWorker):
             trace = _ResidentRows(dev, self._trace)
         nphotons = int(trace.nphotons)
         deterministic = self.deterministic
-        src = self._SV_SRC.format(det=int(deterministic))
+        src = self._SV_SRC.format(det=int(deterministic), dbl=int(bool(
+            self.resolved_options().get('MC_USE_DOUBLE_PRECISION', False))))
         if exportsrc:
             with open(exportsrc, 'w') as f:
                 f.write(src)

@@ -496,6 +496,8 @@ def make_sv(mc, name):
 
 
 SV_CASES = ('mcml_lut_iso_radialpl_trace', 'mcvox_line_mhg_trace', 'mccyl_gk_ubeam_fiz_trace')
+# binary64: the reference's SamplingVolume kernel rendered in double precision (no C restatement)
+SV_DOUBLE_CASES = {'mcml_double_lut_iso_radialpl_trace': 'mcml_lut_iso_radialpl_trace'}
 
 
 # ---------------------------------------------------------------------------
@@ -1220,7 +1222,19 @@ def mccyl_double_hg_line_fiz(mc, **kw):
     return mccyl_hg_line_fiz(mc, types=_double(mc), **kw)
 
 
+def mcml_double_user_plugins(mc, **kw):
+    """User-written phase function, source and detector (OpenCL-C fragments) in binary64."""
+    return mcml_user_plugins(mc, types=_double(mc), **kw)
+
+
+def mcml_double_user_surface_window(mc, **kw):
+    """User-written surface layouts on both sample surfaces in binary64."""
+    return mcml_user_surface_window(mc, types=_double(mc), **kw)
+
+
 DOUBLE_CASES = {
+    'mcml_double_user_plugins': mcml_double_user_plugins,
+    'mcml_double_user_surface_window': mcml_double_user_surface_window,
     'mcml_double_mhg_gauss_cart_flurz': mcml_double_mhg_gauss_cart_flurz,
     'mcml_double_lut_iso_radialpl_trace': mcml_double_lut_iso_radialpl_trace,
     'mcvox_double_gauss_fluence': mcvox_double_gauss_fluence,

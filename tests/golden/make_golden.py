@@ -124,7 +124,7 @@ def main(argv):
                    rng_x_after=res['rng_x'][:t], lut=res['lut'],
                    num_kernels=res['num_kernels'], nphotons=n, nthreads=t,
                    rng_x0=sim.rng_seeds_x[:t], rng_a=sim.rng_seeds_a[:t])
-        if name in cases.SV_CASES:
+        if name in cases.SV_CASES or name in cases.SV_DOUBLE_CASES:
             # the reference's SamplingVolume kernel on the unfiltered trace rows
             tr = rk.packed_bytes()  # noqa: F841  (trace offsets read from the struct below)
             P = sim._packed['trace']
@@ -132,7 +132,8 @@ def main(argv):
             _, do, co, _ = np.frombuffer(bytes(memoryview(P).cast('B')), np.uint32)[:4].tolist()
             rows = res["floats"][do:do + n*ml*8].copy()
             cnt = res["ints"][co:co + n].copy()
-            svres = rk.sampling_volume(cases.make_sv(mc, name), cnt, rows)
+            svres = rk.sampling_volume(
+                cases.make_sv(mc, cases.SV_DOUBLE_CASES.get(name, name)), cnt, rows)
             out.update(sv_accu=svres['accu'], sv_total_weight=svres['total_weight'],
                        sv_packed=np.frombuffer(svres['packed_sv'], np.uint8),
                        sv_packed_trace=np.frombuffer(svres['packed_sv_trace'], np.uint8))

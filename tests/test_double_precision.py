@@ -93,3 +93,40 @@ def test_double_results_come_back_in_reference_units():
     assert abs(a - b) < 5*np.sqrt(2*b/20000)
     a, b = fluence.raw.sum()/20000, flu32.raw.sum()/20000
     assert abs(a - b) < 5*np.sqrt(2*b/20000)
+
+
+def test_sampling_volume_kernel_compiles_in_double():
+    from pyxopto_b200.mcbase.mcsim import compile_kernel
+    sim, _, _ = _sim('mcml_double_lut_iso_radialpl_trace')
+    src = sim._SV_SRC.format(det=1, dbl=1)
+    cubin, log, _ = compile_kernel(src, True, arch='sm_100a',
+                                   extra_options=sim._cl_build_options)
+    assert len(cubin) > 10000 and 'error' not in log.lower()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(cases.SV_DOUBLE_CASES))
+def test_double_sampling_volume_against_the_reference_kernel(name):
+    """``Mc.sampling_volume`` in binary64 against the reference's SamplingVolume kernel
+    rendered in double precision, fed with the same (reference-kernel) trace rows: the
+    64-bit voxel accumulators and the total weight must be equal."""
+    sim, geom, mc = _sim(name)
+    g = golden(name)
+    n, t = int(g['nphotons']), int(g['nthreads'])
+    trace, _, _ = sim.run(n, maxthreads=t, wgsize=t)
+    assert trace.nphotons == n and trace.data.dtype.itemsize % 8 == 0
+    # the rows of the reference kernel (ours agree to 1e-9, tested above)
+    P = sim._packed['trace']
+    do, co = int(P.data_buffer_offset), int(P.count_buffer_offset)
+    ml = int(sim.trace.maxlen)
+    assert np.array_equal(np.asarray(trace.n), g['ints'][co:co + n])
+    rows = g['floats'][do:do + n*ml*8]
+    trace.data.view(np.float64).reshape(-1)[:] = rows
+    trace._device_token = None      # (upload these rows instead of reading the resident ones)
+    sv = cases.make_sv(mc, cases.SV_DOUBLE_CASES[name])
+    sim.sampling_volume(trace, sv)
+    accu, _, _ = sim.download_raw()
+    assert g['sv_accu'].sum() > 0
+    assert np.array_equal(accu[:g['sv_accu'].size], g['sv_accu'])
+    assert sv.weight == int(g['sv_total_weight'])/sv.k
+    assert sv.data.shape == sv.shape

@@ -650,10 +650,12 @@ def test_large_fluence_results_own_their_pinned_grid():
     assert not any(np.shares_memory(flu_e.raw, f.raw) for f in (flu_b, flu_c, flu_d))
 
 
-@pytest.mark.parametrize('name', ['mcvox_gauss_fluence', 'mcvox_isopoint_fluencerate',
-                                  'mcvox_isovoxel_fluence', 'mcvox_ufiber_fluence',
-                                  'mcvox_gk2_line_total', 'mcvox_ubeam_radial'])
-def test_both_mcvox_throughput_loops_against_the_oracle(name):
+@pytest.mark.parametrize('name, method', [
+    ('mcvox_gauss_fluence', 'aw'), ('mcvox_isopoint_fluencerate', 'aw'),
+    ('mcvox_isovoxel_fluence', 'aw'), ('mcvox_ufiber_fluence', 'aw'),
+    ('mcvox_gk2_line_total', 'aw'), ('mcvox_ubeam_radial', 'aw'),
+    ('mcvox_gauss_fluence', 'ar'), ('mcvox_gk2_line_total', 'ar')])
+def test_both_mcvox_throughput_loops_against_the_oracle(name, method):
     """The packet-pool loop (mcvox_pool_loop.cuh, the default where it applies) and the
     lane-resident loop (mcvox_dda_loop.cuh, ``pool_slots = 0``) are both pinned against the
     oracle: totals within 4 sigma, every bin of the marginal fluence profiles and every
@@ -661,15 +663,16 @@ def test_both_mcvox_throughput_loops_against_the_oracle(name):
     n = 300000
     K = 0x7FFFFF
     results = {}
+    from pyxopto_b200.mcbase import mcoptions
     for slots in (64, 0):
-        sim, geom, _ = build_sim(name)
+        sim, geom, _ = build_sim(name, options=[getattr(mcoptions.McMethod, method)])
         sim.pool_slots = slots
         sim.run(n, download=False)
         assert sim.run_report['loop'] == ('packet pool' if slots else 'lane-resident rays')
         results[slots] = sim.download_raw()[0]
     desc = xo_oracle.describe(sim, geom)
     ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
-                        math=xo_oracle.MATH_LIBM)['accu']
+                        math=xo_oracle.MATH_LIBM, method=method)['accu']
 
     def check(a, b, scale, what, nsig):
         a = a.astype(np.float64)/scale/n
