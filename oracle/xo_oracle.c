@@ -83,6 +83,7 @@ typedef struct { float g1, g2, b; } pf_hg2;                  /* mcpf/hg2.py:58 *
 typedef struct { pf_gk gk_1, gk_2; float b; } pf_gk2;        /* mcpf/gk2.py:61 */
 typedef struct { float g, a, beta, inv_a, a1, a2; } pf_mgk;  /* mcpf/mgk.py:64 */
 typedef struct { float n; } pf_pc;                           /* mcpf/pc.py:50 */
+typedef struct { float gamma, a, b; } pf_rayleigh;           /* mcpf/rayleigh.py:54 */
 typedef struct { float n, beta; } pf_mpc;
 typedef struct { p3f direction; float g, p; } pf_hgdir;      /* mcpf/hgdir.py:62-66 */                    /* mcpf/mpc.py:54 */
 
@@ -489,6 +490,21 @@ static float pf_sample_angles(sim_t *s, float *azimuth) {
 			tmp = a1*sim_random(s) + a2;
 			tmp = FP_1 + g*g - m_pow(s, tmp, -inv_a);
 			cos_theta = m_div(tmp, FP_2*g);
+		}
+		return fclip(cos_theta, -FP_1, FP_1);
+	}
+	case XO_PF_RAYLEIGH: {
+		/* mcpf/rayleigh.py:86-104 with its two syntax slips (:96 missing ';', :99 ');')
+		   repaired - the text does not compile as shipped */
+		const pf_rayleigh *p = (const pf_rayleigh *)pf;
+		float b = p->b, a = p->a, tmp;
+		*azimuth = FP_2PI*sim_random(s);
+		if (p->gamma == FP_1) {
+			cos_theta = FP_2*sim_random(s) - FP_1;
+		} else {
+			b = b*(FP_1 - FP_2*sim_random(s));
+			tmp = m_sqrt(b*b*0.25f + a*a*a*0.037037037037037035f);
+			cos_theta = m_cbrt(s, -0.5f*b + tmp) + m_cbrt(s, -0.5f*b - tmp);
 		}
 		return fclip(cos_theta, -FP_1, FP_1);
 	}

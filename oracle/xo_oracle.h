@@ -17,7 +17,8 @@ enum { XO_GEOM_MCML = 0, XO_GEOM_MCVOX = 1, XO_GEOM_MCCYL = 2 };
 enum { XO_METHOD_AW = 0, XO_METHOD_AR = 1, XO_METHOD_MBL = 2 };
 enum { XO_MATH_LIBM = 0, XO_MATH_PORTABLE = 1 };
 enum { XO_PF_HG = 1, XO_PF_MHG = 2, XO_PF_GK = 3, XO_PF_LUT = 4, XO_PF_HG2 = 5,
-	XO_PF_GK2 = 6, XO_PF_MGK = 7, XO_PF_PC = 8, XO_PF_MPC = 9, XO_PF_HGDIR = 10 };
+	XO_PF_GK2 = 6, XO_PF_MGK = 7, XO_PF_PC = 8, XO_PF_MPC = 9, XO_PF_HGDIR = 10,
+	XO_PF_RAYLEIGH = 11 };
 enum {
 	XO_SRC_LINE = 1, XO_SRC_GAUSSIANBEAM = 2, XO_SRC_UNIFORMFIBER = 3,
 	XO_SRC_ISOTROPICPOINT = 4, XO_SRC_UNIFORMBEAM = 5, XO_SRC_LAMBERTIANFIBER = 6,

@@ -25,7 +25,7 @@ METHOD = {'aw': 0, 'albedo_weight': 0, 'ar': 1, 'albedo_rejection': 1,
           'mbl': 2, 'microscopic_beer_lambert': 2}
 MATH_LIBM, MATH_PORTABLE = 0, 1
 PF_KIND = {'Hg': 1, 'MHg': 2, 'Gk': 3, 'Lut': 4, 'LutEx': 4, 'Hg2': 5, 'Gk2': 6,
-           'MGk': 7, 'Pc': 8, 'MPc': 9, 'HgDir': 10}
+           'MGk': 7, 'Pc': 8, 'MPc': 9, 'HgDir': 10, 'Rayleigh': 11}
 SRC_KIND = {'Line': 1, 'GaussianBeam': 2, 'UniformFiber': 3,
             'IsotropicPoint': 4, 'UniformBeam': 5, 'LambertianFiber': 6,
             'IsotropicVoxel': 7, 'UniformFiberLut': 8,

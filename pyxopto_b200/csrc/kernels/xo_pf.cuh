@@ -231,6 +231,29 @@ struct PfPc {                       // mcpf/pc.py:50-52
 	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
 };
 
+// Rayleigh (mcpf/rayleigh.py:54-58 packed struct; Frisvad's importance sampling by Cardano's
+// formula).  The sampling text of the reference does not compile (rayleigh.py:96-100: a
+// missing `;` and a stray `);`): restated here with its evident meaning.
+struct PfRayleigh {
+	float gamma, a, b;
+	static constexpr bool uses_lut = false;
+	__device__ __forceinline__ float sample(Rng &rng, const float *lut, float *azimuth) const {
+		(void)lut;
+		float ct;
+		*azimuth = XO_FP_2PI*rng.next();
+		if (gamma == 1.0f) {
+			ct = 2.0f*rng.next() - 1.0f;                // isotropic
+		} else {
+			const float bb = b*(1.0f - 2.0f*rng.next());
+			const float tmp = M::sqrt(bb*bb*0.25f + a*a*a*0.037037037037037035f);
+			ct = M::cbrt(-0.5f*bb + tmp) + M::cbrt(-0.5f*bb - tmp);
+		}
+		return clipf(ct, -1.0f, 1.0f);
+	}
+	typedef PfPlainFast<PfRayleigh> Fast;
+	__device__ __forceinline__ void prepare(Fast &f) const { f.pf = *this; }
+};
+
 struct PfMPc {                      // mcpf/mpc.py:54-58
 	float n, beta;
 	static constexpr bool uses_lut = false;

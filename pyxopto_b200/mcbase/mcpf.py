@@ -368,6 +368,48 @@ class Pc(PfBase):
         return 'Pc(n={})'.format(self._n)
 
 
+class Rayleigh(PfBase):
+    """Rayleigh scattering (mcpf/rayleigh.py): p ~ (1 + 3 gamma) + (1 - gamma) cos^2.  The
+    reference packs it (rayleigh.py:54-58, 166-176) but its sampling text does not compile
+    (rayleigh.py:96-100); the kernel here samples it with the evident meaning of that text."""
+    cu_type = 'xo::PfRayleigh'
+
+    @staticmethod
+    def cl_type(mc):
+        T = mc.types
+        class ClRayleigh(cltypes.Structure):
+            _fields_ = [('gamma', T.mc_fp_t), ('a', T.mc_fp_t), ('b', T.mc_fp_t)]
+        return ClRayleigh
+
+    def __init__(self, gamma: float):
+        super().__init__()
+        self.gamma = gamma
+
+    def _set_gamma(self, gamma):
+        self._gamma = min(max(float(gamma), 0.0), 1.0)
+
+    gamma = property(lambda self: self._gamma, _set_gamma, None, 'Molecular anisotropy factor.')
+
+    def _precalculated(self):
+        gamma = self._gamma
+        if gamma == 1.0:
+            return 0.0, 0.0
+        return 3.0*(1.0 + 3.0*gamma)/(1.0 - gamma), 4.0*(1.0 + 2.0*gamma)/(1.0 - gamma)
+
+    def cl_pack(self, mc, target=None):
+        if target is None:
+            target = self.fetch_cl_type(mc)()
+        target.gamma = self._gamma
+        target.a, target.b = self._precalculated()
+        return target
+
+    def todict(self):
+        return {'gamma': self._gamma, 'type': type(self).__name__}
+
+    def __repr__(self):
+        return 'Rayleigh(gamma={})'.format(self._gamma)
+
+
 class MPc(Pc):
     """Modified power of cosines (mcpf/mpc.py): b Pc(n) + (1 - b) 3/2 cos^2."""
     cu_type = 'xo::PfMPc'

@@ -551,6 +551,17 @@ def mcml_user_fluence(mc, **kw):
                  rnginit=616161, **kw), dict(rmax=20e-3)
 
 
+def mcml_rayleigh_line_radial(mc, **kw):
+    """Rayleigh phase function (molecular anisotropy 0.3) in a 2-layer stack; the
+    reference's class with its (non-compiling) fragment repaired, tests/user_plugins.py."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Radial(Axis(0, 10e-3, 100)),
+                                  bottom=mc.mcdetector.Total())
+    return mc.Mc(_layers(mc, up.rayleigh(mc, 0.3)), mc.mcsource.Line(), det,
+                 rnginit=271828, **kw), dict(rmax=20e-3)
+
+
 def mcml_user_surface_reflector(mc, **kw):
     """A top surface layout written by a user (the arithmetic of LambertianReflector):
     equals ``mcml_surface_lambert_top`` bit for bit."""
@@ -577,6 +588,10 @@ def mcml_user_surface_window(mc, **kw):
                  rnginit=717171, **kw), dict(rmax=20e-3)
 
 
+for _name, _make in (('mcml_rayleigh_line_radial', mcml_rayleigh_line_radial),):
+    MCML_CASES[_name] = ALL_CASES[_name] = _make
+    GEOMETRY[_name] = 'mcml'
+    GOLDEN_RUN[_name] = (3000, 16)
 MCML_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
 ALL_CASES['mcml_user_plugins_native'] = mcml_user_plugins_native
 GEOMETRY['mcml_user_plugins_native'] = 'mcml'

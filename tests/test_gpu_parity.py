@@ -101,7 +101,7 @@ def test_deterministic_mode_bit_exact(name):
                                   'mcml_hg_ufiberni_radial', 'mcml_mhg_lfiberni_cart',
                                   'mcml_hg_ufiberlutni_total', 'mcml_hg_rectlut_inside',
                                   'mcvox_lfiber_radial', 'mcvox_ufiberlut_fluence',
-                                  'mcml_aniso_line_cart_flu'])
+                                  'mcml_aniso_line_cart_flu', 'mcml_rayleigh_line_radial'])
 def test_throughput_mode_statistics(name):
     """Fast mode vs oracle (libm, different schedule): totals within 4 sigma."""
     sim, geom, _ = build_sim(name)

@@ -511,3 +511,52 @@ inline int mcsim_{loc}_surface_layout_handler(McSim *mcsim, mc_fp_t *n2, mc_fp_t
 
 def user_window(mc, r_window, r_black, n_glass):
     return _user_window_class(mc)(r_window, r_black, n_glass)
+
+
+# ---- Rayleigh: the reference's own class with its fragment repaired ----------------------------
+@functools.lru_cache(maxsize=None)
+def _fixed_rayleigh_class(mc):
+    """``xopto.mcbase.mcpf.Rayleigh`` packs correctly, but its OpenCL-C text does not compile
+    (rayleigh.py:96 lacks a ``;``, :99 closes a block with ``);``, and the constant FP_1d27 it
+    uses expands to a literal with an ``ff`` suffix, mcbase.template.h:484).  This subclass -
+    used only to produce golden vectors with the reference's kernel - carries the same text
+    with those slips repaired."""
+    class FixedRayleigh(mc.mcpf.Rayleigh):
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_pf(const McPf *pf) {
+	dbg_print("Rayleigh scattering phase function:");
+	dbg_print_float(INDENT "gamma:", pf->gamma);
+};
+
+inline mc_fp_t mcsim_pf_sample_angles(McSim *mcsim, mc_fp_t *azimuth){
+	mc_fp_t tmp, cos_theta;
+	mc_fp_t gamma = mcsim_current_pf(mcsim)->gamma;
+	mc_fp_t a = mcsim_current_pf(mcsim)->a;
+	mc_fp_t b = mcsim_current_pf(mcsim)->b;
+
+	*azimuth = FP_2PI*mcsim_random(mcsim);
+
+	if (gamma == FP_1) {
+		cos_theta = FP_2*mcsim_random(mcsim) - FP_1;
+	} else {
+		b = b*(FP_1 - FP_2*mcsim_random(mcsim));
+		tmp = mc_sqrt(b*b*FP_0p25 + a*a*a*FP_LITERAL(0.037037037037037035));
+		cos_theta = mc_cbrt(-FP_0p5*b + tmp) + mc_cbrt(-FP_0p5*b - tmp);
+	};
+
+	return mc_fclip(cos_theta, -FP_1, FP_1);
+};
+'''
+    # (exported under the reference's name: to_dict() / adoption see a `Rayleigh`)
+    FixedRayleigh.__name__ = FixedRayleigh.__qualname__ = 'Rayleigh'
+    return FixedRayleigh
+
+
+def rayleigh(mc, gamma):
+    """Rayleigh phase function: the engine's class, or - for the reference package - the
+    reference's class with its fragment repaired."""
+    if mc.__name__.startswith('xopto'):
+        return _fixed_rayleigh_class(mc)(gamma)
+    return mc.mcpf.Rayleigh(gamma)
