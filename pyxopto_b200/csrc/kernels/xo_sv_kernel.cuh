@@ -68,7 +68,9 @@ SamplingVolume(
 	xo::u64 *accu_buffer)
 {
 	using namespace xo;
-	const bool aligned = (trace.data_off & 3u) == 0u &&
+	// (128-bit loads of an event: single precision only - in binary64 `float` is double
+	// and an event is 64 bytes)
+	const bool aligned = !XO_DOUBLE && (trace.data_off & 3u) == 0u &&
 		(reinterpret_cast<unsigned long long>(fp_buffer) & 15ull) == 0ull;
 	u64 weight_sum = 0;
 	u32 steps = 0;

@@ -670,7 +670,9 @@ class McBase(CuWorker):
         trace_res = fluence_res = detectors_res = None
         if self._trace is not None:
             trace_res = out_trace if out_trace is not None else type(self._trace)(self._trace)
-            if self._trace.filter is not None and self.device_trace_filter:
+            if self._trace.filter is not None and self.device_trace_filter and \
+                    np.dtype(self._types.np_float).itemsize == 4:
+                # (binary64 rows go through the host filter, like the reference's)
                 lazy = out_trace is None and self.lazy_trace_rows
                 n_sel, rows, n_dropped = self.filter_trace_on_device(
                     nphotons, download=not lazy)

@@ -24,8 +24,17 @@ def _has_gpu() -> bool:
 HAS_GPU = _has_gpu()
 
 
+GPU_TEST_TIMEOUT_S = 300     # a kernel that never ends must not hold the GPU box
+
+
 def pytest_collection_modifyitems(config, items):
     if HAS_GPU:
+        # (pytest-timeout, where installed: the watchdog thread ends the process, the
+        # driver tears the context - and the runaway kernel - down)
+        if config.pluginmanager.hasplugin('timeout'):
+            for item in items:
+                if 'gpu' in item.keywords and item.get_closest_marker('timeout') is None:
+                    item.add_marker(pytest.mark.timeout(GPU_TEST_TIMEOUT_S, method='thread'))
         return
     skip = pytest.mark.skip(reason='no CUDA device in this container')
     for item in items:

@@ -124,7 +124,9 @@ def test_double_sampling_volume_against_the_reference_kernel(name):
     trace.data.view(np.float64).reshape(-1)[:] = rows
     trace._device_token = None      # (upload these rows instead of reading the resident ones)
     sv = cases.make_sv(mc, cases.SV_DOUBLE_CASES[name])
-    sim.sampling_volume(trace, sv)
+    sim.sampling_volume(trace, sv, maxthreads=256)
+    assert bytes(memoryview(sim._packed['sv']).cast('B')) == g['sv_packed'].tobytes()
+    assert bytes(memoryview(sim._packed['sv_trace']).cast('B')) == g['sv_packed_trace'].tobytes()
     accu, _, _ = sim.download_raw()
     assert g['sv_accu'].sum() > 0
     assert np.array_equal(accu[:g['sv_accu'].size], g['sv_accu'])
