@@ -930,6 +930,8 @@ class McBase(CuWorker):
         self._packed['sv'] = sv.cl_pack(self, self._packed.get('sv'))
         return self._packed['sv_trace'], self._packed['sv']
 
+    sv_warp_per_packet = True        # throughput-mode SamplingVolume kernel (developer knob)
+
     def sampling_volume(self, trace, sv, wgsize: int = None, maxthreads: int = None,
                         exportsrc: str = None, verbose: bool = False,
                         download: bool = True):
@@ -955,7 +957,12 @@ class McBase(CuWorker):
         if exportsrc:
             with open(exportsrc, 'w') as f:
                 f.write(src)
-        kernel = self._module(src, deterministic).kernel('SamplingVolume')
+        # throughput mode, single precision: one warp per packet, one lane per segment
+        # (xo_sv_kernel.cuh); the reference-structured kernel otherwise
+        warp_kernel = bool(self.sv_warp_per_packet and not deterministic and
+                           np.dtype(self._types.np_float).itemsize == 4)
+        kernel = self._module(src, deterministic).kernel(
+            'SamplingVolumeWarp' if warp_kernel else 'SamplingVolume')
         tp, sp = self._pack_sampling_volume(trace, sv, nphotons)
         counters = np.zeros(4, dtype=np.uint32)   # processed, kernels, steps (u64)
         cbuf = self.cl_r_buffer('counters', counters)
@@ -1002,7 +1009,8 @@ class McBase(CuWorker):
         block = int(wgsize) if wgsize else 256
         grid, block = self.launch_geometry(kernel, block, 0, maxthreads)
         if nphotons:
-            grid = max(1, min(grid, (nphotons + block - 1)//block))
+            per_cta = block//32 if warp_kernel else block
+            grid = max(1, min(grid, (nphotons + per_cta - 1)//per_cta))
         t1 = time.perf_counter()
         ev0, ev1 = self._events
         ev0.record(self._stream)

@@ -375,6 +375,16 @@ def test_sampling_volume_bit_exact_and_fast(name):
     fast.sampling_volume(trace, sv2)
     assert abs(sv2.data.sum() - sv.data.sum()) <= 1e-4*sv.data.sum()
     assert sv2.weight == pytest.approx(sv.weight, rel=1e-6)
+    # the throughput kernel walks the segments of a packet side by side (one warp per
+    # packet): voxel by voxel it differs from the reference-structured kernel by the
+    # rounding of the individual deposits only
+    assert np.allclose(sv2.data, sv.data, rtol=2e-3, atol=2e-5*sv.data.max())
+    # ... and the reference-structured kernel in throughput math stays available
+    fast.sv_warp_per_packet = False
+    sv3 = cases.make_sv(mc2, name)
+    fast.sampling_volume(trace, sv3)
+    assert abs(sv3.data.sum() - sv.data.sum()) <= 1e-4*sv.data.sum()
+    assert np.allclose(sv3.data, sv.data, rtol=2e-3, atol=2e-5*sv.data.max())
 
 
 def _filters(mc):
