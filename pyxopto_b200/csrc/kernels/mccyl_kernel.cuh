@@ -83,11 +83,6 @@ struct __align__(16) CylPfFast { XoPf::Fast v; };
 struct CylFastLayer { CylHot hot; CylAbs abs; CylGeo geo; CylPfFast pf; };
 
 typedef CylDetectors<XoDetOuter, XoDetSpecular> XoDetectors;
-#if XO_TRACE
-typedef TraceCfg XoTrace;
-#else
-typedef TraceNone XoTrace;
-#endif
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetOuter::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
@@ -223,7 +218,7 @@ McKernel(
 	CylCtx ctx; ctx.layers = sh_layers; ctx.num_layers = (i32)num_layers;
 	const P3 src_pos = source.origin();
 	const float rmax2 = rmax*rmax;
-	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
+	const XoTraceCfg &tcfg = *reinterpret_cast<const XoTraceCfg *>(&trace);
 	(void)tcfg;
 
 #if !XO_DETERMINISTIC
@@ -282,7 +277,7 @@ McKernel(
 				if (trace_event(tcfg, float_buffer, packet, trace_count, flags, \
 						pos, dir, weight, opl)) ++trace_count; \
 			} \
-			if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
+			if (done) trace_complete(tcfg, int_buffer, packet, trace_count); \
 		} \
 		flags = 0; \
 		state = done ? ST_DEAD : ST_RUN; \
@@ -575,7 +570,7 @@ McKernel(
 
 			if (done) {
 #if XO_TRACE
-				int_buffer[tcfg.count_off + packet] = (i32)trace_count;
+				trace_complete(tcfg, int_buffer, packet, trace_count);
 #endif
 #if !XO_DETERMINISTIC
 				if (pk_next >= pk_end) {

@@ -75,11 +75,6 @@ struct MlFastLayer { MlHot hot; MlAbs abs; MlPfFast pf; MlAux aux; MlIface iface
 
 typedef Detectors<XoDetTop, XoDetBottom, XoDetSpecular> XoDetectors;
 typedef SurfaceLayouts<XoSurfTop, XoSurfBottom> XoSurface;
-#if XO_TRACE
-typedef TraceCfg XoTrace;
-#else
-typedef TraceNone XoTrace;
-#endif
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetTop::needs_opl || XoDetBottom::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
@@ -276,7 +271,7 @@ McKernel(
 #else
 	(void)rmax;
 #endif
-	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
+	const XoTraceCfg &tcfg = *reinterpret_cast<const XoTraceCfg *>(&trace);
 	(void)tcfg;
 
 	bool started = false;
@@ -304,7 +299,7 @@ McKernel(
 			if (trace_event(tcfg, float_buffer, packet, trace_count, flags, \
 					pos, dir, weight, opl)) ++trace_count; \
 		} \
-		if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
+		if (done) trace_complete(tcfg, int_buffer, packet, trace_count); \
 	} while (0)
 #else
 #define XO_TRACE_TRIP() do { } while (0)

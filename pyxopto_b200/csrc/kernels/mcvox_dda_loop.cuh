@@ -51,7 +51,7 @@
 	const u32 lanemask_lt = (1u << lane) - 1u;
 	const u32 vox_bxy = vox_bx + vox_by;
 	const u32 vox_mx = (1u << vox_bx) - 1u, vox_my = (1u << vox_by) - 1u;
-	const TraceCfg &tcfg = *reinterpret_cast<const TraceCfg *>(&trace);
+	const XoTraceCfg &tcfg = *reinterpret_cast<const XoTraceCfg *>(&trace);
 	(void)tcfg; (void)chunk; (void)nthreads;
 
 	u32 state = ST_DEAD;
@@ -119,7 +119,7 @@
 			if (trace_event(tcfg, float_buffer, packet, trace_count, flags, \
 					pos, dir, weight, opl)) ++trace_count; \
 		} \
-		if (done) int_buffer[tcfg.count_off + packet] = (i32)trace_count; \
+		if (done) trace_complete(tcfg, int_buffer, packet, trace_count); \
 	} while (0)
 #else
 #define XO_TRACE_TRIP() do { } while (0)

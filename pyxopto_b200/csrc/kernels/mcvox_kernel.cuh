@@ -55,11 +55,6 @@ struct VoxCfg {                     // mcvox/mcgeometry/voxel.py:96-121
 };
 
 typedef Detectors<XoDetTop, XoDetBottom, XoDetSpecular> XoDetectors;
-#if XO_TRACE
-typedef TraceCfg XoTrace;
-#else
-typedef TraceNone XoTrace;
-#endif
 
 #define XO_NEEDS_OPL (XO_TRACK_OPL || XoDetTop::needs_opl || XoDetBottom::needs_opl || \
 	XoDetSpecular::needs_opl || XoFluence::needs_opl)
@@ -290,7 +285,7 @@ McKernel(
 		mat = ctx.voxel_material(vx, vy, vz); \
 		flags |= EV_LAUNCH; \
 		if (XO_TRACE & XO_TRACE_START) { \
-			if (trace_event(*reinterpret_cast<const TraceCfg *>(&trace), float_buffer, packet, \
+			if (trace_event(*reinterpret_cast<const XoTraceCfg *>(&trace), float_buffer, packet, \
 					trace_count, flags, pos, dir, weight, opl)) ++trace_count; \
 		} \
 	} while (0)
@@ -425,7 +420,7 @@ McKernel(
 #if XO_TRACE
 			flags |= done ? EV_TERMINATED : 0u;
 			if (XO_TRACE == XO_TRACE_ALL || ((XO_TRACE & XO_TRACE_END) && done)) {
-				if (trace_event(*reinterpret_cast<const TraceCfg *>(&trace), float_buffer, packet,
+				if (trace_event(*reinterpret_cast<const XoTraceCfg *>(&trace), float_buffer, packet,
 						trace_count, flags, pos, dir, weight, opl)) ++trace_count;
 			}
 #endif
@@ -433,7 +428,7 @@ McKernel(
 
 			if (done) {
 #if XO_TRACE
-				int_buffer[reinterpret_cast<const TraceCfg *>(&trace)->count_off + packet] = (i32)trace_count;
+				trace_complete(*reinterpret_cast<const XoTraceCfg *>(&trace), int_buffer, packet, trace_count);
 #endif
 #if !XO_DETERMINISTIC
 				if (pk_next >= pk_end) {

@@ -340,6 +340,10 @@ struct McSim {
 	xo::Rng *rng;
 	const void *pf, *source, *det_top, *det_bottom, *det_specular, *layers, *fluence;
 	const void *surf_top, *surf_bottom;
+	const void *trace;
+	mc_fp_t *float_buffer;
+	mc_int_t *integer_buffer;
+	mc_uint_t event_flags;
 	mc_int_t num_layers;
 	const mc_fp_t *fp_lut_array;
 	mc_accu_t *accumulator_buffer;
@@ -386,6 +390,11 @@ struct McSim {
 #define mcsim_current_pf(psim) (static_cast<const McPf *>((psim)->pf))
 #define mcsim_current_layer_pf(psim) mcsim_current_pf(psim)
 #define mcsim_source(psim) (static_cast<const McSource *>((psim)->source))
+#define mcsim_trace(psim) (static_cast<const McTrace *>((psim)->trace))
+#define mcsim_float_buffer(psim) ((psim)->float_buffer)
+#define mcsim_integer_buffer(psim) ((psim)->integer_buffer)
+#define mcsim_event_flags(psim) ((psim)->event_flags)
+#define __mc_trace_mem
 #define mcsim_top_surface_layout(psim) (static_cast<const McTopSurfaceLayout *>((psim)->surf_top))
 #define mcsim_bottom_surface_layout(psim) (static_cast<const McBottomSurfaceLayout *>((psim)->surf_bottom))
 // return values of mcsim_{top,bottom}_surface_layout_handler (mcml.template.h:262, 999-1001)

@@ -14,6 +14,8 @@ __device__ __forceinline__ void clc_sim_init(McSim &sim, Rng *rng) {
 	sim.det_top = nullptr; sim.det_bottom = nullptr; sim.det_specular = nullptr;
 	sim.layers = nullptr; sim.num_layers = 0; sim.fluence = nullptr;
 	sim.surf_top = nullptr; sim.surf_bottom = nullptr;
+	sim.trace = nullptr; sim.float_buffer = nullptr; sim.integer_buffer = nullptr;
+	sim.event_flags = 0u;
 	sim.fp_lut_array = nullptr;
 	sim.accumulator_buffer = nullptr;
 	sim.state.position = P3{ 0.0f, 0.0f, 0.0f };
@@ -70,6 +72,31 @@ __device__ __forceinline__ void FluUser::deposit(const Accu &acc, const FluWindo
 	(void)mua;
 	mcsim_fluence_deposit_at(&sim, &pos_, w);
 #endif
+}
+#endif
+
+#if XO_USER_TRACE
+__device__ __forceinline__ bool trace_event(const TraceUser &t, float *fbuf, u32 packet,
+		u32 count, u32 flags, const P3 &pos, const P3 &dir, float w, float opl) {
+	McSim sim;
+	Rng none; none.load(0ull); none.a = 0u;
+	clc_sim_init(sim, &none);
+	sim.trace = &t.t;
+	sim.float_buffer = fbuf;
+	sim.event_flags = flags;
+	sim.state.position = pos; sim.state.direction = dir;
+	sim.state.weight = w; sim.state.optical_pathlength = opl;
+	sim.state.photon_index = packet;
+	return mcsim_trace_event(&sim, count) != 0;
+}
+__device__ __forceinline__ void trace_complete(const TraceUser &t, i32 *ibuf, u32 packet, u32 count) {
+	McSim sim;
+	Rng none; none.load(0ull); none.a = 0u;
+	clc_sim_init(sim, &none);
+	sim.trace = &t.t;
+	sim.integer_buffer = ibuf;
+	sim.state.photon_index = packet;
+	mcsim_trace_complete(&sim, count);
 }
 #endif
 

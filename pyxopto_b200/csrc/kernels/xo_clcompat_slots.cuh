@@ -30,6 +30,9 @@
 #ifndef XO_USER_FLUENCE
 #define XO_USER_FLUENCE 0
 #endif
+#ifndef XO_USER_TRACE
+#define XO_USER_TRACE 0
+#endif
 #ifndef XO_USER_SURF_TOP
 #define XO_USER_SURF_TOP 0
 #endif
@@ -109,6 +112,17 @@ struct DetUserSpecular {
 	static constexpr bool needs_opl = false;
 	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;
 };
+#endif
+
+#if XO_USER_TRACE
+// trace: `inline int mcsim_trace_event(McSim *, mc_uint_t event_count)` (1: the event was
+// recorded) and `inline void mcsim_trace_complete(McSim *, mc_uint_t event_count)`
+// (mctrace.py:541-585); the loops reach them through the trace_event / trace_complete
+// overloads below
+struct TraceUser { McTrace t; };
+__device__ __forceinline__ bool trace_event(const TraceUser &t, float *fbuf, u32 packet,
+	u32 count, u32 flags, const P3 &pos, const P3 &dir, float w, float opl);
+__device__ __forceinline__ void trace_complete(const TraceUser &t, i32 *ibuf, u32 packet, u32 count);
 #endif
 
 // sample surface layouts (mcml): `inline int mcsim_<loc>_surface_layout_handler(McSim *,

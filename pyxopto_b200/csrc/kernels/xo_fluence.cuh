@@ -339,6 +339,9 @@ struct TraceCfg {                   // mcbase/mctrace.py:504-510
 	i32 max_events; u32 data_off, count_off, event_mask;
 };
 struct TraceNone { i32 dummy; };
+#ifndef XO_USER_TRACE
+#define XO_USER_TRACE 0             // 1: the trace is a user-written fragment (xo_clcompat_slots.cuh)
+#endif
 
 // one event = 8 floats {x,y,z,px,py,pz,w,pl}; overflow keeps overwriting the
 // last slot while the count keeps growing (mctrace.py:543-545,578-581)
@@ -377,5 +380,24 @@ __device__ __forceinline__ bool trace_event(const TraceCfg &t, float *fbuf, u32 
 #endif
 	return true;
 }
+
+// a packet is finished: its event count (mctrace.py:578-584)
+__device__ __forceinline__ void trace_complete(const TraceCfg &t, i32 *ibuf, u32 packet, u32 count) {
+	ibuf[t.count_off + packet] = (i32)count;
+}
+
+// XoTrace: the kernel parameter; XoTraceCfg: what the loops hand to trace_event /
+// trace_complete (a kernel without a trace still names a TraceCfg it never touches)
+#if XO_TRACE && XO_USER_TRACE
+struct TraceUser;
+typedef TraceUser XoTrace;
+typedef TraceUser XoTraceCfg;
+#elif XO_TRACE
+typedef TraceCfg XoTrace;
+typedef TraceCfg XoTraceCfg;
+#else
+typedef TraceNone XoTrace;
+typedef TraceCfg XoTraceCfg;
+#endif
 
 }  // namespace xo

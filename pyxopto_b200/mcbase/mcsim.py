@@ -230,7 +230,8 @@ class McBase(CuWorker):
         if user:
             # compile-time options as the macros OpenCL-C fragments test (#if MC_USE_...)
             for key in sorted(opts):
-                if key.startswith('MC_') and isinstance(opts[key], (bool, int, np.integer)):
+                if (key.startswith('MC_') or key == 'TRACE_ENTRY_LEN') and \
+                        isinstance(opts[key], (bool, int, np.integer)):
                     lines.append('#define {} {}'.format(key, int(opts[key])))
             lines += ['#define {} 1'.format(self._USER_ADAPTERS[name][1]) for name, _ in user]
         lines += ['#include "xo_core.cuh"', '#include "xo_pf.cuh"',
@@ -287,6 +288,7 @@ class McBase(CuWorker):
         'XoDetBottom': ('xo::DetUserBottom', 'XO_USER_DET_BOTTOM'),
         'XoDetSpecular': ('xo::DetUserSpecular', 'XO_USER_DET_SPECULAR'),
         'XoFluence': ('xo::FluUser', 'XO_USER_FLUENCE'),
+        'XoTrace': ('xo::TraceUser', 'XO_USER_TRACE'),
         'XoSurfTop': ('xo::SurfUserTop', 'XO_USER_SURF_TOP'),
         'XoSurfBottom': ('xo::SurfUserBottom', 'XO_USER_SURF_BOTTOM'),
     }
@@ -315,7 +317,19 @@ class McBase(CuWorker):
                     '(cu_type) nor OpenCL-C fragments this geometry can compile.'.format(
                         name, type(obj).__name__ if obj is not None else None))
             out.append((name, obj))
+        if self._user_trace():
+            # (the kernel headers bind XoTrace themselves: no typedef from the bindings)
+            if 'XoTrace' not in self.user_plugin_slots:
+                raise NotImplementedError(
+                    'A user-written trace ({}) is compiled in the layered geometry '
+                    'only.'.format(type(self._trace).__name__))
+            out.append(('XoTrace', self._trace))
         return out
+
+    def _user_trace(self) -> bool:
+        """True when the trace object carries its own OpenCL-C fragments
+        (``cl_implementation``, mctrace.py:541-585) instead of the built-in event record."""
+        return self._trace is not None and hasattr(self._trace, 'cl_implementation')
 
     def _scattering_pfs(self):
         """Phase functions of the layers / materials a packet can scatter in."""
@@ -399,7 +413,7 @@ class McBase(CuWorker):
         event leaves with one 256-bit store), 1 = 16 bytes (two 128-bit stores),
         0 = scalar stores."""
         tr = self._packed.get('trace')
-        if self._trace is None or tr is None:
+        if self._trace is None or tr is None or self._user_trace():
             return 0
         off = int(tr.data_buffer_offset)
         if np.dtype(self._types.np_float).itemsize != 4:
@@ -497,7 +511,7 @@ class McBase(CuWorker):
         packet.  The reference zero-fills the whole trace buffer before every run
         (16 GB for 1e6 packets x 512 events); here that pass is skipped then."""
         tr = self._trace
-        if tr is None or tr.filter is None or not self.device_trace_filter:
+        if tr is None or tr.filter is None or not self._device_filter_applies():
             return False
         if self.resolved_options().get('MC_USE_EVENTS', False):
             # with an event mask a packet can record nothing at all: the filter then
@@ -670,8 +684,7 @@ class McBase(CuWorker):
         trace_res = fluence_res = detectors_res = None
         if self._trace is not None:
             trace_res = out_trace if out_trace is not None else type(self._trace)(self._trace)
-            if self._trace.filter is not None and self.device_trace_filter and \
-                    np.dtype(self._types.np_float).itemsize == 4:
+            if self._trace.filter is not None and self._device_filter_applies():
                 # (binary64 rows go through the host filter, like the reference's)
                 lazy = out_trace is None and self.lazy_trace_rows
                 n_sel, rows, n_dropped = self.filter_trace_on_device(
@@ -694,7 +707,7 @@ class McBase(CuWorker):
                     n=nphotons, maxlen=int(self._trace.maxlen),
                     ints=(self._cl_buffers['rw_int'], 4*int(tp.count_buffer_offset)),
                     floats=(self._cl_buffers['rw_float'], 4*int(tp.data_buffer_offset)))
-            if out_trace is None and (self._trace.filter is None or self.device_trace_filter):
+            if out_trace is None and (self._trace.filter is None or self._device_filter_applies()):
                 # the rows of this result are still on the device
                 token = object()
                 self._device_trace['token'] = token
@@ -800,6 +813,11 @@ class McBase(CuWorker):
     # only the accepted rows are downloaded; False: the reference's flow
     # (download every row, filter on the host).  Both give identical results.
     device_trace_filter = True
+
+    def _device_filter_applies(self) -> bool:
+        """The device-side filter reads the built-in single-precision event record."""
+        return bool(self.device_trace_filter and not self._user_trace() and
+                    np.dtype(self._types.np_float).itemsize == 4)
     _FILTER_SRC = '#include "xo_trace_kernels.cuh"\n'
 
     # True: the rows accepted by the device-side filter are downloaded when the
@@ -909,9 +927,17 @@ class McBase(CuWorker):
                 return
             buf = self._cl_buffers['sv_resident']
             whole = type('A', (), {'offset': 0, 'size': cells})
-            scaled = self._scale_on_device(buf, whole, 1.0/(sv.k*sv._multiplier(self)))
+            # (a fresh grid takes a free page-locked buffer of the result pool as it is -
+            # no second 64 MB host copy)
+            inv_k = 1.0/(sv.k*sv._multiplier(self))
+            if sv._data is None:
+                scaled, owned = self._scale_on_device(buf, whole, inv_k, want_owned=True)
+            else:
+                scaled, owned = self._scale_on_device(buf, whole, inv_k), False
             if sv._data is not None:
                 sv._data += np.reshape(scaled, sv.shape)
+            elif owned:
+                sv._data = scaled.reshape(sv.shape)
             else:
                 sv._data = np.array(scaled, dtype=np.float64).reshape(sv.shape)
             self._sv_resident = None

@@ -94,7 +94,7 @@ class Mc(McBase):
         return out
 
     user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular',
-                         'XoFluence', 'XoSurfTop', 'XoSurfBottom')
+                         'XoFluence', 'XoSurfTop', 'XoSurfBottom', 'XoTrace')
     clcompat_geometry_header = 'xo_clcompat_mcml.cuh'
 
     def _plugin_objects(self):

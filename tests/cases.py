@@ -562,6 +562,34 @@ def mcml_rayleigh_line_radial(mc, **kw):
                  rnginit=271828, **kw), dict(rmax=20e-3)
 
 
+def mcml_user_trace(mc, **kw):
+    """``mcml_lut_iso_radialpl_trace`` with a user-written trace that restates the built-in
+    event record: equal to it bit for bit."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    params, lut = _hg_lut()
+    det = mc.mcdetector.Detectors(
+        top=mc.mcdetector.RadialPl(Axis(0, 5e-3, 50), Axis(0, 0.05, 100)),
+        bottom=mc.mcdetector.TotalPl(Axis(0, 0.05, 100)))
+    tr = up.user_trace(mc, maxlen=50, options=mc.mctrace.Trace.TRACE_ALL)
+    return mc.Mc(_layers(mc, mc.mcpf.Lut(params, lut)),
+                 mc.mcsource.IsotropicPoint((0, 0, 0.5e-3)), det, trace=tr,
+                 rnginit=777, **kw), dict(rmax=20e-3)
+
+
+def mcml_user_trace_squared(mc, **kw):
+    """A user-written trace that records weight^2 (not in the reference), start / end
+    events only, event mask on the boundary events."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Total(), bottom=mc.mcdetector.Total())
+    T = mc.mctrace.Trace
+    tr = up.user_trace(mc, squared=True, maxlen=40, options=T.TRACE_ALL,
+                       event_mask=T.TRACE_EVENT_BOUNDARY_HIT | T.TRACE_EVENT_LAUNCH)
+    return mc.Mc(_layers(mc, mc.mcpf.Hg(0.8)), mc.mcsource.Line((0, 0, 0), (0.2, 0, 1)), det,
+                 trace=tr, rnginit=818181, **kw), dict(rmax=20e-3)
+
+
 def mcml_user_surface_reflector(mc, **kw):
     """A top surface layout written by a user (the arithmetic of LambertianReflector):
     equals ``mcml_surface_lambert_top`` bit for bit."""
@@ -602,13 +630,19 @@ GOLDEN_RUN['mcml_user_plugins_native'] = (3000, 16)
 USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_user_cubic,
               'mcml_user_fluence': mcml_user_fluence,
               'mcml_user_surface_reflector': mcml_user_surface_reflector,
-              'mcml_user_surface_window': mcml_user_surface_window}
+              'mcml_user_surface_window': mcml_user_surface_window,
+              'mcml_user_trace': mcml_user_trace,
+              'mcml_user_trace_squared': mcml_user_trace_squared}
 USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None,
                    'mcml_user_fluence': None,
                    'mcml_user_surface_reflector': 'mcml_surface_lambert_top',
-                   'mcml_user_surface_window': None}
+                   'mcml_user_surface_window': None,
+                   'mcml_user_trace': 'mcml_lut_iso_radialpl_trace',
+                   'mcml_user_trace_squared': None}
 USER_GEOMETRY = {name: 'mcml' for name in USER_CASES}
 USER_RUN = {name: (3000, 16) for name in USER_CASES}
+USER_RUN['mcml_user_trace'] = (800, 16)
+USER_RUN['mcml_user_trace_squared'] = (800, 16)
 
 
 # ---------------------------------------------------------------------------

@@ -473,11 +473,13 @@ def _raw_run(name, n, threads=256, block=64, deterministic=True):
     kw = dict(maxthreads=threads, wgsize=block) if deterministic else {}
     sim.run(n, download=False, **kw)
     accu, ints, floats = sim.download_raw()
+    sim._raw_trace = (ints, floats)
     return sim, accu, sim.download_seeds()[:threads]
 
 
 @pytest.mark.parametrize('user, native', [('mcml_user_plugins', 'mcml_user_plugins_native'),
-                                          ('mcml_user_surface_reflector', 'mcml_surface_lambert_top')])
+                                          ('mcml_user_surface_reflector', 'mcml_surface_lambert_top'),
+                                          ('mcml_user_trace', 'mcml_lut_iso_radialpl_trace')])
 def test_user_fragments_equal_builtins_bit_exact(user, native):
     """A user-written phase function, source and detector (tests/user_plugins.py)
     that restate Hg / Line / Radial - and a user-written surface layout that restates
@@ -492,6 +494,9 @@ def test_user_fragments_equal_builtins_bit_exact(user, native):
     assert np.array_equal(accu_u, accu_n)
     assert np.array_equal(x_u, x_n)
     assert sim_u.run_report['threads'] == sim_n.run_report['threads']
+    # (trace rows and event counts: a user-written trace writes what the built-in one does)
+    assert np.array_equal(sim_u._raw_trace[0], sim_n._raw_trace[0])
+    assert np.array_equal(sim_u._raw_trace[1].view(np.uint32), sim_n._raw_trace[1].view(np.uint32))
 
 
 @pytest.mark.parametrize('name', sorted(cases.USER_CASES))
@@ -507,6 +512,17 @@ def test_user_fragments_match_reference_kernel(name):
     assert abs(a - b) <= max(1e-3*b, 2*(n/t)**0.5*0x7FFFFF)
     same = np.count_nonzero(accu == g['accu'])/g['accu'].size
     assert same > 0.9
+    if sim.trace is not None:
+        # a user-written trace: its rows against the rows the reference kernel wrote with
+        # the same fragment (north star: 1e-5 relative for the packets that agree in count)
+        from helpers import trajectory_agreement
+        P = sim._packed['trace']
+        do, co, ml = int(P.data_buffer_offset), int(P.count_buffer_offset), int(sim.trace.maxlen)
+        ints, floats = sim._raw_trace
+        frac, worst, _ = trajectory_agreement(
+            floats[do:do + n*ml*8].reshape(n, ml, 8), ints[co:co + n],
+            g['floats'][do:do + n*ml*8].reshape(n, ml, 8), g['ints'][co:co + n])
+        assert frac > 0.9 and worst <= 1e-5, (frac, worst)
     # throughput mode, more packets, against the golden run scaled
     n_fast = 200000
     sim_f, accu_f, _ = _raw_run(name, n_fast, deterministic=False)

@@ -30,7 +30,17 @@ def test_reference_runs_a_user_surface_layout_like_the_builtin():
     assert gu['packed_surface_layouts'].tobytes() == gn['packed_surface_layouts'].tobytes()
 
 
-@pytest.mark.parametrize('name', ['mcml_user_plugins', 'mcml_user_surface_reflector'])
+def test_reference_runs_a_user_trace_like_the_builtin():
+    """Golden vectors of the reference kernel: the user-written trace == Trace, event rows
+    and counts included."""
+    gu, gn = golden('mcml_user_trace'), golden('mcml_lut_iso_radialpl_trace')
+    for key in ('accu', 'ints', 'floats', 'rng_x_after'):
+        assert np.array_equal(gu[key], gn[key]), key
+    assert gu['ints'].sum() > 0
+
+
+@pytest.mark.parametrize('name', ['mcml_user_plugins', 'mcml_user_surface_reflector',
+                                  'mcml_user_trace'])
 def test_oracle_pins_user_fragments_through_equivalent_builtins(name):
     eq = cases.USER_EQUIVALENT[name]
     sim, geom, _ = build_sim(eq)
@@ -51,7 +61,8 @@ def test_user_structs_pack_like_the_reference(name):
     mine = packed_bytes(sim)
     for key in ('layers', 'source', 'detectors') + \
             (('fluence',) if 'packed_fluence' in g.files else ()) + \
-            (('surface_layouts',) if 'packed_surface_layouts' in g.files else ()):
+            (('surface_layouts',) if 'packed_surface_layouts' in g.files else ()) + \
+            (('trace',) if 'packed_trace' in g.files else ()):
         assert mine[key] == g['packed_' + key].tobytes(), key
 
 
@@ -69,6 +80,10 @@ def test_user_fragments_compile_for_sm100a(name, deterministic):
     if name == 'mcml_user_fluence':
         assert 'mcsim_fluence_deposit_at' in src and 'typedef xo::FluUser XoFluence;' in src
         assert 'typedef xo::PfHg XoPf;' in src
+        return
+    if name.startswith('mcml_user_trace'):
+        assert 'mcsim_trace_event' in src and '#define XO_USER_TRACE 1' in src
+        assert '#define TRACE_ENTRY_LEN 8' in src and 'typedef xo::PfUser XoPf;' not in src
         return
     if name.startswith('mcml_user_surface'):
         assert 'mcsim_top_surface_layout_handler' in src

@@ -560,3 +560,65 @@ def rayleigh(mc, gamma):
     if mc.__name__.startswith('xopto'):
         return _fixed_rayleigh_class(mc)(gamma)
     return mc.mcpf.Rayleigh(gamma)
+
+
+# ---- trace (mcbase/mctrace.py:541-585) ------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def _user_trace_class(mc, squared: bool):
+    """A Trace whose device side is written by the user.  ``squared=False`` restates the
+    built-in event record (results must equal those of ``Trace`` bit for bit);
+    ``squared=True`` records the *square* of the packet weight in field 6 - something the
+    reference does not ship.  The host side (buffers, result arrays, filter) is inherited."""
+    class UserTrace(mc.mctrace.Trace):
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McTrace{ mc_int_t max_events; ' \
+                   'mc_size_t data_buffer_offset; mc_size_t count_buffer_offset; ' \
+                   'mc_uint_t event_mask; };\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_trace(__mc_trace_mem const McTrace *trace){
+	dbg_print("user-written trace:");
+	dbg_print_int(INDENT "max_events:", trace->max_events);
+};
+
+inline int mcsim_trace_event(McSim *mcsim, mc_uint_t event_count){
+	__mc_trace_mem const McTrace *trace = mcsim_trace(mcsim);
+	mc_size_t pos = mc_min(event_count, trace->max_events - 1)*TRACE_ENTRY_LEN +
+		mcsim_packet_index(mcsim)*trace->max_events*TRACE_ENTRY_LEN +
+		trace->data_buffer_offset;
+
+	#if MC_USE_EVENTS
+		if (!(trace->event_mask & mcsim_event_flags(mcsim)))
+			return 0;
+	#endif
+
+	mcsim_float_buffer(mcsim)[pos++] = mcsim_position_x(mcsim);
+	mcsim_float_buffer(mcsim)[pos++] = mcsim_position_y(mcsim);
+	mcsim_float_buffer(mcsim)[pos++] = mcsim_position_z(mcsim);
+	mcsim_float_buffer(mcsim)[pos++] = mcsim_direction_x(mcsim);
+	mcsim_float_buffer(mcsim)[pos++] = mcsim_direction_y(mcsim);
+	mcsim_float_buffer(mcsim)[pos++] = mcsim_direction_z(mcsim);
+	mcsim_float_buffer(mcsim)[pos++] = %s;
+	#if MC_TRACK_OPTICAL_PATHLENGTH
+		mcsim_float_buffer(mcsim)[pos++] = mcsim_optical_pathlength(mcsim);
+	#else
+		mcsim_float_buffer(mcsim)[pos++] = FP_0;
+	#endif
+	return 1;
+};
+
+inline void mcsim_trace_complete(McSim *mcsim, mc_uint_t event_count){
+	mcsim_integer_buffer(mcsim)[
+		mcsim_trace(mcsim)->count_buffer_offset +
+		mcsim_packet_index(mcsim)] = (mc_int_t)event_count;
+};
+''' % ('mcsim_weight(mcsim)*mcsim_weight(mcsim)' if squared else 'mcsim_weight(mcsim)')
+
+    return UserTrace
+
+
+def user_trace(mc, squared=False, **kw):
+    return _user_trace_class(mc, bool(squared))(**kw)
