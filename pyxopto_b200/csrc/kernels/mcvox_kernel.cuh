@@ -222,8 +222,14 @@ McKernel(
 	float4 *P_B = P_A + pool_warps*XO_VOX_POOL;
 	float4 *P_C = P_B + pool_warps*XO_VOX_POOL;
 	float4 *P_D = P_C + pool_warps*XO_VOX_POOL;
+#if XO_TRACE
+	// (traced packets: a fifth quad per slot - optical path length, packet, events, flags)
+	float4 *P_T = P_D + pool_warps*XO_VOX_POOL;
+	unsigned char *P_ST = reinterpret_cast<unsigned char *>(P_T + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
+#else
 	float *P_E = reinterpret_cast<float *>(P_D + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
 	unsigned char *P_ST = reinterpret_cast<unsigned char *>(P_E + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
+#endif
 	unsigned char *P_IDX = P_ST + (pool_warps - pool_warp)*XO_VOX_POOL + pool_warp*32u;
 #else
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;

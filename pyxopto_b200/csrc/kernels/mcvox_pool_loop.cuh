@@ -28,8 +28,14 @@
 // length.  The MWC stream belongs to the lane, not to the packet (throughput mode is
 // not stream-aligned with the reference anyway).
 //
+// With a trace (XO_TRACE) a slot carries a fifth quad T = optical path length | packet
+// index | recorded events | pending event flags, every phase records its events with
+// trace_event (one 256-bit store per event) exactly where the lane-resident loop does, and
+// for full traces the clearance shortcut is off (one event per voxel crossing is the
+// product there): every flight walks.
+//
 // Host conditions (mcvox/mc.py): compact map, throughput mode, albedo weight /
-// albedo rejection, no trace, isotropic materials, rmax test compiled out.
+// albedo rejection, isotropic materials, rmax test compiled out.
 {
 	// slot states: the class (INTERACT / WALK set-up / WALK / BOUNDARY) sits in bits 3-4
 	enum : u32 { PS_EMPTY = 0, PS_NEW = 1, PS_RAY = 2, PS_SCAT = 3, PS_FAR = 4, PS_DDA = 8, PS_RUN = 16, PS_BND = 24 };
@@ -53,12 +59,39 @@
 	const u32 vox_bxy = vox_bx + vox_by;
 	const u32 vox_mx = (1u << vox_bx) - 1u, vox_my = (1u << vox_by) - 1u;
 	(void)chunk; (void)nthreads; (void)refill; (void)rmax2; (void)src_pos; (void)int_buffer; (void)float_buffer;
+	u32 packet = 0, trace_count = 0, flags = 0;     // (trace builds: of the slot in hand)
+	(void)packet; (void)trace_count; (void)flags;
 	const u32 vbase_lo = (u32)reinterpret_cast<u64>(voxels8);
 	const u32 vbase_hi = (u32)(reinterpret_cast<u64>(voxels8) >> 32);
 	const float inv_sx = 1.0f/cfg.size.x, inv_sy = 1.0f/cfg.size.y, inv_sz = 1.0f/cfg.size.z;
 #define XO_VOXEL(lo) ((u32)__ldg(reinterpret_cast<const unsigned short *>(((u64)vbase_hi << 32) | (u64)(lo))))
 #define XO_PACK_VOXEL(ix_, iy_, iz_) (vbase_lo + 2u*((u32)((ix_) + 2) | ((u32)((iy_) + 2) << vox_bx) | ((u32)((iz_) + 2) << vox_bxy)))
 #define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
+#define XO_POOL_CLEARANCE (XO_TRACE != XO_TRACE_ALL)
+#if XO_TRACE
+	const XoTraceCfg &tcfg = *reinterpret_cast<const XoTraceCfg *>(&trace);
+	// trace quad of a slot: optical path length | packet | recorded events | pending flags
+#define XO_POOL_LOAD_T() do { const float4 t_ = P_T[slot]; opl = t_.x; packet = __float_as_uint(t_.y); \
+		trace_count = __float_as_uint(t_.z); flags = __float_as_uint(t_.w); } while (0)
+#define XO_POOL_STORE_T() do { P_T[slot] = make_float4(opl, __uint_as_float(packet), \
+		__uint_as_float(trace_count), __uint_as_float(flags)); } while (0)
+	// end of a loop trip of the reference (mcvox.template.c:983-1012): the event, the count
+#define XO_POOL_TRACE_TRIP() do { \
+		flags |= done ? EV_TERMINATED : 0u; \
+		if (XO_TRACE == XO_TRACE_ALL || ((XO_TRACE & XO_TRACE_END) && done)) { \
+			if (trace_event(tcfg, float_buffer, packet, trace_count, flags, pos, dir, weight, opl)) \
+				++trace_count; \
+		} \
+		if (done) trace_complete(tcfg, int_buffer, packet, trace_count); \
+		flags = 0u; \
+	} while (0)
+#define XO_POOL_OPL (true)
+#else
+#define XO_POOL_LOAD_T() do { if (XO_NEEDS_OPL) opl = P_E[slot]; } while (0)
+#define XO_POOL_STORE_T() do { if (XO_NEEDS_OPL) P_E[slot] = opl; } while (0)
+#define XO_POOL_TRACE_TRIP() do { } while (0)
+#define XO_POOL_OPL (XO_NEEDS_OPL)
+#endif
 	// slots of this warp
 	P_ST[lane] = (unsigned char)PS_EMPTY;
 	P_ST[lane + 32u] = (unsigned char)PS_EMPTY;
@@ -130,7 +163,7 @@
 				vlo = __float_as_uint(P_C[slot].w);
 				const u32 misc = __float_as_uint(P_D[slot].w);
 				mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu;
-				if (XO_NEEDS_OPL) opl = P_E[slot];
+				XO_POOL_LOAD_T();
 				if (st == PS_NEW) { const u32 cell = XO_VOXEL(vlo); mat = cell & 0xffu; dcur = cell >> 8; }
 			}
 			VoxHot c_hot;
@@ -143,7 +176,7 @@
 					pos.x = fmaf(dir.x, t_s, pos.x);
 					pos.y = fmaf(dir.y, t_s, pos.y);
 					pos.z = fmaf(dir.z, t_s, pos.z);
-					if (XO_NEEDS_OPL) opl = fmaf(c_hot.n, t_s, opl);
+					if (XO_POOL_OPL) opl = fmaf(c_hot.n, t_s, opl);
 					u32 mat_here = mat;
 					if (st == PS_FAR) {
 						// the flight skipped the walk: voxel of the interaction point from the
@@ -170,9 +203,11 @@
 						float deposit = weight;
 						done = true;
 						weight = 0.0f;
+						flags |= EV_ABSORPTION;
 						if (XoFluence::active) fluence.deposit(acc, window, pos, deposit, c_hot.mua, opl);
 					} else {
 						pf_scatter(c_pf, rng, lut, dir);
+						flags |= EV_SCATTERING;
 					}
 #else
 					{
@@ -189,6 +224,7 @@
 #endif
 					}
 					pf_scatter(c_pf, rng, lut, dir);
+					flags |= EV_ABSORPTION | EV_SCATTERING;
 					if (weight < XO_WEIGHT_MIN) {
 #if XO_USE_LOTTERY
 						if (rng.next_raw() > XO_LOTTERY_CHANCE*4294967296.0f) done = true;
@@ -199,14 +235,15 @@
 					}
 #endif
 					if (mat_here != mat) { mat = mat_here; XO_LOAD_MAT(mat); }
-					if (weight <= 0.0f) done = true;
+					if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; }
+					XO_POOL_TRACE_TRIP();
 					st = done ? PS_EMPTY : PS_RAY;
 				}
 				if (st == PS_RAY || st == PS_NEW) {
 					t_s = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
 					// extent of the flight in voxels along its longest axis against the clearance
 					const float ext = t_s*fmaxf(fabsf(dir.x)*inv_sx, fmaxf(fabsf(dir.y)*inv_sy, fabsf(dir.z)*inv_sz));
-					st = (ext < (float)dcur - 1.0f) ? PS_FAR : PS_DDA;
+					st = (XO_POOL_CLEARANCE && ext < (float)dcur - 1.0f) ? PS_FAR : PS_DDA;
 				}
 				if ((u32)__popc(__ballot_sync(0xffffffffu, st == PS_FAR)) < XO_POOL_THR_I) break;
 			}
@@ -215,7 +252,7 @@
 				P_B[slot] = make_float4(dir.x, dir.y, dir.z, t_s);
 				P_C[slot].w = __uint_as_float(vlo);
 				P_D[slot].w = __uint_as_float(mat | (dcur << 8));
-				if (XO_NEEDS_OPL) P_E[slot] = opl;
+				XO_POOL_STORE_T();
 				P_ST[slot] = (unsigned char)st;
 			}
 		} else if (phase == PH_WALK) {
@@ -224,10 +261,23 @@
 			i32 last_d = 0;
 			float tmx = XO_INF, tmy = XO_INF, tmz = XO_INF, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
 			float t_s = 0.0f, t_evt = 0.0f;
+#if XO_TRACE == XO_TRACE_ALL
+			// (every crossing is an event: the ray itself, the weight and the trace quad)
+			P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
+			float weight = 0.0f, opl = 0.0f;
+#endif
 			if (act) {
 				st = P_ST[slot];
 				const float4 b = P_B[slot];
 				t_s = b.w;
+#if XO_TRACE == XO_TRACE_ALL
+				{
+					const float4 a_ = P_A[slot];
+					pos.x = a_.x; pos.y = a_.y; pos.z = a_.z; weight = a_.w;
+					dir.x = b.x; dir.y = b.y; dir.z = b.z;
+					XO_POOL_LOAD_T();
+				}
+#endif
 				if (st == PS_DDA) {
 					const float4 a = P_A[slot];
 					vlo = __float_as_uint(P_C[slot].w);
@@ -265,6 +315,18 @@
 			asm volatile("" : "+r"(stx), "+r"(sty), "+r"(stz));
 			float step_k = sh_fast[mat].hot.step_k;
 			(void)step_k;
+#if XO_TRACE == XO_TRACE_ALL
+			float n_mat = sh_fast[mat].hot.n;
+#define XO_TRACE_CROSSING(tmin_) do { \
+				P3 pc_ = { fmaf(dir.x, tmin_, pos.x), fmaf(dir.y, tmin_, pos.y), fmaf(dir.z, tmin_, pos.z) }; \
+				if (trace_event(tcfg, float_buffer, packet, trace_count, \
+						flags | EV_BOUNDARY_HIT | EV_REFRACTION, pc_, dir, weight, \
+						fmaf(n_mat, tmin_, opl))) ++trace_count; \
+				flags = 0u; \
+			} while (0)
+#else
+#define XO_TRACE_CROSSING(tmin_) do { } while (0)
+#endif
 			// Two crossings per trip; the lookup of the second one is issued before the first
 			// has returned, and committed only if the first one stayed inside the material.
 			for (;;) {
@@ -302,6 +364,7 @@
 						// of the flight is still Exp(1) distributed, so the free path is rescaled to
 						// the new material (the grid face stays an event).
 #define XO_MATERIAL_CHANGE(m_, tmin_) do { \
+							XO_TRACE_CROSSING(tmin_); \
 							const float k_new_ = sh_fast[m_].hot.step_k; \
 							t_s = fmaf(t_s - (tmin_), k_new_*FastMath::rcp_approx(step_k), (tmin_)); \
 							step_k = k_new_; \
@@ -319,8 +382,10 @@
 								st = PS_BND; t_evt = tmin_a; last_d = d_a;
 							}
 						} else if (!ok_b) {
+							XO_TRACE_CROSSING(tmin_a);      // the reference records every loop trip
 							st = PS_SCAT;
 						} else {
+							XO_TRACE_CROSSING(tmin_a);
 							++iterations;
 							if (qx) tmx += tdx;
 							if (qy) tmy += tdy;
@@ -333,6 +398,8 @@
 								} else {
 									st = PS_BND; t_evt = tmin_b; last_d = d_b;
 								}
+							} else {
+								XO_TRACE_CROSSING(tmin_b);
 							}
 						}
 #undef XO_MATERIAL_CHANGE
@@ -347,8 +414,12 @@
 				P_C[slot] = make_float4(tmx, tmy, tmz, __uint_as_float(vlo));
 				P_D[slot] = make_float4(tdx, tdy, tdz,
 					__uint_as_float(mat | (dcur << 8) | (axis << 16) | (sg << 18)));
+#if XO_TRACE == XO_TRACE_ALL
+				XO_POOL_STORE_T();
+#endif
 				P_ST[slot] = (unsigned char)st;
 			}
+#undef XO_TRACE_CROSSING
 		} else if (phase == PH_BOUNDARY) {
 			// ======== a face between materials of different refractive index, or the face of
 			// the grid (mcvox.template.c:275-388); the walk already moved the voxel address
@@ -362,13 +433,13 @@
 				const u32 misc = __float_as_uint(P_D[slot].w);
 				u32 mat = misc & 0xffu;
 				const u32 axis = (misc >> 16) & 3u, sg = (misc >> 18) & 7u;
-				if (XO_NEEDS_OPL) opl = P_E[slot];
+				XO_POOL_LOAD_T();
 				const VoxHot hot = sh_fast[mat].hot;
 				bool done = false;
 				pos.x = fmaf(dir.x, t_evt, pos.x);
 				pos.y = fmaf(dir.y, t_evt, pos.y);
 				pos.z = fmaf(dir.z, t_evt, pos.z);
-				if (XO_NEEDS_OPL) opl = fmaf(hot.n, t_evt, opl);
+				if (XO_POOL_OPL) opl = fmaf(hot.n, t_evt, opl);
 				const u32 entered = XO_VOXEL(vlo) & 0xffu;
 				const bool escaping = (entered == XO_VOX_SENTINEL);
 				const u32 next_mat = escaping ? 0u : entered;
@@ -382,6 +453,7 @@
 					else if (axis == 1u) through = fresnel_axis_fast(n12, cc, dir.y, dir.x, dir.z, rng);
 					else through = fresnel_axis_fast(n12, cc, dir.z, dir.x, dir.y, rng);
 				}
+				flags |= EV_BOUNDARY_HIT | (through ? EV_REFRACTION : EV_REFLECTION);
 				if (through) {
 					if (escaping) {
 						const i32 iz = (i32)(((vlo - vbase_lo) >> 1) >> vox_bxy) - 2;
@@ -400,12 +472,13 @@
 						((axis == 1u) ? (((sg & 2u) ? 2 : -2) << vox_bx) : (((sg & 4u) ? 2 : -2) << vox_bxy));
 					vlo -= (u32)d;
 				}
-				if (weight <= 0.0f) done = true;
+				if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; }
+				XO_POOL_TRACE_TRIP();
 				P_A[slot] = make_float4(pos.x, pos.y, pos.z, weight);
 				P_B[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
 				P_C[slot].w = __uint_as_float(vlo);
 				P_D[slot].w = __uint_as_float(mat | (1u << 8));   // on a face: clearance 1
-				if (XO_NEEDS_OPL) P_E[slot] = opl;
+				XO_POOL_STORE_T();
 				P_ST[slot] = (unsigned char)(done ? PS_EMPTY : PS_RAY);
 			}
 		} else {
@@ -434,7 +507,18 @@
 				P_B[slot] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, 0.0f);
 				P_C[slot].w = __uint_as_float(XO_PACK_VOXEL(ix, iy, iz));
 				P_D[slot].w = __uint_as_float(0u);
-				if (XO_NEEDS_OPL) P_E[slot] = 0.0f;
+				{
+					float opl = 0.0f;
+					(void)opl;
+					packet = base + lane;
+					trace_count = 0u;
+					flags = EV_LAUNCH;
+#if XO_TRACE & XO_TRACE_START
+					if (trace_event(tcfg, float_buffer, packet, 0u, EV_LAUNCH,
+							L_.pos, L_.dir, L_.weight, 0.0f)) trace_count = 1u;
+#endif
+					XO_POOL_STORE_T();
+				}
 				P_ST[slot] = (unsigned char)PS_NEW;
 				started = true;
 			}
@@ -444,6 +528,11 @@
 #undef XO_LOAD_MAT
 #undef XO_VOXEL
 #undef XO_PACK_VOXEL
+#undef XO_POOL_CLEARANCE
+#undef XO_POOL_LOAD_T
+#undef XO_POOL_STORE_T
+#undef XO_POOL_TRACE_TRIP
+#undef XO_POOL_OPL
 	// every lane drew from its stream: all states go back
 	rng_state_x[gid] = rng.state();
 }

@@ -171,11 +171,12 @@ class Mc(McBase):
 
     def _pool_slots(self, opts=None) -> int:
         """Slots per warp, or 0 where the pool loop does not apply: it covers the compact
-        map in throughput mode with albedo weight / rejection, no trace, isotropic
-        materials and no reachable rmax sphere."""
+        map in throughput mode with albedo weight / rejection, isotropic materials and no
+        reachable rmax sphere (built-in trace included; a user-written trace keeps the
+        lane-resident loop)."""
         opts = self.resolved_options() if opts is None else opts
         if not self.pool_slots or self.deterministic or not self._vox_packed() or \
-                self._trace is not None or self._rmax_needed() or \
+                self._user_trace() or self._rmax_needed() or \
                 isinstance(self._materials[0], mcmaterial.AnisotropicMaterial) or \
                 opts.get('MC_METHOD', 0) not in (0, 1):
             return 0
@@ -190,8 +191,10 @@ class Mc(McBase):
     def _queue_bytes(self, block: int) -> int:
         slots = self._pool_slots()
         if slots:
-            # 4 x float4 + 1 float + 1 state byte per slot, 32 index bytes per warp
-            return (block//32)*(slots*69 + 32) + 32
+            # 4 x float4 + 1 float (traced packets: a fifth float4) + 1 state byte per slot,
+            # 32 index bytes per warp
+            per_slot = 64 + (16 if self._trace is not None else 4) + 1
+            return (block//32)*(slots*per_slot + 32) + 32
         return super()._queue_bytes(block)
 
     def _extra_defines(self, opts):

@@ -213,16 +213,21 @@ def test_fast_mode_agrees_with_deterministic_mode_at_scale(config, n):
     assert checked > 0
 
 
-@pytest.mark.parametrize('name', ['mcvox_line_mhg_trace', 'mcml_lut_iso_radialpl_trace',
-                                  'mccyl_gk_ubeam_fiz_trace'])
+@pytest.mark.parametrize('name', ['mcvox_line_mhg_trace', 'mcvox_line_mhg_trace:lane-resident',
+                                  'mcml_lut_iso_radialpl_trace', 'mccyl_gk_ubeam_fiz_trace'])
 def test_throughput_mode_trace_statistics(name):
     """Trace recording in the throughput loops (mcvox: one event per crossing /
     interaction of the voxel walk, like the reference's loop trips): the
     distribution of per-packet event counts, the overflow fraction and the
     terminal events (position, weight, path length) agree with the oracle."""
     n = 40000
+    name, _, loop = name.partition(':')
     sim, geom, _ = build_sim(name)
+    if loop:
+        sim.pool_slots = 0          # mcvox: the lane-resident loop instead of the packet pool
     sim.run(n, download=False)
+    if geom == 'mcvox':
+        assert sim.run_report['loop'] == ('lane-resident rays' if loop else 'packet pool')
     accu, ints, floats = sim.download_raw()
     desc = xo_oracle.describe(sim, geom)
     ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
@@ -730,3 +735,56 @@ def test_both_mcvox_throughput_loops_against_the_oracle(name, method):
             for axis in range(g.ndim):
                 rest = tuple(i for i in range(g.ndim) if i != axis)
                 check(g.sum(axis=rest), c.sum(axis=rest), k, (slots, 'fluence', axis), 5)
+
+
+@pytest.mark.parametrize('slots', [64, 0])
+def test_voxel_trace_rows_are_consistent(slots):
+    """Full trace of the voxel geometry in throughput mode - packet pool and lane-resident
+    loop: every row is a coherent trajectory (launch event first, unit directions, positions
+    inside the voxel box, each event on the ray the previous one left along its recorded
+    direction, optical path length growing by n x distance, zero tail)."""
+    import benchcfg
+    from pyxopto_b200.mcvox import mc
+    n, maxlen = 20000, 128
+    sim = benchcfg.c4_trace_vox(mc, maxlen=maxlen)
+    sim.pool_slots = slots
+    sim.device_trace_filter = False          # raw rows wanted: zero-filled tails
+    sim.run(n, download=False)
+    assert sim.run_report['loop'] == ('packet pool' if slots else 'lane-resident rays')
+    accu, ints, floats = sim.download_raw()
+    tp = sim._packed['trace']
+    co, do = int(tp.count_buffer_offset), int(tp.data_buffer_offset)
+    cnt = ints[co:co + n]
+    rows = floats[do:do + n*maxlen*8].reshape(n, maxlen, 8).astype(np.float64)
+    assert cnt.min() >= 2
+    nrec = np.minimum(cnt, maxlen)
+    idx = np.arange(maxlen)[None, :]
+    valid = idx < nrec[:, None]
+    assert not rows[~valid].any()
+    dn = np.linalg.norm(rows[..., 3:6], axis=2)
+    assert np.allclose(dn[valid], 1.0, atol=1e-4)
+    assert np.allclose(rows[:, 0, :3], 0.0) and np.allclose(rows[:, 0, 5], 1.0)
+    half, depth = 201/2*5e-6, 201*5e-6
+    pos = rows[..., :3]
+    tol = 1e-9
+    assert np.abs(pos[..., 0][valid]).max() <= half + tol and np.abs(pos[..., 1][valid]).max() <= half + tol
+    assert pos[..., 2][valid].min() >= -tol and pos[..., 2][valid].max() <= depth + tol
+    # consecutive events of packets that did not overflow: event i + 1 lies on the ray that
+    # leaves event i along the direction recorded there
+    whole = cnt <= maxlen
+    pair = valid[:, 1:] & valid[:, :-1] & whole[:, None]
+    disp = pos[:, 1:] - pos[:, :-1]
+    d0 = rows[:, :-1, 3:6]
+    dist = np.linalg.norm(disp, axis=2)
+    cross = np.linalg.norm(np.cross(disp, d0), axis=2)
+    along = (disp*d0).sum(axis=2)
+    assert (cross[pair] <= 2e-4*dist[pair] + 2e-10).all()
+    assert (along[pair] >= -2e-10).all()
+    # optical path length: n x geometric distance (one refractive index in this medium)
+    dpl = rows[:, 1:, 7] - rows[:, :-1, 7]
+    assert (dpl[pair] >= -1e-9).all()
+    assert np.allclose(dpl[pair], 1.337*dist[pair], rtol=2e-3, atol=2e-8)
+    # weights never grow except by the survival lottery (x 10)
+    w = rows[..., 6]
+    ratio = w[:, 1:][pair]/np.maximum(w[:, :-1][pair], 1e-30)
+    assert ((ratio <= 1.0 + 1e-6) | (np.abs(ratio - 10.0) <= 1e-4) | (w[:, 1:][pair] == 0.0)).all()

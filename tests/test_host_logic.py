@@ -48,11 +48,15 @@ def test_loop_selection(change, loop):
         assert sim._queue_bytes(256) == 40*256 + 16
 
 
-def test_a_trace_keeps_the_lane_resident_loop():
+def test_a_traced_run_uses_the_pool_with_a_trace_quad_per_slot():
     sim, geom, _ = build_sim('mcvox_line_mhg_trace')
     sim._pack(600)
-    assert geom == 'mcvox' and sim._loop_name() == 'lane-resident rays'
-    assert _define(sim.kernel_source(block=64), 'XO_VOX_POOL') == '0'
+    assert geom == 'mcvox' and sim._loop_name() == 'packet pool'
+    assert _define(sim.kernel_source(block=64), 'XO_VOX_POOL') == '64'
+    # per warp: 64 slots of 5 quads + 1 state byte, 32 bytes of gather indices
+    assert sim._queue_bytes(64) == 2*(64*81 + 32) + 32
+    sim.pool_slots = 0
+    assert sim._loop_name() == 'lane-resident rays' and sim._queue_bytes(64) == 40*64 + 16
 
 
 def test_pool_thresholds_reach_the_translation_unit():
