@@ -168,6 +168,12 @@ class Mc(McBase):
     # wait for.  0 keeps the packets in the registers of their lane (mcvox_dda_loop.cuh).
     pool_slots = 64
     pool_tuning = {}                 # XO_POOL_* thresholds (developer knob)
+    # A full trace (one event per loop trip) is a store stream: the SM's store path, not the
+    # lane count, bounds it, and the lane-resident loop with its 10 walking lanes per warp
+    # feeds it better than the pool with 25 (C4 on the voxel geometry, 2e5 packets: 1.24 ms
+    # against 1.88 ms; more resident warps lose the same way, profiles/r02y_*).  The pool
+    # records traces correctly (tests) and is kept for start / end traces.
+    pool_full_trace = False
 
     def _pool_slots(self, opts=None) -> int:
         """Slots per warp, or 0 where the pool loop does not apply: it covers the compact
@@ -177,6 +183,7 @@ class Mc(McBase):
         opts = self.resolved_options() if opts is None else opts
         if not self.pool_slots or self.deterministic or not self._vox_packed() or \
                 self._user_trace() or self._rmax_needed() or \
+                (int(opts.get('MC_USE_TRACE', 0)) == 7 and not self.pool_full_trace) or \
                 isinstance(self._materials[0], mcmaterial.AnisotropicMaterial) or \
                 opts.get('MC_METHOD', 0) not in (0, 1):
             return 0

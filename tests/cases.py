@@ -302,6 +302,20 @@ def mcvox_line_mhg_trace(mc, **kw):
     return _fill_skin_vessel(sim, center=250e-6, radius=80e-6), dict(rmax=5e-3)
 
 
+def mcvox_line_mhg_trace_startend(mc, **kw):
+    """Launch and terminal events only (TRACE_START | TRACE_END) in the voxel geometry."""
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc, n=(16, 16, 20))
+    det = mc.mcdetector.Detectors(top=mc.mcdetector.Cartesian(A(-0.2e-3, 0.2e-3, 16)),
+                                  bottom=mc.mcdetector.Radial(A(0, 0.3e-3, 10), cosmin=0.3))
+    T = mc.mctrace.Trace
+    tr = T(maxlen=3, options=T.TRACE_START | T.TRACE_END, plon=True)
+    sim = mc.Mc(vox, _vox_materials(mc, lambda g: mc.mcpf.MHg(g, 0.85), n_vessel=1.36),
+                mc.mcsource.Line((10e-6, -5e-6, 0.0), (0.2, 0.1, 1.0)),
+                detectors=det, trace=tr, rnginit=2468, **kw)
+    return _fill_skin_vessel(sim, center=250e-6, radius=80e-6), dict(rmax=5e-3)
+
+
 def mcvox_isopoint_fluencerate(mc, **kw):
     vox = _vox_grid(mc, n=(20, 20, 20))
     flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='fluence')
@@ -351,12 +365,14 @@ MCVOX_CASES = {
     'mcvox_gk2_line_total': mcvox_gk2_line_total,
     'mcvox_gauss_fluence': mcvox_gauss_fluence,
     'mcvox_line_mhg_trace': mcvox_line_mhg_trace,
+    'mcvox_line_mhg_trace_startend': mcvox_line_mhg_trace_startend,
     'mcvox_isopoint_fluencerate': mcvox_isopoint_fluencerate,
 }
 ALL_CASES.update(MCVOX_CASES)
 GEOMETRY.update({name: 'mcvox' for name in MCVOX_CASES})
 GOLDEN_RUN.update({'mcvox_ubeam_radial': (1500, 16), 'mcvox_ufiber_fluence': (1500, 16),
                    'mcvox_gk2_line_total': (1000, 16), 'mcvox_gauss_fluence': (2000, 16), 'mcvox_line_mhg_trace': (600, 16),
+                   'mcvox_line_mhg_trace_startend': (1500, 16),
                    'mcvox_isopoint_fluencerate': (2000, 16)})
 
 

@@ -214,6 +214,8 @@ def test_fast_mode_agrees_with_deterministic_mode_at_scale(config, n):
 
 
 @pytest.mark.parametrize('name', ['mcvox_line_mhg_trace', 'mcvox_line_mhg_trace:lane-resident',
+                                  'mcvox_line_mhg_trace_startend',
+                                  'mcvox_line_mhg_trace_startend:lane-resident',
                                   'mcml_lut_iso_radialpl_trace', 'mccyl_gk_ubeam_fiz_trace'])
 def test_throughput_mode_trace_statistics(name):
     """Trace recording in the throughput loops (mcvox: one event per crossing /
@@ -223,8 +225,11 @@ def test_throughput_mode_trace_statistics(name):
     n = 40000
     name, _, loop = name.partition(':')
     sim, geom, _ = build_sim(name)
-    if loop:
-        sim.pool_slots = 0          # mcvox: the lane-resident loop instead of the packet pool
+    if geom == 'mcvox':
+        # the packet pool records traces as well; by default a full trace keeps the
+        # lane-resident loop (store-bound, measured faster there)
+        sim.pool_full_trace = not loop
+        sim.pool_slots = 0 if loop else 64
     sim.run(n, download=False)
     if geom == 'mcvox':
         assert sim.run_report['loop'] == ('lane-resident rays' if loop else 'packet pool')
@@ -748,6 +753,7 @@ def test_voxel_trace_rows_are_consistent(slots):
     n, maxlen = 20000, 128
     sim = benchcfg.c4_trace_vox(mc, maxlen=maxlen)
     sim.pool_slots = slots
+    sim.pool_full_trace = True
     sim.device_trace_filter = False          # raw rows wanted: zero-filled tails
     sim.run(n, download=False)
     assert sim.run_report['loop'] == ('packet pool' if slots else 'lane-resident rays')

@@ -48,10 +48,14 @@ def test_loop_selection(change, loop):
         assert sim._queue_bytes(256) == 40*256 + 16
 
 
-def test_a_traced_run_uses_the_pool_with_a_trace_quad_per_slot():
+def test_traces_and_the_pool():
+    """A full trace keeps the lane-resident loop (store-bound: measured slower in the pool)
+    unless asked for; the pool then carries a trace quad per slot."""
     sim, geom, _ = build_sim('mcvox_line_mhg_trace')
     sim._pack(600)
-    assert geom == 'mcvox' and sim._loop_name() == 'packet pool'
+    assert geom == 'mcvox' and sim._loop_name() == 'lane-resident rays'
+    sim.pool_full_trace = True
+    assert sim._loop_name() == 'packet pool'
     assert _define(sim.kernel_source(block=64), 'XO_VOX_POOL') == '64'
     # per warp: 64 slots of 5 quads + 1 state byte, 32 bytes of gather indices
     assert sim._queue_bytes(64) == 2*(64*81 + 32) + 32
