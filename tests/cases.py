@@ -309,7 +309,7 @@ def mcvox_line_mhg_trace_startend(mc, **kw):
     det = mc.mcdetector.Detectors(top=mc.mcdetector.Cartesian(A(-0.2e-3, 0.2e-3, 16)),
                                   bottom=mc.mcdetector.Radial(A(0, 0.3e-3, 10), cosmin=0.3))
     T = mc.mctrace.Trace
-    tr = T(maxlen=3, options=T.TRACE_START | T.TRACE_END, plon=True)
+    tr = T(maxlen=2, options=T.TRACE_START | T.TRACE_END, plon=True)
     sim = mc.Mc(vox, _vox_materials(mc, lambda g: mc.mcpf.MHg(g, 0.85), n_vessel=1.36),
                 mc.mcsource.Line((10e-6, -5e-6, 0.0), (0.2, 0.1, 1.0)),
                 detectors=det, trace=tr, rnginit=2468, **kw)
