@@ -331,6 +331,9 @@ struct FluCylt {                    // mcfluence/fluencecylt.py:79-95
 #ifndef XO_USE_EVENTS
 #define XO_USE_EVENTS 0
 #endif
+#ifndef XO_TRACE_STORE_HINT
+#define XO_TRACE_STORE_HINT 0
+#endif
 #define XO_TRACE_START 1
 #define XO_TRACE_END 2
 #define XO_TRACE_ALL 7
@@ -366,9 +369,25 @@ __device__ __forceinline__ bool trace_event(const TraceCfg &t, float *fbuf, u32 
 	// it one trip later (so that the warp does not wait behind the store until the LSU
 	// has read the operands, 46 % of the stall samples) changed nothing: 2.75 vs 2.69 ms
 	// per 1e6 packets of C4 - the SM's store path itself (~16 B/clk) is the limit.
+#if XO_TRACE_STORE_HINT == 1
+	// (experiment: the event stream marked evict-first in L2 and not allocated in L1, so
+	// that it does not wash the voxel map / lookup tables out of the caches)
+	{
+		unsigned long long pol_;
+		asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_));
+		asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+			:: "l"(dst), "f"(pos.x), "f"(pos.y), "f"(pos.z), "f"(dir.x), "f"(dir.y),
+			   "f"(dir.z), "f"(w), "f"(opl), "l"(pol_) : "memory");
+	}
+#elif XO_TRACE_STORE_HINT == 2
+	asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+		:: "l"(dst), "f"(pos.x), "f"(pos.y), "f"(pos.z), "f"(dir.x), "f"(dir.y),
+		   "f"(dir.z), "f"(w), "f"(opl) : "memory");
+#else
 	asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
 		:: "l"(dst), "f"(pos.x), "f"(pos.y), "f"(pos.z), "f"(dir.x), "f"(dir.y),
 		   "f"(dir.z), "f"(w), "f"(opl) : "memory");
+#endif
 #elif XO_TRACE_ALIGNED
 	float4 *d4 = reinterpret_cast<float4 *>(dst);
 	d4[0] = make_float4(pos.x, pos.y, pos.z, dir.x);

@@ -217,6 +217,7 @@ class McBase(CuWorker):
             '#define XO_FLUENCE_RATE {}'.format(
                 int(bool(opts.get('MC_FLUENCE_MODE_RATE', False)))),
             '#define XO_TRACE_ALIGNED {}'.format(int(self._trace_aligned())),
+            '#define XO_TRACE_STORE_HINT {}'.format(int(self.trace_store_hint)),
             '#define XO_USE_RMAX {}'.format(int(self._rmax_needed())),
             '#define XO_FLU_WINDOW {}'.format(int(self._window_enabled())),
             '#define XO_PF_G0 {}'.format(int(self._pf_isotropic_possible())),
@@ -407,6 +408,9 @@ class McBase(CuWorker):
 
     def _extra_checks(self):
         return []
+
+    # cache hints of the 256-bit event store (developer knob; 0: plain store)
+    trace_store_hint = int(os.environ.get('XOPTO_TRACE_STORE_HINT', '0'))
 
     def _trace_aligned(self) -> int:
         """Alignment class of the trace rows in the float buffer: 2 = 32 bytes (an
