@@ -187,7 +187,7 @@ class Mc(McBase):
                 isinstance(self._materials[0], mcmaterial.AnisotropicMaterial) or \
                 opts.get('MC_METHOD', 0) not in (0, 1):
             return 0
-        return int(self.pool_slots)
+        return 64                    # (the census of the loop reads two slots per lane)
 
     def _loop_name(self) -> str:
         opts = self.resolved_options()
