@@ -215,22 +215,26 @@ McKernel(
 	off_words += 2*priv_len + win_len;
 	off_words = (off_words + 3u) & ~3u;
 #if XO_VOX_POOL
-	// per-warp packet pool (mcvox_pool_loop.cuh): XO_VOX_POOL slots of 4 x float4 + 1 float,
-	// one state byte per slot, 32 bytes of gather indices
+	// per-warp packet pool (mcvox_pool_loop.cuh), field by field: XO_VOX_POOL slots of
+	// 4 x float4 (A, B, C, D), then the optical path length (float) - with a trace a fifth
+	// quad T instead -, where the rmax sphere can be reached the ray parameter of its exit
+	// (float), one state byte per slot, 32 bytes of gather indices
 	const u32 pool_warps = blockDim.x >> 5, pool_warp = threadIdx.x >> 5;
-	float4 *P_A = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + pool_warp*XO_VOX_POOL;
-	float4 *P_B = P_A + pool_warps*XO_VOX_POOL;
-	float4 *P_C = P_B + pool_warps*XO_VOX_POOL;
-	float4 *P_D = P_C + pool_warps*XO_VOX_POOL;
+	unsigned char *pool_next = reinterpret_cast<unsigned char *>(reinterpret_cast<u32 *>(xo_smem) + off_words);
+	float4 *P_A = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
+	float4 *P_B = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
+	float4 *P_C = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
+	float4 *P_D = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
 #if XO_TRACE
-	// (traced packets: a fifth quad per slot - optical path length, packet, events, flags)
-	float4 *P_T = P_D + pool_warps*XO_VOX_POOL;
-	unsigned char *P_ST = reinterpret_cast<unsigned char *>(P_T + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
+	float4 *P_T = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
 #else
-	float *P_E = reinterpret_cast<float *>(P_D + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
-	unsigned char *P_ST = reinterpret_cast<unsigned char *>(P_E + (pool_warps - pool_warp)*XO_VOX_POOL) + pool_warp*XO_VOX_POOL;
+	float *P_E = reinterpret_cast<float *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*4u;
 #endif
-	unsigned char *P_IDX = P_ST + (pool_warps - pool_warp)*XO_VOX_POOL + pool_warp*32u;
+#if XO_USE_RMAX
+	float *P_R = reinterpret_cast<float *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*4u;
+#endif
+	unsigned char *P_ST = pool_next + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL;
+	unsigned char *P_IDX = pool_next + pool_warp*32u;
 #else
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;

@@ -34,8 +34,13 @@
 // for full traces the clearance shortcut is off (one event per voxel crossing is the
 // product there): every flight walks.
 //
+// Where the rmax sphere around the source can be reached (XO_USE_RMAX) a slot also keeps the
+// ray parameter at which its flight leaves the sphere (a ray leaves a convex body once): the
+// first face beyond it is a BND event, the end-of-trip test of the reference follows every
+// interaction and interface.
+//
 // Host conditions (mcvox/mc.py): compact map, throughput mode, albedo weight /
-// albedo rejection, isotropic materials, rmax test compiled out.
+// albedo rejection, isotropic materials.
 {
 	// slot states: the class (INTERACT / WALK set-up / WALK / BOUNDARY) sits in bits 3-4
 	enum : u32 { PS_EMPTY = 0, PS_NEW = 1, PS_RAY = 2, PS_SCAT = 3, PS_FAR = 4, PS_DDA = 8, PS_RUN = 16, PS_BND = 24 };
@@ -59,6 +64,14 @@
 	const u32 vox_bxy = vox_bx + vox_by;
 	const u32 vox_mx = (1u << vox_bx) - 1u, vox_my = (1u << vox_by) - 1u;
 	(void)chunk; (void)nthreads; (void)refill; (void)rmax2; (void)src_pos; (void)int_buffer; (void)float_buffer;
+#if XO_USE_RMAX
+#define XO_POOL_RMAX_TEST() do { \
+		const float ex_ = pos.x - src_pos.x, ey_ = pos.y - src_pos.y, ez_ = pos.z - src_pos.z; \
+		if (ex_*ex_ + ey_*ey_ + ez_*ez_ > rmax2) { done = true; flags |= EV_ESCAPED; } \
+	} while (0)
+#else
+#define XO_POOL_RMAX_TEST() do { } while (0)
+#endif
 	u32 packet = 0, trace_count = 0, flags = 0;     // (trace builds: of the slot in hand)
 	(void)packet; (void)trace_count; (void)flags;
 	const u32 vbase_lo = (u32)reinterpret_cast<u64>(voxels8);
@@ -155,6 +168,9 @@
 			P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
 			float weight = 0.0f, t_s = 0.0f, opl = 0.0f;
 			(void)opl;
+#if XO_USE_RMAX
+			float t_rmax = 0.0f;
+#endif
 			if (act) {
 				st = P_ST[slot];
 				const float4 a = P_A[slot], b = P_B[slot];
@@ -236,6 +252,7 @@
 #endif
 					if (mat_here != mat) { mat = mat_here; XO_LOAD_MAT(mat); }
 					if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; }
+					XO_POOL_RMAX_TEST();
 					XO_POOL_TRACE_TRIP();
 					st = done ? PS_EMPTY : PS_RAY;
 				}
@@ -243,7 +260,17 @@
 					t_s = fminf((FastMath::lg2(rng.next_raw()) - 32.0f)*c_hot.step_k, XO_FLT_MAX);
 					// extent of the flight in voxels along its longest axis against the clearance
 					const float ext = t_s*fmaxf(fabsf(dir.x)*inv_sx, fmaxf(fabsf(dir.y)*inv_sy, fabsf(dir.z)*inv_sz));
-					st = (XO_POOL_CLEARANCE && ext < (float)dcur - 1.0f) ? PS_FAR : PS_DDA;
+					bool far = XO_POOL_CLEARANCE && ext < (float)dcur - 1.0f;
+#if XO_USE_RMAX
+					{   // parameter at which the ray leaves the rmax sphere around the source
+						const float ex = pos.x - src_pos.x, ey = pos.y - src_pos.y, ez = pos.z - src_pos.z;
+						const float b = ex*dir.x + ey*dir.y + ez*dir.z;
+						const float c = ex*ex + ey*ey + ez*ez - rmax2;
+						t_rmax = FastMath::sqrt(fmaxf(fmaf(b, b, -c), 0.0f)) - b;
+						far = far && t_s <= t_rmax;
+					}
+#endif
+					st = far ? PS_FAR : PS_DDA;
 				}
 				if ((u32)__popc(__ballot_sync(0xffffffffu, st == PS_FAR)) < XO_POOL_THR_I) break;
 			}
@@ -253,6 +280,9 @@
 				P_C[slot].w = __uint_as_float(vlo);
 				P_D[slot].w = __uint_as_float(mat | (dcur << 8));
 				XO_POOL_STORE_T();
+#if XO_USE_RMAX
+				P_R[slot] = t_rmax;
+#endif
 				P_ST[slot] = (unsigned char)st;
 			}
 		} else if (phase == PH_WALK) {
@@ -261,6 +291,9 @@
 			i32 last_d = 0;
 			float tmx = XO_INF, tmy = XO_INF, tmz = XO_INF, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
 			float t_s = 0.0f, t_evt = 0.0f;
+#if XO_USE_RMAX
+			const float t_rmax = act ? P_R[slot] : XO_INF;
+#endif
 #if XO_TRACE == XO_TRACE_ALL
 			// (every crossing is an event: the ray itself, the weight and the trace quad)
 			P3 pos = { 0.0f, 0.0f, 0.0f }, dir = { 0.0f, 0.0f, 1.0f };
@@ -345,7 +378,7 @@
 						const i32 d_a = px ? stx : (py ? sty : stz);
 						vlo += (u32)d_a;
 						const u32 cell_a = XO_VOXEL(vlo);
-						const u32 m_a = cell_a & 0xffu;
+						u32 m_a = cell_a & 0xffu;
 						// second crossing, speculative
 						const float tmin_b = fminf(tmx, fminf(tmy, tmz));
 						const bool ok_b = tmin_b < t_s;
@@ -356,8 +389,13 @@
 						const u32 vlo_b = vlo + (u32)d_b;
 						u32 cell_b = 0x100u | mat;
 						if (ok_b) cell_b = XO_VOXEL(vlo_b);
-						const u32 m_b = cell_b & 0xffu;
+						u32 m_b = cell_b & 0xffu;
 						dcur = cell_a >> 8;
+#if XO_USE_RMAX
+						// first face beyond rmax: handled as an event
+						if (tmin_a > t_rmax) m_a = ~0u;
+						if (tmin_b > t_rmax) m_b = ~0u;
+#endif
 #if XO_VOX_SAME_N
 						// Equal refractive indices everywhere: a face between two materials is no
 						// interface event, only the attenuation changes; the remaining optical depth
@@ -473,6 +511,7 @@
 					vlo -= (u32)d;
 				}
 				if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; }
+				XO_POOL_RMAX_TEST();
 				XO_POOL_TRACE_TRIP();
 				P_A[slot] = make_float4(pos.x, pos.y, pos.z, weight);
 				P_B[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
@@ -533,6 +572,7 @@
 #undef XO_POOL_STORE_T
 #undef XO_POOL_TRACE_TRIP
 #undef XO_POOL_OPL
+#undef XO_POOL_RMAX_TEST
 	// every lane drew from its stream: all states go back
 	rng_state_x[gid] = rng.state();
 }

@@ -177,12 +177,12 @@ class Mc(McBase):
 
     def _pool_slots(self, opts=None) -> int:
         """Slots per warp, or 0 where the pool loop does not apply: it covers the compact
-        map in throughput mode with albedo weight / rejection, isotropic materials and no
-        reachable rmax sphere (built-in trace included; a user-written trace keeps the
-        lane-resident loop)."""
+        map in throughput mode with albedo weight / rejection and isotropic materials
+        (start / end traces included; a full trace keeps the lane-resident loop unless
+        ``pool_full_trace``, a user-written trace always)."""
         opts = self.resolved_options() if opts is None else opts
         if not self.pool_slots or self.deterministic or not self._vox_packed() or \
-                self._user_trace() or self._rmax_needed() or \
+                self._user_trace() or \
                 (int(opts.get('MC_USE_TRACE', 0)) == 7 and not self.pool_full_trace) or \
                 isinstance(self._materials[0], mcmaterial.AnisotropicMaterial) or \
                 opts.get('MC_METHOD', 0) not in (0, 1):
@@ -200,7 +200,9 @@ class Mc(McBase):
         if slots:
             # 4 x float4 + 1 float (traced packets: a fifth float4) + 1 state byte per slot,
             # 32 index bytes per warp
-            per_slot = 64 + (16 if self._trace is not None else 4) + 1
+            # ... where the rmax sphere can be reached the ray parameter of its exit (float)
+            per_slot = 64 + (16 if self._trace is not None else 4) + \
+                (4 if self._rmax_needed() else 0) + 1
             return (block//32)*(slots*per_slot + 32) + 32
         return super()._queue_bytes(block)
 

@@ -692,7 +692,8 @@ def test_large_fluence_results_own_their_pinned_grid():
     ('mcvox_gauss_fluence', 'aw'), ('mcvox_isopoint_fluencerate', 'aw'),
     ('mcvox_isovoxel_fluence', 'aw'), ('mcvox_ufiber_fluence', 'aw'),
     ('mcvox_gk2_line_total', 'aw'), ('mcvox_ubeam_radial', 'aw'),
-    ('mcvox_gauss_fluence', 'ar'), ('mcvox_gk2_line_total', 'ar')])
+    ('mcvox_gauss_fluence', 'ar'), ('mcvox_gk2_line_total', 'ar'),
+    ('mcvox_gauss_fluence', 'aw:rmax'), ('mcvox_ubeam_radial', 'aw:rmax')])
 def test_both_mcvox_throughput_loops_against_the_oracle(name, method):
     """The packet-pool loop (mcvox_pool_loop.cuh, the default where it applies) and the
     lane-resident loop (mcvox_dda_loop.cuh, ``pool_slots = 0``) are both pinned against the
@@ -702,8 +703,13 @@ def test_both_mcvox_throughput_loops_against_the_oracle(name, method):
     K = 0x7FFFFF
     results = {}
     from pyxopto_b200.mcbase import mcoptions
+    method, _, rmax = method.partition(':')
     for slots in (64, 0):
         sim, geom, _ = build_sim(name, options=[getattr(mcoptions.McMethod, method)])
+        if rmax:
+            # an rmax sphere the packets do reach (termination by the end-of-trip test)
+            sim.rmax = 0.12e-3
+            assert sim._rmax_needed()
         sim.pool_slots = slots
         sim.run(n, download=False)
         assert sim.run_report['loop'] == ('packet pool' if slots else 'lane-resident rays')

@@ -32,7 +32,7 @@ def test_c3_compiles_the_packet_pool():
 
 @pytest.mark.parametrize('change, loop', [
     (lambda sim: setattr(sim, 'pool_slots', 0), 'lane-resident rays'),
-    (lambda sim: setattr(sim, 'rmax', 50e-6), 'lane-resident rays'),       # sphere inside the box
+    (lambda sim: setattr(sim, 'rmax', 50e-6), 'packet pool'),       # sphere inside the box
     (lambda sim: sim._options.append(mcoptions.McMethod.mbl), 'reference-structured'),
     (lambda sim: sim._options.append(mcoptions.McDeterministic.on), 'reference-structured'),
     (lambda sim: sim._options.append(mcoptions.McMethod.ar), 'packet pool'),
@@ -46,6 +46,10 @@ def test_loop_selection(change, loop):
     assert (_define(src, 'XO_VOX_POOL') == '64') == (loop == 'packet pool')
     if loop != 'packet pool':
         assert sim._queue_bytes(256) == 40*256 + 16
+    else:
+        # (+ one float per slot where the rmax sphere can be reached)
+        rmax = int(_define(src, 'XO_USE_RMAX'))
+        assert sim._queue_bytes(256) == 8*(64*(69 + 4*rmax) + 32) + 32
 
 
 def test_traces_and_the_pool():
