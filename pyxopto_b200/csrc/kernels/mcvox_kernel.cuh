@@ -328,13 +328,13 @@ McKernel(
 						vx = qx; vy = qy; vz = qz; mat = next_mat;
 						bf = EV_REFRACTION;
 					} else {
-						float cc = cos_critical(n1, n2);
+						float cc = xo::cos_critical(n1, n2);
 						float cos1 = (float)nx*dir.x + (float)ny*dir.y + (float)nz*dir.z;
 						P3 fn = { (float)nx, (float)ny, (float)nz };
 						bf = EV_REFLECTION;
 						bool refracted = false;
 						if (cos1 > cc) {
-							float R = reflectance(n1, n2, cos1, cc);
+							float R = xo::reflectance(n1, n2, cos1, cc);
 							if (R < rng.next()) {
 								dir = refract3(dir, fn, n1, n2);
 								vx = qx; vy = qy; vz = qz; mat = next_mat;

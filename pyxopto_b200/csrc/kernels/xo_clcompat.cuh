@@ -334,6 +334,8 @@ struct McSimState {
 	mc_int_t layer_index;
 	mc_cnt_t photon_index;
 	mc_fp_t optical_pathlength;
+	mc_point3_t voxel_index;            // (voxel geometry, xo_clcompat_mcvox.cuh)
+	mc_int_t voxel_material_index;
 };
 struct McSim {
 	McSimState state;
@@ -341,6 +343,8 @@ struct McSim {
 	const void *pf, *source, *det_top, *det_bottom, *det_specular, *layers, *fluence;
 	const void *surf_top, *surf_bottom;
 	const void *trace;
+	const void *voxel_cfg, *materials;      // (voxel geometry)
+	const mc_int_t *voxels;
 	mc_fp_t *float_buffer;
 	mc_int_t *integer_buffer;
 	mc_uint_t event_flags;

@@ -16,6 +16,9 @@ __device__ __forceinline__ void clc_sim_init(McSim &sim, Rng *rng) {
 	sim.surf_top = nullptr; sim.surf_bottom = nullptr;
 	sim.trace = nullptr; sim.float_buffer = nullptr; sim.integer_buffer = nullptr;
 	sim.event_flags = 0u;
+	sim.voxel_cfg = nullptr; sim.materials = nullptr; sim.voxels = nullptr;
+	sim.state.voxel_index.x = 0; sim.state.voxel_index.y = 0; sim.state.voxel_index.z = 0;
+	sim.state.voxel_material_index = 0;
 	sim.fp_lut_array = nullptr;
 	sim.accumulator_buffer = nullptr;
 	sim.state.position = P3{ 0.0f, 0.0f, 0.0f };
@@ -51,6 +54,28 @@ __device__ __forceinline__ void SrcUser::launch(Rng &rng, const Ctx &ctx, Launch
 	L.dir = sim.state.direction;
 	L.weight = sim.state.weight;
 	L.layer = sim.state.layer_index;
+	L.spec_dir = sim.spec_dir;
+	L.spec_weight = sim.spec_weight;
+}
+#endif
+
+#if XO_USER_SOURCE
+template <class Ctx>
+__device__ __forceinline__ void SrcUser::launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const {
+	McSim sim;
+	clc_sim_init(sim, &rng);
+	sim.source = &s;
+	sim.voxel_cfg = &ctx.cfg;
+	sim.materials = ctx.materials;
+	sim.voxels = ctx.voxels;
+	sim.fp_lut_array = ctx.lut;
+	sim.state.position = prev_pos;
+	sim.spec_weight = -1.0f;            // (no specular deposit unless the fragment asks for one)
+	mcsim_launch(&sim);
+	L.pos = sim.state.position;
+	L.dir = sim.state.direction;
+	L.weight = sim.state.weight;
+	L.layer = 0;
 	L.spec_dir = sim.spec_dir;
 	L.spec_weight = sim.spec_weight;
 }

@@ -84,6 +84,10 @@ struct SrcUser {
 	__device__ __forceinline__ P3 origin() const { return s.position; }
 	template <class Ctx>
 	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, Launch &L) const;
+	// voxel geometry: the facade starts at the position of the previous packet of the
+	// work-item, like the reference's simulator state
+	template <class Ctx>
+	__device__ __forceinline__ void launch(Rng &rng, const Ctx &ctx, const P3 &prev_pos, Launch &L) const;
 };
 #endif
 

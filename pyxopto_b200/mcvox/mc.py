@@ -65,8 +65,17 @@ class Mc(McBase):
         return self._materials[material_index]
 
     # -- packing -----------------------------------------------------------------
+    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular',
+                         'XoFluence')
+    clcompat_geometry_header = 'xo_clcompat_mcvox.cuh'
+
     def _plugin_objects(self):
-        return {'XoPf': self._materials[0].pf}
+        dets = self._detectors
+        return {'XoPf': self._materials[0].pf, 'XoSource': self._source,
+                'XoDetTop': dets.top if dets is not None else None,
+                'XoDetBottom': dets.bottom if dets is not None else None,
+                'XoDetSpecular': dets.specular if dets is not None else None,
+                'XoFluence': self._fluence}
 
     def _scattering_pfs(self):
         return [item.pf for item in list(self._materials)]

@@ -606,6 +606,21 @@ def mcml_user_trace_squared(mc, **kw):
                  trace=tr, rnginit=818181, **kw), dict(rmax=20e-3)
 
 
+def mcvox_user_plugins(mc, **kw):
+    """Voxel geometry with a user-written source (starts inside the box, uses the voxel /
+    material accessors), a user-written top detector and a user-written phase function."""
+    import user_plugins as up
+    A = mc.mcgeometry.Axis
+    vox = _vox_grid(mc)
+    flu = mc.mcfluence.Fluence(vox.xaxis, vox.yaxis, vox.zaxis, mode='deposition')
+    det = mc.mcdetector.Detectors(
+        top=up.user_radial(mc, A(0, 0.4e-3, 40)), bottom=mc.mcdetector.Total())
+    src = up.user_vox_beam(mc, (20e-6, -10e-6, 60e-6), (0.3, 0.1, 1.0))
+    sim = mc.Mc(vox, _vox_materials(mc, lambda g: up.user_hg(mc, g)), src,
+                detectors=det, fluence=flu, rnginit=565656, **kw)
+    return _fill_skin_vessel(sim), dict(rmax=25e-3)
+
+
 def mcml_user_surface_reflector(mc, **kw):
     """A top surface layout written by a user (the arithmetic of LambertianReflector):
     equals ``mcml_surface_lambert_top`` bit for bit."""
@@ -647,15 +662,17 @@ USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_us
               'mcml_user_fluence': mcml_user_fluence,
               'mcml_user_surface_reflector': mcml_user_surface_reflector,
               'mcml_user_surface_window': mcml_user_surface_window,
+              'mcvox_user_plugins': mcvox_user_plugins,
               'mcml_user_trace': mcml_user_trace,
               'mcml_user_trace_squared': mcml_user_trace_squared}
 USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None,
                    'mcml_user_fluence': None,
                    'mcml_user_surface_reflector': 'mcml_surface_lambert_top',
                    'mcml_user_surface_window': None,
+                   'mcvox_user_plugins': None,
                    'mcml_user_trace': 'mcml_lut_iso_radialpl_trace',
                    'mcml_user_trace_squared': None}
-USER_GEOMETRY = {name: 'mcml' for name in USER_CASES}
+USER_GEOMETRY = {name: name.split('_')[0] for name in USER_CASES}
 USER_RUN = {name: (3000, 16) for name in USER_CASES}
 USER_RUN['mcml_user_trace'] = (800, 16)
 USER_RUN['mcml_user_trace_squared'] = (800, 16)

@@ -59,7 +59,8 @@ def test_user_structs_pack_like_the_reference(name):
     sim._pack(run_size(name)[0])
     g = golden(name)
     mine = packed_bytes(sim)
-    for key in ('layers', 'source', 'detectors') + \
+    medium = ('materials', 'voxels') if name.startswith('mcvox') else ('layers',)
+    for key in medium + ('source', 'detectors') + \
             (('fluence',) if 'packed_fluence' in g.files else ()) + \
             (('surface_layouts',) if 'packed_surface_layouts' in g.files else ()) + \
             (('trace',) if 'packed_trace' in g.files else ()):
@@ -80,6 +81,11 @@ def test_user_fragments_compile_for_sm100a(name, deterministic):
     if name == 'mcml_user_fluence':
         assert 'mcsim_fluence_deposit_at' in src and 'typedef xo::FluUser XoFluence;' in src
         assert 'typedef xo::PfHg XoPf;' in src
+        return
+    if name.startswith('mcvox'):
+        assert '#include "xo_clcompat_mcvox.cuh"' in src and 'mcsim_voxel_material' in src
+        assert 'typedef xo::SrcUser XoSource;' in src and 'typedef xo::DetUserTop XoDetTop;' in src
+        assert 'typedef xo::PfUser XoPf;' in src and 'typedef xo::DetTotal XoDetBottom;' in src
         return
     if name.startswith('mcml_user_trace'):
         assert 'mcsim_trace_event' in src and '#define XO_USER_TRACE 1' in src

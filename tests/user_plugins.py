@@ -622,3 +622,78 @@ inline void mcsim_trace_complete(McSim *mcsim, mc_uint_t event_count){
 
 def user_trace(mc, squared=False, **kw):
     return _user_trace_class(mc, bool(squared))(**kw)
+
+
+# ---- voxel geometry: a user-written source (mcvox/mcsource) -----------------------------------
+@functools.lru_cache(maxsize=None)
+def _user_vox_beam_class(mc):
+    """Collimated beam that starts INSIDE the voxel box at ``position`` along ``direction``
+    with a weight that depends on the refractive index of the voxel it starts in (so the
+    fragment uses the voxel / material accessors of the voxelised simulator)."""
+    cltypes = _cltypes(mc)
+
+    class UserVoxBeam(mc.mcsource.Source):
+        @staticmethod
+        def cl_type(mc_):
+            T = mc_.types
+            class ClUserVoxBeam(cltypes.Structure):
+                _fields_ = [('position', T.mc_point3f_t), ('direction', T.mc_point3f_t)]
+            return ClUserVoxBeam
+
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McSource{ mc_point3f_t position; ' \
+                   'mc_point3f_t direction; };\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_source(__mc_source_mem const McSource *src){
+	dbg_print("user-written beam inside the voxel box:");
+	dbg_print_point3f(INDENT "position:", &src->position);
+};
+
+inline void mcsim_launch(McSim *mcsim){
+	__mc_source_mem const McSource *src = mcsim_source(mcsim);
+	mc_point3_t voxel;
+	mc_fp_t n_here, n_out;
+
+	mcsim_set_position(mcsim, &src->position);
+	mcsim_set_direction(mcsim, &src->direction);
+	voxel.x = mc_int(mc_fdiv(src->position.x - mcsim_top_left_x(mcsim), mcsim_voxel_size_x(mcsim)));
+	voxel.y = mc_int(mc_fdiv(src->position.y - mcsim_top_left_y(mcsim), mcsim_voxel_size_y(mcsim)));
+	voxel.z = mc_int(mc_fdiv(src->position.z - mcsim_top_left_z(mcsim), mcsim_voxel_size_z(mcsim)));
+	voxel.x = mc_clip(voxel.x, 0, mcsim_shape_x(mcsim) - 1);
+	voxel.y = mc_clip(voxel.y, 0, mcsim_shape_y(mcsim) - 1);
+	voxel.z = mc_clip(voxel.z, 0, mcsim_shape_z(mcsim) - 1);
+	mcsim_set_voxel_index(mcsim, &voxel);
+	/* as if the beam had entered from the surrounding medium at normal incidence */
+	n_here = mc_material_n(mcsim_voxel_material(mcsim, &voxel));
+	n_out = mc_material_n(mcsim_surrounding_material(mcsim));
+	mcsim_set_weight(mcsim, FP_1 - mc_fdiv((n_out - n_here)*(n_out - n_here),
+		(n_out + n_here)*(n_out + n_here)));
+};
+'''
+
+        def __init__(self, position, direction):
+            super().__init__()
+            self.position = np.asarray(position, dtype=np.float64)
+            d = np.asarray(direction, dtype=np.float64)
+            self.direction = d/np.linalg.norm(d)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            target.position.fromarray(self.position)
+            target.direction.fromarray(self.direction)
+            return target, None, None
+
+        def todict(self):
+            return {'type': 'UserVoxBeam', 'position': self.position.tolist(),
+                    'direction': self.direction.tolist()}
+
+    return UserVoxBeam
+
+
+def user_vox_beam(mc, position, direction):
+    return _user_vox_beam_class(mc)(position, direction)
