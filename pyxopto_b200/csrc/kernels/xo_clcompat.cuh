@@ -341,6 +341,7 @@ struct McSim {
 	McSimState state;
 	xo::Rng *rng;
 	const void *pf, *source, *det_top, *det_bottom, *det_specular, *layers, *fluence;
+	const void *det_outer;                  // (cylindrical geometry)
 	const void *surf_top, *surf_bottom;
 	const void *trace;
 	const void *voxel_cfg, *materials;      // (voxel geometry)
@@ -406,6 +407,7 @@ struct McSim {
 #define MC_REFLECTED 1
 #define MC_REFRACTED 2
 #define mcsim_top_detector(psim) (static_cast<const McTopDetector *>((psim)->det_top))
+#define mcsim_outer_detector(psim) (static_cast<const McOuterDetector *>((psim)->det_outer))
 #define mcsim_bottom_detector(psim) (static_cast<const McBottomDetector *>((psim)->det_bottom))
 #define mcsim_specular_detector(psim) (static_cast<const McSpecularDetector *>((psim)->det_specular))
 #define mcsim_fluence(psim) (static_cast<const McFluence *>((psim)->fluence))

@@ -12,6 +12,7 @@ __device__ __forceinline__ void clc_sim_init(McSim &sim, Rng *rng) {
 	sim.rng = rng;
 	sim.pf = nullptr; sim.source = nullptr;
 	sim.det_top = nullptr; sim.det_bottom = nullptr; sim.det_specular = nullptr;
+	sim.det_outer = nullptr;
 	sim.layers = nullptr; sim.num_layers = 0; sim.fluence = nullptr;
 	sim.surf_top = nullptr; sim.surf_bottom = nullptr;
 	sim.trace = nullptr; sim.float_buffer = nullptr; sim.integer_buffer = nullptr;
@@ -169,6 +170,11 @@ __device__ __forceinline__ void DetUserTop::deposit(const Accu &acc, const P3 &p
 #if XO_USER_DET_BOTTOM
 __device__ __forceinline__ void DetUserBottom::deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
 	XO_CLC_DETECTOR_BODY(det_bottom, mcsim_bottom_detector_deposit)
+}
+#endif
+#if XO_USER_DET_OUTER
+__device__ __forceinline__ void DetUserOuter::deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const {
+	XO_CLC_DETECTOR_BODY(det_outer, mcsim_outer_detector_deposit)
 }
 #endif
 #if XO_USER_DET_SPECULAR

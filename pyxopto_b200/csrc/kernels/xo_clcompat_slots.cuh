@@ -23,6 +23,9 @@
 #ifndef XO_USER_DET_BOTTOM
 #define XO_USER_DET_BOTTOM 0
 #endif
+#ifndef XO_USER_DET_OUTER
+#define XO_USER_DET_OUTER 0
+#endif
 #ifndef XO_USER_DET_SPECULAR
 #define XO_USER_DET_SPECULAR 0
 #endif
@@ -104,6 +107,14 @@ struct DetUserTop {
 #if XO_USER_DET_BOTTOM
 struct DetUserBottom {
 	McBottomDetector d;
+	static constexpr bool active = true;
+	static constexpr bool needs_opl = false;
+	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;
+};
+#endif
+#if XO_USER_DET_OUTER
+struct DetUserOuter {               // cylindrical geometry: mcsim_outer_detector_deposit
+	McOuterDetector d;
 	static constexpr bool active = true;
 	static constexpr bool needs_opl = false;
 	__device__ __forceinline__ void deposit(const Accu &acc, const P3 &pos, const P3 &dir, float w, float opl) const;

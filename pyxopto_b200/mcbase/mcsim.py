@@ -288,6 +288,7 @@ class McBase(CuWorker):
         'XoDetTop': ('xo::DetUserTop', 'XO_USER_DET_TOP'),
         'XoDetBottom': ('xo::DetUserBottom', 'XO_USER_DET_BOTTOM'),
         'XoDetSpecular': ('xo::DetUserSpecular', 'XO_USER_DET_SPECULAR'),
+        'XoDetOuter': ('xo::DetUserOuter', 'XO_USER_DET_OUTER'),
         'XoFluence': ('xo::FluUser', 'XO_USER_FLUENCE'),
         'XoTrace': ('xo::TraceUser', 'XO_USER_TRACE'),
         'XoSurfTop': ('xo::SurfUserTop', 'XO_USER_SURF_TOP'),

@@ -52,8 +52,15 @@ class Mc(McBase):
         return self._layers.layer_index(r)
 
     # -- packing -----------------------------------------------------------------
+    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetOuter', 'XoDetSpecular', 'XoFluence')
+    clcompat_geometry_header = 'xo_clcompat_mccyl.cuh'
+
     def _plugin_objects(self):
-        return {'XoPf': self._layers[1].pf}
+        dets = self._detectors
+        return {'XoPf': self._layers[1].pf, 'XoSource': self._source,
+                'XoDetOuter': dets.outer if dets is not None else None,
+                'XoDetSpecular': dets.specular if dets is not None else None,
+                'XoFluence': self._fluence}
 
     def _scattering_pfs(self):
         return [item.pf for item in list(self._layers)[1:]]

@@ -621,6 +621,18 @@ def mcvox_user_plugins(mc, **kw):
     return _fill_skin_vessel(sim), dict(rmax=25e-3)
 
 
+def mccyl_user_plugins(mc, **kw):
+    """Cylindrical geometry with a user-written source (starts in the second cylinder), a
+    user-written outer detector and a user-written phase function."""
+    import user_plugins as up
+    Axis = mc.mcdetector.Axis
+    det = mc.mcdetector.Detectors(outer=up.user_radial(mc, Axis(4e-3, 6e-3, 20), cosmin=0.0),
+                                  specular=mc.mcdetector.Total())
+    src = up.user_cyl_beam(mc, (1.2e-3, 0.4e-3, 0.1e-3), (0.6, 0.2, 0.3))
+    return mc.Mc(_cyl_layers(mc, up.user_hg(mc, 0.8)), src, det,
+                 rnginit=575757, **kw), dict(rmax=25e-3)
+
+
 def mcml_user_surface_reflector(mc, **kw):
     """A top surface layout written by a user (the arithmetic of LambertianReflector):
     equals ``mcml_surface_lambert_top`` bit for bit."""
@@ -663,6 +675,7 @@ USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_us
               'mcml_user_surface_reflector': mcml_user_surface_reflector,
               'mcml_user_surface_window': mcml_user_surface_window,
               'mcvox_user_plugins': mcvox_user_plugins,
+              'mccyl_user_plugins': mccyl_user_plugins,
               'mcml_user_trace': mcml_user_trace,
               'mcml_user_trace_squared': mcml_user_trace_squared}
 USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None,
@@ -670,6 +683,7 @@ USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_c
                    'mcml_user_surface_reflector': 'mcml_surface_lambert_top',
                    'mcml_user_surface_window': None,
                    'mcvox_user_plugins': None,
+                   'mccyl_user_plugins': None,
                    'mcml_user_trace': 'mcml_lut_iso_radialpl_trace',
                    'mcml_user_trace_squared': None}
 USER_GEOMETRY = {name: name.split('_')[0] for name in USER_CASES}

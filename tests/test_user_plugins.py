@@ -82,6 +82,11 @@ def test_user_fragments_compile_for_sm100a(name, deterministic):
         assert 'mcsim_fluence_deposit_at' in src and 'typedef xo::FluUser XoFluence;' in src
         assert 'typedef xo::PfHg XoPf;' in src
         return
+    if name.startswith('mccyl'):
+        assert '#include "xo_clcompat_mccyl.cuh"' in src and 'mc_layer_r_outer' in src
+        assert 'typedef xo::SrcUser XoSource;' in src and 'typedef xo::DetUserOuter XoDetOuter;' in src
+        assert 'typedef xo::PfUser XoPf;' in src
+        return
     if name.startswith('mcvox'):
         assert '#include "xo_clcompat_mcvox.cuh"' in src and 'mcsim_voxel_material' in src
         assert 'typedef xo::SrcUser XoSource;' in src and 'typedef xo::DetUserTop XoDetTop;' in src

@@ -697,3 +697,71 @@ inline void mcsim_launch(McSim *mcsim){
 
 def user_vox_beam(mc, position, direction):
     return _user_vox_beam_class(mc)(position, direction)
+
+
+# ---- cylindrical geometry: a user-written source (mccyl/mcsource) ------------------------------
+@functools.lru_cache(maxsize=None)
+def _user_cyl_beam_class(mc):
+    """Collimated beam that starts INSIDE the cylinder stack at ``position`` along
+    ``direction``; the fragment finds the layer of the start point with the layer accessors
+    of the cylindrical simulator."""
+    cltypes = _cltypes(mc)
+
+    class UserCylBeam(mc.mcsource.Source):
+        @staticmethod
+        def cl_type(mc_):
+            T = mc_.types
+            class ClUserCylBeam(cltypes.Structure):
+                _fields_ = [('position', T.mc_point3f_t), ('direction', T.mc_point3f_t)]
+            return ClUserCylBeam
+
+        @staticmethod
+        def cl_declaration(mc_):
+            return 'struct MC_STRUCT_ATTRIBUTES McSource{ mc_point3f_t position; ' \
+                   'mc_point3f_t direction; };\n'
+
+        @staticmethod
+        def cl_implementation(mc_):
+            return '''
+void dbg_print_source(__mc_source_mem const McSource *src){
+	dbg_print("user-written beam inside the cylinders:");
+	dbg_print_point3f(INDENT "position:", &src->position);
+};
+
+inline void mcsim_launch(McSim *mcsim){
+	__mc_source_mem const McSource *src = mcsim_source(mcsim);
+	mc_fp_t r = mc_sqrt(src->position.x*src->position.x + src->position.y*src->position.y);
+	mc_int_t index = 1, i;
+
+	for (i = 1; i < mcsim_layer_count(mcsim); ++i)
+		if (r < mc_layer_r_outer(mcsim_layer(mcsim, i)) && r >= mc_layer_r_inner(mcsim_layer(mcsim, i)))
+			index = i;
+	mcsim_set_position(mcsim, &src->position);
+	mcsim_set_direction(mcsim, &src->direction);
+	mcsim_set_weight(mcsim, FP_1);
+	mcsim_set_current_layer_index(mcsim, index);
+};
+'''
+
+        def __init__(self, position, direction):
+            super().__init__()
+            self.position = np.asarray(position, dtype=np.float64)
+            d = np.asarray(direction, dtype=np.float64)
+            self.direction = d/np.linalg.norm(d)
+
+        def cl_pack(self, mc_, target=None):
+            if target is None:
+                target = self.cl_type(mc_)()
+            target.position.fromarray(self.position)
+            target.direction.fromarray(self.direction)
+            return target, None, None
+
+        def todict(self):
+            return {'type': 'UserCylBeam', 'position': self.position.tolist(),
+                    'direction': self.direction.tolist()}
+
+    return UserCylBeam
+
+
+def user_cyl_beam(mc, position, direction):
+    return _user_cyl_beam_class(mc)(position, direction)
