@@ -6,8 +6,9 @@
  * /root/reference/xopto).  Floating-point expressions keep the reference's
  * operand order, so with -ffp-contract=off and math=XO_MATH_LIBM this file is
  * bit-identical to the reference kernel compiled by gcc behind clshim.h
- * (oracle/_ref, checked by tests/test_oracle_vs_ref.py in the build container
- * and pinned for the GPU box by tests/golden/).
+ * (oracle/_ref): its outputs on every case of tests/cases.py are committed as
+ * tests/golden/<case>.npz (tests/golden/make_golden.py, run in the container that holds
+ * the reference) and tests/test_oracle_golden.py holds this file to them bit for bit.
  */
 #include <math.h>
 #include <float.h>
