@@ -78,8 +78,44 @@ def compile_kernel(src: str, deterministic: bool, arch: str = TARGET_ARCH,
     return cubin, log, False
 
 
+class _LaneBuffers(dict):
+    """Named device buffers of a simulator.  A sweep runs consecutive configurations on two
+    *lanes* (mcsweep.Sweep): everything a launch writes or re-uploads - accumulators,
+    counters, MWC states, packed medium / plugin tables - exists once per lane, so the kernel
+    of configuration k + 1 may start while configuration k drains; the big read-only inputs
+    (voxel maps) are shared.  Code addresses buffers by their plain names; the lane of the
+    owner picks the instance."""
+    SHARED = ('voxel_data', 'voxel_packed')
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def _key(self, name):
+        lane = self._owner._lane
+        if lane and isinstance(name, str) and name not in self.SHARED:
+            return '{}#{}'.format(name, lane)
+        return name
+
+    def __getitem__(self, name):
+        return super().__getitem__(self._key(name))
+
+    def __setitem__(self, name, value):
+        super().__setitem__(self._key(name), value)
+
+    def __contains__(self, name):
+        return super().__contains__(self._key(name))
+
+    def get(self, name, default=None):
+        return super().get(self._key(name), default)
+
+    def pop(self, name, *default):
+        return super().pop(self._key(name), *default)
+
+
 class CuWorker:
     """Base class of the ``Mc`` simulators."""
+    _lane = 0                        # see _LaneBuffers
 
     def __init__(self, types=mctypes.McDataTypesSingle, cl_devices=None,
                  cl_build_options=None, cl_profiling: bool = False, rnginit=None):
@@ -88,8 +124,9 @@ class CuWorker:
         self._cl_build_options = list(cl_build_options or [])
         self._cl_profiling = bool(cl_profiling)
         self._ctx = None
-        self._stream = None
-        self._cl_buffers = {}
+        self._lane_streams = {}          # lane -> (stream, (event, event))
+        self._lane_seeds = {}            # lane -> (seeds_x, seeds_a) of the lanes above 0
+        self._cl_buffers = _LaneBuffers(self)
         self._np_buffers = {}
         self._allocators = {
             'accumulator': BufferAllocator(types.np_accu),
@@ -99,9 +136,9 @@ class CuWorker:
         self._float_lut = LutManager(types.np_float)
         self._rng = clrng.Random()
         self._rng_seeds_x, self._rng_seeds_a = self._rng.seeds(MAX_SEEDS, xinit=rnginit)
-        self._seeds_on_device = False
+        self._rnginit = rnginit
+        self._seeds_on_device = set()    # lanes whose MWC states are on the device
         self._modules = {}
-        self._events = None
         self._pinned_downloads = {}
 
     # -- device ---------------------------------------------------------------
@@ -124,9 +161,19 @@ class CuWorker:
     def _ensure_device(self):
         if self._ctx is None:
             self._ctx = abi.Context(self._device_ordinal())
-            self._stream = abi.Stream(self._ctx)
-            self._events = (abi.Event(self._ctx), abi.Event(self._ctx))
         return self._ctx
+
+    def _lane_state(self):
+        st = self._lane_streams.get(self._lane)
+        if st is None:
+            self._ensure_device()
+            st = (abi.Stream(self._ctx), (abi.Event(self._ctx), abi.Event(self._ctx)))
+            self._lane_streams[self._lane] = st
+        return st
+
+    # the stream / timing events of the current lane
+    _stream = property(lambda self: self._lane_state()[0])
+    _events = property(lambda self: self._lane_state()[1])
 
     cl_context = property(lambda self: self._ensure_device())
     cl_queue = property(lambda self: (self._ensure_device(), self._stream)[1])
@@ -224,10 +271,23 @@ class CuWorker:
         return buf
 
     def _upload_seeds(self, copy: bool = False):
-        if not self._seeds_on_device or copy:
-            self.cl_r_buffer('rng_seeds_x', self._rng_seeds_x)
-            self.cl_r_buffer('rng_seeds_a', self._rng_seeds_a)
-            self._seeds_on_device = True
+        lane = self._lane
+        if lane not in self._seeds_on_device or copy:
+            if lane == 0:
+                x, a = self._rng_seeds_x, self._rng_seeds_a
+            else:
+                # a lane above 0 draws from its own seed set (hashed initializer, as the
+                # ranks of a sharded run do): two lanes never share a stream
+                if lane not in self._lane_seeds:
+                    from .. import parallel
+                    base = self._rnginit if self._rnginit is not None else \
+                        int(self._rng_seeds_x[0])
+                    self._lane_seeds[lane] = self._rng.seeds(
+                        MAX_SEEDS, xinit=parallel.seed_for_rank(base, lane << 20))
+                x, a = self._lane_seeds[lane]
+            self.cl_r_buffer('rng_seeds_x', x)
+            self.cl_r_buffer('rng_seeds_a', a)
+            self._seeds_on_device.add(lane)
 
     PINNED_MIN_BYTES = 1 << 20
 

@@ -68,6 +68,7 @@ class Sweep:
         self.rank, self.world = int(rank), int(world)
         self.report = {}
         self._mine = None           # assignment of the last run (gather() reuses it)
+        self.overlap = True         # two lanes in throughput mode (see run)
 
     def pilot_costs(self, configs, nphotons: int = 2000, apply=None) -> np.ndarray:
         """Relative cost of every configuration: loop trips of a short pilot run.
@@ -125,15 +126,35 @@ class Sweep:
         self._mine = (len(configs), None if costs is None else np.array(costs, copy=True))
         nphotons = int(nphotons)
         sim._ensure_device()
+        # Two lanes in throughput mode: consecutive configurations run on two streams with
+        # their own accumulators, counters, MWC states and packed tables (mcworker.
+        # _LaneBuffers), so the CTAs of configuration k + 1 move onto the SMs that
+        # configuration k has already left - a kernel of persistent threads ends with a
+        # tail in which the last long-lived packets keep a few warps busy (about 1 ms of a
+        # 3.5 ms kernel at 1e7 packets).  Deterministic mode keeps one lane: every
+        # configuration continues the MWC states of the one before, as in the reference.
+        lanes = 2 if (self.overlap and not sim.deterministic) else 1
         t0 = time.perf_counter()
+        try:
+            return self._run_lanes(sim, mine, configs, nphotons, apply, wgsize, maxthreads,
+                                   lanes, t0)
+        finally:
+            sim._lane = 0
+            sim._accumulator_slot = 0
+
+    def _run_lanes(self, sim, mine, configs, nphotons, apply, wgsize, maxthreads, lanes, t0):
+        from .cu import abi
         rows = counters = None
-        pending = None                  # (row index, event) of the copy in flight
+        pending = None
         slots = [None, None]
         events = [abi.Event(sim.cl_context), abi.Event(sim.cl_context)]
         for k, index in enumerate(mine):
             apply(sim, configs[int(index)])
             slot = k & 1
-            sim._accumulator_slot = slot          # device double buffer
+            if lanes == 2:
+                sim._lane = slot
+            else:
+                sim._accumulator_slot = slot      # device double buffer
             sim.run(nphotons, wgsize=wgsize, maxthreads=maxthreads, download=False,
                     synchronize=False)
             size = int(sim.cl_rw_accumulator_allocator.size)
@@ -151,7 +172,10 @@ class Sweep:
             pending = slot
         if pending is not None:
             events[pending].synchronize()
-        sim._stream.synchronize()
+        for lane in range(lanes):
+            sim._lane = lane
+            sim._stream.synchronize()
+        sim._lane = 0
         sim._accumulator_slot = 0
         iterations = counters[:, 2:4].copy().view(np.uint64).reshape(-1) \
             if rows is not None else np.zeros(0, np.uint64)

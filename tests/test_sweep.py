@@ -95,3 +95,42 @@ def test_pilot_costs_and_balanced_deal():
     got = [p.run(configs, n, maxthreads=1024, wgsize=64, costs=costs)[0] for p in parts]
     assert sorted(np.concatenate(got).tolist()) == list(range(len(configs)))
     assert got[0].tolist() == mcsweep.balanced_partition(costs, 2, 0).tolist()
+
+
+@pytest.mark.gpu
+def test_two_lane_sweep_in_throughput_mode():
+    """Throughput mode runs consecutive configurations on two lanes (own streams,
+    accumulators, counters, MWC states and packed tables): every row must be the result of
+    ITS configuration - statistically equal to a stand-alone run and to the single-lane
+    sweep - and the two lanes must draw from different seed sets."""
+    import benchcfg
+    from pyxopto_b200.mcml import mc
+    n = 400000
+    configs = _configs()
+
+    def fast_sim():
+        return benchcfg.c5_slab(mc)
+
+    sim = fast_sim()
+    sweep = mcsweep.Sweep(sim)
+    assert sweep.overlap
+    idx, rows = sweep.run(configs, n)
+    assert sim._lane == 0 and len(sim._lane_streams) == 2
+    assert not np.array_equal(sim._lane_seeds[1][0][:64], sim.rng_seeds_x[:64])
+    single = mcsweep.Sweep(fast_sim())
+    single.overlap = False
+    _, rows_1 = single.run(configs, n)
+    assert len(single.sim._lane_streams) == 1
+    K = 0x7FFFFF
+    alone = fast_sim()
+    for i, cfg in enumerate(configs):
+        mcsweep._apply_layer_updates(alone, cfg)
+        alone.run(n, download=False)
+        ref = alone.download_raw()[0]
+        for got in (rows[i], rows_1[i]):
+            a, b = got.sum()/K/n, ref.sum()/K/n
+            sigma = np.sqrt(2*max(b, 1e-6)/n)
+            assert abs(a - b) <= 4.5*sigma, (i, a, b)
+            assert int(got.sum()) != int(ref.sum())      # (not the same packets)
+    assert sweep.report['iterations'].shape == (len(configs),)
+    assert (sweep.report['iterations'] > 0).all()
