@@ -200,7 +200,10 @@ McKernel(
 	float *P_R = reinterpret_cast<float *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*4u;
 #endif
 	unsigned char *P_ST = pool_next + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL;
-	unsigned char *P_IDX = pool_next + pool_warp*32u;
+	unsigned char *P_IDX = pool_next + pool_warp*32u; pool_next += pool_warps*32u;
+	// (XO_POOL_QUEUES: five rings of 64 slot numbers per warp)
+	unsigned char *P_Q = pool_next + pool_warp*320u;
+	(void)P_IDX; (void)P_Q;
 #else
 	float4 *q_a = reinterpret_cast<float4 *>(reinterpret_cast<u32 *>(xo_smem) + off_words) + (threadIdx.x & ~31u)*2u;
 	float4 *q_b = q_a + 32;

@@ -8,10 +8,12 @@
 // every phase - interaction, ray set-up, voxel walk, interface - runs with the lanes
 // that happen to be in that state: 22 / 5 / 12 / 1.3 of 32 on the 201^3 skin model
 // (profiles/r02s_*c3*).  Here a warp owns XO_VOX_POOL (64) packet slots in shared
-// memory; every round it takes a census of the slot states (one REDUX), picks the phase
-// with the most candidates, gathers up to 32 slots of that class by rank, loads exactly
-// the fields the phase needs, runs the phase with (nearly) full lanes - several passes
-// while enough lanes stay in the class - and stores the packets back:
+// memory; every round it picks the phase most slots wait for, takes up to 32 slots of that
+// class, loads exactly the fields the phase needs, runs the phase with (nearly) full lanes
+// - several passes while enough lanes stay in the class - and stores the packets back.
+// Which slots wait for what is kept in one ring of slot numbers per class with
+// warp-uniform heads and counts (XO_POOL_QUEUES, default), or found by a census of the
+// slot states (class counts in the bytes of one word, one REDUX) and a gather by rank:
 //
 //   INTERACT  slots NEW / RAY / SCAT / FAR: [voxel of the end point of a flight that
 //             skipped the walk] deposit, scattering, lottery, then the next free path
@@ -46,7 +48,7 @@
 	enum : u32 { PS_EMPTY = 0, PS_NEW = 1, PS_RAY = 2, PS_SCAT = 3, PS_FAR = 4, PS_DDA = 8, PS_RUN = 16, PS_BND = 24 };
 	enum : u32 { PH_INTERACT = 0, PH_WALK = 1, PH_BOUNDARY = 2, PH_LAUNCH = 3 };
 #ifndef XO_POOL_THR_I
-#define XO_POOL_THR_I 16        // INTERACT repeats while this many lanes skip the walk again
+#define XO_POOL_THR_I 20        // INTERACT repeats while this many lanes skip the walk again
 #endif
 #ifndef XO_POOL_THR_W
 #define XO_POOL_THR_W 12        // WALK goes on while this many lanes still walk
@@ -56,6 +58,9 @@
 #endif
 #ifndef XO_POOL_BND
 #define XO_POOL_BND 16          // BND slots that trigger a BOUNDARY phase
+#endif
+#ifndef XO_POOL_QUEUES
+#define XO_POOL_QUEUES 1        // 1: rings of slot numbers per class; 0: census + gather by rank
 #endif
 	static_assert(XO_VOX_POOL == 64, "the census reads two slots per lane");
 	constexpr u32 S = XO_VOX_POOL;
@@ -110,10 +115,64 @@
 	P_ST[lane + 32u] = (unsigned char)PS_EMPTY;
 	P_A[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	P_A[lane + 32u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#if XO_POOL_QUEUES
+	// One ring of slot numbers per class (every slot is in exactly one ring: 64 entries
+	// each never overflow); heads and counts are warp-uniform registers.  A phase pops up
+	// to 32 slots from the ring(s) of its class and pushes every slot it held onto the ring
+	// of its new class (ballot + rank + one byte store per class) - instead of a census of
+	// all 64 slot states and a gather by rank every round.
+	unsigned char *const Q_I = P_Q, *const Q_D = P_Q + 64, *const Q_W = P_Q + 128,
+		*const Q_B = P_Q + 192, *const Q_E = P_Q + 256;
+	Q_E[lane] = (unsigned char)lane;
+	Q_E[lane + 32u] = (unsigned char)(lane + 32u);
+	u32 hI = 0, hD = 0, hW = 0, hB = 0, hE = 0;
+	u32 nI = 0, nD = 0, nW = 0, nB = 0, nE = S;
+#define XO_Q_PUSH(Q_, h_, n_, pred_) do { \
+		const bool p_ = (pred_); \
+		const u32 m_ = __ballot_sync(0xffffffffu, p_); \
+		if (p_) (Q_)[((h_) + (n_) + (u32)__popc(m_ & lanemask_lt)) & 63u] = (unsigned char)slot; \
+		(n_) += (u32)__popc(m_); \
+	} while (0)
+#define XO_Q_POP(Q_, h_, n_, first_, take_) do { \
+		if (lane >= (first_) && lane < (first_) + (take_)) slot = (Q_)[((h_) + lane - (first_)) & 63u]; \
+		(h_) = ((h_) + (take_)) & 63u; (n_) -= (take_); \
+	} while (0)
+#else
+#define XO_Q_PUSH(Q_, h_, n_, pred_) do { } while (0)
+#endif
 	__syncwarp();
 	bool dry = false;               // warp-uniform: the packet budget is exhausted
 
 	for (;;) {
+#if XO_POOL_QUEUES
+		u32 phase;
+		if (!dry && nE >= XO_POOL_LAUNCH) phase = PH_LAUNCH;
+		else if (nE == S) break;
+		else if (nB >= XO_POOL_BND || (nB >= nI && nB >= nD + nW)) phase = PH_BOUNDARY;
+		else phase = (nI >= nD + nW) ? PH_INTERACT : PH_WALK;
+		u32 slot = 0;
+		bool act;
+		if (phase == PH_INTERACT) {
+			const u32 n = nI < 32u ? nI : 32u;
+			act = lane < n;
+			XO_Q_POP(Q_I, hI, nI, 0u, n);
+		} else if (phase == PH_WALK) {
+			// (the slots that still need their walk set-up first)
+			const u32 nd = nD < 32u ? nD : 32u;
+			const u32 nw = nW < 32u - nd ? nW : 32u - nd;
+			act = lane < nd + nw;
+			XO_Q_POP(Q_D, hD, nD, 0u, nd);
+			XO_Q_POP(Q_W, hW, nW, nd, nw);
+		} else if (phase == PH_BOUNDARY) {
+			const u32 n = nB < 32u ? nB : 32u;
+			act = lane < n;
+			XO_Q_POP(Q_B, hB, nB, 0u, n);
+		} else {
+			const u32 n = nE < 32u ? nE : 32u;
+			act = lane < n;
+			XO_Q_POP(Q_E, hE, nE, 0u, n);
+		}
+#else
 		// ---- census of the slot states: class counts in the bytes of one word ------------
 		u32 nI, nD, nW, nB, nE;
 		const u32 s0 = P_ST[lane], s1 = P_ST[lane + 32u];
@@ -161,6 +220,7 @@
 			if (act) slot = P_IDX[lane];
 			__syncwarp();
 		}
+#endif
 
 		if (phase == PH_INTERACT) {
 			// ======== interaction + next free path (mcvox.template.c:925-981, 667-700) ========
@@ -285,6 +345,9 @@
 #endif
 				P_ST[slot] = (unsigned char)st;
 			}
+			XO_Q_PUSH(Q_I, hI, nI, act && st == PS_FAR);
+			XO_Q_PUSH(Q_D, hD, nD, act && st == PS_DDA);
+			XO_Q_PUSH(Q_E, hE, nE, act && st == PS_EMPTY);
 		} else if (phase == PH_WALK) {
 			// ======== walk set-up (DDA slots) and voxel walk =====================================
 			u32 st = PS_EMPTY, vlo = vbase_lo, mat = 0, dcur = 1, sg = 7u;
@@ -457,11 +520,16 @@
 #endif
 				P_ST[slot] = (unsigned char)st;
 			}
+			XO_Q_PUSH(Q_W, hW, nW, act && st == PS_RUN);
+			XO_Q_PUSH(Q_I, hI, nI, act && st == PS_SCAT);
+			XO_Q_PUSH(Q_B, hB, nB, act && st == PS_BND);
 #undef XO_TRACE_CROSSING
 		} else if (phase == PH_BOUNDARY) {
 			// ======== a face between materials of different refractive index, or the face of
 			// the grid (mcvox.template.c:275-388); the walk already moved the voxel address
 			// across the face, along `axis` =========================================================
+			bool survived = false;
+			(void)survived;
 			if (act) {
 				const float4 a = P_A[slot], b = P_B[slot];
 				P3 pos = { a.x, a.y, a.z }, dir = { b.x, b.y, b.z };
@@ -519,7 +587,10 @@
 				P_D[slot].w = __uint_as_float(mat | (1u << 8));   // on a face: clearance 1
 				XO_POOL_STORE_T();
 				P_ST[slot] = (unsigned char)(done ? PS_EMPTY : PS_RAY);
+				survived = !done;
 			}
+			XO_Q_PUSH(Q_I, hI, nI, act && survived);
+			XO_Q_PUSH(Q_E, hE, nE, act && !survived);
 		} else {
 			// ======== new packets into the EMPTY slots =============================================
 			const u32 want = (u32)__popc(__ballot_sync(0xffffffffu, act));
@@ -561,9 +632,16 @@
 				P_ST[slot] = (unsigned char)PS_NEW;
 				started = true;
 			}
+			// (slots taken off the ring of empty slots: launched, or back when the budget ran out)
+			XO_Q_PUSH(Q_I, hI, nI, act && lane < n_new);
+			XO_Q_PUSH(Q_E, hE, nE, act && lane >= n_new);
 		}
 		__syncwarp();
 	}
+#undef XO_Q_PUSH
+#if XO_POOL_QUEUES
+#undef XO_Q_POP
+#endif
 #undef XO_LOAD_MAT
 #undef XO_VOXEL
 #undef XO_PACK_VOXEL

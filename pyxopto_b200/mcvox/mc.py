@@ -9,6 +9,8 @@ on top of the CUDA kernel ``csrc/kernels/mcvox_kernel.cuh``.
 """
 import ctypes
 
+import os
+
 import numpy as np
 
 from ..cl import clinfo, clrng, cltypes            # noqa: F401
@@ -183,6 +185,9 @@ class Mc(McBase):
     # against 1.88 ms; more resident warps lose the same way, profiles/r02y_*).  The pool
     # records traces correctly (tests) and is kept for start / end traces.
     pool_full_trace = False
+    # rings of slot numbers per class (default) or a census of the slot states + a gather by
+    # rank every round (C3: 78.7 against 80.7 ms per 1e8 packets, profiles/r03r_*)
+    pool_queues = bool(int(os.environ.get('XOPTO_POOL_QUEUES', '1')))
 
     def _pool_slots(self, opts=None) -> int:
         """Slots per warp, or 0 where the pool loop does not apply: it covers the compact
@@ -212,12 +217,14 @@ class Mc(McBase):
             # ... where the rmax sphere can be reached the ray parameter of its exit (float)
             per_slot = 64 + (16 if self._trace is not None else 4) + \
                 (4 if self._rmax_needed() else 0) + 1
-            return (block//32)*(slots*per_slot + 32) + 32
+            # ... and five rings of 64 slot numbers per warp (XO_POOL_QUEUES)
+            return (block//32)*(slots*per_slot + 32 + 320) + 32
         return super()._queue_bytes(block)
 
     def _extra_defines(self, opts):
         aniso = isinstance(self._materials[0], mcmaterial.AnisotropicMaterial)
-        return ['#define XO_VOX_POOL {}'.format(self._pool_slots(opts))] + \
+        return ['#define XO_VOX_POOL {}'.format(self._pool_slots(opts)),
+                '#define XO_POOL_QUEUES {}'.format(int(bool(self.pool_queues)))] + \
             ['#define {} {}'.format(k, int(v)) for k, v in sorted(self.pool_tuning.items())] + \
             ['#define XO_VOX_PACKED {}'.format(int(self._vox_packed())),
                 '#define XO_ANISO {}'.format(int(aniso)),

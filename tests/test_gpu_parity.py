@@ -706,15 +706,19 @@ def test_both_mcvox_throughput_loops_against_the_oracle(name, method):
     results = {}
     from pyxopto_b200.mcbase import mcoptions
     method, _, rmax = method.partition(':')
-    for slots in (64, 0):
+    # 64: the pool with its rings of slot numbers (default), 'census': the pool with a census
+    # of the slot states and a gather by rank, 0: the lane-resident loop
+    for slots in (64, 'census', 0):
         sim, geom, _ = build_sim(name, options=[getattr(mcoptions.McMethod, method)])
         if rmax:
             # an rmax sphere the packets do reach (termination by the end-of-trip test)
             sim.rmax = 0.12e-3
             assert sim._rmax_needed()
-        sim.pool_slots = slots
+        sim.pool_slots = 64 if slots else 0
+        sim.pool_queues = slots != 'census'
         sim.run(n, download=False)
         assert sim.run_report['loop'] == ('packet pool' if slots else 'lane-resident rays')
+        assert ('#define XO_POOL_QUEUES 1' in sim._last_src) == (slots != 'census')
         results[slots] = sim.download_raw()[0]
     desc = xo_oracle.describe(sim, geom)
     ref = xo_oracle.run(desc, n, 64, sim.rng_seeds_x[:64], sim.rng_seeds_a[:64],
@@ -728,7 +732,7 @@ def test_both_mcvox_throughput_loops_against_the_oracle(name, method):
         assert not bad.any(), (what, np.flatnonzero(bad)[:5], a[bad][:5], b[bad][:5])
 
     rate = bool(sim.resolved_options().get('MC_FLUENCE_MODE_RATE'))
-    for slots, other in ((64, ref), (0, ref), (64, results[0])):
+    for slots, other in ((64, ref), ('census', ref), (0, ref), (64, results[0])):
         accu = results[slots]
         for det in sim.detectors or ():
             for a in sim.cl_rw_accumulator_allocator.allocations(det):

@@ -25,8 +25,9 @@ def test_c3_compiles_the_packet_pool():
     src = sim.kernel_source(block=1024)
     assert _define(src, 'XO_VOX_POOL') == '64'
     assert _define(src, 'XO_USE_RMAX') == '0'
-    # per warp: 64 slots of 17 words + 1 state byte, 32 bytes of gather indices
-    assert sim._queue_bytes(1024) == 32*(64*69 + 32) + 32
+    # per warp: 64 slots of 17 words + 1 state byte, 32 bytes of gather indices, five rings of
+    # 64 slot numbers
+    assert sim._queue_bytes(1024) == 32*(64*69 + 32 + 320) + 32
     assert sim._queue_bytes(1024) + sim._shared_layout(sim._medium_bytes())[0] < 227*1024
 
 
@@ -49,7 +50,7 @@ def test_loop_selection(change, loop):
     else:
         # (+ one float per slot where the rmax sphere can be reached)
         rmax = int(_define(src, 'XO_USE_RMAX'))
-        assert sim._queue_bytes(256) == 8*(64*(69 + 4*rmax) + 32) + 32
+        assert sim._queue_bytes(256) == 8*(64*(69 + 4*rmax) + 32 + 320) + 32
 
 
 def test_traces_and_the_pool():
@@ -62,7 +63,7 @@ def test_traces_and_the_pool():
     assert sim._loop_name() == 'packet pool'
     assert _define(sim.kernel_source(block=64), 'XO_VOX_POOL') == '64'
     # per warp: 64 slots of 5 quads + 1 state byte, 32 bytes of gather indices
-    assert sim._queue_bytes(64) == 2*(64*81 + 32) + 32
+    assert sim._queue_bytes(64) == 2*(64*81 + 32 + 320) + 32
     sim.pool_slots = 0
     assert sim._loop_name() == 'lane-resident rays' and sim._queue_bytes(64) == 40*64 + 16
 
