@@ -253,7 +253,8 @@
 					pos.y = fmaf(dir.y, t_s, pos.y);
 					pos.z = fmaf(dir.z, t_s, pos.z);
 					if (XO_POOL_OPL) opl = fmaf(c_hot.n, t_s, opl);
-					u32 mat_here = mat;
+					u32 cell_far = 0x100u | XO_VOX_SENTINEL;      // (no look-up: keeps mat, clearance 1 unused)
+					const bool was_far = (st == PS_FAR);
 					if (st == PS_FAR) {
 						// the flight skipped the walk: voxel of the interaction point from the
 						// position, loop trips of the reference = faces crossed on the way
@@ -268,11 +269,9 @@
 							abs(iy - ((i32)((idx0 >> vox_bx) & vox_my) - 2)) +
 							abs(iz - ((i32)(idx0 >> vox_bxy) - 2)));
 						vlo = XO_PACK_VOXEL(ix, iy, iz);
-						const u32 cell = XO_VOXEL(vlo);
-						dcur = cell >> 8;
-						// (a rounding of the end point across a face of the clearance box can
-						// land in another material: adopted after this interaction)
-						if ((cell & 0xffu) != XO_VOX_SENTINEL) mat_here = cell & 0xffu;
+						// (the cell is looked up here and read after the deposit and the
+						// scattering below: the L2 round trip overlaps them)
+						cell_far = XO_VOXEL(vlo);
 					}
 #if XO_METHOD == 1
 					if (rng.next() < c_hot.absorb) {
@@ -310,7 +309,13 @@
 #endif
 					}
 #endif
-					if (mat_here != mat) { mat = mat_here; XO_LOAD_MAT(mat); }
+					if (was_far) {
+						dcur = cell_far >> 8;
+						// (a rounding of the end point across a face of the clearance box can
+						// land in another material: adopted after this interaction)
+						const u32 mat_here = cell_far & 0xffu;
+						if (mat_here != XO_VOX_SENTINEL && mat_here != mat) { mat = mat_here; XO_LOAD_MAT(mat); }
+					}
 					if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; }
 					XO_POOL_RMAX_TEST();
 					XO_POOL_TRACE_TRIP();
