@@ -187,6 +187,15 @@ McKernel(
 	// (float), one state byte per slot, 32 bytes of gather indices
 	const u32 pool_warps = blockDim.x >> 5, pool_warp = threadIdx.x >> 5;
 	unsigned char *pool_next = reinterpret_cast<unsigned char *>(reinterpret_cast<u32 *>(xo_smem) + off_words);
+#ifndef XO_POOL_SOA
+#define XO_POOL_SOA 1
+#endif
+#define XO_POOL_FIELDS (16u + (XO_TRACE ? 4u : 1u) + (XO_USE_RMAX ? 1u : 0u))
+#if XO_POOL_SOA
+	// one array of XO_VOX_POOL floats per component and warp (mcvox_pool_loop.cuh)
+	float *P_F = reinterpret_cast<float *>(pool_next) + pool_warp*(XO_POOL_FIELDS*XO_VOX_POOL);
+	pool_next += pool_warps*XO_POOL_FIELDS*XO_VOX_POOL*4u;
+#else
 	float4 *P_A = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
 	float4 *P_B = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
 	float4 *P_C = reinterpret_cast<float4 *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*16u;
@@ -198,6 +207,7 @@ McKernel(
 #endif
 #if XO_USE_RMAX
 	float *P_R = reinterpret_cast<float *>(pool_next) + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL*4u;
+#endif
 #endif
 	unsigned char *P_ST = pool_next + pool_warp*XO_VOX_POOL; pool_next += pool_warps*XO_VOX_POOL;
 	unsigned char *P_IDX = pool_next + pool_warp*32u; pool_next += pool_warps*32u;

@@ -59,6 +59,9 @@
 #ifndef XO_POOL_BND
 #define XO_POOL_BND 16          // BND slots that trigger a BOUNDARY phase
 #endif
+#ifndef XO_POOL_SOA
+#define XO_POOL_SOA 1           // slot fields as one array per component (see below)
+#endif
 #ifndef XO_POOL_QUEUES
 #define XO_POOL_QUEUES 1        // 1: rings of slot numbers per class; 0: census + gather by rank
 #endif
@@ -86,12 +89,43 @@
 #define XO_PACK_VOXEL(ix_, iy_, iz_) (vbase_lo + 2u*((u32)((ix_) + 2) | ((u32)((iy_) + 2) << vox_bx) | ((u32)((iz_) + 2) << vox_bxy)))
 #define XO_LOAD_MAT(idx) do { const VoxFastMat &F_ = sh_fast[idx]; c_hot = F_.hot; c_pf = F_.pf.v; } while (0)
 #define XO_POOL_CLEARANCE (XO_TRACE != XO_TRACE_ALL)
+	// Slot fields.  XO_POOL_SOA (default): one array of 64 floats per component - a lane
+	// that holds slot s reads bank s mod 32 whatever the component, so the slots a phase
+	// gathered (any 32 of 64) conflict two-way at most.  As 64 x float4 per quad the same
+	// accesses are 128-bit wide and collide whenever two lanes of a quarter-warp hold slots
+	// that are congruent mod 8: measured 9.8e8 bank-conflict cycles per 2e7 packets, the L1 /
+	// shared-memory pipe 84 % busy and binding (profiles/r03s_*).
+#if XO_POOL_SOA
+#define XO_PF_A 0u
+#define XO_PF_B 4u
+#define XO_PF_C 8u
+#define XO_PF_D 12u
+#define XO_PF_T 16u
+#define XO_PF(f_) P_F[(f_)*S + slot]
+#define P4_LOAD(N_) make_float4(XO_PF(XO_PF_##N_), XO_PF(XO_PF_##N_ + 1u), XO_PF(XO_PF_##N_ + 2u), XO_PF(XO_PF_##N_ + 3u))
+#define P4_STORE(N_, x_, y_, z_, w_) do { XO_PF(XO_PF_##N_) = (x_); XO_PF(XO_PF_##N_ + 1u) = (y_); \
+		XO_PF(XO_PF_##N_ + 2u) = (z_); XO_PF(XO_PF_##N_ + 3u) = (w_); } while (0)
+#define P3_STORE(N_, x_, y_, z_) do { XO_PF(XO_PF_##N_) = (x_); XO_PF(XO_PF_##N_ + 1u) = (y_); \
+		XO_PF(XO_PF_##N_ + 2u) = (z_); } while (0)
+#define PW_LOAD(N_) XO_PF(XO_PF_##N_ + 3u)
+#define PW_STORE(N_, v_) (XO_PF(XO_PF_##N_ + 3u) = (v_))
+#define P_E_REF XO_PF(16u)
+#define P_R_REF XO_PF(XO_POOL_FIELDS - 1u)
+#else
+#define P4_LOAD(N_) (P_##N_[slot])
+#define P4_STORE(N_, x_, y_, z_, w_) (P_##N_[slot] = make_float4(x_, y_, z_, w_))
+#define P3_STORE(N_, x_, y_, z_) do { P_##N_[slot].x = (x_); P_##N_[slot].y = (y_); P_##N_[slot].z = (z_); } while (0)
+#define PW_LOAD(N_) (P_##N_[slot].w)
+#define PW_STORE(N_, v_) (P_##N_[slot].w = (v_))
+#define P_E_REF P_E[slot]
+#define P_R_REF P_R[slot]
+#endif
 #if XO_TRACE
 	const XoTraceCfg &tcfg = *reinterpret_cast<const XoTraceCfg *>(&trace);
 	// trace quad of a slot: optical path length | packet | recorded events | pending flags
-#define XO_POOL_LOAD_T() do { const float4 t_ = P_T[slot]; opl = t_.x; packet = __float_as_uint(t_.y); \
+#define XO_POOL_LOAD_T() do { const float4 t_ = P4_LOAD(T); opl = t_.x; packet = __float_as_uint(t_.y); \
 		trace_count = __float_as_uint(t_.z); flags = __float_as_uint(t_.w); } while (0)
-#define XO_POOL_STORE_T() do { P_T[slot] = make_float4(opl, __uint_as_float(packet), \
+#define XO_POOL_STORE_T() do { P4_STORE(T, opl, __uint_as_float(packet), \
 		__uint_as_float(trace_count), __uint_as_float(flags)); } while (0)
 	// end of a loop trip of the reference (mcvox.template.c:983-1012): the event, the count
 #define XO_POOL_TRACE_TRIP() do { \
@@ -105,16 +139,15 @@
 	} while (0)
 #define XO_POOL_OPL (true)
 #else
-#define XO_POOL_LOAD_T() do { if (XO_NEEDS_OPL) opl = P_E[slot]; } while (0)
-#define XO_POOL_STORE_T() do { if (XO_NEEDS_OPL) P_E[slot] = opl; } while (0)
+#define XO_POOL_LOAD_T() do { if (XO_NEEDS_OPL) opl = P_E_REF; } while (0)
+#define XO_POOL_STORE_T() do { if (XO_NEEDS_OPL) P_E_REF = opl; } while (0)
 #define XO_POOL_TRACE_TRIP() do { } while (0)
 #define XO_POOL_OPL (XO_NEEDS_OPL)
 #endif
 	// slots of this warp
 	P_ST[lane] = (unsigned char)PS_EMPTY;
 	P_ST[lane + 32u] = (unsigned char)PS_EMPTY;
-	P_A[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	P_A[lane + 32u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	for (u32 slot = lane; slot < S; slot += 32u) P4_STORE(A, 0.0f, 0.0f, 0.0f, 0.0f);
 #if XO_POOL_QUEUES
 	// One ring of slot numbers per class (every slot is in exactly one ring: 64 entries
 	// each never overflow); heads and counts are warp-uniform registers.  A phase pops up
@@ -233,11 +266,11 @@
 #endif
 			if (act) {
 				st = P_ST[slot];
-				const float4 a = P_A[slot], b = P_B[slot];
+				const float4 a = P4_LOAD(A), b = P4_LOAD(B);
 				pos.x = a.x; pos.y = a.y; pos.z = a.z; weight = a.w;
 				dir.x = b.x; dir.y = b.y; dir.z = b.z; t_s = b.w;
-				vlo = __float_as_uint(P_C[slot].w);
-				const u32 misc = __float_as_uint(P_D[slot].w);
+				vlo = __float_as_uint(PW_LOAD(C));
+				const u32 misc = __float_as_uint(PW_LOAD(D));
 				mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu;
 				XO_POOL_LOAD_T();
 				if (st == PS_NEW) { const u32 cell = XO_VOXEL(vlo); mat = cell & 0xffu; dcur = cell >> 8; }
@@ -340,13 +373,13 @@
 				if ((u32)__popc(__ballot_sync(0xffffffffu, st == PS_FAR)) < XO_POOL_THR_I) break;
 			}
 			if (act) {
-				P_A[slot] = make_float4(pos.x, pos.y, pos.z, weight);
-				P_B[slot] = make_float4(dir.x, dir.y, dir.z, t_s);
-				P_C[slot].w = __uint_as_float(vlo);
-				P_D[slot].w = __uint_as_float(mat | (dcur << 8));
+				P4_STORE(A, pos.x, pos.y, pos.z, weight);
+				P4_STORE(B, dir.x, dir.y, dir.z, t_s);
+				PW_STORE(C, __uint_as_float(vlo));
+				PW_STORE(D, __uint_as_float(mat | (dcur << 8)));
 				XO_POOL_STORE_T();
 #if XO_USE_RMAX
-				P_R[slot] = t_rmax;
+				P_R_REF = t_rmax;
 #endif
 				P_ST[slot] = (unsigned char)st;
 			}
@@ -359,8 +392,9 @@
 			i32 last_d = 0;
 			float tmx = XO_INF, tmy = XO_INF, tmz = XO_INF, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
 			float t_s = 0.0f, t_evt = 0.0f;
+			bool was_dda = false;
 #if XO_USE_RMAX
-			const float t_rmax = act ? P_R[slot] : XO_INF;
+			const float t_rmax = act ? P_R_REF : XO_INF;
 #endif
 #if XO_TRACE == XO_TRACE_ALL
 			// (every crossing is an event: the ray itself, the weight and the trace quad)
@@ -369,20 +403,20 @@
 #endif
 			if (act) {
 				st = P_ST[slot];
-				const float4 b = P_B[slot];
-				t_s = b.w;
+				t_s = PW_LOAD(B);
 #if XO_TRACE == XO_TRACE_ALL
 				{
-					const float4 a_ = P_A[slot];
+					const float4 a_ = P4_LOAD(A), b_ = P4_LOAD(B);
 					pos.x = a_.x; pos.y = a_.y; pos.z = a_.z; weight = a_.w;
-					dir.x = b.x; dir.y = b.y; dir.z = b.z;
+					dir.x = b_.x; dir.y = b_.y; dir.z = b_.z;
 					XO_POOL_LOAD_T();
 				}
 #endif
+				was_dda = (st == PS_DDA);
 				if (st == PS_DDA) {
-					const float4 a = P_A[slot];
-					vlo = __float_as_uint(P_C[slot].w);
-					const u32 misc = __float_as_uint(P_D[slot].w);
+					const float4 a = P4_LOAD(A), b = P4_LOAD(B);
+					vlo = __float_as_uint(PW_LOAD(C));
+					const u32 misc = __float_as_uint(PW_LOAD(D));
 					mat = misc & 0xffu; dcur = (misc >> 8) & 0xffu;
 					const float rx = FastMath::rcp_approx(b.x), ry = FastMath::rcp_approx(b.y),
 						rz = FastMath::rcp_approx(b.z);
@@ -402,7 +436,7 @@
 					tdz = cfg.size.z*fabsf(rz);
 					st = PS_RUN;
 				} else {
-					const float4 c = P_C[slot], d = P_D[slot];
+					const float4 c = P4_LOAD(C), d = P4_LOAD(D);
 					tmx = c.x; tmy = c.y; tmz = c.z; vlo = __float_as_uint(c.w);
 					tdx = d.x; tdy = d.y; tdz = d.z;
 					const u32 misc = __float_as_uint(d.w);
@@ -516,10 +550,11 @@
 			}
 			if (act) {
 				const u32 axis = (last_d == stx) ? 0u : ((last_d == sty) ? 1u : 2u);
-				P_B[slot].w = (st == PS_BND) ? t_evt : t_s;
-				P_C[slot] = make_float4(tmx, tmy, tmz, __uint_as_float(vlo));
-				P_D[slot] = make_float4(tdx, tdy, tdz,
-					__uint_as_float(mat | (dcur << 8) | (axis << 16) | (sg << 18)));
+				PW_STORE(B, (st == PS_BND) ? t_evt : t_s);
+				P4_STORE(C, tmx, tmy, tmz, __uint_as_float(vlo));
+				// (the per-voxel increments of a ray never change: stored by its set-up only)
+				if (was_dda) P3_STORE(D, tdx, tdy, tdz);
+				PW_STORE(D, __uint_as_float(mat | (dcur << 8) | (axis << 16) | (sg << 18)));
 #if XO_TRACE == XO_TRACE_ALL
 				XO_POOL_STORE_T();
 #endif
@@ -536,12 +571,12 @@
 			bool survived = false;
 			(void)survived;
 			if (act) {
-				const float4 a = P_A[slot], b = P_B[slot];
+				const float4 a = P4_LOAD(A), b = P4_LOAD(B);
 				P3 pos = { a.x, a.y, a.z }, dir = { b.x, b.y, b.z };
 				float weight = a.w, opl = 0.0f;
 				const float t_evt = b.w;
-				u32 vlo = __float_as_uint(P_C[slot].w);
-				const u32 misc = __float_as_uint(P_D[slot].w);
+				u32 vlo = __float_as_uint(PW_LOAD(C));
+				const u32 misc = __float_as_uint(PW_LOAD(D));
 				u32 mat = misc & 0xffu;
 				const u32 axis = (misc >> 16) & 3u, sg = (misc >> 18) & 7u;
 				XO_POOL_LOAD_T();
@@ -586,10 +621,10 @@
 				if (weight <= 0.0f) { done = true; flags |= EV_ESCAPED; }
 				XO_POOL_RMAX_TEST();
 				XO_POOL_TRACE_TRIP();
-				P_A[slot] = make_float4(pos.x, pos.y, pos.z, weight);
-				P_B[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-				P_C[slot].w = __uint_as_float(vlo);
-				P_D[slot].w = __uint_as_float(mat | (1u << 8));   // on a face: clearance 1
+				P4_STORE(A, pos.x, pos.y, pos.z, weight);
+				P4_STORE(B, dir.x, dir.y, dir.z, 0.0f);
+				PW_STORE(C, __uint_as_float(vlo));
+				PW_STORE(D, __uint_as_float(mat | (1u << 8)));    // on a face: clearance 1
 				XO_POOL_STORE_T();
 				P_ST[slot] = (unsigned char)(done ? PS_EMPTY : PS_RAY);
 				survived = !done;
@@ -606,7 +641,7 @@
 				(num_packets - base < want ? num_packets - base : want) : 0u;
 			dry = n_new < want;
 			if (lane < n_new) {
-				const float4 prev = P_A[slot];      // (last position of the packet that died here)
+				const float4 prev = P4_LOAD(A);     // (last position of the packet that died here)
 				P3 prev_pos = { prev.x, prev.y, prev.z };
 				Launch L_;
 				source.launch(rng, ctx, prev_pos, L_);
@@ -618,10 +653,10 @@
 				ix = clipi(ix, 0, cfg.nx - 1);
 				iy = clipi(iy, 0, cfg.ny - 1);
 				iz = clipi(iz, 0, cfg.nz - 1);
-				P_A[slot] = make_float4(L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
-				P_B[slot] = make_float4(L_.dir.x, L_.dir.y, L_.dir.z, 0.0f);
-				P_C[slot].w = __uint_as_float(XO_PACK_VOXEL(ix, iy, iz));
-				P_D[slot].w = __uint_as_float(0u);
+				P4_STORE(A, L_.pos.x, L_.pos.y, L_.pos.z, L_.weight);
+				P4_STORE(B, L_.dir.x, L_.dir.y, L_.dir.z, 0.0f);
+				PW_STORE(C, __uint_as_float(XO_PACK_VOXEL(ix, iy, iz)));
+				PW_STORE(D, __uint_as_float(0u));
 				{
 					float opl = 0.0f;
 					(void)opl;
@@ -655,6 +690,13 @@
 #undef XO_POOL_STORE_T
 #undef XO_POOL_TRACE_TRIP
 #undef XO_POOL_OPL
+#undef P4_LOAD
+#undef P4_STORE
+#undef P3_STORE
+#undef PW_LOAD
+#undef PW_STORE
+#undef P_E_REF
+#undef P_R_REF
 #undef XO_POOL_RMAX_TEST
 	// every lane drew from its stream: all states go back
 	rng_state_x[gid] = rng.state();
