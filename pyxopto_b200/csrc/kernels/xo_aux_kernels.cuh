@@ -41,3 +41,13 @@ extern "C" __global__ void AccuScale(const xo::u64 *accu, double *out, xo::u64 n
 	for (xo::u64 i = (xo::u64)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride)
 		out[i] = __dmul_rn(__ull2double_rn(accu[i]), inv_k);
 }
+
+// AccuScaleAdd: grid[i] += (double)accu[i] * inv_k -- the same update for a result that
+// already holds data (fluence.py:349-376 with `out=`: raw += accumulators*(1/k)), for a
+// float64 grid that stays on the device between runs (Mc.lazy_fluence).  Multiply and add
+// are separate round-to-nearest operations (no FMA), as in NumPy.
+extern "C" __global__ void AccuScaleAdd(const xo::u64 *accu, double *grid, xo::u64 n, double inv_k) {
+	const xo::u64 stride = (xo::u64)gridDim.x*blockDim.x;
+	for (xo::u64 i = (xo::u64)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride)
+		grid[i] = __dadd_rn(grid[i], __dmul_rn(__ull2double_rn(accu[i]), inv_k));
+}

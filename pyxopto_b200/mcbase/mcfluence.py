@@ -26,6 +26,28 @@ class _FluenceBase(McObject):
     nphotons = property(lambda self: self._nphotons)
     mode = property(lambda self: self._mode)
 
+    # Device-resident accumulation (``Mc.lazy_fluence``): the simulator keeps the float64
+    # grid of this result on the device across ``run(out=...)`` calls and hands over a
+    # loader; the grid comes to the host when ``raw`` / ``data`` (anything that touches
+    # ``_data``) is read.
+    _pending = None
+    _store = None
+
+    def _materialize(self):
+        loader, self._pending = self._pending, None
+        if loader is not None:
+            loader(self)
+
+    def _get_store(self):
+        self._materialize()
+        return self._store
+
+    def _set_store(self, data):
+        self._materialize()
+        self._store = data
+
+    _data = property(_get_store, _set_store)
+
     def _set_k(self, k):
         self._k = max(1, min(int(k), int(2**31 - 1)))
 

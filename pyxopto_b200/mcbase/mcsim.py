@@ -720,15 +720,10 @@ class McBase(CuWorker):
         if self._fluence is not None:
             fluence_res = out_fluence if out_fluence is not None \
                 else type(self._fluence)(self._fluence)
-            scaled = self._download_scaled_fluence(fluence_res)
-            if scaled is not None:
-                owned = False
-                if isinstance(scaled, tuple):
-                    scaled, owned = scaled
-                fluence_res.update_scaled(scaled, nphotons, owned=owned)
+            if self.lazy_fluence and self._fluence_resident_add(fluence_res, nphotons):
+                pass
             else:
-                data = self._download_allocations(self._fluence, nphotons)
-                fluence_res.update_data(self, data, nphotons=nphotons)
+                self._collect_fluence(fluence_res, nphotons)
         if self._detectors is not None:
             detectors_res = out_detectors if out_detectors is not None \
                 else type(self._detectors)(self._detectors)
@@ -737,6 +732,79 @@ class McBase(CuWorker):
                 if data:
                     detectors_res.update_data(self, res, data, nphotons=nphotons)
         return trace_res, fluence_res, detectors_res
+
+    def _collect_fluence(self, fluence_res, nphotons):
+        """The reference's flow: the accumulators of this run reach the host and are
+        added to the result there (fluence.py:349-376)."""
+        scaled = self._download_scaled_fluence(fluence_res)
+        if scaled is not None:
+            owned = False
+            if isinstance(scaled, tuple):
+                scaled, owned = scaled
+            fluence_res.update_scaled(scaled, nphotons, owned=owned)
+        else:
+            data = self._download_allocations(self._fluence, nphotons)
+            fluence_res.update_data(self, data, nphotons=nphotons)
+
+    # -- device-resident fluence result (SURVEY 8f-4) -----------------------------------
+    # True: the float64 grid of a fluence result stays on the device across
+    # ``run(out=...)`` calls - every run adds ``accumulators*(1/k)`` to it there
+    # (AccuScaleAdd: the same two IEEE operations per cell as the host's
+    # ``raw += accumulators*(1/k)``, so the sums are bit-identical) - and comes to the
+    # host when the result's ``raw`` / ``data`` is read; False: the reference's flow, one
+    # conversion and one download of the whole grid per run.
+    lazy_fluence = False
+    _flu_resident = None             # (weakref to the result, grid cells)
+
+    def _fluence_resident_add(self, result, nphotons: int) -> bool:
+        from . import mcfluence, rngkernel
+        flu = self._fluence
+        if type(result).update_data is not mcfluence._FluenceBase.update_data or \
+                type(result)._data is not mcfluence._FluenceBase._data:
+            return False
+        allocs = self.cl_rw_accumulator_allocator.allocations(flu)
+        if len(allocs) != 1 or not allocs[0].download:
+            return False
+        a = allocs[0]
+        cells = int(a.size)
+        cur = self._flu_resident
+        owner = cur[0]() if cur is not None else None
+        if owner is not result or cur[1] != cells or result._pending is None:
+            if owner is not None:
+                owner._materialize()
+            self._flu_resident = None
+        grid_buf = self._buffer('flu_resident', cells*8)
+        add = True
+        if self._flu_resident is None:
+            have = result._store
+            if have is not None:
+                # a result that already holds host data: it continues on the device
+                if have.size != cells:
+                    return False
+                grid_buf.upload(self._stream, np.ascontiguousarray(have, dtype=np.float64))
+                result._store = None
+            else:
+                add = False
+        src = self._cl_buffers[self._rw_name('accumulator')]
+        mod = rngkernel._aux_module(self, True)
+        mod.kernel('AccuScaleAdd' if add else 'AccuScale').launch(
+            self._stream, 4*self._ctx.info['multiprocessor_count'], 512,
+            [(src, a.offset*8), grid_buf, np.uint64(cells), np.float64(1.0/result.k)])
+        result._nphotons = result._nphotons + nphotons if add else nphotons
+        self._flu_resident = (weakref.ref(result), cells)
+        result._pending = self._fluence_loader(cells)
+        return True
+
+    def _fluence_loader(self, cells: int):
+        def load(result):
+            cur = self._flu_resident
+            if cur is None or cur[0]() is not result:
+                return
+            host, owned = self._pinned_result(cells)
+            self._cl_buffers['flu_resident'].download(self._stream, host)
+            result._store = (host if owned else np.array(host)).reshape(result.shape)
+            self._flu_resident = None
+        return load
 
     # grids of at least this many cells are converted to float64 on the device
     # (AccuScale): the host then only copies the page-locked result

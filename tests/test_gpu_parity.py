@@ -478,6 +478,42 @@ def test_sampling_volume_accumulates_on_the_device(config):
     assert sv_l.data.sum() > d_l.sum()
 
 
+@pytest.mark.parametrize('name', ['mcvox_gauss_fluence', 'mcml_hg_gauss_fluencerzt', 'c3_vox'])
+def test_fluence_result_accumulates_on_the_device(name):
+    """``Mc.lazy_fluence``: a fluence result fed by several ``run(out=...)`` calls keeps its
+    float64 grid on the device (AccuScaleAdd) and comes to the host when ``raw`` is read -
+    bit-identical to the reference flow (one download per run, ``raw += accumulators/k`` on
+    the host, fluence.py:349-376).  A result that already holds host data continues on the
+    device; two results alternate through one simulator."""
+    n = 20000
+    grids = []
+    for lazy in (True, False):
+        # (deterministic mode: both simulators run exactly the same packets)
+        sim = _det_sim(name)[0]
+        sim.lazy_fluence = lazy
+        out = None
+        for _ in range(3):
+            out = sim.run(n, out=out, maxthreads=2048, wgsize=64)
+            assert (out[1]._pending is not None) == lazy
+        flu = out[1]
+        assert flu.nphotons == 3*n
+        raw = np.array(flu.raw, copy=True)
+        assert flu._pending is None and sim._flu_resident is None
+        # the collected result (host data now) goes back to the device for two more runs
+        out = sim.run(n, out=out, maxthreads=2048, wgsize=64)
+        other = sim.run(n, maxthreads=2048, wgsize=64)          # a second, fresh result
+        assert (other[1]._pending is not None) == lazy and out[1]._pending is None
+        out = sim.run(n, out=out, maxthreads=2048, wgsize=64)
+        assert other[1]._pending is None
+        grids.append((raw, np.array(out[1].raw, copy=True), np.array(other[1].raw, copy=True),
+                      out[1].nphotons, other[1].nphotons))
+    (raw_l, five_l, one_l, n5_l, n1_l), (raw_e, five_e, one_e, n5_e, n1_e) = grids
+    assert raw_l.sum() > 0 and raw_l.shape == raw_e.shape
+    assert raw_l.tobytes() == raw_e.tobytes()
+    assert five_l.tobytes() == five_e.tobytes() and one_l.tobytes() == one_e.tobytes()
+    assert (n5_l, n1_l) == (n5_e, n1_e) == (5*n, n)
+
+
 # ---------------------------------------------------------------------------
 # user-written plugins: OpenCL-C fragments compiled through xo_clcompat*.cuh
 def _raw_run(name, n, threads=256, block=64, deterministic=True):

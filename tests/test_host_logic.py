@@ -73,3 +73,35 @@ def test_pool_thresholds_reach_the_translation_unit():
     sim.pool_tuning = {'XO_POOL_THR_W': 10}
     sim._pack(1000)
     assert _define(sim.kernel_source(block=1024), 'XO_POOL_THR_W') == '10'
+
+
+def test_fluence_result_materializes_a_pending_device_grid_on_access():
+    """``Mc.lazy_fluence`` hook of the result objects: whatever touches ``_data`` (``raw``,
+    ``data``, the setters, the copy constructor, ``update``) first runs the pending loader."""
+    from pyxopto_b200.mcbase import mcfluence
+    from pyxopto_b200.mcbase.mcutil.axis import Axis
+    calls = []
+
+    def loader(f):
+        calls.append(f)
+        f._store = np.full(f.shape, 2.0)
+
+    flu = mcfluence.Fluence(Axis(0, 1, 2), Axis(0, 1, 3), Axis(0, 1, 4))
+    assert flu.raw is None and flu._pending is None
+    flu._pending = loader
+    assert flu.raw.shape == (4, 3, 2) and calls == [flu] and flu._pending is None
+    assert flu.raw is flu.raw and len(calls) == 1
+    # a setter collects the pending grid before it overwrites it
+    flu._pending = loader
+    flu.raw = np.zeros(flu.shape)
+    assert len(calls) == 2 and float(flu.raw.sum()) == 0.0
+    # copies and updates see the collected data
+    flu._pending = loader
+    cp = mcfluence.Fluence(flu)
+    assert len(calls) == 3 and float(cp.raw.sum()) == 2.0*24 and cp._pending is None
+    flu._pending = loader
+    cp.update(flu)
+    assert len(calls) == 4 and float(cp.raw.sum()) == 4.0*24
+    rz = mcfluence.FluenceRz(Axis(0, 1, 5), Axis(0, 1, 6))
+    rz._pending = lambda f: setattr(f, '_store', np.ones(30))
+    assert rz.raw_zr.shape == (6, 5) and rz._pending is None
