@@ -316,7 +316,13 @@ def native_arm(config, args, env, cpu_baseline_wanted=True):
     # warm-up (also builds/loads the kernel)
     for _ in range(max(args.warmup, 1)):
         step_device()
-    step_e2e()
+    # (two passes, the first result still held while the second is produced - as in the
+    # timed loop below: large grids come back in page-locked buffers of a small pool that
+    # the results own, and the second 65 MB buffer of C3 is allocated here, not inside
+    # the timed region)
+    held = step_e2e()
+    held = step_e2e()
+    del held
     if finish is not None:
         finish()
     barrier()

@@ -21,8 +21,9 @@
 //     compiler scalarises it away.
 //
 // Nothing here is reference code: the names are the reference's API, the bodies
-// are this engine's.  Not covered (documented in DESIGN.md): double precision,
-// 64-bit counters, OpenCL vector swizzles / operators on float3, image and
+// are this engine's.  Double precision: with XO_DOUBLE the token `float` is
+// `double` for everything below (xo_math_double.cuh), so the same text serves both.
+// Not covered (documented in DESIGN.md): OpenCL vector swizzles / operators on float3, image and
 // work-group built-ins, `printf` debugging (dbg_print* expand to nothing).
 #pragma once
 #include "xo_core.cuh"

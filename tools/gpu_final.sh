@@ -2,7 +2,7 @@
 # round 2, final single-GPU evidence: parity suite, bench lines of every configuration, launch
 # list of the default bench command, full ncu captures of the final kernels
 mkdir -p gpurun_out
-T=${1:-r03e}
+T=${1:-r04b}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv,noheader
 timeout 1500 python -X faulthandler -m pytest tests -m gpu -q --timeout=240 --durations=5 > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -9 gpurun_out/${T}_pytest_gpu.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err; tail -2 gpurun_out/${T}_bench_default.err
@@ -22,6 +22,8 @@ for f in sorted(glob.glob('gpurun_out/%s_bench_*.json' % os.environ['T'])):
         print(f, 'ERR', e)
 P
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_bench_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_launches_bench_default.log 2>&1
-for c in "c3_vox 2e7" "c4_trace 1e6"; do
+for c in "c2_skin 2e7" "c3_vox 2e7" "c4_trace 1e6"; do
   timeout 600 tools/gpu_ncu.sh $c $T
 done
+timeout 300 python tools/lazy_fluence_probe.py c3_vox 2e7 5 2>&1 | tail -2 > gpurun_out/${T}_lazy_fluence_probe.txt
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -2 gpurun_out/${T}_smoke.log
