@@ -19,3 +19,7 @@ for _name in ('clinfo', 'clrng', 'cltypes', 'mcobject', 'mcoptions', 'mctypes', 
 for _name in ('axis', 'boundary', 'buffer', 'fiber', 'geometry', 'lut'):
     _sys.modules.setdefault(__name__ + '.mcutil.' + _name, getattr(mcutil, _name))
 del _name
+
+# xopto.mcvox.mcrun: batch runners (RunMinWeight* / RunMinPacketsTrace) of this geometry
+from ..mcbase import mcrun as _mcrun                        # noqa: E402
+mcrun = _mcrun.geometry_module(__name__, mc, ('top', 'bottom', 'specular'))
