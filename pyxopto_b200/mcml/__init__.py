@@ -21,3 +21,6 @@ del _name
 # xopto.mcml.mcrun: batch runners (RunMinWeight* / RunMinPacketsTrace) of this geometry
 from ..mcbase import mcrun as _mcrun                        # noqa: E402
 mcrun = _mcrun.geometry_module(__name__, mc, ('top', 'bottom', 'specular'))
+from . import mcrun_helper as _helper                        # noqa: E402
+mcrun.McRunHelper, mcrun.helper = _helper.McRunHelper, _helper
+_sys.modules.setdefault(__name__ + '.mcrun.helper', _helper)

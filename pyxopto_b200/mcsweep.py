@@ -228,3 +228,26 @@ def _apply_layer_updates(sim, cfg: dict):
         layer = sim.layers[int(layer_index)]
         for name, value in attrs.items():
             setattr(layer, name, value)
+
+
+def results_from_row(sim, row: np.ndarray, nphotons: int):
+    """``(None, fluence, detectors)`` result objects of one configuration from its row of
+    raw fixed-point accumulators - what ``Mc.run`` returns (``mcsim._collect_results``),
+    with the row in place of the per-plugin downloads.  Same conversion: ``raw =
+    accumulators*(1/k)`` in float64."""
+    accu_dtype = np.dtype(sim.types.np_accu)
+
+    def blocks(obj):
+        return {accu_dtype: [np.array(row[a.offset:a.offset + a.size], dtype=accu_dtype)
+                             for a in sim.cl_rw_accumulator_allocator.allocations(obj)]}
+    fluence_res = detectors_res = None
+    if sim.fluence is not None:
+        fluence_res = type(sim.fluence)(sim.fluence)
+        fluence_res.update_data(sim, blocks(sim.fluence), nphotons=int(nphotons))
+    if sim.detectors is not None:
+        detectors_res = type(sim.detectors)(sim.detectors)
+        for det, res in zip(sim.detectors, detectors_res):
+            data = blocks(det)
+            if data[accu_dtype]:
+                detectors_res.update_data(sim, res, data, nphotons=int(nphotons))
+    return None, fluence_res, detectors_res

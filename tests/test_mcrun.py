@@ -160,3 +160,102 @@ def test_packets_trace_runner_on_the_device():
     assert tr.data.shape[0] == tr.n.size == len(tr)
     assert np.all(tr.terminal['z'] <= 0.0)
     assert r.weight == pytest.approx(float(np.sum(tr.terminal['w'])))
+
+
+# ---------------------------------------------------------------------------
+# McRunHelper (xopto/mcml/mcrun/helper.py): run-script scaffold
+def _skin_helper(musr_values, **mc_kwargs):
+    from pyxopto_b200.mcml import mc
+    from pyxopto_b200.mcml.mcrun import McRunHelper
+
+    class Helper(McRunHelper):
+        sample = -1
+
+        def create_layers(self):
+            air = dict(d=float('inf'), mua=0.0, mus=0.0, n=1.0, pf=mc.mcpf.Hg(0.0))
+            return mc.mclayer.Layers([
+                mc.mclayer.Layer(**air),
+                mc.mclayer.Layer(d=2e-3, mua=1e2, mus=100e2, n=1.33, pf=mc.mcpf.Hg(0.8)),
+                mc.mclayer.Layer(**air)])
+
+        def create_detectors(self):
+            A = mc.mcdetector.Axis
+            return mc.mcdetector.Detectors(top=mc.mcdetector.Radial(A(0.0, 2e-3, 50)),
+                                           bottom=mc.mcdetector.Total())
+
+        def create_fluence(self):
+            A = mc.mcfluence.Axis
+            # (square: FluenceRz.data of the reference broadcasts (nr, nz)*(1, nr),
+            #  fluencerz.py:343-347 - mirrored, so nr == nz here)
+            return mc.mcfluence.FluenceRz(A(0.0, 1e-3, 30), A(0.0, 2e-3, 30))
+
+        def update_layers(self):
+            self.sample += 1
+            self.mc_obj.layers[1].mus = musr_values[self.sample]/(1.0 - 0.8)
+    return Helper(**mc_kwargs)
+
+
+def test_helper_cli_and_hooks():
+    from pyxopto_b200.mcml.mcrun import McRunHelper
+    from pyxopto_b200.mcml.mcrun.helper import McRunHelper as same
+    assert same is McRunHelper
+    opts = McRunHelper.cli_input(n=7, argv=['-f', '3', '-p', '2e6', '-v', '-d', 'B200'])
+    assert opts['first'] == 3 and opts['n'] == 7 and opts['packets'] == 2000000
+    assert opts['verbose'] is True and opts['device'] == 'B200' and opts['mc_dir'] == 'mc'
+    h = _skin_helper([10e2, 20e2])
+    cfg = h.collect_mc_config()
+    assert set(cfg) == {'source', 'surface', 'layers', 'detectors', 'fluence', 'trace',
+                        'rmax', 'run_report'}
+    assert cfg['surface'] is None and cfg['trace'] is None and cfg['fluence']['type'] == 'FluenceRz'
+    h.update()
+    assert h.sample == 0 and h.mc_obj.layers[1].mus == pytest.approx(10e2/0.2)
+    assert h.collect_detectors(None) == {'reflectance': None, 'transmittance': None,
+                                         'specular': None}
+
+
+def test_results_from_an_accumulator_row():
+    """One row of raw accumulators becomes the result objects ``Mc.run`` returns: the
+    blocks of the pack order, scaled by 1/k in float64."""
+    from pyxopto_b200 import mcsweep
+    h = _skin_helper([10e2])
+    sim = h.mc_obj
+    sim._pack(1000)
+    size = sim.cl_rw_accumulator_allocator.size
+    row = (np.arange(size, dtype=np.uint64)*np.uint64(977)) % np.uint64(10007)
+    trace, flu, det = mcsweep.results_from_row(sim, row, 1000)
+    assert trace is None and det.top.nphotons == flu.nphotons == 1000
+    a_top = sim.cl_rw_accumulator_allocator.allocations(sim.detectors.top)[0]
+    a_flu = sim.cl_rw_accumulator_allocator.allocations(sim.fluence)[0]
+    k = sim.types.mc_accu_k
+    assert np.array_equal(det.top.raw, row[a_top.offset:a_top.offset + 50]*(1.0/k))
+    assert flu.raw.shape == sim.fluence.shape
+    assert np.array_equal(flu.raw.ravel(), row[a_flu.offset:a_flu.offset + 900]*(1.0/flu.k))
+    assert type(det.specular).__name__ == 'DetectorDefault'
+    assert det.top.reflectance.shape == (50,)
+
+
+@pytest.mark.gpu
+def test_helper_batch_streams_through_the_sweep_driver():
+    """Deterministic mode: ``run_batch`` through the sweep driver equals the reference's
+    loop of ``run_one`` calls sample by sample (both continue the MWC states from one
+    sample to the next), and the recorded configuration is the sample's."""
+    from pyxopto_b200.mcbase import mcoptions
+    musr = [5e2, 10e2, 20e2, 40e2, 15e2]
+    kw = dict(maxthreads=1024, wgsize=64)
+    batches = []
+    for streamed in (True, False):
+        h = _skin_helper(musr, options=[mcoptions.McDeterministic.on], rnginit=97531)
+        h.streamed = streamed
+        batches.append(h.run_batch(len(musr), 5000, first=100, **kw))
+        assert (h._sweep is not None) == streamed
+    for i, (a, b) in enumerate(zip(*batches)):
+        assert a['index'] == b['index'] == 100 + i and a['num_packets'] == 5000
+        assert a['mc']['layers'] == b['mc']['layers']
+        assert a['mc']['layers']['layers'][1]['mus'] == pytest.approx(musr[i]/0.2)
+        for key in ('reflectance', 'transmittance'):
+            assert a['detectors'][key].sum() > 0
+            assert np.array_equal(a['detectors'][key], b['detectors'][key]), (i, key)
+        assert a['detectors']['specular'] is None
+        assert np.array_equal(a['fluence']['data'], b['fluence']['data'])
+    r = [d['detectors']['reflectance'].sum() for d in batches[0]]
+    assert r[3] > r[0]                      # more scattering, more diffuse reflectance
