@@ -323,8 +323,8 @@ class McBase(CuWorker):
             # (the kernel headers bind XoTrace themselves: no typedef from the bindings)
             if 'XoTrace' not in self.user_plugin_slots:
                 raise NotImplementedError(
-                    'A user-written trace ({}) is compiled in the layered geometry '
-                    'only.'.format(type(self._trace).__name__))
+                    'This simulator has no slot for a user-written trace '
+                    '({}).'.format(type(self._trace).__name__))
             out.append(('XoTrace', self._trace))
         return out
 

@@ -52,7 +52,8 @@ class Mc(McBase):
         return self._layers.layer_index(r)
 
     # -- packing -----------------------------------------------------------------
-    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetOuter', 'XoDetSpecular', 'XoFluence')
+    user_plugin_slots = ('XoPf', 'XoSource', 'XoDetOuter', 'XoDetSpecular', 'XoFluence',
+                         'XoTrace')
     clcompat_geometry_header = 'xo_clcompat_mccyl.cuh'
 
     def _plugin_objects(self):

@@ -68,7 +68,7 @@ class Mc(McBase):
 
     # -- packing -----------------------------------------------------------------
     user_plugin_slots = ('XoPf', 'XoSource', 'XoDetTop', 'XoDetBottom', 'XoDetSpecular',
-                         'XoFluence')
+                         'XoFluence', 'XoTrace')
     clcompat_geometry_header = 'xo_clcompat_mcvox.cuh'
 
     def _plugin_objects(self):

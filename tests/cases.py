@@ -606,6 +606,24 @@ def mcml_user_trace_squared(mc, **kw):
                  trace=tr, rnginit=818181, **kw), dict(rmax=20e-3)
 
 
+def _with_user_trace(native_case, **trace_kw):
+    """``native_case`` with its Trace swapped for the user-written restatement of the
+    built-in event record (tests/user_plugins.py): equal to it bit for bit."""
+    def make(mc, **kw):
+        import user_plugins as up
+        sim, attrs = native_case(mc, **kw)
+        old = sim.trace
+        sim._trace = up.user_trace(mc, maxlen=old.maxlen, options=old.options, plon=old.plon,
+                                   **trace_kw)
+        return sim, attrs
+    make.__doc__ = _with_user_trace.__doc__
+    return make
+
+
+mcvox_user_trace = _with_user_trace(mcvox_line_mhg_trace)
+mccyl_user_trace = _with_user_trace(mccyl_gk_ubeam_fiz_trace)
+
+
 def mcvox_user_plugins(mc, **kw):
     """Voxel geometry with a user-written source (starts inside the box, uses the voxel /
     material accessors), a user-written top detector and a user-written phase function."""
@@ -677,7 +695,8 @@ USER_CASES = {'mcml_user_plugins': mcml_user_plugins, 'mcml_user_cubic': mcml_us
               'mcvox_user_plugins': mcvox_user_plugins,
               'mccyl_user_plugins': mccyl_user_plugins,
               'mcml_user_trace': mcml_user_trace,
-              'mcml_user_trace_squared': mcml_user_trace_squared}
+              'mcml_user_trace_squared': mcml_user_trace_squared,
+              'mcvox_user_trace': mcvox_user_trace, 'mccyl_user_trace': mccyl_user_trace}
 USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_cubic': None,
                    'mcml_user_fluence': None,
                    'mcml_user_surface_reflector': 'mcml_surface_lambert_top',
@@ -685,11 +704,15 @@ USER_EQUIVALENT = {'mcml_user_plugins': 'mcml_user_plugins_native', 'mcml_user_c
                    'mcvox_user_plugins': None,
                    'mccyl_user_plugins': None,
                    'mcml_user_trace': 'mcml_lut_iso_radialpl_trace',
-                   'mcml_user_trace_squared': None}
+                   'mcml_user_trace_squared': None,
+                   'mcvox_user_trace': 'mcvox_line_mhg_trace',
+                   'mccyl_user_trace': 'mccyl_gk_ubeam_fiz_trace'}
 USER_GEOMETRY = {name: name.split('_')[0] for name in USER_CASES}
 USER_RUN = {name: (3000, 16) for name in USER_CASES}
 USER_RUN['mcml_user_trace'] = (800, 16)
 USER_RUN['mcml_user_trace_squared'] = (800, 16)
+USER_RUN['mcvox_user_trace'] = (600, 16)
+USER_RUN['mccyl_user_trace'] = (600, 16)
 
 
 # ---------------------------------------------------------------------------

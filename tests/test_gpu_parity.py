@@ -527,7 +527,9 @@ def _raw_run(name, n, threads=256, block=64, deterministic=True):
 
 @pytest.mark.parametrize('user, native', [('mcml_user_plugins', 'mcml_user_plugins_native'),
                                           ('mcml_user_surface_reflector', 'mcml_surface_lambert_top'),
-                                          ('mcml_user_trace', 'mcml_lut_iso_radialpl_trace')])
+                                          ('mcml_user_trace', 'mcml_lut_iso_radialpl_trace'),
+                                          ('mcvox_user_trace', 'mcvox_line_mhg_trace'),
+                                          ('mccyl_user_trace', 'mccyl_gk_ubeam_fiz_trace')])
 def test_user_fragments_equal_builtins_bit_exact(user, native):
     """A user-written phase function, source and detector (tests/user_plugins.py)
     that restate Hg / Line / Radial - and a user-written surface layout that restates

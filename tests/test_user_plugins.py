@@ -30,17 +30,18 @@ def test_reference_runs_a_user_surface_layout_like_the_builtin():
     assert gu['packed_surface_layouts'].tobytes() == gn['packed_surface_layouts'].tobytes()
 
 
-def test_reference_runs_a_user_trace_like_the_builtin():
+@pytest.mark.parametrize('name', ['mcml_user_trace', 'mcvox_user_trace', 'mccyl_user_trace'])
+def test_reference_runs_a_user_trace_like_the_builtin(name):
     """Golden vectors of the reference kernel: the user-written trace == Trace, event rows
-    and counts included."""
-    gu, gn = golden('mcml_user_trace'), golden('mcml_lut_iso_radialpl_trace')
+    and counts included - in every geometry."""
+    gu, gn = golden(name), golden(cases.USER_EQUIVALENT[name])
     for key in ('accu', 'ints', 'floats', 'rng_x_after'):
         assert np.array_equal(gu[key], gn[key]), key
     assert gu['ints'].sum() > 0
 
 
 @pytest.mark.parametrize('name', ['mcml_user_plugins', 'mcml_user_surface_reflector',
-                                  'mcml_user_trace'])
+                                  'mcml_user_trace', 'mcvox_user_trace', 'mccyl_user_trace'])
 def test_oracle_pins_user_fragments_through_equivalent_builtins(name):
     eq = cases.USER_EQUIVALENT[name]
     sim, geom, _ = build_sim(eq)
@@ -81,6 +82,10 @@ def test_user_fragments_compile_for_sm100a(name, deterministic):
     if name == 'mcml_user_fluence':
         assert 'mcsim_fluence_deposit_at' in src and 'typedef xo::FluUser XoFluence;' in src
         assert 'typedef xo::PfHg XoPf;' in src
+        return
+    if name.endswith('_user_trace') and not name.startswith('mcml'):
+        assert 'mcsim_trace_event' in src and '#define XO_USER_TRACE 1' in src
+        assert 'typedef xo::PfUser XoPf;' not in src
         return
     if name.startswith('mccyl'):
         assert '#include "xo_clcompat_mccyl.cuh"' in src and 'mc_layer_r_outer' in src
